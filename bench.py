@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- aligned Gbp/s of the vacmap_b200 hot path on N B200s (one process per GPU).
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle port of the
+same path on the box's host cores (the reference itself is Python+numba over an
+un-vendored C extension and cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# workload: BASELINE.json configs[1] -- 10k synthetic ONT reads (15 kb, 10 % error), mode H
+# ---------------------------------------------------------------------------
+class ChainGlobalWorkload:
+    """Stage currently wired into the timed region: anchor sort + global non-linear chaining.
+
+    The anchor sets are what minimizer seeding yields for 15 kb / 10 %-error reads
+    (k=15, w=10: ~0.5-0.7k true anchors + repeat/noise hits), generated with
+    tests/synth.py (seeded).
+    """
+    name = "10k synthetic ONT reads (15 kb, 10% err) vs 5 Mb reference, -mode H [stage: global chaining]"
+    read_len = 15000
+
+    def __init__(self, n_reads=10000, seed=1, rank=0):
+        import synth
+        rng = np.random.default_rng(seed * 1000 + rank)
+        distinct = min(n_reads, 500)
+        base = [synth.anchors_global(rng, L=self.read_len, n_true=int(rng.integers(450, 650)),
+                                     n_noise=int(rng.integers(100, 1500))) for _ in range(distinct)]
+        self.anchor_list = []
+        for i in range(n_reads):
+            a = base[i % distinct].copy()
+            a[:, 1] = (a[:, 1] + 7919 * (i // distinct)) % 5_000_000
+            self.anchor_list.append(a)
+        self.n_reads = n_reads
+        self.read_lens = np.full(n_reads, self.read_len, dtype=np.int32)
+        self.off = np.zeros(n_reads + 1, dtype=np.int64)
+        for i, a in enumerate(self.anchor_list):
+            self.off[i + 1] = self.off[i] + len(a)
+        self.rows = np.ascontiguousarray(np.concatenate(self.anchor_list))
+        self.total_anchors = int(self.off[-1])
+        self.bases = int(self.read_lens.sum())
+
+    # algorithmic bytes of the chaining kernel: 16 B anchor in + 8 B S + 4 B P out per anchor
+    def chain_bytes(self):
+        return 28 * self.total_anchors
+
+    def h2d_bytes(self):
+        return self.rows.nbytes + self.off.nbytes
+
+    def d2h_bytes(self):
+        return self.total_anchors * (32 + 8 + 4 + 4) + self.n_reads * 8
+
+
+def cpu_chain_worker(args):
+    """Oracle port of hit2work_1's sort + DP for a slice of reads (one process)."""
+    import oracle
+    anchor_list, L = args
+    t0 = time.perf_counter()
+    for a in anchor_list:
+        srt = a[oracle.argsort_i64(a[:, 0])]
+        if len(a) / L > 5:
+            oracle.chain_fast(srt, 15, 0, 40.0, 50, 1000)
+        else:
+            g = oracle.chain_global_d_all(srt, 15, 40.0, 50, 1000)[0]
+            if g == -1:
+                oracle.chain_fast(srt, 15, 0, 40.0, 50, 1000)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(wl, sample_reads, cores):
+    import multiprocessing as mp
+    import oracle
+    oracle.lib()
+    sample = wl.anchor_list[:sample_reads]
+    chunks = [sample[i::cores] for i in range(cores)]
+    chunks = [c for c in chunks if c]
+    t0 = time.perf_counter()
+    if cores == 1:
+        cpu_chain_worker((chunks[0], wl.read_len))
+    else:
+        with mp.get_context("fork").Pool(len(chunks)) as pool:
+            pool.map(cpu_chain_worker, [(c, wl.read_len) for c in chunks])
+    dt = time.perf_counter() - t0
+    bases = len(sample) * wl.read_len
+    return bases / dt / 1e9, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl = ChainGlobalWorkload(n_reads=args.reads, seed=1)
+    sample = min(wl.n_reads, args.cpu_sample)
+    for _ in range(args.warmup):
+        cpu_baseline(wl, min(sample, 200), cores)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline(wl, sample, cores)
+        vals.append(v)
+        t_all += dt
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "aligned_gbp_per_s", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "reads_per_step": sample, "read_len": wl.read_len},
+            "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
+                             "sample": "%d reads of the workload per step, oracle C port, %d processes" % (sample, cores)},
+            "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=10000, help="reads per GPU per step (configs[1]: 10k)")
+    ap.add_argument("--cpu-sample", type=int, default=2000, help="reads in the bounded CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import vacmap_b200 as vb
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # reads shard across ranks with no data-path collective (weak scaling: fixed work per GPU)
+    wl = ChainGlobalWorkload(n_reads=args.reads, seed=1, rank=rank)
+    ctx = vb._lib.Context(local_rank)
+    ch = vb.GlobalChainer(vb.ChainParams(), ctx=ctx)
+
+    # ---- device-resident: inputs in HBM before the timed region ----
+    ch.upload_ragged(wl.rows, wl.off, wl.read_lens)
+    for _ in range(args.warmup):
+        ch.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.kernel_launches
+    dev_ms = 0.0
+    stage = {"pack": 0.0, "sort": 0.0, "dp_exact": 0.0, "dp_fast": 0.0}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dev_ms += ch.run()                       # CUDA events on the ctx stream around the kernels
+        for k, v in ch.stage_times().items():
+            stage[k] += v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.kernel_launches - l0
+
+    # ---- end to end: host buffers in, host results out, every step ----
+    for _ in range(2):
+        ch.upload_ragged(wl.rows, wl.off, wl.read_lens); ch.run(); ch.download()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ch.upload_ragged(wl.rows, wl.off, wl.read_lens)
+        ch.run()
+        res = ch.download()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+
+    t_dev = torch.tensor([dev_ms / 1000.0, e2e_wall, wall], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    t_max, e2e_max, wall_max = [float(x) for x in t_dev.cpu()]
+
+    if rank == 0:
+        total_bases = wl.bases * world * args.steps
+        value = total_bases / t_max / 1e9
+        e2e = total_bases / e2e_max / 1e9
+        peak, peak_src = peaks()
+        dp_s = stage["dp_exact"] / 1000.0 / args.steps
+        achieved = wl.chain_bytes() / dp_s / 1e9 if dp_s > 0 else 0.0
+        line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000 * t_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl.name, "reads_per_gpu_per_step": wl.n_reads, "read_len": wl.read_len,
+                           "anchors_per_step": wl.total_anchors, "l2": "inputs (%.0f MB/step) larger than L2" %
+                           (wl.rows.nbytes / 1e6), "sharding": "reads split across ranks, no collective"},
+                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": wl.h2d_bytes(),
+                        "d2h_bytes_per_step": wl.d2h_bytes()},
+                "gpu_launches": int(launches),
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+                "roofline": {"bound": "hbm", "kernel": "vm_chain_exact_kernel", "achieved": achieved, "peak": peak,
+                             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "note": "algorithmic bytes = 28 B/anchor (16 in + 8 S + 4 P); the DP is latency/issue-bound, "
+                                     "not HBM-bound (SURVEY 8d)"},
+                "clocks": clocks}
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, dt = cpu_baseline(wl, min(wl.n_reads, args.cpu_sample), cores)
+            line["cpu_baseline"] = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
+                                    "sample": "%d reads of the workload, oracle C port, %d processes, %.1f s" %
+                                              (min(wl.n_reads, args.cpu_sample), cores, dt)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

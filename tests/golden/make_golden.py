@@ -1,0 +1,97 @@
+"""Generate golden vectors by running the REFERENCE's own numba functions.
+
+Run in the build container (where /root/reference exists):
+    python tests/golden/make_golden.py [chain]
+Outputs small .npz fixtures under tests/golden/.  The GPU box has no reference
+tree; tests there compare against these files and against the C oracle.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import refimport  # noqa: E402
+import synth  # noqa: E402
+
+P = "get_optimal_chain_sortbyreadpos_forSV_inv_test_merged_fine_list"
+
+
+def gen_chain():
+    import numba
+    m = refimport.load_mode("clrnano")
+
+    @numba.njit
+    def nb_argsort(a):
+        return np.argsort(a)
+
+    rng = np.random.default_rng(20261017)
+    out = {}
+    # --- argsort permutation cases (numba quicksort) ---
+    ncase = 0
+    for n in (1, 2, 3, 14, 15, 16, 17, 40, 100, 333, 1000, 2500):
+        for div in (1, 3, 50):
+            a = rng.integers(0, max(2, n // div), size=n).astype(np.int64)
+            out["sort_%d_in" % ncase] = a
+            out["sort_%d_out" % ncase] = nb_argsort(a).astype(np.int32)
+            ncase += 1
+    out["sort_count"] = np.array(ncase)
+    # --- global DP cases ---
+    dall = getattr(m, P + "_d_all")
+    dfast = getattr(m, P + "_d_fast_all")
+    cases = []
+    for t in range(14):
+        if t % 3 == 0:
+            a = synth.anchors_tieheavy(rng, n=int(rng.integers(3, 500)))
+        else:
+            a = synth.anchors_global(rng, n_true=int(rng.integers(10, 500)), n_noise=int(rng.integers(0, 900)))
+        cases.append(a)
+    # noise only, large: triggers the opcount bail-out (:24914) -> g = -1
+    cases.append(synth.anchors_global(rng, n_true=0, n_noise=3200, repeats=False))
+    for ci, a in enumerate(cases):
+        a = a[nb_argsort(a[:, 0])]
+        g, S, Pp, A, f = dall(a, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
+        out["g_%d_a" % ci] = a.astype(np.int32) if a.max() < 2**31 else a
+        out["g_%d_exact" % ci] = np.array(g)
+        if g >= 0:
+            out["g_%d_S" % ci] = S
+            out["g_%d_P" % ci] = Pp
+            out["g_%d_A" % ci] = A
+        g, S, Pp, A = dfast(a, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
+        out["g_%d_fg" % ci] = np.array(g)
+        out["g_%d_fS" % ci] = S
+        out["g_%d_fP" % ci] = Pp
+        out["g_%d_fA" % ci] = A
+    out["g_count"] = np.array(len(cases))
+    # --- local DP cases ---
+    fl = getattr(m, P)
+    flm = getattr(m, P + "_mismatch")
+    flf = getattr(m, P + "_fast")
+    flmf = getattr(m, P + "_mismatch_fast")
+    lc = []
+    for t in range(10):
+        if t % 4 == 0:
+            a = synth.anchors_tieheavy(rng, n=int(rng.integers(3, 400)), k=9)
+        else:
+            a = synth.anchors_local(rng, n_true=int(rng.integers(5, 900)), n_noise=int(rng.integers(0, 300)), multi=(t % 2 == 0))
+        lc.append(a)
+    for ci, a in enumerate(lc):
+        a = a[nb_argsort(a[:, 0] + a[:, 3])]
+        out["l_%d_a" % ci] = a.astype(np.int32)
+        for tag, f, sk, mg in (("fl", fl, 40., 99), ("flm", flm, 40., 99), ("fl59", fl, 59., 50),
+                               ("flf", flf, 40., 99), ("flmf", flmf, 40., 99)):
+            sc, path = f(a, kmersize=9, skipcost=sk, maxdiff=30, maxgap=mg)
+            out["l_%d_%s_score" % (ci, tag)] = np.array(sc)
+            out["l_%d_%s_path" % (ci, tag)] = np.array(path, dtype=np.int64).astype(np.int32)
+    out["l_count"] = np.array(len(lc))
+    np.savez_compressed(os.path.join(HERE, "chain.npz"), **out)
+    print("chain.npz:", os.path.getsize(os.path.join(HERE, "chain.npz")), "bytes")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["chain"]
+    if "chain" in what:
+        gen_chain()

@@ -1,0 +1,115 @@
+"""GPU parity: CUDA global chaining (through the C ABI) vs the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain.npz"))
+
+
+def _check_against_oracle(anchor_list, read_lens, results, params):
+    nfast = 0
+    for a, L, r in zip(anchor_list, read_lens, results):
+        a = np.asarray(a, dtype=np.int64)
+        perm = oracle.argsort_i64(a[:, 0])
+        srt = a[perm]
+        assert (r.sorted == srt).all()
+        fast = len(a) / L > 5
+        if not fast:
+            g, S, P, A, op = oracle.chain_global_d_all(srt, params.kmersize, params.skipcost, params.maxdiff, params.maxgap)
+            if g == -1:
+                fast = True
+        if fast:
+            g, S, P, A = oracle.chain_fast(srt, params.kmersize, 0, params.skipcost, params.maxdiff, params.maxgap)
+            nfast += 1
+        assert r.used_fast == fast
+        assert r.g_max_index == g
+        assert (r.S == S).all(), np.flatnonzero(r.S != S)[:5]
+        assert (r.P == P).all()
+        assert (r.S_arg == A).all()
+    return nfast
+
+
+def test_golden_global(gpu_ctx):
+    import vacmap_b200 as vb
+    prm = vb.ChainParams()
+    al, Ls = [], []
+    for ci in range(int(G["g_count"])):
+        a = G["g_%d_a" % ci].astype(np.int64)
+        al.append(a)
+        Ls.append(15000 if len(a) <= 5 * 15000 else 100)
+    res = vb.chain_global_batch(al, Ls, prm, ctx=gpu_ctx)
+    for ci, r in enumerate(res):
+        ge = int(G["g_%d_exact" % ci])
+        if ge >= 0:
+            assert not r.used_fast and r.g_max_index == ge
+            assert (r.S == G["g_%d_S" % ci]).all() and (r.P == G["g_%d_P" % ci]).all() and (r.S_arg == G["g_%d_A" % ci]).all()
+        else:
+            assert r.used_fast and r.g_max_index == int(G["g_%d_fg" % ci])
+            assert (r.S == G["g_%d_fS" % ci]).all() and (r.P == G["g_%d_fP" % ci]).all() and (r.S_arg == G["g_%d_fA" % ci]).all()
+    # the same anchors forced down the fast path (n / read_len > 5)
+    res = vb.chain_global_batch(al, [max(1, len(a) // 6) for a in al], prm, ctx=gpu_ctx)
+    for ci, r in enumerate(res):
+        assert r.used_fast and r.g_max_index == int(G["g_%d_fg" % ci])
+        assert (r.S == G["g_%d_fS" % ci]).all() and (r.P == G["g_%d_fP" % ci]).all() and (r.S_arg == G["g_%d_fA" % ci]).all()
+
+
+def test_random_batch_vs_oracle(gpu_ctx):
+    import vacmap_b200 as vb
+    rng = np.random.default_rng(7)
+    prm = vb.ChainParams()
+    al, Ls = [], []
+    for t in range(160):
+        if t % 5 == 0:
+            a = synth.anchors_tieheavy(rng, n=int(rng.integers(3, 700)))
+            L = 2000
+        else:
+            a = synth.anchors_global(rng, n_true=int(rng.integers(5, 700)), n_noise=int(rng.integers(0, 2500)))
+            L = 15000
+        al.append(a)
+        Ls.append(L)
+    # edge cases: tiny reads, equal positions only, large (beyond the smem classes)
+    al.append(np.array([[5, 100, 1, 15]], dtype=np.int64)); Ls.append(100)
+    al.append(np.array([[5, 100, 1, 15], [5, 300, -1, 15], [5, 100, 1, 15]], dtype=np.int64)); Ls.append(100)
+    al.append(synth.anchors_global(rng, n_true=9000, n_noise=9000, L=200000)); Ls.append(200000)
+    al.append(synth.anchors_global(rng, n_true=0, n_noise=2600, repeats=False)); Ls.append(15000)
+    res = vb.chain_global_batch(al, Ls, prm, ctx=gpu_ctx)
+    nfast = _check_against_oracle(al, Ls, res, prm)
+    assert nfast >= 1
+
+
+def test_empty_and_ragged(gpu_ctx):
+    import vacmap_b200 as vb
+    rng = np.random.default_rng(3)
+    al = [np.zeros((0, 4), np.int64), synth.anchors_global(rng, n_true=50, n_noise=10), np.zeros((0, 4), np.int64)]
+    res = vb.chain_global_batch(al, [100, 15000, 100], ctx=gpu_ctx)
+    assert len(res[0].S) == 0 and len(res[2].S) == 0
+    _check_against_oracle(al[1:2], [15000], res[1:2], vb.ChainParams())
+    assert vb.chain_global_batch([], [], ctx=gpu_ctx) == []
+
+
+def test_full_size_properties(gpu_ctx):
+    """BASELINE config[1] scale (10k reads): size-independent properties of the result."""
+    import vacmap_b200 as vb
+    rng = np.random.default_rng(11)
+    base = [synth.anchors_global(rng, n_true=int(rng.integers(300, 700)), n_noise=int(rng.integers(100, 1500)))
+            for _ in range(200)]
+    al = [base[i % len(base)] for i in range(10000)]
+    res = vb.chain_global_batch(al, [15000] * len(al), ctx=gpu_ctx)
+    for i, r in enumerate(res):
+        n = len(r.S)
+        # sortedness of the replayed argsort and of S_arg; P points backwards; g_max is the first maximum
+        assert (np.diff(r.sorted[:, 0]) >= 0).all()
+        assert sorted(r.S_arg.tolist()) == list(range(n))
+        assert (np.diff(r.S[r.S_arg]) >= 0).all()
+        ok = (r.P == vb._lib.NOPRE) | ((r.P >= 0) & (r.P < np.arange(n)))
+        assert ok.all()
+        assert r.g_max_index == int(np.argmax(r.S))
+        # identical inputs give identical outputs (idempotence across the batch)
+        j = i % len(base)
+        if i >= len(base):
+            assert (r.S == res[j].S).all() and (r.P == res[j].P).all() and (r.S_arg == res[j].S_arg).all()

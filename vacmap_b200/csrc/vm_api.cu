@@ -1,0 +1,317 @@
+// C ABI of libvacmap_b200.so -- see include/vacmap_b200.h.
+#include "vm_ctx.cuh"
+#include "vm_chain.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+int vm_launch_gather(const VmAnchor *in, const int64_t *off, int n_reads, const int32_t *perm,
+                     VmAnchor *sorted, int64_t *sorted_rows, long long total, cudaStream_t stream);
+
+extern "C" {
+
+int vm_abi_version(void) { return 1; }
+
+int vm_ctx_create(int device, vm_ctx **out)
+{
+    if (!out) return VM_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return VM_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return VM_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return VM_ERR_CUDA;
+    vm_ctx *c = new vm_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return VM_ERR_CUDA;
+    }
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return VM_OK;
+}
+
+void vm_ctx_destroy(vm_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    VmChainState &s = c->chain;
+    VmDevBuf *bufs[] = {&s.rows, &s.off_dev, &s.anch, &s.perm, &s.sorted, &s.sorted_rows, &s.S, &s.P,
+                        &s.S_arg, &s.gmax, &s.opcount, &s.ids, &s.gcl, &s.rgl, &s.fast_scratch, &s.fast_off,
+                        &c->extra, &c->readgapcost, &c->log2cache};
+    for (VmDevBuf *b : bufs) b->release();
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *vm_last_error(vm_ctx *c) { return c ? c->err.c_str() : "null ctx"; }
+
+int64_t vm_kernel_launches(vm_ctx *c) { return c ? c->launches : 0; }
+
+int vm_set_tables(vm_ctx *c, const float *extra, int64_t n_extra, const float *readgapcost,
+                  int64_t n_readgapcost, const double *log2cache, int64_t n_log2cache)
+{
+    if (!c || !extra || !readgapcost || !log2cache || n_extra < 2 || n_readgapcost < 1 || n_log2cache < 2)
+        return VM_ERR_ARG;
+    cudaSetDevice(c->device);
+    VM_CUDA_OK(c, c->extra.ensure(n_extra * sizeof(float)));
+    VM_CUDA_OK(c, c->readgapcost.ensure(n_readgapcost * sizeof(float)));
+    VM_CUDA_OK(c, c->log2cache.ensure(n_log2cache * sizeof(double)));
+    VM_CUDA_OK(c, cudaMemcpyAsync(c->extra.p, extra, n_extra * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VM_CUDA_OK(c, cudaMemcpyAsync(c->readgapcost.p, readgapcost, n_readgapcost * sizeof(float),
+                                  cudaMemcpyHostToDevice, c->stream));
+    VM_CUDA_OK(c, cudaMemcpyAsync(c->log2cache.p, log2cache, n_log2cache * sizeof(double),
+                                  cudaMemcpyHostToDevice, c->stream));
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->n_extra = n_extra;
+    c->n_readgapcost = n_readgapcost;
+    c->n_log2cache = n_log2cache;
+    return VM_OK;
+}
+
+} // extern "C"
+
+// gapcost_list as built inside the reference njit functions with libm log2
+// (global :24843-24846; local :27317-27322)
+static void vm_host_gapcost(int kmersize, int maxdiff, bool local, std::vector<double> &out)
+{
+    out.assign(maxdiff + 1, 0.0);
+    for (int g = 1; g <= maxdiff; ++g) {
+        double lg = std::log2((double)g);
+        if (!local || g <= 10) out[g] = 0.01 * kmersize * g + 0.5 * lg;
+        else out[g] = 0.01 * kmersize * g + 2 * lg;
+    }
+}
+
+// large_readgapcost_list (:28270-28275), float32
+static void vm_host_large_readgap(int maxgap, int large_readgap, std::vector<float> &out)
+{
+    out.assign(maxgap + 1, 0.0f);
+    for (int r = 1; r <= maxgap; ++r) {
+        if (large_readgap <= r) out[r] = (float)(0.5 * r);
+        else out[r] = (float)(0.1 * std::log2((double)(r + 1)));
+    }
+}
+
+static const int kCaps[] = {256, 512, 1024, 2048, 4096, 8192, VM_CHAIN_SMEM_CAP};
+static const int kNumCaps = 7;
+
+// Fill VmChainArgs from ctx + state (device pointers).
+static int vm_chain_args(vm_ctx *c, VmChainState &s, VmChainArgs &A)
+{
+    if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
+    const vm_chain_params &p = s.prm;
+    if (p.maxdiff + 1 > VM_GCL_MAX || p.maxgap + 1 > VM_RGL_MAX + 100000) { c->err = "maxdiff too large"; return VM_ERR_ARG; }
+    std::vector<double> gcl;
+    vm_host_gapcost(p.kmersize, p.maxdiff, p.variant != 0, gcl);
+    VM_CUDA_OK(c, s.gcl.ensure(gcl.size() * sizeof(double)));
+    VM_CUDA_OK(c, cudaMemcpyAsync(s.gcl.p, gcl.data(), gcl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    A.rgcost = nullptr;
+    A.n_rg = 0;
+    if (p.variant == 1) {
+        A.rgcost = c->readgapcost.as<float>();
+        A.n_rg = (int)c->n_readgapcost;
+    } else if (p.variant == 2) {
+        if (p.maxgap + 1 > VM_RGL_MAX) { c->err = "maxgap too large for the local DP"; return VM_ERR_ARG; }
+        std::vector<float> rg;
+        vm_host_large_readgap(p.maxgap, p.large_readgap, rg);
+        VM_CUDA_OK(c, s.rgl.ensure(rg.size() * sizeof(float)));
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.rgl.p, rg.data(), rg.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        A.rgcost = s.rgl.as<float>();
+        A.n_rg = (int)rg.size();
+    }
+    // the staging vectors above are pageable: make sure the copies are done before they go away
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    A.anchors = s.sorted.as<VmAnchor>();
+    A.off = s.off_dev.as<int64_t>();
+    A.S = s.S.as<double>();
+    A.P = s.P.as<int32_t>();
+    A.S_arg = s.S_arg.as<int32_t>();
+    A.gmax = s.gmax.as<int64_t>();
+    A.opcount = s.opcount.as<int64_t>();
+    A.extra = c->extra.as<float>();
+    A.extra_size = c->n_extra - 1;
+    A.log2cache = c->log2cache.as<double>();
+    A.log2cache_size = c->n_log2cache - 1;
+    A.gapcost_list = s.gcl.as<double>();
+    A.skipcost = p.skipcost;
+    A.maxdiff = p.maxdiff;
+    A.maxgap = p.maxgap;
+    A.max_factor = p.max_factor;
+    return VM_OK;
+}
+
+extern "C" {
+
+int vm_chain_global_upload(vm_ctx *c, const vm_chain_params *prm, int64_t n_reads, const int64_t *anchors,
+                           const int64_t *off, const int32_t *read_len)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!prm || n_reads < 0 || !off || (n_reads > 0 && !read_len)) { c->err = "bad argument"; return VM_ERR_ARG; }
+    if (n_reads >= (1LL << 31)) { c->err = "too many reads in one batch"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    VmChainState &s = c->chain;
+    s.loaded = false;
+    s.prm = *prm;
+    s.n_reads = n_reads;
+    s.total = off[n_reads];
+    if (s.total > 0 && !anchors) { c->err = "anchors is null"; return VM_ERR_ARG; }
+    for (int64_t r = 0; r < n_reads; ++r) {
+        if (off[r + 1] < off[r] || off[r + 1] - off[r] >= (1LL << 31) - 16) { c->err = "bad offsets"; return VM_ERR_ARG; }
+    }
+    s.off.assign(off, off + n_reads + 1);
+    s.read_len.assign(read_len, read_len + n_reads);
+    const size_t T = (size_t)std::max<int64_t>(s.total, 1);
+    VM_CUDA_OK(c, s.rows.ensure(T * 32));
+    VM_CUDA_OK(c, s.off_dev.ensure((n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.anch.ensure(T * 16));
+    VM_CUDA_OK(c, s.perm.ensure(T * 4));
+    VM_CUDA_OK(c, s.sorted.ensure(T * 16));
+    VM_CUDA_OK(c, s.sorted_rows.ensure(T * 32));
+    VM_CUDA_OK(c, s.S.ensure(T * 8));
+    VM_CUDA_OK(c, s.P.ensure(T * 4));
+    VM_CUDA_OK(c, s.S_arg.ensure(T * 4));
+    VM_CUDA_OK(c, s.gmax.ensure((n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.opcount.ensure((n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.ids.ensure((n_reads + 1) * 4 * 2));
+    if (s.total > 0)
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.rows.p, anchors, (size_t)s.total * 32, cudaMemcpyHostToDevice, c->stream));
+    VM_CUDA_OK(c, cudaMemcpyAsync(s.off_dev.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    s.loaded = true;
+    return VM_OK;
+}
+
+int vm_chain_global_run(vm_ctx *c, float *kernel_ms)
+{
+    if (!c) return VM_ERR_ARG;
+    VmChainState &s = c->chain;
+    if (!s.loaded) { c->err = "vm_chain_global_upload first"; return VM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    VmChainArgs A;
+    int rc = vm_chain_args(c, s, A);
+    if (rc != VM_OK) return rc;
+    const int n_reads = (int)s.n_reads;
+    const bool by_end = s.prm.variant != 0;
+    s.used_fast.assign(n_reads, 0);
+
+    // class binning on the host: which reads go to which smem capacity / fast path
+    std::vector<std::vector<int>> cls(kNumCaps + 1);
+    std::vector<int> fast_ids;
+    bool may_bail = false;
+    for (int r = 0; r < n_reads; ++r) {
+        const int64_t n = s.off[r + 1] - s.off[r];
+        if (n <= 0) continue;
+        // hit2work_1 :23570 -- n / read_len > 5 goes straight to the fast DP (global only)
+        if (!by_end && (double)n / (double)s.read_len[r] > 5.0) { fast_ids.push_back(r); continue; }
+        int k = 0;
+        while (k < kNumCaps && n > kCaps[k]) ++k;
+        cls[k].push_back(r);
+        if (n > 2000) may_bail = true;   // opcount/i > 1000 needs i > 2000 (global); local needs opcount > 1e5
+    }
+
+    cudaEvent_t *ev = c->ev;
+    VM_CUDA_OK(c, cudaEventRecord(ev[0], c->stream));
+    c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
+    VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
+    c->launches += vm_launch_sort_replay(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), n_reads, by_end ? 1 : 0,
+                                         s.perm.as<int32_t>(), nullptr, nullptr, c->stream);
+    c->launches += vm_launch_gather(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), n_reads, s.perm.as<int32_t>(),
+                                    s.sorted.as<VmAnchor>(), s.sorted_rows.as<int64_t>(), s.total, c->stream);
+    VM_CUDA_OK(c, cudaEventRecord(ev[2], c->stream));
+
+    // exact DP, one launch per capacity class
+    std::vector<int> ids_host;
+    std::vector<int> cls_start(kNumCaps + 2, 0);
+    for (int k = 0; k <= kNumCaps; ++k) {
+        cls_start[k] = (int)ids_host.size();
+        ids_host.insert(ids_host.end(), cls[k].begin(), cls[k].end());
+    }
+    cls_start[kNumCaps + 1] = (int)ids_host.size();
+    if (!ids_host.empty())
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.ids.p, ids_host.data(), ids_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k <= kNumCaps; ++k) {
+        const int cnt = cls_start[k + 1] - cls_start[k];
+        if (cnt == 0) continue;
+        const bool smem = k < kNumCaps;
+        c->launches += vm_launch_chain_exact(s.prm.variant, A, s.ids.as<int>() + cls_start[k], cnt,
+                                             smem ? kCaps[k] : 0, smem, c->stream);
+    }
+    VM_CUDA_OK(c, cudaEventRecord(ev[3], c->stream));
+
+    // reads whose exact DP bailed out (opcount rule) join the fast list
+    if (may_bail) {
+        std::vector<int64_t> g(n_reads);
+        VM_CUDA_OK(c, cudaMemcpyAsync(g.data(), s.gmax.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
+        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        for (int r : ids_host)
+            if (g[r] < 0) fast_ids.push_back(r);
+    }
+    if (!fast_ids.empty()) {
+        std::vector<int64_t> soff(fast_ids.size() + 1, 0);
+        for (size_t t = 0; t < fast_ids.size(); ++t) {
+            const int r = fast_ids[t];
+            const int64_t n = s.off[r + 1] - s.off[r];
+            soff[t + 1] = soff[t] + 2 * n + (int64_t)s.read_len[r] + 64;
+            s.used_fast[r] = 1;
+        }
+        VM_CUDA_OK(c, s.fast_scratch.ensure((size_t)soff.back() * 8));
+        VM_CUDA_OK(c, s.fast_off.ensure(soff.size() * 8 + fast_ids.size() * 4));
+        int *fids_dev = (int *)((char *)s.fast_off.p + soff.size() * 8);
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.fast_off.p, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemcpyAsync(fids_dev, fast_ids.data(), fast_ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        c->launches += vm_launch_chain_fast(s.prm.variant, A, s.prm.fast_t, fids_dev, (int)fast_ids.size(),
+                                            s.fast_scratch.as<long long>(), s.fast_off.as<int64_t>(), c->stream);
+    }
+    VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, cudaGetLastError());
+    for (int t = 0; t < 4; ++t) cudaEventElapsedTime(&s.ms[t], ev[t], ev[t + 1]);
+    if (kernel_ms) cudaEventElapsedTime(kernel_ms, ev[0], ev[4]);
+    return VM_OK;
+}
+
+int vm_chain_global_times(vm_ctx *c, float *ms4)
+{
+    if (!c || !ms4) return VM_ERR_ARG;
+    memcpy(ms4, c->chain.ms, sizeof(float) * 4);
+    return VM_OK;
+}
+
+int vm_chain_global_download(vm_ctx *c, int64_t *sorted, double *S, int32_t *P, int32_t *S_arg,
+                             int64_t *g_max_index, int32_t *used_fast)
+{
+    if (!c) return VM_ERR_ARG;
+    VmChainState &s = c->chain;
+    if (!s.loaded) { c->err = "nothing to download"; return VM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    const size_t T = (size_t)s.total;
+    if (T > 0) {
+        if (sorted) VM_CUDA_OK(c, cudaMemcpyAsync(sorted, s.sorted_rows.p, T * 32, cudaMemcpyDeviceToHost, c->stream));
+        if (S) VM_CUDA_OK(c, cudaMemcpyAsync(S, s.S.p, T * 8, cudaMemcpyDeviceToHost, c->stream));
+        if (P) VM_CUDA_OK(c, cudaMemcpyAsync(P, s.P.p, T * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (S_arg) VM_CUDA_OK(c, cudaMemcpyAsync(S_arg, s.S_arg.p, T * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (g_max_index && s.n_reads > 0)
+        VM_CUDA_OK(c, cudaMemcpyAsync(g_max_index, s.gmax.p, (size_t)s.n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    if (used_fast && s.n_reads > 0) memcpy(used_fast, s.used_fast.data(), (size_t)s.n_reads * 4);
+    return VM_OK;
+}
+
+int vm_chain_global_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_reads, const int64_t *anchors,
+                          const int64_t *off, const int32_t *read_len, int64_t *sorted, double *S, int32_t *P,
+                          int32_t *S_arg, int64_t *g_max_index, int32_t *used_fast, float *kernel_ms)
+{
+    int rc = vm_chain_global_upload(c, prm, n_reads, anchors, off, read_len);
+    if (rc != VM_OK) return rc;
+    rc = vm_chain_global_run(c, kernel_ms);
+    if (rc != VM_OK) return rc;
+    return vm_chain_global_download(c, sorted, S, P, S_arg, g_max_index, used_fast);
+}
+
+} // extern "C"

@@ -1,0 +1,634 @@
+// Non-linear anchor chaining kernels (see vm_chain.cuh for the design note).
+#include "vm_chain.cuh"
+#include <math_constants.h>
+
+// ---------------------------------------------------------------------------
+// pack: int64[total][4] rows -> 16-byte VmAnchor (coalesced: one thread per row)
+// ---------------------------------------------------------------------------
+__global__ void vm_pack_kernel(const longlong4 *__restrict__ rows, VmAnchor *__restrict__ out, long long total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    longlong4 r = rows[i];
+    VmAnchor a;
+    a.x = (int32_t)r.x;
+    a.y = (uint32_t)r.y;
+    a.s = (int32_t)r.z;
+    a.l = (int32_t)r.w;
+    out[i] = a;
+}
+
+int vm_launch_pack(const int64_t *rows_dev, VmAnchor *out, long long total, cudaStream_t stream)
+{
+    if (total <= 0) return 0;
+    int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    vm_pack_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const longlong4 *)rows_dev, out, total);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
+// numba argsort replay (numba/misc/quicksort.py): the permutation among equal
+// keys depends on the exact pivot/swap sequence, and the DP's tie-breaking
+// depends on that permutation, so the algorithm is replayed literally.
+// One thread per read; keys are read positions (global DP, reference :23572)
+// or read end positions (local DP, :28585).
+// ---------------------------------------------------------------------------
+template <int KEY_IS_END>
+__device__ __forceinline__ int vm_key(const VmAnchor *a, int idx)
+{
+    if (KEY_IS_END) return a[idx].x + a[idx].l;
+    return a[idx].x;
+}
+
+template <int KEY_IS_END>
+__global__ void vm_sort_replay_kernel(const VmAnchor *__restrict__ in, const int64_t *__restrict__ off,
+                                      int n_reads, int32_t *__restrict__ perm)
+{
+    int rid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rid >= n_reads) return;
+    const long long base = off[rid];
+    const int n = (int)(off[rid + 1] - base);
+    const VmAnchor *A = in + base;
+    int32_t *R = perm + base;
+    for (int t = 0; t < n; ++t) R[t] = t;
+    if (n < 2) return;
+    int stack_lo[100], stack_hi[100];
+    int sp = 1;
+    stack_lo[0] = 0;
+    stack_hi[0] = n - 1;
+    while (sp > 0) {
+        --sp;
+        int low = stack_lo[sp], high = stack_hi[sp];
+        while (high - low >= 15) {
+            int mid = (low + high) >> 1, tmp;
+            if (vm_key<KEY_IS_END>(A, R[mid]) < vm_key<KEY_IS_END>(A, R[low])) { tmp = R[low]; R[low] = R[mid]; R[mid] = tmp; }
+            if (vm_key<KEY_IS_END>(A, R[high]) < vm_key<KEY_IS_END>(A, R[mid])) { tmp = R[high]; R[high] = R[mid]; R[mid] = tmp; }
+            if (vm_key<KEY_IS_END>(A, R[mid]) < vm_key<KEY_IS_END>(A, R[low])) { tmp = R[low]; R[low] = R[mid]; R[mid] = tmp; }
+            const int pivot = vm_key<KEY_IS_END>(A, R[mid]);
+            tmp = R[high]; R[high] = R[mid]; R[mid] = tmp;
+            int i = low, j = high - 1;
+            for (;;) {
+                while (i < high && vm_key<KEY_IS_END>(A, R[i]) < pivot) ++i;
+                while (j >= low && pivot < vm_key<KEY_IS_END>(A, R[j])) --j;
+                if (i >= j) break;
+                tmp = R[i]; R[i] = R[j]; R[j] = tmp;
+                ++i; --j;
+            }
+            tmp = R[i]; R[i] = R[high]; R[high] = tmp;
+            if (high - i > i - low) {
+                if (high > i) { stack_lo[sp] = i + 1; stack_hi[sp] = high; ++sp; }
+                high = i - 1;
+            } else {
+                if (i > low) { stack_lo[sp] = low; stack_hi[sp] = i - 1; ++sp; }
+                low = i + 1;
+            }
+        }
+        for (int i = low + 1; i <= high; ++i) {
+            const int k = R[i];
+            const int v = vm_key<KEY_IS_END>(A, k);
+            int j = i;
+            while (j > low && v < vm_key<KEY_IS_END>(A, R[j - 1])) { R[j] = R[j - 1]; --j; }
+            R[j] = k;
+        }
+    }
+}
+
+// gather anchors through the permutation (one thread per anchor, binary search for the read)
+__global__ void vm_gather_kernel(const VmAnchor *__restrict__ in, const int64_t *__restrict__ off, int n_reads,
+                                 const int32_t *__restrict__ perm, VmAnchor *__restrict__ sorted,
+                                 longlong4 *__restrict__ sorted_rows, long long total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = n_reads;   // largest r with off[r] <= i
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const long long base = off[lo];
+    VmAnchor a = in[base + perm[i]];
+    sorted[i] = a;
+    if (sorted_rows) {
+        longlong4 r;
+        r.x = a.x; r.y = (long long)a.y; r.z = a.s; r.w = a.l;
+        sorted_rows[i] = r;
+    }
+}
+
+int vm_launch_sort_replay(const VmAnchor *in, const int64_t *off, int n_reads, int key_is_end,
+                          int32_t *perm, VmAnchor *sorted, int64_t *sorted_rows, cudaStream_t stream)
+{
+    if (n_reads <= 0) return 0;
+    int threads = 32;   // divergent serial work per thread: keep warps small-grained across SMs
+    int blocks = (n_reads + threads - 1) / threads;
+    if (key_is_end) vm_sort_replay_kernel<1><<<blocks, threads, 0, stream>>>(in, off, n_reads, perm);
+    else vm_sort_replay_kernel<0><<<blocks, threads, 0, stream>>>(in, off, n_reads, perm);
+    return 1;
+}
+
+int vm_launch_gather(const VmAnchor *in, const int64_t *off, int n_reads, const int32_t *perm,
+                     VmAnchor *sorted, int64_t *sorted_rows, long long total, cudaStream_t stream)
+{
+    if (total <= 0) return 0;
+    int threads = 256;
+    long long blocks = (total + threads - 1) / threads;
+    vm_gather_kernel<<<(unsigned)blocks, threads, 0, stream>>>(in, off, n_reads, perm, sorted,
+                                                              (longlong4 *)sorted_rows, total);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
+// exact chaining DP, one warp per read
+// ---------------------------------------------------------------------------
+struct VmScoreCtx {
+    double skipcost;
+    int maxdiff;
+    int maxgap;
+    const double *gcl;   // smem
+    const float *rgl;    // smem
+    const float *extra;
+    long long extra_size;
+    const double *log2cache;
+    long long log2cache_size;
+};
+
+// Candidate score of chaining anchor i after predecessor j.  The order of the
+// float64 additions follows the reference expressions exactly
+// (:24990, :24996 global; :27462, :27476-27480 local; :28416-28428 multi-chain).
+template <int VARIANT>
+__device__ __forceinline__ double vm_pair_score(const VmScoreCtx &c, const VmAnchor &ai, const VmAnchor &aj,
+                                                double Sj, bool &skip)
+{
+    int bonus, readgap;
+    long long refgap;
+    vm_pair_gaps(ai, aj, bonus, readgap, refgap);
+    skip = false;
+    if (VARIANT != 0 && (ai.x - aj.x - aj.l) < 0 && bonus <= 0) { skip = true; return -CUDART_INF; }
+    long long gapcost = vm_llabs((long long)readgap - refgap);
+    if (ai.s == aj.s && refgap >= 0 && readgap <= c.maxgap && gapcost <= (long long)c.maxdiff) {
+        double t = Sj + (double)bonus;
+        t = t - c.gcl[gapcost];
+        if (VARIANT != 0) t = t - (double)c.rgl[readgap];
+        return t;
+    }
+    if (VARIANT == 0) {
+        if (gapcost > c.extra_size) gapcost = c.extra_size;
+        double t = Sj - c.skipcost;
+        t = t + (double)bonus;
+        t = t - (double)__ldg(c.extra + gapcost);
+        return t;
+    } else if (VARIANT == 1) {
+        if (gapcost > c.extra_size) gapcost = c.extra_size;
+        const double e = (double)__ldg(c.extra + gapcost);
+        double pen;
+        if (ai.s != aj.s) pen = (50.0 < c.skipcost ? 50.0 : c.skipcost) + e;
+        else pen = c.skipcost + e;
+        double t = Sj + (double)bonus;
+        return t - pen;
+    } else {
+        const long long g = gapcost < c.log2cache_size ? gapcost : c.log2cache_size;
+        const double pen = c.skipcost + __ldg(c.log2cache + g);
+        double t = Sj + (double)bonus;
+        return t - pen;
+    }
+}
+
+// number of q in [0, hi) with S[arg[q]] < target (LEQ: <= target); arg ascending in S.
+template <bool LEQ>
+__device__ __forceinline__ int vm_warp_count(const double *S, const int32_t *arg, int lo, int hi,
+                                             double target, int lane)
+{
+    while (lo < hi) {
+        const int span = hi - lo;
+        const int step = (span + 31) >> 5;
+        int p = lo + (lane + 1) * step - 1;
+        if (p > hi - 1) p = hi - 1;
+        const double v = S[arg[p]];
+        const bool pred = LEQ ? (v <= target) : (v < target);
+        const int c = __popc(__ballot_sync(VM_FULL, pred));
+        if (c == 32) {
+            lo = hi;
+        } else {
+            int pc = lo + (c + 1) * step - 1;
+            if (pc > hi - 1) pc = hi - 1;
+            int nlo = lo;
+            if (c > 0) {
+                int pp = lo + c * step - 1;
+                if (pp > hi - 1) pp = hi - 1;
+                nlo = pp + 1;
+            }
+            hi = pc;
+            lo = nlo;
+        }
+    }
+    return lo;
+}
+
+// Insert index k into arg[0..k) keeping it ascending in S; ties placed exactly
+// where the reference's search puts them.
+template <int VARIANT>
+__device__ __forceinline__ void vm_insert_one(const double *S, int32_t *arg, int k, int lane)
+{
+    const double target = S[k];
+    const double top = S[arg[k - 1]];
+    int pos;
+    if (VARIANT == 0 ? (top < target) : (top <= target)) {
+        pos = k;                                  // new best (or tie, local): append
+    } else if (VARIANT != 0) {
+        // smallorequal2target_1d_point(...) + 1 (:27389) == upper bound
+        pos = vm_warp_count<true>(S, arg, 0, k, target, lane);
+    } else {
+        // insertpoint_score (:19369-19387): replay its binary search knowing
+        // a = #{S < target}, b = #{S <= target}
+        const int b = vm_warp_count<true>(S, arg, 0, k, target, lane);
+        if (b == 0) {
+            pos = 0;
+        } else {
+            const int a = vm_warp_count<false>(S, arg, 0, b, target, lane);
+            if (a == b) {
+                pos = a;
+            } else {
+                int i = 0, j = k;
+                pos = -1;
+                while (i < j) {
+                    const int mid = (i + j) >> 1;
+                    if (mid < a) i = mid + 1;
+                    else if (mid >= b) j = mid;
+                    else { pos = mid + 1; break; }
+                }
+                if (pos < 0) pos = j;
+            }
+        }
+    }
+    // shift arg[pos..k) up by one, highest chunk first
+    for (int hi = k; hi > pos; hi -= 32) {
+        const int idx = hi - 1 - lane;
+        int v = 0;
+        if (idx >= pos) v = arg[idx];
+        __syncwarp();
+        if (idx >= pos) arg[idx + 1] = v;
+    }
+    __syncwarp();
+    if (lane == 0) arg[pos] = k;
+    __syncwarp();
+}
+
+template <int VARIANT, bool SMEM>
+__global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const int *__restrict__ read_ids, int cap)
+{
+    extern __shared__ __align__(16) unsigned char vm_smem[];
+    const int lane = threadIdx.x;
+    const int rid = read_ids[blockIdx.x];
+    const long long base = A.off[rid];
+    const int n = (int)(A.off[rid + 1] - base);
+    const VmAnchor *__restrict__ a = A.anchors + base;
+
+    double *gcl = (double *)vm_smem;
+    float *rgl = (float *)(gcl + VM_GCL_MAX);
+    double *S;
+    int32_t *arg;
+    if (SMEM) {
+        S = (double *)(rgl + VM_RGL_MAX);
+        arg = (int32_t *)(S + cap);
+    } else {
+        S = A.S + base;
+        arg = A.S_arg + base;
+    }
+    for (int t = lane; t <= A.maxdiff && t < VM_GCL_MAX; t += 32) gcl[t] = A.gapcost_list[t];
+    if (VARIANT != 0)
+        for (int t = lane; t < A.n_rg && t < VM_RGL_MAX; t += 32) rgl[t] = A.rgcost[t];
+    __syncwarp();
+    if (n <= 0) {
+        if (lane == 0) { A.gmax[rid] = -1; A.opcount[rid] = 0; }
+        return;
+    }
+
+    VmScoreCtx c;
+    c.skipcost = A.skipcost; c.maxdiff = A.maxdiff; c.maxgap = A.maxgap;
+    c.gcl = gcl; c.rgl = rgl; c.extra = A.extra; c.extra_size = A.extra_size;
+    c.log2cache = A.log2cache; c.log2cache_size = A.log2cache_size;
+
+    int32_t *P = A.P + base;
+    const VmAnchor a0 = a[0];
+    int prekey = VARIANT == 0 ? a0.x : a0.x + a0.l;
+    if (VARIANT == 0) {
+        // coverage of the first read position (:24865-24876): run length, capped at 20
+        const bool eq = lane < n && a[lane].x == a0.x;
+        const unsigned m = __ballot_sync(VM_FULL, eq);
+        int run = (m == VM_FULL) ? 32 : (__ffs(~m) - 1);
+        if (run > 20) run = 20;
+        c.skipcost = A.skipcost + (double)run;
+        c.maxdiff = A.maxdiff - run > 10 ? A.maxdiff - run : 10;
+    }
+    int testspace_en = 1;
+    if (lane == 0) { arg[0] = 0; S[0] = (double)a0.l; P[0] = VM_NOPRE; }
+    __syncwarp();
+    double g_max_scores = (double)a0.l;
+    int g_max_index = 0;
+    long long opcount = 0;
+    long long result = 0;
+    bool bailed = false;
+
+    for (int i = 1; i < n; ++i) {
+        const VmAnchor ai = a[i];
+        const int key = VARIANT == 0 ? ai.x : ai.x + ai.l;
+        if (prekey < key) {
+            if (VARIANT == 0) {
+                if (((double)opcount / (double)i) > (double)A.max_factor) { bailed = true; result = -1; break; }
+            } else {
+                if (opcount > 100000 && ((double)opcount / (double)prekey) > 1000.0) { bailed = true; result = -2; break; }
+            }
+            for (int k = testspace_en; k < i; ++k) vm_insert_one<VARIANT>(S, arg, k, lane);
+            testspace_en = i;
+            if (VARIANT == 0) {
+                const bool eq = (i + lane) < n && a[i + lane].x == ai.x;
+                const unsigned m = __ballot_sync(VM_FULL, eq);
+                int run = (m == VM_FULL) ? 32 : (__ffs(~m) - 1);
+                if (run > 20) run = 20;
+                c.skipcost = A.skipcost + (double)run;
+                c.maxdiff = A.maxdiff - run > 10 ? A.maxdiff - run : 10;
+            }
+            prekey = key;
+        }
+        double max_scores = (double)ai.l;
+        int pre_index = VM_NOPRE;
+        const double li = (double)ai.l;
+        for (int top = testspace_en; top > 0; top -= 32) {
+            const int q = top - 1 - lane;
+            const bool valid = q >= 0;
+            int j = 0;
+            double Sj = 0.0, t = -CUDART_INF;
+            bool skip = false;
+            if (valid) {
+                j = arg[q];
+                Sj = S[j];
+                const VmAnchor aj = a[j];
+                t = vm_pair_score<VARIANT>(c, ai, aj, Sj, skip);
+            }
+            // running max the reference would hold just before visiting this lane's j
+            double inc = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double o = __shfl_up_sync(VM_FULL, inc, d);
+                if (lane >= d && o > inc) inc = o;
+            }
+            double exc = __shfl_up_sync(VM_FULL, inc, 1);
+            if (lane == 0 || !(exc > max_scores)) exc = max_scores;
+            bool brk;
+            if (VARIANT == 0) brk = valid && !(Sj > (exc - li));   // :24949 / else break :25003
+            else brk = valid && (Sj < (exc - li));                 // :27413
+            const unsigned bm = __ballot_sync(VM_FULL, brk);
+            const unsigned vm = __ballot_sync(VM_FULL, valid);
+            const int nvalid = __popc(vm);
+            int first = bm ? (__ffs(bm) - 1) : nvalid;
+            // lanes at/after the break are never evaluated
+            if (lane >= first) t = -CUDART_INF;
+            if (VARIANT == 0) opcount += first;                      // counted inside the if (:24951)
+            else opcount += bm ? first + 1 : nvalid;                 // counted before the test (:27410)
+            // arg-max, lowest lane (= first visited) wins ties
+            double bt = t;
+            int bl = lane;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) {
+                const double ot = __shfl_xor_sync(VM_FULL, bt, d);
+                const int ol = __shfl_xor_sync(VM_FULL, bl, d);
+                if (ot > bt || (ot == bt && ol < bl)) { bt = ot; bl = ol; }
+            }
+            const int bj = __shfl_sync(VM_FULL, j, bl);
+            if (bt > max_scores) { max_scores = bt; pre_index = bj; }
+            if (bm) break;
+        }
+        if (lane == 0) { S[i] = max_scores; P[i] = pre_index; }
+        __syncwarp();
+        if (max_scores > g_max_scores) { g_max_scores = max_scores; g_max_index = i; }
+    }
+    if (!bailed) {
+        for (int k = testspace_en; k < n; ++k) vm_insert_one<VARIANT>(S, arg, k, lane);
+        result = g_max_index;
+        if (SMEM) {
+            double *So = A.S + base;
+            int32_t *Ao = A.S_arg + base;
+            for (int t = lane; t < n; t += 32) { So[t] = S[t]; Ao[t] = arg[t]; }
+        }
+    }
+    if (lane == 0) { A.gmax[rid] = result; A.opcount[rid] = opcount; }
+}
+
+template <int VARIANT>
+static int vm_launch_exact_v(const VmChainArgs &args, const int *ids, int n_ids, int cap, bool use_smem,
+                             cudaStream_t stream)
+{
+    if (n_ids <= 0) return 0;
+    if (use_smem) {
+        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 12;
+        cudaFuncSetAttribute(vm_chain_exact_kernel<VARIANT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        vm_chain_exact_kernel<VARIANT, true><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+    } else {
+        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;
+        vm_chain_exact_kernel<VARIANT, false><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+    }
+    return 1;
+}
+
+int vm_launch_chain_exact(int variant, const VmChainArgs &args, const int *read_ids_dev, int n_ids,
+                          int cap, bool use_smem, cudaStream_t stream)
+{
+    switch (variant) {
+    case 0: return vm_launch_exact_v<0>(args, read_ids_dev, n_ids, cap, use_smem, stream);
+    case 1: return vm_launch_exact_v<1>(args, read_ids_dev, n_ids, cap, use_smem, stream);
+    default: return vm_launch_exact_v<2>(args, read_ids_dev, n_ids, cap, use_smem, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// heuristic ("fast") DP: `_d_fast_all` :25033-25339 and the local `_fast`
+// fall-backs :26938-27303, :27891-28248.  The algorithm is defined by its
+// integer-score buckets and closest-diagonal probe, so it is replayed step by
+// step: warp-uniform scalar control flow (every lane computes the same values,
+// lane 0 stores), with the S_arg_i tail shift done by all lanes.
+// scratch per read (int64): Si[n], target[n], count[cnt]
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int vm_ips_distance(const long long *Si, long long target, int k, const int32_t *arg,
+                                               long long tdist, const long long *dist)
+{
+    int i = 0, j = k;
+    if (Si[arg[0]] > target) return 0;
+    if (Si[arg[k - 1]] < target) return k;
+    while (i < j) {
+        const int mid = (i + j) >> 1;
+        const long long now = Si[arg[mid]];
+        if (now < target) i = mid + 1;
+        else if (now > target) j = mid;
+        else {
+            const long long nd = dist[arg[mid]];
+            if (nd < tdist) i = mid + 1;
+            else if (nd > tdist) j = mid;
+            else return mid + 1;
+        }
+    }
+    return j;
+}
+
+__device__ __forceinline__ int vm_closest_distance(long long tdist, const long long *dist, const int32_t *arg,
+                                                   int st, int en)
+{
+    int i = st, j = en;
+    if (dist[arg[i]] >= tdist) return i;
+    if (dist[arg[j - 1]] <= tdist) return j - 1;
+    while (i < j) {
+        const int mid = (i + j) >> 1;
+        const long long nd = dist[arg[mid]];
+        if (nd < tdist) i = mid + 1;
+        else if (nd > tdist) j = mid;
+        else return mid;
+    }
+    if ((tdist - dist[arg[j - 1]]) < (dist[arg[j]] - tdist)) return j - 1;
+    return j;
+}
+
+__device__ __forceinline__ void vm_shift_insert(int32_t *arg, int pos, int k, int lane)
+{
+    for (int hi = k; hi > pos; hi -= 32) {
+        const int idx = hi - 1 - lane;
+        int v = 0;
+        if (idx >= pos) v = arg[idx];
+        __syncwarp();
+        if (idx >= pos) arg[idx + 1] = v;
+    }
+    __syncwarp();
+    if (lane == 0) arg[pos] = k;
+    __syncwarp();
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(32) vm_chain_fast_kernel(VmChainArgs A, int fast_t, const int *__restrict__ read_ids,
+                                                           long long *__restrict__ scratch,
+                                                           const int64_t *__restrict__ scratch_off)
+{
+    extern __shared__ __align__(16) unsigned char vm_smem[];
+    const int lane = threadIdx.x;
+    const int rid = read_ids[blockIdx.x];
+    const long long base = A.off[rid];
+    const int n = (int)(A.off[rid + 1] - base);
+    const VmAnchor *__restrict__ a = A.anchors + base;
+    double *gcl = (double *)vm_smem;
+    float *rgl = (float *)(gcl + VM_GCL_MAX);
+    for (int t = lane; t <= A.maxdiff && t < VM_GCL_MAX; t += 32) gcl[t] = A.gapcost_list[t];
+    if (VARIANT != 0)
+        for (int t = lane; t < A.n_rg && t < VM_RGL_MAX; t += 32) rgl[t] = A.rgcost[t];
+    __syncwarp();
+    if (n <= 0) {
+        if (lane == 0) A.gmax[rid] = -1;
+        return;
+    }
+    double *S = A.S + base;
+    int32_t *P = A.P + base;
+    int32_t *arg = A.S_arg + base;
+    const long long sbase = scratch_off[blockIdx.x];
+    const long long cnt_size = scratch_off[blockIdx.x + 1] - sbase - 2LL * n;
+    long long *Si = scratch + sbase;
+    long long *target = Si + n;
+    long long *count = target + n;
+
+    VmScoreCtx c;
+    c.skipcost = A.skipcost; c.maxdiff = A.maxdiff; c.maxgap = A.maxgap;
+    c.gcl = gcl; c.rgl = rgl; c.extra = A.extra; c.extra_size = A.extra_size;
+    c.log2cache = A.log2cache; c.log2cache_size = A.log2cache_size;
+
+    const int lastpos = a[n - 1].x;
+    const long long readlength = (long long)lastpos + 1000;
+    for (int t = lane; t < n; t += 32) {
+        const VmAnchor v = a[t];
+        if (v.s == 1) target[t] = (long long)v.y - v.x + readlength;
+        else target[t] = -((long long)v.y + v.x + readlength);
+    }
+    for (long long t = lane; t < cnt_size; t += 32) count[t] = 0;
+    __syncwarp();
+
+    const VmAnchor a0 = a[0];
+    int prekey = VARIANT == 0 ? a0.x : a0.x + a0.l;
+    int testspace_en_i = 1;
+    if (lane == 0) {
+        arg[0] = 0; S[0] = (double)a0.l; Si[0] = a0.l; P[0] = VM_NOPRE;
+        if (a0.l < cnt_size) count[a0.l] = 1;
+    }
+    __syncwarp();
+    double g_max_scores = (double)a0.l;
+    int g_max_index = 0;
+    long long max_score_i = 0;
+
+    for (int i = 1; i < n; ++i) {
+        const VmAnchor ai = a[i];
+        double max_scores = (double)ai.l;
+        int pre_index = VM_NOPRE;
+        const int key = VARIANT == 0 ? ai.x : ai.x + ai.l;
+        if (prekey < key) {
+            for (int k = testspace_en_i; k < i; ++k) {
+                const long long sk = Si[k];
+                if (lane == 0 && sk < cnt_size) count[sk] += 1;
+                if (sk > max_score_i) max_score_i = sk;
+                const int loc = vm_ips_distance(Si, sk, k, arg, target[k], target);
+                vm_shift_insert(arg, loc, k, lane);
+            }
+            testspace_en_i = i;
+            if (VARIANT == 0) {
+                const bool eq = (i + lane) < n && a[i + lane].x == ai.x;
+                const unsigned m = __ballot_sync(VM_FULL, eq);
+                int run = (m == VM_FULL) ? 32 : (__ffs(~m) - 1);
+                if (run > 20) run = 20;
+                c.skipcost = A.skipcost + (double)run;
+                c.maxdiff = A.maxdiff - run > 10 ? A.maxdiff - run : 10;
+            }
+            prekey = key;
+        }
+        long long c_score_i = max_score_i;
+        int en_loc = testspace_en_i;
+        const long long f_kmersize = (long long)ai.l + 1;
+        while ((double)c_score_i > (max_scores - (double)f_kmersize)) {
+            const long long now_count = (c_score_i >= 0 && c_score_i < cnt_size) ? count[c_score_i] : 0;
+            if (now_count == 0) { --c_score_i; continue; }
+            const int st_loc = en_loc - (int)now_count;
+            if (now_count > fast_t) {
+                const int j = arg[vm_closest_distance(target[i], target, arg, st_loc, en_loc)];
+                bool skip;
+                const double t = vm_pair_score<VARIANT>(c, ai, a[j], S[j], skip);
+                if (!skip && t > max_scores) { max_scores = t; pre_index = j; }
+            } else {
+                for (int q = en_loc - 1; q >= st_loc; --q) {
+                    const int j = arg[q];
+                    bool skip;
+                    const double t = vm_pair_score<VARIANT>(c, ai, a[j], S[j], skip);
+                    if (!skip && t > max_scores) { max_scores = t; pre_index = j; }
+                }
+            }
+            en_loc = st_loc;
+            --c_score_i;
+        }
+        if (lane == 0) { S[i] = max_scores; Si[i] = (long long)max_scores; P[i] = pre_index; }
+        __syncwarp();
+        if (max_scores > g_max_scores) { g_max_scores = max_scores; g_max_index = i; }
+    }
+    for (int k = testspace_en_i; k < n; ++k) {
+        const long long sk = Si[k];
+        if (lane == 0 && sk < cnt_size) count[sk] += 1;
+        const int loc = vm_ips_distance(Si, sk, k, arg, target[k], target);
+        vm_shift_insert(arg, loc, k, lane);
+    }
+    if (lane == 0) A.gmax[rid] = g_max_index;
+}
+
+int vm_launch_chain_fast(int variant, const VmChainArgs &args, int fast_t, const int *read_ids_dev,
+                         int n_ids, long long *scratch_i64, const int64_t *scratch_off,
+                         cudaStream_t stream)
+{
+    if (n_ids <= 0) return 0;
+    size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;
+    switch (variant) {
+    case 0: vm_chain_fast_kernel<0><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
+    case 1: vm_chain_fast_kernel<1><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
+    default: vm_chain_fast_kernel<2><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
+    }
+    return 1;
+}

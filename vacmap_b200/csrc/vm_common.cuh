@@ -1,0 +1,70 @@
+// Shared device/host helpers for the vacmap_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#define VM_FULL 0xffffffffu
+#define VM_NOPRE (-9999999)
+
+// A seed/anchor as the reference's 4-tuple (readpos, refpos, strand, len)
+// (mammap_clrnano.py:23985) packed to 16 bytes so one LDG.128 / LDS.128 fetches it.
+// refpos is the GLOBAL concatenated reference coordinate; GRCh38-sized references
+// exceed 2^31, so it is carried as uint32 and widened to int64 for gap arithmetic.
+struct __align__(16) VmAnchor {
+    int32_t x;      // read position (start)
+    uint32_t y;     // global reference position (leftmost)
+    int32_t s;      // strand +1 / -1
+    int32_t l;      // length
+};
+
+struct VmError {
+    std::string msg;
+};
+
+#define VM_CUDA_OK(ctx, call)                                                        \
+    do {                                                                             \
+        cudaError_t _e = (call);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            char _b[512];                                                            \
+            snprintf(_b, sizeof(_b), "%s:%d %s -> %s", __FILE__, __LINE__, #call,    \
+                     cudaGetErrorString(_e));                                        \
+            (ctx)->err = _b;                                                         \
+            return VM_ERR_CUDA;                                                      \
+        }                                                                            \
+    } while (0)
+
+// pairwise gap geometry shared by all chaining variants
+// (reference: mammap_clrnano.py:24953-24984 global, 27418-27456 local)
+__device__ __forceinline__ void vm_pair_gaps(const VmAnchor &ai, const VmAnchor &aj,
+                                             int &bonus, int &readgap, long long &refgap)
+{
+    const int rg = ai.x - aj.x - aj.l;
+    const long long yi = (long long)ai.y, yj = (long long)aj.y;
+    if (rg < 0) {
+        const int b = ai.x + ai.l - aj.x - aj.l;
+        const int ov = aj.x + aj.l - ai.x;
+        bonus = b;
+        readgap = 0;
+        if (ai.s == aj.s) {
+            if (ai.s == 1) refgap = yi + ov - (yj + aj.l);
+            else refgap = yj - (yi + b);
+        } else {
+            if (aj.s == -1) refgap = yi + ov - yj + 1;
+            else refgap = yi + b - 1 - (yj + aj.l);
+        }
+    } else {
+        bonus = ai.l;
+        readgap = rg;
+        if (ai.s == aj.s) {
+            if (ai.s == 1) refgap = yi - yj - aj.l;
+            else refgap = yj - yi - ai.l;
+        } else {
+            if (aj.s == -1) refgap = yi - yj + 1;
+            else refgap = yi + ai.l - 1 - yj - aj.l;
+        }
+    }
+}
+
+__device__ __forceinline__ long long vm_llabs(long long v) { return v < 0 ? -v : v; }

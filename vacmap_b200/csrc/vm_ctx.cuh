@@ -1,0 +1,79 @@
+// Per-GPU context of libvacmap_b200: stream, growable device arenas, tables.
+#pragma once
+#include "../../include/vacmap_b200.h"
+#include "vm_common.cuh"
+#include <string>
+#include <vector>
+
+struct VmDevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct VmPinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+// state of the stage-level global-chaining call (upload / run / download)
+struct VmChainState {
+    bool loaded = false;
+    vm_chain_params prm{};
+    int64_t n_reads = 0;
+    int64_t total = 0;
+    std::vector<int64_t> off;
+    std::vector<int32_t> read_len;
+    VmDevBuf rows, off_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
+        fast_scratch, fast_off;
+    std::vector<int32_t> used_fast;
+    float ms[4] = {0, 0, 0, 0};
+};
+
+struct vm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 0;
+    // tables
+    VmDevBuf extra, readgapcost, log2cache;
+    int64_t n_extra = 0, n_readgapcost = 0, n_log2cache = 0;
+    VmChainState chain;
+};
