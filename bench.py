@@ -138,6 +138,7 @@ def cpu_baseline(wl, sample_reads, cores):
     import multiprocessing as mp
     import oracle
     oracle.lib()
+    oracle.tables()   # built once, inherited by the forked workers
     sample = wl.anchor_list[:sample_reads]
     chunks = [sample[i::cores] for i in range(cores)]
     chunks = [c for c in chunks if c]
