@@ -52,6 +52,7 @@ def gen_chain():
     # noise only, large: triggers the opcount bail-out (:24914) -> g = -1
     cases.append(synth.anchors_global(rng, n_true=0, n_noise=3200, repeats=False))
     for ci, a in enumerate(cases):
+        out["g_%d_raw" % ci] = a.astype(np.int32)   # as index.map() would hand them over (unsorted)
         a = a[nb_argsort(a[:, 0])]
         g, S, Pp, A, f = dall(a, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
         out["g_%d_a" % ci] = a.astype(np.int32) if a.max() < 2**31 else a

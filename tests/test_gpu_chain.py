@@ -39,12 +39,13 @@ def test_golden_global(gpu_ctx):
     prm = vb.ChainParams()
     al, Ls = [], []
     for ci in range(int(G["g_count"])):
-        a = G["g_%d_a" % ci].astype(np.int64)
+        a = G["g_%d_raw" % ci].astype(np.int64)
         al.append(a)
         Ls.append(15000 if len(a) <= 5 * 15000 else 100)
     res = vb.chain_global_batch(al, Ls, prm, ctx=gpu_ctx)
     for ci, r in enumerate(res):
         ge = int(G["g_%d_exact" % ci])
+        assert (r.sorted == G["g_%d_a" % ci]).all()
         if ge >= 0:
             assert not r.used_fast and r.g_max_index == ge
             assert (r.S == G["g_%d_S" % ci]).all() and (r.P == G["g_%d_P" % ci]).all() and (r.S_arg == G["g_%d_A" % ci]).all()

@@ -5,8 +5,6 @@
 #include <cmath>
 #include <cstring>
 
-int vm_launch_gather(const VmAnchor *in, const int64_t *off, int n_reads, const int32_t *perm,
-                     VmAnchor *sorted, int64_t *sorted_rows, long long total, cudaStream_t stream);
 
 extern "C" {
 
@@ -40,7 +38,7 @@ void vm_ctx_destroy(vm_ctx *c)
     cudaStreamSynchronize(c->stream);
     VmChainState &s = c->chain;
     VmDevBuf *bufs[] = {&s.rows, &s.off_dev, &s.anch, &s.perm, &s.sorted, &s.sorted_rows, &s.S, &s.P,
-                        &s.S_arg, &s.gmax, &s.opcount, &s.ids, &s.gcl, &s.rgl, &s.fast_scratch, &s.fast_off,
+                        &s.S_arg, &s.gmax, &s.opcount, &s.ids, &s.gcl, &s.rgl, &s.fast_scratch, &s.fast_off, &s.sort_scratch,
                         &c->extra, &c->readgapcost, &c->log2cache};
     for (VmDevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ev[i]);
@@ -165,6 +163,14 @@ int vm_chain_global_upload(vm_ctx *c, const vm_chain_params *prm, int64_t n_read
     }
     s.off.assign(off, off + n_reads + 1);
     s.read_len.assign(read_len, read_len + n_reads);
+    // the fast DP indexes a per-score counter by integer chain score (<= last read position + k):
+    // size it from the larger of the declared read length and the largest anchor end actually present
+    s.cnt_len.assign(n_reads, 0);
+    for (int64_t r = 0; r < n_reads; ++r) {
+        int64_t mx = 0;
+        for (int64_t t = off[r]; t < off[r + 1]; ++t) mx = std::max(mx, anchors[t * 4] + anchors[t * 4 + 3]);
+        s.cnt_len[r] = (int32_t)std::min<int64_t>(std::max<int64_t>(mx, s.read_len[r]), INT32_MAX - 128);
+    }
     const size_t T = (size_t)std::max<int64_t>(s.total, 1);
     VM_CUDA_OK(c, s.rows.ensure(T * 32));
     VM_CUDA_OK(c, s.off_dev.ensure((n_reads + 1) * 8));
@@ -178,6 +184,7 @@ int vm_chain_global_upload(vm_ctx *c, const vm_chain_params *prm, int64_t n_read
     VM_CUDA_OK(c, s.gmax.ensure((n_reads + 1) * 8));
     VM_CUDA_OK(c, s.opcount.ensure((n_reads + 1) * 8));
     VM_CUDA_OK(c, s.ids.ensure((n_reads + 1) * 4 * 2));
+    VM_CUDA_OK(c, s.sort_scratch.ensure(T * 12));
     if (s.total > 0)
         VM_CUDA_OK(c, cudaMemcpyAsync(s.rows.p, anchors, (size_t)s.total * 32, cudaMemcpyHostToDevice, c->stream));
     VM_CUDA_OK(c, cudaMemcpyAsync(s.off_dev.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -214,17 +221,7 @@ int vm_chain_global_run(vm_ctx *c, float *kernel_ms)
         if (n > 2000) may_bail = true;   // opcount/i > 1000 needs i > 2000 (global); local needs opcount > 1e5
     }
 
-    cudaEvent_t *ev = c->ev;
-    VM_CUDA_OK(c, cudaEventRecord(ev[0], c->stream));
-    c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
-    VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
-    c->launches += vm_launch_sort_replay(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), n_reads, by_end ? 1 : 0,
-                                         s.perm.as<int32_t>(), nullptr, nullptr, c->stream);
-    c->launches += vm_launch_gather(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), n_reads, s.perm.as<int32_t>(),
-                                    s.sorted.as<VmAnchor>(), s.sorted_rows.as<int64_t>(), s.total, c->stream);
-    VM_CUDA_OK(c, cudaEventRecord(ev[2], c->stream));
-
-    // exact DP, one launch per capacity class
+    // read ids grouped by capacity class (shared by the sort and DP launches)
     std::vector<int> ids_host;
     std::vector<int> cls_start(kNumCaps + 2, 0);
     for (int k = 0; k <= kNumCaps; ++k) {
@@ -232,8 +229,32 @@ int vm_chain_global_run(vm_ctx *c, float *kernel_ms)
         ids_host.insert(ids_host.end(), cls[k].begin(), cls[k].end());
     }
     cls_start[kNumCaps + 1] = (int)ids_host.size();
+    const int n_exact = (int)ids_host.size();
+    ids_host.insert(ids_host.end(), fast_ids.begin(), fast_ids.end());   // fast-path reads still need sorting
     if (!ids_host.empty())
         VM_CUDA_OK(c, cudaMemcpyAsync(s.ids.p, ids_host.data(), ids_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
+
+    cudaEvent_t *ev = c->ev;
+    VM_CUDA_OK(c, cudaEventRecord(ev[0], c->stream));
+    c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
+    VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
+    for (int k = 0; k <= kNumCaps; ++k) {
+        const int cnt = cls_start[k + 1] - cls_start[k];
+        if (cnt == 0) continue;
+        const bool smem = k < kNumCaps && kCaps[k] <= VM_SORT_SMEM_CAP;
+        c->launches += vm_launch_sort_anchors(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(),
+                                              s.ids.as<int>() + cls_start[k], cnt, smem ? kCaps[k] : 0, smem,
+                                              by_end ? 1 : 0, s.perm.as<int32_t>(), s.sort_scratch.as<int32_t>(),
+                                              s.sorted.as<VmAnchor>(), s.sorted_rows.as<int64_t>(), c->stream);
+    }
+    if (!fast_ids.empty())
+        c->launches += vm_launch_sort_anchors(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), s.ids.as<int>() + n_exact,
+                                              (int)fast_ids.size(), 0, false, by_end ? 1 : 0, s.perm.as<int32_t>(),
+                                              s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(),
+                                              s.sorted_rows.as<int64_t>(), c->stream);
+    VM_CUDA_OK(c, cudaEventRecord(ev[2], c->stream));
+
+    // exact DP, one launch per capacity class
     for (int k = 0; k <= kNumCaps; ++k) {
         const int cnt = cls_start[k + 1] - cls_start[k];
         if (cnt == 0) continue;
@@ -248,15 +269,15 @@ int vm_chain_global_run(vm_ctx *c, float *kernel_ms)
         std::vector<int64_t> g(n_reads);
         VM_CUDA_OK(c, cudaMemcpyAsync(g.data(), s.gmax.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
         VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        for (int r : ids_host)
-            if (g[r] < 0) fast_ids.push_back(r);
+        for (int t = 0; t < n_exact; ++t)
+            if (g[ids_host[t]] < 0) fast_ids.push_back(ids_host[t]);
     }
     if (!fast_ids.empty()) {
         std::vector<int64_t> soff(fast_ids.size() + 1, 0);
         for (size_t t = 0; t < fast_ids.size(); ++t) {
             const int r = fast_ids[t];
             const int64_t n = s.off[r + 1] - s.off[r];
-            soff[t + 1] = soff[t] + 2 * n + (int64_t)s.read_len[r] + 64;
+            soff[t + 1] = soff[t] + 2 * n + (int64_t)s.cnt_len[r] + 64;
             s.used_fast[r] = 1;
         }
         VM_CUDA_OK(c, s.fast_scratch.ensure((size_t)soff.back() * 8));

@@ -1,5 +1,6 @@
 // Non-linear anchor chaining kernels (see vm_chain.cuh for the design note).
 #include "vm_chain.cuh"
+#include "vm_sort.cuh"
 #include <math_constants.h>
 
 // ---------------------------------------------------------------------------
@@ -28,113 +29,76 @@ int vm_launch_pack(const int64_t *rows_dev, VmAnchor *out, long long total, cuda
 }
 
 // ---------------------------------------------------------------------------
-// numba argsort replay (numba/misc/quicksort.py): the permutation among equal
-// keys depends on the exact pivot/swap sequence, and the DP's tie-breaking
-// depends on that permutation, so the algorithm is replayed literally.
-// One thread per read; keys are read positions (global DP, reference :23572)
-// or read end positions (local DP, :28585).
+// anchor sort: warp-cooperative replay of numba's argsort (vm_sort.cuh), one warp
+// per read.  Keys are read positions (global DP, reference :23572) or read end
+// positions (local DP, :28585).  The sorted anchors are gathered in the same
+// kernel (coalesced 16-byte stores; the random 16-byte loads hit L2).
 // ---------------------------------------------------------------------------
-template <int KEY_IS_END>
-__device__ __forceinline__ int vm_key(const VmAnchor *a, int idx)
+template <int KEY_IS_END, bool SMEM>
+__global__ void __launch_bounds__(32) vm_sort_anchors_kernel(const VmAnchor *__restrict__ in,
+                                                             const int64_t *__restrict__ off,
+                                                             const int *__restrict__ read_ids, int cap,
+                                                             int32_t *__restrict__ perm, int32_t *__restrict__ gscratch,
+                                                             VmAnchor *__restrict__ sorted,
+                                                             longlong4 *__restrict__ sorted_rows)
 {
-    if (KEY_IS_END) return a[idx].x + a[idx].l;
-    return a[idx].x;
-}
-
-template <int KEY_IS_END>
-__global__ void vm_sort_replay_kernel(const VmAnchor *__restrict__ in, const int64_t *__restrict__ off,
-                                      int n_reads, int32_t *__restrict__ perm)
-{
-    int rid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rid >= n_reads) return;
+    extern __shared__ __align__(16) unsigned char vm_smem[];
+    const int lane = threadIdx.x;
+    const int rid = read_ids[blockIdx.x];
     const long long base = off[rid];
     const int n = (int)(off[rid + 1] - base);
+    if (n <= 0) return;
     const VmAnchor *A = in + base;
-    int32_t *R = perm + base;
-    for (int t = 0; t < n; ++t) R[t] = t;
-    if (n < 2) return;
-    int stack_lo[100], stack_hi[100];
-    int sp = 1;
-    stack_lo[0] = 0;
-    stack_hi[0] = n - 1;
-    while (sp > 0) {
-        --sp;
-        int low = stack_lo[sp], high = stack_hi[sp];
-        while (high - low >= 15) {
-            int mid = (low + high) >> 1, tmp;
-            if (vm_key<KEY_IS_END>(A, R[mid]) < vm_key<KEY_IS_END>(A, R[low])) { tmp = R[low]; R[low] = R[mid]; R[mid] = tmp; }
-            if (vm_key<KEY_IS_END>(A, R[high]) < vm_key<KEY_IS_END>(A, R[mid])) { tmp = R[high]; R[high] = R[mid]; R[mid] = tmp; }
-            if (vm_key<KEY_IS_END>(A, R[mid]) < vm_key<KEY_IS_END>(A, R[low])) { tmp = R[low]; R[low] = R[mid]; R[mid] = tmp; }
-            const int pivot = vm_key<KEY_IS_END>(A, R[mid]);
-            tmp = R[high]; R[high] = R[mid]; R[mid] = tmp;
-            int i = low, j = high - 1;
-            for (;;) {
-                while (i < high && vm_key<KEY_IS_END>(A, R[i]) < pivot) ++i;
-                while (j >= low && pivot < vm_key<KEY_IS_END>(A, R[j])) --j;
-                if (i >= j) break;
-                tmp = R[i]; R[i] = R[j]; R[j] = tmp;
-                ++i; --j;
-            }
-            tmp = R[i]; R[i] = R[high]; R[high] = tmp;
-            if (high - i > i - low) {
-                if (high > i) { stack_lo[sp] = i + 1; stack_hi[sp] = high; ++sp; }
-                high = i - 1;
-            } else {
-                if (i > low) { stack_lo[sp] = low; stack_hi[sp] = i - 1; ++sp; }
-                low = i + 1;
-            }
-        }
-        for (int i = low + 1; i <= high; ++i) {
-            const int k = R[i];
-            const int v = vm_key<KEY_IS_END>(A, k);
-            int j = i;
-            while (j > low && v < vm_key<KEY_IS_END>(A, R[j - 1])) { R[j] = R[j - 1]; --j; }
-            R[j] = k;
+    int *keys, *R, *Lpos, *Rpos;
+    if (SMEM) {
+        keys = (int *)vm_smem;
+        R = keys + cap;
+        Lpos = R + cap;
+        Rpos = Lpos + cap;
+    } else {
+        keys = gscratch + 3 * base;
+        Lpos = keys + n;
+        Rpos = Lpos + n;
+        R = perm + base;
+    }
+    for (int t = lane; t < n; t += 32) {
+        const VmAnchor a = A[t];
+        keys[t] = KEY_IS_END ? a.x + a.l : a.x;
+    }
+    __syncwarp();
+    vm_warp_argsort_replay<int>(keys, R, Lpos, Rpos, n, lane);
+    for (int t = lane; t < n; t += 32) {
+        const int src = R[t];
+        if (SMEM) perm[base + t] = src;
+        const VmAnchor a = A[src];
+        sorted[base + t] = a;
+        if (sorted_rows) {
+            longlong4 r;
+            r.x = a.x; r.y = (long long)a.y; r.z = a.s; r.w = a.l;
+            sorted_rows[base + t] = r;
         }
     }
 }
 
-// gather anchors through the permutation (one thread per anchor, binary search for the read)
-__global__ void vm_gather_kernel(const VmAnchor *__restrict__ in, const int64_t *__restrict__ off, int n_reads,
-                                 const int32_t *__restrict__ perm, VmAnchor *__restrict__ sorted,
-                                 longlong4 *__restrict__ sorted_rows, long long total)
+int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int *read_ids_dev, int n_ids, int cap,
+                           bool use_smem, int key_is_end, int32_t *perm, int32_t *gscratch, VmAnchor *sorted,
+                           int64_t *sorted_rows, cudaStream_t stream)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int lo = 0, hi = n_reads;   // largest r with off[r] <= i
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (off[mid] <= i) lo = mid; else hi = mid;
+    if (n_ids <= 0) return 0;
+    longlong4 *rows = (longlong4 *)sorted_rows;
+    if (use_smem) {
+        const size_t smem = (size_t)cap * 16;
+        if (key_is_end) {
+            cudaFuncSetAttribute(vm_sort_anchors_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            vm_sort_anchors_kernel<1, true><<<n_ids, 32, smem, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+        } else {
+            cudaFuncSetAttribute(vm_sort_anchors_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            vm_sort_anchors_kernel<0, true><<<n_ids, 32, smem, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+        }
+    } else {
+        if (key_is_end) vm_sort_anchors_kernel<1, false><<<n_ids, 32, 0, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+        else vm_sort_anchors_kernel<0, false><<<n_ids, 32, 0, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
     }
-    const long long base = off[lo];
-    VmAnchor a = in[base + perm[i]];
-    sorted[i] = a;
-    if (sorted_rows) {
-        longlong4 r;
-        r.x = a.x; r.y = (long long)a.y; r.z = a.s; r.w = a.l;
-        sorted_rows[i] = r;
-    }
-}
-
-int vm_launch_sort_replay(const VmAnchor *in, const int64_t *off, int n_reads, int key_is_end,
-                          int32_t *perm, VmAnchor *sorted, int64_t *sorted_rows, cudaStream_t stream)
-{
-    if (n_reads <= 0) return 0;
-    int threads = 32;   // divergent serial work per thread: keep warps small-grained across SMs
-    int blocks = (n_reads + threads - 1) / threads;
-    if (key_is_end) vm_sort_replay_kernel<1><<<blocks, threads, 0, stream>>>(in, off, n_reads, perm);
-    else vm_sort_replay_kernel<0><<<blocks, threads, 0, stream>>>(in, off, n_reads, perm);
-    return 1;
-}
-
-int vm_launch_gather(const VmAnchor *in, const int64_t *off, int n_reads, const int32_t *perm,
-                     VmAnchor *sorted, int64_t *sorted_rows, long long total, cudaStream_t stream)
-{
-    if (total <= 0) return 0;
-    int threads = 256;
-    long long blocks = (total + threads - 1) / threads;
-    vm_gather_kernel<<<(unsigned)blocks, threads, 0, stream>>>(in, off, n_reads, perm, sorted,
-                                                              (longlong4 *)sorted_rows, total);
     return 1;
 }
 

@@ -48,5 +48,7 @@ int vm_launch_chain_fast(int variant, const VmChainArgs &args, int fast_t, const
                          int n_ids, long long *scratch_i64, const int64_t *scratch_off,
                          cudaStream_t stream);
 int vm_launch_pack(const int64_t *rows_dev, VmAnchor *out, long long total, cudaStream_t stream);
-int vm_launch_sort_replay(const VmAnchor *in, const int64_t *off, int n_reads, int key_is_end,
-                          int32_t *perm, VmAnchor *sorted, int64_t *sorted_rows, cudaStream_t stream);
+#define VM_SORT_SMEM_CAP 8192      // anchors; 16 B each (keys, perm, two stop lists) -> 128 KB
+int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int *read_ids_dev, int n_ids, int cap,
+                           bool use_smem, int key_is_end, int32_t *perm, int32_t *gscratch, VmAnchor *sorted,
+                           int64_t *sorted_rows, cudaStream_t stream);

@@ -58,9 +58,9 @@ struct VmChainState {
     int64_t n_reads = 0;
     int64_t total = 0;
     std::vector<int64_t> off;
-    std::vector<int32_t> read_len;
+    std::vector<int32_t> read_len, cnt_len;
     VmDevBuf rows, off_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
-        fast_scratch, fast_off;
+        fast_scratch, fast_off, sort_scratch;
     std::vector<int32_t> used_fast;
     float ms[4] = {0, 0, 0, 0};
 };
