@@ -171,3 +171,126 @@ def chain_local(a, kmersize, variant, skipcost, maxdiff, maxgap, large_readgap=3
     path = np.zeros((n, 4), np.int64)
     m = lib().orc_local_traceback(_p(a), _p(P), g, _p(path))
     return float(S[g]), path[:m].copy(), S, P, used_fast
+
+
+# ---------------------------------------------------------------------------
+# natives restated from the absent third-party packages (parity unpinned)
+# ---------------------------------------------------------------------------
+class KcResult(ctypes.Structure):
+    _fields_ = [("score", ctypes.c_int32), ("max_t", ctypes.c_int32), ("max_q", ctypes.c_int32),
+                ("zdropped", ctypes.c_int32), ("n_cigar", ctypes.c_int32), ("q_e", ctypes.c_int32),
+                ("t_e", ctypes.c_int32), ("ndel", ctypes.c_int32), ("nins", ctypes.c_int32)]
+
+
+_OPS = "MIDNSHP=X"
+
+
+def _declare_natives(L):
+    if getattr(L, "_natives_declared", False):
+        return
+    i64, vp, i32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32
+    L.orc_sketch.restype = i64
+    L.orc_sketch.argtypes = [ctypes.c_char_p, i64, i32, i32, vp, vp, i64]
+    L.orc_index_build.restype = vp
+    L.orc_index_build.argtypes = [ctypes.c_char_p, vp, i32, i32, i32]
+    L.orc_index_free.argtypes = [vp]
+    L.orc_index_stats.argtypes = [vp, vp, vp, vp]
+    L.orc_index_export.argtypes = [vp, vp, vp, vp]
+    L.orc_map.restype = i64
+    L.orc_map.argtypes = [vp, ctypes.c_char_p, i64, i32, i32, vp, i64]
+    L.orc_k_cigar.restype = i32
+    L.orc_k_cigar.argtypes = [ctypes.c_char_p, i32, ctypes.c_char_p, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                              vp, i32, ctypes.POINTER(KcResult)]
+    L.orc_edit_distance.restype = i64
+    L.orc_edit_distance.argtypes = [ctypes.c_char_p, i64, ctypes.c_char_p, i64]
+    L._natives_declared = True
+
+
+def sketch(seq, w, k):
+    """minimap2 mm_sketch restated: returns (hash uint64[n], pos_last<<1|strand uint64[n])."""
+    L = lib(); _declare_natives(L)
+    b = seq.encode() if isinstance(seq, str) else seq
+    cap = len(b) + 16
+    h = np.zeros(cap, np.uint64)
+    y = np.zeros(cap, np.uint64)
+    n = L.orc_sketch(b, len(b), w, k, _p(h), _p(y), cap)
+    return h[:n].copy(), y[:n].copy()
+
+
+class Index:
+    """Minimizer index over a list of (name, sequence) contigs (global concatenated coordinates)."""
+
+    def __init__(self, contigs, w=10, k=15):
+        L = lib(); _declare_natives(L)
+        self.w, self.k = w, k
+        self.names = [n for n, _ in contigs]
+        self.seqs = [s.upper() for _, s in contigs]
+        self.offsets = np.zeros(len(contigs) + 1, np.int64)
+        for i, s in enumerate(self.seqs):
+            self.offsets[i + 1] = self.offsets[i] + len(s)
+        self._cat = "".join(self.seqs).encode()
+        self.h = L.orc_index_build(self._cat, _p(self.offsets), len(contigs), w, k)
+        nk, no, mo = np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1, np.int32)
+        L.orc_index_stats(self.h, _p(nk), _p(no), _p(mo))
+        self.n_keys, self.n_occ, self.mid_occ_default = int(nk[0]), int(no[0]), int(mo[0])
+
+    def export(self):
+        keys = np.zeros(self.n_keys, np.uint64)
+        start = np.zeros(self.n_keys + 1, np.int64)
+        occ = np.zeros(self.n_occ, np.uint64)
+        lib().orc_index_export(self.h, _p(keys), _p(start), _p(occ))
+        return keys, start, occ
+
+    def map(self, seq, check_num=100, mid_occ=-1):
+        """-> int64[n,4] rows (readpos_start, refpos_global_leftmost, strand, len)."""
+        L = lib()
+        b = seq.encode() if isinstance(seq, str) else seq
+        cap = max(4096, 4 * len(b))
+        while True:
+            rows = np.zeros((cap, 4), np.int64)
+            n = L.orc_map(self.h, b, len(b), check_num, mid_occ, _p(rows), cap)
+            if n >= 0:
+                return rows[:n].copy()
+            cap = -n + 16
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_index_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def k_cigar_ops(target, query, match=2, mismatch=-4, gap_open_1=4, gap_extend_1=2, gap_open_2=24, gap_extend_2=1,
+                bw=-1, zdropvalue=-1, eqx=False):
+    """-> (ops uint32[n] BAM-encoded, KcResult)."""
+    L = lib(); _declare_natives(L)
+    t = target.encode() if isinstance(target, str) else target
+    q = query.encode() if isinstance(query, str) else query
+    cap = len(t) + len(q) + 4
+    ops = np.zeros(cap, np.uint32)
+    res = KcResult()
+    rc = L.orc_k_cigar(t, len(t), q, len(q), match, mismatch, gap_open_1, gap_extend_1, gap_open_2, gap_extend_2,
+                       bw, zdropvalue, 1 if eqx else 0, _p(ops), cap, ctypes.byref(res))
+    assert rc == 0
+    return ops[:res.n_cigar].copy(), res
+
+
+def ops_to_string(ops):
+    return "".join("%d%s" % (int(o) >> 4, _OPS[int(o) & 0xf]) for o in ops)
+
+
+def k_cigar(target, query, match=2, mismatch=-4, gap_open_1=4, gap_extend_1=2, gap_open_2=24, gap_extend_2=1,
+            bw=-1, zdropvalue=-1, eqx=False):
+    """vacmap_index.k_cigar contract: (cigar, zdropcode, q_e, t_e, ndel, nins)."""
+    ops, r = k_cigar_ops(target, query, match, mismatch, gap_open_1, gap_extend_1, gap_open_2, gap_extend_2,
+                         bw, zdropvalue, eqx)
+    return ops_to_string(ops), r.zdropped, r.q_e, r.t_e, r.ndel, r.nins
+
+
+def edit_distance(a, b):
+    L = lib(); _declare_natives(L)
+    a = a.encode() if isinstance(a, str) else a
+    b = b.encode() if isinstance(b, str) else b
+    return int(L.orc_edit_distance(a, len(a), b, len(b)))

@@ -74,3 +74,96 @@ def anchors_local(rng, L=15000, k=9, n_true=1000, n_noise=300, ref0=1_000_000, m
                      1 if rng.random() < 0.5 else -1, ln))
     a = np.array(rows, dtype=np.int64)
     return a[rng.permutation(len(a))]
+
+
+# ---------------------------------------------------------------------------
+# sequences: references, reads with ONT/HiFi-like errors, simple SV donors
+# ---------------------------------------------------------------------------
+_B = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.zeros(256, dtype=np.uint8)
+for _a, _b in zip(b"ACGTN", b"TGCAN"):
+    _COMP[_a] = _b
+
+
+def random_seq(rng, n):
+    return _B[rng.integers(0, 4, size=n)]
+
+
+def make_reference(seed, length, n_contigs=1, repeat_frac=0.05):
+    """i.i.d. ACGT contigs `chr1..`, with `repeat_frac` of the sequence overwritten by diverged copies
+    of earlier 0.3-6 kb segments (exercises the occurrence filter / coverage logic)."""
+    rng = np.random.default_rng(seed)
+    per = length // n_contigs
+    contigs = []
+    for c in range(n_contigs):
+        s = random_seq(rng, per).copy()
+        covered = 0
+        while covered < repeat_frac * per and per > 20000:
+            ln = int(rng.integers(300, 6000))
+            src = int(rng.integers(0, per - ln))
+            dst = int(rng.integers(0, per - ln))
+            seg = s[src:src + ln].copy()
+            nmut = int(ln * rng.uniform(0, 0.1))
+            pos = rng.integers(0, ln, size=nmut)
+            seg[pos] = _B[rng.integers(0, 4, size=nmut)]
+            s[dst:dst + ln] = seg
+            covered += ln
+        contigs.append(("chr%d" % (c + 1), s.tobytes().decode()))
+    return contigs
+
+
+def mutate(rng, seq_u8, err, ratio=(4, 3, 3)):
+    """per-base i.i.d. errors at rate `err`, sub:ins:del = ratio"""
+    n = len(seq_u8)
+    r = rng.random(n)
+    tot = float(sum(ratio))
+    ps, pi = err * ratio[0] / tot, err * ratio[1] / tot
+    out = []
+    kinds = np.where(r < ps, 1, np.where(r < ps + pi, 2, np.where(r < err, 3, 0)))
+    rnd = rng.integers(0, 4, size=n)
+    for i in range(n):
+        k = kinds[i]
+        if k == 0:
+            out.append(seq_u8[i])
+        elif k == 1:
+            b = _B[rnd[i]]
+            out.append(b if b != seq_u8[i] else _B[(rnd[i] + 1) & 3])
+        elif k == 2:
+            out.append(seq_u8[i])
+            out.append(_B[rnd[i]])
+        # k == 3: deletion
+    return np.array(out, dtype=np.uint8)
+
+
+def make_reads(contigs, seed, n_reads, read_len=15000, err=0.10, ratio=(4, 3, 3), sv_frac=0.0):
+    """Reads drawn uniformly; strand ~ Bernoulli(0.5).  With `sv_frac`, a read gets one event from
+    {DEL, INS, INV, DUP, TRA} of 100-1000 bp applied to its source segment before errors."""
+    rng = np.random.default_rng(seed)
+    arrs = [np.frombuffer(s.encode(), dtype=np.uint8) for _, s in contigs]
+    reads = []
+    for i in range(n_reads):
+        c = int(rng.integers(0, len(arrs)))
+        ref = arrs[c]
+        ln = min(read_len, len(ref) - 1)
+        st = int(rng.integers(0, len(ref) - ln))
+        seg = ref[st:st + ln].copy()
+        if rng.random() < sv_frac and ln > 4000:
+            sz = int(rng.integers(100, 1000))
+            p = int(rng.integers(1000, ln - 1000 - sz))
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                seg = np.concatenate([seg[:p], seg[p + sz:]])
+            elif kind == 1:
+                seg = np.concatenate([seg[:p], random_seq(rng, sz), seg[p:]])
+            elif kind == 2:
+                seg = np.concatenate([seg[:p], _COMP[seg[p:p + sz]][::-1], seg[p + sz:]])
+            elif kind == 3:
+                seg = np.concatenate([seg[:p + sz], seg[p:p + sz], seg[p + sz:]])
+            else:
+                q = int(rng.integers(0, len(ref) - sz))
+                seg = np.concatenate([seg[:p], ref[q:q + sz], seg[p:]])
+        if rng.random() < 0.5:
+            seg = _COMP[seg][::-1]
+        seg = mutate(rng, seg, err, ratio)
+        reads.append(("read_%d" % i, seg.tobytes().decode()))
+    return reads
