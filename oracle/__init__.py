@@ -294,3 +294,30 @@ def edit_distance(a, b):
     a = a.encode() if isinstance(a, str) else a
     b = b.encode() if isinstance(b, str) else b
     return int(L.orc_edit_distance(a, len(a), b, len(b)))
+
+
+def local_reseed_scan(ctg, wins, raw_by_x, seq, rc_seq, k, readstart, readend):
+    """orc_local_reseed: the 9-mer table build + read scan + diagonal merge of guide_1 (:23138-23344).
+    -> int64[n,4] anchors in the reference's emission order."""
+    L = lib(); _declare_natives(L)
+    if not hasattr(L, "_reseed_declared"):
+        i64, vp, i32 = ctypes.c_int64, ctypes.c_void_p, ctypes.c_int32
+        L.orc_local_reseed.restype = i64
+        L.orc_local_reseed.argtypes = [ctypes.c_char_p, vp, vp, i32, vp, vp, i64, ctypes.c_char_p, ctypes.c_char_p,
+                                       i64, i32, i64, i64, ctypes.POINTER(ctypes.c_void_p)]
+        L.orc_free.argtypes = [vp]
+        L._reseed_declared = True
+    lo = np.array([w[0] for w in wins], dtype=np.int64)
+    hi = np.array([w[1] for w in wins], dtype=np.int64)
+    gx = np.ascontiguousarray(raw_by_x[:, 0].astype(np.int32))
+    gy = np.ascontiguousarray(raw_by_x[:, 1].astype(np.int64))
+    out = ctypes.c_void_p()
+    n = L.orc_local_reseed(ctg.cat(), _p(lo), _p(hi), len(wins), _p(gx), _p(gy), len(gx), seq.encode(), rc_seq.encode(),
+                           len(seq), k, readstart, readend, ctypes.byref(out))
+    if n > 0:
+        rows = np.ctypeslib.as_array(ctypes.cast(out, ctypes.POINTER(ctypes.c_int64)), shape=(n, 4)).copy()
+    else:
+        rows = np.zeros((0, 4), np.int64)
+    if out.value:
+        L.orc_free(out)
+    return rows

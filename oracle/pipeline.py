@@ -46,6 +46,12 @@ class Contigs:
             self.starts.append(off)
             off += len(s)
         self.total = off
+        self._cat = None
+
+    def cat(self):
+        if self._cat is None:
+            self._cat = "".join(self.seqs).encode()
+        return self._cat
 
     def cid(self, pos):
         c = 0
@@ -270,9 +276,50 @@ def _build_tables(se, ctg, k, look_span):
     return single, multi_tab, retry
 
 
+def guide_windows(raw, ctg, look_span=7000):
+    """Window construction of guide_1 (:23095-23154) -> (list of GLOBAL [lo, hi) ranges in insertion
+    order, guide chain sorted by read position)."""
+    readgap = 0
+    pre = raw[0]
+    for now in raw[1:]:
+        if abs(int(now[0]) - int(pre[0])) > readgap:
+            readgap = abs(int(now[0]) - int(pre[0]))
+        pre = now
+    readgap = max(readgap + 1000, 5000)
+    raw = raw[oracle.argsort_i64(raw[:, 1])]
+
+    def ranges(se):
+        out = []
+        for (min_ref, max_ref) in se:
+            c = ctg.cid(min_ref)
+            if c != ctg.cid(max_ref):
+                return out, True
+            cs = ctg.starts[c]
+            lookfurther = min(look_span, min_ref - cs)
+            lo, hi, _ = slice(min_ref - lookfurther - cs, max_ref + look_span - cs).indices(len(ctg.seqs[c]))
+            out.append((cs + lo, cs + max(hi, lo)))
+        return out, False
+
+    wins, retry = ranges(_windows(raw, readgap, ctg, False))
+    if retry:
+        wins, retry = ranges(_windows(raw, readgap, ctg, True))
+    raw = raw[oracle.argsort_i64(raw[:, 0])]
+    return wins, raw
+
+
 def local_reseed(out, raw, seq, rc_seq, ctg, k):
-    """get_localmap_multi_all_forDP_inv_guide_1 :23069-23345.  `raw`: int64[m,4] guide chain;
-    appends (x, y, strand, len) tuples to `out` in the reference's emission order."""
+    """guide_1 (:23069-23345) with the scan done by the C restatement orc_local_reseed."""
+    wins, raw = guide_windows(raw, ctg)
+    L = len(seq)
+    readstart = max(0, int(raw[0][0]) - 7000)
+    readend = min(L - k + 1, int(raw[-1][0]) + 7000)
+    rows = oracle.local_reseed_scan(ctg, wins, raw, seq, rc_seq, k, readstart, readend)
+    out.extend(tuple(int(v) for v in r) for r in rows)
+
+
+def local_reseed_py(out, raw, seq, rc_seq, ctg, k):
+    """get_localmap_multi_all_forDP_inv_guide_1 :23069-23345, pure Python (cross-check of the C scan).
+    `raw`: int64[m,4] guide chain; appends (x, y, strand, len) tuples to `out` in emission order."""
     look_span = 7000
     readgap = 0
     pre = raw[0]

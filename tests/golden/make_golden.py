@@ -92,7 +92,53 @@ def gen_chain():
     print("chain.npz:", os.path.getsize(os.path.join(HERE, "chain.npz")), "bytes")
 
 
+def gen_e2e():
+    """End-to-end records from the reference's own get_readmap_DP_test / get_bam_dict_str run over the
+    oracle's vacmap_index / edlib shim.  Inputs are regenerated from seeds (tests/synth.py) except the
+    reference's testdata pair, which is copied as a fixture (BASELINE configs[0])."""
+    import gzip
+    import json
+    import shutil
+    import refrun
+    import oracle.shim as shim
+    td = os.path.join(HERE, "testdata")
+    os.makedirs(td, exist_ok=True)
+    for f in ("read.fasta", "reference.fasta"):
+        with open(os.path.join(refimport.REF_ROOT, "testdata", f), "rb") as fi, gzip.open(os.path.join(td, f + ".gz"), "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    out = {"cases": []}
+
+    def case(name, ref, reads, mode, **opt):
+        R = refrun.ReferenceRunner(ref, mode=mode, **opt)
+        recs, sams = [], []
+        for rid, seq in reads:
+            r = R.align(rid, seq)
+            recs.append([list(x) for x in r])
+            sams.append(R.mod.get_bam_dict_str(r, seq.upper(), None, R.contig2iloc, R.contig2seq, R.option["md"],
+                                               R.option["shortcs"], R.option["cigar2cg"], R.option["markunbalancetra"],
+                                               R.option) if r else [])
+        out["cases"].append({"name": name, "mode": mode, "opt": opt, "records": recs, "sam": sams})
+        print(name, "reads", len(reads), "records", sum(len(r) for r in recs))
+
+    ref = [(n, s) for n, s, _ in shim.read_fastx(os.path.join(td, "reference.fasta.gz"))]
+    reads = [(r[0], r[1]) for r in shim.read_fastx(os.path.join(td, "read.fasta.gz"))]
+    case("testdata_H", ref, reads, "H")
+    case("testdata_H_eqx_md", ref, reads, "H", eqx=True, md=True)
+    ref2 = synth.make_reference(1, 300000)
+    reads2 = synth.make_reads(ref2, 11, 16, read_len=6000, err=0.10, sv_frac=0.5)
+    case("synth300k_H", ref2, reads2, "H")
+    case("synth300k_H_eqx", ref2, reads2[:6], "H", eqx=True, md=True)
+    ref3 = synth.make_reference(3, 600000, n_contigs=2)
+    reads3 = synth.make_reads(ref3, 12, 8, read_len=15000, err=0.10, sv_frac=0.3)
+    case("synth600k_2ctg_H", ref3, reads3, "H")
+    with gzip.open(os.path.join(HERE, "e2e.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("e2e.json.gz:", os.path.getsize(os.path.join(HERE, "e2e.json.gz")), "bytes")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["chain"]
     if "chain" in what:
         gen_chain()
+    if "e2e" in what:
+        gen_e2e()
