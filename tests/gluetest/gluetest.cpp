@@ -1,0 +1,253 @@
+// TEST HARNESS (not product): runs the product's host driver + glue (vm_pipeline.hpp, vm_glue.hpp)
+// on a CPU-only box with the ORACLE's C stage functions standing in for the CUDA kernels, so the
+// glue can be checked against the reference-generated golden records without a GPU.
+#include "../../vacmap_b200/csrc/vm_pipeline.hpp"
+#include <cstdio>
+
+extern "C" {
+// oracle/orc_*.c
+typedef struct { const float *extra; int64_t extra_size; const float *readgapcost; const double *log2cache; int64_t log2cache_size; } orc_tables;
+void orc_argsort_i64(const int64_t *A, int64_t n, int64_t *R);
+int64_t orc_chain_global_d_all(const int64_t *a, int64_t n, int kmersize, double skipcost_in, int64_t maxdiff_in, int64_t maxgap,
+                               const orc_tables *tb, int64_t max_factor, double *S, int32_t *P, int32_t *S_arg, int64_t *opcount_out);
+int64_t orc_chain_fast(const int64_t *a, int64_t n, int kmersize, int variant, double skipcost_in, int64_t maxdiff_in, int64_t maxgap,
+                       int64_t fast_t, const orc_tables *tb, const float *rgcost, double *S, int32_t *P, int32_t *S_arg_i);
+int64_t orc_chain_local(const int64_t *a, int64_t n, int kmersize, int variant, double skipcost, int64_t maxdiff, int64_t maxgap,
+                        const orc_tables *tb, const float *rgcost, double *S, int64_t *P, int64_t *S_arg, int64_t *opcount_out);
+void orc_large_readgap_table(int maxgap, int large_readgap, float *out);
+int64_t orc_map(void *h, const char *seq, int64_t len, int32_t check_num, int32_t mid_occ, int64_t *rows, int64_t cap);
+int64_t orc_local_reseed(const char *ref, const int64_t *win_lo, const int64_t *win_hi, int32_t n_win, const int32_t *gx,
+                         const int64_t *gy, int64_t n_guide, const char *seq, const char *rc_seq, int64_t L, int32_t k,
+                         int64_t readstart, int64_t readend, int64_t **rows_out);
+void orc_free(void *p);
+typedef struct { int32_t score, max_t, max_q, zdropped, n_cigar, q_e, t_e, ndel, nins; } orc_kc_result;
+int orc_k_cigar(const char *target, int32_t tlen, const char *query, int32_t qlen, int32_t match, int32_t mismatch, int32_t q1,
+                int32_t e1, int32_t q2, int32_t e2, int32_t bw, int32_t zdrop, int32_t eqx, uint32_t *cigar, int32_t cigar_cap,
+                orc_kc_result *res);
+int64_t orc_edit_distance(const char *a, int64_t n, const char *b, int64_t m);
+}
+
+using namespace vmp;
+
+static std::string revcomp(const std::string &s)
+{
+    std::string r(s.size(), 'N');
+    for (size_t i = 0; i < s.size(); ++i) {
+        const char c = s[s.size() - 1 - i];
+        r[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    }
+    return r;
+}
+
+struct OracleBackend : public Backend {
+    void *index;
+    const orc_tables *tb;
+    const char *ref;
+    OracleBackend(void *ix, const orc_tables *t, const char *r) : index(ix), tb(t), ref(r) {}
+
+    std::string materialize(const ReadBatch &b, int read, const vmg::SeqRef &s) const
+    {
+        std::string out;
+        if (s.src == 0) out.assign(ref + s.lo, (size_t)(s.hi - s.lo));
+        else {
+            std::string fwd(b.seq + b.off[read], (size_t)b.len(read));
+            if (s.src == 2) fwd = revcomp(fwd);
+            out = fwd.substr((size_t)s.lo, (size_t)(s.hi - s.lo));
+        }
+        if (s.comp)
+            for (char &c : out) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+        if (s.reverse) std::reverse(out.begin(), out.end());
+        return out;
+    }
+
+    void seed(const ReadBatch &b, int check_num, Ragged<Anc> &anchors, std::vector<char> &need_reverse) override
+    {
+        anchors.clear();
+        need_reverse.assign((size_t)b.n, 0);
+        for (int64_t r = 0; r < b.n; ++r) {
+            const int64_t L = b.len(r);
+            std::vector<int64_t> rows((size_t)(4 * (4 * L + 4096)));
+            int64_t m = orc_map(index, b.seq + b.off[r], L, check_num, -1, rows.data(), (int64_t)rows.size() / 4);
+            if (m < 0) { rows.resize((size_t)(-m * 4 + 64)); m = orc_map(index, b.seq + b.off[r], L, check_num, -1, rows.data(), -m + 16); }
+            // get_reversed_chain_numpy_rough :21202-21217
+            int64_t neg = 0, pos = 0;
+            for (int64_t t = 0; t < m; ++t) (rows[t * 4 + 2] == 1 ? pos : neg)++;
+            const bool flip = m >= 3 && neg > pos;
+            need_reverse[r] = flip;
+            for (int64_t t = 0; t < m; ++t) {
+                const int64_t q = flip ? m - 1 - t : t;
+                Anc a{rows[q * 4], rows[q * 4 + 1], (int32_t)rows[q * 4 + 2], (int32_t)rows[q * 4 + 3]};
+                if (flip) { a.x = L - a.x - a.l; a.s = -a.s; }
+                anchors.data.push_back(a);
+            }
+            anchors.close_row();
+        }
+    }
+
+    static void to_rows(const Anc *a, int64_t n, std::vector<int64_t> &rows)
+    {
+        rows.resize((size_t)n * 4);
+        for (int64_t t = 0; t < n; ++t) { rows[t * 4] = a[t].x; rows[t * 4 + 1] = a[t].y; rows[t * 4 + 2] = a[t].s; rows[t * 4 + 3] = a[t].l; }
+    }
+
+    void chain_global(const Ragged<Anc> &anchors, const std::vector<int64_t> &read_len, int kmersize, double skipcost,
+                      int maxdiff, int maxgap, ChainOut &out) override
+    {
+        out = ChainOut();
+        out.gmax.assign((size_t)anchors.rows(), -1);
+        for (int64_t r = 0; r < anchors.rows(); ++r) {
+            const int64_t n = anchors.size(r);
+            std::vector<int64_t> keys((size_t)n), perm((size_t)n), rows;
+            for (int64_t t = 0; t < n; ++t) keys[t] = anchors.row(r)[t].x;
+            orc_argsort_i64(keys.data(), n, perm.data());
+            std::vector<Anc> srt((size_t)n);
+            for (int64_t t = 0; t < n; ++t) srt[t] = anchors.row(r)[perm[t]];
+            to_rows(srt.data(), n, rows);
+            std::vector<double> S((size_t)n);
+            std::vector<int32_t> P((size_t)n), A((size_t)n);
+            if (n > 0) {
+                int64_t g = -1;
+                const bool fast = (double)n / (double)read_len[r] > 5.0;
+                if (!fast) g = orc_chain_global_d_all(rows.data(), n, kmersize, skipcost, maxdiff, maxgap, tb, 1000, S.data(), P.data(), A.data(), nullptr);
+                if (fast || g == -1) g = orc_chain_fast(rows.data(), n, kmersize, 0, skipcost, maxdiff, maxgap, 5, tb, nullptr, S.data(), P.data(), A.data());
+                out.gmax[r] = g;
+            }
+            out.sorted.data.insert(out.sorted.data.end(), srt.begin(), srt.end());
+            out.sorted.close_row();
+            out.S.insert(out.S.end(), S.begin(), S.end());
+            out.P.insert(out.P.end(), P.begin(), P.end());
+            out.S_arg.insert(out.S_arg.end(), A.begin(), A.end());
+        }
+    }
+
+    void reseed(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                Ragged<Anc> &local) override
+    {
+        local.clear();
+        size_t q = 0;
+        for (int64_t r = 0; r < b.n; ++r) {
+            while (q < jobs.size() && jobs[q].read == r) {
+                const vmg::GuideJob &j = jobs[q].job;
+                std::string fwd(b.seq + b.off[r], (size_t)b.len(r)), rc = revcomp(fwd);
+                if (need_reverse[r]) std::swap(fwd, rc);
+                int64_t *rows = nullptr;
+                const int64_t m = orc_local_reseed(ref, j.win_lo.data(), j.win_hi.data(), (int32_t)j.win_lo.size(), j.gx.data(),
+                                                   j.gy.data(), (int64_t)j.gx.size(), fwd.c_str(), rc.c_str(), b.len(r), 9,
+                                                   j.readstart, j.readend, &rows);
+                for (int64_t t = 0; t < m; ++t)
+                    local.data.push_back(Anc{rows[t * 4], rows[t * 4 + 1], (int32_t)rows[t * 4 + 2], (int32_t)rows[t * 4 + 3]});
+                if (rows) orc_free(rows);
+                ++q;
+            }
+            local.close_row();
+        }
+    }
+
+    void chain_local(const Ragged<Anc> &anchors, const std::vector<int> &variant, const std::vector<double> &skipcost,
+                     int maxdiff, int maxgap, ChainOut &out) override
+    {
+        out = ChainOut();
+        out.gmax.assign((size_t)anchors.rows(), -1);
+        std::vector<float> lrg((size_t)maxgap + 1);
+        orc_large_readgap_table(maxgap, 30, lrg.data());
+        for (int64_t r = 0; r < anchors.rows(); ++r) {
+            const int64_t n = variant[r] ? anchors.size(r) : 0;
+            std::vector<int64_t> keys((size_t)n), perm((size_t)n), rows;
+            for (int64_t t = 0; t < n; ++t) keys[t] = anchors.row(r)[t].x + anchors.row(r)[t].l;
+            orc_argsort_i64(keys.data(), n, perm.data());
+            std::vector<Anc> srt((size_t)n);
+            for (int64_t t = 0; t < n; ++t) srt[t] = anchors.row(r)[perm[t]];
+            to_rows(srt.data(), n, rows);
+            std::vector<double> S((size_t)n);
+            std::vector<int32_t> P((size_t)n), A32((size_t)n);
+            if (n > 0) {
+                std::vector<int64_t> P64((size_t)n), A64((size_t)n);
+                const float *rg = variant[r] == 1 ? tb->readgapcost : lrg.data();
+                int64_t g = orc_chain_local(rows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, tb, rg, S.data(), P64.data(), A64.data(), nullptr);
+                if (g == -2) g = orc_chain_fast(rows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, 5, tb, rg, S.data(), P.data(), A32.data());
+                else for (int64_t t = 0; t < n; ++t) P[t] = (int32_t)P64[t];
+                out.gmax[r] = g;
+            }
+            out.sorted.data.insert(out.sorted.data.end(), srt.begin(), srt.end());
+            out.sorted.close_row();
+            out.S.insert(out.S.end(), S.begin(), S.end());
+            out.P.insert(out.P.end(), P.begin(), P.end());
+            out.S_arg.insert(out.S_arg.end(), A32.begin(), A32.end());
+        }
+    }
+
+    void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) override
+    {
+        for (EdJob &j : jobs) {
+            const std::string x = materialize(b, j.read, j.a), y = materialize(b, j.read, j.b);
+            j.dist = orc_edit_distance(x.data(), (int64_t)x.size(), y.data(), (int64_t)y.size());
+        }
+    }
+
+    void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) override
+    {
+        for (ExtJobRef &j : jobs) {
+            const std::string t = materialize(b, j.read, j.job.target), q = materialize(b, j.read, j.job.query);
+            orc_kc_result res;
+            std::vector<uint32_t> cig(t.size() + q.size() + 4);
+            orc_k_cigar(t.data(), (int32_t)t.size(), q.data(), (int32_t)q.size(), 2, -4, 4, 4, 4, 4, 100, 50, 0, cig.data(), (int32_t)cig.size(), &res);
+            j.job.q_e = res.q_e;
+            j.job.t_e = res.t_e;
+        }
+    }
+
+    void fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) override
+    {
+        for (FillJobRef &j : jobs) {
+            const std::string t = materialize(b, j.read, j.job.target), q = materialize(b, j.read, j.job.query);
+            orc_kc_result res;
+            std::vector<uint32_t> cig(t.size() + q.size() + 4);
+            orc_k_cigar(t.data(), (int32_t)t.size(), q.data(), (int32_t)q.size(), 2, -4, 4, 2, 24, 1, -1, -1, eqx ? 1 : 0, cig.data(), (int32_t)cig.size(), &res);
+            j.cigar.assign(cig.begin(), cig.begin() + res.n_cigar);
+        }
+    }
+};
+
+extern "C" {
+
+struct gt_options {
+    double global_skipcost, local_skipcost, maxdivergence, accept;
+    int32_t global_maxdiff, local_maxdiff, check_num, eqx, hardclip, nodiscard, max_guides, local_maxgap, clamp40, kmersize, threads;
+};
+
+// returns number of records; flat outputs sized by the caller (rec_cap rows of 9 int64, cigar_cap uint32)
+int64_t gt_align_batch(void *orc_index, const orc_tables *tb, const char *ref, const int64_t *ctg_start, const int64_t *ctg_len,
+                       int32_t n_ctg, const char *reads, const int64_t *read_off, int64_t n_reads, const gt_options *o,
+                       int64_t *rec_rows, int64_t rec_cap, uint32_t *cigar, int64_t cigar_cap, int64_t *n_cigar_out)
+{
+    vmg::Contigs ctg;
+    for (int c = 0; c < n_ctg; ++c) { ctg.names.push_back("c" + std::to_string(c)); ctg.start.push_back(ctg_start[c]); ctg.len.push_back(ctg_len[c]); }
+    ctg.seq = ref;
+    ctg.total = n_ctg ? ctg_start[n_ctg - 1] + ctg_len[n_ctg - 1] : 0;
+    vmg::Options opt;
+    opt.global_skipcost = o->global_skipcost; opt.local_skipcost = o->local_skipcost; opt.maxdivergence = o->maxdivergence;
+    opt.global_maxdiff = o->global_maxdiff; opt.local_maxdiff = o->local_maxdiff; opt.check_num = o->check_num;
+    opt.eqx = o->eqx; opt.hardclip = o->hardclip; opt.nodiscard = o->nodiscard;
+    opt.mode = vmg::ModeConst{o->accept, o->max_guides, o->local_maxgap, o->clamp40 != 0};
+    OracleBackend be(orc_index, tb, ref);
+    Driver drv(be, ctg, opt, o->kmersize, o->threads);
+    ReadBatch b;
+    b.n = n_reads; b.seq = reads; b.off = read_off;
+    BatchResult res;
+    drv.align_batch(b, res);
+    int64_t nrec = 0, ncig = 0;
+    for (int64_t r = 0; r < n_reads; ++r)
+        for (const vmg::Record &rec : res.records[r]) {
+            if (nrec < rec_cap && ncig + (int64_t)rec.cigar.size() <= cigar_cap) {
+                int64_t *row = rec_rows + nrec * 9;
+                row[0] = r; row[1] = rec.contig; row[2] = rec.strand; row[3] = rec.q_st; row[4] = rec.q_en;
+                row[5] = rec.r_st; row[6] = rec.r_en; row[7] = rec.mapq; row[8] = (int64_t)rec.cigar.size();
+                memcpy(cigar + ncig, rec.cigar.data(), rec.cigar.size() * 4);
+            }
+            ++nrec;
+            ncig += (int64_t)rec.cigar.size();
+        }
+    *n_cigar_out = ncig;
+    return nrec;
+}
+}

@@ -1,0 +1,387 @@
+// Batch driver of the per-read alignment pipeline (host C++17).
+//
+// Mirrors get_readmap_DP_test (mammap_clrnano.py:24023-24084) for a whole batch of reads:
+// the hot loops run as batched kernel launches behind `Backend`; everything between them is
+// the host glue of vm_glue.hpp, run in parallel over the reads of the batch.  The driver is
+// backend-agnostic so that the glue can be unit-tested on a CPU-only box with a test backend
+// (tests/gluetest); the product only ever instantiates the CUDA backend (vm_backend_cuda.cu).
+#pragma once
+#include "vm_glue.hpp"
+#include <atomic>
+#include <functional>
+#include <thread>
+
+namespace vmp {
+
+using vmg::Anc;
+using vmg::Path;
+
+template <typename T> struct Ragged {
+    std::vector<T> data;
+    std::vector<int64_t> off{0};
+    int64_t rows() const { return (int64_t)off.size() - 1; }
+    int64_t size(int64_t r) const { return off[r + 1] - off[r]; }
+    const T *row(int64_t r) const { return data.data() + off[r]; }
+    T *row(int64_t r) { return data.data() + off[r]; }
+    void clear() { data.clear(); off.assign(1, 0); }
+    void close_row() { off.push_back((int64_t)data.size()); }
+};
+
+struct ReadBatch {
+    int64_t n = 0;
+    const char *seq = nullptr;     // upper-case bases, all reads concatenated
+    const int64_t *off = nullptr;  // [n+1]
+    int64_t len(int64_t r) const { return off[r + 1] - off[r]; }
+};
+
+struct ChainOut {                  // per batch, ragged like the input anchors
+    Ragged<Anc> sorted;
+    std::vector<double> S;
+    std::vector<int32_t> P, S_arg;
+    std::vector<int64_t> gmax;     // per read
+};
+
+struct GuideJobRef { int32_t read; vmg::GuideJob job; };
+struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; };
+struct ExtJobRef { int32_t read; vmg::ExtJob job; };
+struct FillJobRef { int32_t read; vmg::FillJob job; std::vector<uint32_t> cigar; };
+
+// The hot loops.  Every method processes the jobs of a whole batch.
+struct Backend {
+    virtual ~Backend() {}
+    // minimizer seeding + cluster filter + majority-strand flip (index.map + :21202-21217)
+    virtual void seed(const ReadBatch &b, int check_num, Ragged<Anc> &anchors, std::vector<char> &need_reverse) = 0;
+    // argsort by read position + global DP (exact / fast as hit2work_1 chooses)
+    virtual void chain_global(const Ragged<Anc> &anchors, const std::vector<int64_t> &read_len, int kmersize,
+                              double skipcost, int maxdiff, int maxgap, ChainOut &out) = 0;
+    // local 9-mer re-seeding; anchors of all guide jobs of a read are concatenated in job order
+    virtual void reseed(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                        Ragged<Anc> &local /* rows = reads */) = 0;
+    // argsort by read end + local DP variant 1 / 2 (+ fast fall-back); rows with variant 0 are skipped
+    virtual void chain_local(const Ragged<Anc> &anchors, const std::vector<int> &variant,
+                             const std::vector<double> &skipcost, int maxdiff, int maxgap, ChainOut &out) = 0;
+    virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) = 0;
+    virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
+    virtual void fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
+};
+
+static inline void parallel_for(int64_t n, int threads, const std::function<void(int64_t)> &fn)
+{
+    if (threads <= 1 || n < 2) {
+        for (int64_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int64_t> next(0);
+    std::vector<std::thread> pool;
+    const int nt = (int)std::min<int64_t>(threads, n);
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&]() {
+            for (;;) {
+                const int64_t i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                const int64_t i1 = std::min(n, i0 + 16);
+                for (int64_t i = i0; i < i1; ++i) fn(i);
+            }
+        });
+    for (std::thread &t : pool) t.join();
+}
+
+struct ReadState {
+    bool alive = false;
+    bool need_reverse = false;
+    int mapq = 0;
+    std::vector<Path> guides;
+    size_t n_guides_used = 0;
+    Path asc;                       // local chain, ascending read order
+    // extend_func state
+    vmg::AlnList al;
+    size_t n0 = 0;
+    bool filtered = false;
+    bool nofilter = false;
+    bool redo = false;
+    std::vector<vmg::ExtJob> ext;
+    vmg::AlnList kept;
+    std::vector<vmg::FillJob> fills;
+    std::vector<vmg::Record> recs;
+};
+
+struct BatchResult {
+    std::vector<std::vector<vmg::Record>> records;   // per read, in the reference's emission order
+};
+
+// map the oriented sequences of the per-read driver onto the stored orientations:
+// after need_reverse the reference swaps testseq / rc_testseq (:24063-24065)
+static inline void orient(vmg::SeqRef &s, bool need_reverse)
+{
+    if (need_reverse && s.src != 0) s.src = 3 - s.src;
+}
+
+class Driver {
+public:
+    Driver(Backend &be, const vmg::Contigs &ctg, const vmg::Options &opt, int kmersize, int threads)
+        : be_(be), ctg_(ctg), opt_(opt), k_(kmersize), threads_(threads) {}
+
+    void align_batch(const ReadBatch &b, BatchResult &res)
+    {
+        const int64_t n = b.n;
+        res.records.assign((size_t)n, {});
+        std::vector<ReadState> st((size_t)n);
+        // host copies of the oriented reads are needed by fix_simple_inv only; built lazily there
+
+        // ---- 1-2. seeding + global chaining ----
+        Ragged<Anc> anchors;
+        std::vector<char> need_rev;
+        be_.seed(b, opt_.check_num, anchors, need_rev);
+        std::vector<int64_t> read_len((size_t)n);
+        for (int64_t r = 0; r < n; ++r) read_len[r] = b.len(r);
+        // decode_hit :23986 -- reads with <= 2 anchors are unmapped: drop their rows
+        Ragged<Anc> ganch;
+        for (int64_t r = 0; r < n; ++r) {
+            if (anchors.size(r) > 2) ganch.data.insert(ganch.data.end(), anchors.row(r), anchors.row(r) + anchors.size(r));
+            ganch.close_row();
+        }
+        ChainOut g;
+        be_.chain_global(ganch, read_len, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, g);
+
+        // ---- 3. hit2work bookkeeping + guide selection ----
+        std::vector<std::vector<GuideJobRef>> gjobs((size_t)n);
+        parallel_for(n, threads_, [&](int64_t r) {
+            const int64_t m = g.sorted.size(r);
+            if (m <= 2) return;
+            const int64_t o = g.sorted.off[r];
+            vmg::GlobalResult gr;
+            vmg::hit2work(g.sorted.row(r), g.S.data() + o, g.P.data() + o, g.S_arg.data() + o, m, g.gmax[r], read_len[r],
+                          opt_.mode.accept, gr);
+            if (!gr.ok) return;
+            ReadState &s = st[r];
+            s.alive = true;
+            s.need_reverse = need_rev[r] != 0;
+            s.mapq = gr.mapq;
+            s.guides.swap(gr.guides);
+            s.n_guides_used = vmg::select_guides(s.guides, opt_.mode);
+            for (size_t gi = 0; gi < s.n_guides_used; ++gi) {
+                GuideJobRef j;
+                j.read = (int32_t)r;
+                vmg::make_guide_job(s.guides[gi], read_len[r], 9, ctg_, j.job);
+                gjobs[r].push_back(std::move(j));
+            }
+        });
+        std::vector<GuideJobRef> all_gjobs;
+        for (int64_t r = 0; r < n; ++r)
+            for (GuideJobRef &j : gjobs[r]) all_gjobs.push_back(std::move(j));
+        gjobs.clear();
+
+        // ---- 4-5. local re-seeding + local chaining ----
+        Ragged<Anc> local;
+        be_.reseed(b, need_rev, all_gjobs, local);
+        std::vector<int> variant((size_t)n, 0);
+        std::vector<double> skip((size_t)n, opt_.local_skipcost);
+        for (int64_t r = 0; r < n; ++r) {
+            if (!st[r].alive) continue;
+            if (local.size(r) == 0) { st[r].alive = false; continue; }   // np.array([]) indexing raises in the reference
+            if (st[r].guides.size() > 1) {
+                variant[r] = 2;
+                if (opt_.mode.clamp40) skip[r] = std::min(skip[r], 40.0);
+            } else variant[r] = 1;
+        }
+        ChainOut lc;
+        be_.chain_local(local, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
+
+        // ---- 6. traceback, then extend_func as a staged state machine ----
+        parallel_for(n, threads_, [&](int64_t r) {
+            ReadState &s = st[r];
+            if (!s.alive) return;
+            const int64_t o = lc.sorted.off[r];
+            vmg::local_traceback(lc.sorted.row(r), lc.P.data() + o, lc.gmax[r], s.asc);
+            if (s.asc.size() <= 1) s.alive = false;
+            s.nofilter = opt_.nodiscard;
+        });
+        std::vector<int64_t> todo;
+        for (int64_t r = 0; r < n; ++r)
+            if (st[r].alive) todo.push_back(r);
+        extend_pass(b, read_len, st, todo);
+        // second pass (:24079-24080): paired large indels after a filtered sub-alignment
+        std::vector<int64_t> again;
+        for (int64_t r : todo) {
+            ReadState &s = st[r];
+            if (s.alive && !s.recs.empty() && !opt_.nodiscard && s.filtered && vmg::paired_indel(s.recs)) {
+                s.nofilter = true;
+                again.push_back(r);
+            }
+        }
+        if (!again.empty()) extend_pass(b, read_len, st, again);
+        for (int64_t r = 0; r < n; ++r)
+            if (st[r].alive) res.records[r].swap(st[r].recs);
+    }
+
+private:
+    // one extend_func call (:19238-19303) for every read in `ids`
+    void extend_pass(const ReadBatch &b, const std::vector<int64_t> &read_len, std::vector<ReadState> &st,
+                     const std::vector<int64_t> &ids)
+    {
+        const int64_t m = (int64_t)ids.size();
+        // a. rebuild_chain_break + divergence filter jobs
+        std::vector<std::vector<EdJob>> edj((size_t)m);
+        parallel_for(m, threads_, [&](int64_t t) {
+            const int64_t r = ids[t];
+            ReadState &s = st[r];
+            s.recs.clear();
+            s.filtered = false;
+            try {
+                vmg::rebuild_chain_break(ctg_, s.asc, opt_.local_maxdiff, s.al);
+                for (size_t i = 0; i < s.al.size(); ++i) {
+                    EdJob j;
+                    j.read = (int32_t)r;
+                    vmg::query_target(s.al[i].front(), s.al[i].back(), read_len[r], ctg_, j.b, j.a);
+                    if (std::min(j.a.len(), j.b.len()) == 0) throw vmg::ReadDropped("division by zero");
+                    orient(j.a, s.need_reverse);
+                    orient(j.b, s.need_reverse);
+                    edj[t].push_back(j);
+                }
+            } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); }
+        });
+        std::vector<EdJob> ed;
+        std::vector<int64_t> ed_start((size_t)m + 1, 0);
+        for (int64_t t = 0; t < m; ++t) {
+            ed_start[t] = (int64_t)ed.size();
+            ed.insert(ed.end(), edj[t].begin(), edj[t].end());
+        }
+        ed_start[m] = (int64_t)ed.size();
+        be_.edit_distance(b, ed);
+        parallel_for(m, threads_, [&](int64_t t) {
+            ReadState &s = st[ids[t]];
+            if (!s.alive) return;
+            vmg::AlnList keep;
+            for (int64_t q = ed_start[t]; q < ed_start[t + 1]; ++q) {
+                const double ratio = (double)ed[q].dist / (double)std::min(ed[q].a.len(), ed[q].b.len());
+                if (!(ratio > opt_.maxdivergence)) keep.push_back(std::move(s.al[q - ed_start[t]]));
+            }
+            s.al.swap(keep);
+        });
+        // b. edge extension, two dependency rounds
+        extend_rounds(b, read_len, st, ids);
+        // c. misplaced sub-alignments, second extension when something was dropped
+        std::vector<int64_t> changed;
+        for (int64_t t = 0; t < m; ++t) {
+            ReadState &s = st[ids[t]];
+            if (!s.alive) continue;
+            s.n0 = s.al.size();
+            if (s.al.size() > 2 && !s.nofilter) {
+                size_t iloc = 0;
+                while (iloc + 2 < s.al.size())
+                    if (!vmg::drop_misplaced(s.al, iloc)) ++iloc;
+            }
+            if (s.al.size() < s.n0) { s.filtered = true; changed.push_back(ids[t]); }
+        }
+        if (!changed.empty()) extend_rounds(b, read_len, st, changed);
+        // d. merge / inversion fix / fill jobs
+        std::vector<std::vector<FillJobRef>> fj((size_t)m);
+        parallel_for(m, threads_, [&](int64_t t) {
+            const int64_t r = ids[t];
+            ReadState &s = st[r];
+            if (!s.alive) return;
+            try {
+                vmg::merge_conjacent(s.al, ctg_);
+                if (s.al.size() > 2) {
+                    std::string oriented = oriented_read(b, r, s.need_reverse);
+                    vmg::fix_simple_inv(s.al, ctg_, oriented.data(), read_len[r]);
+                }
+                s.kept.assign(s.al.size(), Path());
+                s.fills.clear();
+                for (size_t i = 0; i < s.al.size(); ++i)
+                    vmg::split_alignment(s.al[i], (int)i, read_len[r], ctg_, s.kept[i], s.fills);
+                for (vmg::FillJob &f : s.fills) {
+                    FillJobRef j;
+                    j.read = (int32_t)r;
+                    j.job = f;
+                    orient(j.job.target, s.need_reverse);
+                    orient(j.job.query, s.need_reverse);
+                    fj[t].push_back(std::move(j));
+                }
+            } catch (const vmg::ReadDropped &) { s.alive = false; fj[t].clear(); }
+        });
+        std::vector<FillJobRef> fills;
+        std::vector<int64_t> f_start((size_t)m + 1, 0);
+        for (int64_t t = 0; t < m; ++t) {
+            f_start[t] = (int64_t)fills.size();
+            for (FillJobRef &j : fj[t]) fills.push_back(std::move(j));
+        }
+        f_start[m] = (int64_t)fills.size();
+        be_.fill(b, opt_.eqx, fills);
+        // e. records
+        parallel_for(m, threads_, [&](int64_t t) {
+            const int64_t r = ids[t];
+            ReadState &s = st[r];
+            if (!s.alive) return;
+            std::vector<std::vector<uint32_t>> cig(s.al.size());
+            for (int64_t q = f_start[t]; q < f_start[t + 1]; ++q) {
+                std::vector<uint32_t> &dst = cig[fills[q].job.aln];
+                dst.insert(dst.end(), fills[q].cigar.begin(), fills[q].cigar.end());
+            }
+            try {
+                vmg::make_records(s.kept, cig, s.mapq, read_len[r], ctg_, s.need_reverse, opt_.hardclip, s.recs);
+            } catch (const vmg::ReadDropped &) { s.alive = false; s.recs.clear(); }
+            if (s.recs.empty()) s.alive = false;
+        });
+    }
+
+    void extend_rounds(const ReadBatch &b, const std::vector<int64_t> &read_len, std::vector<ReadState> &st,
+                       const std::vector<int64_t> &ids)
+    {
+        const int64_t m = (int64_t)ids.size();
+        for (int round = 0; round < 2; ++round) {
+            parallel_for(m, threads_, [&](int64_t t) {
+                ReadState &s = st[ids[t]];
+                s.ext.clear();
+                if (!s.alive || s.al.empty()) return;
+                vmg::extend_prepare(round, read_len[ids[t]], s.al, ctg_, s.ext);
+            });
+            std::vector<ExtJobRef> jobs;
+            std::vector<int64_t> start((size_t)m + 1, 0);
+            for (int64_t t = 0; t < m; ++t) {
+                start[t] = (int64_t)jobs.size();
+                ReadState &s = st[ids[t]];
+                for (vmg::ExtJob &e : s.ext) {
+                    ExtJobRef j;
+                    j.read = (int32_t)ids[t];
+                    j.job = e;
+                    orient(j.job.target, s.need_reverse);
+                    orient(j.job.query, s.need_reverse);
+                    jobs.push_back(j);
+                }
+            }
+            start[m] = (int64_t)jobs.size();
+            if (jobs.empty()) continue;
+            be_.extend(b, jobs);
+            parallel_for(m, threads_, [&](int64_t t) {
+                ReadState &s = st[ids[t]];
+                if (!s.alive) return;
+                for (int64_t q = start[t]; q < start[t + 1]; ++q) {
+                    s.ext[q - start[t]].q_e = jobs[q].job.q_e;
+                    s.ext[q - start[t]].t_e = jobs[q].job.t_e;
+                }
+                vmg::extend_apply(s.al, s.ext);
+            });
+        }
+    }
+
+    static std::string oriented_read(const ReadBatch &b, int64_t r, bool need_reverse)
+    {
+        std::string s(b.seq + b.off[r], (size_t)b.len(r));
+        if (!need_reverse) return s;
+        std::string rc(s.size(), 'N');
+        for (size_t i = 0; i < s.size(); ++i) {
+            const char c = s[s.size() - 1 - i];
+            rc[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+        }
+        return rc;
+    }
+
+    Backend &be_;
+    const vmg::Contigs &ctg_;
+    vmg::Options opt_;
+    int k_;
+    int threads_;
+};
+
+} // namespace vmp
