@@ -110,6 +110,75 @@ int vm_chain_global_download(vm_ctx *ctx, int64_t *sorted, double *S, int32_t *P
 /* per-kernel device time of the last run (ms): [pack, sort, dp_exact, dp_fast] */
 int vm_chain_global_times(vm_ctx *ctx, float *ms4);
 
+/* ------------------------------------------------------------------------
+ * Reference index.  Replaces `vacmap_index.Aligner(path, w=, k=)` (vacmap:344; a minimap2
+ * .mmi built by `minimap2 -d`, vacmap:329-336) and its accessors `.k`, `.seq_offset`
+ * (vacmap:358-361, clrnano:24098-24102) and `.seq(name)` (vacmap:363).  Sequences are
+ * upper-cased and every non-ACGT base becomes N (what mappy's .seq() hands back).
+ * Holds, in HBM: the reference (1 B/base), the (w,k)-minimizer hash table, and the
+ * positions of every 9-mer of the reference for the local re-seeding stage.
+ * ---------------------------------------------------------------------- */
+typedef struct vm_index_handle vm_index_handle;
+
+int vm_index_create(vm_ctx *ctx, int32_t n_contigs, const char *const *names, const char *const *seqs,
+                    const int64_t *lens, int32_t w, int32_t k, vm_index_handle **out);
+void vm_index_destroy(vm_index_handle *h);
+int vm_index_info(vm_index_handle *h, int32_t *k, int32_t *w, int32_t *n_contigs, int64_t *n_minimizers,
+                  int64_t *n_keys, int32_t *mid_occ);
+/* contig i: name, global start offset (`seq_offset[i][2]`), length, pointer to its (library-owned) sequence */
+int vm_index_contig(vm_index_handle *h, int32_t i, const char **name, int64_t *start, int64_t *len, const char **seq);
+
+/* ------------------------------------------------------------------------
+ * Per-read alignment of a batch.  Replaces get_readmap_DP_test (clrnano:24023-24084) as
+ * called by the worker loop get_list_of_readmap_stdout (clrnano:24117): seeding ->
+ * global non-linear chaining -> local re-seeding + chaining -> extension -> records.
+ * Parameters are the `option` dict keys the live path reads (vacmap:257-296) plus the
+ * per-mode constants that differ between mammap_clrnano / _ccs / _sensitive.
+ * ---------------------------------------------------------------------- */
+typedef struct vm_align_params {
+    double global_skipcost;   /* option['golbal_skipcost'] */
+    double local_skipcost;    /* option['local_skipcost'] */
+    double maxdivergence;     /* option['maxdivergence'] */
+    double accept_score;      /* primary-chain threshold: 60 (H) / 40 (L, S)  (clrnano:23650) */
+    int32_t global_maxdiff;   /* option['golbal_maxdiff'] */
+    int32_t local_maxdiff;    /* option['local_maxdiff'] */
+    int32_t check_num;        /* option['c'] "Top N clusters" */
+    int32_t eqx;              /* option['eqx'] */
+    int32_t hardclip;         /* option['H'] */
+    int32_t nodiscard;        /* option['nodiscard'] */
+    int32_t max_guides;       /* 5 (H) / 3 (L) / 0 = unlimited (S)  (clrnano:28581) */
+    int32_t local_maxgap;     /* 99 (H, S) / 50 (L)  (clrnano:24061) */
+    int32_t clamp40;          /* 1 in mode L: min(skipcost, 40) in the multi-chain local DP */
+    int32_t host_threads;     /* host glue threads, 0 = all cores */
+} vm_align_params;
+
+/* One alignment record = one row of `onemapinfolist` (clrnano:20760):
+ * (readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar). */
+typedef struct vm_record {
+    int32_t contig;      /* index into the contig table */
+    int32_t strand;      /* +1 / -1 */
+    int64_t q_st, q_en;  /* query span */
+    int64_t r_st, r_en;  /* reference span, contig coordinates */
+    int32_t mapq;
+    int32_t cigar_len;   /* number of ops */
+    int64_t cigar_off;   /* into the result's CIGAR arena */
+} vm_record;
+
+typedef struct vm_result vm_result;
+
+/* seqs: upper-case bases of all reads concatenated; seq_off[n_reads+1].  The result arena is
+ * library-allocated and freed with vm_result_free.  Reads that do not map, or that the
+ * reference would drop through an exception (clrnano:24116-24125), simply have no records. */
+int vm_align_batch(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
+                   const char *seqs, const int64_t *seq_off, vm_result **out);
+int64_t vm_result_num_records(vm_result *r);
+int64_t vm_result_num_cigar_ops(vm_result *r);
+const int64_t *vm_result_read_offsets(vm_result *r);   /* [n_reads+1] into the record array */
+const vm_record *vm_result_records(vm_result *r);
+const uint32_t *vm_result_cigar(vm_result *r);         /* BAM encoding len<<4|op, ops MIDNSHP=X */
+const char *vm_result_stage_times(vm_result *r);       /* "stage=ms;..." wall milliseconds per stage */
+void vm_result_free(vm_result *r);
+
 #ifdef __cplusplus
 }
 #endif

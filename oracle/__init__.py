@@ -14,6 +14,7 @@ Parity status:
 """
 import ctypes
 import os
+import re as _re
 import subprocess
 
 import numpy as np
@@ -224,7 +225,8 @@ class Index:
         L = lib(); _declare_natives(L)
         self.w, self.k = w, k
         self.names = [n for n, _ in contigs]
-        self.seqs = [s.upper() for _, s in contigs]
+        # mappy's Aligner.seq() hands back the index's 4-bit sequence: every non-ACGT base reads as N
+        self.seqs = [_re.sub("[^ACGT]", "N", s.upper().replace("U", "T")) for _, s in contigs]
         self.offsets = np.zeros(len(contigs) + 1, np.int64)
         for i, s in enumerate(self.seqs):
             self.offsets[i + 1] = self.offsets[i] + len(s)

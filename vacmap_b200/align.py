@@ -1,0 +1,223 @@
+"""Host mirror of the reference's per-read alignment interface, over the CUDA library.
+
+``Index`` stands where the reference uses ``vacmap_index.Aligner(path, w=, k=)`` (``vacmap:344``);
+``Aligner.align_batch`` stands where the worker loop calls ``get_readmap_DP_test`` for every read
+(``mammap_clrnano.py:24117``) and returns, per read, the same ``onemapinfolist`` rows
+``(readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar)`` (``:20760``).
+"""
+import collections
+import ctypes
+import gzip
+
+import numpy as np
+
+from . import _lib
+
+OPS = "MIDNSHP=X"
+
+Record = collections.namedtuple("Record", "readid contig strand q_st q_en r_st r_en mapq cigar")
+
+
+class AlignParamsC(ctypes.Structure):
+    _fields_ = [("global_skipcost", ctypes.c_double), ("local_skipcost", ctypes.c_double),
+                ("maxdivergence", ctypes.c_double), ("accept_score", ctypes.c_double)] + \
+               [(n, ctypes.c_int32) for n in ("global_maxdiff", "local_maxdiff", "check_num", "eqx", "hardclip", "nodiscard",
+                                              "max_guides", "local_maxgap", "clamp40", "host_threads")]
+
+
+class RecordC(ctypes.Structure):
+    _fields_ = [("contig", ctypes.c_int32), ("strand", ctypes.c_int32), ("q_st", ctypes.c_int64), ("q_en", ctypes.c_int64),
+                ("r_st", ctypes.c_int64), ("r_en", ctypes.c_int64), ("mapq", ctypes.c_int32), ("cigar_len", ctypes.c_int32),
+                ("cigar_off", ctypes.c_int64)]
+
+
+RECORD_DTYPE = np.dtype([("contig", "<i4"), ("strand", "<i4"), ("q_st", "<i8"), ("q_en", "<i8"), ("r_st", "<i8"),
+                         ("r_en", "<i8"), ("mapq", "<i4"), ("cigar_len", "<i4"), ("cigar_off", "<i8")])
+
+# per-mode constants that differ between mammap_clrnano (H), mammap_ccs (L), mammap_sensitive (S)
+MODE_CONST = {"H": dict(accept=60.0, max_guides=5, local_maxgap=99, clamp40=0),
+              "L": dict(accept=40.0, max_guides=3, local_maxgap=50, clamp40=1),
+              "S": dict(accept=40.0, max_guides=0, local_maxgap=99, clamp40=0)}
+
+
+def default_option(mode="H", **over):
+    """The `pdict` the reference CLI builds (vacmap:177-296) -- note the load-bearing `golbal_` spelling."""
+    skips = {"L": (59., 40., 0.1), "H": (40., 40., 0.2)}.get(mode, (30., 30., 0.5))
+    opt = {"mode": mode, "c": 100, "eqx": False, "md": False, "cigar2cg": False, "copycomments": False, "H": False,
+           "fakecigar": False, "Q": False, "debug": False, "shortcs": True, "rg-id": "1", "local_kmersize": 9,
+           "local_skipcost": skips[0], "golbal_skipcost": skips[1], "maxdivergence": skips[2],
+           "golbal_maxdiff": 50, "local_maxdiff": 30, "markunbalancetra": mode in ("L", "H"),
+           "nodiscard": mode not in ("L", "H")}
+    opt.update(over)
+    return opt
+
+
+def read_fastx(path, read_comment=False):
+    """FASTA / FASTQ(.gz) reader with the `vacmap_index.fastx_read` tuple contract (vacmap:445)."""
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "rt") as f:
+        name, comment, seq, qual, mode = None, None, [], [], None
+        for line in f:
+            line = line.rstrip("\r\n")
+            if not line:
+                continue
+            if line[0] in ">@" and mode != "qual":
+                if name is not None:
+                    yield _rec(name, comment, seq, qual, read_comment)
+                hdr = line[1:].split(None, 1)
+                name, comment = (hdr[0] if hdr else ""), (hdr[1] if len(hdr) > 1 else None)
+                seq, qual, mode = [], [], ("fa" if line[0] == ">" else "fq")
+            elif line[0] == "+" and mode == "fq":
+                mode = "qual"
+            elif mode == "qual":
+                qual.append(line)
+                if sum(map(len, qual)) >= sum(map(len, seq)):
+                    mode = "fq_done"
+            else:
+                seq.append(line)
+        if name is not None:
+            yield _rec(name, comment, seq, qual, read_comment)
+
+
+def _rec(name, comment, seq, qual, read_comment):
+    s = "".join(seq)
+    q = "".join(qual) if qual else None
+    return (name, s, q, comment) if read_comment else (name, s, q)
+
+
+def _declare(L):
+    if getattr(L, "_align_declared", False):
+        return
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_index_create.argtypes = [vp, i32, vp, vp, vp, i32, i32, ctypes.POINTER(vp)]
+    L.vm_index_destroy.argtypes = [vp]
+    L.vm_index_destroy.restype = None
+    L.vm_index_info.argtypes = [vp] + [vp] * 6
+    L.vm_index_contig.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.vm_align_batch.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
+    for f in ("vm_result_num_records", "vm_result_num_cigar_ops"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = i64
+    for f in ("vm_result_read_offsets", "vm_result_records", "vm_result_cigar"):
+        getattr(L, f).argtypes = [vp]
+        getattr(L, f).restype = vp
+    L.vm_result_stage_times.argtypes = [vp]
+    L.vm_result_stage_times.restype = ctypes.c_char_p
+    L.vm_result_free.argtypes = [vp]
+    L.vm_result_free.restype = None
+    L._align_declared = True
+
+
+class Index:
+    """Reference index resident on one GPU: `.k`, `.w`, `.seq_offset`, `.seq(name)` as the reference uses them."""
+
+    def __init__(self, ref, w=10, k=15, ctx=None, device=0):
+        """ref: path to a FASTA(.gz) or a list of (name, sequence)."""
+        L = _lib.load()
+        _declare(L)
+        self.ctx = ctx or _lib.default_context(device)
+        contigs = [(n, s) for n, s, _ in read_fastx(ref)] if isinstance(ref, (str, bytes)) else list(ref)
+        self.k, self.w = int(k), int(w)
+        self.names = [n for n, _ in contigs]
+        enc = [s.encode() if isinstance(s, str) else bytes(s) for _, s in contigs]
+        n = len(contigs)
+        names_c = (ctypes.c_char_p * n)(*[x.encode() for x in self.names])
+        seqs_c = (ctypes.c_char_p * n)(*enc)
+        lens = np.array([len(e) for e in enc], dtype=np.int64)
+        h = ctypes.c_void_p()
+        _lib.check(self.ctx.h, L.vm_index_create(self.ctx.h, n, names_c, seqs_c, _lib.ptr(lens), self.w, self.k,
+                                                 ctypes.byref(h)))
+        self.h = h
+        self.lens = lens
+        self.starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        info = [ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()]
+        L.vm_index_info(self.h, *[ctypes.byref(x) for x in info])
+        self.n_minimizers, self.n_keys, self.mid_occ = info[3].value, info[4].value, info[5].value
+
+    @property
+    def seq_offset(self):
+        return [(n.encode(), int(l), int(s)) for n, l, s in zip(self.names, self.lens, self.starts)]
+
+    def seq(self, name, start=0, end=0x7fffffff):
+        i = self.names.index(name)
+        p, ln = ctypes.c_char_p(), ctypes.c_int64()
+        _lib.load().vm_index_contig(self.h, i, None, None, ctypes.byref(ln), ctypes.byref(p))
+        return ctypes.string_at(p, ln.value).decode()[start:end]
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.load().vm_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Aligner:
+    """Batch form of the reference worker loop: reads in, `onemapinfolist` per read out."""
+
+    def __init__(self, index, option=None, mode="H", host_threads=0):
+        self.index = index
+        self.mode = mode
+        self.option = option or default_option(mode)
+        mc = MODE_CONST[mode]
+        o = self.option
+        self.params = AlignParamsC(o["golbal_skipcost"], o["local_skipcost"], o["maxdivergence"], mc["accept"],
+                                   o["golbal_maxdiff"], o["local_maxdiff"], o["c"], int(o["eqx"]), int(o["H"]),
+                                   int(o["nodiscard"]), mc["max_guides"], mc["local_maxgap"], mc["clamp40"], host_threads)
+        self.last_stage_ms = {}
+
+    def align_packed(self, seq_cat, seq_off):
+        """seq_cat: bytes of all (upper-case) reads; seq_off int64[n+1].
+        -> (rec_off int64[n+1], records structured array, cigar uint32 array)."""
+        L = _lib.load()
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        n = len(seq_off) - 1
+        res = ctypes.c_void_p()
+        ctx = self.index.ctx
+        buf = (ctypes.c_char * len(seq_cat)).from_buffer_copy(seq_cat) if not isinstance(seq_cat, bytes) else seq_cat
+        _lib.check(ctx.h, L.vm_align_batch(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off),
+                                           ctypes.byref(res)))
+        try:
+            nrec, nops = L.vm_result_num_records(res), L.vm_result_num_cigar_ops(res)
+            off = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_offsets(res), ctypes.POINTER(ctypes.c_int64)),
+                                        shape=(n + 1,)).copy()
+            if nrec:
+                raw = ctypes.string_at(L.vm_result_records(res), nrec * RECORD_DTYPE.itemsize)
+                recs = np.frombuffer(raw, dtype=RECORD_DTYPE).copy()
+            else:
+                recs = np.zeros(0, dtype=RECORD_DTYPE)
+            if nops:
+                cig = np.ctypeslib.as_array(ctypes.cast(L.vm_result_cigar(res), ctypes.POINTER(ctypes.c_uint32)),
+                                            shape=(nops,)).copy()
+            else:
+                cig = np.zeros(0, dtype=np.uint32)
+            txt = (L.vm_result_stage_times(res) or b"").decode()
+            self.last_stage_ms = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in txt.split(";") if "=" in kv}
+        finally:
+            L.vm_result_free(res)
+        return off, recs, cig
+
+    def align_batch(self, reads):
+        """reads: list of (readid, sequence).  -> list (per read) of lists of Record."""
+        enc = [s.upper().encode() for _, s in reads]
+        off = np.zeros(len(reads) + 1, dtype=np.int64)
+        for i, e in enumerate(enc):
+            off[i + 1] = off[i] + len(e)
+        rec_off, recs, cig = self.align_packed(b"".join(enc), off)
+        out = []
+        for i, (rid, _) in enumerate(reads):
+            rows = []
+            for r in recs[rec_off[i]:rec_off[i + 1]]:
+                ops = cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]]
+                rows.append(Record(rid, self.index.names[r["contig"]], "+" if r["strand"] == 1 else "-", int(r["q_st"]),
+                                   int(r["q_en"]), int(r["r_st"]), int(r["r_en"]), int(r["mapq"]), cigar_string(ops)))
+            out.append(rows)
+        return out
+
+
+def cigar_string(ops):
+    return "".join("%d%s" % (int(o) >> 4, OPS[int(o) & 0xf]) for o in ops)

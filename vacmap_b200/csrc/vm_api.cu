@@ -8,7 +8,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 1; }
+int vm_abi_version(void) { return 2; }
 
 int vm_ctx_create(int device, vm_ctx **out)
 {

@@ -1,0 +1,147 @@
+// Reference index: minimizer hash table (global seeding) and 9-mer position index (local
+// re-seeding), built on the host, resident in HBM.
+//
+// Replaces what the reference gets from `vacmap_index.Aligner(path, w, k)` (vacmap:344; a
+// minimap2 .mmi built by `minimap2 -d`, vacmap:329-336) and, for the local stage, the per-read
+// numba Dict of all 9-mers of the guide windows (mammap_clrnano.py:23073-23087, 23138-23140):
+// on a 180 GB part the 9-mer positions of the WHOLE reference fit in HBM (4 B per base), so the
+// per-read table build disappears and a window lookup becomes a range query in a sorted list.
+#pragma once
+#include "vm_common.cuh"
+#include <string>
+#include <vector>
+
+#define VM_HT_EMPTY 0xffffffffffffffffULL
+#define VM_K9 9
+#define VM_K9_KEYS 1953125   // 5^9
+
+struct VmHtSlot {
+    uint64_t key;     // minimizer hash (VM_HT_EMPTY = free)
+    uint32_t start;   // offset into occ
+    uint32_t count;
+};
+
+struct VmIndexDev {           // device pointers, passed to kernels by value
+    const VmHtSlot *ht;
+    uint64_t ht_mask;
+    const uint64_t *occ;      // global last-base position << 1 | strand, ascending per key
+    const uint32_t *kpos;     // 9-mer start positions (global), sorted by (code, position)
+    const int64_t *koff;      // VM_K9_KEYS + 1 offsets into kpos
+    const uint8_t *ref;       // concatenated upper-case reference
+    int64_t ref_len;
+    int32_t w, k;
+    int32_t mid_occ;
+};
+
+struct VmIndex {
+    int w = 10, k = 15;
+    int mid_occ_default = 10;
+    std::vector<std::string> names;
+    std::vector<int64_t> ctg_start, ctg_len;
+    std::string ref;                       // host copy (upper-case, non-ACGT -> N)
+    std::vector<VmHtSlot> ht;
+    std::vector<uint64_t> occ;
+    std::vector<uint32_t> kpos;
+    std::vector<int64_t> koff;
+    int64_t n_keys = 0;
+    // device copies
+    void *d_ht = nullptr, *d_occ = nullptr, *d_kpos = nullptr, *d_koff = nullptr, *d_ref = nullptr;
+    VmIndexDev dev{};
+};
+
+// base -> 0..3 (ACGT/U, either case), 4 otherwise (minimap2 seq_nt4_table)
+__host__ __device__ __forceinline__ int vm_nt4(unsigned char c)
+{
+    switch (c) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': case 'U': case 'u': return 3;
+    default: return 4;
+    }
+}
+
+// minimap2 sketch.c hash64 (invertible integer hash)
+__host__ __device__ __forceinline__ uint64_t vm_hash64(uint64_t key, uint64_t mask)
+{
+    key = (~key + (key << 21)) & mask;
+    key = key ^ key >> 24;
+    key = ((key + (key << 3)) + (key << 8)) & mask;
+    key = key ^ key >> 14;
+    key = ((key + (key << 2)) + (key << 4)) & mask;
+    key = key ^ key >> 28;
+    key = (key + (key << 31)) & mask;
+    return key;
+}
+
+__host__ __device__ __forceinline__ uint64_t vm_ht_hash(uint64_t key)
+{
+    key *= 0x9E3779B97F4A7C15ULL;
+    return key ^ (key >> 29);
+}
+
+// (w,k)-minimizer sketch of one sequence, minimap2 2.29 `mm_sketch` (non-HPC) semantics:
+// every k-mer tying the window minimum is emitted, symmetric k-mers are skipped without
+// occupying a window slot, an ambiguous base resets the run length but not the k-mer registers.
+// emit(hash, last_base_pos << 1 | strand) is called in position order.  One caller = one
+// sequential state machine (host: per contig; device: one thread per read).
+template <typename Emit>
+__host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len, int w, int k, Emit emit)
+{
+    const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
+    uint64_t kmer0 = 0, kmer1 = 0;
+    uint64_t bufx[256], bufy[256];
+    uint64_t minx = ~0ULL, miny = ~0ULL;
+    int l = 0, buf_pos = 0, min_pos = 0, kmer_span = 0;
+    for (int j = 0; j < w; ++j) { bufx[j] = ~0ULL; bufy[j] = ~0ULL; }
+    for (int64_t i = 0; i < len; ++i) {
+        const int c = vm_nt4(str[i]);
+        uint64_t infox = ~0ULL, infoy = ~0ULL;
+        if (c < 4) {
+            kmer_span = l + 1 < k ? l + 1 : k;
+            kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
+            kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
+            if (kmer0 == kmer1) continue;
+            const int z = kmer0 < kmer1 ? 0 : 1;
+            ++l;
+            if (l >= k && kmer_span < 256) {
+                infox = vm_hash64(z ? kmer1 : kmer0, mask) << 8 | (uint64_t)kmer_span;
+                infoy = (uint64_t)i << 1 | (uint64_t)z;
+            }
+        } else { l = 0; kmer_span = 0; }
+        bufx[buf_pos] = infox;
+        bufy[buf_pos] = infoy;
+        if (l == w + k - 1 && minx != ~0ULL) {
+            for (int j = buf_pos + 1; j < w; ++j)
+                if (minx == bufx[j] && bufy[j] != miny) emit(bufx[j] >> 8, bufy[j]);
+            for (int j = 0; j < buf_pos; ++j)
+                if (minx == bufx[j] && bufy[j] != miny) emit(bufx[j] >> 8, bufy[j]);
+        }
+        if (infox <= minx) {
+            if (l >= w + k && minx != ~0ULL) emit(minx >> 8, miny);
+            minx = infox; miny = infoy; min_pos = buf_pos;
+        } else if (buf_pos == min_pos) {
+            if (l >= w + k - 1 && minx != ~0ULL) emit(minx >> 8, miny);
+            minx = ~0ULL;
+            for (int j = buf_pos + 1; j < w; ++j)
+                if (minx >= bufx[j]) { minx = bufx[j]; miny = bufy[j]; min_pos = j; }
+            for (int j = 0; j <= buf_pos; ++j)
+                if (minx >= bufx[j]) { minx = bufx[j]; miny = bufy[j]; min_pos = j; }
+            if (l >= w + k - 1 && minx != ~0ULL) {
+                for (int j = buf_pos + 1; j < w; ++j)
+                    if (minx == bufx[j] && miny != bufy[j]) emit(bufx[j] >> 8, bufy[j]);
+                for (int j = 0; j <= buf_pos; ++j)
+                    if (minx == bufx[j] && miny != bufy[j]) emit(bufx[j] >> 8, bufy[j]);
+            }
+        }
+        if (++buf_pos == w) buf_pos = 0;
+    }
+    if (minx != ~0ULL) emit(minx >> 8, miny);
+}
+
+// 9-mer code over the 5-letter alphabet ACGTN (anything else reads as N)
+__host__ __device__ __forceinline__ int vm_code5(unsigned char c) { return vm_nt4(c); }
+
+VmIndex *vm_index_build_host(const std::vector<std::string> &names, const std::vector<std::string> &seqs, int w, int k);
+int vm_index_upload(VmIndex *ix, std::string &err);
+void vm_index_free(VmIndex *ix);

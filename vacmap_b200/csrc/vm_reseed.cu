@@ -1,0 +1,248 @@
+// Local 9-mer re-seeding on the GPU.
+//
+// Replaces get_localmap_multi_all_forDP_inv_guide_1 (mammap_clrnano.py:23069-23345) from the
+// point where the reference windows are known (window construction is host glue).  The
+// reference builds a per-read hash table of every 9-mer of the windows and probes it with every
+// read position; here the 9-mer positions of the WHOLE reference sit in HBM sorted by
+// (code, position) (vm_index.cuh), so a probe is a range query: lower_bound(window start) in
+// the code's position run, then walk while inside the window -- the same occurrences, in the
+// same (window, ascending position) order the reference inserted them, duplicates from
+// overlapping windows included.
+//
+//   kernel 1 (vm_reseed_hits_kernel): one block per guide job; each thread owns one read
+//     position per chunk, applies the guide-proximity filter (:23216-23231) and writes its hits
+//     at an offset obtained from a block scan, so hits are ordered exactly like the reference's
+//     scan: (read position, forward before reverse, window, reference position).  HBM-bound
+//     gather: 2 strands x (2 offsets + ~log2(run) probes) per read position.
+//   kernel 2 (vm_reseed_merge_kernel): one warp per job (lane 0 works); replays the
+//     same-diagonal merge (:23235-23252, 23294-23312) over the ordered hits with the diagonal
+//     table (`pointdict`) in global memory, emitting anchors in the reference's order.
+#include "vm_reseed.cuh"
+
+struct VmHit {
+    int32_t iloc_s;    // iloc << 1 | (strand == -1)
+    uint32_t refloc;
+};
+
+__device__ __forceinline__ int vm_kmer_code(const uint8_t *s)
+{
+    int code = 0;
+#pragma unroll
+    for (int i = 0; i < VM_K9; ++i) code = code * 5 + vm_code5(s[i]);
+    return code;
+}
+
+// findClosest_1 :17560-17581
+__device__ __forceinline__ void vm_find_closest(const int32_t *arr, int n, int target, int &b0, int &b1, int &i0, int &i1)
+{
+    if (target <= arr[0]) { b0 = b1 = arr[0] - target; i0 = i1 = 0; return; }
+    if (target >= arr[n - 1]) { b0 = b1 = target - arr[n - 1]; i0 = i1 = n - 1; return; }
+    int i = 0, j = n;
+    while (i < j) {
+        const int mid = (i + j) >> 1;
+        const int v = arr[mid];
+        if (v == target) { b0 = b1 = 0; i0 = i1 = mid; return; }
+        if (target < v) j = mid; else i = mid + 1;
+    }
+    b0 = abs(arr[j - 1] - target);
+    b1 = abs(arr[j] - target);
+    i0 = j - 1;
+    i1 = j;
+}
+
+// visit every accepted (refloc) of one k-mer code for one read position, in reference order
+template <typename F>
+__device__ __forceinline__ void vm_probe(const VmIndexDev &ix, int code, const int64_t *win_lo, const int64_t *win_hi, int n_win,
+                                         long long rgap, long long r1, long long r2, long long interval, F visit)
+{
+    const int64_t b = ix.koff[code], e = ix.koff[code + 1];
+    if (b == e) return;
+    for (int w = 0; w < n_win; ++w) {
+        const long long lo = win_lo[w], hi = win_hi[w] - VM_K9;   // k-mer start must be <= hi
+        int64_t l = b, h = e;
+        while (l < h) {                       // lower_bound(lo)
+            const int64_t mid = (l + h) >> 1;
+            if ((long long)ix.kpos[mid] < lo) l = mid + 1; else h = mid;
+        }
+        for (; l < e; ++l) {
+            const long long refloc = ix.kpos[l];
+            if (refloc > hi) break;
+            long long d = refloc - r1;
+            if (d < 0) d = -d;
+            long long diff = rgap - d;
+            if (diff < 0) diff = -diff;
+            if (diff < 500 || (r1 + interval >= refloc && r1 - interval <= refloc) ||
+                (r2 + interval >= refloc && r2 - interval <= refloc))
+                visit((uint32_t)refloc);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) vm_reseed_hits_kernel(VmIndexDev ix, const VmReseedJobDev *__restrict__ jobs,
+                                                             const uint8_t *__restrict__ reads_fwd,
+                                                             const uint8_t *__restrict__ reads_rc,
+                                                             const int64_t *__restrict__ read_off,
+                                                             const int64_t *__restrict__ win_lo_all,
+                                                             const int64_t *__restrict__ win_hi_all,
+                                                             const int32_t *__restrict__ gx_all, const int64_t *__restrict__ gy_all,
+                                                             VmHit *__restrict__ hits_all, int32_t *__restrict__ n_hits,
+                                                             int32_t *__restrict__ overflow)
+{
+    __shared__ int s_scan[256];
+    const VmReseedJobDev J = jobs[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int64_t rbase = read_off[J.read];
+    const int L = (int)(read_off[J.read + 1] - rbase);
+    const uint8_t *seq = (J.need_reverse ? reads_rc : reads_fwd) + rbase;     // oriented testseq
+    const uint8_t *rcs = (J.need_reverse ? reads_fwd : reads_rc) + rbase;     // oriented rc_testseq
+    const int64_t *win_lo = win_lo_all + J.win_off, *win_hi = win_hi_all + J.win_off;
+    const int32_t *gx = gx_all + J.g_off;
+    const int64_t *gy = gy_all + J.g_off;
+    VmHit *hits = hits_all + J.hit_off;
+    int running = 0;
+    bool over = false;
+    for (int i0 = J.readstart; i0 < J.readend; i0 += blockDim.x) {
+        const int iloc = i0 + tid;
+        int cnt = 0;
+        int fcode = -1, rcode = -1;
+        long long rgap = 0, r1 = 0, r2 = 0, interval = 0;
+        if (iloc < J.readend) {
+            fcode = vm_kmer_code(seq + iloc);
+            const bool have_rev = iloc != 0;                      // rc[-(0+k):-0] == '' (:23212)
+            if (have_rev) rcode = vm_kmer_code(rcs + (L - iloc - VM_K9));
+            if (have_rev && fcode == rcode) { fcode = -1; rcode = -1; }   // palindrome: skip the position
+            else {
+                int b0, b1, c0, c1;
+                vm_find_closest(gx, J.n_guide, iloc, b0, b1, c0, c1);
+                interval = b0 + b1 + 500;
+                if (interval > 2000) interval = 2000;
+                r1 = gy[c0];
+                r2 = gy[c1];
+                rgap = iloc - gx[c0];
+                if (rgap < 0) rgap = -rgap;
+                if (fcode >= 0) vm_probe(ix, fcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t) { ++cnt; });
+                if (rcode >= 0) vm_probe(ix, rcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t) { ++cnt; });
+            }
+        }
+        s_scan[tid] = cnt;
+        __syncthreads();
+        for (int d = 1; d < 256; d <<= 1) {
+            const int t = tid >= d ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += t;
+            __syncthreads();
+        }
+        int o = running + s_scan[tid] - cnt;
+        const int total = s_scan[255];
+        __syncthreads();
+        if (cnt > 0 && !J.count_only) {
+            if (o + cnt > J.hit_cap) over = true;
+            else {
+                if (fcode >= 0)
+                    vm_probe(ix, fcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval,
+                             [&](uint32_t refloc) { hits[o].iloc_s = iloc << 1; hits[o].refloc = refloc; ++o; });
+                if (rcode >= 0)
+                    vm_probe(ix, rcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval,
+                             [&](uint32_t refloc) { hits[o].iloc_s = iloc << 1 | 1; hits[o].refloc = refloc; ++o; });
+            }
+        }
+        running += total;
+    }
+    if (over) atomicExch(overflow, 1);
+    if (tid == 0) n_hits[blockIdx.x] = running;
+}
+
+struct VmPoint {
+    long long key;
+    int c0;
+    unsigned c1;
+    int c2;
+    int c3;
+};
+#define VM_PT_EMPTY 0x7fffffffffffffffLL
+
+__global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDev *__restrict__ jobs,
+                                                             const VmHit *__restrict__ hits_all,
+                                                             const int32_t *__restrict__ n_hits,
+                                                             VmPoint *__restrict__ table_all, int32_t *__restrict__ order_all,
+                                                             VmAnchor *__restrict__ out_all, int32_t *__restrict__ n_out)
+{
+    const VmReseedJobDev J = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const int n = n_hits[blockIdx.x];
+    if (n > J.hit_cap) { if (lane == 0) n_out[blockIdx.x] = 0; return; }
+    const VmHit *hits = hits_all + J.hit_off;
+    VmPoint *tab = table_all + J.tab_off;
+    const int tmask = J.tab_size - 1;
+    int32_t *order = order_all + J.hit_off;
+    VmAnchor *out = out_all + 2 * J.hit_off;
+    // clear the diagonal table with all lanes
+    for (int t = lane; t < J.tab_size; t += 32) tab[t].key = VM_PT_EMPTY;
+    __syncwarp();
+    if (lane != 0) return;
+    int n_pts = 0, m = 0;
+    const int k = VM_K9;
+    for (int q = 0; q < n; ++q) {
+        const VmHit hit = hits[q];
+        const int iloc = hit.iloc_s >> 1;
+        const int strand = (hit.iloc_s & 1) ? -1 : 1;
+        const long long refloc = hit.refloc;
+        const long long point = strand == 1 ? refloc - iloc : -(refloc + iloc);
+        unsigned long long h = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
+        int s = (int)((h ^ (h >> 31)) & (unsigned long long)tmask);
+        while (tab[s].key != VM_PT_EMPTY && tab[s].key != point) s = (s + 1) & tmask;
+        VmPoint p = tab[s];
+        if (p.key == VM_PT_EMPTY) {
+            p.key = point; p.c0 = iloc; p.c1 = (unsigned)refloc; p.c2 = strand; p.c3 = k;
+            tab[s] = p;
+            order[n_pts++] = s;
+        } else if (p.c0 + p.c3 >= iloc) {
+            const int bonus = iloc - (p.c0 + p.c3) + k;
+            if (bonus > 0) {
+                if (p.c3 + bonus < 20) {
+                    if (strand == 1) { p.c2 = 1; p.c3 += bonus; }
+                    else { p.c1 = (unsigned)refloc; p.c2 = -1; p.c3 += bonus; }
+                } else {
+                    VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
+                    out[m++] = a;
+                    if (strand == 1) { const int c3 = p.c3; p.c0 += c3; p.c1 += (unsigned)c3; p.c2 = 1; p.c3 = bonus; }
+                    else { p.c0 += p.c3; p.c1 = (unsigned)refloc; p.c2 = -1; p.c3 = bonus; }
+                }
+                tab[s] = p;
+            }
+        } else {
+            VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
+            out[m++] = a;
+            p.c0 = iloc; p.c1 = (unsigned)refloc; p.c2 = strand; p.c3 = k;
+            tab[s] = p;
+        }
+    }
+    for (int q = 0; q < n_pts; ++q) {
+        const VmPoint p = tab[order[q]];
+        VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
+        out[m++] = a;
+    }
+    n_out[blockIdx.x] = m;
+}
+
+int vm_reseed_launch(const VmIndexDev &ix, const VmReseedJobDev *jobs_dev, int n_jobs, const uint8_t *reads_fwd,
+                     const uint8_t *reads_rc, const int64_t *read_off, const int64_t *win_lo, const int64_t *win_hi,
+                     const int32_t *gx, const int64_t *gy, void *hits, int32_t *n_hits, int32_t *overflow, void *table,
+                     int32_t *order, VmAnchor *out, int32_t *n_out, cudaStream_t stream)
+{
+    if (n_jobs <= 0) return 0;
+    vm_reseed_hits_kernel<<<n_jobs, 256, 0, stream>>>(ix, jobs_dev, reads_fwd, reads_rc, read_off, win_lo, win_hi, gx, gy,
+                                                      (VmHit *)hits, n_hits, overflow);
+    return 1;
+}
+
+int vm_reseed_merge_launch(const VmReseedJobDev *jobs_dev, int n_jobs, const void *hits, const int32_t *n_hits, void *table,
+                           int32_t *order, VmAnchor *out, int32_t *n_out, cudaStream_t stream)
+{
+    if (n_jobs <= 0) return 0;
+    vm_reseed_merge_kernel<<<n_jobs, 32, 0, stream>>>(jobs_dev, (const VmHit *)hits, n_hits, (VmPoint *)table, order, out, n_out);
+    return 1;
+}
+
+size_t vm_reseed_hit_bytes() { return sizeof(VmHit); }
+size_t vm_reseed_point_bytes() { return sizeof(VmPoint); }
