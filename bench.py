@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""bench.py -- aligned Gbp/s of the vacmap_b200 hot path on N B200s (one process per GPU).
+"""bench.py -- aligned Gbp/s of the vacmap_b200 per-read alignment path on N B200s.
 
-Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
-prints ONE JSON line on rank 0.  `--impl reference` times the CPU oracle port of the
-same path on the box's host cores (the reference itself is Python+numba over an
-un-vendored C extension and cannot be built here).
+Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N > 1, one rank
+per GPU) prints ONE JSON line on rank 0.  A step = one pass of the whole hot path (seeding ->
+global chaining -> local re-seeding + chaining -> extension -> records) over one batch of
+synthetic reads per GPU.  `--impl reference` times the CPU oracle port of the same path on
+the host cores (the reference is Python + numba over an un-vendored C extension that cannot
+be built here).
 """
 import argparse
 import json
@@ -20,13 +22,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+READ_LEN = 15000
+ERR = 0.10
+REF_LEN = 5_000_000
+WORKLOAD = "10k synthetic ONT reads (15 kb, 10% err) vs 5 Mb reference, -mode H, 1xB200 (BASELINE configs[1])"
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -41,10 +47,9 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
@@ -55,145 +60,134 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in self.rows if len(r) >= 9 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in self.rows if len(r) >= 9 and num(r[2]) is not None]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
+                for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def make_workload(n_reads, rank=0):
+    """BASELINE configs[1]: i.i.d. 5 Mb reference with 5 % diverged repeats (seed 1); 15 kb reads with
+    10 % i.i.d. errors (sub:ins:del 4:3:3), seed 11 + rank."""
+    import synth
+    ref = synth.make_reference(1, REF_LEN)
+    reads = synth.make_reads(ref, 11 + rank, n_reads, read_len=READ_LEN, err=ERR)
+    enc = [s.encode() for _, s in reads]
+    off = np.zeros(n_reads + 1, dtype=np.int64)
+    for i, e in enumerate(enc):
+        off[i + 1] = off[i] + len(e)
+    return ref, reads, b"".join(enc), off
+
+
 # ---------------------------------------------------------------------------
-# workload: BASELINE.json configs[1] -- 10k synthetic ONT reads (15 kb, 10 % error), mode H
+# CPU arm: the oracle port of the whole path, one process per core
 # ---------------------------------------------------------------------------
-class ChainGlobalWorkload:
-    """Stage currently wired into the timed region: anchor sort + global non-linear chaining.
-
-    The anchor sets are what minimizer seeding yields for 15 kb / 10 %-error reads
-    (k=15, w=10: ~0.5-0.7k true anchors + repeat/noise hits), generated with
-    tests/synth.py (seeded).
-    """
-    name = "10k synthetic ONT reads (15 kb, 10% err) vs 5 Mb reference, -mode H [stage: global chaining]"
-    read_len = 15000
-
-    def __init__(self, n_reads=10000, seed=1, rank=0):
-        import synth
-        rng = np.random.default_rng(seed * 1000 + rank)
-        distinct = min(n_reads, 500)
-        base = [synth.anchors_global(rng, L=self.read_len, n_true=int(rng.integers(450, 650)),
-                                     n_noise=int(rng.integers(100, 1500))) for _ in range(distinct)]
-        self.anchor_list = []
-        for i in range(n_reads):
-            a = base[i % distinct].copy()
-            a[:, 1] = (a[:, 1] + 7919 * (i // distinct)) % 5_000_000
-            self.anchor_list.append(a)
-        self.n_reads = n_reads
-        self.read_lens = np.full(n_reads, self.read_len, dtype=np.int32)
-        self.off = np.zeros(n_reads + 1, dtype=np.int64)
-        for i, a in enumerate(self.anchor_list):
-            self.off[i + 1] = self.off[i] + len(a)
-        self.rows = np.ascontiguousarray(np.concatenate(self.anchor_list))
-        self.total_anchors = int(self.off[-1])
-        self.bases = int(self.read_lens.sum())
-
-    # algorithmic bytes of the chaining kernel: 16 B anchor in + 8 B S + 4 B P out per anchor (SURVEY 8d)
-    def chain_bytes(self):
-        return 28 * self.total_anchors
-
-    def h2d_bytes(self):
-        return self.rows.nbytes + self.off.nbytes
-
-    def d2h_bytes(self):
-        return self.total_anchors * (32 + 8 + 4 + 4) + self.n_reads * 8
+_CPU = {}
 
 
-def cpu_chain_worker(args):
-    """Oracle port of hit2work_1's sort + DP for a slice of reads (one process)."""
+def _cpu_init(ref):
     import oracle
-    anchor_list, L = args
-    t0 = time.perf_counter()
-    for a in anchor_list:
-        srt = a[oracle.argsort_i64(a[:, 0])]
-        if len(a) / L > 5:
-            oracle.chain_fast(srt, 15, 0, 40.0, 50, 1000)
-        else:
-            g = oracle.chain_global_d_all(srt, 15, 40.0, 50, 1000)[0]
-            if g == -1:
-                oracle.chain_fast(srt, 15, 0, 40.0, 50, 1000)
-    return time.perf_counter() - t0
+    import oracle.pipeline as pl
+    oracle.tables()
+    _CPU["ix"] = oracle.Index(ref, w=10, k=15)
+    _CPU["ctg"] = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
 
 
-def cpu_baseline(wl, sample_reads, cores):
+def _cpu_work(chunk):
+    import oracle.pipeline as pl
+    import vacmap_b200.align as va
+    opt = va.default_option("H")
+    bases = 0
+    for rid, seq in chunk:
+        if pl.align_read(rid, seq, _CPU["ix"], _CPU["ctg"], opt, "H"):
+            bases += len(seq)
+    return bases
+
+
+def cpu_baseline(ref, reads, cores):
+    """Aligned Gbp/s of the oracle pipeline over `reads` with `cores` processes (index build excluded)."""
     import multiprocessing as mp
-    import oracle
-    oracle.lib()
-    oracle.tables()   # built once, inherited by the forked workers
-    sample = wl.anchor_list[:sample_reads]
-    chunks = [sample[i::cores] for i in range(cores)]
+    chunks = [reads[i::cores] for i in range(cores)]
     chunks = [c for c in chunks if c]
+    _cpu_init(ref)                       # built once, inherited by the forked workers
     t0 = time.perf_counter()
-    if cores == 1:
-        cpu_chain_worker((chunks[0], wl.read_len))
+    if len(chunks) == 1:
+        bases = _cpu_work(chunks[0])
     else:
         with mp.get_context("fork").Pool(len(chunks)) as pool:
-            pool.map(cpu_chain_worker, [(c, wl.read_len) for c in chunks])
+            bases = sum(pool.map(_cpu_work, chunks))
     dt = time.perf_counter() - t0
-    bases = len(sample) * wl.read_len
     return bases / dt / 1e9, dt
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
-    wl = ChainGlobalWorkload(n_reads=args.reads, seed=1)
-    sample = min(wl.n_reads, args.cpu_sample)
-    for _ in range(args.warmup):
-        cpu_baseline(wl, min(sample, 200), cores)
-    vals = []
-    t_all = 0.0
+    sample = min(args.reads, args.cpu_sample)
+    ref, reads, _, _ = make_workload(sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(ref, reads[:cores], cores)
+    vals, t_all = [], 0.0
     for _ in range(args.steps):
-        v, dt = cpu_baseline(wl, sample, cores)
+        v, dt = cpu_baseline(ref, reads, cores)
         vals.append(v)
         t_all += dt
     v = float(np.mean(vals))
-    line = {"impl": "reference", "metric": "aligned_gbp_per_s", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl.name, "reads_per_step": sample, "read_len": wl.read_len},
-            "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
-                             "sample": "%d reads of the workload per step, oracle C port, %d processes" % (sample, cores)},
-            "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps({
+        "impl": "reference", "metric": "aligned_gbp_per_s", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_step": sample, "read_len": READ_LEN, "err": ERR, "ref_len": REF_LEN},
+        "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
+                         "sample": "%d reads of the workload per step; oracle port (C stages + Python glue), %d processes"
+                                   % (sample, cores)},
+        "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+KERNEL_BYTES_NOTE = {
+    "k_fill": "B = sum(q+t) sequence bytes + q*t direction bytes (traceback matrix exceeds SMEM) per fill segment",
+    "k_edit_distance": "B = sum(q+t) sequence bytes (bit-vector state stays in registers/SMEM)",
+    "k_reseed_hits": "B = read bytes x2 strands + 8 B per hit written (x2 launches: count + fill)",
+    "k_reseed_merge": "B = 8 B per hit read + 16 B per anchor out",
+    "chain_local_kernels": "B = 28 B per anchor (16 in + 8 S + 4 P)",
+    "chain_global_kernels": "B = 28 B per anchor (16 in + 8 S + 4 P)",
+    "k_extend": "B = sum(q+t) sequence bytes",
+}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU per step (configs[1]: 10k)")
-    ap.add_argument("--cpu-sample", type=int, default=2000, help="reads in the bounded CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="reads in the bounded CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-
     if args.impl == "reference":
         run_reference(args)
         return
+    args.warmup = max(args.warmup, 3)
 
     import torch
     import vacmap_b200 as vb
@@ -202,88 +196,123 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     dist = None
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # reads shard across ranks with no data-path collective (weak scaling: fixed work per GPU)
-    wl = ChainGlobalWorkload(n_reads=args.reads, seed=1, rank=rank)
+    # reads shard across ranks (no data-path collective): weak scaling, fixed work per GPU
+    ref, reads, cat, off = make_workload(args.reads, rank)
     ctx = vb._lib.Context(local_rank)
-    ch = vb.GlobalChainer(vb.ChainParams(), ctx=ctx)
+    ix = vb.Index(ref, w=10, k=15, ctx=ctx)
+    al = vb.Aligner(ix, vb.default_option("H"), "H")
+    bases = int(off[-1])
 
-    # ---- device-resident: inputs in HBM before the timed region ----
-    ch.upload_ragged(wl.rows, wl.off, wl.read_lens)
+    # ---- device-resident: reads already in HBM when the timed region starts ----
+    al.upload_reads(cat, off)
     for _ in range(args.warmup):
-        ch.run()
+        rec_off, recs, cig = al.align_packed(cat, off, resident=True)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     l0 = ctx.kernel_launches
-    dev_ms = 0.0
-    stage = {"pack": 0.0, "sort": 0.0, "dp_exact": 0.0, "dp_fast": 0.0}
+    stage = {}
+    aligned = 0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        dev_ms += ch.run()                       # CUDA events on the ctx stream around the kernels
-        for k, v in ch.stage_times().items():
-            stage[k] += v
+        rec_off, recs, cig = al.align_packed(cat, off, resident=True)
+        for k, v in al.last_stage_ms.items():
+            stage[k] = stage.get(k, 0.0) + v
+        mapped = np.diff(rec_off) > 0
+        aligned += int(np.diff(off)[mapped].sum())
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = ctx.kernel_launches - l0
 
-    # ---- end to end: host buffers in, host results out, every step ----
-    for _ in range(2):
-        ch.upload_ragged(wl.rows, wl.off, wl.read_lens); ch.run(); ch.download()
+    # ---- end to end: host reads in, host records out, every step ----
+    for _ in range(1):
+        al.align_packed(cat, off)
     barrier()
     t0 = time.perf_counter()
+    aligned_e2e = 0
     for _ in range(args.steps):
-        ch.upload_ragged(wl.rows, wl.off, wl.read_lens)
-        ch.run()
-        res = ch.download()
+        rec_off, recs, cig = al.align_packed(cat, off)
+        aligned_e2e += int(np.diff(off)[np.diff(rec_off) > 0].sum())
     barrier()
     e2e_wall = time.perf_counter() - t0
+    d2h = recs.nbytes + cig.nbytes + rec_off.nbytes
 
-    t_dev = torch.tensor([dev_ms / 1000.0, e2e_wall, wall], dtype=torch.float64, device="cuda")
+    t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([aligned, aligned_e2e, len(recs)], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    t_max, e2e_max, wall_max = [float(x) for x in t_dev.cpu()]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        # final gather of the alignment records on rank 0 (fixed-size rows; CIGAR arenas stay per rank)
+        n_local = torch.tensor([len(recs)], dtype=torch.int64, device="cuda")
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, n_local)
+        mx = int(max(int(s.item()) for s in sizes))
+        payload = torch.zeros((mx, vb.align.RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+        if len(recs):
+            payload[:len(recs)] = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1)).cuda()
+        gathered = [torch.zeros_like(payload) for _ in range(world)] if rank == 0 else None
+        dist.gather(payload, gathered, dst=0)
+    wall_max, e2e_max = [float(x) for x in t.cpu()]
+    aligned_all, aligned_e2e_all, nrec_all = [float(x) for x in tot.cpu()]
 
     if rank == 0:
-        total_bases = wl.bases * world * args.steps
-        value = total_bases / t_max / 1e9
-        e2e = total_bases / e2e_max / 1e9
+        value = aligned_all / wall_max / 1e9
+        e2e = aligned_e2e_all / e2e_max / 1e9
         peak, peak_src = peaks()
-        dp_s = stage["dp_exact"] / 1000.0 / args.steps
-        achieved = wl.chain_bytes() / dp_s / 1e9 if dp_s > 0 else 0.0
+        per_step = {k: v / args.steps for k, v in stage.items()}
+        kern = {k: v for k, v in per_step.items() if k.startswith("k_") or k.endswith("_kernels")}
+        top = max(kern, key=kern.get) if kern else None
+        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_ed_cells",
+                                                      "n_reseed_hits", "n_chain_anchors")}
+        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_cells"],
+                     "k_edit_distance": 2.0 * bases,
+                     "k_reseed_hits": 2 * (2.0 * bases) + 8.0 * counts["n_reseed_hits"],
+                     "k_reseed_merge": 8.0 * counts["n_reseed_hits"] + 16.0 * counts["n_reseed_hits"] / 4,
+                     "chain_local_kernels": 28.0 * counts["n_chain_anchors"], "chain_global_kernels": 28.0 * counts["n_chain_anchors"],
+                     "k_extend": 0.0}
+        roof = None
+        if top:
+            secs = kern[top] / 1000.0
+            achieved = alg_bytes.get(top, 0.0) / secs / 1e9 if secs > 0 else 0.0
+            roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "kernel_ms_per_step": kern[top],
+                    "bytes_per_step": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
+                    "gcups": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
+                    "note": "integer DP wavefront: compute/latency-bound, not HBM-bound (SURVEY 8d); the HBM fraction is "
+                            "reported because north_star asks for it"}
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1000 * t_max / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl.name, "reads_per_gpu_per_step": wl.n_reads, "read_len": wl.read_len,
-                           "anchors_per_step": wl.total_anchors, "l2": "inputs (%.0f MB/step) larger than L2" %
-                           (wl.rows.nbytes / 1e6), "sharding": "reads split across ranks, no collective"},
-                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": wl.h2d_bytes(),
-                        "d2h_bytes_per_step": wl.d2h_bytes()},
+                "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": args.reads, "read_len": READ_LEN, "err": ERR,
+                           "ref_len": REF_LEN, "mode": "H", "k": 15, "w": 10,
+                           "l2": "per-step working set (reads 2x%.0f MB + anchors, hits, direction matrices >1 GB) exceeds "
+                                 "the 126 MB L2" % (bases / 1e6),
+                           "sharding": "reads split across ranks, index replicated per GPU, records gathered on rank 0"},
+                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": len(cat) + off.nbytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches),
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
-                "roofline": {"bound": "hbm", "kernel": "vm_chain_exact_kernel", "achieved": achieved, "peak": peak,
-                             "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                             "note": "algorithmic bytes = 28 B/anchor (16 in + 8 S + 4 P); the DP is latency/issue-bound, "
-                                     "not HBM-bound (SURVEY 8d)"},
-                "clocks": clocks}
+                "records_per_step": nrec_all,
+                "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
+                "work_per_step": counts,
+                "roofline": roof, "clocks": clocks}
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            v, dt = cpu_baseline(wl, min(wl.n_reads, args.cpu_sample), cores)
+            sample = min(args.reads, args.cpu_sample)
+            v, dt = cpu_baseline(ref, reads[:sample], cores)
             line["cpu_baseline"] = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
-                                    "sample": "%d reads of the workload, oracle C port, %d processes, %.1f s" %
-                                              (min(wl.n_reads, args.cpu_sample), cores, dt)}
+                                    "sample": "%d reads of the workload, oracle port (C stages + Python glue), %d processes, "
+                                              "%.1f s" % (sample, cores, dt)}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

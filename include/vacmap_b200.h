@@ -171,6 +171,12 @@ typedef struct vm_result vm_result;
  * reference would drop through an exception (clrnano:24116-24125), simply have no records. */
 int vm_align_batch(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
                    const char *seqs, const int64_t *seq_off, vm_result **out);
+/* Two-step form for measuring with the reads already resident in HBM: vm_reads_upload copies the
+ * batch (forward + reverse-complement strands) to the device, vm_align_resident then runs the
+ * same pipeline on it (same arguments; seqs/seq_off are still needed by the host glue). */
+int vm_reads_upload(vm_ctx *ctx, vm_index_handle *index, int64_t n_reads, const char *seqs, const int64_t *seq_off);
+int vm_align_resident(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
+                      const char *seqs, const int64_t *seq_off, vm_result **out);
 int64_t vm_result_num_records(vm_result *r);
 int64_t vm_result_num_cigar_ops(vm_result *r);
 const int64_t *vm_result_read_offsets(vm_result *r);   /* [n_reads+1] into the record array */

@@ -291,11 +291,24 @@ def k_cigar(target, query, match=2, mismatch=-4, gap_open_1=4, gap_extend_1=2, g
     return ops_to_string(ops), r.zdropped, r.q_e, r.t_e, r.ndel, r.nins
 
 
-def edit_distance(a, b):
+def edit_distance_dp(a, b):
+    """plain two-row DP (the definition)"""
     L = lib(); _declare_natives(L)
     a = a.encode() if isinstance(a, str) else a
     b = b.encode() if isinstance(b, str) else b
     return int(L.orc_edit_distance(a, len(a), b, len(b)))
+
+
+def edit_distance(a, b):
+    """Myers bit-vector NW distance (what edlib runs); equals edit_distance_dp (tests/test_oracle_natives.py)."""
+    L = lib(); _declare_natives(L)
+    if not hasattr(L, "_bv_declared"):
+        L.orc_edit_distance_bv.restype = ctypes.c_int64
+        L.orc_edit_distance_bv.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_char_p, ctypes.c_int64]
+        L._bv_declared = True
+    a = a.encode() if isinstance(a, str) else a
+    b = b.encode() if isinstance(b, str) else b
+    return int(L.orc_edit_distance_bv(a, len(a), b, len(b)))
 
 
 def local_reseed_scan(ctg, wins, raw_by_x, seq, rc_seq, k, readstart, readend):

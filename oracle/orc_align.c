@@ -191,6 +191,51 @@ int orc_k_cigar(const char *target, int32_t tlen, const char *query, int32_t qle
     return rc;
 }
 
+/*
+ * Global unit-cost edit distance, Myers / Hyyro bit-vector blocks (what edlib itself runs for
+ * task='distance', mode NW).  Used by the timed CPU baseline so that the baseline is not
+ * handicapped by a quadratic scalar DP; orc_edit_distance below (plain DP) pins it in the tests.
+ */
+int64_t orc_edit_distance_bv(const char *pat, int64_t m, const char *txt, int64_t n)
+{
+    if (m == 0) return n;
+    if (n == 0) return m;
+    const int64_t W = (m + 63) / 64;
+    uint64_t *peq = (uint64_t *)calloc((size_t)(256 * W), 8);
+    uint64_t *Pv = (uint64_t *)malloc(8 * (size_t)W), *Mv = (uint64_t *)calloc((size_t)W, 8);
+    for (int64_t i = 0; i < m; ++i) peq[(size_t)(unsigned char)pat[i] * W + i / 64] |= 1ULL << (i % 64);
+    for (int64_t w = 0; w < W; ++w) Pv[w] = ~0ULL;
+    int64_t score = 64 * W;
+    for (int64_t j = 0; j < n; ++j) {
+        const uint64_t *eqrow = peq + (size_t)(unsigned char)txt[j] * W;
+        int hin = 1;
+        for (int64_t w = 0; w < W; ++w) {
+            uint64_t Eq = eqrow[w];
+            const uint64_t pv = Pv[w], mv = Mv[w];
+            const uint64_t neg = hin < 0 ? 1ULL : 0ULL;
+            const uint64_t Xv = Eq | mv;
+            Eq |= neg;
+            const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            uint64_t Ph = mv | ~(Xh | pv);
+            uint64_t Mh = pv & Xh;
+            const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            Ph <<= 1; Mh <<= 1;
+            Mh |= neg;
+            Ph |= hin > 0 ? 1ULL : 0ULL;
+            Pv[w] = Mh | ~(Xv | Ph);
+            Mv[w] = Ph & Xv;
+            hin = hout;
+        }
+        score += hin;
+    }
+    for (int64_t b = m - 64 * (W - 1); b < 64; ++b) {
+        if (Pv[W - 1] >> b & 1ULL) --score;
+        if (Mv[W - 1] >> b & 1ULL) ++score;
+    }
+    free(peq); free(Pv); free(Mv);
+    return score;
+}
+
 /* Global unit-cost edit distance (edlib NW, task='distance').  Plain two-row DP. */
 int64_t orc_edit_distance(const char *a, int64_t n, const char *b, int64_t m)
 {

@@ -118,21 +118,20 @@ def mutate(rng, seq_u8, err, ratio=(4, 3, 3)):
     r = rng.random(n)
     tot = float(sum(ratio))
     ps, pi = err * ratio[0] / tot, err * ratio[1] / tot
-    out = []
     kinds = np.where(r < ps, 1, np.where(r < ps + pi, 2, np.where(r < err, 3, 0)))
     rnd = rng.integers(0, 4, size=n)
-    for i in range(n):
-        k = kinds[i]
-        if k == 0:
-            out.append(seq_u8[i])
-        elif k == 1:
-            b = _B[rnd[i]]
-            out.append(b if b != seq_u8[i] else _B[(rnd[i] + 1) & 3])
-        elif k == 2:
-            out.append(seq_u8[i])
-            out.append(_B[rnd[i]])
-        # k == 3: deletion
-    return np.array(out, dtype=np.uint8)
+    # vectorised assembly: kind 0 copy, 1 substitution, 2 copy + inserted base, 3 deletion
+    sub = _B[rnd]
+    sub = np.where(sub != seq_u8, sub, _B[(rnd + 1) & 3])
+    first = np.where(kinds == 1, sub, seq_u8)
+    counts = np.where(kinds == 3, 0, np.where(kinds == 2, 2, 1))
+    pos = np.cumsum(counts) - counts
+    out = np.empty(int(counts.sum()), dtype=np.uint8)
+    keep = kinds != 3
+    out[pos[keep]] = first[keep]
+    ins = kinds == 2
+    out[pos[ins] + 1] = _B[rnd[ins]]
+    return out
 
 
 def make_reads(contigs, seed, n_reads, read_len=15000, err=0.10, ratio=(4, 3, 3), sv_frac=0.0):

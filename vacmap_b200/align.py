@@ -95,6 +95,8 @@ def _declare(L):
     L.vm_index_info.argtypes = [vp] + [vp] * 6
     L.vm_index_contig.argtypes = [vp, i32, vp, vp, vp, vp]
     L.vm_align_batch.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
+    L.vm_align_resident.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
+    L.vm_reads_upload.argtypes = [vp, vp, i64, vp, vp]
     for f in ("vm_result_num_records", "vm_result_num_cigar_ops"):
         getattr(L, f).argtypes = [vp]
         getattr(L, f).restype = i64
@@ -170,7 +172,14 @@ class Aligner:
                                    int(o["nodiscard"]), mc["max_guides"], mc["local_maxgap"], mc["clamp40"], host_threads)
         self.last_stage_ms = {}
 
-    def align_packed(self, seq_cat, seq_off):
+    def upload_reads(self, seq_cat, seq_off):
+        """Put a packed batch in HBM ahead of `align_packed(..., resident=True)` (device-resident timing)."""
+        L = _lib.load()
+        seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
+        ctx = self.index.ctx
+        _lib.check(ctx.h, L.vm_reads_upload(ctx.h, self.index.h, len(seq_off) - 1, seq_cat, _lib.ptr(seq_off)))
+
+    def align_packed(self, seq_cat, seq_off, resident=False):
         """seq_cat: bytes of all (upper-case) reads; seq_off int64[n+1].
         -> (rec_off int64[n+1], records structured array, cigar uint32 array)."""
         L = _lib.load()
@@ -179,8 +188,8 @@ class Aligner:
         res = ctypes.c_void_p()
         ctx = self.index.ctx
         buf = (ctypes.c_char * len(seq_cat)).from_buffer_copy(seq_cat) if not isinstance(seq_cat, bytes) else seq_cat
-        _lib.check(ctx.h, L.vm_align_batch(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off),
-                                           ctypes.byref(res)))
+        fn = L.vm_align_resident if resident else L.vm_align_batch
+        _lib.check(ctx.h, fn(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off), ctypes.byref(res)))
         try:
             nrec, nops = L.vm_result_num_records(res), L.vm_result_num_cigar_ops(res)
             off = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_offsets(res), ctypes.POINTER(ctypes.c_int64)),

@@ -36,6 +36,8 @@ void vm_ctx_destroy(vm_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->backend && c->backend_free) c->backend_free(c->backend);
+    c->backend = nullptr;
     VmChainState &s = c->chain;
     VmDevBuf *bufs[] = {&s.rows, &s.off_dev, &s.anch, &s.perm, &s.sorted, &s.sorted_rows, &s.S, &s.P,
                         &s.S_arg, &s.gmax, &s.opcount, &s.ids, &s.gcl, &s.rgl, &s.fast_scratch, &s.fast_off, &s.sort_scratch,

@@ -44,9 +44,31 @@ public:
         for (VmDevBuf *x : b) x->release();
     }
     StageTimer timer;
+    bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
+    void set_index(vm_index_handle *ih) { ih_ = ih; }
+
+    // device time of a group of launches, CUDA events on the ctx stream
+    struct KTimer {
+        CudaBackend *be; const char *name; cudaEvent_t a, b;
+        KTimer(CudaBackend *be_, const char *n) : be(be_), name(n)
+        {
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, be->c_->stream);
+        }
+        void stop()
+        {
+            cudaEventRecord(b, be->c_->stream);
+            cudaEventSynchronize(b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            be->timer.add(name, ms);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+        }
+    };
 
     void upload_reads(const ReadBatch &b)
     {
+        if (reads_resident && off_host_.size() == (size_t)b.n + 1 && std::equal(off_host_.begin(), off_host_.end(), b.off)) return;
         const size_t total = (size_t)b.off[b.n];
         std::string rc(total, 'N');
         for (int64_t r = 0; r < b.n; ++r) {
@@ -107,6 +129,7 @@ public:
             rl.push_back((int32_t)std::min<int64_t>(read_len[r], INT32_MAX));
         }
         const int64_t n = (int64_t)ids.size(), T = off.back();
+        chain_anchors_ += (double)T;
         std::vector<int64_t> srt((size_t)T * 4), gmax((size_t)n);
         std::vector<double> S((size_t)T);
         std::vector<int32_t> P((size_t)T), A((size_t)T), uf((size_t)n);
@@ -215,10 +238,12 @@ public:
         BE_OK(cudaMemsetAsync(d_over, 0, 4, c_->stream));
         const VmIndexDev &ix = ih_->ix->dev;
         // pass 1: count hits
+        KTimer kt1(this, "k_reseed_hits");
         c_->launches += vm_reseed_launch(ix, d_jobs.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
                                          read_off_.as<int64_t>(), d_wlo.as<int64_t>(), d_whi.as<int64_t>(), d_gx.as<int32_t>(),
                                          d_gy.as<int64_t>(), nullptr, d_n_hits, d_over, nullptr, nullptr, nullptr, nullptr,
                                          c_->stream);
+        kt1.stop();
         std::vector<int32_t> n_hits((size_t)nj);
         BE_OK(cudaMemcpyAsync(n_hits.data(), d_n_hits, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
@@ -240,12 +265,17 @@ public:
         BE_OK(d_out.ensure((size_t)hit_off * 2 * sizeof(VmAnchor) + 64));
         BE_OK(cudaMemcpyAsync(d_jobs.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
         int32_t *d_n_out = d_nh.as<int32_t>();   // reuse after the counts are on the host
+        KTimer kt2(this, "k_reseed_hits");
         c_->launches += vm_reseed_launch(ix, d_jobs.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
                                          read_off_.as<int64_t>(), d_wlo.as<int64_t>(), d_whi.as<int64_t>(), d_gx.as<int32_t>(),
                                          d_gy.as<int64_t>(), d_hits.p, d_n_hits, d_over, nullptr, nullptr, nullptr, nullptr,
                                          c_->stream);
+        kt2.stop();
+        KTimer kt3(this, "k_reseed_merge");
         c_->launches += vm_reseed_merge_launch(d_jobs.as<VmReseedJobDev>(), nj, d_hits.p, d_n_hits, d_tab.p, d_order.as<int32_t>(),
                                                d_out.as<VmAnchor>(), d_n_out + nj + 1, c_->stream);
+        kt3.stop();
+        reseed_hits_ += (double)hit_off;
         std::vector<int32_t> n_out((size_t)nj), over(1);
         BE_OK(d_nh.ensure((size_t)nj * 8 + 64));
         BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out + nj + 1, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
@@ -308,7 +338,10 @@ public:
         if (max_words > 32 * 64) throw std::runtime_error("edit distance: sequence longer than 131072 bases is not supported yet");
         BE_OK(jobs_.ensure(J.size() * sizeof(VmAlnJobDev)));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_edit_distance");
         c_->launches += vm_launch_edit_distance(jobs_.as<VmAlnJobDev>(), nj, sources(), max_words, c_->stream);
+        kt.stop();
+        for (int j = 0; j < nj; ++j) ed_cells_ += (double)J[j].q.len * (double)J[j].t.len;
         BE_OK(cudaMemcpyAsync(J.data(), jobs_.p, J.size() * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
         BE_OK(cudaGetLastError());
@@ -330,7 +363,9 @@ public:
         }
         BE_OK(jobs_.ensure(J.size() * sizeof(VmAlnJobDev)));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_extend");
         c_->launches += vm_launch_extend(jobs_.as<VmAlnJobDev>(), nj, sources(), c_->stream);
+        kt.stop();
         BE_OK(cudaMemcpyAsync(J.data(), jobs_.p, J.size() * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
         BE_OK(cudaGetLastError());
@@ -375,6 +410,12 @@ public:
         BE_OK(d_cig.ensure((size_t)out_off * 4 + 64));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_fill");
+        for (int j = 0; j < nj; ++j) {
+            fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;
+            fill_bases_ += (double)J[j].t.len + (double)J[j].q.len;
+        }
+        fill_jobs_ += nj;
         for (int k = 0; k <= ncap; ++k) {
             const int cnt = start[k + 1] - start[k];
             if (cnt == 0) continue;
@@ -382,6 +423,7 @@ public:
                                            k < ncap ? caps[k] : 0, d_dir.as<uint8_t>(), d_sc.as<int32_t>(), d_cig.as<uint32_t>(),
                                            c_->stream);
         }
+        kt.stop();
         std::vector<uint32_t> cig((size_t)out_off);
         BE_OK(cudaMemcpyAsync(J.data(), jobs_.p, J.size() * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaMemcpyAsync(cig.data(), d_cig.p, cig.size() * 4, cudaMemcpyDeviceToHost, c_->stream));
@@ -389,6 +431,13 @@ public:
         BE_OK(cudaGetLastError());
         for (int j = 0; j < nj; ++j) jobs[j].cigar.assign(cig.begin() + J[j].out_off, cig.begin() + J[j].out_off + J[j].n_out);
         timer.add("fill", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+
+    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0;
+    void reset_counters()
+    {
+        timer.ms.clear();
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = 0;
     }
 
 private:
@@ -483,8 +532,8 @@ int vm_index_contig(vm_index_handle *h, int32_t i, const char **name, int64_t *s
     return VM_OK;
 }
 
-int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
-                   const int64_t *seq_off, vm_result **out)
+static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                         const int64_t *seq_off, int resident, vm_result **out)
 {
     if (!c) return VM_ERR_ARG;
     if (!h || !p || !out || n_reads < 0 || !seq_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
@@ -503,7 +552,14 @@ int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int6
     opt.mode = vmg::ModeConst{p->accept_score, p->max_guides, p->local_maxgap, p->clamp40 != 0};
     vm_result *res = new vm_result();
     try {
-        CudaBackend be(c, h);
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.set_index(h);
+        be.reset_counters();
+        be.reads_resident = resident != 0;
         int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
         Driver drv(be, h->ctg, opt, h->ix->k, threads);
         ReadBatch b;
@@ -530,6 +586,12 @@ int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int6
             res->rec_off[r + 1] = (int64_t)res->recs.size();
         }
         be.timer.add("total", total);
+        be.timer.add("n_fill_cells", be.fill_cells_);
+        be.timer.add("n_fill_bases", be.fill_bases_);
+        be.timer.add("n_fill_jobs", be.fill_jobs_);
+        be.timer.add("n_ed_cells", be.ed_cells_);
+        be.timer.add("n_reseed_hits", be.reseed_hits_);
+        be.timer.add("n_chain_anchors", be.chain_anchors_);
         for (auto &kv : be.timer.ms) {
             res->stage_names.push_back(kv.first);
             res->stage_ms.push_back(kv.second);
@@ -542,6 +604,40 @@ int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int6
     }
     *out = res;
     return VM_OK;
+}
+
+int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                   const int64_t *seq_off, vm_result **out)
+{
+    return vm_align_impl(c, h, p, n_reads, seqs, seq_off, 0, out);
+}
+
+int vm_reads_upload(vm_ctx *c, vm_index_handle *h, int64_t n_reads, const char *seqs, const int64_t *seq_off)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!h || n_reads < 0 || !seq_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.reads_resident = false;
+        ReadBatch b;
+        b.n = n_reads; b.seq = seqs; b.off = seq_off;
+        be.upload_reads(b);
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
+int vm_align_resident(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                      const int64_t *seq_off, vm_result **out)
+{
+    return vm_align_impl(c, h, p, n_reads, seqs, seq_off, 1, out);
 }
 
 int64_t vm_result_num_records(vm_result *r) { return r ? (int64_t)r->recs.size() : 0; }

@@ -76,4 +76,7 @@ struct vm_ctx {
     VmDevBuf extra, readgapcost, log2cache;
     int64_t n_extra = 0, n_readgapcost = 0, n_log2cache = 0;
     VmChainState chain;
+    // persistent alignment backend (vm_backend_cuda.cu); destroyed through backend_free
+    void *backend = nullptr;
+    void (*backend_free)(void *) = nullptr;
 };
