@@ -177,6 +177,13 @@ int vm_align_batch(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *p
 int vm_reads_upload(vm_ctx *ctx, vm_index_handle *index, int64_t n_reads, const char *seqs, const int64_t *seq_off);
 int vm_align_resident(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
                       const char *seqs, const int64_t *seq_off, vm_result **out);
+/* Stage-level entry point of the base-level kernels on raw sequence pairs (parity tests).
+ * kind 0: edlib.align(query, target, task='distance') (clrnano:19251)        -> out0[j] = distance
+ * kind 1: mp.k_cigar(t, q, 2,-4, 4,4,4,4, bw=100, zdropvalue=50) (clrnano:2381) -> out0 = q_e, out1 = t_e
+ * kind 2: mp.k_cigar(t, q, 2,-4, 4,2,24,1, bw=-1, zdropvalue=-1, eqx) (clrnano:21554) -> out0[j] = number of
+ *         CIGAR ops, written at cigar[cig_off[j]...], cig_off[j] = sum_{i<j} (tlen_i + qlen_i + 2). */
+int vm_pairs_batch(vm_ctx *ctx, int32_t kind, int32_t eqx, int64_t n_pairs, const char *targets, const int64_t *t_off,
+                   const char *queries, const int64_t *q_off, int64_t *out0, int64_t *out1, uint32_t *cigar);
 int64_t vm_result_num_records(vm_result *r);
 int64_t vm_result_num_cigar_ops(vm_result *r);
 const int64_t *vm_result_read_offsets(vm_result *r);   /* [n_reads+1] into the record array */

@@ -230,3 +230,34 @@ class Aligner:
 
 def cigar_string(ops):
     return "".join("%d%s" % (int(o) >> 4, OPS[int(o) & 0xf]) for o in ops)
+
+
+def pairs_batch(kind, targets, queries, eqx=False, ctx=None, device=0):
+    """Stage-level base-level kernels on raw (target, query) string pairs.
+    kind 'distance' -> list of int; 'extend' -> list of (q_e, t_e); 'fill' -> list of CIGAR strings."""
+    L = _lib.load()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_pairs_batch.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    ctx = ctx or _lib.default_context(device)
+    n = len(targets)
+    tb, qb = [t.encode() for t in targets], [q.encode() for q in queries]
+    t_off = np.zeros(n + 1, np.int64)
+    q_off = np.zeros(n + 1, np.int64)
+    for i in range(n):
+        t_off[i + 1] = t_off[i] + len(tb[i])
+        q_off[i + 1] = q_off[i] + len(qb[i])
+    out0, out1 = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    k = {"distance": 0, "extend": 1, "fill": 2}[kind]
+    cap = int(t_off[-1] + q_off[-1] + 2 * n + 16)
+    cig = np.zeros(cap if k == 2 else 1, np.uint32)
+    _lib.check(ctx.h, L.vm_pairs_batch(ctx.h, k, int(eqx), n, b"".join(tb), _lib.ptr(t_off), b"".join(qb), _lib.ptr(q_off),
+                                       _lib.ptr(out0), _lib.ptr(out1), _lib.ptr(cig)))
+    if k == 0:
+        return [int(v) for v in out0]
+    if k == 1:
+        return [(int(a), int(b)) for a, b in zip(out0, out1)]
+    res, co = [], 0
+    for i in range(n):
+        res.append(cigar_string(cig[co:co + int(out0[i])]))
+        co += len(tb[i]) + len(qb[i]) + 2
+    return res

@@ -34,6 +34,9 @@ struct VmSeqSources {
 
 int vm_launch_edit_distance(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int max_words, cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);
-// tcap: shared-memory score arrays hold targets up to tcap bases (0 = use global scratch)
-int vm_launch_fill(VmAlnJobDev *jobs, const int *job_ids, int n_ids, VmSeqSources src, int eqx, int tcap, uint8_t *dir,
-                   int32_t *score_scratch, uint32_t *cigar_out, cudaStream_t stream);
+// dir: direction bytes, vm_fill_dir_bytes(tlen, qlen) per job at dir_off (8-byte aligned);
+// band_scratch: 3 * qlen ints per job whose target exceeds vm_fill_band_rows() rows (sc_off, else -1)
+size_t vm_fill_dir_bytes(int tlen, int qlen);
+int vm_fill_band_rows();
+int vm_launch_fill(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int eqx, uint8_t *dir, int32_t *band_scratch,
+                   uint32_t *cigar_out, cudaStream_t stream);

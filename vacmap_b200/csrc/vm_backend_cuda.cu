@@ -312,7 +312,7 @@ public:
     VmSeqSources sources() const
     {
         VmSeqSources S;
-        S.ref = ih_->ix->dev.ref;
+        S.ref = ih_ ? ih_->ix->dev.ref : nullptr;
         S.reads_fwd = reads_fwd_.as<uint8_t>();
         S.reads_rc = reads_rc_.as<uint8_t>();
         S.read_off = read_off_.as<int64_t>();
@@ -379,10 +379,8 @@ public:
         const int nj = (int)jobs.size();
         if (nj == 0) return;
         std::vector<VmAlnJobDev> J((size_t)nj);
-        static const int caps[] = {256, 512, 1024, 2048, 4096};
-        const int ncap = 5;
-        std::vector<std::vector<int>> cls(ncap + 1);
         int64_t out_off = 0, dir_off = 0, sc_off = 0;
+        const int band_rows = vm_fill_band_rows();
         for (int j = 0; j < nj; ++j) {
             memset(&J[j], 0, sizeof(VmAlnJobDev));
             J[j].t = spec(jobs[j].job.target);
@@ -391,38 +389,22 @@ public:
             J[j].out_off = out_off;
             J[j].dir_off = dir_off;
             out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
-            dir_off += (int64_t)J[j].t.len * J[j].q.len;
-            int k = 0;
-            while (k < ncap && J[j].t.len > caps[k]) ++k;
-            if (k == ncap) { J[j].sc_off = sc_off; sc_off += 11LL * J[j].t.len; }
+            dir_off += (int64_t)((vm_fill_dir_bytes(J[j].t.len, J[j].q.len) + 7) & ~(size_t)7);
+            if (J[j].t.len > band_rows) { J[j].sc_off = sc_off; sc_off += 3LL * J[j].q.len; }
             else J[j].sc_off = -1;
-            cls[k].push_back(j);
-        }
-        VmDevBuf &d_ids = aux0_, &d_dir = aux5_, &d_sc = aux6_, &d_cig = aux8_;
-        std::vector<int> ids;
-        std::vector<int> start(ncap + 2, 0);
-        for (int k = 0; k <= ncap; ++k) { start[k] = (int)ids.size(); ids.insert(ids.end(), cls[k].begin(), cls[k].end()); }
-        start[ncap + 1] = (int)ids.size();
-        BE_OK(jobs_.ensure(J.size() * sizeof(VmAlnJobDev)));
-        BE_OK(d_ids.ensure(ids.size() * 4 + 64));
-        BE_OK(d_dir.ensure((size_t)dir_off + 64));
-        BE_OK(d_sc.ensure((size_t)sc_off * 4 + 64));
-        BE_OK(d_cig.ensure((size_t)out_off * 4 + 64));
-        BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_ids.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c_->stream));
-        KTimer kt(this, "k_fill");
-        for (int j = 0; j < nj; ++j) {
             fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;
             fill_bases_ += (double)J[j].t.len + (double)J[j].q.len;
         }
         fill_jobs_ += nj;
-        for (int k = 0; k <= ncap; ++k) {
-            const int cnt = start[k + 1] - start[k];
-            if (cnt == 0) continue;
-            c_->launches += vm_launch_fill(jobs_.as<VmAlnJobDev>(), d_ids.as<int>() + start[k], cnt, sources(), eqx ? 1 : 0,
-                                           k < ncap ? caps[k] : 0, d_dir.as<uint8_t>(), d_sc.as<int32_t>(), d_cig.as<uint32_t>(),
-                                           c_->stream);
-        }
+        VmDevBuf &d_dir = aux5_, &d_sc = aux6_, &d_cig = aux8_;
+        BE_OK(jobs_.ensure(J.size() * sizeof(VmAlnJobDev)));
+        BE_OK(d_dir.ensure((size_t)dir_off + 64));
+        BE_OK(d_sc.ensure((size_t)sc_off * 4 + 64));
+        BE_OK(d_cig.ensure((size_t)out_off * 4 + 64));
+        BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_fill");
+        c_->launches += vm_launch_fill(jobs_.as<VmAlnJobDev>(), nj, sources(), eqx ? 1 : 0, d_dir.as<uint8_t>(),
+                                       d_sc.as<int32_t>(), d_cig.as<uint32_t>(), c_->stream);
         kt.stop();
         std::vector<uint32_t> cig((size_t)out_off);
         BE_OK(cudaMemcpyAsync(J.data(), jobs_.p, J.size() * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
@@ -610,6 +592,75 @@ int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int6
                    const int64_t *seq_off, vm_result **out)
 {
     return vm_align_impl(c, h, p, n_reads, seqs, seq_off, 0, out);
+}
+
+// Stage-level entry point for the base-level kernels on raw sequence pairs (parity tests).
+// kind 0: global edit distance -> out0[j]; kind 1: z-drop edge extension -> out0 = q_e, out1 = t_e;
+// kind 2: global fill -> CIGAR ops of pair j at cigar[cig_off[j] .. cig_off[j] + out0[j]),
+//         cig_off[j] = sum over i < j of (tlen_i + qlen_i + 2).
+int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const char *targets, const int64_t *t_off,
+                   const char *queries, const int64_t *q_off, int64_t *out0, int64_t *out1, uint32_t *cigar)
+{
+    if (!c) return VM_ERR_ARG;
+    if (n_pairs < 0 || !t_off || !q_off || !out0 || kind < 0 || kind > 2) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, nullptr);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        // one pseudo-read holding every target followed by every query
+        const int64_t tt = t_off[n_pairs], tq = q_off[n_pairs];
+        std::string cat((size_t)(tt + tq), 'N');
+        if (tt) memcpy(&cat[0], targets, (size_t)tt);
+        if (tq) memcpy(&cat[(size_t)tt], queries, (size_t)tq);
+        for (char &ch : cat) ch = "ACGTN"[vm_nt4((unsigned char)ch)];
+        const int64_t off[2] = {0, tt + tq};
+        ReadBatch b;
+        b.n = 1; b.seq = cat.data(); b.off = off;
+        be.reads_resident = false;
+        be.upload_reads(b);
+        be.reset_counters();
+        auto ref_of = [&](int64_t lo, int64_t hi) { vmg::SeqRef s; s.src = 1; s.lo = lo; s.hi = hi; return s; };
+        if (kind == 0) {
+            std::vector<EdJob> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].a = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+                jobs[j].b = ref_of(t_off[j], t_off[j + 1]);
+            }
+            be.edit_distance(b, jobs);
+            for (int64_t j = 0; j < n_pairs; ++j) out0[j] = jobs[j].dist;
+        } else if (kind == 1) {
+            std::vector<ExtJobRef> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].job.target = ref_of(t_off[j], t_off[j + 1]);
+                jobs[j].job.query = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+            }
+            be.extend(b, jobs);
+            for (int64_t j = 0; j < n_pairs; ++j) { out0[j] = jobs[j].job.q_e; if (out1) out1[j] = jobs[j].job.t_e; }
+        } else {
+            std::vector<FillJobRef> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].job.target = ref_of(t_off[j], t_off[j + 1]);
+                jobs[j].job.query = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+            }
+            be.fill(b, eqx != 0, jobs);
+            int64_t co = 0;
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                out0[j] = (int64_t)jobs[j].cigar.size();
+                if (cigar && !jobs[j].cigar.empty()) memcpy(cigar + co, jobs[j].cigar.data(), jobs[j].cigar.size() * 4);
+                co += (t_off[j + 1] - t_off[j]) + (q_off[j + 1] - q_off[j]) + 2;
+            }
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
 }
 
 int vm_reads_upload(vm_ctx *c, vm_index_handle *h, int64_t n_reads, const char *seqs, const int64_t *seq_off)
