@@ -60,9 +60,31 @@ struct OracleBackend : public Backend {
         return out;
     }
 
-    void seed(const ReadBatch &b, int check_num, Ragged<Anc> &anchors, std::vector<char> &need_reverse) override
+    static void put(ChainOut &out, int64_t r, const std::vector<Anc> &srt, const std::vector<double> &S,
+                    const std::vector<int32_t> &P, const std::vector<int32_t> &A, int64_t g)
     {
-        anchors.clear();
+        out.start[r] = (int64_t)out.sorted_store.size();
+        out.cnt[r] = (int32_t)srt.size();
+        out.gmax[r] = g;
+        for (size_t t = 0; t < srt.size(); ++t) {
+            out.sorted_store.push_back(vmg::Anc32{(int32_t)srt[t].x, (uint32_t)srt[t].y, srt[t].s, srt[t].l});
+            out.S_store.push_back(S[t]);
+            out.P_store.push_back(P[t]);
+            out.A_store.push_back(A[t]);
+        }
+    }
+
+    static void to_rows(const Anc *a, int64_t n, std::vector<int64_t> &rows)
+    {
+        rows.resize((size_t)n * 4);
+        for (int64_t t = 0; t < n; ++t) { rows[t * 4] = a[t].x; rows[t * 4 + 1] = a[t].y; rows[t * 4 + 2] = a[t].s; rows[t * 4 + 3] = a[t].l; }
+    }
+
+    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+                    std::vector<char> &need_reverse, ChainOut &out) override
+    {
+        out = ChainOut();
+        out.start.assign((size_t)b.n, 0); out.cnt.assign((size_t)b.n, 0); out.gmax.assign((size_t)b.n, -1);
         need_reverse.assign((size_t)b.n, 0);
         for (int64_t r = 0; r < b.n; ++r) {
             const int64_t L = b.len(r);
@@ -74,58 +96,44 @@ struct OracleBackend : public Backend {
             for (int64_t t = 0; t < m; ++t) (rows[t * 4 + 2] == 1 ? pos : neg)++;
             const bool flip = m >= 3 && neg > pos;
             need_reverse[r] = flip;
+            std::vector<Anc> anch;
             for (int64_t t = 0; t < m; ++t) {
                 const int64_t q = flip ? m - 1 - t : t;
                 Anc a{rows[q * 4], rows[q * 4 + 1], (int32_t)rows[q * 4 + 2], (int32_t)rows[q * 4 + 3]};
                 if (flip) { a.x = L - a.x - a.l; a.s = -a.s; }
-                anchors.data.push_back(a);
+                anch.push_back(a);
             }
-            anchors.close_row();
-        }
-    }
-
-    static void to_rows(const Anc *a, int64_t n, std::vector<int64_t> &rows)
-    {
-        rows.resize((size_t)n * 4);
-        for (int64_t t = 0; t < n; ++t) { rows[t * 4] = a[t].x; rows[t * 4 + 1] = a[t].y; rows[t * 4 + 2] = a[t].s; rows[t * 4 + 3] = a[t].l; }
-    }
-
-    void chain_global(const Ragged<Anc> &anchors, const std::vector<int64_t> &read_len, int kmersize, double skipcost,
-                      int maxdiff, int maxgap, ChainOut &out) override
-    {
-        out = ChainOut();
-        out.gmax.assign((size_t)anchors.rows(), -1);
-        for (int64_t r = 0; r < anchors.rows(); ++r) {
-            const int64_t n = anchors.size(r);
-            std::vector<int64_t> keys((size_t)n), perm((size_t)n), rows;
-            for (int64_t t = 0; t < n; ++t) keys[t] = anchors.row(r)[t].x;
+            const int64_t n = (int64_t)anch.size();
+            std::vector<int64_t> keys((size_t)n), perm((size_t)n), srows;
+            for (int64_t t = 0; t < n; ++t) keys[t] = anch[t].x;
             orc_argsort_i64(keys.data(), n, perm.data());
             std::vector<Anc> srt((size_t)n);
-            for (int64_t t = 0; t < n; ++t) srt[t] = anchors.row(r)[perm[t]];
-            to_rows(srt.data(), n, rows);
+            for (int64_t t = 0; t < n; ++t) srt[t] = anch[perm[t]];
+            to_rows(srt.data(), n, srows);
             std::vector<double> S((size_t)n);
             std::vector<int32_t> P((size_t)n), A((size_t)n);
+            int64_t g = -1;
             if (n > 0) {
-                int64_t g = -1;
-                const bool fast = (double)n / (double)read_len[r] > 5.0;
-                if (!fast) g = orc_chain_global_d_all(rows.data(), n, kmersize, skipcost, maxdiff, maxgap, tb, 1000, S.data(), P.data(), A.data(), nullptr);
-                if (fast || g == -1) g = orc_chain_fast(rows.data(), n, kmersize, 0, skipcost, maxdiff, maxgap, 5, tb, nullptr, S.data(), P.data(), A.data());
-                out.gmax[r] = g;
+                const bool fast = (double)n / (double)L > 5.0;
+                if (!fast) g = orc_chain_global_d_all(srows.data(), n, kmersize, skipcost, maxdiff, maxgap, tb, 1000, S.data(), P.data(), A.data(), nullptr);
+                if (fast || g == -1) g = orc_chain_fast(srows.data(), n, kmersize, 0, skipcost, maxdiff, maxgap, 5, tb, nullptr, S.data(), P.data(), A.data());
             }
-            out.sorted.data.insert(out.sorted.data.end(), srt.begin(), srt.end());
-            out.sorted.close_row();
-            out.S.insert(out.S.end(), S.begin(), S.end());
-            out.P.insert(out.P.end(), P.begin(), P.end());
-            out.S_arg.insert(out.S_arg.end(), A.begin(), A.end());
+            put(out, r, srt, S, P, A, g);
         }
+        out.adopt_stores();
     }
 
-    void reseed(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
-                Ragged<Anc> &local) override
+    void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                      const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                      ChainOut &out) override
     {
-        local.clear();
+        out = ChainOut();
+        out.start.assign((size_t)b.n, 0); out.cnt.assign((size_t)b.n, 0); out.gmax.assign((size_t)b.n, -1);
+        std::vector<float> lrg((size_t)maxgap + 1);
+        orc_large_readgap_table(maxgap, 30, lrg.data());
         size_t q = 0;
         for (int64_t r = 0; r < b.n; ++r) {
+            std::vector<Anc> anch;
             while (q < jobs.size() && jobs[q].read == r) {
                 const vmg::GuideJob &j = jobs[q].job;
                 std::string fwd(b.seq + b.off[r], (size_t)b.len(r)), rc = revcomp(fwd);
@@ -135,45 +143,30 @@ struct OracleBackend : public Backend {
                                                    j.gy.data(), (int64_t)j.gx.size(), fwd.c_str(), rc.c_str(), b.len(r), 9,
                                                    j.readstart, j.readend, &rows);
                 for (int64_t t = 0; t < m; ++t)
-                    local.data.push_back(Anc{rows[t * 4], rows[t * 4 + 1], (int32_t)rows[t * 4 + 2], (int32_t)rows[t * 4 + 3]});
+                    anch.push_back(Anc{rows[t * 4], rows[t * 4 + 1], (int32_t)rows[t * 4 + 2], (int32_t)rows[t * 4 + 3]});
                 if (rows) orc_free(rows);
                 ++q;
             }
-            local.close_row();
-        }
-    }
-
-    void chain_local(const Ragged<Anc> &anchors, const std::vector<int> &variant, const std::vector<double> &skipcost,
-                     int maxdiff, int maxgap, ChainOut &out) override
-    {
-        out = ChainOut();
-        out.gmax.assign((size_t)anchors.rows(), -1);
-        std::vector<float> lrg((size_t)maxgap + 1);
-        orc_large_readgap_table(maxgap, 30, lrg.data());
-        for (int64_t r = 0; r < anchors.rows(); ++r) {
-            const int64_t n = variant[r] ? anchors.size(r) : 0;
-            std::vector<int64_t> keys((size_t)n), perm((size_t)n), rows;
-            for (int64_t t = 0; t < n; ++t) keys[t] = anchors.row(r)[t].x + anchors.row(r)[t].l;
+            const int64_t n = variant[r] ? (int64_t)anch.size() : 0;
+            std::vector<int64_t> keys((size_t)n), perm((size_t)n), srows;
+            for (int64_t t = 0; t < n; ++t) keys[t] = anch[t].x + anch[t].l;
             orc_argsort_i64(keys.data(), n, perm.data());
             std::vector<Anc> srt((size_t)n);
-            for (int64_t t = 0; t < n; ++t) srt[t] = anchors.row(r)[perm[t]];
-            to_rows(srt.data(), n, rows);
+            for (int64_t t = 0; t < n; ++t) srt[t] = anch[perm[t]];
+            to_rows(srt.data(), n, srows);
             std::vector<double> S((size_t)n);
             std::vector<int32_t> P((size_t)n), A32((size_t)n);
+            int64_t g = -1;
             if (n > 0) {
                 std::vector<int64_t> P64((size_t)n), A64((size_t)n);
                 const float *rg = variant[r] == 1 ? tb->readgapcost : lrg.data();
-                int64_t g = orc_chain_local(rows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, tb, rg, S.data(), P64.data(), A64.data(), nullptr);
-                if (g == -2) g = orc_chain_fast(rows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, 5, tb, rg, S.data(), P.data(), A32.data());
+                g = orc_chain_local(srows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, tb, rg, S.data(), P64.data(), A64.data(), nullptr);
+                if (g == -2) g = orc_chain_fast(srows.data(), n, 9, variant[r], skipcost[r], maxdiff, maxgap, 5, tb, rg, S.data(), P.data(), A32.data());
                 else for (int64_t t = 0; t < n; ++t) P[t] = (int32_t)P64[t];
-                out.gmax[r] = g;
             }
-            out.sorted.data.insert(out.sorted.data.end(), srt.begin(), srt.end());
-            out.sorted.close_row();
-            out.S.insert(out.S.end(), S.begin(), S.end());
-            out.P.insert(out.P.end(), P.begin(), P.end());
-            out.S_arg.insert(out.S_arg.end(), A32.begin(), A32.end());
+            put(out, r, srt, S, P, A32, g);
         }
+        out.adopt_stores();
     }
 
     void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) override

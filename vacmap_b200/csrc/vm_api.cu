@@ -1,10 +1,9 @@
-// C ABI of libvacmap_b200.so -- see include/vacmap_b200.h.
+// C ABI of libvacmap_b200.so -- context, tables, and the chaining stage (see include/vacmap_b200.h).
 #include "vm_ctx.cuh"
 #include "vm_chain.cuh"
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-
 
 extern "C" {
 
@@ -39,7 +38,7 @@ void vm_ctx_destroy(vm_ctx *c)
     if (c->backend && c->backend_free) c->backend_free(c->backend);
     c->backend = nullptr;
     VmChainState &s = c->chain;
-    VmDevBuf *bufs[] = {&s.rows, &s.off_dev, &s.anch, &s.perm, &s.sorted, &s.sorted_rows, &s.S, &s.P,
+    VmDevBuf *bufs[] = {&s.rows, &s.off_dev, &s.cnt_dev, &s.anch, &s.perm, &s.sorted, &s.sorted_rows, &s.S, &s.P,
                         &s.S_arg, &s.gmax, &s.opcount, &s.ids, &s.gcl, &s.rgl, &s.fast_scratch, &s.fast_off, &s.sort_scratch,
                         &c->extra, &c->readgapcost, &c->log2cache};
     for (VmDevBuf *b : bufs) b->release();
@@ -101,23 +100,22 @@ static const int kCaps[] = {256, 512, 1024, 2048, 4096, 8192, VM_CHAIN_SMEM_CAP}
 static const int kNumCaps = 7;
 
 // Fill VmChainArgs from ctx + state (device pointers).
-static int vm_chain_args(vm_ctx *c, VmChainState &s, VmChainArgs &A)
+static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, VmChainArgs &A)
 {
     if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
-    const vm_chain_params &p = s.prm;
-    if (p.maxdiff + 1 > VM_GCL_MAX || p.maxgap + 1 > VM_RGL_MAX + 100000) { c->err = "maxdiff too large"; return VM_ERR_ARG; }
+    if (p.maxdiff + 1 > VM_GCL_MAX) { c->err = "maxdiff too large"; return VM_ERR_ARG; }
     std::vector<double> gcl;
     vm_host_gapcost(p.kmersize, p.maxdiff, p.variant != 0, gcl);
     VM_CUDA_OK(c, s.gcl.ensure(gcl.size() * sizeof(double)));
     VM_CUDA_OK(c, cudaMemcpyAsync(s.gcl.p, gcl.data(), gcl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     A.rgcost = nullptr;
     A.n_rg = 0;
+    std::vector<float> rg;
     if (p.variant == 1) {
         A.rgcost = c->readgapcost.as<float>();
         A.n_rg = (int)c->n_readgapcost;
     } else if (p.variant == 2) {
         if (p.maxgap + 1 > VM_RGL_MAX) { c->err = "maxgap too large for the local DP"; return VM_ERR_ARG; }
-        std::vector<float> rg;
         vm_host_large_readgap(p.maxgap, p.large_readgap, rg);
         VM_CUDA_OK(c, s.rgl.ensure(rg.size() * sizeof(float)));
         VM_CUDA_OK(c, cudaMemcpyAsync(s.rgl.p, rg.data(), rg.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -128,6 +126,7 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, VmChainArgs &A)
     VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     A.anchors = s.sorted.as<VmAnchor>();
     A.off = s.off_dev.as<int64_t>();
+    A.cnt = s.cnt_dev.as<int32_t>();
     A.S = s.S.as<double>();
     A.P = s.P.as<int32_t>();
     A.S_arg = s.S_arg.as<int32_t>();
@@ -142,6 +141,132 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, VmChainArgs &A)
     A.maxdiff = p.maxdiff;
     A.maxgap = p.maxgap;
     A.max_factor = p.max_factor;
+    return VM_OK;
+}
+
+// Chaining core on DEVICE input: unsorted anchors of read r at d_anch[start[r] .. start[r]+cnt[r]).
+// Runs argsort replay + exact DP (+ fast DP where hit2work_1 / the local DP would) for the reads in
+// `ids`; results land in s.sorted / s.S / s.P / s.S_arg (same offsets) and s.gmax[r].  The device
+// copies of start/cnt must already be in s.off_dev / s.cnt_dev (vm_chain_prepare).  cnt_len[r] bounds
+// the integer score of a chain of read r (sizes the fast DP's per-score counters).
+int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch, const std::vector<int64_t> &start,
+                  const std::vector<int32_t> &cnt, const std::vector<int32_t> &read_len, const std::vector<int32_t> &cnt_len,
+                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4)
+{
+    (void)start;
+    VmChainState &s = c->chain;
+    VmChainArgs A;
+    int rc = vm_chain_args(c, s, prm, A);
+    if (rc != VM_OK) return rc;
+    const bool by_end = prm.variant != 0;
+    std::vector<std::vector<int>> cls(kNumCaps + 1);
+    std::vector<int> fast_ids;
+    bool may_bail = false;
+    for (int r : ids) {
+        const int64_t n = cnt[r];
+        if (n <= 0) continue;
+        // hit2work_1 :23570 -- n / read_len > 5 goes straight to the fast DP (global only)
+        if (!by_end && (double)n / (double)read_len[r] > 5.0) { fast_ids.push_back(r); continue; }
+        int k = 0;
+        while (k < kNumCaps && n > kCaps[k]) ++k;
+        cls[k].push_back(r);
+        // global: opcount/i > 1000 needs i > 2000; local: opcount > 100000 needs n(n-1)/2 > 100000
+        if (by_end ? n > 440 : n > 2000) may_bail = true;
+    }
+    std::vector<int> ids_host;
+    std::vector<int> cls_start(kNumCaps + 2, 0);
+    for (int k = 0; k <= kNumCaps; ++k) {
+        cls_start[k] = (int)ids_host.size();
+        ids_host.insert(ids_host.end(), cls[k].begin(), cls[k].end());
+    }
+    cls_start[kNumCaps + 1] = (int)ids_host.size();
+    const int n_exact = (int)ids_host.size();
+    ids_host.insert(ids_host.end(), fast_ids.begin(), fast_ids.end());   // fast-path reads still need sorting
+    VM_CUDA_OK(c, s.ids.ensure(ids_host.size() * 4 + 64));
+    if (!ids_host.empty())
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.ids.p, ids_host.data(), ids_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
+
+    cudaEvent_t *ev = c->ev;
+    VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
+    for (int k = 0; k <= kNumCaps; ++k) {
+        const int n_k = cls_start[k + 1] - cls_start[k];
+        if (n_k == 0) continue;
+        const bool smem = k < kNumCaps && kCaps[k] <= VM_SORT_SMEM_CAP;
+        c->launches += vm_launch_sort_anchors(d_anch, s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(),
+                                              s.ids.as<int>() + cls_start[k], n_k, smem ? kCaps[k] : 0, smem, by_end ? 1 : 0,
+                                              s.perm.as<int32_t>(), s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(),
+                                              sorted_rows_dev, c->stream);
+    }
+    if (!fast_ids.empty())
+        c->launches += vm_launch_sort_anchors(d_anch, s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(), s.ids.as<int>() + n_exact,
+                                              (int)fast_ids.size(), 0, false, by_end ? 1 : 0, s.perm.as<int32_t>(),
+                                              s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(), sorted_rows_dev, c->stream);
+    VM_CUDA_OK(c, cudaEventRecord(ev[2], c->stream));
+    for (int k = 0; k <= kNumCaps; ++k) {
+        const int n_k = cls_start[k + 1] - cls_start[k];
+        if (n_k == 0) continue;
+        const bool smem = k < kNumCaps;
+        c->launches += vm_launch_chain_exact(prm.variant, A, s.ids.as<int>() + cls_start[k], n_k, smem ? kCaps[k] : 0, smem,
+                                             c->stream);
+    }
+    VM_CUDA_OK(c, cudaEventRecord(ev[3], c->stream));
+    // reads whose exact DP bailed out (opcount rule) join the fast list
+    if (may_bail) {
+        s.gmax_host.resize(cnt.size());
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.gmax_host.data(), s.gmax.p, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        for (int t = 0; t < n_exact; ++t)
+            if (s.gmax_host[ids_host[t]] < 0) fast_ids.push_back(ids_host[t]);
+    }
+    if (!fast_ids.empty()) {
+        std::vector<int64_t> soff(fast_ids.size() + 1, 0);
+        for (size_t t = 0; t < fast_ids.size(); ++t) {
+            const int r = fast_ids[t];
+            soff[t + 1] = soff[t] + 2LL * cnt[r] + (int64_t)cnt_len[r] + 64;
+            if (used_fast) (*used_fast)[r] = 1;
+        }
+        VM_CUDA_OK(c, s.fast_scratch.ensure((size_t)soff.back() * 8));
+        VM_CUDA_OK(c, s.fast_off.ensure(soff.size() * 8 + fast_ids.size() * 4));
+        int *fids_dev = (int *)((char *)s.fast_off.p + soff.size() * 8);
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.fast_off.p, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemcpyAsync(fids_dev, fast_ids.data(), fast_ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        c->launches += vm_launch_chain_fast(prm.variant, A, prm.fast_t, fids_dev, (int)fast_ids.size(),
+                                            s.fast_scratch.as<long long>(), s.fast_off.as<int64_t>(), c->stream);
+        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));   // soff / fast_ids are stack-lifetime staging
+    }
+    VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
+    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, cudaGetLastError());
+    if (ms4) {
+        ms4[0] = 0;
+        for (int t = 1; t < 4; ++t) cudaEventElapsedTime(&ms4[t], ev[t], ev[t + 1]);
+    }
+    return VM_OK;
+}
+
+// size the chaining state for `span` anchor slots and `n_reads` reads; upload start / cnt
+int vm_chain_prepare(vm_ctx *c, int64_t n_reads, int64_t span, const std::vector<int64_t> &start, const std::vector<int32_t> &cnt,
+                     bool want_rows)
+{
+    VmChainState &s = c->chain;
+    const size_t T = (size_t)std::max<int64_t>(span, 1);
+    VM_CUDA_OK(c, s.off_dev.ensure((size_t)(n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.cnt_dev.ensure((size_t)(n_reads + 1) * 4));
+    VM_CUDA_OK(c, s.perm.ensure(T * 4));
+    VM_CUDA_OK(c, s.sorted.ensure(T * 16));
+    if (want_rows) VM_CUDA_OK(c, s.sorted_rows.ensure(T * 32));
+    VM_CUDA_OK(c, s.S.ensure(T * 8));
+    VM_CUDA_OK(c, s.P.ensure(T * 4));
+    VM_CUDA_OK(c, s.S_arg.ensure(T * 4));
+    VM_CUDA_OK(c, s.gmax.ensure((size_t)(n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.opcount.ensure((size_t)(n_reads + 1) * 8));
+    VM_CUDA_OK(c, s.sort_scratch.ensure(T * 12));
+    if (n_reads > 0) {
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.off_dev.p, start.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.cnt_dev.p, cnt.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemsetAsync(s.gmax.p, 0xff, (size_t)n_reads * 8, c->stream));   // -1: not chained
+        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    }
     return VM_OK;
 }
 
@@ -168,28 +293,20 @@ int vm_chain_global_upload(vm_ctx *c, const vm_chain_params *prm, int64_t n_read
     // the fast DP indexes a per-score counter by integer chain score (<= last read position + k):
     // size it from the larger of the declared read length and the largest anchor end actually present
     s.cnt_len.assign(n_reads, 0);
+    s.cnt.assign(n_reads, 0);
     for (int64_t r = 0; r < n_reads; ++r) {
         int64_t mx = 0;
         for (int64_t t = off[r]; t < off[r + 1]; ++t) mx = std::max(mx, anchors[t * 4] + anchors[t * 4 + 3]);
         s.cnt_len[r] = (int32_t)std::min<int64_t>(std::max<int64_t>(mx, s.read_len[r]), INT32_MAX - 128);
+        s.cnt[r] = (int32_t)(off[r + 1] - off[r]);
     }
     const size_t T = (size_t)std::max<int64_t>(s.total, 1);
     VM_CUDA_OK(c, s.rows.ensure(T * 32));
-    VM_CUDA_OK(c, s.off_dev.ensure((n_reads + 1) * 8));
     VM_CUDA_OK(c, s.anch.ensure(T * 16));
-    VM_CUDA_OK(c, s.perm.ensure(T * 4));
-    VM_CUDA_OK(c, s.sorted.ensure(T * 16));
-    VM_CUDA_OK(c, s.sorted_rows.ensure(T * 32));
-    VM_CUDA_OK(c, s.S.ensure(T * 8));
-    VM_CUDA_OK(c, s.P.ensure(T * 4));
-    VM_CUDA_OK(c, s.S_arg.ensure(T * 4));
-    VM_CUDA_OK(c, s.gmax.ensure((n_reads + 1) * 8));
-    VM_CUDA_OK(c, s.opcount.ensure((n_reads + 1) * 8));
-    VM_CUDA_OK(c, s.ids.ensure((n_reads + 1) * 4 * 2));
-    VM_CUDA_OK(c, s.sort_scratch.ensure(T * 12));
+    int rc = vm_chain_prepare(c, n_reads, s.total, s.off, s.cnt, true);
+    if (rc != VM_OK) return rc;
     if (s.total > 0)
         VM_CUDA_OK(c, cudaMemcpyAsync(s.rows.p, anchors, (size_t)s.total * 32, cudaMemcpyHostToDevice, c->stream));
-    VM_CUDA_OK(c, cudaMemcpyAsync(s.off_dev.p, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     s.loaded = true;
     return VM_OK;
@@ -201,100 +318,18 @@ int vm_chain_global_run(vm_ctx *c, float *kernel_ms)
     VmChainState &s = c->chain;
     if (!s.loaded) { c->err = "vm_chain_global_upload first"; return VM_ERR_STATE; }
     cudaSetDevice(c->device);
-    VmChainArgs A;
-    int rc = vm_chain_args(c, s, A);
-    if (rc != VM_OK) return rc;
     const int n_reads = (int)s.n_reads;
-    const bool by_end = s.prm.variant != 0;
     s.used_fast.assign(n_reads, 0);
-
-    // class binning on the host: which reads go to which smem capacity / fast path
-    std::vector<std::vector<int>> cls(kNumCaps + 1);
-    std::vector<int> fast_ids;
-    bool may_bail = false;
-    for (int r = 0; r < n_reads; ++r) {
-        const int64_t n = s.off[r + 1] - s.off[r];
-        if (n <= 0) continue;
-        // hit2work_1 :23570 -- n / read_len > 5 goes straight to the fast DP (global only)
-        if (!by_end && (double)n / (double)s.read_len[r] > 5.0) { fast_ids.push_back(r); continue; }
-        int k = 0;
-        while (k < kNumCaps && n > kCaps[k]) ++k;
-        cls[k].push_back(r);
-        if (n > 2000) may_bail = true;   // opcount/i > 1000 needs i > 2000 (global); local needs opcount > 1e5
-    }
-
-    // read ids grouped by capacity class (shared by the sort and DP launches)
-    std::vector<int> ids_host;
-    std::vector<int> cls_start(kNumCaps + 2, 0);
-    for (int k = 0; k <= kNumCaps; ++k) {
-        cls_start[k] = (int)ids_host.size();
-        ids_host.insert(ids_host.end(), cls[k].begin(), cls[k].end());
-    }
-    cls_start[kNumCaps + 1] = (int)ids_host.size();
-    const int n_exact = (int)ids_host.size();
-    ids_host.insert(ids_host.end(), fast_ids.begin(), fast_ids.end());   // fast-path reads still need sorting
-    if (!ids_host.empty())
-        VM_CUDA_OK(c, cudaMemcpyAsync(s.ids.p, ids_host.data(), ids_host.size() * 4, cudaMemcpyHostToDevice, c->stream));
-
-    cudaEvent_t *ev = c->ev;
-    VM_CUDA_OK(c, cudaEventRecord(ev[0], c->stream));
+    std::vector<int> ids(n_reads);
+    for (int r = 0; r < n_reads; ++r) ids[r] = r;
+    VM_CUDA_OK(c, cudaEventRecord(c->ev[0], c->stream));
     c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
-    VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
-    for (int k = 0; k <= kNumCaps; ++k) {
-        const int cnt = cls_start[k + 1] - cls_start[k];
-        if (cnt == 0) continue;
-        const bool smem = k < kNumCaps && kCaps[k] <= VM_SORT_SMEM_CAP;
-        c->launches += vm_launch_sort_anchors(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(),
-                                              s.ids.as<int>() + cls_start[k], cnt, smem ? kCaps[k] : 0, smem,
-                                              by_end ? 1 : 0, s.perm.as<int32_t>(), s.sort_scratch.as<int32_t>(),
-                                              s.sorted.as<VmAnchor>(), s.sorted_rows.as<int64_t>(), c->stream);
-    }
-    if (!fast_ids.empty())
-        c->launches += vm_launch_sort_anchors(s.anch.as<VmAnchor>(), s.off_dev.as<int64_t>(), s.ids.as<int>() + n_exact,
-                                              (int)fast_ids.size(), 0, false, by_end ? 1 : 0, s.perm.as<int32_t>(),
-                                              s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(),
-                                              s.sorted_rows.as<int64_t>(), c->stream);
-    VM_CUDA_OK(c, cudaEventRecord(ev[2], c->stream));
-
-    // exact DP, one launch per capacity class
-    for (int k = 0; k <= kNumCaps; ++k) {
-        const int cnt = cls_start[k + 1] - cls_start[k];
-        if (cnt == 0) continue;
-        const bool smem = k < kNumCaps;
-        c->launches += vm_launch_chain_exact(s.prm.variant, A, s.ids.as<int>() + cls_start[k], cnt,
-                                             smem ? kCaps[k] : 0, smem, c->stream);
-    }
-    VM_CUDA_OK(c, cudaEventRecord(ev[3], c->stream));
-
-    // reads whose exact DP bailed out (opcount rule) join the fast list
-    if (may_bail) {
-        std::vector<int64_t> g(n_reads);
-        VM_CUDA_OK(c, cudaMemcpyAsync(g.data(), s.gmax.p, (size_t)n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
-        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-        for (int t = 0; t < n_exact; ++t)
-            if (g[ids_host[t]] < 0) fast_ids.push_back(ids_host[t]);
-    }
-    if (!fast_ids.empty()) {
-        std::vector<int64_t> soff(fast_ids.size() + 1, 0);
-        for (size_t t = 0; t < fast_ids.size(); ++t) {
-            const int r = fast_ids[t];
-            const int64_t n = s.off[r + 1] - s.off[r];
-            soff[t + 1] = soff[t] + 2 * n + (int64_t)s.cnt_len[r] + 64;
-            s.used_fast[r] = 1;
-        }
-        VM_CUDA_OK(c, s.fast_scratch.ensure((size_t)soff.back() * 8));
-        VM_CUDA_OK(c, s.fast_off.ensure(soff.size() * 8 + fast_ids.size() * 4));
-        int *fids_dev = (int *)((char *)s.fast_off.p + soff.size() * 8);
-        VM_CUDA_OK(c, cudaMemcpyAsync(s.fast_off.p, soff.data(), soff.size() * 8, cudaMemcpyHostToDevice, c->stream));
-        VM_CUDA_OK(c, cudaMemcpyAsync(fids_dev, fast_ids.data(), fast_ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        c->launches += vm_launch_chain_fast(s.prm.variant, A, s.prm.fast_t, fids_dev, (int)fast_ids.size(),
-                                            s.fast_scratch.as<long long>(), s.fast_off.as<int64_t>(), c->stream);
-    }
-    VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
-    VM_CUDA_OK(c, cudaGetLastError());
-    for (int t = 0; t < 4; ++t) cudaEventElapsedTime(&s.ms[t], ev[t], ev[t + 1]);
-    if (kernel_ms) cudaEventElapsedTime(kernel_ms, ev[0], ev[4]);
+    VM_CUDA_OK(c, cudaEventRecord(c->ev[5], c->stream));
+    int rc = vm_chain_core(c, s.prm, s.anch.as<VmAnchor>(), s.off, s.cnt, s.read_len, s.cnt_len, ids, s.sorted_rows.as<int64_t>(),
+                           &s.used_fast, s.ms);
+    if (rc != VM_OK) return rc;
+    cudaEventElapsedTime(&s.ms[0], c->ev[0], c->ev[5]);
+    if (kernel_ms) *kernel_ms = s.ms[0] + s.ms[1] + s.ms[2] + s.ms[3];
     return VM_OK;
 }
 

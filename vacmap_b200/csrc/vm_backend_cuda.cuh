@@ -1,0 +1,487 @@
+// CUDA backend of the batch driver (vm_pipeline.hpp).
+//
+// One instance per vm_ctx, alive for the life of the context: every device arena and pinned
+// staging buffer is reused across batches.  Consecutive hot loops hand their data over on the
+// device (seeding -> sort -> global DP; re-seeding -> concat -> sort -> local DP); the host only
+// receives what its glue needs (sorted anchors, S, P, S_arg, g_max; CIGAR ops compacted on the
+// device) through page-locked buffers.  There is no CPU implementation of any stage here.
+#pragma once
+#include "vm_ctx.cuh"
+#include "vm_chain.cuh"
+#include "vm_index.cuh"
+#include "vm_seed.cuh"
+#include "vm_reseed.cuh"
+#include "vm_align.cuh"
+#include "vm_pipeline.hpp"
+#include <chrono>
+#include <map>
+
+using namespace vmp;
+
+struct vm_index_handle {
+    VmIndex *ix = nullptr;
+    vmg::Contigs ctg;
+};
+
+#define BE_OK(call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess) throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- small plumbing kernels ----
+// reverse complement of every read of the batch (one thread per base)
+__global__ void vm_revcomp_kernel(const uint8_t *__restrict__ fwd, const int64_t *__restrict__ off, int n_reads, int64_t total,
+                                  uint8_t *__restrict__ rc)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int lo = 0, hi = n_reads;   // read containing base i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int64_t b = off[lo], e = off[lo + 1];
+    const uint8_t ch = fwd[e - 1 - (i - b)];
+    rc[i] = ch == 'A' ? 'T' : ch == 'C' ? 'G' : ch == 'G' ? 'C' : ch == 'T' ? 'A' : 'N';
+}
+
+// gather variable-length segments: segment j = src[src_off[j] .. +len[j]) -> dst[dst_off[j] ..)
+template <typename T>
+__global__ void vm_gather_segments_kernel(const T *__restrict__ src, const int64_t *__restrict__ src_off,
+                                          const int64_t *__restrict__ dst_off, const int32_t *__restrict__ len,
+                                          T *__restrict__ dst)
+{
+    const int j = blockIdx.x;
+    const int n = len[j];
+    const T *s = src + src_off[j];
+    T *d = dst + dst_off[j];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) d[t] = s[t];
+}
+
+namespace {
+
+struct StageTimer {
+    std::map<std::string, double> ms;
+    void add(const char *k, double v) { ms[k] += v; }
+};
+
+class CudaBackend : public Backend {
+public:
+    CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih) {}
+    ~CudaBackend() override
+    {
+        seed_.release();
+        VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
+                         &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_};
+        for (VmDevBuf *x : b) x->release();
+        VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_};
+        for (VmPinnedBuf *x : p) x->release();
+    }
+    StageTimer timer;
+    bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
+    void set_index(vm_index_handle *ih) { ih_ = ih; }
+    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0;
+    void reset_counters()
+    {
+        timer.ms.clear();
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = 0;
+    }
+
+    // device time of a group of launches, CUDA events on the ctx stream
+    struct KTimer {
+        CudaBackend *be; const char *name; cudaEvent_t a, b;
+        KTimer(CudaBackend *be_, const char *n) : be(be_), name(n)
+        {
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventRecord(a, be->c_->stream);
+        }
+        void stop()
+        {
+            cudaEventRecord(b, be->c_->stream);
+            cudaEventSynchronize(b);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, a, b);
+            be->timer.add(name, ms);
+            cudaEventDestroy(a); cudaEventDestroy(b);
+        }
+    };
+    struct WallTimer {
+        CudaBackend *be; const char *name; std::chrono::steady_clock::time_point t0;
+        WallTimer(CudaBackend *b, const char *n) : be(b), name(n), t0(std::chrono::steady_clock::now()) {}
+        ~WallTimer() { be->timer.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+    };
+
+    void upload_reads(const ReadBatch &b)
+    {
+        if (reads_resident && off_host_.size() == (size_t)b.n + 1 && std::equal(off_host_.begin(), off_host_.end(), b.off)) return;
+        const size_t total = (size_t)b.off[b.n];
+        BE_OK(reads_fwd_.ensure(total + 64));
+        BE_OK(reads_rc_.ensure(total + 64));
+        BE_OK(read_off_.ensure((size_t)(b.n + 1) * 8));
+        BE_OK(cudaMemcpyAsync(reads_fwd_.p, b.seq, total, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(read_off_.p, b.off, (size_t)(b.n + 1) * 8, cudaMemcpyHostToDevice, c_->stream));
+        if (total > 0) {
+            vm_revcomp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c_->stream>>>(reads_fwd_.as<uint8_t>(), read_off_.as<int64_t>(),
+                                                                                      (int)b.n, (int64_t)total, reads_rc_.as<uint8_t>());
+            c_->launches += 1;
+        }
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        off_host_.assign(b.off, b.off + b.n + 1);
+    }
+
+    // ---- seeding + global chaining, anchors never leave the device in between ----
+    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+                    std::vector<char> &need_reverse, ChainOut &out) override
+    {
+        WallTimer wt(this, "seed_chain");
+        upload_reads(b);
+        std::vector<int32_t> n_out, nrev;
+        std::vector<int64_t> a_off;
+        std::string err;
+        {
+            KTimer kt(this, "k_seed");
+            if (vm_seed_batch(seed_, ih_->ix->dev, reads_fwd_.as<uint8_t>(), read_off_.as<int64_t>(), off_host_, check_num, -1,
+                              c_->stream, n_out, nrev, a_off, &c_->launches, err))
+                throw std::runtime_error(err);
+            kt.stop();
+        }
+        const int64_t n = b.n;
+        need_reverse.assign((size_t)n, 0);
+        for (int64_t r = 0; r < n; ++r) need_reverse[r] = (char)nrev[r];
+        out = ChainOut();
+        out.start.assign(a_off.begin(), a_off.begin() + n);
+        out.cnt = n_out;
+        out.gmax.assign((size_t)n, -1);
+        const int64_t span = a_off[n];
+        chain_anchors_ += (double)span;
+        std::vector<int32_t> rl((size_t)n);
+        std::vector<int> ids;
+        for (int64_t r = 0; r < n; ++r) {
+            rl[r] = (int32_t)std::min<int64_t>(b.len(r), INT32_MAX - 128);
+            if (n_out[r] > 2) ids.push_back((int)r);      // decode_hit :23986 -- <= 2 anchors: unmapped, not chained
+        }
+        vm_chain_params prm{kmersize, skipcost, maxdiff, maxgap, 1000, 5, 30, 0};
+        if (vm_chain_prepare(c_, n, span, out.start, out.cnt, false) != VM_OK) throw std::runtime_error("chain: " + c_->err);
+        float ms4[4] = {0, 0, 0, 0};
+        if (vm_chain_core(c_, prm, seed_.out.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, nullptr, ms4) != VM_OK)
+            throw std::runtime_error("chain: " + c_->err);
+        timer.add("chain_global_kernels", ms4[1] + ms4[2] + ms4[3]);
+        VmChainState &s = c_->chain;
+        const size_t T = (size_t)std::max<int64_t>(span, 1);
+        BE_OK(h_sorted_.ensure(T * 16));
+        BE_OK(h_S_.ensure(T * 8));
+        BE_OK(h_P_.ensure(T * 4));
+        BE_OK(h_A_.ensure(T * 4));
+        BE_OK(h_gmax_.ensure((size_t)(n + 1) * 8));
+        if (span > 0) {
+            BE_OK(cudaMemcpyAsync(h_sorted_.p, s.sorted.p, (size_t)span * 16, cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaMemcpyAsync(h_S_.p, s.S.p, (size_t)span * 8, cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaMemcpyAsync(h_P_.p, s.P.p, (size_t)span * 4, cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaMemcpyAsync(h_A_.p, s.S_arg.p, (size_t)span * 4, cudaMemcpyDeviceToHost, c_->stream));
+        }
+        if (n > 0) BE_OK(cudaMemcpyAsync(h_gmax_.p, s.gmax.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        out.sorted = h_sorted_.as<Anc32>();
+        out.S = h_S_.as<double>();
+        out.P = h_P_.as<int32_t>();
+        out.S_arg = h_A_.as<int32_t>();
+        for (int64_t r = 0; r < n; ++r) out.gmax[r] = h_gmax_.as<int64_t>()[r];
+    }
+
+    // ---- local re-seeding + local chaining ----
+    void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                      const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                      ChainOut &out) override
+    {
+        WallTimer wt(this, "reseed_chain");
+        const int64_t n = b.n;
+        const int nj = (int)jobs.size();
+        out = ChainOut();
+        out.start.assign((size_t)n, 0);
+        out.cnt.assign((size_t)n, 0);
+        out.gmax.assign((size_t)n, -1);
+        if (nj == 0) return;
+        std::vector<VmReseedJobDev> J((size_t)nj);
+        std::vector<int64_t> wlo, whi, gy;
+        std::vector<int32_t> gx;
+        for (int j = 0; j < nj; ++j) {
+            const vmg::GuideJob &g = jobs[j].job;
+            VmReseedJobDev &d = J[j];
+            memset(&d, 0, sizeof(d));
+            d.read = jobs[j].read;
+            d.need_reverse = need_reverse[jobs[j].read] ? 1 : 0;
+            d.readstart = g.readstart;
+            d.readend = g.readend;
+            d.n_win = (int32_t)g.win_lo.size();
+            d.n_guide = (int32_t)g.gx.size();
+            d.win_off = (int64_t)wlo.size();
+            d.g_off = (int64_t)gx.size();
+            wlo.insert(wlo.end(), g.win_lo.begin(), g.win_lo.end());
+            whi.insert(whi.end(), g.win_hi.begin(), g.win_hi.end());
+            gx.insert(gx.end(), g.gx.begin(), g.gx.end());
+            gy.insert(gy.end(), g.gy.begin(), g.gy.end());
+            d.count_only = 1;
+        }
+        BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev)));
+        BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
+        BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
+        BE_OK(d_gx_.ensure(gx.size() * 4 + 64));
+        BE_OK(d_gy_.ensure(gy.size() * 8 + 64));
+        BE_OK(d_nh_.ensure((size_t)nj * 8 + 64));
+        BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_wlo_.p, wlo.data(), wlo.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gx_.p, gx.data(), gx.size() * 4, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gy_.p, gy.data(), gy.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        int32_t *d_n_hits = d_nh_.as<int32_t>(), *d_over = d_nh_.as<int32_t>() + nj, *d_n_out = d_nh_.as<int32_t>() + nj + 1;
+        BE_OK(cudaMemsetAsync(d_over, 0, 4, c_->stream));
+        const VmIndexDev &ix = ih_->ix->dev;
+        // pass 1: count hits per job
+        {
+            KTimer kt(this, "k_reseed_hits");
+            c_->launches += vm_reseed_launch(ix, jobs_.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
+                                             read_off_.as<int64_t>(), d_wlo_.as<int64_t>(), d_whi_.as<int64_t>(),
+                                             d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), nullptr, d_n_hits, d_over, nullptr, nullptr,
+                                             nullptr, nullptr, c_->stream);
+            kt.stop();
+        }
+        std::vector<int32_t> n_hits((size_t)nj);
+        BE_OK(cudaMemcpyAsync(n_hits.data(), d_n_hits, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        int64_t hit_off = 0, tab_off = 0;
+        for (int j = 0; j < nj; ++j) {
+            J[j].count_only = 0;
+            J[j].hit_off = hit_off;
+            J[j].hit_cap = n_hits[j];
+            hit_off += n_hits[j];
+            int ts = 64;
+            while (ts < n_hits[j] + 8) ts <<= 1;
+            J[j].tab_off = tab_off;
+            J[j].tab_size = ts;
+            tab_off += ts;
+        }
+        reseed_hits_ += (double)hit_off;
+        BE_OK(d_hits_.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
+        BE_OK(d_tab_.ensure((size_t)tab_off * vm_reseed_point_bytes() + 64));
+        BE_OK(d_order_.ensure((size_t)hit_off * 4 + 64));
+        BE_OK(d_rout_.ensure((size_t)hit_off * 2 * sizeof(VmAnchor) + 64));
+        BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
+        {
+            KTimer kt(this, "k_reseed_hits");
+            c_->launches += vm_reseed_launch(ix, jobs_.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
+                                             read_off_.as<int64_t>(), d_wlo_.as<int64_t>(), d_whi_.as<int64_t>(),
+                                             d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), d_hits_.p, d_n_hits, d_over, nullptr, nullptr,
+                                             nullptr, nullptr, c_->stream);
+            kt.stop();
+        }
+        {
+            KTimer kt(this, "k_reseed_merge");
+            c_->launches += vm_reseed_merge_launch(jobs_.as<VmReseedJobDev>(), nj, d_hits_.p, d_n_hits, d_tab_.p,
+                                                   d_order_.as<int32_t>(), d_rout_.as<VmAnchor>(), d_n_out, c_->stream);
+            kt.stop();
+        }
+        std::vector<int32_t> n_out((size_t)nj), over(1);
+        BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaMemcpyAsync(over.data(), d_over, 4, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        if (over[0]) throw std::runtime_error("reseed: hit buffer overflow (count and fill passes disagree)");
+        // concatenate the jobs of each read into one dense anchor list on the device
+        std::vector<int64_t> seg(2 * (size_t)nj);   // [src_off | dst_off]
+        int64_t dense = 0;
+        {
+            size_t q = 0;
+            for (int64_t r = 0; r < n; ++r) {
+                out.start[r] = dense;
+                while (q < jobs.size() && jobs[q].read == r) {
+                    seg[q] = 2 * J[q].hit_off;
+                    seg[(size_t)nj + q] = dense;
+                    dense += n_out[q];
+                    ++q;
+                }
+                out.cnt[r] = variant[r] ? (int32_t)(dense - out.start[r]) : 0;
+            }
+        }
+        BE_OK(d_dense_.ensure((size_t)std::max<int64_t>(dense, 1) * sizeof(VmAnchor)));
+        BE_OK(d_seg_.ensure(seg.size() * 8 + 64));
+        BE_OK(cudaMemcpyAsync(d_seg_.p, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        vm_gather_segments_kernel<VmAnchor><<<nj, 128, 0, c_->stream>>>(d_rout_.as<VmAnchor>(), d_seg_.as<int64_t>(),
+                                                                        d_seg_.as<int64_t>() + nj, d_n_out, d_dense_.as<VmAnchor>());
+        c_->launches += 1;
+        chain_anchors_ += (double)dense;
+        // local DP per (variant, skipcost) group
+        if (vm_chain_prepare(c_, n, dense, out.start, out.cnt, false) != VM_OK) throw std::runtime_error("chain: " + c_->err);
+        std::map<std::pair<int, double>, std::vector<int>> groups;
+        std::vector<int32_t> rl((size_t)n);
+        for (int64_t r = 0; r < n; ++r) {
+            rl[r] = (int32_t)std::min<int64_t>(b.len(r) + 64, INT32_MAX - 128);
+            if (variant[r] != 0 && out.cnt[r] > 0) groups[{variant[r], skipcost[r]}].push_back((int)r);
+        }
+        for (auto &g : groups) {
+            vm_chain_params prm{9, g.first.second, maxdiff, maxgap, 1000, 5, 30, g.first.first};
+            float ms4[4] = {0, 0, 0, 0};
+            if (vm_chain_core(c_, prm, d_dense_.as<VmAnchor>(), out.start, out.cnt, rl, rl, g.second, nullptr, nullptr, ms4) != VM_OK)
+                throw std::runtime_error("chain: " + c_->err);
+            timer.add("chain_local_kernels", ms4[1] + ms4[2] + ms4[3]);
+        }
+        VmChainState &s = c_->chain;
+        const size_t T = (size_t)std::max<int64_t>(dense, 1);
+        BE_OK(h_lsorted_.ensure(T * 16));
+        BE_OK(h_lP_.ensure(T * 4));
+        BE_OK(h_lgmax_.ensure((size_t)(n + 1) * 8));
+        if (dense > 0) {
+            BE_OK(cudaMemcpyAsync(h_lsorted_.p, s.sorted.p, (size_t)dense * 16, cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaMemcpyAsync(h_lP_.p, s.P.p, (size_t)dense * 4, cudaMemcpyDeviceToHost, c_->stream));
+        }
+        BE_OK(cudaMemcpyAsync(h_lgmax_.p, s.gmax.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(cudaGetLastError());
+        out.sorted = h_lsorted_.as<Anc32>();
+        out.P = h_lP_.as<int32_t>();
+        for (int64_t r = 0; r < n; ++r) out.gmax[r] = h_lgmax_.as<int64_t>()[r];
+    }
+
+    static VmSeqSpec spec(const vmg::SeqRef &s)
+    {
+        VmSeqSpec d;
+        d.lo = s.lo;
+        d.len = (int32_t)(s.hi - s.lo);
+        d.src = s.src;
+        d.reverse = s.reverse;
+        d.comp = s.comp;
+        return d;
+    }
+
+    VmSeqSources sources() const
+    {
+        VmSeqSources S;
+        S.ref = ih_ ? ih_->ix->dev.ref : nullptr;
+        S.reads_fwd = reads_fwd_.as<uint8_t>();
+        S.reads_rc = reads_rc_.as<uint8_t>();
+        S.read_off = read_off_.as<int64_t>();
+        return S;
+    }
+
+    VmAlnJobDev *stage_jobs(size_t nj)
+    {
+        BE_OK(h_jobs_.ensure(nj * sizeof(VmAlnJobDev) + 64));
+        BE_OK(jobs_.ensure(nj * sizeof(VmAlnJobDev) + 64));
+        return h_jobs_.as<VmAlnJobDev>();
+    }
+
+    void edit_distance(const ReadBatch &, std::vector<EdJob> &jobs) override
+    {
+        WallTimer wt(this, "edit_distance");
+        const int nj = (int)jobs.size();
+        if (nj == 0) return;
+        VmAlnJobDev *J = stage_jobs((size_t)nj);
+        int max_words = 1;
+        for (int j = 0; j < nj; ++j) {
+            memset(&J[j], 0, sizeof(VmAlnJobDev));
+            // the shorter sequence is the bit-vector pattern (fewer 64-row blocks)
+            const bool a_short = jobs[j].a.len() <= jobs[j].b.len();
+            J[j].q = spec(a_short ? jobs[j].a : jobs[j].b);
+            J[j].t = spec(a_short ? jobs[j].b : jobs[j].a);
+            J[j].read = jobs[j].read;
+            max_words = std::max(max_words, (J[j].q.len + 63) / 64);
+            ed_cells_ += (double)J[j].q.len * (double)J[j].t.len;
+        }
+        if (max_words > 32 * 64) throw std::runtime_error("edit distance: sequence longer than 131072 bases is not supported yet");
+        BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_edit_distance");
+        c_->launches += vm_launch_edit_distance(jobs_.as<VmAlnJobDev>(), nj, sources(), max_words, c_->stream);
+        kt.stop();
+        BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(cudaGetLastError());
+        for (int j = 0; j < nj; ++j) jobs[j].dist = J[j].result0;
+    }
+
+    void extend(const ReadBatch &, std::vector<ExtJobRef> &jobs) override
+    {
+        WallTimer wt(this, "extend");
+        const int nj = (int)jobs.size();
+        if (nj == 0) return;
+        VmAlnJobDev *J = stage_jobs((size_t)nj);
+        for (int j = 0; j < nj; ++j) {
+            memset(&J[j], 0, sizeof(VmAlnJobDev));
+            J[j].t = spec(jobs[j].job.target);
+            J[j].q = spec(jobs[j].job.query);
+            J[j].read = jobs[j].read;
+        }
+        BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_extend");
+        c_->launches += vm_launch_extend(jobs_.as<VmAlnJobDev>(), nj, sources(), c_->stream);
+        kt.stop();
+        BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(cudaGetLastError());
+        for (int j = 0; j < nj; ++j) { jobs[j].job.q_e = (int32_t)J[j].result0; jobs[j].job.t_e = (int32_t)J[j].result1; }
+    }
+
+    void fill(const ReadBatch &, bool eqx, std::vector<FillJobRef> &jobs) override
+    {
+        WallTimer wt(this, "fill");
+        const int nj = (int)jobs.size();
+        if (nj == 0) return;
+        VmAlnJobDev *J = stage_jobs((size_t)nj);
+        int64_t out_off = 0, dir_off = 0, sc_off = 0;
+        const int band_rows = vm_fill_band_rows();
+        for (int j = 0; j < nj; ++j) {
+            memset(&J[j], 0, sizeof(VmAlnJobDev));
+            J[j].t = spec(jobs[j].job.target);
+            J[j].q = spec(jobs[j].job.query);
+            J[j].read = jobs[j].read;
+            J[j].out_off = out_off;
+            J[j].dir_off = dir_off;
+            out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
+            dir_off += (int64_t)((vm_fill_dir_bytes(J[j].t.len, J[j].q.len) + 7) & ~(size_t)7);
+            if (J[j].t.len > band_rows) { J[j].sc_off = sc_off; sc_off += 3LL * J[j].q.len; }
+            else J[j].sc_off = -1;
+            fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;
+            fill_bases_ += (double)J[j].t.len + (double)J[j].q.len;
+        }
+        fill_jobs_ += nj;
+        BE_OK(d_dir_.ensure((size_t)dir_off + 64));
+        BE_OK(d_sc_.ensure((size_t)sc_off * 4 + 64));
+        BE_OK(d_cig_.ensure((size_t)out_off * 4 + 64));
+        BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        KTimer kt(this, "k_fill");
+        c_->launches += vm_launch_fill(jobs_.as<VmAlnJobDev>(), nj, sources(), eqx ? 1 : 0, d_dir_.as<uint8_t>(), d_sc_.as<int32_t>(),
+                                       d_cig_.as<uint32_t>(), c_->stream);
+        kt.stop();
+        BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(cudaGetLastError());
+        // compact the CIGAR ops on the device, then one dense D2H
+        BE_OK(h_misc_.ensure((size_t)nj * 20 + 64));
+        int64_t *src_off = h_misc_.as<int64_t>(), *dst_off = src_off + nj;
+        int32_t *len = (int32_t *)(dst_off + nj);
+        int64_t dense = 0;
+        for (int j = 0; j < nj; ++j) { src_off[j] = J[j].out_off; dst_off[j] = dense; len[j] = J[j].n_out; dense += J[j].n_out; }
+        BE_OK(d_seg_.ensure((size_t)nj * 20 + 64));
+        BE_OK(d_cigd_.ensure((size_t)std::max<int64_t>(dense, 1) * 4));
+        BE_OK(h_cig_.ensure((size_t)std::max<int64_t>(dense, 1) * 4));
+        BE_OK(cudaMemcpyAsync(d_seg_.p, h_misc_.p, (size_t)nj * 20, cudaMemcpyHostToDevice, c_->stream));
+        const int64_t *dseg = d_seg_.as<int64_t>();
+        vm_gather_segments_kernel<uint32_t><<<nj, 32, 0, c_->stream>>>(d_cig_.as<uint32_t>(), dseg, dseg + nj,
+                                                                      (const int32_t *)(dseg + 2 * nj), d_cigd_.as<uint32_t>());
+        c_->launches += 1;
+        if (dense > 0) BE_OK(cudaMemcpyAsync(h_cig_.p, d_cigd_.p, (size_t)dense * 4, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(cudaGetLastError());
+        const uint32_t *cig = h_cig_.as<uint32_t>();
+        for (int j = 0; j < nj; ++j) jobs[j].cigar.assign(cig + dst_off[j], cig + dst_off[j] + len[j]);
+    }
+
+private:
+    vm_ctx *c_;
+    vm_index_handle *ih_;
+    VmSeedBufs seed_;
+    VmDevBuf reads_fwd_, reads_rc_, read_off_, jobs_, d_wlo_, d_whi_, d_gx_, d_gy_, d_nh_, d_hits_, d_tab_, d_order_, d_rout_,
+        d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_;
+    VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_;
+    std::vector<int64_t> off_host_;
+};
+
+} // namespace

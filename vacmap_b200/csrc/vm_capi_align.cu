@@ -1,0 +1,271 @@
+// vm_index_* / vm_align_* / vm_pairs_* C ABI over the CUDA backend (vm_backend_cuda.cuh).
+#include "vm_backend_cuda.cuh"
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+struct vm_result {
+    std::vector<int64_t> rec_off;        // per read
+    std::vector<vm_record> recs;
+    std::vector<uint32_t> cigar;
+    std::vector<double> stage_ms;
+    std::vector<std::string> stage_names;
+    std::string stage_text;
+};
+
+extern "C" {
+
+int vm_index_create(vm_ctx *c, int32_t n_contigs, const char *const *names, const char *const *seqs, const int64_t *lens,
+                    int32_t w, int32_t k, vm_index_handle **out)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!out || n_contigs <= 0 || !names || !seqs || !lens || k < 1 || k > 28 || w < 1 || w > 255) {
+        c->err = "bad argument";
+        return VM_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    std::vector<std::string> nm, sq;
+    for (int i = 0; i < n_contigs; ++i) {
+        nm.emplace_back(names[i]);
+        sq.emplace_back(seqs[i], (size_t)lens[i]);
+    }
+    vm_index_handle *h = new vm_index_handle();
+    h->ix = vm_index_build_host(nm, sq, w, k);
+    if ((int64_t)h->ix->ref.size() >= (1LL << 32) - 64) {
+        c->err = "reference longer than 2^32 bases is not supported";
+        vm_index_free(h->ix);
+        delete h;
+        return VM_ERR_ARG;
+    }
+    std::string err;
+    if (vm_index_upload(h->ix, err)) {
+        c->err = err;
+        vm_index_free(h->ix);
+        delete h;
+        return VM_ERR_CUDA;
+    }
+    h->ctg.names = h->ix->names;
+    h->ctg.start = h->ix->ctg_start;
+    h->ctg.len = h->ix->ctg_len;
+    h->ctg.seq = h->ix->ref.data();
+    h->ctg.total = (int64_t)h->ix->ref.size();
+    *out = h;
+    return VM_OK;
+}
+
+void vm_index_destroy(vm_index_handle *h)
+{
+    if (!h) return;
+    vm_index_free(h->ix);
+    delete h;
+}
+
+int vm_index_info(vm_index_handle *h, int32_t *k, int32_t *w, int32_t *n_contigs, int64_t *n_minimizers, int64_t *n_keys,
+                  int32_t *mid_occ)
+{
+    if (!h) return VM_ERR_ARG;
+    if (k) *k = h->ix->k;
+    if (w) *w = h->ix->w;
+    if (n_contigs) *n_contigs = (int32_t)h->ix->names.size();
+    if (n_minimizers) *n_minimizers = (int64_t)h->ix->occ.size();
+    if (n_keys) *n_keys = h->ix->n_keys;
+    if (mid_occ) *mid_occ = h->ix->mid_occ_default;
+    return VM_OK;
+}
+
+int vm_index_contig(vm_index_handle *h, int32_t i, const char **name, int64_t *start, int64_t *len, const char **seq)
+{
+    if (!h || i < 0 || i >= (int32_t)h->ix->names.size()) return VM_ERR_ARG;
+    if (name) *name = h->ix->names[i].c_str();
+    if (start) *start = h->ix->ctg_start[i];
+    if (len) *len = h->ix->ctg_len[i];
+    if (seq) *seq = h->ix->ref.data() + h->ix->ctg_start[i];
+    return VM_OK;
+}
+
+static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                         const int64_t *seq_off, int resident, vm_result **out)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!h || !p || !out || n_reads < 0 || !seq_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
+    if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    vmg::Options opt;
+    opt.global_skipcost = p->global_skipcost;
+    opt.local_skipcost = p->local_skipcost;
+    opt.maxdivergence = p->maxdivergence;
+    opt.global_maxdiff = p->global_maxdiff;
+    opt.local_maxdiff = p->local_maxdiff;
+    opt.check_num = p->check_num;
+    opt.eqx = p->eqx != 0;
+    opt.hardclip = p->hardclip != 0;
+    opt.nodiscard = p->nodiscard != 0;
+    opt.mode = vmg::ModeConst{p->accept_score, p->max_guides, p->local_maxgap, p->clamp40 != 0};
+    vm_result *res = new vm_result();
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.set_index(h);
+        be.reset_counters();
+        be.reads_resident = resident != 0;
+        int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        Driver drv(be, h->ctg, opt, h->ix->k, threads);
+        ReadBatch b;
+        b.n = n_reads;
+        b.seq = seqs;
+        b.off = seq_off;
+        BatchResult br;
+        auto t0 = std::chrono::steady_clock::now();
+        drv.align_batch(b, br);
+        const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        res->rec_off.assign((size_t)n_reads + 1, 0);
+        for (int64_t r = 0; r < n_reads; ++r) {
+            for (const vmg::Record &rec : br.records[r]) {
+                vm_record o;
+                o.contig = rec.contig;
+                o.strand = rec.strand;
+                o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
+                o.mapq = rec.mapq;
+                o.cigar_off = (int64_t)res->cigar.size();
+                o.cigar_len = (int32_t)rec.cigar.size();
+                res->cigar.insert(res->cigar.end(), rec.cigar.begin(), rec.cigar.end());
+                res->recs.push_back(o);
+            }
+            res->rec_off[r + 1] = (int64_t)res->recs.size();
+        }
+        be.timer.add("total", total);
+        be.timer.add("n_fill_cells", be.fill_cells_);
+        be.timer.add("n_fill_bases", be.fill_bases_);
+        be.timer.add("n_fill_jobs", be.fill_jobs_);
+        be.timer.add("n_ed_cells", be.ed_cells_);
+        be.timer.add("n_reseed_hits", be.reseed_hits_);
+        be.timer.add("n_chain_anchors", be.chain_anchors_);
+        for (auto &kv : be.timer.ms) {
+            res->stage_names.push_back(kv.first);
+            res->stage_ms.push_back(kv.second);
+            res->stage_text += kv.first + "=" + std::to_string(kv.second) + ";";
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        delete res;
+        return VM_ERR_CUDA;
+    }
+    *out = res;
+    return VM_OK;
+}
+
+int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                   const int64_t *seq_off, vm_result **out)
+{
+    return vm_align_impl(c, h, p, n_reads, seqs, seq_off, 0, out);
+}
+
+// Stage-level entry point for the base-level kernels on raw sequence pairs (parity tests).
+// kind 0: global edit distance -> out0[j]; kind 1: z-drop edge extension -> out0 = q_e, out1 = t_e;
+// kind 2: global fill -> CIGAR ops of pair j at cigar[cig_off[j] .. cig_off[j] + out0[j]),
+//         cig_off[j] = sum over i < j of (tlen_i + qlen_i + 2).
+int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const char *targets, const int64_t *t_off,
+                   const char *queries, const int64_t *q_off, int64_t *out0, int64_t *out1, uint32_t *cigar)
+{
+    if (!c) return VM_ERR_ARG;
+    if (n_pairs < 0 || !t_off || !q_off || !out0 || kind < 0 || kind > 2) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, nullptr);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        // one pseudo-read holding every target followed by every query
+        const int64_t tt = t_off[n_pairs], tq = q_off[n_pairs];
+        std::string cat((size_t)(tt + tq), 'N');
+        if (tt) memcpy(&cat[0], targets, (size_t)tt);
+        if (tq) memcpy(&cat[(size_t)tt], queries, (size_t)tq);
+        for (char &ch : cat) ch = "ACGTN"[vm_nt4((unsigned char)ch)];
+        const int64_t off[2] = {0, tt + tq};
+        ReadBatch b;
+        b.n = 1; b.seq = cat.data(); b.off = off;
+        be.reads_resident = false;
+        be.upload_reads(b);
+        be.reset_counters();
+        auto ref_of = [&](int64_t lo, int64_t hi) { vmg::SeqRef s; s.src = 1; s.lo = lo; s.hi = hi; return s; };
+        if (kind == 0) {
+            std::vector<EdJob> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].a = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+                jobs[j].b = ref_of(t_off[j], t_off[j + 1]);
+            }
+            be.edit_distance(b, jobs);
+            for (int64_t j = 0; j < n_pairs; ++j) out0[j] = jobs[j].dist;
+        } else if (kind == 1) {
+            std::vector<ExtJobRef> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].job.target = ref_of(t_off[j], t_off[j + 1]);
+                jobs[j].job.query = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+            }
+            be.extend(b, jobs);
+            for (int64_t j = 0; j < n_pairs; ++j) { out0[j] = jobs[j].job.q_e; if (out1) out1[j] = jobs[j].job.t_e; }
+        } else {
+            std::vector<FillJobRef> jobs((size_t)n_pairs);
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                jobs[j].read = 0;
+                jobs[j].job.target = ref_of(t_off[j], t_off[j + 1]);
+                jobs[j].job.query = ref_of(tt + q_off[j], tt + q_off[j + 1]);
+            }
+            be.fill(b, eqx != 0, jobs);
+            int64_t co = 0;
+            for (int64_t j = 0; j < n_pairs; ++j) {
+                out0[j] = (int64_t)jobs[j].cigar.size();
+                if (cigar && !jobs[j].cigar.empty()) memcpy(cigar + co, jobs[j].cigar.data(), jobs[j].cigar.size() * 4);
+                co += (t_off[j + 1] - t_off[j]) + (q_off[j + 1] - q_off[j]) + 2;
+            }
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
+int vm_reads_upload(vm_ctx *c, vm_index_handle *h, int64_t n_reads, const char *seqs, const int64_t *seq_off)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!h || n_reads < 0 || !seq_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.reads_resident = false;
+        ReadBatch b;
+        b.n = n_reads; b.seq = seqs; b.off = seq_off;
+        be.upload_reads(b);
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
+int vm_align_resident(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                      const int64_t *seq_off, vm_result **out)
+{
+    return vm_align_impl(c, h, p, n_reads, seqs, seq_off, 1, out);
+}
+
+int64_t vm_result_num_records(vm_result *r) { return r ? (int64_t)r->recs.size() : 0; }
+int64_t vm_result_num_cigar_ops(vm_result *r) { return r ? (int64_t)r->cigar.size() : 0; }
+const int64_t *vm_result_read_offsets(vm_result *r) { return r ? r->rec_off.data() : nullptr; }
+const vm_record *vm_result_records(vm_result *r) { return r ? r->recs.data() : nullptr; }
+const uint32_t *vm_result_cigar(vm_result *r) { return r ? r->cigar.data() : nullptr; }
+const char *vm_result_stage_times(vm_result *r) { return r ? r->stage_text.c_str() : ""; }
+void vm_result_free(vm_result *r) { delete r; }
+
+} // extern "C"

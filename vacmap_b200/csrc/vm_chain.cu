@@ -37,6 +37,7 @@ int vm_launch_pack(const int64_t *rows_dev, VmAnchor *out, long long total, cuda
 template <int KEY_IS_END, bool SMEM>
 __global__ void __launch_bounds__(32) vm_sort_anchors_kernel(const VmAnchor *__restrict__ in,
                                                              const int64_t *__restrict__ off,
+                                                             const int32_t *__restrict__ cnt,
                                                              const int *__restrict__ read_ids, int cap,
                                                              int32_t *__restrict__ perm, int32_t *__restrict__ gscratch,
                                                              VmAnchor *__restrict__ sorted,
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(32) vm_sort_anchors_kernel(const VmAnchor *__r
     const int lane = threadIdx.x;
     const int rid = read_ids[blockIdx.x];
     const long long base = off[rid];
-    const int n = (int)(off[rid + 1] - base);
+    const int n = cnt[rid];
     if (n <= 0) return;
     const VmAnchor *A = in + base;
     int *keys, *R, *Lpos, *Rpos;
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(32) vm_sort_anchors_kernel(const VmAnchor *__r
     }
 }
 
-int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int *read_ids_dev, int n_ids, int cap,
+int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int32_t *cnt, const int *read_ids_dev, int n_ids, int cap,
                            bool use_smem, int key_is_end, int32_t *perm, int32_t *gscratch, VmAnchor *sorted,
                            int64_t *sorted_rows, cudaStream_t stream)
 {
@@ -90,14 +91,14 @@ int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int *re
         const size_t smem = (size_t)cap * 16;
         if (key_is_end) {
             cudaFuncSetAttribute(vm_sort_anchors_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            vm_sort_anchors_kernel<1, true><<<n_ids, 32, smem, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+            vm_sort_anchors_kernel<1, true><<<n_ids, 32, smem, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
         } else {
             cudaFuncSetAttribute(vm_sort_anchors_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            vm_sort_anchors_kernel<0, true><<<n_ids, 32, smem, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+            vm_sort_anchors_kernel<0, true><<<n_ids, 32, smem, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
         }
     } else {
-        if (key_is_end) vm_sort_anchors_kernel<1, false><<<n_ids, 32, 0, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
-        else vm_sort_anchors_kernel<0, false><<<n_ids, 32, 0, stream>>>(in, off, read_ids_dev, cap, perm, gscratch, sorted, rows);
+        if (key_is_end) vm_sort_anchors_kernel<1, false><<<n_ids, 32, 0, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
+        else vm_sort_anchors_kernel<0, false><<<n_ids, 32, 0, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
     }
     return 1;
 }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
     const int lane = threadIdx.x;
     const int rid = read_ids[blockIdx.x];
     const long long base = A.off[rid];
-    const int n = (int)(A.off[rid + 1] - base);
+    const int n = A.cnt[rid];
     const VmAnchor *__restrict__ a = A.anchors + base;
 
     double *gcl = (double *)vm_smem;
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(32) vm_chain_fast_kernel(VmChainArgs A, int fa
     const int lane = threadIdx.x;
     const int rid = read_ids[blockIdx.x];
     const long long base = A.off[rid];
-    const int n = (int)(A.off[rid + 1] - base);
+    const int n = A.cnt[rid];
     const VmAnchor *__restrict__ a = A.anchors + base;
     double *gcl = (double *)vm_smem;
     float *rgl = (float *)(gcl + VM_GCL_MAX);

@@ -23,7 +23,8 @@
 
 struct VmChainArgs {
     const VmAnchor *anchors;   // sorted, concatenated
-    const int64_t *off;        // [n_reads+1]
+    const int64_t *off;        // [n_reads] start of each read's anchors
+    const int32_t *cnt;        // [n_reads] number of anchors
     double *S;                 // outputs, concatenated like anchors
     int32_t *P;
     int32_t *S_arg;
@@ -49,6 +50,6 @@ int vm_launch_chain_fast(int variant, const VmChainArgs &args, int fast_t, const
                          cudaStream_t stream);
 int vm_launch_pack(const int64_t *rows_dev, VmAnchor *out, long long total, cudaStream_t stream);
 #define VM_SORT_SMEM_CAP 8192      // anchors; 16 B each (keys, perm, two stop lists) -> 128 KB
-int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int *read_ids_dev, int n_ids, int cap,
+int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int32_t *cnt, const int *read_ids_dev, int n_ids, int cap,
                            bool use_smem, int key_is_end, int32_t *perm, int32_t *gscratch, VmAnchor *sorted,
                            int64_t *sorted_rows, cudaStream_t stream);

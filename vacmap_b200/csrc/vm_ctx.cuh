@@ -28,6 +28,7 @@ struct VmDevBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
+// page-locked host staging buffer (D2H / H2D at full PCIe rate, no hidden bounce copy)
 struct VmPinnedBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -51,15 +52,17 @@ struct VmPinnedBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
-// state of the stage-level global-chaining call (upload / run / download)
+// state of the chaining stage (stage-level upload / run / download, and the pipeline's device path)
 struct VmChainState {
     bool loaded = false;
     vm_chain_params prm{};
     int64_t n_reads = 0;
     int64_t total = 0;
-    std::vector<int64_t> off;
+    std::vector<int64_t> off;            // start of each read's anchors (n_reads + 1 for the stage-level call)
+    std::vector<int32_t> cnt;            // anchors per read
     std::vector<int32_t> read_len, cnt_len;
-    VmDevBuf rows, off_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
+    std::vector<int64_t> gmax_host;
+    VmDevBuf rows, off_dev, cnt_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
         fast_scratch, fast_off, sort_scratch;
     std::vector<int32_t> used_fast;
     float ms[4] = {0, 0, 0, 0};
@@ -80,3 +83,10 @@ struct vm_ctx {
     void *backend = nullptr;
     void (*backend_free)(void *) = nullptr;
 };
+
+// chaining core on device-resident anchors (vm_api.cu), used by the pipeline backend
+int vm_chain_prepare(vm_ctx *c, int64_t n_reads, int64_t span, const std::vector<int64_t> &start, const std::vector<int32_t> &cnt,
+                     bool want_rows);
+int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch, const std::vector<int64_t> &start,
+                  const std::vector<int32_t> &cnt, const std::vector<int32_t> &read_len, const std::vector<int32_t> &cnt_len,
+                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4);

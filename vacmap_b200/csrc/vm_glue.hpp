@@ -28,6 +28,14 @@ struct Anc {
 };
 typedef std::vector<Anc> Path;
 
+// anchor as the kernels store it (16 bytes; == VmAnchor): what the chaining stages hand back
+struct Anc32 {
+    int32_t x;
+    uint32_t y;
+    int32_t s, l;
+};
+static inline Anc widen(const Anc32 &a) { return Anc{a.x, (int64_t)a.y, a.s, a.l}; }
+
 struct ReadDropped : public std::runtime_error {
     explicit ReadDropped(const char *m) : std::runtime_error(m) {}
 };
@@ -146,7 +154,7 @@ struct GlobalResult {
     std::vector<Path> guides;  // [0] primary chain, then secondary chains; each DESCENDING read order
 };
 
-static void hit2work(const Anc *a, const double *S, const int32_t *P, const int32_t *S_arg, int64_t n, int64_t g,
+static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const int32_t *S_arg, int64_t n, int64_t g,
                      int64_t L, double accept, GlobalResult &out, int bin_size = 100, double overlap = 0.5)
 {
     out = GlobalResult();
@@ -161,7 +169,7 @@ static void hit2work(const Anc *a, const double *S, const int32_t *P, const int3
         used[take] = 1;
         const double score = S[take];
         for (;;) {
-            path.push_back(a[take]);
+            path.push_back(widen(a[take]));
             S_arr.push_back(S[take]);
             if (P[take] == kNoPre) break;
             take = P[take];
@@ -183,7 +191,7 @@ static void hit2work(const Anc *a, const double *S, const int32_t *P, const int3
         used[take] = 1;
         double score = S[take];
         for (;;) {
-            path.push_back(a[take]);
+            path.push_back(widen(a[take]));
             if (P[take] == kNoPre) break;
             take = P[take];
             if (used[take]) { score = score - S[take]; break; }
@@ -456,26 +464,26 @@ static void make_guide_job(const Path &chain, int64_t L, int k, const Contigs &c
 // ---------------------------------------------------------------------------
 // local traceback with overlap trimming (:27508-27527); result ASCENDING read order
 // ---------------------------------------------------------------------------
-static void local_traceback(const Anc *a, const int32_t *P, int64_t g, Path &asc)
+static void local_traceback(const Anc32 *a, const int32_t *P, int64_t g, Path &asc)
 {
     Path path;
     int64_t take = g;
-    path.push_back(a[take]);
-    const Anc *pre = &a[take];
+    path.push_back(widen(a[take]));
+    Anc pre = widen(a[take]);
     for (;;) {
         if (P[take] == kNoPre) break;
         take = P[take];
-        const Anc *now = &a[take];
-        if (pre->x < now->x + now->l) {
-            const int64_t ov = now->x + now->l - pre->x;
+        const Anc now = widen(a[take]);
+        if (pre.x < now.x + now.l) {
+            const int64_t ov = now.x + now.l - pre.x;
             Anc t;
-            t.x = pre->x + ov;
-            t.y = pre->s == 1 ? pre->y + ov : pre->y;
-            t.s = pre->s;
-            t.l = (int32_t)(pre->l - ov);
+            t.x = pre.x + ov;
+            t.y = pre.s == 1 ? pre.y + ov : pre.y;
+            t.s = pre.s;
+            t.l = (int32_t)(pre.l - ov);
             path.back() = t;
         }
-        path.push_back(*now);
+        path.push_back(now);
         pre = now;
     }
     asc.assign(path.rbegin(), path.rend());

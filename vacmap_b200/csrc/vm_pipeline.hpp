@@ -14,18 +14,8 @@
 namespace vmp {
 
 using vmg::Anc;
+using vmg::Anc32;
 using vmg::Path;
-
-template <typename T> struct Ragged {
-    std::vector<T> data;
-    std::vector<int64_t> off{0};
-    int64_t rows() const { return (int64_t)off.size() - 1; }
-    int64_t size(int64_t r) const { return off[r + 1] - off[r]; }
-    const T *row(int64_t r) const { return data.data() + off[r]; }
-    T *row(int64_t r) { return data.data() + off[r]; }
-    void clear() { data.clear(); off.assign(1, 0); }
-    void close_row() { off.push_back((int64_t)data.size()); }
-};
 
 struct ReadBatch {
     int64_t n = 0;
@@ -34,11 +24,24 @@ struct ReadBatch {
     int64_t len(int64_t r) const { return off[r + 1] - off[r]; }
 };
 
-struct ChainOut {                  // per batch, ragged like the input anchors
-    Ragged<Anc> sorted;
-    std::vector<double> S;
-    std::vector<int32_t> P, S_arg;
-    std::vector<int64_t> gmax;     // per read
+// Result of a chaining stage for a batch.  Read r owns slots [start[r], start[r] + cnt[r]) of the
+// flat arrays, which live in backend-owned (pinned) memory until the next call of the same stage;
+// the *_store vectors are optional owning storage for test backends.
+struct ChainOut {
+    std::vector<int64_t> start;
+    std::vector<int32_t> cnt;
+    std::vector<int64_t> gmax;      // g_max_index per read (-1: not chained)
+    const Anc32 *sorted = nullptr;  // anchors after the argsort
+    const double *S = nullptr;      // global stage only
+    const int32_t *P = nullptr;
+    const int32_t *S_arg = nullptr; // global stage only
+    std::vector<Anc32> sorted_store;
+    std::vector<double> S_store;
+    std::vector<int32_t> P_store, A_store;
+    void adopt_stores()
+    {
+        sorted = sorted_store.data(); S = S_store.data(); P = P_store.data(); S_arg = A_store.data();
+    }
 };
 
 struct GuideJobRef { int32_t read; vmg::GuideJob job; };
@@ -46,20 +49,19 @@ struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; };
 struct ExtJobRef { int32_t read; vmg::ExtJob job; };
 struct FillJobRef { int32_t read; vmg::FillJob job; std::vector<uint32_t> cigar; };
 
-// The hot loops.  Every method processes the jobs of a whole batch.
+// The hot loops.  Every method processes the jobs of a whole batch; consecutive hot loops whose
+// hand-over needs no host decision are fused so the data never leaves the device in between.
 struct Backend {
     virtual ~Backend() {}
-    // minimizer seeding + cluster filter + majority-strand flip (index.map + :21202-21217)
-    virtual void seed(const ReadBatch &b, int check_num, Ragged<Anc> &anchors, std::vector<char> &need_reverse) = 0;
-    // argsort by read position + global DP (exact / fast as hit2work_1 chooses)
-    virtual void chain_global(const Ragged<Anc> &anchors, const std::vector<int64_t> &read_len, int kmersize,
-                              double skipcost, int maxdiff, int maxgap, ChainOut &out) = 0;
-    // local 9-mer re-seeding; anchors of all guide jobs of a read are concatenated in job order
-    virtual void reseed(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
-                        Ragged<Anc> &local /* rows = reads */) = 0;
-    // argsort by read end + local DP variant 1 / 2 (+ fast fall-back); rows with variant 0 are skipped
-    virtual void chain_local(const Ragged<Anc> &anchors, const std::vector<int> &variant,
-                             const std::vector<double> &skipcost, int maxdiff, int maxgap, ChainOut &out) = 0;
+    // minimizer seeding + cluster filter + majority-strand flip (index.map + :21202-21217), then
+    // argsort by read position + global DP (exact / fast as hit2work_1 chooses, :23570-23579)
+    virtual void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+                            std::vector<char> &need_reverse, ChainOut &out) = 0;
+    // local 9-mer re-seeding (anchors of all guide jobs of a read concatenated in job order), then
+    // argsort by read end + local DP variant[r] in {1, 2} (+ fast fall-back); variant 0 = skip the read
+    virtual void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                              const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                              ChainOut &out) = 0;
     virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) = 0;
     virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
     virtual void fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
@@ -98,7 +100,6 @@ struct ReadState {
     size_t n0 = 0;
     bool filtered = false;
     bool nofilter = false;
-    bool redo = false;
     std::vector<vmg::ExtJob> ext;
     vmg::AlnList kept;
     std::vector<vmg::FillJob> fills;
@@ -126,32 +127,22 @@ public:
         const int64_t n = b.n;
         res.records.assign((size_t)n, {});
         std::vector<ReadState> st((size_t)n);
-        // host copies of the oriented reads are needed by fix_simple_inv only; built lazily there
-
-        // ---- 1-2. seeding + global chaining ----
-        Ragged<Anc> anchors;
-        std::vector<char> need_rev;
-        be_.seed(b, opt_.check_num, anchors, need_rev);
         std::vector<int64_t> read_len((size_t)n);
         for (int64_t r = 0; r < n; ++r) read_len[r] = b.len(r);
-        // decode_hit :23986 -- reads with <= 2 anchors are unmapped: drop their rows
-        Ragged<Anc> ganch;
-        for (int64_t r = 0; r < n; ++r) {
-            if (anchors.size(r) > 2) ganch.data.insert(ganch.data.end(), anchors.row(r), anchors.row(r) + anchors.size(r));
-            ganch.close_row();
-        }
+
+        // ---- 1-2. seeding + global chaining (fused on the device) ----
+        std::vector<char> need_rev;
         ChainOut g;
-        be_.chain_global(ganch, read_len, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, g);
+        be_.seed_chain(b, opt_.check_num, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, need_rev, g);
 
         // ---- 3. hit2work bookkeeping + guide selection ----
         std::vector<std::vector<GuideJobRef>> gjobs((size_t)n);
         parallel_for(n, threads_, [&](int64_t r) {
-            const int64_t m = g.sorted.size(r);
-            if (m <= 2) return;
-            const int64_t o = g.sorted.off[r];
+            const int64_t m = g.cnt[r];
+            if (m <= 2) return;                       // decode_hit :23986 -- <= 2 anchors: unmapped
+            const int64_t o = g.start[r];
             vmg::GlobalResult gr;
-            vmg::hit2work(g.sorted.row(r), g.S.data() + o, g.P.data() + o, g.S_arg.data() + o, m, g.gmax[r], read_len[r],
-                          opt_.mode.accept, gr);
+            vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
             if (!gr.ok) return;
             ReadState &s = st[r];
             s.alive = true;
@@ -167,32 +158,29 @@ public:
             }
         });
         std::vector<GuideJobRef> all_gjobs;
-        for (int64_t r = 0; r < n; ++r)
-            for (GuideJobRef &j : gjobs[r]) all_gjobs.push_back(std::move(j));
-        gjobs.clear();
-
-        // ---- 4-5. local re-seeding + local chaining ----
-        Ragged<Anc> local;
-        be_.reseed(b, need_rev, all_gjobs, local);
         std::vector<int> variant((size_t)n, 0);
         std::vector<double> skip((size_t)n, opt_.local_skipcost);
         for (int64_t r = 0; r < n; ++r) {
+            for (GuideJobRef &j : gjobs[r]) all_gjobs.push_back(std::move(j));
             if (!st[r].alive) continue;
-            if (local.size(r) == 0) { st[r].alive = false; continue; }   // np.array([]) indexing raises in the reference
             if (st[r].guides.size() > 1) {
                 variant[r] = 2;
                 if (opt_.mode.clamp40) skip[r] = std::min(skip[r], 40.0);
             } else variant[r] = 1;
         }
+        gjobs.clear();
+
+        // ---- 4-5. local re-seeding + local chaining (fused on the device) ----
         ChainOut lc;
-        be_.chain_local(local, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
+        be_.reseed_chain(b, need_rev, all_gjobs, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
 
         // ---- 6. traceback, then extend_func as a staged state machine ----
         parallel_for(n, threads_, [&](int64_t r) {
             ReadState &s = st[r];
             if (!s.alive) return;
-            const int64_t o = lc.sorted.off[r];
-            vmg::local_traceback(lc.sorted.row(r), lc.P.data() + o, lc.gmax[r], s.asc);
+            if (lc.cnt[r] == 0) { s.alive = false; return; }   // np.array([]) indexing raises in the reference
+            const int64_t o = lc.start[r];
+            vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
             if (s.asc.size() <= 1) s.alive = false;
             s.nofilter = opt_.nodiscard;
         });
