@@ -177,6 +177,13 @@ int vm_align_batch(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *p
 int vm_reads_upload(vm_ctx *ctx, vm_index_handle *index, int64_t n_reads, const char *seqs, const int64_t *seq_off);
 int vm_align_resident(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
                       const char *seqs, const int64_t *seq_off, vm_result **out);
+/* Stage-level seeding: per read, what `index_object.map(seq, check_num, mid_occ=-1)` (clrnano:23985)
+ * followed by get_reversed_chain_numpy_rough (clrnano:21202-21217) yields: int64 rows
+ * (readpos, refpos_global, strand, len) in rows[row_off[r] .. row_off[r+1]) and the flip flag.
+ * Returns VM_ERR_NOMEM (row_off filled) when `cap` rows are not enough. */
+int vm_seed_batch_rows(vm_ctx *ctx, vm_index_handle *index, int32_t check_num, int64_t n_reads, const char *seqs,
+                       const int64_t *seq_off, int64_t *rows, int64_t cap, int64_t *row_off, int32_t *need_reverse);
+
 /* Stage-level entry point of the base-level kernels on raw sequence pairs (parity tests).
  * kind 0: edlib.align(query, target, task='distance') (clrnano:19251)        -> out0[j] = distance
  * kind 1: mp.k_cigar(t, q, 2,-4, 4,4,4,4, bw=100, zdropvalue=50) (clrnano:2381) -> out0 = q_e, out1 = t_e

@@ -1,0 +1,56 @@
+"""GPU parity of the seeding stage (chunk-parallel sketch, hash lookup, cluster filter, strand flip)
+against the oracle's restatement of `vacmap_index.map` + get_reversed_chain_numpy_rough."""
+import numpy as np
+import pytest
+
+import oracle
+import oracle.pipeline as pl
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def with_ns(rng, s, n_runs):
+    a = np.frombuffer(s.encode(), dtype=np.uint8).copy()
+    for _ in range(n_runs):
+        p = int(rng.integers(0, len(a) - 1))
+        ln = int(rng.choice([1, 1, 2, 5, 20, 60, 300]))
+        a[p:p + ln] = ord("N")
+    return a.tobytes().decode()
+
+
+def check(ix, ox, reads, check_num):
+    from vacmap_b200.align import seed_batch
+    got = seed_batch(ix, reads, check_num)
+    for s, (rows, rev) in zip(reads, got):
+        want = ox.map(s.upper(), check_num=check_num, mid_occ=-1)
+        wrev, want = pl.reverse_rough(want, len(s))
+        assert rev == wrev
+        assert rows.shape == want.shape and (rows == want).all(), len(s)
+
+
+def test_seeding_matches_oracle(gpu_ctx):
+    import vacmap_b200 as vb
+    rng = np.random.default_rng(41)
+    ref = synth.make_reference(41, 600000, n_contigs=2, repeat_frac=0.15)
+    ix, ox = vb.Index(ref, ctx=gpu_ctx), oracle.Index(ref)
+    reads = [s for _, s in synth.make_reads(ref, 42, 40, read_len=7000, err=0.08)]
+    reads += [with_ns(rng, s, int(rng.integers(1, 12))) for s in reads[:16]]          # ambiguous bases, incl. in warm-up zones
+    reads += ["ACGT", "A" * 500, "ACGTACGTACGTACGTACGTACGTACGTACGTACGT" * 20, "N" * 300, reads[0][:14], reads[0][:15], reads[0][:25],
+              reads[1][:127], reads[1][:128], reads[1][:129], reads[2][:256 + 24]]
+    palin = "ACGTTGCATGCAACGT" * 40                                                     # rich in symmetric k-mers (k = 15?) and repeats
+    reads += [palin, reads[3][:1000] + palin + reads[3][1000:2000]]
+    check(ix, ox, reads, 100)
+    check(ix, ox, reads, -1)
+    check(ix, ox, reads[:30], 3)        # the top-N cluster filter actually drops clusters
+    ix.close()
+
+
+def test_seeding_other_kw(gpu_ctx):
+    import vacmap_b200 as vb
+    ref = synth.make_reference(43, 300000)
+    reads = [s for _, s in synth.make_reads(ref, 44, 12, read_len=5000, err=0.01, ratio=(1, 1, 1))]
+    for w, k in ((10, 19), (5, 11), (19, 21)):
+        ix, ox = vb.Index(ref, w=w, k=k, ctx=gpu_ctx), oracle.Index(ref, w=w, k=k)
+        check(ix, ox, reads, 100)
+        ix.close()

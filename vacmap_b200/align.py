@@ -261,3 +261,27 @@ def pairs_batch(kind, targets, queries, eqx=False, ctx=None, device=0):
         res.append(cigar_string(cig[co:co + int(out0[i])]))
         co += len(tb[i]) + len(qb[i]) + 2
     return res
+
+
+def seed_batch(index, reads, check_num=100):
+    """Stage-level seeding: per read (int64[n,4] anchors after the cluster filter and strand flip, need_reverse)."""
+    L = _lib.load()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_seed_batch_rows.argtypes = [vp, vp, i32, i64, vp, vp, vp, i64, vp, vp]
+    enc = [s.upper().encode() for s in reads]
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    for i, e in enumerate(enc):
+        off[i + 1] = off[i] + len(e)
+    cap = max(4096, 2 * int(off[-1]))
+    row_off = np.zeros(len(reads) + 1, dtype=np.int64)
+    nrev = np.zeros(len(reads), dtype=np.int32)
+    while True:
+        rows = np.zeros((cap, 4), dtype=np.int64)
+        rc = L.vm_seed_batch_rows(index.ctx.h, index.h, check_num, len(reads), b"".join(enc), _lib.ptr(off), _lib.ptr(rows), cap,
+                                  _lib.ptr(row_off), _lib.ptr(nrev))
+        if rc == -4:
+            cap = int(row_off[-1]) + 16
+            continue
+        _lib.check(index.ctx.h, rc)
+        break
+    return [(rows[row_off[i]:row_off[i + 1]].copy(), bool(nrev[i])) for i in range(len(reads))]

@@ -130,6 +130,19 @@ public:
         off_host_.assign(b.off, b.off + b.n + 1);
     }
 
+    // stage-level: seeding only, anchors copied to the host (parity tests)
+    void seed_only(const ReadBatch &b, int check_num, std::vector<VmAnchor> &flat, std::vector<int64_t> &a_off,
+                   std::vector<int32_t> &n_out, std::vector<int32_t> &nrev)
+    {
+        upload_reads(b);
+        std::string err;
+        if (vm_seed_batch(seed_, ih_->ix->dev, reads_fwd_.as<uint8_t>(), read_off_.as<int64_t>(), off_host_, check_num, -1,
+                          c_->stream, n_out, nrev, a_off, &c_->launches, err))
+            throw std::runtime_error(err);
+        flat.resize((size_t)a_off[b.n]);
+        if (!flat.empty()) BE_OK(cudaMemcpy(flat.data(), seed_.out.p, flat.size() * sizeof(VmAnchor), cudaMemcpyDeviceToHost));
+    }
+
     // ---- seeding + global chaining, anchors never leave the device in between ----
     void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
                     std::vector<char> &need_reverse, ChainOut &out) override

@@ -232,6 +232,47 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
     return VM_OK;
 }
 
+// Stage-level seeding: what `index_object.map(seq, check_num, mid_occ=-1)` followed by
+// get_reversed_chain_numpy_rough returns per read.  rows: int64[cap][4]; row_off[n_reads+1] receives
+// the ragged offsets; returns VM_ERR_NOMEM (with row_off filled) when cap is too small.
+int vm_seed_batch_rows(vm_ctx *c, vm_index_handle *h, int32_t check_num, int64_t n_reads, const char *seqs, const int64_t *seq_off,
+                       int64_t *rows, int64_t cap, int64_t *row_off, int32_t *need_reverse)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!h || n_reads < 0 || !seq_off || !row_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.set_index(h);
+        be.reads_resident = false;
+        ReadBatch b;
+        b.n = n_reads; b.seq = seqs; b.off = seq_off;
+        std::vector<VmAnchor> flat;
+        std::vector<int64_t> a_off;
+        std::vector<int32_t> n_out, nrev;
+        be.seed_only(b, check_num, flat, a_off, n_out, nrev);
+        row_off[0] = 0;
+        for (int64_t r = 0; r < n_reads; ++r) row_off[r + 1] = row_off[r] + n_out[r];
+        if (row_off[n_reads] > cap) { c->err = "row buffer too small"; return VM_ERR_NOMEM; }
+        for (int64_t r = 0; r < n_reads; ++r) {
+            if (need_reverse) need_reverse[r] = nrev[r];
+            for (int32_t t = 0; t < n_out[r]; ++t) {
+                const VmAnchor &a = flat[(size_t)a_off[r] + t];
+                int64_t *o = rows + (row_off[r] + t) * 4;
+                o[0] = a.x; o[1] = (int64_t)a.y; o[2] = a.s; o[3] = a.l;
+            }
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
 int vm_reads_upload(vm_ctx *c, vm_index_handle *h, int64_t n_reads, const char *seqs, const int64_t *seq_off)
 {
     if (!c) return VM_ERR_ARG;

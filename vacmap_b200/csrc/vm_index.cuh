@@ -85,8 +85,14 @@ __host__ __device__ __forceinline__ uint64_t vm_ht_hash(uint64_t key)
 // occupying a window slot, an ambiguous base resets the run length but not the k-mer registers.
 // emit(hash, last_base_pos << 1 | strand) is called in position order.  One caller = one
 // sequential state machine (host: per contig; device: one thread per read).
-template <typename Emit>
-__host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len, int w, int k, Emit emit)
+// Range form: the machine starts FRESH at `begin` (i.e. as if the sequence started there) and runs
+// to `end`; positions are reported in the coordinates of `str`.  observe(i, kind) is called for every
+// base (kind 0 = counted k-mer position, 1 = ambiguous base, 2 = symmetric k-mer) and may return false
+// to stop; `flush` = emit the pending minimum when the loop ran to `end` (minimap2 does at the end of
+// the sequence).  Used with a warm-up by the chunk-parallel device sketch (vm_seed.cu).
+template <typename Emit, typename Observe>
+__host__ __device__ inline void vm_sketch_range(const unsigned char *str, int64_t begin, int64_t end, int w, int k, bool flush,
+                                                Emit emit, Observe observe)
 {
     const uint64_t shift1 = 2 * (uint64_t)(k - 1), mask = (1ULL << 2 * k) - 1;
     uint64_t kmer0 = 0, kmer1 = 0;
@@ -94,14 +100,18 @@ __host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len,
     uint64_t minx = ~0ULL, miny = ~0ULL;
     int l = 0, buf_pos = 0, min_pos = 0, kmer_span = 0;
     for (int j = 0; j < w; ++j) { bufx[j] = ~0ULL; bufy[j] = ~0ULL; }
-    for (int64_t i = 0; i < len; ++i) {
+    bool stopped = false;
+    for (int64_t i = begin; i < end; ++i) {
         const int c = vm_nt4(str[i]);
         uint64_t infox = ~0ULL, infoy = ~0ULL;
         if (c < 4) {
             kmer_span = l + 1 < k ? l + 1 : k;
             kmer0 = (kmer0 << 2 | (uint64_t)c) & mask;
             kmer1 = (kmer1 >> 2) | (3ULL ^ (uint64_t)c) << shift1;
-            if (kmer0 == kmer1) continue;
+            if (kmer0 == kmer1) {
+                if (!observe(i, 2)) { stopped = true; break; }
+                continue;
+            }
             const int z = kmer0 < kmer1 ? 0 : 1;
             ++l;
             if (l >= k && kmer_span < 256) {
@@ -135,8 +145,15 @@ __host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len,
             }
         }
         if (++buf_pos == w) buf_pos = 0;
+        if (!observe(i, c < 4 ? 0 : 1)) { stopped = true; break; }
     }
-    if (minx != ~0ULL) emit(minx >> 8, miny);
+    if (flush && !stopped && minx != ~0ULL) emit(minx >> 8, miny);
+}
+
+template <typename Emit>
+__host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len, int w, int k, Emit emit)
+{
+    vm_sketch_range(str, 0, len, w, k, true, emit, [](int64_t, int) { return true; });
 }
 
 // 9-mer code over the 5-letter alphabet ACGTN (anything else reads as N)

@@ -10,24 +10,97 @@
 // run, 8 B each, contiguous); the expansion writes 16 B per anchor, coalesced per minimizer.
 #include "vm_seed.cuh"
 
-// ---- 1. sketch: one thread per read, literal mm_sketch state machine ----
-__global__ void vm_sketch_kernel(const uint8_t *__restrict__ reads, const int64_t *__restrict__ off, int n_reads,
-                                 int w, int k, uint64_t *__restrict__ mz_hash, uint32_t *__restrict__ mz_posz,
-                                 int32_t *__restrict__ n_mz)
+// ---- 1. sketch, chunk-parallel and exact ----
+// mm_sketch is a sequential window machine, but its state is history-free after a short clean
+// run: once k non-ambiguous bases have refilled the k-mer registers and w+k further positions
+// were all "counted" (neither ambiguous nor a symmetric k-mer), the last w window slots, the
+// current minimum (always the latest slot attaining the window minimum) and the saturated run
+// length are functions of those positions alone.  So one thread per VM_SK_CHUNK positions
+// starts a FRESH machine a warm-up before its chunk, keeps only emissions whose position falls
+// inside its chunk, and runs on until w slots past the chunk end (every slot is emitted at the
+// latest when it leaves the window).  If the warm-up zone is not clean (N's, symmetric k-mers)
+// it is widened x4 until it is, or until it reaches the start of the read, where the machine is
+// exact by definition.  Emissions are position-sorted, so concatenating the chunks in order
+// reproduces the sequential output.
+#define VM_SK_CHUNK 128
+
+__global__ void vm_sketch_chunk_kernel(const uint8_t *__restrict__ reads, const int64_t *__restrict__ off,
+                                       const int64_t *__restrict__ chunk_off, int n_reads, int64_t n_chunks, int w, int k,
+                                       uint64_t *__restrict__ mz_hash, uint32_t *__restrict__ mz_posz,
+                                       int32_t *__restrict__ chunk_cnt)
 {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const int64_t base = off[r];
-    const int64_t len = off[r + 1] - base;
+    const int64_t cid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cid >= n_chunks) return;
+    int lo = 0, hi = n_reads;   // read owning this chunk
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (chunk_off[mid] <= cid) lo = mid; else hi = mid;
+    }
+    const int64_t base = off[lo];
+    const int64_t L = off[lo + 1] - base;
+    const int64_t c0 = (cid - chunk_off[lo]) * VM_SK_CHUNK;
+    const int64_t c1 = c0 + VM_SK_CHUNK < L ? c0 + VM_SK_CHUNK : L;
+    const unsigned char *str = reads + base;
+    uint64_t *oh = mz_hash + base + c0;
+    uint32_t *op = mz_posz + base + c0;
+    int64_t warm = 2 * k + w + 8;
     int cnt = 0;
-    uint64_t *oh = mz_hash + base;
-    uint32_t *op = mz_posz + base;
-    vm_sketch(reads + base, len, w, k, [&](uint64_t h, uint64_t y) {
-        oh[cnt] = h;
-        op[cnt] = (uint32_t)y;
-        ++cnt;
-    });
-    n_mz[r] = cnt;
+    for (;;) {
+        const int64_t s = c0 - warm > 0 ? c0 - warm : 0;
+        cnt = 0;
+        bool regs_bad = false;
+        int64_t last_bad = -1;
+        int slots_after = 0;
+        vm_sketch_range(str, s, L, w, k, true,
+                        [&](uint64_t h, uint64_t y) {
+                            const int64_t pos = (int64_t)(y >> 1);
+                            if (pos >= c0 && pos < c1) { oh[cnt] = h; op[cnt] = (uint32_t)y; ++cnt; }
+                        },
+                        [&](int64_t i, int kind) {
+                            if (i < c0) {
+                                if (kind == 1 && i < s + k) regs_bad = true;
+                                if (kind != 0) last_bad = i;
+                            } else if (i >= c1) {
+                                if (kind != 2 && ++slots_after > w) return false;
+                            }
+                            return true;
+                        });
+        // the first k positions of the clean run refill the registers (their symmetric test may still
+        // see stale bits), the following w + k are judged with correct registers
+        (void)regs_bad;
+        if (s == 0 || last_bad < c0 - (w + 2 * k)) break;
+        warm *= 4;
+    }
+    chunk_cnt[cid] = cnt;
+}
+
+// compaction of the per-chunk outputs to the front of each read's slot range: one warp per read
+__global__ void __launch_bounds__(32) vm_sketch_compact_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
+                                                               const int32_t *__restrict__ chunk_cnt, uint64_t *__restrict__ mz_hash,
+                                                               uint32_t *__restrict__ mz_posz, int32_t *__restrict__ n_mz)
+{
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int64_t base = off[r];
+    const int64_t c_lo = chunk_off[r], c_hi = chunk_off[r + 1];
+    int total = 0;
+    for (int64_t c = c_lo; c < c_hi; ++c) {
+        const int cnt = chunk_cnt[c];
+        const int64_t src = base + (c - c_lo) * VM_SK_CHUNK, dst = base + total;
+        if (src != dst) {
+            for (int t0 = 0; t0 < cnt; t0 += 32) {
+                const int t = t0 + lane;
+                uint64_t h = 0;
+                uint32_t p = 0;
+                if (t < cnt) { h = mz_hash[src + t]; p = mz_posz[src + t]; }
+                __syncwarp();
+                if (t < cnt) { mz_hash[dst + t] = h; mz_posz[dst + t] = p; }
+                __syncwarp();
+            }
+        }
+        total += cnt;
+    }
+    if (lane == 0) n_mz[r] = total;
 }
 
 // ---- 2. lookup + per-read exclusive scan of hit counts: one warp per read ----
@@ -259,8 +332,23 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     SEED_OK(B.a_off.ensure((size_t)(n + 1) * 8 + 64));
     SEED_OK(B.t_off.ensure((size_t)(n + 1) * 8 + 64));
     if (mid_occ < 0) mid_occ = ix.mid_occ;
-    vm_sketch_kernel<<<(n + 31) / 32, 32, 0, stream>>>(reads_dev, off_dev, n, ix.w, ix.k, B.mz_hash.as<uint64_t>(),
-                                                      B.mz_posz.as<uint32_t>(), B.n_mz.as<int32_t>());
+    {
+        std::vector<int64_t> chunk_off(n + 1, 0);
+        for (int r = 0; r < n; ++r)
+            chunk_off[r + 1] = chunk_off[r] + (off_host[r + 1] - off_host[r] + VM_SK_CHUNK - 1) / VM_SK_CHUNK;
+        const int64_t n_chunks = chunk_off[n];
+        SEED_OK(B.chunk_off.ensure((size_t)(n + 1) * 8 + 64));
+        SEED_OK(B.chunk_cnt.ensure((size_t)n_chunks * 4 + 64));
+        SEED_OK(cudaMemcpyAsync(B.chunk_off.p, chunk_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
+        SEED_OK(cudaStreamSynchronize(stream));
+        if (n_chunks > 0)
+            vm_sketch_chunk_kernel<<<(unsigned)((n_chunks + 63) / 64), 64, 0, stream>>>(
+                reads_dev, off_dev, B.chunk_off.as<int64_t>(), n, n_chunks, ix.w, ix.k, B.mz_hash.as<uint64_t>(),
+                B.mz_posz.as<uint32_t>(), B.chunk_cnt.as<int32_t>());
+        vm_sketch_compact_kernel<<<n, 32, 0, stream>>>(off_dev, B.chunk_off.as<int64_t>(), B.chunk_cnt.as<int32_t>(),
+                                                       B.mz_hash.as<uint64_t>(), B.mz_posz.as<uint32_t>(), B.n_mz.as<int32_t>());
+        *launches += 1;
+    }
     vm_seed_lookup_kernel<<<n, 32, 0, stream>>>(ix, off_dev, B.mz_hash.as<uint64_t>(), B.n_mz.as<int32_t>(), mid_occ,
                                                 B.mz_start.as<uint32_t>(), B.mz_cnt.as<uint32_t>(), B.mz_aoff.as<uint32_t>(),
                                                 B.n_anchor.as<int32_t>());

@@ -5,11 +5,11 @@
 
 struct VmSeedBufs {
     VmDevBuf mz_hash, mz_posz, mz_start, mz_cnt, mz_aoff, n_mz, n_anchor, n_out, need_rev, a_off, t_off, raw, out, table,
-        compact;
+        compact, chunk_off, chunk_cnt;
     void release()
     {
         VmDevBuf *b[] = {&mz_hash, &mz_posz, &mz_start, &mz_cnt, &mz_aoff, &n_mz, &n_anchor, &n_out, &need_rev, &a_off,
-                         &t_off, &raw, &out, &table, &compact};
+                         &t_off, &raw, &out, &table, &compact, &chunk_off, &chunk_cnt};
         for (VmDevBuf *x : b) x->release();
     }
 };
