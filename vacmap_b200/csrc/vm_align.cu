@@ -49,28 +49,40 @@ __device__ __forceinline__ int vm_at(const VmSeqView &v, int i)
 // ---------------------------------------------------------------------------
 // edit distance
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) vm_edit_distance_kernel(VmAlnJobDev *jobs, VmSeqSources S, int max_words)
+// GT > 0: every lane owns GT 64-row blocks whose Pv/Mv words live in REGISTERS (loops fully
+// unrolled); GT == 0: generic version for very long patterns, words per lane decided at run time
+// (state in local memory).
+template <int GT>
+__global__ void __launch_bounds__(32) vm_edit_distance_kernel(VmAlnJobDev *jobs, const int *__restrict__ job_ids, VmSeqSources S,
+                                                              int max_words)
 {
     extern __shared__ unsigned long long vm_peq[];   // [5][max_words]
-    VmAlnJobDev &J = jobs[blockIdx.x];
+    VmAlnJobDev &J = jobs[job_ids[blockIdx.x]];
     const int lane = threadIdx.x;
     const VmSeqView pat = vm_view(S, J.q, J.read), txt = vm_view(S, J.t, J.read);
     const int m = pat.len, n = txt.len;
     if (m == 0 || n == 0) { if (lane == 0) J.result0 = m + n; return; }
     const int W = (m + 63) >> 6;
-    const int G = (W + 31) >> 5;
+    const int G = GT > 0 ? GT : (W + 31) >> 5;
     const int used = (W + G - 1) / G;
     for (int w = lane; w < W; w += 32) {
-        unsigned long long e[5] = {0, 0, 0, 0, 0};
+        unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
         for (int b = 0; b < 64; ++b) {
             const int i = w * 64 + b;
-            if (i < m) e[vm_at(pat, i)] |= 1ULL << b;
+            if (i < m) {
+                const int c = vm_at(pat, i);
+                const unsigned long long bit = 1ULL << b;
+                if (c == 0) e0 |= bit; else if (c == 1) e1 |= bit; else if (c == 2) e2 |= bit; else if (c == 3) e3 |= bit; else e4 |= bit;
+            }
         }
-        for (int c = 0; c < 5; ++c) vm_peq[c * max_words + w] = e[c];
+        vm_peq[w] = e0; vm_peq[max_words + w] = e1; vm_peq[2 * max_words + w] = e2; vm_peq[3 * max_words + w] = e3;
+        vm_peq[4 * max_words + w] = e4;
     }
     __syncwarp();
-    unsigned long long Pv[VM_ED_MAXG], Mv[VM_ED_MAXG];
-    for (int g = 0; g < G; ++g) { Pv[g] = ~0ULL; Mv[g] = 0ULL; }
+    constexpr int NW = GT > 0 ? GT : VM_ED_MAXG;
+    unsigned long long Pv[NW], Mv[NW];
+#pragma unroll
+    for (int g = 0; g < NW; ++g) { Pv[g] = ~0ULL; Mv[g] = 0ULL; }
     int score = 64 * W;
     const int w0 = lane * G;
     const bool owns_last = lane < used && (W - 1) >= w0 && (W - 1) < w0 + G;
@@ -81,50 +93,79 @@ __global__ void __launch_bounds__(32) vm_edit_distance_kernel(VmAlnJobDev *jobs,
         int hout = 0;
         if (lane < used && j >= 0 && j < n) {
             int hin = lane == 0 ? 1 : hin_from;   // D[0][j] - D[0][j-1] = 1 (global alignment)
-            const int c = vm_at(txt, j);
-            for (int g = 0; g < G; ++g) {
-                const int w = w0 + g;
-                if (w >= W) break;
-                unsigned long long Eq = vm_peq[c * max_words + w];
-                const unsigned long long pv = Pv[g], mv = Mv[g];
-                const unsigned long long neg = hin < 0 ? 1ULL : 0ULL;
-                const unsigned long long Xv = Eq | mv;
-                Eq |= neg;
-                const unsigned long long Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-                unsigned long long Ph = mv | ~(Xh | pv);
-                unsigned long long Mh = pv & Xh;
-                const int ho = (int)(Ph >> 63) - (int)(Mh >> 63);
-                Ph <<= 1;
-                Mh <<= 1;
-                Mh |= neg;
-                Ph |= hin > 0 ? 1ULL : 0ULL;
-                Pv[g] = Mh | ~(Xv | Ph);
-                Mv[g] = Ph & Xv;
-                hin = ho;
-                if (w == W - 1) score += ho;
+            const unsigned long long *eqrow = vm_peq + vm_at(txt, j) * max_words + w0;
+#pragma unroll
+            for (int g = 0; g < NW; ++g) {
+                if (g < G && w0 + g < W) {
+                    unsigned long long Eq = eqrow[g];
+                    const unsigned long long pv = Pv[g], mv = Mv[g];
+                    const unsigned long long neg = hin < 0 ? 1ULL : 0ULL;
+                    const unsigned long long Xv = Eq | mv;
+                    Eq |= neg;
+                    const unsigned long long Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                    unsigned long long Ph = mv | ~(Xh | pv);
+                    unsigned long long Mh = pv & Xh;
+                    const int ho = (int)(Ph >> 63) - (int)(Mh >> 63);
+                    Ph <<= 1;
+                    Mh <<= 1;
+                    Mh |= neg;
+                    Ph |= hin > 0 ? 1ULL : 0ULL;
+                    Pv[g] = Mh | ~(Xv | Ph);
+                    Mv[g] = Ph & Xv;
+                    hin = ho;
+                    if (w0 + g == W - 1) score += ho;
+                }
             }
             hout = hin;
         }
         hout_prev = hout;
     }
     if (owns_last) {
-        const int g = (W - 1) - w0;
+        const int gl = (W - 1) - w0;
+        unsigned long long pvl = 0, mvl = 0;
+#pragma unroll
+        for (int g = 0; g < NW; ++g)
+            if (g == gl) { pvl = Pv[g]; mvl = Mv[g]; }
         const int first_pad = m - 64 * (W - 1);     // bits >= first_pad of the last word are padding rows
         for (int b = first_pad; b < 64; ++b) {
-            if (Pv[g] >> b & 1ULL) --score;
-            if (Mv[g] >> b & 1ULL) ++score;
+            if (pvl >> b & 1ULL) --score;
+            if (mvl >> b & 1ULL) ++score;
         }
         J.result0 = score;
     }
 }
 
-int vm_launch_edit_distance(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int max_words, cudaStream_t stream)
+template <int GT>
+static void vm_ed_launch_class(VmAlnJobDev *jobs, const int *ids, int n_ids, VmSeqSources src, int max_words, cudaStream_t stream)
 {
-    if (n_jobs <= 0) return 0;
+    if (n_ids <= 0) return;
     const size_t smem = (size_t)max_words * 5 * 8;
-    cudaFuncSetAttribute(vm_edit_distance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vm_edit_distance_kernel<<<n_jobs, 32, smem, stream>>>(jobs, src, max_words);
-    return 1;
+    cudaFuncSetAttribute(vm_edit_distance_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    vm_edit_distance_kernel<GT><<<n_ids, 32, smem, stream>>>(jobs, ids, src, max_words);
+}
+
+// ids_dev: job indices grouped by class; class_start[0..6]: classes GT = 1, 2, 4, 8, 16, generic;
+// class_words[c]: largest pattern word count in class c (sizes the Peq table in shared memory)
+int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
+                            cudaStream_t stream)
+{
+    int launches = 0;
+    for (int c = 0; c < 6; ++c) {
+        const int n_ids = class_start[c + 1] - class_start[c];
+        if (n_ids <= 0) continue;
+        const int *ids = ids_dev + class_start[c];
+        const int mw = class_words[c] > 0 ? class_words[c] : 1;
+        switch (c) {
+        case 0: vm_ed_launch_class<1>(jobs, ids, n_ids, src, mw, stream); break;
+        case 1: vm_ed_launch_class<2>(jobs, ids, n_ids, src, mw, stream); break;
+        case 2: vm_ed_launch_class<4>(jobs, ids, n_ids, src, mw, stream); break;
+        case 3: vm_ed_launch_class<8>(jobs, ids, n_ids, src, mw, stream); break;
+        case 4: vm_ed_launch_class<16>(jobs, ids, n_ids, src, mw, stream); break;
+        default: vm_ed_launch_class<0>(jobs, ids, n_ids, src, mw, stream); break;
+        }
+        ++launches;
+    }
+    return launches;
 }
 
 // ---------------------------------------------------------------------------

@@ -32,7 +32,8 @@ struct VmSeqSources {
     const int64_t *read_off;
 };
 
-int vm_launch_edit_distance(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int max_words, cudaStream_t stream);
+int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
+                            cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);
 // dir: direction bytes, vm_fill_dir_bytes(tlen, qlen) per job at dir_off (8-byte aligned);
 // band_scratch: 3 * qlen ints per job whose target exceeds vm_fill_band_rows() rows (sc_off, else -1)

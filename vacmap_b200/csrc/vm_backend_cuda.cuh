@@ -400,9 +400,25 @@ public:
             ed_cells_ += (double)J[j].q.len * (double)J[j].t.len;
         }
         if (max_words > 32 * 64) throw std::runtime_error("edit distance: sequence longer than 131072 bases is not supported yet");
+        // class by words per lane: 1, 2, 4, 8, 16 (state in registers), else generic
+        std::vector<std::vector<int>> cls(6);
+        int class_words[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < nj; ++j) {
+            const int W = (J[j].q.len + 63) / 64, G = (W + 31) / 32;
+            const int k = G <= 1 ? 0 : G <= 2 ? 1 : G <= 4 ? 2 : G <= 8 ? 3 : G <= 16 ? 4 : 5;
+            cls[k].push_back(j);
+            class_words[k] = std::max(class_words[k], W);
+        }
+        std::vector<int> ids;
+        int class_start[7];
+        for (int k = 0; k < 6; ++k) { class_start[k] = (int)ids.size(); ids.insert(ids.end(), cls[k].begin(), cls[k].end()); }
+        class_start[6] = (int)ids.size();
+        BE_OK(d_seg_.ensure(ids.size() * 4 + 64));
+        BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
         KTimer kt(this, "k_edit_distance");
-        c_->launches += vm_launch_edit_distance(jobs_.as<VmAlnJobDev>(), nj, sources(), max_words, c_->stream);
+        c_->launches += vm_launch_edit_distance(jobs_.as<VmAlnJobDev>(), d_seg_.as<int>(), class_start, class_words, sources(),
+                                                c_->stream);
         kt.stop();
         BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
