@@ -183,6 +183,12 @@ struct VmClSlot {
     int first;
 };
 
+__global__ void vm_cl_init_kernel(VmClSlot *t, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { t[i].key = VM_CL_EMPTY; t[i].count = 0; t[i].first = 0x7fffffff; }
+}
+
 __device__ __forceinline__ long long vm_cluster_key(const VmAnchor &a)
 {
     const long long diag = a.s == 1 ? (long long)a.y - a.x : (long long)a.y + a.x;
@@ -374,10 +380,9 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     SEED_OK(cudaMemcpyAsync(B.a_off.p, a_off_host.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
     SEED_OK(cudaMemcpyAsync(B.t_off.p, t_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
     if (t_off[n] > 0) {
-        // {key = EMPTY (0x7f ff..), count = 0, first = INT_MAX}: fill with a tiny kernel-free pattern
-        std::vector<VmClSlot> init((size_t)t_off[n], VmClSlot{VM_CL_EMPTY, 0, 0x7fffffff});
-        SEED_OK(cudaMemcpyAsync(B.table.p, init.data(), init.size() * sizeof(VmClSlot), cudaMemcpyHostToDevice, stream));
-        SEED_OK(cudaStreamSynchronize(stream));
+        vm_cl_init_kernel<<<(unsigned)((t_off[n] + 255) / 256), 256, 0, stream>>>(B.table.as<VmClSlot>(), t_off[n]);
+        *launches += 1;
+        SEED_OK(cudaStreamSynchronize(stream));   // a_off / t_off staging vectors are about to go out of scope
     }
     vm_seed_expand_kernel<<<n, 32, 0, stream>>>(ix, off_dev, B.mz_posz.as<uint32_t>(), B.n_mz.as<int32_t>(),
                                                 B.mz_start.as<uint32_t>(), B.mz_cnt.as<uint32_t>(), B.mz_aoff.as<uint32_t>(),
