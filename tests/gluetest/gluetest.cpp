@@ -189,15 +189,20 @@ struct OracleBackend : public Backend {
         }
     }
 
-    void fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) override
+    std::vector<uint32_t> fill_ops_;
+    const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) override
     {
+        fill_ops_.clear();
         for (FillJobRef &j : jobs) {
             const std::string t = materialize(b, j.read, j.job.target), q = materialize(b, j.read, j.job.query);
             orc_kc_result res;
             std::vector<uint32_t> cig(t.size() + q.size() + 4);
             orc_k_cigar(t.data(), (int32_t)t.size(), q.data(), (int32_t)q.size(), 2, -4, 4, 2, 24, 1, -1, -1, eqx ? 1 : 0, cig.data(), (int32_t)cig.size(), &res);
-            j.cigar.assign(cig.begin(), cig.begin() + res.n_cigar);
+            j.cig_off = (int64_t)fill_ops_.size();
+            j.cig_len = res.n_cigar;
+            fill_ops_.insert(fill_ops_.end(), cig.begin(), cig.begin() + res.n_cigar);
         }
+        return fill_ops_.data();
     }
 };
 

@@ -448,11 +448,11 @@ public:
         for (int j = 0; j < nj; ++j) { jobs[j].job.q_e = (int32_t)J[j].result0; jobs[j].job.t_e = (int32_t)J[j].result1; }
     }
 
-    void fill(const ReadBatch &, bool eqx, std::vector<FillJobRef> &jobs) override
+    const uint32_t *fill(const ReadBatch &, bool eqx, std::vector<FillJobRef> &jobs) override
     {
         WallTimer wt(this, "fill");
         const int nj = (int)jobs.size();
-        if (nj == 0) return;
+        if (nj == 0) return nullptr;
         VmAlnJobDev *J = stage_jobs((size_t)nj);
         int64_t out_off = 0, dir_off = 0, sc_off = 0;
         const int band_rows = vm_fill_band_rows();
@@ -499,8 +499,8 @@ public:
         if (dense > 0) BE_OK(cudaMemcpyAsync(h_cig_.p, d_cigd_.p, (size_t)dense * 4, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
         BE_OK(cudaGetLastError());
-        const uint32_t *cig = h_cig_.as<uint32_t>();
-        for (int j = 0; j < nj; ++j) jobs[j].cigar.assign(cig + dst_off[j], cig + dst_off[j] + len[j]);
+        for (int j = 0; j < nj; ++j) { jobs[j].cig_off = dst_off[j]; jobs[j].cig_len = len[j]; }
+        return h_cig_.as<uint32_t>();
     }
 
 private:

@@ -113,6 +113,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         be.reads_resident = resident != 0;
         int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
         Driver drv(be, h->ctg, opt, h->ix->k, threads);
+        drv.on_time = [&](const char *nm, double ms) { be.timer.add(nm, ms); };
         ReadBatch b;
         b.n = n_reads;
         b.seq = seqs;
@@ -121,6 +122,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         auto t0 = std::chrono::steady_clock::now();
         drv.align_batch(b, br);
         const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        auto t1 = std::chrono::steady_clock::now();
         res->rec_off.assign((size_t)n_reads + 1, 0);
         for (int64_t r = 0; r < n_reads; ++r) {
             for (const vmg::Record &rec : br.records[r]) {
@@ -137,6 +139,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
             res->rec_off[r + 1] = (int64_t)res->recs.size();
         }
         be.timer.add("total", total);
+        be.timer.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         be.timer.add("n_fill_cells", be.fill_cells_);
         be.timer.add("n_fill_bases", be.fill_bases_);
         be.timer.add("n_fill_jobs", be.fill_jobs_);
@@ -217,11 +220,11 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
                 jobs[j].job.target = ref_of(t_off[j], t_off[j + 1]);
                 jobs[j].job.query = ref_of(tt + q_off[j], tt + q_off[j + 1]);
             }
-            be.fill(b, eqx != 0, jobs);
+            const uint32_t *ops = be.fill(b, eqx != 0, jobs);
             int64_t co = 0;
             for (int64_t j = 0; j < n_pairs; ++j) {
-                out0[j] = (int64_t)jobs[j].cigar.size();
-                if (cigar && !jobs[j].cigar.empty()) memcpy(cigar + co, jobs[j].cigar.data(), jobs[j].cigar.size() * 4);
+                out0[j] = (int64_t)jobs[j].cig_len;
+                if (cigar && jobs[j].cig_len > 0) memcpy(cigar + co, ops + jobs[j].cig_off, (size_t)jobs[j].cig_len * 4);
                 co += (t_off[j + 1] - t_off[j]) + (q_off[j + 1] - q_off[j]) + 2;
             }
         }

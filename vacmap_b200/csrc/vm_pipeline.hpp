@@ -8,6 +8,7 @@
 #pragma once
 #include "vm_glue.hpp"
 #include <atomic>
+#include <chrono>
 #include <functional>
 #include <thread>
 
@@ -47,7 +48,8 @@ struct ChainOut {
 struct GuideJobRef { int32_t read; vmg::GuideJob job; };
 struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; };
 struct ExtJobRef { int32_t read; vmg::ExtJob job; };
-struct FillJobRef { int32_t read; vmg::FillJob job; std::vector<uint32_t> cigar; };
+// CIGAR ops of a fill job: cig[cig_off .. cig_off + cig_len) of the array Backend::fill hands back
+struct FillJobRef { int32_t read; vmg::FillJob job; int64_t cig_off = 0; int32_t cig_len = 0; };
 
 // The hot loops.  Every method processes the jobs of a whole batch; consecutive hot loops whose
 // hand-over needs no host decision are fused so the data never leaves the device in between.
@@ -64,7 +66,8 @@ struct Backend {
                               ChainOut &out) = 0;
     virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) = 0;
     virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
-    virtual void fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
+    // sets cig_off / cig_len of every job; the returned array stays valid until the next fill()
+    virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
 };
 
 static inline void parallel_for(int64_t n, int threads, const std::function<void(int64_t)> &fn)
@@ -122,6 +125,17 @@ public:
     Driver(Backend &be, const vmg::Contigs &ctg, const vmg::Options &opt, int kmersize, int threads)
         : be_(be), ctg_(ctg), opt_(opt), k_(kmersize), threads_(threads) {}
 
+    // optional wall-clock accounting of the host glue phases (name, milliseconds)
+    std::function<void(const char *, double)> on_time;
+    struct Phase {
+        Driver *d; const char *name; std::chrono::steady_clock::time_point t0;
+        Phase(Driver *d_, const char *n) : d(d_), name(n), t0(std::chrono::steady_clock::now()) {}
+        ~Phase()
+        {
+            if (d->on_time) d->on_time(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    };
+
     void align_batch(const ReadBatch &b, BatchResult &res)
     {
         const int64_t n = b.n;
@@ -137,6 +151,7 @@ public:
 
         // ---- 3. hit2work bookkeeping + guide selection ----
         std::vector<std::vector<GuideJobRef>> gjobs((size_t)n);
+        Phase *ph = new Phase(this, "g_hit2work");
         parallel_for(n, threads_, [&](int64_t r) {
             const int64_t m = g.cnt[r];
             if (m <= 2) return;                       // decode_hit :23986 -- <= 2 anchors: unmapped
@@ -169,12 +184,14 @@ public:
             } else variant[r] = 1;
         }
         gjobs.clear();
+        delete ph;
 
         // ---- 4-5. local re-seeding + local chaining (fused on the device) ----
         ChainOut lc;
         be_.reseed_chain(b, need_rev, all_gjobs, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
 
         // ---- 6. traceback, then extend_func as a staged state machine ----
+        ph = new Phase(this, "g_traceback");
         parallel_for(n, threads_, [&](int64_t r) {
             ReadState &s = st[r];
             if (!s.alive) return;
@@ -184,6 +201,7 @@ public:
             if (s.asc.size() <= 1) s.alive = false;
             s.nofilter = opt_.nodiscard;
         });
+        delete ph;
         std::vector<int64_t> todo;
         for (int64_t r = 0; r < n; ++r)
             if (st[r].alive) todo.push_back(r);
@@ -198,8 +216,12 @@ public:
             }
         }
         if (!again.empty()) extend_pass(b, read_len, st, again);
-        for (int64_t r = 0; r < n; ++r)
-            if (st[r].alive) res.records[r].swap(st[r].recs);
+        {
+            Phase p2(this, "g_finish");
+            for (int64_t r = 0; r < n; ++r)
+                if (st[r].alive) res.records[r].swap(st[r].recs);
+            st.clear();
+        }
     }
 
 private:
@@ -209,6 +231,7 @@ private:
     {
         const int64_t m = (int64_t)ids.size();
         // a. rebuild_chain_break + divergence filter jobs
+        Phase *ph = new Phase(this, "g_ext_rebuild");
         std::vector<std::vector<EdJob>> edj((size_t)m);
         parallel_for(m, threads_, [&](int64_t t) {
             const int64_t r = ids[t];
@@ -235,7 +258,9 @@ private:
             ed.insert(ed.end(), edj[t].begin(), edj[t].end());
         }
         ed_start[m] = (int64_t)ed.size();
+        delete ph;
         be_.edit_distance(b, ed);
+        ph = new Phase(this, "g_ext_edges");
         parallel_for(m, threads_, [&](int64_t t) {
             ReadState &s = st[ids[t]];
             if (!s.alive) return;
@@ -262,6 +287,8 @@ private:
             if (s.al.size() < s.n0) { s.filtered = true; changed.push_back(ids[t]); }
         }
         if (!changed.empty()) extend_rounds(b, read_len, st, changed);
+        delete ph;
+        ph = new Phase(this, "g_ext_split");
         // d. merge / inversion fix / fill jobs
         std::vector<std::vector<FillJobRef>> fj((size_t)m);
         parallel_for(m, threads_, [&](int64_t t) {
@@ -295,7 +322,9 @@ private:
             for (FillJobRef &j : fj[t]) fills.push_back(std::move(j));
         }
         f_start[m] = (int64_t)fills.size();
-        be_.fill(b, opt_.eqx, fills);
+        delete ph;
+        const uint32_t *cig_ops = be_.fill(b, opt_.eqx, fills);
+        Phase p3(this, "g_ext_records");
         // e. records
         parallel_for(m, threads_, [&](int64_t t) {
             const int64_t r = ids[t];
@@ -304,7 +333,7 @@ private:
             std::vector<std::vector<uint32_t>> cig(s.al.size());
             for (int64_t q = f_start[t]; q < f_start[t + 1]; ++q) {
                 std::vector<uint32_t> &dst = cig[fills[q].job.aln];
-                dst.insert(dst.end(), fills[q].cigar.begin(), fills[q].cigar.end());
+                dst.insert(dst.end(), cig_ops + fills[q].cig_off, cig_ops + fills[q].cig_off + fills[q].cig_len);
             }
             try {
                 vmg::make_records(s.kept, cig, s.mapq, read_len[r], ctg_, s.need_reverse, opt_.hardclip, s.recs);
