@@ -21,31 +21,6 @@
 #define VM_NEG (-0x40000000)
 #define VM_ED_MAXG 64
 
-struct VmSeqView {
-    const uint8_t *p;   // address of element 0
-    int step;           // +1 / -1
-    int comp;
-    int len;
-};
-
-__device__ __forceinline__ VmSeqView vm_view(const VmSeqSources &S, const VmSeqSpec &s, int read)
-{
-    const uint8_t *base = s.src == 0 ? S.ref : ((s.src == 1 ? S.reads_fwd : S.reads_rc) + S.read_off[read]);
-    VmSeqView v;
-    v.len = s.len;
-    v.comp = s.comp;
-    if (s.reverse) { v.p = base + s.lo + s.len - 1; v.step = -1; }
-    else { v.p = base + s.lo; v.step = 1; }
-    return v;
-}
-
-__device__ __forceinline__ int vm_at(const VmSeqView &v, int i)
-{
-    int c = vm_code5(__ldg(v.p + (long long)i * v.step));
-    if (v.comp && c < 4) c = 3 - c;
-    return c;
-}
-
 // ---------------------------------------------------------------------------
 // edit distance
 // ---------------------------------------------------------------------------
@@ -287,148 +262,3 @@ int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream
     return 1;
 }
 
-// ---------------------------------------------------------------------------
-// global fill with traceback: strip-per-lane pipelined wavefront, registers only
-//
-// Lane l of the warp owns VM_FILL_R consecutive target rows; at pipeline step s it computes the
-// column q = s - l of its strip top to bottom in registers (H of the previous column, F1, F2 per
-// row; E1/E2 carried down the column), takes H/E1/E2 of the row above from lane l-1 with three
-// shuffles, and stores its VM_FILL_R direction bytes as ONE 8-byte word at [step][lane] -- a
-// coalesced 256-byte line per warp step.  No shared memory, so 32 warps/SM stay resident and the
-// latency of the (global-memory) traceback of one warp hides behind the DP of the others.
-// Targets longer than 32*VM_FILL_R rows are processed in bands; the bottom row of a band is
-// handed to the next through 3*qlen ints of global scratch.
-// ---------------------------------------------------------------------------
-#define VM_FILL_R 8
-#define VM_FILL_ROWS (32 * VM_FILL_R)
-
-__device__ __forceinline__ long long vm_fill_dir_index(int t, int q, int qlen)
-{
-    const int band = t / VM_FILL_ROWS, tb = t % VM_FILL_ROWS;
-    const int lane = tb / VM_FILL_R, r = tb % VM_FILL_R;
-    return (long long)band * (qlen + 32) * VM_FILL_ROWS + (long long)(q + lane) * VM_FILL_ROWS + lane * VM_FILL_R + r;
-}
-
-__global__ void __launch_bounds__(128) vm_fill_kernel(VmAlnJobDev *jobs, int n_jobs, VmSeqSources S, int eqx,
-                                                      uint8_t *__restrict__ dir_all, int32_t *__restrict__ band_scratch,
-                                                      uint32_t *__restrict__ cigar_out)
-{
-    const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (job >= n_jobs) return;
-    VmAlnJobDev &J = jobs[job];
-    const int lane = threadIdx.x & 31;
-    const VmSeqView T = vm_view(S, J.t, J.read), Q = vm_view(S, J.q, J.read);
-    const int tlen = T.len, qlen = Q.len;
-    if (tlen <= 0 || qlen <= 0) { if (lane == 0) J.n_out = 0; return; }
-    const VmGapPar g{2, -4, 4, 2, 24, 1};
-    uint8_t *dir = dir_all + J.dir_off;
-    int32_t *bs = J.sc_off >= 0 ? band_scratch + J.sc_off : nullptr;
-    const int nbands = (tlen + VM_FILL_ROWS - 1) / VM_FILL_ROWS;
-    for (int band = 0; band < nbands; ++band) {
-        const int row0 = band * VM_FILL_ROWS + lane * VM_FILL_R;
-        int tc[VM_FILL_R], Hleft[VM_FILL_R], F1[VM_FILL_R], F2[VM_FILL_R];
-#pragma unroll
-        for (int r = 0; r < VM_FILL_R; ++r) {
-            const int t = row0 + r;
-            tc[r] = t < tlen ? vm_at(T, t) : 4;
-            const int hb = vm_boundary_h(g, t + 1);     // H(t, -1)
-            Hleft[r] = hb;
-            F1[r] = hb - g.q1 - g.e1;
-            F2[r] = hb - g.q2 - g.e2;
-        }
-        int Hdiag_top = row0 == 0 ? 0 : vm_boundary_h(g, row0);   // H(row0-1, -1)
-        const int rows_in_band = (tlen - band * VM_FILL_ROWS) < VM_FILL_ROWS ? (tlen - band * VM_FILL_ROWS) : VM_FILL_ROWS;
-        const int last_lane = (rows_in_band - 1) / VM_FILL_R;
-        uint8_t *dband = dir + (long long)band * (qlen + 32) * VM_FILL_ROWS;
-        int outH = 0, outE1 = 0, outE2 = 0, qc_pipe = 4;
-        const int nsteps = qlen + last_lane;
-        for (int s = 0; s < nsteps; ++s) {
-            int inH = __shfl_up_sync(VM_FULL, outH, 1);
-            int inE1 = __shfl_up_sync(VM_FULL, outE1, 1);
-            int inE2 = __shfl_up_sync(VM_FULL, outE2, 1);
-            int qc = __shfl_up_sync(VM_FULL, qc_pipe, 1);
-            const int q = s - lane;
-            if (lane == 0) {
-                qc = s < qlen ? vm_at(Q, s) : 4;
-                if (band == 0) {
-                    inH = vm_boundary_h(g, q + 1);      // H(-1, q)
-                    inE1 = inH - g.q1 - g.e1;
-                    inE2 = inH - g.q2 - g.e2;
-                } else if (q < qlen) {
-                    inH = bs[q];
-                    inE1 = bs[qlen + q];
-                    inE2 = bs[2 * qlen + q];
-                }
-            }
-            qc_pipe = qc;
-            if (q >= 0 && q < qlen && row0 < tlen) {
-                int hd = Hdiag_top, e1 = inE1, e2 = inE2, lastH = 0;
-                unsigned long long packed = 0;
-#pragma unroll
-                for (int r = 0; r < VM_FILL_R; ++r) {
-                    if (row0 + r < tlen) {
-                        const int hold = Hleft[r];
-                        int H, E1n, F1n, E2n, F2n;
-                        unsigned d;
-                        vm_cell(g, tc[r], qc, hd, e1, F1[r], e2, F2[r], H, E1n, F1n, E2n, F2n, d);
-                        Hleft[r] = H; F1[r] = F1n; F2[r] = F2n;
-                        e1 = E1n; e2 = E2n;
-                        hd = hold;
-                        lastH = H;
-                        packed |= (unsigned long long)d << (8 * r);
-                    }
-                }
-                outH = lastH; outE1 = e1; outE2 = e2;
-                Hdiag_top = inH;
-                *(unsigned long long *)(dband + (long long)s * VM_FILL_ROWS + lane * VM_FILL_R) = packed;
-                if (band + 1 < nbands && lane == 31) { bs[q] = outH; bs[qlen + q] = e1; bs[2 * qlen + q] = e2; }
-            }
-        }
-        __syncwarp();
-    }
-    if (lane != 0) return;
-    // ksw_backtrack (left-aligned), ops pushed in reverse then flipped
-    uint32_t *out = cigar_out + J.out_off;
-    int n = 0;
-    int i = tlen - 1, j = qlen - 1, state = 0;
-    while (i >= 0 && j >= 0) {
-        const unsigned tmp = dir[vm_fill_dir_index(i, j, qlen)];
-        if (state == 0) state = tmp & 7;
-        else if (!((tmp >> (state + 2)) & 1)) state = 0;
-        if (state == 0) state = tmp & 7;
-        unsigned op;
-        if (state == 0) {
-            op = 0;
-            if (eqx) op = vm_at(T, i) == vm_at(Q, j) ? 7 : 8;
-            --i; --j;
-        } else if (state == 1 || state == 3) { op = 2; --i; }
-        else { op = 1; --j; }
-        if (n > 0 && (out[n - 1] & 0xf) == op) out[n - 1] += 1u << 4;
-        else out[n++] = 1u << 4 | op;
-    }
-    if (i >= 0) {
-        if (n > 0 && (out[n - 1] & 0xf) == 2u) out[n - 1] += (unsigned)(i + 1) << 4;
-        else out[n++] = (unsigned)(i + 1) << 4 | 2u;
-    }
-    if (j >= 0) {
-        if (n > 0 && (out[n - 1] & 0xf) == 1u) out[n - 1] += (unsigned)(j + 1) << 4;
-        else out[n++] = (unsigned)(j + 1) << 4 | 1u;
-    }
-    for (int x = 0, y = n - 1; x < y; ++x, --y) { const uint32_t t = out[x]; out[x] = out[y]; out[y] = t; }
-    J.n_out = n;
-}
-
-size_t vm_fill_dir_bytes(int tlen, int qlen)
-{
-    const size_t nbands = ((size_t)tlen + VM_FILL_ROWS - 1) / VM_FILL_ROWS;
-    return nbands * ((size_t)qlen + 32) * VM_FILL_ROWS;
-}
-int vm_fill_band_rows() { return VM_FILL_ROWS; }
-
-int vm_launch_fill(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int eqx, uint8_t *dir, int32_t *band_scratch,
-                   uint32_t *cigar_out, cudaStream_t stream)
-{
-    if (n_jobs <= 0) return 0;
-    vm_fill_kernel<<<(n_jobs + 3) / 4, 128, 0, stream>>>(jobs, n_jobs, src, eqx, dir, band_scratch, cigar_out);
-    return 1;
-}

@@ -2,6 +2,7 @@
 // Job descriptors shared between the host backend and the kernels (see vm_align.cu).
 #pragma once
 #include "vm_common.cuh"
+#include <vector>
 
 // one side of an alignment job: a slice of the reference or of a read, optionally reversed /
 // complemented on the fly (the reference materialises reversed / reverse-complemented strings,
@@ -32,12 +33,53 @@ struct VmSeqSources {
     const int64_t *read_off;
 };
 
+#ifdef __CUDACC__
+#include "vm_index.cuh"
+struct VmSeqView {
+    const uint8_t *p;   // address of element 0
+    int step;           // +1 / -1
+    int comp;
+    int len;
+};
+
+__device__ __forceinline__ VmSeqView vm_view(const VmSeqSources &S, const VmSeqSpec &s, int read)
+{
+    const uint8_t *base = s.src == 0 ? S.ref : ((s.src == 1 ? S.reads_fwd : S.reads_rc) + S.read_off[read]);
+    VmSeqView v;
+    v.len = s.len;
+    v.comp = s.comp;
+    if (s.reverse) { v.p = base + s.lo + s.len - 1; v.step = -1; }
+    else { v.p = base + s.lo; v.step = 1; }
+    return v;
+}
+
+__device__ __forceinline__ int vm_at(const VmSeqView &v, int i)
+{
+    int c = vm_code5(__ldg(v.p + (long long)i * v.step));
+    if (v.comp && c < 4) c = 3 - c;
+    return c;
+}
+
+#endif
+
 int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
                             cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);
-// dir: direction bytes, vm_fill_dir_bytes(tlen, qlen) per job at dir_off (8-byte aligned);
-// band_scratch: 3 * qlen ints per job whose target exceeds vm_fill_band_rows() rows (sc_off, else -1)
-size_t vm_fill_dir_bytes(int tlen, int qlen);
-int vm_fill_band_rows();
-int vm_launch_fill(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, int eqx, uint8_t *dir, int32_t *band_scratch,
-                   uint32_t *cigar_out, cudaStream_t stream);
+
+// ---- global fill (vm_fill.cu) ----
+// Two jobs share a warp (one per half of every half2 register); b = -1: no partner.
+struct VmFillPair { int32_t a, b; };
+// One launch = one capacity class: R target rows per lane (32*R rows per band), pairs [pair_begin, pair_end)
+struct VmFillLaunch {
+    int R, multiband, pair_begin, pair_end, blocks;
+    long long dir_words_per_warp, band_words_per_warp;
+};
+struct VmFillPlan {
+    std::vector<VmFillPair> pairs;
+    std::vector<VmFillLaunch> launches;
+    size_t dir_words = 0, band_words = 0;   // scratch needed (uint32 words), shared by the launches
+};
+void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan);
+// counters_dev: one zeroed int per launch; returns the number of kernel launches
+int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs_dev, const VmFillPair *pairs_dev, VmSeqSources src, int eqx,
+                   uint32_t *dir_scratch, uint32_t *band_scratch, int *counters_dev, uint32_t *cigar_out, cudaStream_t stream);

@@ -73,7 +73,7 @@ public:
     {
         seed_.release();
         VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
-                         &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_};
+                         &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_};
         for (VmDevBuf *x : b) x->release();
         VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_};
         for (VmPinnedBuf *x : p) x->release();
@@ -454,30 +454,32 @@ public:
         const int nj = (int)jobs.size();
         if (nj == 0) return nullptr;
         VmAlnJobDev *J = stage_jobs((size_t)nj);
-        int64_t out_off = 0, dir_off = 0, sc_off = 0;
-        const int band_rows = vm_fill_band_rows();
+        int64_t out_off = 0;
         for (int j = 0; j < nj; ++j) {
             memset(&J[j], 0, sizeof(VmAlnJobDev));
             J[j].t = spec(jobs[j].job.target);
             J[j].q = spec(jobs[j].job.query);
             J[j].read = jobs[j].read;
             J[j].out_off = out_off;
-            J[j].dir_off = dir_off;
             out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
-            dir_off += (int64_t)((vm_fill_dir_bytes(J[j].t.len, J[j].q.len) + 7) & ~(size_t)7);
-            if (J[j].t.len > band_rows) { J[j].sc_off = sc_off; sc_off += 3LL * J[j].q.len; }
-            else J[j].sc_off = -1;
             fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;
             fill_bases_ += (double)J[j].t.len + (double)J[j].q.len;
         }
         fill_jobs_ += nj;
-        BE_OK(d_dir_.ensure((size_t)dir_off + 64));
-        BE_OK(d_sc_.ensure((size_t)sc_off * 4 + 64));
+        vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_);
+        BE_OK(d_dir_.ensure(plan_.dir_words * 4 + 64));
+        BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
         BE_OK(d_cig_.ensure((size_t)out_off * 4 + 64));
+        BE_OK(d_pairs_.ensure(plan_.pairs.size() * sizeof(VmFillPair) + plan_.launches.size() * 4 + 64));
+        int *d_ctr = (int *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
         BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+        if (!plan_.pairs.empty())
+            BE_OK(cudaMemcpyAsync(d_pairs_.p, plan_.pairs.data(), plan_.pairs.size() * sizeof(VmFillPair), cudaMemcpyHostToDevice,
+                                  c_->stream));
+        BE_OK(cudaMemsetAsync(d_ctr, 0, plan_.launches.size() * 4 + 4, c_->stream));
         KTimer kt(this, "k_fill");
-        c_->launches += vm_launch_fill(jobs_.as<VmAlnJobDev>(), nj, sources(), eqx ? 1 : 0, d_dir_.as<uint8_t>(), d_sc_.as<int32_t>(),
-                                       d_cig_.as<uint32_t>(), c_->stream);
+        c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
+                                       d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(), c_->stream);
         kt.stop();
         BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
@@ -508,7 +510,8 @@ private:
     vm_index_handle *ih_;
     VmSeedBufs seed_;
     VmDevBuf reads_fwd_, reads_rc_, read_off_, jobs_, d_wlo_, d_whi_, d_gx_, d_gy_, d_nh_, d_hits_, d_tab_, d_order_, d_rout_,
-        d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_;
+        d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_;
+    VmFillPlan plan_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_;
     std::vector<int64_t> off_host_;
 };

@@ -1,0 +1,406 @@
+// Global dual-affine fill with traceback: replaces mp.k_cigar(target, query, 2, -4, 4, 2, 24, 1, bw=-1,
+// zdropvalue=-1, eqx) at mammap_clrnano.py:21554, 21598.  Recurrences, tie order (diag > E1 > F1 > E2 > F2),
+// left-aligned gaps and boundary conditions are those of oracle/orc_align.c (ksw2 extd2 semantics).
+//
+// Design (sm_100a, no tensor cores -- integer-valued DP, nothing here is a dense contraction):
+//  * Difference recurrences.  The kernel carries ksw2's u/v/x/y quantities (differences between neighbouring
+//    cells, all within +-64 for these penalties) instead of absolute scores.  Every comparison of the absolute
+//    recurrence is a comparison of the same two numbers shifted by H(i-1,j-1), so the direction bits are
+//    identical, and the small range makes the arithmetic EXACT in fp16.  Two jobs share a warp: job A lives in
+//    the low half and job B in the high half of every half2 register, one HADD2 / HMNMX2 / HSET2 serves both
+//    (the packed-integer video instructions are emulated on this architecture, half2 is native and splits
+//    between the FMA pipe (HADD2, HFMA2.RELU) and the ALU pipe (HSET2, HMNMX2, LOP3)).
+//  * Strip-per-lane pipelined wavefront.  Lane l owns R consecutive target rows (R = 2..16 by capacity
+//    class, so a 270-row job runs with R = 10 and no idle rows); at step s it sweeps column s - l of its strip
+//    in registers and hands v/x1/x2 of its bottom row to lane l+1 with three shuffles.
+//  * Direction bytes (3 source bits, 4 gap-continuation bits, 1 match bit for eqx) go to a per-warp scratch
+//    region laid out [step][word][lane] -- every store instruction writes one full 128-byte line -- that is
+//    reused by the next pair of the persistent warp, so the traceback reads mostly hit L2.
+//  * Traceback: two walker lanes (one per job) run on 32-step x R-row tiles the whole warp stages into shared
+//    memory with one round trip, instead of one dependent global load per path cell.
+#include "vm_align.cuh"
+#include <algorithm>
+#include <cuda_fp16.h>
+
+namespace {
+
+struct VmGapPar2 {
+    int match, mismatch, q1, e1, q2, e2;
+};
+__host__ __device__ constexpr VmGapPar2 vm_fill_par() { return VmGapPar2{2, -4, 4, 2, 24, 1}; }
+
+// H on the boundary row / column after `len` gap bases (0 for len == 0)
+__device__ __forceinline__ int vm_hb(int len)
+{
+    constexpr VmGapPar2 g = vm_fill_par();
+    if (len <= 0) return 0;
+    const int a = -(g.q1 + g.e1 * len), b = -(g.q2 + g.e2 * len);
+    return a > b ? a : b;
+}
+
+__device__ __forceinline__ __half2 vm_h2(unsigned bits) { return *reinterpret_cast<__half2 *>(&bits); }
+__device__ __forceinline__ unsigned vm_u32(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
+__device__ __forceinline__ __half2 vm_h2i(int v) { return __half2half2(__int2half_rn(v)); }
+#define VM_H2C(x) __floats2half2_rn((float)(x), (float)(x))
+
+// fp16 bit pattern of a base code; N (and padding) is NaN so that both the ordered == and the ordered != test
+// fail and the substitution score becomes 0
+__device__ __forceinline__ unsigned vm_code_half(int c)
+{
+    return c == 0 ? 0x0000u : c == 1 ? 0x3c00u : c == 2 ? 0x4000u : c == 3 ? 0x4200u : 0x7fffu;
+}
+
+// One cell for both jobs.  in: v = v(i-1,j), x1/x2 = x(i-1,j) from the cell above; u/y1/y2 = from the cell to the
+// left.  out: the same quantities for (i,j), and the direction bits of job A in byte 0 / job B in byte 2.
+__device__ __forceinline__ void vm_cell2(__half2 tc, __half2 qc, __half2 &v, __half2 &x1, __half2 &x2, __half2 &u, __half2 &y1,
+                                         __half2 &y2, unsigned &dir)
+{
+    constexpr VmGapPar2 g = vm_fill_par();
+    const unsigned eqm = __heq2_mask(tc, qc);
+    const __half2 ne1 = __hne2(tc, qc);
+    __half2 z = __hfma2(ne1, VM_H2C(g.mismatch), vm_h2(eqm & (g.match == 2 ? 0x40004000u : 0u)));
+    const __half2 a = __hadd2(x1, v), b = __hadd2(y1, u), a2 = __hadd2(x2, v), b2 = __hadd2(y2, u);
+    unsigned m, dl;
+    m = __hgt2_mask(a, z);  z = __hmax2(z, a);  dl = m & 0x00010001u;
+    m = __hgt2_mask(b, z);  z = __hmax2(z, b);  dl = (dl & ~m) | (m & 0x00020002u);
+    m = __hgt2_mask(a2, z); z = __hmax2(z, a2); dl = (dl & ~m) | (m & 0x00030003u);
+    m = __hgt2_mask(b2, z); z = __hmax2(z, b2); dl = (dl & ~m) | (m & 0x00040004u);
+    const __half2 un = __hsub2(z, v), vn = __hsub2(z, u);
+    const __half2 one = VM_H2C(1), zero = VM_H2C(0);
+    const __half2 t1 = __hsub2(VM_H2C(g.q1), z);          // -(z - q1)
+    const __half2 ap = __hfma2_relu(one, a, t1), bp = __hfma2_relu(one, b, t1);
+    const __half2 t2 = __hsub2(VM_H2C(g.q2), z);
+    const __half2 a2p = __hfma2_relu(one, a2, t2), b2p = __hfma2_relu(one, b2, t2);
+    unsigned d = dl | (eqm & 0x00800080u);
+    d |= __hgt2_mask(ap, zero) & 0x00080008u;
+    d |= __hgt2_mask(bp, zero) & 0x00100010u;
+    d |= __hgt2_mask(a2p, zero) & 0x00200020u;
+    d |= __hgt2_mask(b2p, zero) & 0x00400040u;
+    x1 = __hsub2(ap, VM_H2C(g.q1 + g.e1));
+    y1 = __hsub2(bp, VM_H2C(g.q1 + g.e1));
+    x2 = __hsub2(a2p, VM_H2C(g.q2 + g.e2));
+    y2 = __hsub2(b2p, VM_H2C(g.q2 + g.e2));
+    u = un;
+    v = vn;
+    dir = d;
+}
+
+template <int R, bool MB>
+__global__ void __launch_bounds__(128) vm_fill_kernel(VmAlnJobDev *jobs, const VmFillPair *__restrict__ pairs, int pair_begin,
+                                                      int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
+                                                      long long dir_words_per_warp, uint32_t *band_all,
+                                                      long long band_words_per_warp, int *counter, uint32_t *cigar_out)
+{
+    static_assert(R % 2 == 0 && R >= 2 && R <= 16, "rows per lane");
+    constexpr VmGapPar2 g = vm_fill_par();
+    static_assert(g.match == 2, "score constants are folded into vm_cell2");
+    constexpr int RW = R / 2, ROWS = 32 * R;
+    __shared__ uint32_t tile[4][2][32][RW];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * 4 + warp;
+    uint32_t *dir = dir_all + gw * dir_words_per_warp;
+    uint32_t *bs = MB ? band_all + gw * band_words_per_warp : nullptr;
+    const __half2 nan2 = vm_h2(0x7fff7fffu);
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = pair_begin + atomicAdd(counter, 1);
+        p = __shfl_sync(VM_FULL, p, 0);
+        if (p >= pair_end) break;
+        const VmFillPair pr = pairs[p];
+        const bool hasB = pr.b >= 0;
+        VmAlnJobDev &JA = jobs[pr.a];
+        VmAlnJobDev &JB = jobs[hasB ? pr.b : pr.a];
+        const VmSeqView TA = vm_view(S, JA.t, JA.read), QA = vm_view(S, JA.q, JA.read);
+        const VmSeqView TB = vm_view(S, JB.t, JB.read), QB = vm_view(S, JB.q, JB.read);
+        const int tA = TA.len, qA = QA.len, tB = hasB ? TB.len : 0, qB = hasB ? QB.len : 0;
+        const int tlen = tA > tB ? tA : tB, qlen = qA > qB ? qA : qB;
+        const int nbands = MB ? (tlen + ROWS - 1) / ROWS : 1;
+        unsigned tN = 0;     // bit 0 / 1: the target of job A / B holds an N (eqx needs the sequences there)
+        // ---------------- forward pass ----------------
+        for (int band = 0; band < nbands; ++band) {
+            const int row0 = band * ROWS + lane * R;
+            __half2 tc[R], u[R], y1[R], y2[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int t = row0 + r;
+                const int ca = t < tA ? vm_at(TA, t) : 4, cb = t < tB ? vm_at(TB, t) : 4;
+                if (t < tA && ca == 4) tN |= 1u;
+                if (t < tB && cb == 4) tN |= 2u;
+                tc[r] = vm_h2(vm_code_half(ca) | vm_code_half(cb) << 16);
+                u[r] = vm_h2i(vm_hb(t + 1) - vm_hb(t));           // H(t,-1) - H(t-1,-1)
+                y1[r] = VM_H2C(-(g.q1 + g.e1));
+                y2[r] = VM_H2C(-(g.q2 + g.e2));
+            }
+            const int rows_in_band = (tlen - band * ROWS) < ROWS ? (tlen - band * ROWS) : ROWS;
+            const int last_lane = (rows_in_band - 1) / R;
+            const int nsteps = qlen + last_lane;
+            uint32_t *dband = dir + (long long)band * (qlen + 32) * (RW * 32) + lane;
+            __half2 outV = nan2, outX1 = nan2, outX2 = nan2, qc_pipe = nan2, qbuf = nan2;
+            __half2 hv = nan2, hx1 = nan2, hx2 = nan2;
+            for (int s = 0; s < nsteps; ++s) {
+                if ((s & 31) == 0) {          // stage the next 32 query columns (and band hand-over values)
+                    const int col = s + lane;
+                    const int ca = col < qA ? vm_at(QA, col) : 4, cb = col < qB ? vm_at(QB, col) : 4;
+                    qbuf = vm_h2(vm_code_half(ca) | vm_code_half(cb) << 16);
+                    if (MB && band > 0 && col < qlen) {
+                        hv = vm_h2(bs[col]);
+                        hx1 = vm_h2(bs[qlen + col]);
+                        hx2 = vm_h2(bs[2 * qlen + col]);
+                    }
+                }
+                __half2 inV = __shfl_up_sync(VM_FULL, outV, 1);
+                __half2 inX1 = __shfl_up_sync(VM_FULL, outX1, 1);
+                __half2 inX2 = __shfl_up_sync(VM_FULL, outX2, 1);
+                __half2 qc = __shfl_up_sync(VM_FULL, qc_pipe, 1);
+                const __half2 q0 = __shfl_sync(VM_FULL, qbuf, s & 31);
+                __half2 v0 = nan2, x10 = nan2, x20 = nan2;
+                if (MB) {
+                    v0 = __shfl_sync(VM_FULL, hv, s & 31);
+                    x10 = __shfl_sync(VM_FULL, hx1, s & 31);
+                    x20 = __shfl_sync(VM_FULL, hx2, s & 31);
+                }
+                if (lane == 0) {
+                    qc = q0;
+                    if (!MB || band == 0) {
+                        inV = vm_h2i(vm_hb(s + 1) - vm_hb(s));      // H(-1,q) - H(-1,q-1)
+                        inX1 = VM_H2C(-(g.q1 + g.e1));
+                        inX2 = VM_H2C(-(g.q2 + g.e2));
+                    } else { inV = v0; inX1 = x10; inX2 = x20; }
+                }
+                qc_pipe = qc;
+                const int q = s - lane;
+                if (q >= 0 && q < qlen && lane <= last_lane) {
+                    __half2 v = inV, x1 = inX1, x2 = inX2;
+                    uint32_t *dst = dband + (long long)s * (RW * 32);
+                    unsigned dprev = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        unsigned d;
+                        vm_cell2(tc[r], qc, v, x1, x2, u[r], y1[r], y2[r], d);
+                        if (r & 1) dst[(r >> 1) * 32] = __byte_perm(dprev, d, 0x6420);   // [A even, B even, A odd, B odd]
+                        else dprev = d;
+                    }
+                    outV = v; outX1 = x1; outX2 = x2;
+                    if (MB && band + 1 < nbands && lane == 31) {
+                        bs[q] = vm_u32(v);
+                        bs[qlen + q] = vm_u32(x1);
+                        bs[2 * qlen + q] = vm_u32(x2);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---------------- traceback (ksw_backtrack, left-aligned): lane 0 walks job A, lane 1 job B ----------------
+        tN = __reduce_or_sync(VM_FULL, tN);
+        const int w = lane & 1;
+        const VmSeqView &Tw = w ? TB : TA, &Qw = w ? QB : QA;
+        const int tw = w ? tB : tA, qw = w ? qB : qA;
+        const bool walker = lane < 2 && tw > 0 && qw > 0;
+        uint32_t *out = cigar_out + (w ? JB.out_off : JA.out_off);
+        int i = tw - 1, j = qw - 1, state = 0, n = 0;
+        unsigned cur_op = 0, cur_len = 0;
+        const bool checkN = eqx && ((tN >> w) & 1u);
+        for (;;) {
+            const bool need = walker && i >= 0 && j >= 0;
+            const unsigned needmask = __ballot_sync(VM_FULL, need) & 3u;
+            if (!needmask) break;
+#pragma unroll
+            for (int ws = 0; ws < 2; ++ws) {
+                const int ii = __shfl_sync(VM_FULL, i, ws), jj = __shfl_sync(VM_FULL, j, ws);
+                if (needmask >> ws & 1u) {
+                    const int band_t = ii / ROWS, lane_t = (ii % ROWS) / R, step = jj + lane_t - lane;
+                    if (step >= 0) {
+                        const uint32_t *src = dir + ((long long)band_t * (qlen + 32) + step) * (RW * 32) + lane_t;
+#pragma unroll
+                        for (int m = 0; m < RW; ++m) tile[warp][ws][lane][m] = src[m * 32];
+                    }
+                }
+            }
+            __syncwarp();
+            if (need) {
+                const int band_t = i / ROWS, lane_t = (i % ROWS) / R, s_hi = j + lane_t;
+                while (i >= 0 && j >= 0) {
+                    const int tb = i % ROWS, lc = tb / R, r = tb % R, s = j + lc;
+                    if (i / ROWS != band_t || lc != lane_t || s <= s_hi - 32) break;
+                    const unsigned tmp = (tile[warp][w][s_hi - s][r >> 1] >> (((r & 1) * 2 + w) * 8)) & 0xffu;
+                    if (state == 0) state = tmp & 7;
+                    else if (!((tmp >> (state + 2)) & 1)) state = 0;
+                    if (state == 0) state = tmp & 7;
+                    unsigned op;
+                    if (state == 0) {
+                        op = 0;
+                        if (eqx) {
+                            op = (tmp & 0x80u) ? 7u : 8u;
+                            if (checkN && op == 8u && vm_at(Tw, i) == vm_at(Qw, j)) op = 7u;
+                        }
+                        --i; --j;
+                    } else if (state == 1 || state == 3) { op = 2; --i; }
+                    else { op = 1; --j; }
+                    if (op == cur_op) ++cur_len;
+                    else {
+                        if (cur_len) out[n++] = cur_len << 4 | cur_op;
+                        cur_op = op;
+                        cur_len = 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (walker) {
+            if (i >= 0) {
+                if (cur_len && cur_op == 2u) cur_len += (unsigned)(i + 1);
+                else {
+                    if (cur_len) out[n++] = cur_len << 4 | cur_op;
+                    cur_op = 2u;
+                    cur_len = (unsigned)(i + 1);
+                }
+            }
+            if (j >= 0) {
+                if (cur_len && cur_op == 1u) cur_len += (unsigned)(j + 1);
+                else {
+                    if (cur_len) out[n++] = cur_len << 4 | cur_op;
+                    cur_op = 1u;
+                    cur_len = (unsigned)(j + 1);
+                }
+            }
+            if (cur_len) out[n++] = cur_len << 4 | cur_op;
+            if (w == 0) JA.n_out = n;
+            else JB.n_out = n;
+        }
+        __syncwarp();
+        // ops were pushed end to start: flip them, all lanes helping
+#pragma unroll
+        for (int ws = 0; ws < 2; ++ws) {
+            const int nn = __shfl_sync(VM_FULL, walker ? n : 0, ws);
+            uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
+            for (int x = lane; x < nn / 2; x += 32) {
+                const uint32_t a = o[x], b = o[nn - 1 - x];
+                o[x] = b;
+                o[nn - 1 - x] = a;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int R, bool MB>
+int vm_fill_occupancy()
+{
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vm_fill_kernel<R, MB>, 128, 0) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+int vm_fill_blocks_per_sm(int R, bool mb)
+{
+    if (mb) return vm_fill_occupancy<16, true>();
+    switch (R) {
+    case 2: return vm_fill_occupancy<2, false>();
+    case 4: return vm_fill_occupancy<4, false>();
+    case 6: return vm_fill_occupancy<6, false>();
+    case 8: return vm_fill_occupancy<8, false>();
+    case 10: return vm_fill_occupancy<10, false>();
+    case 12: return vm_fill_occupancy<12, false>();
+    case 14: return vm_fill_occupancy<14, false>();
+    default: return vm_fill_occupancy<16, false>();
+    }
+}
+
+} // namespace
+
+// Capacity classes: rows class rc = ceil(tlen / 64) for tlen <= 512 (R = 2 * rc rows per lane, one band),
+// rc = 9 beyond (R = 16, several bands); column class by qlen (<= 512, <= 4096, longer) so that one very long
+// query does not size the scratch of every resident warp.  Inside a class jobs are ordered by qlen and paired
+// with their neighbour: both halves of the half2 registers do useful work for (nearly) the whole sweep.
+void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan)
+{
+    plan.pairs.clear();
+    plan.launches.clear();
+    plan.dir_words = plan.band_words = 0;
+    constexpr int NCLS = 27, NB = 1024;
+    auto key_of = [&](int j, int &cls) {
+        const int tl = J[j].t.len, ql = J[j].q.len;
+        const int rc = tl <= 512 ? (tl + 63) / 64 : 9;
+        const int qc = ql <= 512 ? 0 : ql <= 4096 ? 1 : 2;
+        cls = (rc - 1) * 3 + qc;
+        const int b = qc == 0 ? ql >> 1 : qc == 1 ? ql >> 3 : std::min(ql >> 8, NB - 1);
+        return cls * NB + b;
+    };
+    std::vector<int32_t> count((size_t)NCLS * NB + 1, 0);
+    std::vector<int32_t> keys((size_t)nj, -1);
+    for (int j = 0; j < nj; ++j) {
+        if (J[j].t.len <= 0 || J[j].q.len <= 0) continue;
+        int cls;
+        keys[j] = key_of(j, cls);
+        ++count[(size_t)keys[j] + 1];
+    }
+    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
+    const int n_live = count.back();
+    std::vector<int32_t> order((size_t)n_live);
+    {
+        std::vector<int32_t> pos(count.begin(), count.end() - 1);
+        for (int j = 0; j < nj; ++j)
+            if (keys[j] >= 0) order[(size_t)pos[keys[j]]++] = j;
+    }
+    const size_t mem_cap_words = (size_t)6 << 28;     // 6 GiB of direction scratch at most
+    for (int cls = 0; cls < NCLS; ++cls) {
+        const int lo = count[(size_t)cls * NB], hi = count[(size_t)(cls + 1) * NB];
+        if (hi <= lo) continue;
+        const int rc = cls / 3 + 1;
+        VmFillLaunch L;
+        L.multiband = rc == 9;
+        L.R = L.multiband ? 16 : 2 * rc;
+        L.pair_begin = (int)plan.pairs.size();
+        int max_q = 0, max_t = 0;
+        for (int x = lo; x < hi; x += 2) {
+            VmFillPair pr;
+            pr.a = order[x];
+            pr.b = x + 1 < hi ? order[x + 1] : -1;
+            plan.pairs.push_back(pr);
+        }
+        for (int x = lo; x < hi; ++x) {
+            max_q = std::max(max_q, J[order[x]].q.len);
+            max_t = std::max(max_t, J[order[x]].t.len);
+        }
+        L.pair_end = (int)plan.pairs.size();
+        const int rows = 32 * L.R;
+        const long long nbands = L.multiband ? (max_t + rows - 1) / rows : 1;
+        L.dir_words_per_warp = nbands * ((long long)max_q + 32) * (L.R / 2) * 32;
+        L.band_words_per_warp = L.multiband ? 3LL * max_q + 32 : 0;
+        const int n_pairs = L.pair_end - L.pair_begin;
+        long long blocks = std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0));
+        const long long fit = (long long)(mem_cap_words / (size_t)(4 * L.dir_words_per_warp));
+        blocks = std::max<long long>(1, std::min(blocks, std::max<long long>(fit, 1)));
+        L.blocks = (int)blocks;
+        plan.dir_words = std::max(plan.dir_words, (size_t)(blocks * 4 * L.dir_words_per_warp));
+        plan.band_words = std::max(plan.band_words, (size_t)(blocks * 4 * L.band_words_per_warp));
+        plan.launches.push_back(L);
+    }
+}
+
+int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs, const VmFillPair *pairs, VmSeqSources src, int eqx, uint32_t *dir,
+                   uint32_t *band, int *counters, uint32_t *cigar_out, cudaStream_t stream)
+{
+    int n = 0;
+    for (size_t li = 0; li < plan.launches.size(); ++li) {
+        const VmFillLaunch &L = plan.launches[li];
+        int *ctr = counters + li;
+#define VM_FILL_GO(RR, MBB)                                                                                           \
+    vm_fill_kernel<RR, MBB><<<L.blocks, 128, 0, stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir,       \
+                                                           L.dir_words_per_warp, band, L.band_words_per_warp, ctr, cigar_out)
+        if (L.multiband) VM_FILL_GO(16, true);
+        else switch (L.R) {
+            case 2: VM_FILL_GO(2, false); break;
+            case 4: VM_FILL_GO(4, false); break;
+            case 6: VM_FILL_GO(6, false); break;
+            case 8: VM_FILL_GO(8, false); break;
+            case 10: VM_FILL_GO(10, false); break;
+            case 12: VM_FILL_GO(12, false); break;
+            case 14: VM_FILL_GO(14, false); break;
+            default: VM_FILL_GO(16, false); break;
+            }
+#undef VM_FILL_GO
+        ++n;
+    }
+    return n;
+}
