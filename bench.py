@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--reads", type=int, default=10000, help="reads per GPU per step (configs[1]: 10k)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="reads in the bounded CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workers", type=int, default=0, help="sub-batches in flight per GPU (0 = library default)")
+    ap.add_argument("--chunk", type=int, default=0, help="reads per sub-batch (0 = automatic)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -211,7 +213,7 @@ def main():
     ref, reads, cat, off = make_workload(args.reads, rank)
     ctx = vb._lib.Context(local_rank)
     ix = vb.Index(ref, w=10, k=15, ctx=ctx)
-    al = vb.Aligner(ix, vb.default_option("H"), "H")
+    al = vb.Aligner(ix, vb.default_option("H"), "H", workers=args.workers, chunk_reads=args.chunk)
     bases = int(off[-1])
 
     # ---- device-resident: reads already in HBM when the timed region starts ----

@@ -150,6 +150,8 @@ typedef struct vm_align_params {
     int32_t local_maxgap;     /* 99 (H, S) / 50 (L)  (clrnano:24061) */
     int32_t clamp40;          /* 1 in mode L: min(skipcost, 40) in the multi-chain local DP */
     int32_t host_threads;     /* host glue threads, 0 = all cores */
+    int32_t workers;          /* sub-batches in flight (own CUDA stream each), 0 = default (4), 1 = lock-step */
+    int32_t chunk_reads;      /* reads per sub-batch, 0 = automatic */
 } vm_align_params;
 
 /* One alignment record = one row of `onemapinfolist` (clrnano:20760):
@@ -186,6 +188,8 @@ int vm_seed_batch_rows(vm_ctx *ctx, vm_index_handle *index, int32_t check_num, i
 
 /* Stage-level entry point of the base-level kernels on raw sequence pairs (parity tests).
  * kind 0: edlib.align(query, target, task='distance') (clrnano:19251)        -> out0[j] = distance
+ * kind 3: as kind 0, computed inside the band |i - j| <= out1[j] (out1 is an INPUT): out0[j] = the exact distance
+ *         when it is <= out1[j], else some value > out1[j] -- all the divergence filter (clrnano:19252) needs
  * kind 1: mp.k_cigar(t, q, 2,-4, 4,4,4,4, bw=100, zdropvalue=50) (clrnano:2381) -> out0 = q_e, out1 = t_e
  * kind 2: mp.k_cigar(t, q, 2,-4, 4,2,24,1, bw=-1, zdropvalue=-1, eqx) (clrnano:21554) -> out0[j] = number of
  *         CIGAR ops, written at cigar[cig_off[j]...], cig_off[j] = sum_{i<j} (tlen_i + qlen_i + 2). */

@@ -63,3 +63,27 @@ def test_edit_distance_matches_oracle(gpu_ctx):
     got = pairs_batch("distance", ts, qs, ctx=gpu_ctx)
     for t, q, g in zip(ts, qs, got):
         assert g == oracle.edit_distance(q, t), (len(t), len(q))
+
+
+def test_banded_edit_distance_is_exact_inside_the_band(gpu_ctx):
+    """kind 3: exact when the distance is <= k, some value > k otherwise (slot reuse: bands far narrower than
+    the pattern, bands of a few blocks, k = 0, k one below / equal to the true distance)."""
+    from vacmap_b200.align import pairs_batch
+    rng = np.random.default_rng(34)
+    ts, qs = pairs(rng, 60, 1, 900, err=0.2)
+    t2, q2 = pairs(rng, 10, 6000, 16000, err=0.12)
+    t3, q3 = pairs(rng, 4, 20000, 40000, err=0.03)
+    ts += t2 + t3 + ["ACGT", "ACGTACGTAA"]
+    qs += q2 + q3 + ["ACGT", "ACGTACGTCC"]
+    exact = pairs_batch("distance", ts, qs, ctx=gpu_ctx)
+    for t, q, d in zip(ts[:70], qs[:70], exact[:70]):
+        assert d == oracle.edit_distance(q, t)
+    for mk in (lambda d, m: d, lambda d, m: max(d - 1, 0), lambda d, m: int(0.2 * m), lambda d, m: d + 70,
+               lambda d, m: 0, lambda d, m: int(0.5 * m), lambda d, m: d // 2):
+        band = [mk(d, min(len(t), len(q))) for t, q, d in zip(ts, qs, exact)]
+        got = pairs_batch("distance", ts, qs, ctx=gpu_ctx, band=band)
+        for t, q, d, k, g in zip(ts, qs, exact, band, got):
+            if d <= k:
+                assert g == d, (len(t), len(q), d, k, g)
+            else:
+                assert g > k, (len(t), len(q), d, k, g)

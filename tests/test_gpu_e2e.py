@@ -46,10 +46,20 @@ def test_cuda_matches_oracle_on_fresh_reads(gpu_ctx, seed, mode, kw):
     reads.append(("random", synth.random_seq(np.random.default_rng(1), 3000).tobytes().decode()))
     opt = vb.default_option(mode, **kw)
     ix = vb.Index(ref, ctx=gpu_ctx)
-    got = vb.Aligner(ix, opt, mode).align_batch(reads)
+    got = vb.Aligner(ix, opt, mode, workers=1).align_batch(reads)
     ox = oracle.Index(ref)
     ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
     for (rid, seq), g in zip(reads, got):
         want = pl.align_read(rid, seq, ox, ctg, opt, mode)
         assert [tuple(r) for r in g] == [tuple(w) for w in want], rid
+    # pipelined sub-batches (own stream / arenas per worker) must give the very same records, in read order
+    piped = vb.Aligner(ix, opt, mode, workers=3, chunk_reads=4).align_batch(reads)
+    assert piped == got
+    al = vb.Aligner(ix, opt, mode, workers=2, chunk_reads=5)
+    enc = [s.upper().encode() for _, s in reads]
+    off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+    al.upload_reads(b"".join(enc), off)
+    a = al.align_packed(b"".join(enc), off, resident=True)
+    b = vb.Aligner(ix, opt, mode, workers=1).align_packed(b"".join(enc), off)
+    assert all((x == y).all() for x, y in zip(a, b))
     ix.close()

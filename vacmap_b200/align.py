@@ -22,7 +22,8 @@ class AlignParamsC(ctypes.Structure):
     _fields_ = [("global_skipcost", ctypes.c_double), ("local_skipcost", ctypes.c_double),
                 ("maxdivergence", ctypes.c_double), ("accept_score", ctypes.c_double)] + \
                [(n, ctypes.c_int32) for n in ("global_maxdiff", "local_maxdiff", "check_num", "eqx", "hardclip", "nodiscard",
-                                              "max_guides", "local_maxgap", "clamp40", "host_threads")]
+                                              "max_guides", "local_maxgap", "clamp40", "host_threads", "workers",
+                                              "chunk_reads")]
 
 
 class RecordC(ctypes.Structure):
@@ -161,7 +162,7 @@ class Index:
 class Aligner:
     """Batch form of the reference worker loop: reads in, `onemapinfolist` per read out."""
 
-    def __init__(self, index, option=None, mode="H", host_threads=0):
+    def __init__(self, index, option=None, mode="H", host_threads=0, workers=0, chunk_reads=0):
         self.index = index
         self.mode = mode
         self.option = option or default_option(mode)
@@ -169,7 +170,7 @@ class Aligner:
         o = self.option
         self.params = AlignParamsC(o["golbal_skipcost"], o["local_skipcost"], o["maxdivergence"], mc["accept"],
                                    o["golbal_maxdiff"], o["local_maxdiff"], o["c"], int(o["eqx"]), int(o["H"]),
-                                   int(o["nodiscard"]), mc["max_guides"], mc["local_maxgap"], mc["clamp40"], host_threads)
+                                   int(o["nodiscard"]), mc["max_guides"], mc["local_maxgap"], mc["clamp40"], host_threads, workers, chunk_reads)
         self.last_stage_ms = {}
 
     def upload_reads(self, seq_cat, seq_off):
@@ -232,9 +233,9 @@ def cigar_string(ops):
     return "".join("%d%s" % (int(o) >> 4, OPS[int(o) & 0xf]) for o in ops)
 
 
-def pairs_batch(kind, targets, queries, eqx=False, ctx=None, device=0):
+def pairs_batch(kind, targets, queries, eqx=False, ctx=None, device=0, band=None):
     """Stage-level base-level kernels on raw (target, query) string pairs.
-    kind 'distance' -> list of int; 'extend' -> list of (q_e, t_e); 'fill' -> list of CIGAR strings."""
+    kind 'distance' -> list of int (with `band` = list of half-widths k: exact when <= k, else some value > k); 'extend' -> list of (q_e, t_e); 'fill' -> list of CIGAR strings."""
     L = _lib.load()
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     L.vm_pairs_batch.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
@@ -248,11 +249,14 @@ def pairs_batch(kind, targets, queries, eqx=False, ctx=None, device=0):
         q_off[i + 1] = q_off[i] + len(qb[i])
     out0, out1 = np.zeros(n, np.int64), np.zeros(n, np.int64)
     k = {"distance": 0, "extend": 1, "fill": 2}[kind]
+    if k == 0 and band is not None:
+        k = 3
+        out1[:] = np.asarray(band, np.int64)
     cap = int(t_off[-1] + q_off[-1] + 2 * n + 16)
     cig = np.zeros(cap if k == 2 else 1, np.uint32)
     _lib.check(ctx.h, L.vm_pairs_batch(ctx.h, k, int(eqx), n, b"".join(tb), _lib.ptr(t_off), b"".join(qb), _lib.ptr(q_off),
                                        _lib.ptr(out0), _lib.ptr(out1), _lib.ptr(cig)))
-    if k == 0:
+    if k in (0, 3):
         return [int(v) for v in out0]
     if k == 1:
         return [(int(a), int(b)) for a, b in zip(out0, out1)]

@@ -19,124 +19,197 @@
 #include "vm_index.cuh"
 
 #define VM_NEG (-0x40000000)
-#define VM_ED_MAXG 64
 
 // ---------------------------------------------------------------------------
 // edit distance
 // ---------------------------------------------------------------------------
-// GT > 0: every lane owns GT 64-row blocks whose Pv/Mv words live in REGISTERS (loops fully
-// unrolled); GT == 0: generic version for very long patterns, words per lane decided at run time
-// (state in local memory).
-template <int GT>
-__global__ void __launch_bounds__(32) vm_edit_distance_kernel(VmAlnJobDev *jobs, const int *__restrict__ job_ids, VmSeqSources S,
-                                                              int max_words)
+// Banded Myers/Hyyro bit-vector NW distance, one warp per job.
+//  * The pattern's 64-row blocks are dealt to the lanes CYCLICALLY (block b -> lane b % 32); block b works on
+//    text column j at step tau = j + b, so its horizontal carry comes from the previous lane's previous step
+//    (lane 31 hands over to lane 0), one shuffle per slot and step.
+//  * Only the blocks that intersect the Ukkonen band are computed.  An edit path of cost <= k between strings
+//    whose lengths differ by D = n - m stays on the diagonals [min(0,D) - x, max(0,D) + x], x = (k - |D|) / 2,
+//    so the band is only k + 1 diagonals wide.  A block entering the band starts from vertical deltas of +1
+//    below the score of the block above it, a block whose upper neighbour has left the band gets a horizontal
+//    carry of +1: both are costs of real edit paths, so the result is never below the true distance and equals
+//    it whenever the true distance is <= k.  Result > k therefore means "distance > k" (the value is then only
+//    an upper bound); k < 0 or k >= max(m, n) is the plain full computation.
+//  * A lane time-multiplexes G register slots: blocks b and b + 32*G never overlap in time because
+//    65 * 32 * G > band width + 63 (the host picks G that way), so the Pv/Mv words of a lane live in registers
+//    and their updates within a step are independent (instruction-level parallelism G).
+//  * Two-level band: a job that needs G > 1 slots first runs with the widest band ONE slot per lane can hold
+//    (2016 diagonals); a result inside that band is already exact (typical reads diverge far less than the
+//    filter's threshold), otherwise the full band is run.
+//  * The text flows through a shared-memory ring refilled with one coalesced load every 32 steps; the Peq
+//    table is built with warp ballots from coalesced pattern loads.
+#define VM_ED_SPAN 2080   // 65 * 32: time between the starts of blocks b and b + 32
+
+// one banded pass: rows i with j - ku <= i <= j + kd of every column j; GE = slots per lane in use (1 or G)
+template <int G>
+__device__ __forceinline__ int vm_ed_pass(const unsigned long long *peq, uint8_t *ring, int ring_mask, const VmSeqView &txt,
+                                          int m, int n, int W, int kd, int ku, int GE, int lane)
 {
-    extern __shared__ unsigned long long vm_peq[];   // [5][max_words]
+    unsigned long long Pv[G], Mv[G];
+    int sc[G], cb[G], lo[G], hi[G];
+    unsigned out[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        Pv[g] = ~0ULL; Mv[g] = 0ULL; sc[g] = 0; out[g] = 0u;
+        cb[g] = g < GE ? lane + 32 * g : W;
+        lo[g] = 64 * cb[g] - kd > 0 ? 64 * cb[g] - kd : 0;
+        hi[g] = 64 * cb[g] + 63 + ku < n - 1 ? 64 * cb[g] + 63 + ku : n - 1;
+    }
+    int result = -1;
+    const int nsteps = n + W - 1;
+    for (int tau = 0; tau < nsteps; ++tau) {
+        if ((tau & 31) == 0) {
+            __syncwarp();
+            const int col = tau + lane;
+            if (col < n) ring[col & ring_mask] = (uint8_t)vm_at(txt, col);
+            __syncwarp();
+        }
+        unsigned rot[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) rot[g] = (g == 0 || GE > 1) ? __shfl_sync(VM_FULL, out[g], (lane + 31) & 31) : 0u;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const unsigned inp = lane != 0 ? rot[g] : (GE == 1 ? rot[0] : rot[(g + G - 1) % G]);
+            int b = cb[g];
+            if (b < W && tau - b > hi[g]) {          // this block has left the band: the slot moves on
+                b += 32 * GE;
+                cb[g] = b;
+                lo[g] = 64 * b - kd > 0 ? 64 * b - kd : 0;
+                hi[g] = 64 * b + 63 + ku < n - 1 ? 64 * b + 63 + ku : n - 1;
+            }
+            const int j = tau - b;
+            unsigned o = 0u;
+            if (b < W && j >= lo[g] && j <= hi[g]) {
+                const int in_ho = (int)((inp >> 1) & 3u) - 1;
+                unsigned long long pv = Pv[g], mv = Mv[g];
+                int s = sc[g];
+                if (j == lo[g]) {                    // entering the band (or column 0)
+                    pv = ~0ULL;
+                    mv = 0ULL;
+                    s = lo[g] == 0 ? 64 * (b + 1) : (int)(inp >> 3) - in_ho + 64;
+                }
+                const int hin = (b >= 1 && j <= 64 * b - 1 + ku) ? in_ho : 1;
+                unsigned long long Eq = peq[(size_t)ring[j & ring_mask] * W + b];
+                const unsigned long long neg = hin < 0 ? 1ULL : 0ULL;
+                const unsigned long long Xv = Eq | mv;
+                Eq |= neg;
+                const unsigned long long Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                unsigned long long Ph = mv | ~(Xh | pv);
+                unsigned long long Mh = pv & Xh;
+                const int ho = (int)(Ph >> 63) - (int)(Mh >> 63);
+                Ph <<= 1;
+                Mh <<= 1;
+                Mh |= neg;
+                Ph |= hin > 0 ? 1ULL : 0ULL;
+                pv = Mh | ~(Xv | Ph);
+                mv = Ph & Xv;
+                s += ho;
+                Pv[g] = pv; Mv[g] = mv; sc[g] = s;
+                o = 1u | (unsigned)(ho + 1) << 1 | (unsigned)s << 3;
+                if (b == W - 1 && j == n - 1) {
+                    // rows >= m of the last block are padding: take their vertical deltas back out
+                    const int first_pad = m - 64 * (W - 1);
+                    const unsigned long long padmask = first_pad >= 64 ? 0ULL : ~0ULL << first_pad;
+                    result = s - __popcll(pv & padmask) + __popcll(mv & padmask);
+                }
+            }
+            out[g] = o;
+        }
+    }
+    __syncwarp();
+    return __reduce_max_sync(VM_FULL, result);
+}
+
+template <int G>
+__global__ void __launch_bounds__(32) vm_edit_distance_kernel(VmAlnJobDev *jobs, const int *__restrict__ job_ids, VmSeqSources S,
+                                                              int max_words, int ring_mask)
+{
+    extern __shared__ unsigned long long vm_peq[];   // [5][W] of this job, then the text ring
     VmAlnJobDev &J = jobs[job_ids[blockIdx.x]];
     const int lane = threadIdx.x;
     const VmSeqView pat = vm_view(S, J.q, J.read), txt = vm_view(S, J.t, J.read);
     const int m = pat.len, n = txt.len;
     if (m == 0 || n == 0) { if (lane == 0) J.result0 = m + n; return; }
+    const int longest = m > n ? m : n;
+    const int k = (J.out_off < 0 || J.out_off >= longest) ? longest : (int)J.out_off;
+    const int D = n - m, aD = D < 0 ? -D : D;
+    if (aD > k) { if (lane == 0) J.result0 = (long long)k + 1; return; }
     const int W = (m + 63) >> 6;
-    const int G = GT > 0 ? GT : (W + 31) >> 5;
-    const int used = (W + G - 1) / G;
-    for (int w = lane; w < W; w += 32) {
-        unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
-        for (int b = 0; b < 64; ++b) {
-            const int i = w * 64 + b;
-            if (i < m) {
-                const int c = vm_at(pat, i);
-                const unsigned long long bit = 1ULL << b;
-                if (c == 0) e0 |= bit; else if (c == 1) e1 |= bit; else if (c == 2) e2 |= bit; else if (c == 3) e3 |= bit; else e4 |= bit;
-            }
-        }
-        vm_peq[w] = e0; vm_peq[max_words + w] = e1; vm_peq[2 * max_words + w] = e2; vm_peq[3 * max_words + w] = e3;
-        vm_peq[4 * max_words + w] = e4;
+    unsigned *peq32 = reinterpret_cast<unsigned *>(vm_peq);
+    uint8_t *ring = reinterpret_cast<uint8_t *>(vm_peq + 5 * (size_t)max_words);
+    for (int i0 = 0; i0 < 64 * W; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i < m ? vm_at(pat, i) : 5;
+        const unsigned e0 = __ballot_sync(VM_FULL, c == 0), e1 = __ballot_sync(VM_FULL, c == 1),
+                       e2 = __ballot_sync(VM_FULL, c == 2), e3 = __ballot_sync(VM_FULL, c == 3),
+                       e4 = __ballot_sync(VM_FULL, c == 4);
+        if (lane < 5) peq32[(size_t)lane * 2 * W + (i0 >> 5)] = lane == 0 ? e0 : lane == 1 ? e1 : lane == 2 ? e2 : lane == 3 ? e3 : e4;
     }
-    __syncwarp();
-    constexpr int NW = GT > 0 ? GT : VM_ED_MAXG;
-    unsigned long long Pv[NW], Mv[NW];
-#pragma unroll
-    for (int g = 0; g < NW; ++g) { Pv[g] = ~0ULL; Mv[g] = 0ULL; }
-    int score = 64 * W;
-    const int w0 = lane * G;
-    const bool owns_last = lane < used && (W - 1) >= w0 && (W - 1) < w0 + G;
-    int hout_prev = 0;
-    for (int tau = 0; tau < n + used - 1; ++tau) {
-        const int hin_from = __shfl_up_sync(VM_FULL, hout_prev, 1);
-        const int j = tau - lane;
-        int hout = 0;
-        if (lane < used && j >= 0 && j < n) {
-            int hin = lane == 0 ? 1 : hin_from;   // D[0][j] - D[0][j-1] = 1 (global alignment)
-            const unsigned long long *eqrow = vm_peq + vm_at(txt, j) * max_words + w0;
-#pragma unroll
-            for (int g = 0; g < NW; ++g) {
-                if (g < G && w0 + g < W) {
-                    unsigned long long Eq = eqrow[g];
-                    const unsigned long long pv = Pv[g], mv = Mv[g];
-                    const unsigned long long neg = hin < 0 ? 1ULL : 0ULL;
-                    const unsigned long long Xv = Eq | mv;
-                    Eq |= neg;
-                    const unsigned long long Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-                    unsigned long long Ph = mv | ~(Xh | pv);
-                    unsigned long long Mh = pv & Xh;
-                    const int ho = (int)(Ph >> 63) - (int)(Mh >> 63);
-                    Ph <<= 1;
-                    Mh <<= 1;
-                    Mh |= neg;
-                    Ph |= hin > 0 ? 1ULL : 0ULL;
-                    Pv[g] = Mh | ~(Xv | Ph);
-                    Mv[g] = Ph & Xv;
-                    hin = ho;
-                    if (w0 + g == W - 1) score += ho;
-                }
-            }
-            hout = hin;
+    const int up = D > 0 ? D : 0, dn = D < 0 ? -D : 0;
+    if (G > 1 && W > 32 && aD <= VM_ED_SPAN - 65) {
+        const int x1 = (VM_ED_SPAN - 65 - aD) / 2, k1 = aD + 2 * x1;
+        if (k1 < k) {
+            const int r = vm_ed_pass<G>(vm_peq, ring, ring_mask, txt, m, n, W, x1 + dn + (k1 == 0), x1 + up, 1, lane);
+            if (r <= k1) { if (lane == 0) J.result0 = r; return; }
         }
-        hout_prev = hout;
     }
-    if (owns_last) {
-        const int gl = (W - 1) - w0;
-        unsigned long long pvl = 0, mvl = 0;
-#pragma unroll
-        for (int g = 0; g < NW; ++g)
-            if (g == gl) { pvl = Pv[g]; mvl = Mv[g]; }
-        const int first_pad = m - 64 * (W - 1);     // bits >= first_pad of the last word are padding rows
-        for (int b = first_pad; b < 64; ++b) {
-            if (pvl >> b & 1ULL) --score;
-            if (mvl >> b & 1ULL) ++score;
-        }
-        J.result0 = score;
-    }
+    const int x = (k - aD) / 2;
+    const int r = vm_ed_pass<G>(vm_peq, ring, ring_mask, txt, m, n, W, x + dn + (aD + 2 * x == 0), x + up, G, lane);
+    if (lane == 0) J.result0 = r;
 }
 
-template <int GT>
+template <int G>
 static void vm_ed_launch_class(VmAlnJobDev *jobs, const int *ids, int n_ids, VmSeqSources src, int max_words, cudaStream_t stream)
 {
     if (n_ids <= 0) return;
-    const size_t smem = (size_t)max_words * 5 * 8;
-    cudaFuncSetAttribute(vm_edit_distance_kernel<GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    vm_edit_distance_kernel<GT><<<n_ids, 32, smem, stream>>>(jobs, ids, src, max_words);
+    int ring = 64;
+    while (ring < max_words + 64) ring <<= 1;
+    const size_t smem = (size_t)max_words * 5 * 8 + (size_t)ring;
+    vm_smem_optin(vm_edit_distance_kernel<G>);
+    vm_edit_distance_kernel<G><<<n_ids, 32, smem, stream>>>(jobs, ids, src, max_words, ring - 1);
 }
 
-// ids_dev: job indices grouped by class; class_start[0..6]: classes GT = 1, 2, 4, 8, 16, generic;
-// class_words[c]: largest pattern word count in class c (sizes the Peq table in shared memory)
+// register slots per lane a job needs: its band must fit (65*32*G > band width + 63) unless every block has its own slot
+int vm_ed_slots(int m, int n, long long band)
+{
+    const int longest = m > n ? m : n;
+    const long long k = (band < 0 || band >= longest) ? longest : band;
+    const int W = (m + 63) / 64;
+    const int g_all = (W + 31) / 32;
+    const long long d = n > m ? n - m : m - n, x = k > d ? (k - d) / 2 : 0;
+    const int g_band = (int)((d + 2 * x + 1 + 63) / VM_ED_SPAN + 1);
+    const int g = g_all < g_band ? g_all : g_band;
+    return g < 1 ? 1 : g;
+}
+
+const int VM_ED_CLASS_G[VM_ED_NCLASS] = {1, 2, 3, 4, 6, 8, 12, 16, 32, 64};
+
+// ids_dev: job indices grouped by class; class_start[0..VM_ED_NCLASS]; class_words[c]: largest pattern word
+// count in class c (sizes the Peq table and the text ring in shared memory)
 int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
                             cudaStream_t stream)
 {
     int launches = 0;
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < VM_ED_NCLASS; ++c) {
         const int n_ids = class_start[c + 1] - class_start[c];
         if (n_ids <= 0) continue;
         const int *ids = ids_dev + class_start[c];
         const int mw = class_words[c] > 0 ? class_words[c] : 1;
-        switch (c) {
-        case 0: vm_ed_launch_class<1>(jobs, ids, n_ids, src, mw, stream); break;
-        case 1: vm_ed_launch_class<2>(jobs, ids, n_ids, src, mw, stream); break;
-        case 2: vm_ed_launch_class<4>(jobs, ids, n_ids, src, mw, stream); break;
-        case 3: vm_ed_launch_class<8>(jobs, ids, n_ids, src, mw, stream); break;
-        case 4: vm_ed_launch_class<16>(jobs, ids, n_ids, src, mw, stream); break;
-        default: vm_ed_launch_class<0>(jobs, ids, n_ids, src, mw, stream); break;
+        switch (VM_ED_CLASS_G[c]) {
+        case 1: vm_ed_launch_class<1>(jobs, ids, n_ids, src, mw, stream); break;
+        case 2: vm_ed_launch_class<2>(jobs, ids, n_ids, src, mw, stream); break;
+        case 3: vm_ed_launch_class<3>(jobs, ids, n_ids, src, mw, stream); break;
+        case 4: vm_ed_launch_class<4>(jobs, ids, n_ids, src, mw, stream); break;
+        case 6: vm_ed_launch_class<6>(jobs, ids, n_ids, src, mw, stream); break;
+        case 8: vm_ed_launch_class<8>(jobs, ids, n_ids, src, mw, stream); break;
+        case 12: vm_ed_launch_class<12>(jobs, ids, n_ids, src, mw, stream); break;
+        case 16: vm_ed_launch_class<16>(jobs, ids, n_ids, src, mw, stream); break;
+        case 32: vm_ed_launch_class<32>(jobs, ids, n_ids, src, mw, stream); break;
+        default: vm_ed_launch_class<64>(jobs, ids, n_ids, src, mw, stream); break;
         }
         ++launches;
     }

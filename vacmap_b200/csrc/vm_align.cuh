@@ -19,7 +19,7 @@ struct VmAlnJobDev {
     VmSeqSpec t, q;    // target, query
     int32_t read;
     int32_t n_out;     // fill: number of CIGAR ops written
-    int64_t out_off;   // fill: offset of this job's CIGAR ops; edit distance / extension: unused
+    int64_t out_off;   // fill: offset of this job's CIGAR ops; edit distance: band half-width k (-1: none)
     int64_t dir_off;   // fill: offset of the direction matrix (bytes)
     int64_t sc_off;    // fill: offset of global score scratch (ints), or -1 when shared memory is used
     int64_t result0;   // edit distance: distance; extension: q_e
@@ -62,6 +62,11 @@ __device__ __forceinline__ int vm_at(const VmSeqView &v, int i)
 
 #endif
 
+// Edit distance: the job's band half-width k travels in out_off (-1 = unbanded); result0 is the exact distance
+// when it is <= k, otherwise some value > k.  Jobs are grouped by the number of register slots per lane.
+#define VM_ED_NCLASS 10
+extern const int VM_ED_CLASS_G[VM_ED_NCLASS];
+int vm_ed_slots(int m, int n, long long band);
 int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
                             cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);

@@ -7,7 +7,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 2; }
+int vm_abi_version(void) { return 3; }
 
 int vm_ctx_create(int device, vm_ctx **out)
 {
@@ -35,6 +35,8 @@ void vm_ctx_destroy(vm_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (vm_ctx *k : c->kids) vm_ctx_destroy(k);
+    c->kids.clear();
     if (c->backend && c->backend_free) c->backend_free(c->backend);
     c->backend = nullptr;
     VmChainState &s = c->chain;
@@ -73,6 +75,23 @@ int vm_set_tables(vm_ctx *c, const float *extra, int64_t n_extra, const float *r
 }
 
 } // extern "C"
+
+vm_ctx *vm_ctx_worker(vm_ctx *parent, int i)
+{
+    while ((int)parent->kids.size() <= i) {
+        vm_ctx *k = nullptr;
+        if (vm_ctx_create(parent->device, &k) != VM_OK) return nullptr;
+        parent->kids.push_back(k);
+    }
+    vm_ctx *k = parent->kids[i];
+    k->extra.alias(parent->extra);
+    k->readgapcost.alias(parent->readgapcost);
+    k->log2cache.alias(parent->log2cache);
+    k->n_extra = parent->n_extra;
+    k->n_readgapcost = parent->n_readgapcost;
+    k->n_log2cache = parent->n_log2cache;
+    return k;
+}
 
 // gapcost_list as built inside the reference njit functions with libm log2
 // (global :24843-24846; local :27317-27322)

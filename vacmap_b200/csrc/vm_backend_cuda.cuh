@@ -112,22 +112,46 @@ public:
         ~WallTimer() { be->timer.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
     };
 
+    // b.off may start anywhere inside b.seq (a sub-batch of a larger batch): the device copy is rebased to 0
     void upload_reads(const ReadBatch &b)
     {
-        if (reads_resident && off_host_.size() == (size_t)b.n + 1 && std::equal(off_host_.begin(), off_host_.end(), b.off)) return;
-        const size_t total = (size_t)b.off[b.n];
+        const int64_t base = b.off[0];
+        if (reads_resident && off_host_.size() == (size_t)b.n + 1) {
+            bool same = true;
+            for (int64_t i = 0; i <= b.n && same; ++i) same = off_host_[i] == b.off[i] - base;
+            if (same) return;
+        }
+        const size_t total = (size_t)(b.off[b.n] - base);
+        off_host_.resize((size_t)b.n + 1);
+        for (int64_t i = 0; i <= b.n; ++i) off_host_[i] = b.off[i] - base;
         BE_OK(reads_fwd_.ensure(total + 64));
         BE_OK(reads_rc_.ensure(total + 64));
         BE_OK(read_off_.ensure((size_t)(b.n + 1) * 8));
-        BE_OK(cudaMemcpyAsync(reads_fwd_.p, b.seq, total, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(read_off_.p, b.off, (size_t)(b.n + 1) * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(reads_fwd_.p, b.seq + base, total, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(read_off_.p, off_host_.data(), (size_t)(b.n + 1) * 8, cudaMemcpyHostToDevice, c_->stream));
         if (total > 0) {
             vm_revcomp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c_->stream>>>(reads_fwd_.as<uint8_t>(), read_off_.as<int64_t>(),
                                                                                       (int)b.n, (int64_t)total, reads_rc_.as<uint8_t>());
             c_->launches += 1;
         }
         BE_OK(cudaStreamSynchronize(c_->stream));
-        off_host_.assign(b.off, b.off + b.n + 1);
+    }
+
+    // reads [r0, r0 + n) of a batch another backend of this device already holds in HBM (device-to-device)
+    void copy_reads_from(const CudaBackend &src, int64_t r0, int64_t n)
+    {
+        const int64_t base = src.off_host_[(size_t)r0];
+        const size_t total = (size_t)(src.off_host_[(size_t)(r0 + n)] - base);
+        off_host_.resize((size_t)n + 1);
+        for (int64_t i = 0; i <= n; ++i) off_host_[i] = src.off_host_[(size_t)(r0 + i)] - base;
+        BE_OK(reads_fwd_.ensure(total + 64));
+        BE_OK(reads_rc_.ensure(total + 64));
+        BE_OK(read_off_.ensure((size_t)(n + 1) * 8));
+        BE_OK(cudaMemcpyAsync(reads_fwd_.p, src.reads_fwd_.as<uint8_t>() + base, total, cudaMemcpyDeviceToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(reads_rc_.p, src.reads_rc_.as<uint8_t>() + base, total, cudaMemcpyDeviceToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(read_off_.p, off_host_.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        reads_resident = true;
     }
 
     // stage-level: seeding only, anchors copied to the host (parity tests)
@@ -388,7 +412,9 @@ public:
         const int nj = (int)jobs.size();
         if (nj == 0) return;
         VmAlnJobDev *J = stage_jobs((size_t)nj);
-        int max_words = 1;
+        std::vector<std::vector<int>> cls(VM_ED_NCLASS);
+        std::vector<int64_t> work((size_t)nj);
+        int class_words[VM_ED_NCLASS] = {0};
         for (int j = 0; j < nj; ++j) {
             memset(&J[j], 0, sizeof(VmAlnJobDev));
             // the shorter sequence is the bit-vector pattern (fewer 64-row blocks)
@@ -396,23 +422,27 @@ public:
             J[j].q = spec(a_short ? jobs[j].a : jobs[j].b);
             J[j].t = spec(a_short ? jobs[j].b : jobs[j].a);
             J[j].read = jobs[j].read;
-            max_words = std::max(max_words, (J[j].q.len + 63) / 64);
-            ed_cells_ += (double)J[j].q.len * (double)J[j].t.len;
-        }
-        if (max_words > 32 * 64) throw std::runtime_error("edit distance: sequence longer than 131072 bases is not supported yet");
-        // class by words per lane: 1, 2, 4, 8, 16 (state in registers), else generic
-        std::vector<std::vector<int>> cls(6);
-        int class_words[6] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < nj; ++j) {
-            const int W = (J[j].q.len + 63) / 64, G = (W + 31) / 32;
-            const int k = G <= 1 ? 0 : G <= 2 ? 1 : G <= 4 ? 2 : G <= 8 ? 3 : G <= 16 ? 4 : 5;
+            J[j].out_off = jobs[j].band;
+            const int m = J[j].q.len, n = J[j].t.len, W = (m + 63) / 64;
+            const int G = vm_ed_slots(m, n, jobs[j].band);
+            int k = 0;
+            while (k < VM_ED_NCLASS && VM_ED_CLASS_G[k] < G) ++k;
+            if (k == VM_ED_NCLASS) throw std::runtime_error("edit distance: sequence pair too long for the register-resident band");
             cls[k].push_back(j);
             class_words[k] = std::max(class_words[k], W);
+            work[j] = (int64_t)(n + W) * VM_ED_CLASS_G[k];
+            const int64_t kk = jobs[j].band < 0 ? std::max(m, n) : jobs[j].band;
+            ed_cells_ += (double)std::min<int64_t>(m, kk + 64) * (double)n;   // cells inside the (k + 1)-diagonal band
         }
         std::vector<int> ids;
-        int class_start[7];
-        for (int k = 0; k < 6; ++k) { class_start[k] = (int)ids.size(); ids.insert(ids.end(), cls[k].begin(), cls[k].end()); }
-        class_start[6] = (int)ids.size();
+        int class_start[VM_ED_NCLASS + 1];
+        for (int k = 0; k < VM_ED_NCLASS; ++k) {
+            // longest jobs first: the tail of a launch is one warp deep
+            std::sort(cls[k].begin(), cls[k].end(), [&](int x, int y) { return work[x] != work[y] ? work[x] > work[y] : x < y; });
+            class_start[k] = (int)ids.size();
+            ids.insert(ids.end(), cls[k].begin(), cls[k].end());
+        }
+        class_start[VM_ED_NCLASS] = (int)ids.size();
         BE_OK(d_seg_.ensure(ids.size() * 4 + 64));
         BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));

@@ -111,19 +111,86 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         be.set_index(h);
         be.reset_counters();
         be.reads_resident = resident != 0;
-        int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
-        Driver drv(be, h->ctg, opt, h->ix->k, threads);
-        drv.on_time = [&](const char *nm, double ms) { be.timer.add(nm, ms); };
-        ReadBatch b;
-        b.n = n_reads;
-        b.seq = seqs;
-        b.off = seq_off;
+        const int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        // Sub-batches in flight: each worker owns a CUDA stream, device arenas and a Driver, so the host glue of
+        // one sub-batch overlaps the kernels of the others and small launches share the GPU.
+        int workers = p->workers > 0 ? p->workers : 4;
+        int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 2 * workers - 1) / (2 * workers));
+        const int64_t n_chunks = n_reads > 0 ? (n_reads + chunk - 1) / chunk : 0;
+        if (n_chunks < 2) workers = 1;
+        workers = (int)std::min<int64_t>(workers, std::max<int64_t>(n_chunks, 1));
         BatchResult br;
         auto t0 = std::chrono::steady_clock::now();
-        drv.align_batch(b, br);
+        if (workers <= 1) {
+            Driver drv(be, h->ctg, opt, h->ix->k, threads);
+            drv.on_time = [&](const char *nm, double ms) { be.timer.add(nm, ms); };
+            ReadBatch b;
+            b.n = n_reads;
+            b.seq = seqs;
+            b.off = seq_off;
+            drv.align_batch(b, br);
+        } else {
+            br.records.assign((size_t)n_reads, {});
+            std::vector<CudaBackend *> wbe((size_t)workers, nullptr);
+            for (int w = 0; w < workers; ++w) {
+                vm_ctx *wc = vm_ctx_worker(c, w);
+                if (!wc) throw std::runtime_error("cannot create a worker context");
+                if (!wc->backend) {
+                    wc->backend = new CudaBackend(wc, h);
+                    wc->backend_free = [](void *q) { delete (CudaBackend *)q; };
+                }
+                wbe[w] = (CudaBackend *)wc->backend;
+                wbe[w]->set_index(h);
+                wbe[w]->reset_counters();
+                wc->launches = 0;
+            }
+            std::atomic<int64_t> next(0);
+            std::vector<std::string> errs((size_t)workers);
+            std::vector<std::thread> pool;
+            const int wthreads = std::max(2, (2 * threads + workers - 1) / workers);
+            for (int w = 0; w < workers; ++w)
+                pool.emplace_back([&, w]() {
+                    try {
+                        cudaSetDevice(c->device);
+                        CudaBackend &wb = *wbe[w];
+                        Driver drv(wb, h->ctg, opt, h->ix->k, wthreads);
+                        drv.on_time = [&wb](const char *nm, double ms) { wb.timer.add(nm, ms); };
+                        for (;;) {
+                            const int64_t ci = next.fetch_add(1);
+                            if (ci >= n_chunks) break;
+                            const int64_t r0 = ci * chunk, nr = std::min(n_reads, r0 + chunk) - r0;
+                            ReadBatch sb;
+                            sb.n = nr;
+                            sb.seq = seqs;
+                            sb.off = seq_off + r0;
+                            if (resident) wb.copy_reads_from(be, r0, nr);
+                            else wb.reads_resident = false;
+                            BatchResult sr;
+                            drv.align_batch(sb, sr);
+                            for (int64_t i = 0; i < nr; ++i) br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+                        }
+                    } catch (const std::exception &e) { errs[w] = e.what(); if (errs[w].empty()) errs[w] = "error"; }
+                });
+            for (std::thread &t : pool) t.join();
+            for (const std::string &e : errs)
+                if (!e.empty()) throw std::runtime_error(e);
+            for (int w = 0; w < workers; ++w) {
+                for (auto &kv : wbe[w]->timer.ms) be.timer.add(kv.first.c_str(), kv.second);
+                be.fill_cells_ += wbe[w]->fill_cells_; be.fill_bases_ += wbe[w]->fill_bases_; be.fill_jobs_ += wbe[w]->fill_jobs_;
+                be.ed_cells_ += wbe[w]->ed_cells_; be.reseed_hits_ += wbe[w]->reseed_hits_; be.chain_anchors_ += wbe[w]->chain_anchors_;
+                c->launches += c->kids[w]->launches;
+            }
+        }
         const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         auto t1 = std::chrono::steady_clock::now();
         res->rec_off.assign((size_t)n_reads + 1, 0);
+        {
+            size_t nrec = 0, nops = 0;
+            for (int64_t r = 0; r < n_reads; ++r)
+                for (const vmg::Record &rec : br.records[r]) { ++nrec; nops += rec.cigar.size(); }
+            res->recs.reserve(nrec);
+            res->cigar.reserve(nops);
+        }
         for (int64_t r = 0; r < n_reads; ++r) {
             for (const vmg::Record &rec : br.records[r]) {
                 vm_record o;
@@ -138,6 +205,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
             }
             res->rec_off[r + 1] = (int64_t)res->recs.size();
         }
+        be.timer.add("n_workers", workers);
         be.timer.add("total", total);
         be.timer.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         be.timer.add("n_fill_cells", be.fill_cells_);
@@ -168,13 +236,15 @@ int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int6
 
 // Stage-level entry point for the base-level kernels on raw sequence pairs (parity tests).
 // kind 0: global edit distance -> out0[j]; kind 1: z-drop edge extension -> out0 = q_e, out1 = t_e;
+// kind 3: as kind 0 inside the Ukkonen band |row - column| <= out1[j] (an INPUT here): out0[j] is the exact
+//         distance when it is <= out1[j], otherwise some value > out1[j] (what the divergence filter needs);
 // kind 2: global fill -> CIGAR ops of pair j at cigar[cig_off[j] .. cig_off[j] + out0[j]),
 //         cig_off[j] = sum over i < j of (tlen_i + qlen_i + 2).
 int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const char *targets, const int64_t *t_off,
                    const char *queries, const int64_t *q_off, int64_t *out0, int64_t *out1, uint32_t *cigar)
 {
     if (!c) return VM_ERR_ARG;
-    if (n_pairs < 0 || !t_off || !q_off || !out0 || kind < 0 || kind > 2) { c->err = "bad argument"; return VM_ERR_ARG; }
+    if (n_pairs < 0 || !t_off || !q_off || !out0 || kind < 0 || kind > 3 || (kind == 3 && !out1)) { c->err = "bad argument"; return VM_ERR_ARG; }
     cudaSetDevice(c->device);
     try {
         if (!c->backend) {
@@ -195,12 +265,13 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
         be.upload_reads(b);
         be.reset_counters();
         auto ref_of = [&](int64_t lo, int64_t hi) { vmg::SeqRef s; s.src = 1; s.lo = lo; s.hi = hi; return s; };
-        if (kind == 0) {
+        if (kind == 0 || kind == 3) {
             std::vector<EdJob> jobs((size_t)n_pairs);
             for (int64_t j = 0; j < n_pairs; ++j) {
                 jobs[j].read = 0;
                 jobs[j].a = ref_of(tt + q_off[j], tt + q_off[j + 1]);
                 jobs[j].b = ref_of(t_off[j], t_off[j + 1]);
+                jobs[j].band = kind == 3 ? out1[j] : -1;
             }
             be.edit_distance(b, jobs);
             for (int64_t j = 0; j < n_pairs; ++j) out0[j] = jobs[j].dist;

@@ -90,10 +90,10 @@ int vm_launch_sort_anchors(const VmAnchor *in, const int64_t *off, const int32_t
     if (use_smem) {
         const size_t smem = (size_t)cap * 16;
         if (key_is_end) {
-            cudaFuncSetAttribute(vm_sort_anchors_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            vm_smem_optin(vm_sort_anchors_kernel<1, true>);
             vm_sort_anchors_kernel<1, true><<<n_ids, 32, smem, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
         } else {
-            cudaFuncSetAttribute(vm_sort_anchors_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            vm_smem_optin(vm_sort_anchors_kernel<0, true>);
             vm_sort_anchors_kernel<0, true><<<n_ids, 32, smem, stream>>>(in, off, cnt, read_ids_dev, cap, perm, gscratch, sorted, rows);
         }
     } else {
@@ -387,8 +387,7 @@ static int vm_launch_exact_v(const VmChainArgs &args, const int *ids, int n_ids,
     if (n_ids <= 0) return 0;
     if (use_smem) {
         size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 12;
-        cudaFuncSetAttribute(vm_chain_exact_kernel<VARIANT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
+        vm_smem_optin(vm_chain_exact_kernel<VARIANT, true>);
         vm_chain_exact_kernel<VARIANT, true><<<n_ids, 32, smem, stream>>>(args, ids, cap);
     } else {
         size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;

@@ -35,6 +35,19 @@ struct VmError {
         }                                                                            \
     } while (0)
 
+// Let a kernel use all opt-in dynamic shared memory.  The value is the same on every call, so concurrent
+// worker threads launching the same kernel with different sizes cannot lower each other's limit.
+template <typename F>
+static inline void vm_smem_optin(F kernel)
+{
+    cudaFuncAttributes a;
+    int dev = 0, mx = 0;
+    if (cudaFuncGetAttributes(&a, kernel) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&mx, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mx - (int)a.sharedSizeBytes);
+}
+
 // pairwise gap geometry shared by all chaining variants
 // (reference: mammap_clrnano.py:24953-24984 global, 27418-27456 local)
 __device__ __forceinline__ void vm_pair_gaps(const VmAnchor &ai, const VmAnchor &aj,

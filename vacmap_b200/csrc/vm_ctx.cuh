@@ -8,9 +8,12 @@
 struct VmDevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;   // alias of another context's buffer (worker contexts share the score tables)
+    void alias(const VmDevBuf &o) { if (!borrowed) release(); p = o.p; cap = o.cap; borrowed = true; }
     cudaError_t ensure(size_t bytes)
     {
         if (bytes <= cap) return cudaSuccess;
+        if (borrowed) return cudaErrorInvalidValue;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -21,9 +24,10 @@ struct VmDevBuf {
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && !borrowed) cudaFree(p);
         p = nullptr;
         cap = 0;
+        borrowed = false;
     }
     template <typename T> T *as() const { return (T *)p; }
 };
@@ -82,7 +86,12 @@ struct vm_ctx {
     // persistent alignment backend (vm_backend_cuda.cu); destroyed through backend_free
     void *backend = nullptr;
     void (*backend_free)(void *) = nullptr;
+    // worker contexts of the pipelined batch driver: own stream, chain state and backend; tables aliased
+    std::vector<vm_ctx *> kids;
 };
+
+// worker context i of `parent` (created on first use; its tables alias the parent's)
+vm_ctx *vm_ctx_worker(vm_ctx *parent, int i);
 
 // chaining core on device-resident anchors (vm_api.cu), used by the pipeline backend
 int vm_chain_prepare(vm_ctx *c, int64_t n_reads, int64_t span, const std::vector<int64_t> &start, const std::vector<int32_t> &cnt,

@@ -8,6 +8,7 @@
 #pragma once
 #include "vm_glue.hpp"
 #include <atomic>
+#include <cmath>
 #include <chrono>
 #include <functional>
 #include <thread>
@@ -46,7 +47,8 @@ struct ChainOut {
 };
 
 struct GuideJobRef { int32_t read; vmg::GuideJob job; };
-struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; };
+// band: half-width k of the Ukkonen band (-1 = none); dist is exact when <= band, else only known to be > band
+struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; int64_t band = -1; };
 struct ExtJobRef { int32_t read; vmg::ExtJob job; };
 // CIGAR ops of a fill job: cig[cig_off .. cig_off + cig_len) of the array Backend::fill hands back
 struct FillJobRef { int32_t read; vmg::FillJob job; int64_t cig_off = 0; int32_t cig_len = 0; };
@@ -247,6 +249,7 @@ private:
                     if (std::min(j.a.len(), j.b.len()) == 0) throw vmg::ReadDropped("division by zero");
                     orient(j.a, s.need_reverse);
                     orient(j.b, s.need_reverse);
+                    j.band = divergence_band(std::min(j.a.len(), j.b.len()));
                     edj[t].push_back(j);
                 }
             } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); }
@@ -380,6 +383,17 @@ private:
                 vmg::extend_apply(s.al, s.ext);
             });
         }
+    }
+
+    // largest distance d that still passes the divergence filter `d / minlen > maxdivergence` (:19252-19254):
+    // the filter only needs the exact distance up to there, so the kernel computes inside that band
+    int64_t divergence_band(int64_t minlen) const
+    {
+        if (!(opt_.maxdivergence * (double)minlen < 1e9)) return -1;
+        int64_t d = (int64_t)std::floor(opt_.maxdivergence * (double)minlen);
+        while (d > 0 && (double)d / (double)minlen > opt_.maxdivergence) --d;
+        while (!((double)(d + 1) / (double)minlen > opt_.maxdivergence)) ++d;
+        return std::max<int64_t>(d, 0);
     }
 
     static std::string oriented_read(const ReadBatch &b, int64_t r, bool need_reverse)
