@@ -3,6 +3,8 @@
 // glue can be checked against the reference-generated golden records without a GPU.
 #include "../../vacmap_b200/csrc/vm_pipeline.hpp"
 #include <cstdio>
+#include <cstdlib>
+#include <map>
 
 extern "C" {
 // oracle/orc_*.c
@@ -229,10 +231,13 @@ int64_t gt_align_batch(void *orc_index, const orc_tables *tb, const char *ref, c
     opt.mode = vmg::ModeConst{o->accept, o->max_guides, o->local_maxgap, o->clamp40 != 0};
     OracleBackend be(orc_index, tb, ref);
     Driver drv(be, ctg, opt, o->kmersize, o->threads);
+    std::map<std::string, double> phase_ms;
+    if (getenv("GT_TIMES")) drv.on_time = [&](const char *nm, double ms) { phase_ms[nm] += ms; };
     ReadBatch b;
     b.n = n_reads; b.seq = reads; b.off = read_off;
     BatchResult res;
     drv.align_batch(b, res);
+    for (auto &kv : phase_ms) fprintf(stderr, "GT_TIME %s %.3f\n", kv.first.c_str(), kv.second);
     int64_t nrec = 0, ncig = 0;
     for (int64_t r = 0; r < n_reads; ++r)
         for (const vmg::Record &rec : res.records[r]) {

@@ -196,8 +196,9 @@ class Aligner:
             off = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_offsets(res), ctypes.POINTER(ctypes.c_int64)),
                                         shape=(n + 1,)).copy()
             if nrec:
-                raw = ctypes.string_at(L.vm_result_records(res), nrec * RECORD_DTYPE.itemsize)
-                recs = np.frombuffer(raw, dtype=RECORD_DTYPE).copy()
+                raw = np.ctypeslib.as_array(ctypes.cast(L.vm_result_records(res), ctypes.POINTER(ctypes.c_uint8)),
+                                            shape=(nrec * RECORD_DTYPE.itemsize,))
+                recs = raw.view(RECORD_DTYPE).copy()
             else:
                 recs = np.zeros(0, dtype=RECORD_DTYPE)
             if nops:

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <malloc.h>
 
 extern "C" {
 
@@ -18,6 +19,10 @@ int vm_ctx_create(int device, vm_ctx **out)
     if (e != cudaSuccess || ndev <= 0) return VM_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return VM_ERR_ARG;
     if (cudaSetDevice(device) != cudaSuccess) return VM_ERR_CUDA;
+    // Batches allocate and free large host arrays (job lists, result arenas) every call: keep them on the
+    // heap instead of fresh mmaps, so they are not page-faulted in again for every batch.
+    static const bool heap_tuned = [] { mallopt(M_MMAP_THRESHOLD, 1 << 30); mallopt(M_TRIM_THRESHOLD, 1 << 30); return true; }();
+    (void)heap_tuned;
     vm_ctx *c = new vm_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {

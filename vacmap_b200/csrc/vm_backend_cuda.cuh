@@ -80,6 +80,7 @@ public:
     }
     StageTimer timer;
     bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
+    int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
     double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0;
     void reset_counters()
@@ -240,9 +241,14 @@ public:
         out.gmax.assign((size_t)n, -1);
         if (nj == 0) return;
         std::vector<VmReseedJobDev> J((size_t)nj);
-        std::vector<int64_t> wlo, whi, gy;
-        std::vector<int32_t> gx;
+        std::vector<int64_t> w_off((size_t)nj + 1, 0), g_off((size_t)nj + 1, 0);
         for (int j = 0; j < nj; ++j) {
+            w_off[j + 1] = w_off[j] + (int64_t)jobs[j].job.win_lo.size();
+            g_off[j + 1] = g_off[j] + (int64_t)jobs[j].job.gx.size();
+        }
+        std::vector<int64_t> wlo((size_t)w_off[nj]), whi((size_t)w_off[nj]), gy((size_t)g_off[nj]);
+        std::vector<int32_t> gx((size_t)g_off[nj]);
+        parallel_for(nj, host_threads, [&](int64_t j) {
             const vmg::GuideJob &g = jobs[j].job;
             VmReseedJobDev &d = J[j];
             memset(&d, 0, sizeof(d));
@@ -252,14 +258,14 @@ public:
             d.readend = g.readend;
             d.n_win = (int32_t)g.win_lo.size();
             d.n_guide = (int32_t)g.gx.size();
-            d.win_off = (int64_t)wlo.size();
-            d.g_off = (int64_t)gx.size();
-            wlo.insert(wlo.end(), g.win_lo.begin(), g.win_lo.end());
-            whi.insert(whi.end(), g.win_hi.begin(), g.win_hi.end());
-            gx.insert(gx.end(), g.gx.begin(), g.gx.end());
-            gy.insert(gy.end(), g.gy.begin(), g.gy.end());
+            d.win_off = w_off[j];
+            d.g_off = g_off[j];
+            std::copy(g.win_lo.begin(), g.win_lo.end(), wlo.begin() + w_off[j]);
+            std::copy(g.win_hi.begin(), g.win_hi.end(), whi.begin() + w_off[j]);
+            std::copy(g.gx.begin(), g.gx.end(), gx.begin() + g_off[j]);
+            std::copy(g.gy.begin(), g.gy.end(), gy.begin() + g_off[j]);
             d.count_only = 1;
-        }
+        }, 64);
         BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev)));
         BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
         BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
@@ -484,12 +490,14 @@ public:
         const int nj = (int)jobs.size();
         if (nj == 0) return nullptr;
         VmAlnJobDev *J = stage_jobs((size_t)nj);
-        int64_t out_off = 0;
-        for (int j = 0; j < nj; ++j) {
+        parallel_for(nj, host_threads, [&](int64_t j) {
             memset(&J[j], 0, sizeof(VmAlnJobDev));
             J[j].t = spec(jobs[j].job.target);
             J[j].q = spec(jobs[j].job.query);
             J[j].read = jobs[j].read;
+        }, 1024);
+        int64_t out_off = 0;
+        for (int j = 0; j < nj; ++j) {
             J[j].out_off = out_off;
             out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
             fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;

@@ -111,6 +111,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         be.set_index(h);
         be.reset_counters();
         be.reads_resident = resident != 0;
+        be.host_threads = p->host_threads > 0 ? p->host_threads : HostPool::get().size();
         const int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
         // Sub-batches in flight: each worker owns a CUDA stream, device arenas and a Driver, so the host glue of
         // one sub-batch overlaps the kernels of the others and small launches share the GPU.
@@ -142,12 +143,13 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
                 wbe[w] = (CudaBackend *)wc->backend;
                 wbe[w]->set_index(h);
                 wbe[w]->reset_counters();
+                wbe[w]->host_threads = be.host_threads;
                 wc->launches = 0;
             }
             std::atomic<int64_t> next(0);
             std::vector<std::string> errs((size_t)workers);
             std::vector<std::thread> pool;
-            const int wthreads = std::max(2, (2 * threads + workers - 1) / workers);
+            const int wthreads = threads;   // the shared HostPool arbitrates between the workers
             for (int w = 0; w < workers; ++w)
                 pool.emplace_back([&, w]() {
                     try {
@@ -183,28 +185,31 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         }
         const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         auto t1 = std::chrono::steady_clock::now();
+        // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel
         res->rec_off.assign((size_t)n_reads + 1, 0);
-        {
-            size_t nrec = 0, nops = 0;
-            for (int64_t r = 0; r < n_reads; ++r)
-                for (const vmg::Record &rec : br.records[r]) { ++nrec; nops += rec.cigar.size(); }
-            res->recs.reserve(nrec);
-            res->cigar.reserve(nops);
-        }
+        std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
         for (int64_t r = 0; r < n_reads; ++r) {
+            int64_t ops = 0;
+            for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
+            res->rec_off[r + 1] = res->rec_off[r] + (int64_t)br.records[r].size();
+            cig_off[r + 1] = cig_off[r] + ops;
+        }
+        res->recs.resize((size_t)res->rec_off[n_reads]);
+        res->cigar.resize((size_t)cig_off[n_reads]);
+        parallel_for(n_reads, threads, [&](int64_t r) {
+            int64_t ri = res->rec_off[r], co = cig_off[r];
             for (const vmg::Record &rec : br.records[r]) {
-                vm_record o;
+                vm_record &o = res->recs[(size_t)ri++];
                 o.contig = rec.contig;
                 o.strand = rec.strand;
                 o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
                 o.mapq = rec.mapq;
-                o.cigar_off = (int64_t)res->cigar.size();
+                o.cigar_off = co;
                 o.cigar_len = (int32_t)rec.cigar.size();
-                res->cigar.insert(res->cigar.end(), rec.cigar.begin(), rec.cigar.end());
-                res->recs.push_back(o);
+                std::copy(rec.cigar.begin(), rec.cigar.end(), res->cigar.begin() + co);
+                co += (int64_t)rec.cigar.size();
             }
-            res->rec_off[r + 1] = (int64_t)res->recs.size();
-        }
+        }, 64);
         be.timer.add("n_workers", workers);
         be.timer.add("total", total);
         be.timer.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());

@@ -184,10 +184,11 @@ static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const in
     const double scores = S[g];
     const double max_scores = scores > 0 ? scores : 0;
     if (!(hit && max_scores > accept)) return;   // nothing below can change the verdict
+    Path path;
     for (int64_t q = n - 1; q >= 0; --q) {
         int64_t take = S_arg[q];
         if (used[take]) continue;
-        Path path;
+        path.clear();
         used[take] = 1;
         double score = S[take];
         for (;;) {
@@ -199,7 +200,7 @@ static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const in
         }
         if (score > 40) {
             scores_list.push_back(score);
-            path_list.push_back(std::move(path));
+            path_list.push_back(path);
         }
     }
     std::vector<int64_t> order;
@@ -209,29 +210,39 @@ static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const in
         for (size_t i = 0; i < order.size(); ++i)
             if (order[i] == 0) { order[i] = order[0]; order[0] = 0; break; }
     }
-    auto binset = [&](const Path &p) {
-        std::set<int64_t> s;
-        for (const Anc &v : p) s.insert(v.x / bin_size);
-        return s;
+    // 100-bp read-bin sets as sorted unique vectors (the reference's Python sets are only ever
+    // intersected and counted, :23672-23694)
+    auto binset = [&](const Path &p, std::vector<int64_t> &s) {
+        s.clear();
+        s.reserve(p.size());
+        for (const Anc &v : p) s.push_back(v.x / bin_size);
+        std::sort(s.begin(), s.end());
+        s.erase(std::unique(s.begin(), s.end()), s.end());
     };
-    std::vector<std::set<int64_t>> prim_sets;
+    std::vector<std::vector<int64_t>> prim_sets(1);
     std::vector<std::vector<double>> prim_scores;
-    prim_sets.push_back(binset(path_list[order[0]]));
+    binset(path_list[order[0]], prim_sets[0]);
     prim_scores.push_back({scores_list[order[0]]});
+    std::vector<int64_t> b;
     for (size_t oi = 1; oi < order.size(); ++oi) {
         const int64_t iloc = order[oi];
-        std::set<int64_t> b = binset(path_list[iloc]);
+        binset(path_list[iloc], b);
         double best = 0.0;
         size_t pref = 0;
         for (size_t p = 0; p < prim_sets.size(); ++p) {
-            size_t inter = 0;
-            const std::set<int64_t> &ps = prim_sets[p];
-            for (int64_t v : b) inter += ps.count(v);
+            const std::vector<int64_t> &ps = prim_sets[p];
+            size_t inter = 0, i = 0, j = 0;
+            if (!b.empty() && !ps.empty() && b.front() <= ps.back() && ps.front() <= b.back())
+                while (i < b.size() && j < ps.size()) {
+                    if (b[i] < ps[j]) ++i;
+                    else if (ps[j] < b[i]) ++j;
+                    else { ++inter; ++i; ++j; }
+                }
             const double ov = (double)inter / (double)std::min(ps.size(), b.size());
             if (ov > best) { best = ov; pref = p; }
         }
         if (best < overlap) {
-            prim_sets.push_back(std::move(b));
+            prim_sets.push_back(b);
             prim_scores.push_back({scores_list[iloc]});
         } else prim_scores[pref].push_back(scores_list[iloc]);
     }
@@ -246,19 +257,24 @@ static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const in
     // select_secondary_alignment :23505-23538
     std::vector<const Path *> secondary;
     if (path_list.size() > 1) {
-        std::vector<double> loc2score((size_t)L, 0.0);
-        int64_t en = L;
-        for (size_t t = 0; t < path_list[0].size() && t < S_arr.size(); ++t) {
-            const int64_t st = path_list[0][t].x;
-            for (int64_t q = st; q < en; ++q) loc2score[q] = S_arr[t];
-            en = st;
-        }
+        // loc2score[q] (:23508-23515) = S of the primary-chain anchor with the largest start <= q, 0 below the
+        // chain; the chain is in descending read order, so a lookup is one binary search
+        const Path &prim = path_list[0];
+        const size_t np = std::min(prim.size(), S_arr.size());
+        auto loc2score_at = [&](int64_t q) -> double {
+            size_t lo = 0, hi = np;          // first t with prim[t].x <= q
+            while (lo < hi) {
+                const size_t mid = (lo + hi) >> 1;
+                if (prim[mid].x <= q) hi = mid; else lo = mid + 1;
+            }
+            return lo < np ? S_arr[lo] : 0.0;
+        };
         for (size_t oi = 1; oi < order.size(); ++oi) {
             const Path &one = path_list[order[oi]];
             const double f2s = scores_list[order[oi]];
             const int64_t en_loc = one.front().x, st_loc = one.back().x;
             if (en_loc - st_loc < 50) continue;
-            const double f1s = std::max(loc2score[en_loc] - loc2score[st_loc], 1.0);
+            const double f1s = std::max(loc2score_at(en_loc) - loc2score_at(st_loc), 1.0);
             if (f2s / f1s > 0.9 || std::fabs(f1s - f2s) < 40) {
                 bool skip = false;
                 for (const Path *pri : secondary) {

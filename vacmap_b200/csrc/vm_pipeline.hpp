@@ -8,6 +8,10 @@
 #pragma once
 #include "vm_glue.hpp"
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <cmath>
 #include <chrono>
 #include <functional>
@@ -72,25 +76,138 @@ struct Backend {
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
 };
 
-static inline void parallel_for(int64_t n, int threads, const std::function<void(int64_t)> &fn)
-{
-    if (threads <= 1 || n < 2) {
-        for (int64_t i = 0; i < n; ++i) fn(i);
-        return;
+// Process-wide pool of host threads shared by every Driver / backend (the pipelined workers all draw from
+// it, so the host is never oversubscribed).  parallel_for hands out blocks of indices; the caller works too.
+class HostPool {
+public:
+    static HostPool &get()
+    {
+        static HostPool pool((int)std::max(1u, std::thread::hardware_concurrency()));
+        return pool;
     }
-    std::atomic<int64_t> next(0);
-    std::vector<std::thread> pool;
-    const int nt = (int)std::min<int64_t>(threads, n);
-    for (int t = 0; t < nt; ++t)
-        pool.emplace_back([&]() {
+    int size() const { return (int)threads_.size() + 1; }
+
+    void run(int64_t n, int max_threads, int64_t grain, const std::function<void(int64_t)> &fn)
+    {
+        if (n <= 0) return;
+        if (max_threads <= 1 || n <= grain || threads_.empty()) {
+            for (int64_t i = 0; i < n; ++i) fn(i);
+            return;
+        }
+        auto job = std::make_shared<Job>();
+        job->n = n;
+        job->grain = grain;
+        job->fn = &fn;
+        job->helpers_wanted = (int)std::min<int64_t>(std::min<int64_t>(max_threads - 1, (int64_t)threads_.size()), (n + grain - 1) / grain - 1);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            queue_.push_back(job);
+        }
+        cv_.notify_all();
+        work(*job);
+        std::unique_lock<std::mutex> lk(job->mu);
+        job->cv.wait(lk, [&] { return job->active == 0 && job->next.load() >= job->n; });
+        if (job->failed) std::rethrow_exception(job->error);
+    }
+
+private:
+    struct Job {
+        int64_t n = 0, grain = 1;
+        const std::function<void(int64_t)> *fn = nullptr;
+        std::atomic<int64_t> next{0};
+        int helpers_wanted = 0, helpers = 0;   // guarded by HostPool::mu_
+        int active = 0;                        // guarded by mu
+        bool failed = false;
+        std::exception_ptr error;
+        std::mutex mu;
+        std::condition_variable cv;
+    };
+
+    explicit HostPool(int n)
+    {
+        for (int t = 1; t < n; ++t) threads_.emplace_back([this] { loop(); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread &t : threads_) t.join();
+    }
+
+    void work(Job &job)
+    {
+        {
+            std::lock_guard<std::mutex> lk(job.mu);
+            ++job.active;
+        }
+        try {
             for (;;) {
-                const int64_t i0 = next.fetch_add(16);
-                if (i0 >= n) break;
-                const int64_t i1 = std::min(n, i0 + 16);
-                for (int64_t i = i0; i < i1; ++i) fn(i);
+                const int64_t i0 = job.next.fetch_add(job.grain);
+                if (i0 >= job.n) break;
+                const int64_t i1 = std::min(job.n, i0 + job.grain);
+                for (int64_t i = i0; i < i1; ++i) (*job.fn)(i);
             }
-        });
-    for (std::thread &t : pool) t.join();
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(job.mu);
+            if (!job.failed) { job.failed = true; job.error = std::current_exception(); }
+            job.next.store(job.n);
+        }
+        {
+            std::lock_guard<std::mutex> lk(job.mu);
+            --job.active;
+        }
+        job.cv.notify_all();
+    }
+
+    void loop()
+    {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                for (;;) {
+                    while (!queue_.empty() && (queue_.front()->next.load() >= queue_.front()->n ||
+                                               queue_.front()->helpers >= queue_.front()->helpers_wanted))
+                        queue_.pop_front();
+                    if (stop_ || !queue_.empty()) break;
+                    cv_.wait(lk);
+                }
+                if (stop_) return;
+                job = queue_.front();
+                ++job->helpers;
+                // spread the pool over the jobs in flight: the next idle thread looks at the next job first
+                if (queue_.size() > 1) { queue_.pop_front(); queue_.push_back(job); }
+            }
+            work(*job);
+        }
+    }
+
+    std::vector<std::thread> threads_;
+    std::deque<std::shared_ptr<Job>> queue_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+static inline void parallel_for(int64_t n, int threads, const std::function<void(int64_t)> &fn, int64_t grain = 16)
+{
+    HostPool::get().run(n, threads, grain, fn);
+}
+
+// out = concatenation of parts[0..m) (moved), start[t] = offset of parts[t] in out; parallel over the parts
+template <typename T>
+static inline void parallel_concat(std::vector<std::vector<T>> &parts, int threads, std::vector<T> &out, std::vector<int64_t> &start)
+{
+    const int64_t m = (int64_t)parts.size();
+    start.assign((size_t)m + 1, 0);
+    for (int64_t t = 0; t < m; ++t) start[t + 1] = start[t] + (int64_t)parts[t].size();
+    out.resize((size_t)start[m]);
+    parallel_for(m, threads, [&](int64_t t) {
+        std::move(parts[t].begin(), parts[t].end(), out.begin() + start[t]);
+    }, 64);
 }
 
 struct ReadState {
@@ -175,10 +292,11 @@ public:
             }
         });
         std::vector<GuideJobRef> all_gjobs;
+        std::vector<int64_t> gj_start;
+        parallel_concat(gjobs, threads_, all_gjobs, gj_start);
         std::vector<int> variant((size_t)n, 0);
         std::vector<double> skip((size_t)n, opt_.local_skipcost);
         for (int64_t r = 0; r < n; ++r) {
-            for (GuideJobRef &j : gjobs[r]) all_gjobs.push_back(std::move(j));
             if (!st[r].alive) continue;
             if (st[r].guides.size() > 1) {
                 variant[r] = 2;
@@ -220,8 +338,10 @@ public:
         if (!again.empty()) extend_pass(b, read_len, st, again);
         {
             Phase p2(this, "g_finish");
-            for (int64_t r = 0; r < n; ++r)
+            parallel_for(n, threads_, [&](int64_t r) {
                 if (st[r].alive) res.records[r].swap(st[r].recs);
+                st[r] = ReadState();     // the per-read state is torn down by the pool, not serially
+            }, 64);
             st.clear();
         }
     }
@@ -255,12 +375,8 @@ private:
             } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); }
         });
         std::vector<EdJob> ed;
-        std::vector<int64_t> ed_start((size_t)m + 1, 0);
-        for (int64_t t = 0; t < m; ++t) {
-            ed_start[t] = (int64_t)ed.size();
-            ed.insert(ed.end(), edj[t].begin(), edj[t].end());
-        }
-        ed_start[m] = (int64_t)ed.size();
+        std::vector<int64_t> ed_start;
+        parallel_concat(edj, threads_, ed, ed_start);
         delete ph;
         be_.edit_distance(b, ed);
         ph = new Phase(this, "g_ext_edges");
@@ -319,12 +435,8 @@ private:
             } catch (const vmg::ReadDropped &) { s.alive = false; fj[t].clear(); }
         });
         std::vector<FillJobRef> fills;
-        std::vector<int64_t> f_start((size_t)m + 1, 0);
-        for (int64_t t = 0; t < m; ++t) {
-            f_start[t] = (int64_t)fills.size();
-            for (FillJobRef &j : fj[t]) fills.push_back(std::move(j));
-        }
-        f_start[m] = (int64_t)fills.size();
+        std::vector<int64_t> f_start;
+        parallel_concat(fj, threads_, fills, f_start);
         delete ph;
         const uint32_t *cig_ops = be_.fill(b, opt_.eqx, fills);
         Phase p3(this, "g_ext_records");
