@@ -264,71 +264,95 @@ public:
             std::copy(g.win_hi.begin(), g.win_hi.end(), whi.begin() + w_off[j]);
             std::copy(g.gx.begin(), g.gx.end(), gx.begin() + g_off[j]);
             std::copy(g.gy.begin(), g.gy.end(), gy.begin() + g_off[j]);
-            d.count_only = 1;
         }, 64);
+        // one pass with room for 3 hits per read position; the rare job that needs more is re-run below
+        int64_t hit_off = 0;
+        for (int j = 0; j < nj; ++j) {
+            const int64_t span = std::max<int64_t>(0, (int64_t)J[j].readend - J[j].readstart);
+            J[j].hit_off = hit_off;
+            J[j].hit_cap = (int32_t)std::min<int64_t>(3 * span + 64, INT32_MAX);
+            hit_off += J[j].hit_cap;
+        }
         BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev)));
         BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
         BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
         BE_OK(d_gx_.ensure(gx.size() * 4 + 64));
         BE_OK(d_gy_.ensure(gy.size() * 8 + 64));
         BE_OK(d_nh_.ensure((size_t)nj * 8 + 64));
+        BE_OK(d_hits_.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_wlo_.p, wlo.data(), wlo.size() * 8, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_gx_.p, gx.data(), gx.size() * 4, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_gy_.p, gy.data(), gy.size() * 8, cudaMemcpyHostToDevice, c_->stream));
-        int32_t *d_n_hits = d_nh_.as<int32_t>(), *d_over = d_nh_.as<int32_t>() + nj, *d_n_out = d_nh_.as<int32_t>() + nj + 1;
-        BE_OK(cudaMemsetAsync(d_over, 0, 4, c_->stream));
+        int32_t *d_n_hits = d_nh_.as<int32_t>(), *d_n_out = d_nh_.as<int32_t>() + nj;
         const VmIndexDev &ix = ih_->ix->dev;
-        // pass 1: count hits per job
         {
             KTimer kt(this, "k_reseed_hits");
             c_->launches += vm_reseed_launch(ix, jobs_.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
                                              read_off_.as<int64_t>(), d_wlo_.as<int64_t>(), d_whi_.as<int64_t>(),
-                                             d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), nullptr, d_n_hits, d_over, nullptr, nullptr,
-                                             nullptr, nullptr, c_->stream);
+                                             d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), d_hits_.p, d_n_hits, c_->stream);
             kt.stop();
         }
         std::vector<int32_t> n_hits((size_t)nj);
         BE_OK(cudaMemcpyAsync(n_hits.data(), d_n_hits, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
-        int64_t hit_off = 0, tab_off = 0;
+        {
+            // jobs that overflowed their capacity: exact room at the end of the hit buffer, second launch
+            std::vector<int> redo;
+            std::vector<VmReseedJobDev> RJ;
+            for (int j = 0; j < nj; ++j)
+                if (n_hits[j] > J[j].hit_cap) {
+                    J[j].hit_off = hit_off;
+                    J[j].hit_cap = n_hits[j];
+                    hit_off += n_hits[j];
+                    redo.push_back(j);
+                    RJ.push_back(J[j]);
+                }
+            if (!redo.empty()) {
+                // growing the buffer must keep the hits already written
+                VmDevBuf bigger;
+                BE_OK(bigger.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
+                BE_OK(cudaMemcpyAsync(bigger.p, d_hits_.p, (size_t)RJ[0].hit_off * vm_reseed_hit_bytes(), cudaMemcpyDeviceToDevice,
+                                      c_->stream));
+                BE_OK(cudaStreamSynchronize(c_->stream));
+                d_hits_.release();
+                d_hits_ = bigger;
+                BE_OK(d_seg_.ensure(RJ.size() * (sizeof(VmReseedJobDev) + 4) + 64));
+                BE_OK(cudaMemcpyAsync(d_seg_.p, RJ.data(), RJ.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
+                int32_t *d_rn = (int32_t *)(d_seg_.as<VmReseedJobDev>() + RJ.size());
+                KTimer kt(this, "k_reseed_hits");
+                c_->launches += vm_reseed_launch(ix, d_seg_.as<VmReseedJobDev>(), (int)RJ.size(), reads_fwd_.as<uint8_t>(),
+                                                 reads_rc_.as<uint8_t>(), read_off_.as<int64_t>(), d_wlo_.as<int64_t>(),
+                                                 d_whi_.as<int64_t>(), d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), d_hits_.p, d_rn,
+                                                 c_->stream);
+                kt.stop();
+            }
+        }
+        int64_t dense_hits = 0, tab_off = 0;
         for (int j = 0; j < nj; ++j) {
-            J[j].count_only = 0;
-            J[j].hit_off = hit_off;
-            J[j].hit_cap = n_hits[j];
-            hit_off += n_hits[j];
+            J[j].dense_off = dense_hits;
+            dense_hits += n_hits[j];
             int ts = 64;
             while (ts < n_hits[j] + 8) ts <<= 1;
             J[j].tab_off = tab_off;
             J[j].tab_size = ts;
             tab_off += ts;
         }
-        reseed_hits_ += (double)hit_off;
-        BE_OK(d_hits_.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
+        reseed_hits_ += (double)dense_hits;
         BE_OK(d_tab_.ensure((size_t)tab_off * vm_reseed_point_bytes() + 64));
-        BE_OK(d_order_.ensure((size_t)hit_off * 4 + 64));
-        BE_OK(d_rout_.ensure((size_t)hit_off * 2 * sizeof(VmAnchor) + 64));
+        BE_OK(d_order_.ensure((size_t)dense_hits * 4 + 64));
+        BE_OK(d_rout_.ensure((size_t)dense_hits * 2 * sizeof(VmAnchor) + 64));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
-        {
-            KTimer kt(this, "k_reseed_hits");
-            c_->launches += vm_reseed_launch(ix, jobs_.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
-                                             read_off_.as<int64_t>(), d_wlo_.as<int64_t>(), d_whi_.as<int64_t>(),
-                                             d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), d_hits_.p, d_n_hits, d_over, nullptr, nullptr,
-                                             nullptr, nullptr, c_->stream);
-            kt.stop();
-        }
         {
             KTimer kt(this, "k_reseed_merge");
             c_->launches += vm_reseed_merge_launch(jobs_.as<VmReseedJobDev>(), nj, d_hits_.p, d_n_hits, d_tab_.p,
                                                    d_order_.as<int32_t>(), d_rout_.as<VmAnchor>(), d_n_out, c_->stream);
             kt.stop();
         }
-        std::vector<int32_t> n_out((size_t)nj), over(1);
+        std::vector<int32_t> n_out((size_t)nj);
         BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaMemcpyAsync(over.data(), d_over, 4, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
-        if (over[0]) throw std::runtime_error("reseed: hit buffer overflow (count and fill passes disagree)");
         // concatenate the jobs of each read into one dense anchor list on the device
         std::vector<int64_t> seg(2 * (size_t)nj);   // [src_off | dst_off]
         int64_t dense = 0;
@@ -337,7 +361,7 @@ public:
             for (int64_t r = 0; r < n; ++r) {
                 out.start[r] = dense;
                 while (q < jobs.size() && jobs[q].read == r) {
-                    seg[q] = 2 * J[q].hit_off;
+                    seg[q] = 2 * J[q].dense_off;
                     seg[(size_t)nj + q] = dense;
                     dense += n_out[q];
                     ++q;

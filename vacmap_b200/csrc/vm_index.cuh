@@ -52,6 +52,13 @@ struct VmIndex {
 // base -> 0..3 (ACGT/U, either case), 4 otherwise (minimap2 seq_nt4_table)
 __host__ __device__ __forceinline__ int vm_nt4(unsigned char c)
 {
+#ifdef __CUDA_ARCH__
+    // branch-free on the device: letters A C G T U (either case) by a bit mask, code from bits 1..2 of the ASCII code
+    const unsigned u = (c & 0xDFu) - 'A';
+    const unsigned x = ((c & 0xDFu) >> 1) & 3u;          // A 0, C 1, T/U 2, G 3
+    const bool ok = u < 26u && ((0x00180045u >> u) & 1u);
+    return ok ? (int)(x ^ (x >> 1)) : 4;
+#endif
     switch (c) {
     case 'A': case 'a': return 0;
     case 'C': case 'c': return 1;

@@ -78,19 +78,36 @@ __device__ __forceinline__ void vm_probe(const VmIndexDev &ix, int code, const i
     }
 }
 
-__global__ void __launch_bounds__(256) vm_reseed_hits_kernel(VmIndexDev ix, const VmReseedJobDev *__restrict__ jobs,
-                                                             const uint8_t *__restrict__ reads_fwd,
-                                                             const uint8_t *__restrict__ reads_rc,
-                                                             const int64_t *__restrict__ read_off,
-                                                             const int64_t *__restrict__ win_lo_all,
-                                                             const int64_t *__restrict__ win_hi_all,
-                                                             const int32_t *__restrict__ gx_all, const int64_t *__restrict__ gy_all,
-                                                             VmHit *__restrict__ hits_all, int32_t *__restrict__ n_hits,
-                                                             int32_t *__restrict__ overflow)
+// 9-mer code of the staged 5-letter codes c[0..8]
+__device__ __forceinline__ int vm_kmer_code_staged(const uint8_t *c)
 {
-    __shared__ int s_scan[256];
+    int code = 0;
+#pragma unroll
+    for (int i = 0; i < VM_K9; ++i) code = code * 5 + c[i];
+    return code;
+}
+
+#define VM_RS_THREADS 256
+#define VM_RS_KEEP 3      // hits a thread keeps in registers between counting and writing
+
+// Single pass: every thread probes its read position once, keeps its first VM_RS_KEEP hits in registers, the
+// block scans the counts (warp shuffles + one shared-memory exchange) and the hits are written in the
+// reference's scan order.  A job whose hits exceed its capacity is only counted (n_hits > hit_cap tells the
+// host to re-run it with the exact capacity).
+__global__ void __launch_bounds__(VM_RS_THREADS) vm_reseed_hits_kernel(VmIndexDev ix, const VmReseedJobDev *__restrict__ jobs,
+                                                                       const uint8_t *__restrict__ reads_fwd,
+                                                                       const uint8_t *__restrict__ reads_rc,
+                                                                       const int64_t *__restrict__ read_off,
+                                                                       const int64_t *__restrict__ win_lo_all,
+                                                                       const int64_t *__restrict__ win_hi_all,
+                                                                       const int32_t *__restrict__ gx_all,
+                                                                       const int64_t *__restrict__ gy_all,
+                                                                       VmHit *__restrict__ hits_all, int32_t *__restrict__ n_hits)
+{
+    __shared__ int s_warp[VM_RS_THREADS / 32];
+    __shared__ uint8_t s_f[VM_RS_THREADS + VM_K9], s_r[VM_RS_THREADS + VM_K9];
     const VmReseedJobDev J = jobs[blockIdx.x];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rbase = read_off[J.read];
     const int L = (int)(read_off[J.read + 1] - rbase);
     const uint8_t *seq = (J.need_reverse ? reads_rc : reads_fwd) + rbase;     // oriented testseq
@@ -100,16 +117,27 @@ __global__ void __launch_bounds__(256) vm_reseed_hits_kernel(VmIndexDev ix, cons
     const int64_t *gy = gy_all + J.g_off;
     VmHit *hits = hits_all + J.hit_off;
     int running = 0;
-    bool over = false;
-    for (int i0 = J.readstart; i0 < J.readend; i0 += blockDim.x) {
+    for (int i0 = J.readstart; i0 < J.readend; i0 += VM_RS_THREADS) {
+        // stage the 5-letter codes of this chunk: forward bases [i0, i0+264), and the reverse-complement strand
+        // bases the chunk's k-mers read, s_r[u] = rc[L - i0 - 9 - (THREADS - 1) + u]
+        __syncthreads();
+        for (int u = tid; u < VM_RS_THREADS + VM_K9; u += VM_RS_THREADS) {
+            const int pf = i0 + u;
+            s_f[u] = pf < L ? (uint8_t)vm_code5(seq[pf]) : (uint8_t)4;
+            const int pr = L - i0 - VM_K9 - (VM_RS_THREADS - 1) + u;
+            s_r[u] = (pr >= 0 && pr < L) ? (uint8_t)vm_code5(rcs[pr]) : (uint8_t)4;
+        }
+        __syncthreads();
         const int iloc = i0 + tid;
         int cnt = 0;
         int fcode = -1, rcode = -1;
         long long rgap = 0, r1 = 0, r2 = 0, interval = 0;
+        uint32_t keep[VM_RS_KEEP];
+        unsigned keep_rev = 0;
         if (iloc < J.readend) {
-            fcode = vm_kmer_code(seq + iloc);
+            fcode = vm_kmer_code_staged(s_f + tid);
             const bool have_rev = iloc != 0;                      // rc[-(0+k):-0] == '' (:23212)
-            if (have_rev) rcode = vm_kmer_code(rcs + (L - iloc - VM_K9));
+            if (have_rev) rcode = vm_kmer_code_staged(s_r + (VM_RS_THREADS - 1 - tid));
             if (have_rev && fcode == rcode) { fcode = -1; rcode = -1; }   // palindrome: skip the position
             else {
                 int b0, b1, c0, c1;
@@ -120,24 +148,45 @@ __global__ void __launch_bounds__(256) vm_reseed_hits_kernel(VmIndexDev ix, cons
                 r2 = gy[c1];
                 rgap = iloc - gx[c0];
                 if (rgap < 0) rgap = -rgap;
-                if (fcode >= 0) vm_probe(ix, fcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t) { ++cnt; });
-                if (rcode >= 0) vm_probe(ix, rcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t) { ++cnt; });
+                if (fcode >= 0)
+                    vm_probe(ix, fcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t refloc) {
+#pragma unroll
+                        for (int t = 0; t < VM_RS_KEEP; ++t)
+                            if (cnt == t) keep[t] = refloc;
+                        ++cnt;
+                    });
+                if (rcode >= 0)
+                    vm_probe(ix, rcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval, [&](uint32_t refloc) {
+#pragma unroll
+                        for (int t = 0; t < VM_RS_KEEP; ++t)
+                            if (cnt == t) { keep[t] = refloc; keep_rev |= 1u << t; }
+                        ++cnt;
+                    });
             }
         }
-        s_scan[tid] = cnt;
-        __syncthreads();
-        for (int d = 1; d < 256; d <<= 1) {
-            const int t = tid >= d ? s_scan[tid - d] : 0;
-            __syncthreads();
-            s_scan[tid] += t;
-            __syncthreads();
+        // block-wide exclusive scan of cnt
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(VM_FULL, incl, d);
+            if (lane >= d) incl += t;
         }
-        int o = running + s_scan[tid] - cnt;
-        const int total = s_scan[255];
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        if (cnt > 0 && !J.count_only) {
-            if (o + cnt > J.hit_cap) over = true;
-            else {
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < VM_RS_THREADS / 32; ++w) {
+            const int t = s_warp[w];
+            if (w < warp) before += t;
+            total += t;
+        }
+        int o = running + before + incl - cnt;
+        if (cnt > 0 && (long long)running + total <= (long long)J.hit_cap) {
+            if (cnt <= VM_RS_KEEP) {
+#pragma unroll
+                for (int t = 0; t < VM_RS_KEEP; ++t)
+                    if (t < cnt) { hits[o + t].iloc_s = iloc << 1 | (int)((keep_rev >> t) & 1u); hits[o + t].refloc = keep[t]; }
+            } else {
                 if (fcode >= 0)
                     vm_probe(ix, fcode, win_lo, win_hi, J.n_win, rgap, r1, r2, interval,
                              [&](uint32_t refloc) { hits[o].iloc_s = iloc << 1; hits[o].refloc = refloc; ++o; });
@@ -148,7 +197,6 @@ __global__ void __launch_bounds__(256) vm_reseed_hits_kernel(VmIndexDev ix, cons
         }
         running += total;
     }
-    if (over) atomicExch(overflow, 1);
     if (tid == 0) n_hits[blockIdx.x] = running;
 }
 
@@ -170,12 +218,12 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
     const VmReseedJobDev J = jobs[blockIdx.x];
     const int lane = threadIdx.x;
     const int n = n_hits[blockIdx.x];
-    if (n > J.hit_cap) { if (lane == 0) n_out[blockIdx.x] = 0; return; }
+    if (n > J.hit_cap) { if (lane == 0) n_out[blockIdx.x] = 0; return; }   // never after the host's re-run
     const VmHit *hits = hits_all + J.hit_off;
     VmPoint *tab = table_all + J.tab_off;
     const int tmask = J.tab_size - 1;
-    int32_t *order = order_all + J.hit_off;
-    VmAnchor *out = out_all + 2 * J.hit_off;
+    int32_t *order = order_all + J.dense_off;
+    VmAnchor *out = out_all + 2 * J.dense_off;
     // clear the diagonal table with all lanes
     for (int t = lane; t < J.tab_size; t += 32) tab[t].key = VM_PT_EMPTY;
     __syncwarp();
@@ -227,12 +275,11 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
 
 int vm_reseed_launch(const VmIndexDev &ix, const VmReseedJobDev *jobs_dev, int n_jobs, const uint8_t *reads_fwd,
                      const uint8_t *reads_rc, const int64_t *read_off, const int64_t *win_lo, const int64_t *win_hi,
-                     const int32_t *gx, const int64_t *gy, void *hits, int32_t *n_hits, int32_t *overflow, void *table,
-                     int32_t *order, VmAnchor *out, int32_t *n_out, cudaStream_t stream)
+                     const int32_t *gx, const int64_t *gy, void *hits, int32_t *n_hits, cudaStream_t stream)
 {
     if (n_jobs <= 0) return 0;
-    vm_reseed_hits_kernel<<<n_jobs, 256, 0, stream>>>(ix, jobs_dev, reads_fwd, reads_rc, read_off, win_lo, win_hi, gx, gy,
-                                                      (VmHit *)hits, n_hits, overflow);
+    vm_reseed_hits_kernel<<<n_jobs, VM_RS_THREADS, 0, stream>>>(ix, jobs_dev, reads_fwd, reads_rc, read_off, win_lo, win_hi, gx, gy,
+                                                                (VmHit *)hits, n_hits);
     return 1;
 }
 
