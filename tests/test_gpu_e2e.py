@@ -63,3 +63,22 @@ def test_cuda_matches_oracle_on_fresh_reads(gpu_ctx, seed, mode, kw):
     b = vb.Aligner(ix, opt, mode, workers=1).align_packed(b"".join(enc), off)
     assert all((x == y).all() for x, y in zip(a, b))
     ix.close()
+
+
+def test_edit_distance_upper_bound_never_undercuts(gpu_ctx, monkeypatch):
+    """VM_ED_CHECK makes the backend run the exact kernel next to the bound through the anchors and raise if the
+    bound is ever below the distance; the records must still equal the oracle's (modes with 0.2 / 0.5 thresholds)."""
+    import vacmap_b200 as vb
+    monkeypatch.setenv("VM_ED_CHECK", "1")
+    for seed, mode in ((41, "H"), (42, "S")):
+        ref = synth.make_reference(seed, 300000, n_contigs=2)
+        reads = synth.make_reads(ref, seed + 100, 16, read_len=9000, err=0.12, sv_frac=0.5)
+        opt = vb.default_option(mode)
+        ix = vb.Index(ref, ctx=gpu_ctx)
+        got = vb.Aligner(ix, opt, mode, workers=1).align_batch(reads)
+        ox = oracle.Index(ref)
+        ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+        for (rid, seq), g in zip(reads, got):
+            want = pl.align_read(rid, seq, ox, ctg, opt, mode)
+            assert [tuple(r) for r in g] == [tuple(w) for w in want], rid
+        ix.close()

@@ -217,6 +217,103 @@ int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *cl
 }
 
 // ---------------------------------------------------------------------------
+// edit distance, upper bound through the chain's exact-match segments
+// ---------------------------------------------------------------------------
+// The divergence filter (mammap_clrnano.py:19251-19254) only asks whether distance / min(len) exceeds a
+// threshold.  Any alignment's cost bounds the distance from above, and the sub-alignment's own anchors spell
+// one out: walk the match segments (mismatches on them are counted, so nothing is assumed about the
+// anchors) and align each gap between consecutive segments optimally (unit-cost NW, Myers bit-vector with
+// the <= 128-base query gap in two registers).  If that cost is already within the threshold the exact
+// distance is not needed; the few jobs it does not settle go to vm_edit_distance_kernel.
+// One warp per job, one lane per segment (+ the gap in front of it); J.dir_off / J.n_out = offset / number
+// of the job's segments, J.result0 = the bound.
+struct VmMatchSeg { int32_t q, t, l; };
+
+__device__ __forceinline__ int vm_gap_distance(const VmSeqView &Q, int q0, int m, const VmSeqView &T, int t0, int n)
+{
+    if (m <= 0) return n;
+    if (n <= 0) return m;
+    unsigned long long P[5][2];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) { P[c][0] = 0ULL; P[c][1] = 0ULL; }
+    for (int i = 0; i < m; ++i) {
+        const int c = vm_at(Q, q0 + i);
+        const unsigned long long lo = i < 64 ? 1ULL << i : 0ULL, hi = i >= 64 ? 1ULL << (i - 64) : 0ULL;
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc)
+            if (c == cc) { P[cc][0] |= lo; P[cc][1] |= hi; }
+    }
+    const bool two = m > 64;
+    unsigned long long Pv0 = ~0ULL, Mv0 = 0ULL, Pv1 = ~0ULL, Mv1 = 0ULL;
+    const unsigned long long last = 1ULL << ((m - 1) & 63);
+    int score = m;
+    for (int j = 0; j < n; ++j) {
+        const int c = vm_at(T, t0 + j);
+        unsigned long long E0 = 0ULL, E1 = 0ULL;
+#pragma unroll
+        for (int cc = 0; cc < 5; ++cc)
+            if (c == cc) { E0 = P[cc][0]; E1 = P[cc][1]; }
+        // block 0, horizontal input +1 (global alignment: D[0][j] = j)
+        unsigned long long Xv = E0 | Mv0;
+        unsigned long long Xh = (((E0 & Pv0) + Pv0) ^ Pv0) | E0;
+        unsigned long long Ph = Mv0 | ~(Xh | Pv0);
+        unsigned long long Mh = Pv0 & Xh;
+        if (!two) score += (Ph & last) ? 1 : ((Mh & last) ? -1 : 0);
+        const int ho = (int)(Ph >> 63) - (int)(Mh >> 63);
+        Ph = Ph << 1 | 1ULL;
+        Mh <<= 1;
+        Pv0 = Mh | ~(Xv | Ph);
+        Mv0 = Ph & Xv;
+        if (two) {
+            const unsigned long long neg = ho < 0 ? 1ULL : 0ULL;
+            Xv = E1 | Mv1;
+            E1 |= neg;
+            Xh = (((E1 & Pv1) + Pv1) ^ Pv1) | E1;
+            Ph = Mv1 | ~(Xh | Pv1);
+            Mh = Pv1 & Xh;
+            score += (Ph & last) ? 1 : ((Mh & last) ? -1 : 0);
+            Ph <<= 1;
+            Mh <<= 1;
+            Mh |= neg;
+            Ph |= ho > 0 ? 1ULL : 0ULL;
+            Pv1 = Mh | ~(Xv | Ph);
+            Mv1 = Ph & Xv;
+        }
+    }
+    return score;
+}
+
+__global__ void __launch_bounds__(128) vm_ed_upper_kernel(VmAlnJobDev *jobs, const int *__restrict__ job_ids, int n_jobs,
+                                                          const VmMatchSeg *__restrict__ segs, VmSeqSources S)
+{
+    const int w = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n_jobs) return;
+    VmAlnJobDev &J = jobs[job_ids[w]];
+    const VmSeqView Q = vm_view(S, J.q, J.read), T = vm_view(S, J.t, J.read);
+    const VmMatchSeg *sg = segs + J.dir_off;
+    const int n = J.n_out;
+    long long cost = 0;
+    for (int i = lane; i <= n; i += 32) {
+        int cq = 0, ct = 0;
+        if (i > 0) { const VmMatchSeg p = sg[i - 1]; cq = p.q + p.l; ct = p.t + p.l; }
+        int nq = Q.len, nt = T.len, l = 0;
+        if (i < n) { const VmMatchSeg a = sg[i]; nq = a.q; nt = a.t; l = a.l; }
+        cost += vm_gap_distance(Q, cq, nq - cq, T, ct, nt - ct);
+        for (int x = 0; x < l; ++x) cost += vm_at(Q, nq + x) != vm_at(T, nt + x);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) cost += __shfl_xor_sync(VM_FULL, cost, d);
+    if (lane == 0) J.result0 = cost;
+}
+
+int vm_launch_ed_upper(VmAlnJobDev *jobs, const int *ids_dev, int n_jobs, const void *segs_dev, VmSeqSources src, cudaStream_t stream)
+{
+    if (n_jobs <= 0) return 0;
+    vm_ed_upper_kernel<<<(n_jobs + 3) / 4, 128, 0, stream>>>(jobs, ids_dev, n_jobs, (const VmMatchSeg *)segs_dev, src);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
 // shared cell update (ksw2 extd2 recurrences, see oracle/orc_align.c)
 // ---------------------------------------------------------------------------
 struct VmGapPar {

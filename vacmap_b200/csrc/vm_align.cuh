@@ -69,6 +69,8 @@ extern const int VM_ED_CLASS_G[VM_ED_NCLASS];
 int vm_ed_slots(int m, int n, long long band);
 int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
                             cudaStream_t stream);
+// upper bound of the distance through the job's match segments (J.dir_off / J.n_out into segs_dev, 12-byte {q, t, l})
+int vm_launch_ed_upper(VmAlnJobDev *jobs, const int *ids_dev, int n_jobs, const void *segs_dev, VmSeqSources src, cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);
 
 // ---- global fill (vm_fill.cu) ----

@@ -73,7 +73,7 @@ public:
     {
         seed_.release();
         VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
-                         &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_};
+                         &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_, &d_msegs_};
         for (VmDevBuf *x : b) x->release();
         VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_};
         for (VmPinnedBuf *x : p) x->release();
@@ -82,11 +82,11 @@ public:
     bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
-    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0;
+    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0;
     void reset_counters()
     {
         timer.ms.clear();
-        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = 0;
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = 0;
     }
 
     // device time of a group of launches, CUDA events on the ctx stream
@@ -436,32 +436,91 @@ public:
         return h_jobs_.as<VmAlnJobDev>();
     }
 
-    void edit_distance(const ReadBatch &, std::vector<EdJob> &jobs) override
+    // Divergence filter distances.  Jobs that come with their chain's match segments are first bounded from
+    // above by the alignment through those segments (vm_ed_upper_kernel); a bound within the job's band settles
+    // the filter, so only the jobs it leaves open (none on typical reads) run the exact banded kernel.
+    void edit_distance(const ReadBatch &, std::vector<EdJob> &jobs, const std::vector<vmg::MatchSeg> &segs) override
     {
         WallTimer wt(this, "edit_distance");
         const int nj = (int)jobs.size();
         if (nj == 0) return;
+        const bool check = getenv("VM_ED_CHECK") != nullptr;   // debug: also run the exact kernel and compare
+        std::vector<int> open_jobs;
+        std::vector<int> ub;
+        for (int j = 0; j < nj; ++j) {
+            if (jobs[j].seg_n > 0 && jobs[j].band >= 0) ub.push_back(j);
+            else open_jobs.push_back(j);
+        }
+        std::vector<int64_t> bound;
+        if (!ub.empty()) {
+            const int nu = (int)ub.size();
+            VmAlnJobDev *J = stage_jobs((size_t)nu);
+            parallel_for(nu, host_threads, [&](int64_t t) {
+                const EdJob &e = jobs[ub[t]];
+                memset(&J[t], 0, sizeof(VmAlnJobDev));
+                J[t].q = spec(e.a);
+                J[t].t = spec(e.b);
+                J[t].read = e.read;
+                J[t].dir_off = e.seg_off;
+                J[t].n_out = e.seg_n;
+            }, 1024);
+            static_assert(sizeof(vmg::MatchSeg) == 12, "match segment layout");
+            BE_OK(d_msegs_.ensure(segs.size() * sizeof(vmg::MatchSeg) + 64));
+            BE_OK(d_seg_.ensure((size_t)nu * 4 + 64));
+            std::vector<int> ids((size_t)nu);
+            for (int t = 0; t < nu; ++t) ids[t] = t;
+            BE_OK(cudaMemcpyAsync(d_msegs_.p, segs.data(), segs.size() * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
+            BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, c_->stream));
+            BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
+            KTimer kt(this, "k_ed_upper");
+            c_->launches += vm_launch_ed_upper(jobs_.as<VmAlnJobDev>(), d_seg_.as<int>(), nu, d_msegs_.p, sources(), c_->stream);
+            kt.stop();
+            BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaStreamSynchronize(c_->stream));
+            BE_OK(cudaGetLastError());
+            bound.assign((size_t)nj, -1);
+            for (int t = 0; t < nu; ++t) {
+                const int j = ub[t];
+                bound[j] = J[t].result0;
+                if (J[t].result0 <= jobs[j].band && !check) jobs[j].dist = J[t].result0;
+                else open_jobs.push_back(j);
+            }
+            ed_upper_jobs_ += nu;
+        }
+        if (open_jobs.empty()) return;
+        ed_exact(jobs, open_jobs);
+        if (check)
+            for (int j : ub)
+                if (bound[j] < jobs[j].dist && jobs[j].dist <= jobs[j].band)
+                    throw std::runtime_error("VM_ED_CHECK: upper bound " + std::to_string(bound[j]) + " below the distance " +
+                                             std::to_string(jobs[j].dist));
+    }
+
+    void ed_exact(std::vector<EdJob> &jobs, const std::vector<int> &which)
+    {
+        const int nj = (int)which.size();
         VmAlnJobDev *J = stage_jobs((size_t)nj);
         std::vector<std::vector<int>> cls(VM_ED_NCLASS);
         std::vector<int64_t> work((size_t)nj);
         int class_words[VM_ED_NCLASS] = {0};
         for (int j = 0; j < nj; ++j) {
+            const EdJob &e = jobs[which[j]];
             memset(&J[j], 0, sizeof(VmAlnJobDev));
             // the shorter sequence is the bit-vector pattern (fewer 64-row blocks)
-            const bool a_short = jobs[j].a.len() <= jobs[j].b.len();
-            J[j].q = spec(a_short ? jobs[j].a : jobs[j].b);
-            J[j].t = spec(a_short ? jobs[j].b : jobs[j].a);
-            J[j].read = jobs[j].read;
-            J[j].out_off = jobs[j].band;
+            const bool a_short = e.a.len() <= e.b.len();
+            J[j].q = spec(a_short ? e.a : e.b);
+            J[j].t = spec(a_short ? e.b : e.a);
+            J[j].read = e.read;
+            J[j].out_off = e.band;
             const int m = J[j].q.len, n = J[j].t.len, W = (m + 63) / 64;
-            const int G = vm_ed_slots(m, n, jobs[j].band);
+            const int G = vm_ed_slots(m, n, e.band);
             int k = 0;
             while (k < VM_ED_NCLASS && VM_ED_CLASS_G[k] < G) ++k;
             if (k == VM_ED_NCLASS) throw std::runtime_error("edit distance: sequence pair too long for the register-resident band");
             cls[k].push_back(j);
             class_words[k] = std::max(class_words[k], W);
             work[j] = (int64_t)(n + W) * VM_ED_CLASS_G[k];
-            const int64_t kk = jobs[j].band < 0 ? std::max(m, n) : jobs[j].band;
+            const int64_t kk = e.band < 0 ? std::max(m, n) : e.band;
             ed_cells_ += (double)std::min<int64_t>(m, kk + 64) * (double)n;   // cells inside the (k + 1)-diagonal band
         }
         std::vector<int> ids;
@@ -483,7 +542,7 @@ public:
         BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
         BE_OK(cudaGetLastError());
-        for (int j = 0; j < nj; ++j) jobs[j].dist = J[j].result0;
+        for (int j = 0; j < nj; ++j) jobs[which[j]].dist = J[j].result0;
     }
 
     void extend(const ReadBatch &, std::vector<ExtJobRef> &jobs) override
@@ -572,7 +631,7 @@ private:
     vm_index_handle *ih_;
     VmSeedBufs seed_;
     VmDevBuf reads_fwd_, reads_rc_, read_off_, jobs_, d_wlo_, d_whi_, d_gx_, d_gy_, d_nh_, d_hits_, d_tab_, d_order_, d_rout_,
-        d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_;
+        d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_, d_msegs_;
     VmFillPlan plan_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_;
     std::vector<int64_t> off_host_;

@@ -179,7 +179,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
             for (int w = 0; w < workers; ++w) {
                 for (auto &kv : wbe[w]->timer.ms) be.timer.add(kv.first.c_str(), kv.second);
                 be.fill_cells_ += wbe[w]->fill_cells_; be.fill_bases_ += wbe[w]->fill_bases_; be.fill_jobs_ += wbe[w]->fill_jobs_;
-                be.ed_cells_ += wbe[w]->ed_cells_; be.reseed_hits_ += wbe[w]->reseed_hits_; be.chain_anchors_ += wbe[w]->chain_anchors_;
+                be.ed_cells_ += wbe[w]->ed_cells_; be.ed_upper_jobs_ += wbe[w]->ed_upper_jobs_; be.reseed_hits_ += wbe[w]->reseed_hits_; be.chain_anchors_ += wbe[w]->chain_anchors_;
                 c->launches += c->kids[w]->launches;
             }
         }
@@ -217,6 +217,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         be.timer.add("n_fill_bases", be.fill_bases_);
         be.timer.add("n_fill_jobs", be.fill_jobs_);
         be.timer.add("n_ed_cells", be.ed_cells_);
+        be.timer.add("n_ed_upper_jobs", be.ed_upper_jobs_);
         be.timer.add("n_reseed_hits", be.reseed_hits_);
         be.timer.add("n_chain_anchors", be.chain_anchors_);
         for (auto &kv : be.timer.ms) {
@@ -278,7 +279,7 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
                 jobs[j].b = ref_of(t_off[j], t_off[j + 1]);
                 jobs[j].band = kind == 3 ? out1[j] : -1;
             }
-            be.edit_distance(b, jobs);
+            be.edit_distance(b, jobs, std::vector<vmg::MatchSeg>());
             for (int64_t j = 0; j < n_pairs; ++j) out0[j] = jobs[j].dist;
         } else if (kind == 1) {
             std::vector<ExtJobRef> jobs((size_t)n_pairs);

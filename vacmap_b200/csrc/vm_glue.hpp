@@ -578,6 +578,38 @@ static void query_target(const Anc &pre, const Anc &now, int64_t L, const Contig
     }
 }
 
+// Exact-match segments of one sub-alignment in the coordinates of its divergence-filter job
+// (query_target above): (query offset, target offset, length), ascending, clipped to the two slices and
+// trimmed so that consecutive segments overlap in neither sequence.  They let the device bound the edit
+// distance from above by an alignment that runs through the chain's anchors (vm_ed_upper_kernel).
+struct MatchSeg { int32_t q, t, l; };
+static inline bool match_segments(const Path &aln, int64_t qlen, int64_t tlen, std::vector<MatchSeg> &out, int64_t max_qgap)
+{
+    const size_t first = out.size();
+    if (aln.size() < 2) return false;
+    const Anc &pre = aln.front(), &now = aln.back();
+    const bool fwd = pre.s == 1;
+    int64_t cq = 0, ct = 0;
+    const size_t n = aln.size();
+    for (size_t k = 0; k < n; ++k) {
+        const Anc &a = fwd ? aln[k] : aln[n - 1 - k];     // ascending in the job's query coordinate
+        if (a.s != pre.s) { out.resize(first); return false; }
+        int64_t q = fwd ? a.x - pre.x : now.x - a.x - a.l;
+        int64_t t = fwd ? a.y - pre.y : a.y - (now.y + now.l);
+        int64_t l = a.l;
+        int64_t d = std::max<int64_t>(std::max<int64_t>(cq - q, ct - t), 0);
+        q += d; t += d; l -= d;
+        l = std::min(l, std::min(qlen - q, tlen - t));
+        if (l <= 0) continue;
+        if (q - cq > max_qgap) { out.resize(first); return false; }
+        out.push_back(MatchSeg{(int32_t)q, (int32_t)t, (int32_t)l});
+        cq = q + l;
+        ct = t + l;
+    }
+    if (qlen - cq > max_qgap) { out.resize(first); return false; }
+    return true;
+}
+
 struct ExtJob {      // one z-drop edge extension (k_cigar 2,-4,4,4,4,4 bw 100 zdrop 50)
     int32_t aln = 0;
     int32_t side = 0;    // 0: left of the first anchor, 1: right of the last anchor

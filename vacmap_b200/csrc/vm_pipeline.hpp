@@ -52,7 +52,9 @@ struct ChainOut {
 
 struct GuideJobRef { int32_t read; vmg::GuideJob job; };
 // band: half-width k of the Ukkonen band (-1 = none); dist is exact when <= band, else only known to be > band
-struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; int64_t band = -1; };
+// seg_off/seg_n: exact-match segments of the job inside the array handed to Backend::edit_distance (seg_n = 0:
+// none); with them a backend may return in `dist` any upper bound of the distance that is <= band
+struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; int64_t band = -1; int64_t seg_off = 0; int32_t seg_n = 0; };
 struct ExtJobRef { int32_t read; vmg::ExtJob job; };
 // CIGAR ops of a fill job: cig[cig_off .. cig_off + cig_len) of the array Backend::fill hands back
 struct FillJobRef { int32_t read; vmg::FillJob job; int64_t cig_off = 0; int32_t cig_len = 0; };
@@ -70,7 +72,8 @@ struct Backend {
     virtual void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
                               const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
                               ChainOut &out) = 0;
-    virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs) = 0;
+    // a = query, b = target of get_query_target_for_cigar; segs: exact-match segments the jobs refer to
+    virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const std::vector<vmg::MatchSeg> &segs) = 0;
     virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
     // sets cig_off / cig_len of every job; the returned array stays valid until the next fill()
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
@@ -355,6 +358,7 @@ private:
         // a. rebuild_chain_break + divergence filter jobs
         Phase *ph = new Phase(this, "g_ext_rebuild");
         std::vector<std::vector<EdJob>> edj((size_t)m);
+        std::vector<std::vector<vmg::MatchSeg>> segj((size_t)m);
         parallel_for(m, threads_, [&](int64_t t) {
             const int64_t r = ids[t];
             ReadState &s = st[r];
@@ -367,18 +371,25 @@ private:
                     j.read = (int32_t)r;
                     vmg::query_target(s.al[i].front(), s.al[i].back(), read_len[r], ctg_, j.b, j.a);
                     if (std::min(j.a.len(), j.b.len()) == 0) throw vmg::ReadDropped("division by zero");
+                    j.seg_off = (int64_t)segj[t].size();
+                    j.seg_n = vmg::match_segments(s.al[i], j.a.len(), j.b.len(), segj[t], 128) ? (int32_t)(segj[t].size() - (size_t)j.seg_off) : 0;
                     orient(j.a, s.need_reverse);
                     orient(j.b, s.need_reverse);
                     j.band = divergence_band(std::min(j.a.len(), j.b.len()));
                     edj[t].push_back(j);
                 }
-            } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); }
+            } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); segj[t].clear(); }
         });
         std::vector<EdJob> ed;
-        std::vector<int64_t> ed_start;
+        std::vector<int64_t> ed_start, seg_start;
+        std::vector<vmg::MatchSeg> segs;
         parallel_concat(edj, threads_, ed, ed_start);
+        parallel_concat(segj, threads_, segs, seg_start);
+        parallel_for(m, threads_, [&](int64_t t) {
+            for (int64_t q = ed_start[t]; q < ed_start[t + 1]; ++q) ed[q].seg_off += seg_start[t];
+        }, 256);
         delete ph;
-        be_.edit_distance(b, ed);
+        be_.edit_distance(b, ed, segs);
         ph = new Phase(this, "g_ext_edges");
         parallel_for(m, threads_, [&](int64_t t) {
             ReadState &s = st[ids[t]];
