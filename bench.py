@@ -227,6 +227,7 @@ def main():
     stage = {}
     aligned = 0
     t0 = time.perf_counter()
+    cpu0 = time.process_time()
     for _ in range(args.steps):
         rec_off, recs, cig = al.align_packed(cat, off, resident=True)
         for k, v in al.last_stage_ms.items():
@@ -235,6 +236,7 @@ def main():
         aligned += int(np.diff(off)[mapped].sum())
     barrier()
     wall = time.perf_counter() - t0
+    cpu_busy = (time.process_time() - cpu0) / max(wall, 1e-9)      # host cores kept busy by this rank
     clocks = sampler.stop()
     launches = ctx.kernel_launches - l0
 
@@ -303,7 +305,7 @@ def main():
                                  "the 126 MB L2" % (bases / 1e6),
                            "sharding": "reads split across ranks, index replicated per GPU, records gathered on rank 0"},
                 "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": len(cat) + off.nbytes, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "host_cores_busy": round(cpu_busy, 2), "host_cores": os.cpu_count(),
                 "records_per_step": nrec_all,
                 "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
                 "work_per_step": counts,

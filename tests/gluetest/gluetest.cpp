@@ -82,7 +82,7 @@ struct OracleBackend : public Backend {
         for (int64_t t = 0; t < n; ++t) { rows[t * 4] = a[t].x; rows[t * 4 + 1] = a[t].y; rows[t * 4 + 2] = a[t].s; rows[t * 4 + 3] = a[t].l; }
     }
 
-    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap, double,
                     std::vector<char> &need_reverse, ChainOut &out) override
     {
         out = ChainOut();

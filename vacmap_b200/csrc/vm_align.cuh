@@ -86,7 +86,10 @@ struct VmFillPlan {
     std::vector<VmFillLaunch> launches;
     size_t dir_words = 0, band_words = 0;   // scratch needed (uint32 words), shared by the launches
 };
-void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan);
-// counters_dev: one zeroed int per launch; returns the number of kernel launches
+void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan, int host_threads = 1);
+// counters_dev: one zeroed int per launch.  The CIGAR ops of job j end up in dense_out[results[j].x .. + results[j].y)
+// (results: uint2 per job, zero-initialised by the caller; dense_count: zeroed 64-bit bump allocator;
+// cigar_scratch: per-job room of tlen + qlen + 2 ops at J.out_off).  Returns the number of kernel launches.
 int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs_dev, const VmFillPair *pairs_dev, VmSeqSources src, int eqx,
-                   uint32_t *dir_scratch, uint32_t *band_scratch, int *counters_dev, uint32_t *cigar_out, cudaStream_t stream);
+                   uint32_t *dir_scratch, uint32_t *band_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
+                   unsigned long long *dense_count, void *results, cudaStream_t stream);

@@ -12,9 +12,11 @@
 #include "vm_seed.cuh"
 #include "vm_reseed.cuh"
 #include "vm_align.cuh"
+#include "vm_extract.cuh"
 #include "vm_pipeline.hpp"
 #include <chrono>
 #include <map>
+#include <mutex>
 
 using namespace vmp;
 
@@ -66,16 +68,50 @@ struct StageTimer {
     void add(const char *k, double v) { ms[k] += v; }
 };
 
+// Optional wall-clock timeline of every timed phase of every worker (VM_TIMELINE=<file>): one line per phase,
+// "worker name start_ms end_ms", for looking at how host glue and kernels of the pipelined workers overlap.
+struct Timeline {
+    std::mutex mu;
+    std::vector<std::string> lines;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    const char *path = getenv("VM_TIMELINE");
+    static Timeline &get() { static Timeline t; return t; }
+    void add(const void *who, const char *name, std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b)
+    {
+        if (!path) return;
+        char buf[160];
+        snprintf(buf, sizeof(buf), "%p %s %.3f %.3f", who, name, std::chrono::duration<double, std::milli>(a - t0).count(),
+                 std::chrono::duration<double, std::milli>(b - t0).count());
+        std::lock_guard<std::mutex> lk(mu);
+        lines.push_back(buf);
+    }
+    void flush()
+    {
+        if (!path) return;
+        std::lock_guard<std::mutex> lk(mu);
+        FILE *f = fopen(path, "a");
+        if (!f) return;
+        for (const std::string &l : lines) fprintf(f, "%s\n", l.c_str());
+        fprintf(f, "# flush\n");
+        fclose(f);
+        lines.clear();
+    }
+};
+
 class CudaBackend : public Backend {
 public:
     CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih) {}
     ~CudaBackend() override
     {
         seed_.release();
+        gx_.release();
+        lx_.release();
+        { VmDevBuf *xb[] = {&x_ids_, &x_used_, &x_tmp_anc_, &x_tmp_S_, &x_tmp_len_, &x_tmp_score_}; for (VmDevBuf *x : xb) x->release(); }
         VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
                          &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_, &d_msegs_};
         for (VmDevBuf *x : b) x->release();
-        VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_};
+        VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_, &h_gx_, &h_gy_,
+                            &h_segs_};
         for (VmPinnedBuf *x : p) x->release();
     }
     StageTimer timer;
@@ -91,8 +127,8 @@ public:
 
     // device time of a group of launches, CUDA events on the ctx stream
     struct KTimer {
-        CudaBackend *be; const char *name; cudaEvent_t a, b;
-        KTimer(CudaBackend *be_, const char *n) : be(be_), name(n)
+        CudaBackend *be; const char *name; cudaEvent_t a, b; std::chrono::steady_clock::time_point w0;
+        KTimer(CudaBackend *be_, const char *n) : be(be_), name(n), w0(std::chrono::steady_clock::now())
         {
             cudaEventCreate(&a); cudaEventCreate(&b);
             cudaEventRecord(a, be->c_->stream);
@@ -105,12 +141,18 @@ public:
             cudaEventElapsedTime(&ms, a, b);
             be->timer.add(name, ms);
             cudaEventDestroy(a); cudaEventDestroy(b);
+            Timeline::get().add(be, name, w0, std::chrono::steady_clock::now());
         }
     };
     struct WallTimer {
         CudaBackend *be; const char *name; std::chrono::steady_clock::time_point t0;
         WallTimer(CudaBackend *b, const char *n) : be(b), name(n), t0(std::chrono::steady_clock::now()) {}
-        ~WallTimer() { be->timer.add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); }
+        ~WallTimer()
+        {
+            const auto t1 = std::chrono::steady_clock::now();
+            be->timer.add(name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            Timeline::get().add(be, name, t0, t1);
+        }
     };
 
     // b.off may start anywhere inside b.seq (a sub-batch of a larger batch): the device copy is rebased to 0
@@ -169,7 +211,7 @@ public:
     }
 
     // ---- seeding + global chaining, anchors never leave the device in between ----
-    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+    void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap, double accept,
                     std::vector<char> &need_reverse, ChainOut &out) override
     {
         WallTimer wt(this, "seed_chain");
@@ -205,26 +247,91 @@ public:
         if (vm_chain_core(c_, prm, seed_.out.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, nullptr, ms4) != VM_OK)
             throw std::runtime_error("chain: " + c_->err);
         timer.add("chain_global_kernels", ms4[1] + ms4[2] + ms4[3]);
+        // chains extracted on the device: only what hit2work_1 keeps goes to the host
+        extract(true, n, span, ids, accept, gx_, out);
+    }
+
+    // result buffers of one extraction (global / local stage), reused across batches
+    struct Extracted {
+        VmDevBuf rec, anc, S, len, score, counters;
+        VmPinnedBuf h_rec, h_anc, h_S, h_len, h_score, h_counters;
+        void release()
+        {
+            VmDevBuf *d[] = {&rec, &anc, &S, &len, &score, &counters};
+            for (VmDevBuf *x : d) x->release();
+            VmPinnedBuf *h[] = {&h_rec, &h_anc, &h_S, &h_len, &h_score, &h_counters};
+            for (VmPinnedBuf *x : h) x->release();
+        }
+    };
+
+    void extract(bool global, int64_t n, int64_t span, const std::vector<int> &ids, double accept, Extracted &X, ChainOut &out)
+    {
+        static_assert(sizeof(ExtractRec) == sizeof(VmExtractRec), "extract record layout");
         VmChainState &s = c_->chain;
         const size_t T = (size_t)std::max<int64_t>(span, 1);
-        BE_OK(h_sorted_.ensure(T * 16));
-        BE_OK(h_S_.ensure(T * 8));
-        BE_OK(h_P_.ensure(T * 4));
-        BE_OK(h_A_.ensure(T * 4));
-        BE_OK(h_gmax_.ensure((size_t)(n + 1) * 8));
-        if (span > 0) {
-            BE_OK(cudaMemcpyAsync(h_sorted_.p, s.sorted.p, (size_t)span * 16, cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaMemcpyAsync(h_S_.p, s.S.p, (size_t)span * 8, cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaMemcpyAsync(h_P_.p, s.P.p, (size_t)span * 4, cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaMemcpyAsync(h_A_.p, s.S_arg.p, (size_t)span * 4, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(X.rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
+        BE_OK(X.anc.ensure(T * 16));
+        BE_OK(X.counters.ensure(64));
+        BE_OK(x_tmp_anc_.ensure(T * 16));
+        BE_OK(x_ids_.ensure(ids.size() * 4 + 64));
+        if (global) {
+            BE_OK(X.S.ensure(T * 8));
+            BE_OK(X.len.ensure(T * 4));
+            BE_OK(X.score.ensure(T * 8));
+            BE_OK(x_used_.ensure(T));
+            BE_OK(x_tmp_S_.ensure(T * 8));
+            BE_OK(x_tmp_len_.ensure(T * 4));
+            BE_OK(x_tmp_score_.ensure(T * 8));
+            BE_OK(cudaMemsetAsync(x_used_.p, 0, T, c_->stream));
         }
-        if (n > 0) BE_OK(cudaMemcpyAsync(h_gmax_.p, s.gmax.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaMemsetAsync(X.counters.p, 0, 64, c_->stream));
+        BE_OK(cudaMemsetAsync(X.rec.p, 0, (size_t)(n + 1) * sizeof(VmExtractRec), c_->stream));
+        if (!ids.empty()) BE_OK(cudaMemcpyAsync(x_ids_.p, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, c_->stream));
+        VmExtractOut O;
+        O.rec = X.rec.as<VmExtractRec>();
+        O.anc = X.anc.as<VmAnchor>();
+        O.S = X.S.as<double>();
+        O.chain_len = X.len.as<int32_t>();
+        O.chain_score = X.score.as<double>();
+        O.n_anc_total = X.counters.as<unsigned long long>();
+        O.n_chain_total = X.counters.as<unsigned long long>() + 1;
+        {
+            KTimer kt(this, global ? "k_extract_global" : "k_extract_local");
+            if (global)
+                c_->launches += vm_launch_extract_global(x_ids_.as<int>(), (int)ids.size(), s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(),
+                                                         s.sorted.as<VmAnchor>(), s.S.as<double>(), s.P.as<int32_t>(),
+                                                         s.S_arg.as<int32_t>(), s.gmax.as<int64_t>(), accept, x_used_.as<uint8_t>(),
+                                                         x_tmp_anc_.as<VmAnchor>(), x_tmp_S_.as<double>(), x_tmp_len_.as<int32_t>(),
+                                                         x_tmp_score_.as<double>(), O, c_->stream);
+            else
+                c_->launches += vm_launch_extract_local(x_ids_.as<int>(), (int)ids.size(), s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(),
+                                                        s.sorted.as<VmAnchor>(), s.P.as<int32_t>(), s.gmax.as<int64_t>(),
+                                                        x_tmp_anc_.as<VmAnchor>(), O, c_->stream);
+            kt.stop();
+        }
+        BE_OK(X.h_counters.ensure(64));
+        BE_OK(X.h_rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
+        BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 16, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaMemcpyAsync(X.h_rec.p, X.rec.p, (size_t)n * sizeof(VmExtractRec), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
-        out.sorted = h_sorted_.as<Anc32>();
-        out.S = h_S_.as<double>();
-        out.P = h_P_.as<int32_t>();
-        out.S_arg = h_A_.as<int32_t>();
-        for (int64_t r = 0; r < n; ++r) out.gmax[r] = h_gmax_.as<int64_t>()[r];
+        BE_OK(cudaGetLastError());
+        const size_t na = (size_t)X.h_counters.as<unsigned long long>()[0], nc = (size_t)X.h_counters.as<unsigned long long>()[1];
+        BE_OK(X.h_anc.ensure(std::max<size_t>(na, 1) * 16));
+        if (na) BE_OK(cudaMemcpyAsync(X.h_anc.p, X.anc.p, na * 16, cudaMemcpyDeviceToHost, c_->stream));
+        if (global) {
+            BE_OK(X.h_S.ensure(std::max<size_t>(na, 1) * 8));
+            BE_OK(X.h_len.ensure(std::max<size_t>(nc, 1) * 4));
+            BE_OK(X.h_score.ensure(std::max<size_t>(nc, 1) * 8));
+            if (na) BE_OK(cudaMemcpyAsync(X.h_S.p, X.S.p, na * 8, cudaMemcpyDeviceToHost, c_->stream));
+            if (nc) BE_OK(cudaMemcpyAsync(X.h_len.p, X.len.p, nc * 4, cudaMemcpyDeviceToHost, c_->stream));
+            if (nc) BE_OK(cudaMemcpyAsync(X.h_score.p, X.score.p, nc * 8, cudaMemcpyDeviceToHost, c_->stream));
+        }
+        BE_OK(cudaStreamSynchronize(c_->stream));
+        out.rec = X.h_rec.as<ExtractRec>();
+        out.x_anc = X.h_anc.as<Anc32>();
+        out.x_S = X.h_S.as<double>();
+        out.x_len = X.h_len.as<int32_t>();
+        out.x_score = X.h_score.as<double>();
     }
 
     // ---- local re-seeding + local chaining ----
@@ -240,14 +347,20 @@ public:
         out.cnt.assign((size_t)n, 0);
         out.gmax.assign((size_t)n, -1);
         if (nj == 0) return;
+        WallTimer *hs = new WallTimer(this, "h_reseed_stage");
         std::vector<VmReseedJobDev> J((size_t)nj);
         std::vector<int64_t> w_off((size_t)nj + 1, 0), g_off((size_t)nj + 1, 0);
         for (int j = 0; j < nj; ++j) {
             w_off[j + 1] = w_off[j] + (int64_t)jobs[j].job.win_lo.size();
             g_off[j + 1] = g_off[j] + (int64_t)jobs[j].job.gx.size();
         }
-        std::vector<int64_t> wlo((size_t)w_off[nj]), whi((size_t)w_off[nj]), gy((size_t)g_off[nj]);
-        std::vector<int32_t> gx((size_t)g_off[nj]);
+        std::vector<int64_t> wlo((size_t)w_off[nj]), whi((size_t)w_off[nj]);
+        // the guide points are the bulk of this stage's upload: staged in page-locked memory
+        const size_t n_g = (size_t)g_off[nj];
+        BE_OK(h_gy_.ensure(n_g * 8 + 64));
+        BE_OK(h_gx_.ensure(n_g * 4 + 64));
+        int64_t *gy = h_gy_.as<int64_t>();
+        int32_t *gx = h_gx_.as<int32_t>();
         parallel_for(nj, host_threads, [&](int64_t j) {
             const vmg::GuideJob &g = jobs[j].job;
             VmReseedJobDev &d = J[j];
@@ -262,8 +375,8 @@ public:
             d.g_off = g_off[j];
             std::copy(g.win_lo.begin(), g.win_lo.end(), wlo.begin() + w_off[j]);
             std::copy(g.win_hi.begin(), g.win_hi.end(), whi.begin() + w_off[j]);
-            std::copy(g.gx.begin(), g.gx.end(), gx.begin() + g_off[j]);
-            std::copy(g.gy.begin(), g.gy.end(), gy.begin() + g_off[j]);
+            std::copy(g.gx.begin(), g.gx.end(), gx + g_off[j]);
+            std::copy(g.gy.begin(), g.gy.end(), gy + g_off[j]);
         }, 64);
         // one pass with room for 3 hits per read position; the rare job that needs more is re-run below
         int64_t hit_off = 0;
@@ -276,17 +389,18 @@ public:
         BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev)));
         BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
         BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
-        BE_OK(d_gx_.ensure(gx.size() * 4 + 64));
-        BE_OK(d_gy_.ensure(gy.size() * 8 + 64));
+        BE_OK(d_gx_.ensure(n_g * 4 + 64));
+        BE_OK(d_gy_.ensure(n_g * 8 + 64));
         BE_OK(d_nh_.ensure((size_t)nj * 8 + 64));
         BE_OK(d_hits_.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_wlo_.p, wlo.data(), wlo.size() * 8, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_gx_.p, gx.data(), gx.size() * 4, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_gy_.p, gy.data(), gy.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gx_.p, gx, n_g * 4, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gy_.p, gy, n_g * 8, cudaMemcpyHostToDevice, c_->stream));
         int32_t *d_n_hits = d_nh_.as<int32_t>(), *d_n_out = d_nh_.as<int32_t>() + nj;
         const VmIndexDev &ix = ih_->ix->dev;
+        delete hs;
         {
             KTimer kt(this, "k_reseed_hits");
             c_->launches += vm_reseed_launch(ix, jobs_.as<VmReseedJobDev>(), nj, reads_fwd_.as<uint8_t>(), reads_rc_.as<uint8_t>(),
@@ -391,21 +505,11 @@ public:
                 throw std::runtime_error("chain: " + c_->err);
             timer.add("chain_local_kernels", ms4[1] + ms4[2] + ms4[3]);
         }
-        VmChainState &s = c_->chain;
-        const size_t T = (size_t)std::max<int64_t>(dense, 1);
-        BE_OK(h_lsorted_.ensure(T * 16));
-        BE_OK(h_lP_.ensure(T * 4));
-        BE_OK(h_lgmax_.ensure((size_t)(n + 1) * 8));
-        if (dense > 0) {
-            BE_OK(cudaMemcpyAsync(h_lsorted_.p, s.sorted.p, (size_t)dense * 16, cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaMemcpyAsync(h_lP_.p, s.P.p, (size_t)dense * 4, cudaMemcpyDeviceToHost, c_->stream));
-        }
-        BE_OK(cudaMemcpyAsync(h_lgmax_.p, s.gmax.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
-        BE_OK(cudaGetLastError());
-        out.sorted = h_lsorted_.as<Anc32>();
-        out.P = h_lP_.as<int32_t>();
-        for (int64_t r = 0; r < n; ++r) out.gmax[r] = h_lgmax_.as<int64_t>()[r];
+        // best chain of every read traced back (and trimmed) on the device
+        std::vector<int> xids;
+        for (int64_t r = 0; r < n; ++r)
+            if (variant[r] != 0 && out.cnt[r] > 0) xids.push_back((int)r);
+        extract(false, n, dense, xids, 0.0, lx_, out);
     }
 
     static VmSeqSpec spec(const vmg::SeqRef &s)
@@ -469,7 +573,16 @@ public:
             BE_OK(d_seg_.ensure((size_t)nu * 4 + 64));
             std::vector<int> ids((size_t)nu);
             for (int t = 0; t < nu; ++t) ids[t] = t;
-            BE_OK(cudaMemcpyAsync(d_msegs_.p, segs.data(), segs.size() * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
+            BE_OK(h_segs_.ensure(segs.size() * sizeof(vmg::MatchSeg) + 64));
+            {
+                const int64_t blk = 1 << 16, nb = ((int64_t)segs.size() + blk - 1) / blk;
+                vmg::MatchSeg *dst = h_segs_.as<vmg::MatchSeg>();
+                parallel_for(nb, host_threads, [&](int64_t b) {
+                    const int64_t lo = b * blk, hi = std::min<int64_t>((int64_t)segs.size(), lo + blk);
+                    memcpy(dst + lo, segs.data() + lo, (size_t)(hi - lo) * sizeof(vmg::MatchSeg));
+                }, 1);
+            }
+            BE_OK(cudaMemcpyAsync(d_msegs_.p, h_segs_.p, segs.size() * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
             KTimer kt(this, "k_ed_upper");
@@ -573,56 +686,67 @@ public:
         const int nj = (int)jobs.size();
         if (nj == 0) return nullptr;
         VmAlnJobDev *J = stage_jobs((size_t)nj);
-        parallel_for(nj, host_threads, [&](int64_t j) {
-            memset(&J[j], 0, sizeof(VmAlnJobDev));
-            J[j].t = spec(jobs[j].job.target);
-            J[j].q = spec(jobs[j].job.query);
-            J[j].read = jobs[j].read;
-        }, 1024);
         int64_t out_off = 0;
-        for (int j = 0; j < nj; ++j) {
-            J[j].out_off = out_off;
-            out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
-            fill_cells_ += (double)J[j].t.len * (double)J[j].q.len;
-            fill_bases_ += (double)J[j].t.len + (double)J[j].q.len;
+        {
+            WallTimer w1(this, "h_fill_stage");
+            parallel_for(nj, host_threads, [&](int64_t j) {
+                memset(&J[j], 0, sizeof(VmAlnJobDev));
+                J[j].t = spec(jobs[j].job.target);
+                J[j].q = spec(jobs[j].job.query);
+                J[j].read = jobs[j].read;
+            }, 1024);
+            double cells = 0, bases = 0;
+            for (int j = 0; j < nj; ++j) {
+                J[j].out_off = out_off;
+                out_off += (int64_t)J[j].t.len + J[j].q.len + 2;
+                cells += (double)J[j].t.len * (double)J[j].q.len;
+            }
+            bases = (double)(out_off - 2LL * nj);
+            fill_cells_ += cells;
+            fill_bases_ += bases;
+            fill_jobs_ += nj;
         }
-        fill_jobs_ += nj;
-        vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_);
+        {
+            WallTimer w2(this, "h_fill_plan");
+            vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads);
+        }
         BE_OK(d_dir_.ensure(plan_.dir_words * 4 + 64));
         BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
         BE_OK(d_cig_.ensure((size_t)out_off * 4 + 64));
+        BE_OK(d_cigd_.ensure((size_t)out_off * 4 + 64));
+        BE_OK(d_seg_.ensure((size_t)nj * 8 + 64));
         BE_OK(d_pairs_.ensure(plan_.pairs.size() * sizeof(VmFillPair) + plan_.launches.size() * 4 + 64));
-        int *d_ctr = (int *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
+        // [pairs | dense counter (8 bytes, 8-aligned) | one launch counter each]
+        unsigned long long *d_count = (unsigned long long *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
+        int *d_ctr = (int *)(d_count + 1);
         BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
         if (!plan_.pairs.empty())
             BE_OK(cudaMemcpyAsync(d_pairs_.p, plan_.pairs.data(), plan_.pairs.size() * sizeof(VmFillPair), cudaMemcpyHostToDevice,
                                   c_->stream));
-        BE_OK(cudaMemsetAsync(d_ctr, 0, plan_.launches.size() * 4 + 4, c_->stream));
+        BE_OK(cudaMemsetAsync(d_count, 0, 8 + plan_.launches.size() * 4 + 4, c_->stream));
+        BE_OK(cudaMemsetAsync(d_seg_.p, 0, (size_t)nj * 8, c_->stream));
         KTimer kt(this, "k_fill");
         c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
-                                       d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(), c_->stream);
+                                       d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(),
+                                       d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
         kt.stop();
-        BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
+        WallTimer w3(this, "h_fill_post");
+        // per job (offset, length) into the dense CIGAR arena the kernel filled, then one dense D2H
+        BE_OK(h_misc_.ensure((size_t)nj * 8 + 64));
+        unsigned long long *h_count = h_misc_.as<unsigned long long>();
+        uint32_t *h_res = (uint32_t *)(h_count + 1);
+        BE_OK(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
         BE_OK(cudaGetLastError());
-        // compact the CIGAR ops on the device, then one dense D2H
-        BE_OK(h_misc_.ensure((size_t)nj * 20 + 64));
-        int64_t *src_off = h_misc_.as<int64_t>(), *dst_off = src_off + nj;
-        int32_t *len = (int32_t *)(dst_off + nj);
-        int64_t dense = 0;
-        for (int j = 0; j < nj; ++j) { src_off[j] = J[j].out_off; dst_off[j] = dense; len[j] = J[j].n_out; dense += J[j].n_out; }
-        BE_OK(d_seg_.ensure((size_t)nj * 20 + 64));
-        BE_OK(d_cigd_.ensure((size_t)std::max<int64_t>(dense, 1) * 4));
-        BE_OK(h_cig_.ensure((size_t)std::max<int64_t>(dense, 1) * 4));
-        BE_OK(cudaMemcpyAsync(d_seg_.p, h_misc_.p, (size_t)nj * 20, cudaMemcpyHostToDevice, c_->stream));
-        const int64_t *dseg = d_seg_.as<int64_t>();
-        vm_gather_segments_kernel<uint32_t><<<nj, 32, 0, c_->stream>>>(d_cig_.as<uint32_t>(), dseg, dseg + nj,
-                                                                      (const int32_t *)(dseg + 2 * nj), d_cigd_.as<uint32_t>());
-        c_->launches += 1;
-        if (dense > 0) BE_OK(cudaMemcpyAsync(h_cig_.p, d_cigd_.p, (size_t)dense * 4, cudaMemcpyDeviceToHost, c_->stream));
+        const size_t dense = (size_t)*h_count;
+        BE_OK(h_cig_.ensure(std::max<size_t>(dense, 1) * 4));
+        if (dense > 0) BE_OK(cudaMemcpyAsync(h_cig_.p, d_cigd_.p, dense * 4, cudaMemcpyDeviceToHost, c_->stream));
+        parallel_for(nj, host_threads, [&](int64_t j) {
+            jobs[j].cig_off = h_res[2 * j];
+            jobs[j].cig_len = (int32_t)h_res[2 * j + 1];
+        }, 4096);
         BE_OK(cudaStreamSynchronize(c_->stream));
-        BE_OK(cudaGetLastError());
-        for (int j = 0; j < nj; ++j) { jobs[j].cig_off = dst_off[j]; jobs[j].cig_len = len[j]; }
         return h_cig_.as<uint32_t>();
     }
 
@@ -633,7 +757,9 @@ private:
     VmDevBuf reads_fwd_, reads_rc_, read_off_, jobs_, d_wlo_, d_whi_, d_gx_, d_gy_, d_nh_, d_hits_, d_tab_, d_order_, d_rout_,
         d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_, d_msegs_;
     VmFillPlan plan_;
-    VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_;
+    Extracted gx_, lx_;
+    VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
+    VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;
     std::vector<int64_t> off_host_;
 };
 

@@ -116,9 +116,20 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
         // Sub-batches in flight: each worker owns a CUDA stream, device arenas and a Driver, so the host glue of
         // one sub-batch overlaps the kernels of the others and small launches share the GPU.
         int workers = p->workers > 0 ? p->workers : 4;
-        int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 2 * workers - 1) / (2 * workers));
-        const int64_t n_chunks = n_reads > 0 ? (n_reads + chunk - 1) / chunk : 0;
-        if (n_chunks < 2) workers = 1;
+        int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + workers - 1) / workers);
+        if (n_reads <= chunk) workers = 1;
+        // equal chunks, a whole number of rounds per worker (every chunk pays the same fixed chain of launch and
+        // synchronisation latencies: fewer, larger chunks win, and a ragged last round would leave workers idle)
+        std::vector<int64_t> bounds(1, 0);
+        if (workers > 1) {
+            const int64_t rounds = std::max<int64_t>(1, (n_reads + chunk * workers - 1) / (chunk * workers));
+            const int64_t parts = rounds * workers;
+            for (int64_t i = 1; i <= parts; ++i) {
+                const int64_t e = n_reads * i / parts;
+                if (e > bounds.back()) bounds.push_back(e);
+            }
+        } else bounds.push_back(n_reads);
+        const int64_t n_chunks = (int64_t)bounds.size() - 1;
         workers = (int)std::min<int64_t>(workers, std::max<int64_t>(n_chunks, 1));
         BatchResult br;
         auto t0 = std::chrono::steady_clock::now();
@@ -156,11 +167,15 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
                         cudaSetDevice(c->device);
                         CudaBackend &wb = *wbe[w];
                         Driver drv(wb, h->ctg, opt, h->ix->k, wthreads);
-                        drv.on_time = [&wb](const char *nm, double ms) { wb.timer.add(nm, ms); };
+                        drv.on_time = [&wb](const char *nm, double ms) {
+                            wb.timer.add(nm, ms);
+                            const auto t1 = std::chrono::steady_clock::now();
+                            Timeline::get().add(&wb, nm, t1 - std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double, std::milli>(ms)), t1);
+                        };
                         for (;;) {
                             const int64_t ci = next.fetch_add(1);
                             if (ci >= n_chunks) break;
-                            const int64_t r0 = ci * chunk, nr = std::min(n_reads, r0 + chunk) - r0;
+                            const int64_t r0 = bounds[(size_t)ci], nr = bounds[(size_t)ci + 1] - r0;
                             ReadBatch sb;
                             sb.n = nr;
                             sb.seq = seqs;
@@ -211,6 +226,7 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
             }
         }, 64);
         be.timer.add("n_workers", workers);
+        Timeline::get().flush();
         be.timer.add("total", total);
         be.timer.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         be.timer.add("n_fill_cells", be.fill_cells_);

@@ -1,0 +1,29 @@
+// Device-side chain extraction (see vm_extract.cu): what the host glue needs of a chaining stage, compacted.
+#pragma once
+#include "vm_common.cuh"
+
+// per read: where its extracted anchors / chain records sit in the dense output arrays
+struct VmExtractRec {
+    long long anc_off;
+    long long meta_off;
+    int32_t n_anc;
+    int32_t n_chains;     // global stage: chains kept (0 = read not accepted); local stage: 1 when a path exists
+};
+
+struct VmExtractOut {
+    VmExtractRec *rec;                    // [n_reads]
+    VmAnchor *anc;                        // dense; global: chains back to back, each in DESCENDING read order;
+                                          //        local: the trimmed best chain in ASCENDING read order
+    double *S;                            // global: S of every anchor of the primary chain (0 for the others)
+    int32_t *chain_len;                   // global: anchors per chain, discovery order (primary first)
+    double *chain_score;                  // global: score per chain
+    unsigned long long *n_anc_total;      // bump allocators, zeroed by the host
+    unsigned long long *n_chain_total;
+};
+
+int vm_launch_extract_global(const int *ids_dev, int n_ids, const int64_t *off, const int32_t *cnt, const VmAnchor *sorted,
+                             const double *S, const int32_t *P, const int32_t *S_arg, const int64_t *gmax, double accept,
+                             uint8_t *used_zeroed, VmAnchor *tmp_anc, double *tmp_S, int32_t *tmp_len, double *tmp_score,
+                             const VmExtractOut &out, cudaStream_t stream);
+int vm_launch_extract_local(const int *ids_dev, int n_ids, const int64_t *off, const int32_t *cnt, const VmAnchor *sorted,
+                            const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out, cudaStream_t stream);

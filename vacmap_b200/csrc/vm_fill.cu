@@ -19,7 +19,9 @@
 //  * Traceback: two walker lanes (one per job) run on 32-step x R-row tiles the whole warp stages into shared
 //    memory with one round trip, instead of one dependent global load per path cell.
 #include "vm_align.cuh"
+#include "vm_hostpool.hpp"
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_fp16.h>
 
 namespace {
@@ -89,7 +91,8 @@ template <int R, bool MB>
 __global__ void __launch_bounds__(128) vm_fill_kernel(VmAlnJobDev *jobs, const VmFillPair *__restrict__ pairs, int pair_begin,
                                                       int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
                                                       long long dir_words_per_warp, uint32_t *band_all,
-                                                      long long band_words_per_warp, int *counter, uint32_t *cigar_out)
+                                                      long long band_words_per_warp, int *counter, uint32_t *cigar_out,
+                                                      uint32_t *dense_out, unsigned long long *dense_count, uint2 *results)
 {
     static_assert(R % 2 == 0 && R >= 2 && R <= 16, "rows per lane");
     constexpr VmGapPar2 g = vm_fill_par();
@@ -264,20 +267,19 @@ __global__ void __launch_bounds__(128) vm_fill_kernel(VmAlnJobDev *jobs, const V
                 }
             }
             if (cur_len) out[n++] = cur_len << 4 | cur_op;
-            if (w == 0) JA.n_out = n;
-            else JB.n_out = n;
         }
         __syncwarp();
-        // ops were pushed end to start: flip them, all lanes helping
+        // ops were pushed end to start: claim room in the dense CIGAR arena and copy them over flipped, all lanes helping
 #pragma unroll
         for (int ws = 0; ws < 2; ++ws) {
+            if (ws == 1 && !hasB) break;
             const int nn = __shfl_sync(VM_FULL, walker ? n : 0, ws);
-            uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
-            for (int x = lane; x < nn / 2; x += 32) {
-                const uint32_t a = o[x], b = o[nn - 1 - x];
-                o[x] = b;
-                o[nn - 1 - x] = a;
-            }
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(dense_count, (unsigned long long)nn);
+            base = __shfl_sync(VM_FULL, base, 0);
+            const uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
+            for (int x = lane; x < nn; x += 32) dense_out[base + x] = o[nn - 1 - x];
+            if (lane == 0) results[ws ? pr.b : pr.a] = make_uint2((unsigned)base, (unsigned)nn);
         }
         __syncwarp();
     }
@@ -312,36 +314,57 @@ int vm_fill_blocks_per_sm(int R, bool mb)
 // rc = 9 beyond (R = 16, several bands); column class by qlen (<= 512, <= 4096, longer) so that one very long
 // query does not size the scratch of every resident warp.  Inside a class jobs are ordered by qlen and paired
 // with their neighbour: both halves of the half2 registers do useful work for (nearly) the whole sweep.
-void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan)
+void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, int host_threads)
 {
     plan.pairs.clear();
     plan.launches.clear();
     plan.dir_words = plan.band_words = 0;
-    constexpr int NCLS = 27, NB = 1024;
-    auto key_of = [&](int j, int &cls) {
+    constexpr int NCLS = 27, NB = 1024, NKEY = NCLS * NB;
+    auto key_of = [&](int j) {
         const int tl = J[j].t.len, ql = J[j].q.len;
+        if (tl <= 0 || ql <= 0) return -1;
         const int rc = tl <= 512 ? (tl + 63) / 64 : 9;
         const int qc = ql <= 512 ? 0 : ql <= 4096 ? 1 : 2;
-        cls = (rc - 1) * 3 + qc;
+        const int cls = (rc - 1) * 3 + qc;
         const int b = qc == 0 ? ql >> 1 : qc == 1 ? ql >> 3 : std::min(ql >> 8, NB - 1);
         return cls * NB + b;
     };
-    std::vector<int32_t> count((size_t)NCLS * NB + 1, 0);
-    std::vector<int32_t> keys((size_t)nj, -1);
-    for (int j = 0; j < nj; ++j) {
-        if (J[j].t.len <= 0 || J[j].q.len <= 0) continue;
-        int cls;
-        keys[j] = key_of(j, cls);
-        ++count[(size_t)keys[j] + 1];
-    }
-    for (size_t k = 1; k < count.size(); ++k) count[k] += count[k - 1];
-    const int n_live = count.back();
-    std::vector<int32_t> order((size_t)n_live);
+    // stable counting sort of the jobs by key: per-slice histograms, then one pass of offsets
+    const int T = std::max(1, std::min(host_threads, nj / 8192 + 1));
+    std::vector<int32_t> keys((size_t)nj);
+    std::vector<std::vector<int32_t>> hist((size_t)T, std::vector<int32_t>((size_t)NKEY, 0));
+    auto slice = [&](int t, int &lo, int &hi) { lo = (int)((long long)nj * t / T); hi = (int)((long long)nj * (t + 1) / T); };
+    vmp::parallel_for(T, T, [&](int64_t t) {
+        int lo, hi;
+        slice((int)t, lo, hi);
+        std::vector<int32_t> &h = hist[(size_t)t];
+        for (int j = lo; j < hi; ++j) {
+            keys[j] = key_of(j);
+            if (keys[j] >= 0) ++h[(size_t)keys[j]];
+        }
+    }, 1);
+    std::vector<int32_t> count((size_t)NKEY + 1, 0);
     {
-        std::vector<int32_t> pos(count.begin(), count.end() - 1);
-        for (int j = 0; j < nj; ++j)
-            if (keys[j] >= 0) order[(size_t)pos[keys[j]]++] = j;
+        int32_t run = 0;
+        for (int k = 0; k < NKEY; ++k) {
+            count[(size_t)k] = run;
+            for (int t = 0; t < T; ++t) {
+                const int32_t c = hist[(size_t)t][(size_t)k];
+                hist[(size_t)t][(size_t)k] = run;     // where slice t starts writing key k
+                run += c;
+            }
+        }
+        count[(size_t)NKEY] = run;
     }
+    const int n_live = count[(size_t)NKEY];
+    std::vector<int32_t> order((size_t)n_live);
+    vmp::parallel_for(T, T, [&](int64_t t) {
+        int lo, hi;
+        slice((int)t, lo, hi);
+        std::vector<int32_t> &pos = hist[(size_t)t];
+        for (int j = lo; j < hi; ++j)
+            if (keys[j] >= 0) order[(size_t)pos[(size_t)keys[j]]++] = j;
+    }, 1);
     const size_t mem_cap_words = (size_t)6 << 28;     // 6 GiB of direction scratch at most
     for (int cls = 0; cls < NCLS; ++cls) {
         const int lo = count[(size_t)cls * NB], hi = count[(size_t)(cls + 1) * NB];
@@ -368,7 +391,9 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan)
         L.dir_words_per_warp = nbands * ((long long)max_q + 32) * (L.R / 2) * 32;
         L.band_words_per_warp = L.multiband ? 3LL * max_q + 32 : 0;
         const int n_pairs = L.pair_end - L.pair_begin;
-        long long blocks = std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0));
+        static const double frac = getenv("VM_FILL_SM_FRAC") ? atof(getenv("VM_FILL_SM_FRAC")) : 1.0;   // experiment knob
+        long long blocks = std::min<long long>((n_pairs + 3) / 4,
+                                               (long long)(frac * sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0)));
         const long long fit = (long long)(mem_cap_words / (size_t)(4 * L.dir_words_per_warp));
         blocks = std::max<long long>(1, std::min(blocks, std::max<long long>(fit, 1)));
         L.blocks = (int)blocks;
@@ -379,7 +404,8 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan)
 }
 
 int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs, const VmFillPair *pairs, VmSeqSources src, int eqx, uint32_t *dir,
-                   uint32_t *band, int *counters, uint32_t *cigar_out, cudaStream_t stream)
+                   uint32_t *band, int *counters, uint32_t *cigar_out, uint32_t *dense_out, unsigned long long *dense_count,
+                   void *results, cudaStream_t stream)
 {
     int n = 0;
     for (size_t li = 0; li < plan.launches.size(); ++li) {
@@ -387,7 +413,8 @@ int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs, const VmFillPair *
         int *ctr = counters + li;
 #define VM_FILL_GO(RR, MBB)                                                                                           \
     vm_fill_kernel<RR, MBB><<<L.blocks, 128, 0, stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir,       \
-                                                           L.dir_words_per_warp, band, L.band_words_per_warp, ctr, cigar_out)
+                                                           L.dir_words_per_warp, band, L.band_words_per_warp, ctr, cigar_out,      \
+                                                           dense_out, dense_count, (uint2 *)results)
         if (L.multiband) VM_FILL_GO(16, true);
         else switch (L.R) {
             case 2: VM_FILL_GO(2, false); break;

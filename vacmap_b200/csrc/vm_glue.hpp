@@ -47,6 +47,16 @@ static void argsort_replay(const K *A, int64_t n, std::vector<int64_t> &R)
     R.resize((size_t)n);
     for (int64_t t = 0; t < n; ++t) R[t] = t;
     if (n < 2) return;
+    {
+        // strictly monotone keys have a single sorted order, whatever the algorithm: no replay needed
+        bool asc = true, desc = true;
+        for (int64_t t = 1; t < n && (asc || desc); ++t) {
+            if (!(A[t - 1] < A[t])) asc = false;
+            if (!(A[t] < A[t - 1])) desc = false;
+        }
+        if (asc) return;
+        if (desc) { std::reverse(R.begin(), R.end()); return; }
+    }
     int64_t slo[100], shi[100];
     int sp = 1;
     slo[0] = 0; shi[0] = n - 1;
@@ -154,6 +164,9 @@ struct GlobalResult {
     std::vector<Path> guides;  // [0] primary chain, then secondary chains; each DESCENDING read order
 };
 
+static void hit2work_chains(std::vector<Path> &path_list, std::vector<double> &scores_list, const std::vector<double> &S_arr,
+                            int64_t L, GlobalResult &out, int bin_size, double overlap);
+
 static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const int32_t *S_arg, int64_t n, int64_t g,
                      int64_t L, double accept, GlobalResult &out, int bin_size = 100, double overlap = 0.5)
 {
@@ -203,6 +216,33 @@ static void hit2work(const Anc32 *a, const double *S, const int32_t *P, const in
             path_list.push_back(path);
         }
     }
+    hit2work_chains(path_list, scores_list, S_arr, L, out, bin_size, overlap);
+}
+
+// The same bookkeeping from chains that were already extracted (on the device, vm_extract.cu): chain c is
+// anc[sum(len[0..c)) .. + len[c]) in descending read order, chain 0 the primary one with its S values in S_prim.
+static void hit2work_extracted(const Anc32 *anc, const double *S_prim, const int32_t *len, const double *score, int n_chains,
+                               int64_t L, GlobalResult &out, int bin_size = 100, double overlap = 0.5)
+{
+    out = GlobalResult();
+    if (n_chains <= 0) return;
+    std::vector<Path> path_list((size_t)n_chains);
+    std::vector<double> scores_list(score, score + n_chains);
+    int64_t o = 0;
+    for (int c = 0; c < n_chains; ++c) {
+        Path &p = path_list[(size_t)c];
+        p.resize((size_t)len[c]);
+        for (int32_t t = 0; t < len[c]; ++t) p[(size_t)t] = widen(anc[o + t]);
+        o += len[c];
+    }
+    std::vector<double> S_arr(S_prim, S_prim + len[0]);
+    hit2work_chains(path_list, scores_list, S_arr, L, out, bin_size, overlap);
+}
+
+static void hit2work_chains(std::vector<Path> &path_list, std::vector<double> &scores_list, const std::vector<double> &S_arr,
+                            int64_t L, GlobalResult &out, int bin_size, double overlap)
+{
+    (void)L;
     std::vector<int64_t> order;
     argsort_replay<double>(scores_list.data(), (int64_t)scores_list.size(), order);
     std::reverse(order.begin(), order.end());

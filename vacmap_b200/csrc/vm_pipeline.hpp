@@ -7,6 +7,7 @@
 // (tests/gluetest); the product only ever instantiates the CUDA backend (vm_backend_cuda.cu).
 #pragma once
 #include "vm_glue.hpp"
+#include "vm_hostpool.hpp"
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -33,6 +34,12 @@ struct ReadBatch {
 // Result of a chaining stage for a batch.  Read r owns slots [start[r], start[r] + cnt[r]) of the
 // flat arrays, which live in backend-owned (pinned) memory until the next call of the same stage;
 // the *_store vectors are optional owning storage for test backends.
+// where a read's device-extracted chains sit in ChainOut::x_* (layout of VmExtractRec, vm_extract.cuh)
+struct ExtractRec {
+    long long anc_off, meta_off;
+    int32_t n_anc, n_chains;
+};
+
 struct ChainOut {
     std::vector<int64_t> start;
     std::vector<int32_t> cnt;
@@ -41,6 +48,14 @@ struct ChainOut {
     const double *S = nullptr;      // global stage only
     const int32_t *P = nullptr;
     const int32_t *S_arg = nullptr; // global stage only
+    // Compact form, when the backend extracts the chains itself (sorted / S / P / S_arg are then not filled):
+    // global stage -- the chains hit2work_1 keeps (score > 40), primary first, each in descending read order,
+    // with the primary chain's S values; local stage -- the trimmed best chain in ascending read order.
+    const ExtractRec *rec = nullptr;
+    const Anc32 *x_anc = nullptr;
+    const double *x_S = nullptr;
+    const int32_t *x_len = nullptr;
+    const double *x_score = nullptr;
     std::vector<Anc32> sorted_store;
     std::vector<double> S_store;
     std::vector<int32_t> P_store, A_store;
@@ -65,7 +80,8 @@ struct Backend {
     virtual ~Backend() {}
     // minimizer seeding + cluster filter + majority-strand flip (index.map + :21202-21217), then
     // argsort by read position + global DP (exact / fast as hit2work_1 chooses, :23570-23579)
-    virtual void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap,
+    // `accept`: primary-chain score threshold of hit2work_1 (:23650), for backends that extract the chains
+    virtual void seed_chain(const ReadBatch &b, int check_num, int kmersize, double skipcost, int maxdiff, int maxgap, double accept,
                             std::vector<char> &need_reverse, ChainOut &out) = 0;
     // local 9-mer re-seeding (anchors of all guide jobs of a read concatenated in job order), then
     // argsort by read end + local DP variant[r] in {1, 2} (+ fast fall-back); variant 0 = skip the read
@@ -78,140 +94,6 @@ struct Backend {
     // sets cig_off / cig_len of every job; the returned array stays valid until the next fill()
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
 };
-
-// Process-wide pool of host threads shared by every Driver / backend (the pipelined workers all draw from
-// it, so the host is never oversubscribed).  parallel_for hands out blocks of indices; the caller works too.
-class HostPool {
-public:
-    static HostPool &get()
-    {
-        static HostPool pool((int)std::max(1u, std::thread::hardware_concurrency()));
-        return pool;
-    }
-    int size() const { return (int)threads_.size() + 1; }
-
-    void run(int64_t n, int max_threads, int64_t grain, const std::function<void(int64_t)> &fn)
-    {
-        if (n <= 0) return;
-        if (max_threads <= 1 || n <= grain || threads_.empty()) {
-            for (int64_t i = 0; i < n; ++i) fn(i);
-            return;
-        }
-        auto job = std::make_shared<Job>();
-        job->n = n;
-        job->grain = grain;
-        job->fn = &fn;
-        job->helpers_wanted = (int)std::min<int64_t>(std::min<int64_t>(max_threads - 1, (int64_t)threads_.size()), (n + grain - 1) / grain - 1);
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            queue_.push_back(job);
-        }
-        cv_.notify_all();
-        work(*job);
-        std::unique_lock<std::mutex> lk(job->mu);
-        job->cv.wait(lk, [&] { return job->active == 0 && job->next.load() >= job->n; });
-        if (job->failed) std::rethrow_exception(job->error);
-    }
-
-private:
-    struct Job {
-        int64_t n = 0, grain = 1;
-        const std::function<void(int64_t)> *fn = nullptr;
-        std::atomic<int64_t> next{0};
-        int helpers_wanted = 0, helpers = 0;   // guarded by HostPool::mu_
-        int active = 0;                        // guarded by mu
-        bool failed = false;
-        std::exception_ptr error;
-        std::mutex mu;
-        std::condition_variable cv;
-    };
-
-    explicit HostPool(int n)
-    {
-        for (int t = 1; t < n; ++t) threads_.emplace_back([this] { loop(); });
-    }
-    ~HostPool()
-    {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (std::thread &t : threads_) t.join();
-    }
-
-    void work(Job &job)
-    {
-        {
-            std::lock_guard<std::mutex> lk(job.mu);
-            ++job.active;
-        }
-        try {
-            for (;;) {
-                const int64_t i0 = job.next.fetch_add(job.grain);
-                if (i0 >= job.n) break;
-                const int64_t i1 = std::min(job.n, i0 + job.grain);
-                for (int64_t i = i0; i < i1; ++i) (*job.fn)(i);
-            }
-        } catch (...) {
-            std::lock_guard<std::mutex> lk(job.mu);
-            if (!job.failed) { job.failed = true; job.error = std::current_exception(); }
-            job.next.store(job.n);
-        }
-        {
-            std::lock_guard<std::mutex> lk(job.mu);
-            --job.active;
-        }
-        job.cv.notify_all();
-    }
-
-    void loop()
-    {
-        for (;;) {
-            std::shared_ptr<Job> job;
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                for (;;) {
-                    while (!queue_.empty() && (queue_.front()->next.load() >= queue_.front()->n ||
-                                               queue_.front()->helpers >= queue_.front()->helpers_wanted))
-                        queue_.pop_front();
-                    if (stop_ || !queue_.empty()) break;
-                    cv_.wait(lk);
-                }
-                if (stop_) return;
-                job = queue_.front();
-                ++job->helpers;
-                // spread the pool over the jobs in flight: the next idle thread looks at the next job first
-                if (queue_.size() > 1) { queue_.pop_front(); queue_.push_back(job); }
-            }
-            work(*job);
-        }
-    }
-
-    std::vector<std::thread> threads_;
-    std::deque<std::shared_ptr<Job>> queue_;
-    std::mutex mu_;
-    std::condition_variable cv_;
-    bool stop_ = false;
-};
-
-static inline void parallel_for(int64_t n, int threads, const std::function<void(int64_t)> &fn, int64_t grain = 16)
-{
-    HostPool::get().run(n, threads, grain, fn);
-}
-
-// out = concatenation of parts[0..m) (moved), start[t] = offset of parts[t] in out; parallel over the parts
-template <typename T>
-static inline void parallel_concat(std::vector<std::vector<T>> &parts, int threads, std::vector<T> &out, std::vector<int64_t> &start)
-{
-    const int64_t m = (int64_t)parts.size();
-    start.assign((size_t)m + 1, 0);
-    for (int64_t t = 0; t < m; ++t) start[t + 1] = start[t] + (int64_t)parts[t].size();
-    out.resize((size_t)start[m]);
-    parallel_for(m, threads, [&](int64_t t) {
-        std::move(parts[t].begin(), parts[t].end(), out.begin() + start[t]);
-    }, 64);
-}
 
 struct ReadState {
     bool alive = false;
@@ -269,7 +151,7 @@ public:
         // ---- 1-2. seeding + global chaining (fused on the device) ----
         std::vector<char> need_rev;
         ChainOut g;
-        be_.seed_chain(b, opt_.check_num, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, need_rev, g);
+        be_.seed_chain(b, opt_.check_num, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, opt_.mode.accept, need_rev, g);
 
         // ---- 3. hit2work bookkeeping + guide selection ----
         std::vector<std::vector<GuideJobRef>> gjobs((size_t)n);
@@ -279,7 +161,11 @@ public:
             if (m <= 2) return;                       // decode_hit :23986 -- <= 2 anchors: unmapped
             const int64_t o = g.start[r];
             vmg::GlobalResult gr;
-            vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
+            if (g.rec) {
+                const ExtractRec &x = g.rec[r];
+                vmg::hit2work_extracted(g.x_anc + x.anc_off, g.x_S + x.anc_off, g.x_len + x.meta_off, g.x_score + x.meta_off,
+                                        x.n_chains, read_len[r], gr);
+            } else vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
             if (!gr.ok) return;
             ReadState &s = st[r];
             s.alive = true;
@@ -320,7 +206,11 @@ public:
             if (!s.alive) return;
             if (lc.cnt[r] == 0) { s.alive = false; return; }   // np.array([]) indexing raises in the reference
             const int64_t o = lc.start[r];
-            vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
+            if (lc.rec) {
+                const ExtractRec &x = lc.rec[r];
+                s.asc.resize((size_t)x.n_anc);
+                for (int32_t t = 0; t < x.n_anc; ++t) s.asc[(size_t)t] = vmg::widen(lc.x_anc[x.anc_off + t]);
+            } else vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
             if (s.asc.size() <= 1) s.alive = false;
             s.nofilter = opt_.nodiscard;
         });
