@@ -150,7 +150,7 @@ typedef struct vm_align_params {
     int32_t local_maxgap;     /* 99 (H, S) / 50 (L)  (clrnano:24061) */
     int32_t clamp40;          /* 1 in mode L: min(skipcost, 40) in the multi-chain local DP */
     int32_t host_threads;     /* host glue threads, 0 = all cores */
-    int32_t workers;          /* sub-batches in flight (own CUDA stream each), 0 = default (4), 1 = lock-step */
+    int32_t workers;          /* sub-batches in flight (own CUDA stream each), 0 = default (6), 1 = lock-step */
     int32_t chunk_reads;      /* reads per sub-batch, 0 = automatic */
 } vm_align_params;
 
@@ -173,6 +173,17 @@ typedef struct vm_result vm_result;
  * reference would drop through an exception (clrnano:24116-24125), simply have no records. */
 int vm_align_batch(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads,
                    const char *seqs, const int64_t *seq_off, vm_result **out);
+/* Asynchronous form: vm_align_submit queues the batch (cut into sub-batches for the context's worker pool, each
+ * worker with its own CUDA stream) and returns at once; vm_align_wait blocks until it is done and hands back the
+ * result (or the error).  A batch submitted while the previous one is still draining keeps the device busy across
+ * batch boundaries.  seqs / seq_off must stay valid until vm_align_wait returns; resident != 0: the reads were put
+ * in HBM by vm_reads_upload and must not be replaced while jobs that use them are in flight.
+ * vm_align_batch == submit + wait.  The reference has no counterpart: its workers take one read at a time
+ * (clrnano:24110-24117); this is the batch seam of the B200 design. */
+typedef struct vm_job vm_job;
+int vm_align_submit(vm_ctx *ctx, vm_index_handle *index, const vm_align_params *prm, int64_t n_reads, const char *seqs,
+                    const int64_t *seq_off, int32_t resident, vm_job **out);
+int vm_align_wait(vm_job *job, vm_result **out);
 /* Two-step form for measuring with the reads already resident in HBM: vm_reads_upload copies the
  * batch (forward + reverse-complement strands) to the device, vm_align_resident then runs the
  * same pipeline on it (same arguments; seqs/seq_off are still needed by the host glue). */

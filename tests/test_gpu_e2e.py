@@ -62,6 +62,15 @@ def test_cuda_matches_oracle_on_fresh_reads(gpu_ctx, seed, mode, kw):
     a = al.align_packed(b"".join(enc), off, resident=True)
     b = vb.Aligner(ix, opt, mode, workers=1).align_packed(b"".join(enc), off)
     assert all((x == y).all() for x, y in zip(a, b))
+    # two batches in flight at once (submit / wait): same records as one after the other
+    al2 = vb.Aligner(ix, opt, mode, workers=2, chunk_reads=7)
+    h1 = al2.submit_packed(b"".join(enc), off)
+    h2 = al2.submit_packed(b"".join(enc[::-1]), np.concatenate([[0], np.cumsum([len(e) for e in enc[::-1]])]).astype(np.int64))
+    r1, r2 = al2.wait(h1), al2.wait(h2)
+    assert all((x == y).all() for x, y in zip(r1, b))
+    want2 = vb.Aligner(ix, opt, mode, workers=1).align_batch([(rid, s) for rid, s in reads[::-1]])
+    n_rec = [len(w) for w in want2]
+    assert list(np.diff(r2[0])) == n_rec
     ix.close()
 
 

@@ -97,6 +97,8 @@ def _declare(L):
     L.vm_index_contig.argtypes = [vp, i32, vp, vp, vp, vp]
     L.vm_align_batch.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
     L.vm_align_resident.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
+    L.vm_align_submit.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, i32, ctypes.POINTER(vp)]
+    L.vm_align_wait.argtypes = [vp, ctypes.POINTER(vp)]
     L.vm_reads_upload.argtypes = [vp, vp, i64, vp, vp]
     for f in ("vm_result_num_records", "vm_result_num_cigar_ops"):
         getattr(L, f).argtypes = [vp]
@@ -180,17 +182,26 @@ class Aligner:
         ctx = self.index.ctx
         _lib.check(ctx.h, L.vm_reads_upload(ctx.h, self.index.h, len(seq_off) - 1, seq_cat, _lib.ptr(seq_off)))
 
-    def align_packed(self, seq_cat, seq_off, resident=False):
-        """seq_cat: bytes of all (upper-case) reads; seq_off int64[n+1].
-        -> (rec_off int64[n+1], records structured array, cigar uint32 array)."""
+    def submit_packed(self, seq_cat, seq_off, resident=False):
+        """Queue a packed batch (vm_align_submit) and return a handle for `wait`; batches submitted back to back keep
+        the device busy across batch boundaries.  seq_cat / seq_off are kept alive by the handle."""
         L = _lib.load()
         seq_off = np.ascontiguousarray(seq_off, dtype=np.int64)
         n = len(seq_off) - 1
-        res = ctypes.c_void_p()
+        job = ctypes.c_void_p()
         ctx = self.index.ctx
         buf = (ctypes.c_char * len(seq_cat)).from_buffer_copy(seq_cat) if not isinstance(seq_cat, bytes) else seq_cat
-        fn = L.vm_align_resident if resident else L.vm_align_batch
-        _lib.check(ctx.h, fn(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off), ctypes.byref(res)))
+        _lib.check(ctx.h, L.vm_align_submit(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off),
+                                            1 if resident else 0, ctypes.byref(job)))
+        return (job, n, buf, seq_off)
+
+    def wait(self, handle):
+        """-> (rec_off int64[n+1], records structured array, cigar uint32 array) of a submitted batch."""
+        L = _lib.load()
+        job, n, _buf, _off = handle
+        res = ctypes.c_void_p()
+        ctx = self.index.ctx
+        _lib.check(ctx.h, L.vm_align_wait(job, ctypes.byref(res)))
         try:
             nrec, nops = L.vm_result_num_records(res), L.vm_result_num_cigar_ops(res)
             off = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_offsets(res), ctypes.POINTER(ctypes.c_int64)),
@@ -211,6 +222,11 @@ class Aligner:
         finally:
             L.vm_result_free(res)
         return off, recs, cig
+
+    def align_packed(self, seq_cat, seq_off, resident=False):
+        """seq_cat: bytes of all (upper-case) reads; seq_off int64[n+1].
+        -> (rec_off int64[n+1], records structured array, cigar uint32 array)."""
+        return self.wait(self.submit_packed(seq_cat, seq_off, resident=resident))
 
     def align_batch(self, reads):
         """reads: list of (readid, sequence).  -> list (per read) of lists of Record."""

@@ -8,7 +8,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 3; }
+int vm_abi_version(void) { return 4; }
 
 int vm_ctx_create(int device, vm_ctx **out)
 {
@@ -40,6 +40,8 @@ void vm_ctx_destroy(vm_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->pool && c->pool_free) c->pool_free(c->pool);
+    c->pool = nullptr;
     for (vm_ctx *k : c->kids) vm_ctx_destroy(k);
     c->kids.clear();
     if (c->backend && c->backend_free) c->backend_free(c->backend);

@@ -83,14 +83,161 @@ int vm_index_contig(vm_index_handle *h, int32_t i, const char **name, int64_t *s
     return VM_OK;
 }
 
-static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
-                         const int64_t *seq_off, int resident, vm_result **out)
+} // extern "C"
+
+// ---------------------------------------------------------------------------
+// Batches as jobs: a batch is cut into equal sub-batches ("chunks"), every chunk is one task for the context's
+// pool of worker threads.  A worker owns a CUDA stream, device arenas and a backend, so the host glue of one chunk
+// overlaps the kernels of the others, and the chunks of a batch submitted while another one is still draining
+// start at once (vm_align_submit / vm_align_wait): the pipeline does not run empty between batches.
+// ---------------------------------------------------------------------------
+struct vm_job {
+    vm_ctx *c = nullptr;
+    vm_index_handle *h = nullptr;
+    vmg::Options opt;
+    int threads = 1, resident = 0, workers = 1;
+    int64_t n_reads = 0;
+    const char *seqs = nullptr;
+    const int64_t *seq_off = nullptr;
+    std::vector<int64_t> bounds;
+    BatchResult br;
+    std::mutex mu;
+    std::condition_variable cv;
+    int64_t chunks_left = 0;
+    std::string err;
+    StageTimer timer;
+    double fill_cells = 0, fill_bases = 0, fill_jobs = 0, ed_cells = 0, ed_upper = 0, reseed_hits = 0, chain_anchors = 0;
+    int64_t launches = 0;
+    std::chrono::steady_clock::time_point t0, t_done;
+};
+
+namespace {
+
+void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::string &err)
+{
+    std::lock_guard<std::mutex> lk(job->mu);
+    for (auto &kv : wb.timer.ms) job->timer.add(kv.first.c_str(), kv.second);
+    job->fill_cells += wb.fill_cells_; job->fill_bases += wb.fill_bases_; job->fill_jobs += wb.fill_jobs_;
+    job->ed_cells += wb.ed_cells_; job->ed_upper += wb.ed_upper_jobs_; job->reseed_hits += wb.reseed_hits_;
+    job->chain_anchors += wb.chain_anchors_;
+    job->launches += launches;
+    if (!err.empty() && job->err.empty()) job->err = err;
+    if (--job->chunks_left == 0) {
+        job->t_done = std::chrono::steady_clock::now();
+        job->cv.notify_all();
+    }
+}
+
+// one chunk of a job on backend `wb` (context `wc`); parent = backend holding the resident reads
+void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend *parent)
+{
+    std::string err;
+    const int64_t l0 = wc->launches;
+    try {
+        cudaSetDevice(job->c->device);
+        wb.set_index(job->h);
+        wb.reset_counters();
+        wb.host_threads = job->threads;
+        Driver drv(wb, job->h->ctg, job->opt, job->h->ix->k, job->threads);
+        drv.on_time = [&wb](const char *nm, double ms) {
+            wb.timer.add(nm, ms);
+            const auto t1 = std::chrono::steady_clock::now();
+            Timeline::get().add(&wb, nm, t1 - std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                                  std::chrono::duration<double, std::milli>(ms)), t1);
+        };
+        const int64_t r0 = job->bounds[(size_t)ci], nr = job->bounds[(size_t)ci + 1] - r0;
+        ReadBatch sb;
+        sb.n = nr;
+        sb.seq = job->seqs;
+        sb.off = job->seq_off + r0;
+        if (parent != &wb) {
+            if (job->resident) wb.copy_reads_from(*parent, r0, nr);
+            else wb.reads_resident = false;
+        }
+        BatchResult sr;
+        drv.align_batch(sb, sr);
+        for (int64_t i = 0; i < nr; ++i) job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+    } catch (const std::exception &e) {
+        err = e.what();
+        if (err.empty()) err = "error";
+    }
+    job_absorb(job, wb, wc->launches - l0, err);
+}
+
+struct AlignPool {
+    vm_ctx *c;
+    std::vector<std::thread> threads;
+    std::deque<std::pair<vm_job *, int64_t>> queue;
+    std::mutex mu;
+    std::condition_variable cv;
+    bool stop = false;
+
+    explicit AlignPool(vm_ctx *c_) : c(c_) {}
+    ~AlignPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (std::thread &t : threads) t.join();
+    }
+    // called from the submitting thread: worker contexts and backends are created here, not in the workers
+    bool ensure(int workers, vm_index_handle *h)
+    {
+        while ((int)threads.size() < workers) {
+            const int w = (int)threads.size();
+            vm_ctx *wc = vm_ctx_worker(c, w);
+            if (!wc) return false;
+            if (!wc->backend) {
+                wc->backend = new CudaBackend(wc, h);
+                wc->backend_free = [](void *q) { delete (CudaBackend *)q; };
+            }
+            threads.emplace_back([this, w] { loop(w); });
+        }
+        for (int w = 0; w < (int)threads.size(); ++w) vm_ctx_worker(c, w);   // refresh the table aliases
+        return true;
+    }
+    void push(vm_job *job)
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (int64_t ci = 0; ci + 1 < (int64_t)job->bounds.size(); ++ci) queue.emplace_back(job, ci);
+        }
+        cv.notify_all();
+    }
+    void loop(int w)
+    {
+        for (;;) {
+            std::pair<vm_job *, int64_t> task;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || !queue.empty(); });
+                if (stop) return;
+                task = queue.front();
+                queue.pop_front();
+            }
+            vm_ctx *wc = c->kids[(size_t)w];
+            run_chunk(task.first, task.second, wc, *(CudaBackend *)wc->backend, (CudaBackend *)c->backend);
+        }
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                    const int64_t *seq_off, int32_t resident, vm_job **out)
 {
     if (!c) return VM_ERR_ARG;
     if (!h || !p || !out || n_reads < 0 || !seq_off || (n_reads > 0 && !seqs)) { c->err = "bad argument"; return VM_ERR_ARG; }
     if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
     cudaSetDevice(c->device);
-    vmg::Options opt;
+    vm_job *job = new vm_job();
+    job->c = c;
+    job->h = h;
+    vmg::Options &opt = job->opt;
     opt.global_skipcost = p->global_skipcost;
     opt.local_skipcost = p->local_skipcost;
     opt.maxdivergence = p->maxdivergence;
@@ -101,153 +248,133 @@ static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p
     opt.hardclip = p->hardclip != 0;
     opt.nodiscard = p->nodiscard != 0;
     opt.mode = vmg::ModeConst{p->accept_score, p->max_guides, p->local_maxgap, p->clamp40 != 0};
-    vm_result *res = new vm_result();
+    job->threads = p->host_threads > 0 ? p->host_threads : HostPool::get().size();
+    job->resident = resident != 0;
+    job->n_reads = n_reads;
+    job->seqs = seqs;
+    job->seq_off = seq_off;
     try {
         if (!c->backend) {
             c->backend = new CudaBackend(c, h);
-            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+            c->backend_free = [](void *q) { delete (CudaBackend *)q; };
         }
         CudaBackend &be = *(CudaBackend *)c->backend;
         be.set_index(h);
-        be.reset_counters();
         be.reads_resident = resident != 0;
-        be.host_threads = p->host_threads > 0 ? p->host_threads : HostPool::get().size();
-        const int threads = p->host_threads > 0 ? p->host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
-        // Sub-batches in flight: each worker owns a CUDA stream, device arenas and a Driver, so the host glue of
-        // one sub-batch overlaps the kernels of the others and small launches share the GPU.
-        int workers = p->workers > 0 ? p->workers : 4;
-        int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + workers - 1) / workers);
+        int workers = p->workers > 0 ? p->workers : 6;
+        const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + workers - 1) / workers);
         if (n_reads <= chunk) workers = 1;
         // equal chunks, a whole number of rounds per worker (every chunk pays the same fixed chain of launch and
         // synchronisation latencies: fewer, larger chunks win, and a ragged last round would leave workers idle)
-        std::vector<int64_t> bounds(1, 0);
+        job->bounds.assign(1, 0);
         if (workers > 1) {
             const int64_t rounds = std::max<int64_t>(1, (n_reads + chunk * workers - 1) / (chunk * workers));
             const int64_t parts = rounds * workers;
             for (int64_t i = 1; i <= parts; ++i) {
                 const int64_t e = n_reads * i / parts;
-                if (e > bounds.back()) bounds.push_back(e);
+                if (e > job->bounds.back()) job->bounds.push_back(e);
             }
-        } else bounds.push_back(n_reads);
-        const int64_t n_chunks = (int64_t)bounds.size() - 1;
-        workers = (int)std::min<int64_t>(workers, std::max<int64_t>(n_chunks, 1));
-        BatchResult br;
-        auto t0 = std::chrono::steady_clock::now();
+        } else job->bounds.push_back(n_reads);
+        job->workers = workers;
+        job->chunks_left = (int64_t)job->bounds.size() - 1;
+        job->br.records.assign((size_t)n_reads, {});
+        job->t0 = std::chrono::steady_clock::now();
         if (workers <= 1) {
-            Driver drv(be, h->ctg, opt, h->ix->k, threads);
-            drv.on_time = [&](const char *nm, double ms) { be.timer.add(nm, ms); };
-            ReadBatch b;
-            b.n = n_reads;
-            b.seq = seqs;
-            b.off = seq_off;
-            drv.align_batch(b, br);
+            // lock-step: the whole batch on the context's own backend, in the calling thread
+            run_chunk(job, 0, c, be, &be);
         } else {
-            br.records.assign((size_t)n_reads, {});
-            std::vector<CudaBackend *> wbe((size_t)workers, nullptr);
-            for (int w = 0; w < workers; ++w) {
-                vm_ctx *wc = vm_ctx_worker(c, w);
-                if (!wc) throw std::runtime_error("cannot create a worker context");
-                if (!wc->backend) {
-                    wc->backend = new CudaBackend(wc, h);
-                    wc->backend_free = [](void *q) { delete (CudaBackend *)q; };
-                }
-                wbe[w] = (CudaBackend *)wc->backend;
-                wbe[w]->set_index(h);
-                wbe[w]->reset_counters();
-                wbe[w]->host_threads = be.host_threads;
-                wc->launches = 0;
+            if (!c->pool) {
+                c->pool = new AlignPool(c);
+                c->pool_free = [](void *q) { delete (AlignPool *)q; };
             }
-            std::atomic<int64_t> next(0);
-            std::vector<std::string> errs((size_t)workers);
-            std::vector<std::thread> pool;
-            const int wthreads = threads;   // the shared HostPool arbitrates between the workers
-            for (int w = 0; w < workers; ++w)
-                pool.emplace_back([&, w]() {
-                    try {
-                        cudaSetDevice(c->device);
-                        CudaBackend &wb = *wbe[w];
-                        Driver drv(wb, h->ctg, opt, h->ix->k, wthreads);
-                        drv.on_time = [&wb](const char *nm, double ms) {
-                            wb.timer.add(nm, ms);
-                            const auto t1 = std::chrono::steady_clock::now();
-                            Timeline::get().add(&wb, nm, t1 - std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double, std::milli>(ms)), t1);
-                        };
-                        for (;;) {
-                            const int64_t ci = next.fetch_add(1);
-                            if (ci >= n_chunks) break;
-                            const int64_t r0 = bounds[(size_t)ci], nr = bounds[(size_t)ci + 1] - r0;
-                            ReadBatch sb;
-                            sb.n = nr;
-                            sb.seq = seqs;
-                            sb.off = seq_off + r0;
-                            if (resident) wb.copy_reads_from(be, r0, nr);
-                            else wb.reads_resident = false;
-                            BatchResult sr;
-                            drv.align_batch(sb, sr);
-                            for (int64_t i = 0; i < nr; ++i) br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
-                        }
-                    } catch (const std::exception &e) { errs[w] = e.what(); if (errs[w].empty()) errs[w] = "error"; }
-                });
-            for (std::thread &t : pool) t.join();
-            for (const std::string &e : errs)
-                if (!e.empty()) throw std::runtime_error(e);
-            for (int w = 0; w < workers; ++w) {
-                for (auto &kv : wbe[w]->timer.ms) be.timer.add(kv.first.c_str(), kv.second);
-                be.fill_cells_ += wbe[w]->fill_cells_; be.fill_bases_ += wbe[w]->fill_bases_; be.fill_jobs_ += wbe[w]->fill_jobs_;
-                be.ed_cells_ += wbe[w]->ed_cells_; be.ed_upper_jobs_ += wbe[w]->ed_upper_jobs_; be.reseed_hits_ += wbe[w]->reseed_hits_; be.chain_anchors_ += wbe[w]->chain_anchors_;
-                c->launches += c->kids[w]->launches;
-            }
-        }
-        const double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        auto t1 = std::chrono::steady_clock::now();
-        // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel
-        res->rec_off.assign((size_t)n_reads + 1, 0);
-        std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
-        for (int64_t r = 0; r < n_reads; ++r) {
-            int64_t ops = 0;
-            for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
-            res->rec_off[r + 1] = res->rec_off[r] + (int64_t)br.records[r].size();
-            cig_off[r + 1] = cig_off[r] + ops;
-        }
-        res->recs.resize((size_t)res->rec_off[n_reads]);
-        res->cigar.resize((size_t)cig_off[n_reads]);
-        parallel_for(n_reads, threads, [&](int64_t r) {
-            int64_t ri = res->rec_off[r], co = cig_off[r];
-            for (const vmg::Record &rec : br.records[r]) {
-                vm_record &o = res->recs[(size_t)ri++];
-                o.contig = rec.contig;
-                o.strand = rec.strand;
-                o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
-                o.mapq = rec.mapq;
-                o.cigar_off = co;
-                o.cigar_len = (int32_t)rec.cigar.size();
-                std::copy(rec.cigar.begin(), rec.cigar.end(), res->cigar.begin() + co);
-                co += (int64_t)rec.cigar.size();
-            }
-        }, 64);
-        be.timer.add("n_workers", workers);
-        Timeline::get().flush();
-        be.timer.add("total", total);
-        be.timer.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
-        be.timer.add("n_fill_cells", be.fill_cells_);
-        be.timer.add("n_fill_bases", be.fill_bases_);
-        be.timer.add("n_fill_jobs", be.fill_jobs_);
-        be.timer.add("n_ed_cells", be.ed_cells_);
-        be.timer.add("n_ed_upper_jobs", be.ed_upper_jobs_);
-        be.timer.add("n_reseed_hits", be.reseed_hits_);
-        be.timer.add("n_chain_anchors", be.chain_anchors_);
-        for (auto &kv : be.timer.ms) {
-            res->stage_names.push_back(kv.first);
-            res->stage_ms.push_back(kv.second);
-            res->stage_text += kv.first + "=" + std::to_string(kv.second) + ";";
+            AlignPool &pool = *(AlignPool *)c->pool;
+            if (!pool.ensure(workers, h)) throw std::runtime_error("cannot create a worker context");
+            pool.push(job);
         }
     } catch (const std::exception &e) {
         c->err = e.what();
-        delete res;
+        delete job;
         return VM_ERR_CUDA;
     }
+    *out = job;
+    return VM_OK;
+}
+
+int vm_align_wait(vm_job *job, vm_result **out)
+{
+    if (!job || !out) return VM_ERR_ARG;
+    vm_ctx *c = job->c;
+    {
+        std::unique_lock<std::mutex> lk(job->mu);
+        job->cv.wait(lk, [&] { return job->chunks_left == 0; });
+    }
+    if (!job->err.empty()) {
+        c->err = job->err;
+        delete job;
+        return VM_ERR_CUDA;
+    }
+    cudaSetDevice(c->device);
+    const int64_t n_reads = job->n_reads;
+    BatchResult &br = job->br;
+    vm_result *res = new vm_result();
+    const double total = std::chrono::duration<double, std::milli>(job->t_done - job->t0).count();
+    auto t1 = std::chrono::steady_clock::now();
+    // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel
+    res->rec_off.assign((size_t)n_reads + 1, 0);
+    std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
+    for (int64_t r = 0; r < n_reads; ++r) {
+        int64_t ops = 0;
+        for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
+        res->rec_off[r + 1] = res->rec_off[r] + (int64_t)br.records[r].size();
+        cig_off[r + 1] = cig_off[r] + ops;
+    }
+    res->recs.resize((size_t)res->rec_off[n_reads]);
+    res->cigar.resize((size_t)cig_off[n_reads]);
+    parallel_for(n_reads, job->threads, [&](int64_t r) {
+        int64_t ri = res->rec_off[r], co = cig_off[r];
+        for (const vmg::Record &rec : br.records[r]) {
+            vm_record &o = res->recs[(size_t)ri++];
+            o.contig = rec.contig;
+            o.strand = rec.strand;
+            o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
+            o.mapq = rec.mapq;
+            o.cigar_off = co;
+            o.cigar_len = (int32_t)rec.cigar.size();
+            std::copy(rec.cigar.begin(), rec.cigar.end(), res->cigar.begin() + co);
+            co += (int64_t)rec.cigar.size();
+        }
+    }, 64);
+    Timeline::get().flush();
+    StageTimer &tm = job->timer;
+    tm.add("n_workers", job->workers);
+    tm.add("total", total);
+    tm.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+    tm.add("n_fill_cells", job->fill_cells);
+    tm.add("n_fill_bases", job->fill_bases);
+    tm.add("n_fill_jobs", job->fill_jobs);
+    tm.add("n_ed_cells", job->ed_cells);
+    tm.add("n_ed_upper_jobs", job->ed_upper);
+    tm.add("n_reseed_hits", job->reseed_hits);
+    tm.add("n_chain_anchors", job->chain_anchors);
+    for (auto &kv : tm.ms) {
+        res->stage_names.push_back(kv.first);
+        res->stage_ms.push_back(kv.second);
+        res->stage_text += kv.first + "=" + std::to_string(kv.second) + ";";
+    }
+    if (job->workers > 1) c->launches += job->launches;   // lock-step jobs counted on the context directly
+    delete job;
     *out = res;
     return VM_OK;
+}
+
+static int vm_align_impl(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,
+                         const int64_t *seq_off, int resident, vm_result **out)
+{
+    if (!out) { if (c) c->err = "bad argument"; return VM_ERR_ARG; }
+    vm_job *job = nullptr;
+    const int rc = vm_align_submit(c, h, p, n_reads, seqs, seq_off, resident, &job);
+    if (rc != VM_OK) return rc;
+    return vm_align_wait(job, out);
 }
 
 int vm_align_batch(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int64_t n_reads, const char *seqs,

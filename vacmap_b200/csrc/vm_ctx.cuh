@@ -88,6 +88,9 @@ struct vm_ctx {
     void (*backend_free)(void *) = nullptr;
     // worker contexts of the pipelined batch driver: own stream, chain state and backend; tables aliased
     std::vector<vm_ctx *> kids;
+    // pool of worker threads serving this context's alignment jobs (vm_capi_align.cu); stopped before the kids go
+    void *pool = nullptr;
+    void (*pool_free)(void *) = nullptr;
 };
 
 // worker context i of `parent` (created on first use; its tables alias the parent's)
