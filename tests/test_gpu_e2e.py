@@ -91,3 +91,35 @@ def test_edit_distance_upper_bound_never_undercuts(gpu_ctx, monkeypatch):
             want = pl.align_read(rid, seq, ox, ctg, opt, mode)
             assert [tuple(r) for r in g] == [tuple(w) for w in want], rid
         ix.close()
+
+
+@pytest.mark.parametrize("ci", range(len(E2E["cases"])))
+def test_cuda_sam_text_matches_reference(gpu_ctx, ci):
+    """Reads in, SAM text out (CUDA path + vacmap_b200.sam) == the lines the reference's get_bam_dict_str wrote."""
+    import vacmap_b200 as vb
+    case = E2E["cases"][ci]
+    ref, reads = case_inputs(case["name"])
+    ix = vb.Index(ref, w=10, k=15, ctx=gpu_ctx)
+    got = vb.Aligner(ix, option_for(case), case["mode"]).sam_lines(reads)
+    assert got == case["sam"]
+    ix.close()
+
+
+def test_command_line_on_testdata(tmp_path):
+    """BASELINE configs[0]: `-ref testdata/reference.fasta -read testdata/read.fasta -mode H` -> 3 alignments
+    (README:124), the inverted middle segment primary (FLAG 16), the flanks supplementary (FLAG 2048)."""
+    import gzip
+    import os
+    import shutil
+    import vacmap_b200.__main__ as cli
+    td = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testdata")
+    for f in ("reference.fasta", "read.fasta"):
+        with gzip.open(os.path.join(td, f + ".gz"), "rb") as fi, open(tmp_path / f, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    out = tmp_path / "out.sam"
+    cli.main(["-ref", str(tmp_path / "reference.fasta"), "-read", str(tmp_path / "read.fasta"), "-mode", "H", "-o", str(out)])
+    lines = out.read_text().splitlines()
+    body = [l for l in lines if not l.startswith("@")]
+    assert lines[0] == "@HD\tVN:1.0" and any(l.startswith("@SQ\tSN:") for l in lines)
+    assert body == E2E["cases"][0]["sam"][0]
+    assert sorted(l.split("\t")[1] for l in body) == ["16", "2048", "2048"]

@@ -1,0 +1,126 @@
+"""`python -m vacmap_b200 -ref R -read Q [Q ...] -mode H|L|S -o out.sam` -- the reference's command line
+(`vacmap:95-296`) over the CUDA path, for the flags that reach the per-read alignment path and its SAM text.
+Reads stream through in super-batches (one vm_align_submit per batch, the next one submitted before the previous
+is collected); records of a batch are written in read order, a read that does not map writes nothing (quirk A2).
+Not mirrored: BAM output through samtools, `.mmi` index files, BAM input, `-mode R` and `-mode asm`."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+from . import align, sam
+
+
+def build_parser():
+    p = argparse.ArgumentParser(prog="vacmap_b200", description="VACmap per-read alignment path on B200 (CUDA)")
+    p.add_argument("-ref", required=True)
+    p.add_argument("-read", required=True, nargs="+")
+    p.add_argument("-mode", required=True, choices=["H", "L", "S"])
+    p.add_argument("-o", default="-")
+    p.add_argument("--force", action="store_true")
+    p.add_argument("-t", type=int, default=0, help="host glue threads (0 = all cores)")
+    p.add_argument("-k", type=int, default=15)
+    p.add_argument("-w", type=int, default=10)
+    p.add_argument("-c", type=int, default=100)
+    p.add_argument("-maxdivergence", type=float)
+    p.add_argument("-globalpenalty", type=float)
+    p.add_argument("-localpenalty", type=float)
+    p.add_argument("-globalmaxdiff", type=int, default=50)
+    p.add_argument("-localmaxdiff", type=int, default=30)
+    for f in ("eqx", "MD", "L", "markunbalancetra", "nodiscard", "copycomments", "H", "fakecigar", "Q"):
+        p.add_argument("--" + f, action="store_true")
+    p.add_argument("--cs", nargs="?", const="short", default=None)
+    p.add_argument("--rg-id", dest="rg_id", default="1")
+    p.add_argument("--batch-bases", type=int, default=150_000_000, help="bases per super-batch")
+    p.add_argument("--device", type=int, default=0)
+    return p
+
+
+def options_from(args):
+    """The `pdict` of vacmap:177-296 (mode defaults, `golbal_` spelling and all)."""
+    opt = align.default_option(args.mode)
+    opt.update({"c": args.c, "eqx": args.eqx, "md": args.MD, "cigar2cg": args.L, "copycomments": args.copycomments, "H": args.H,
+                "fakecigar": args.fakecigar, "Q": args.Q, "rg-id": args.rg_id, "golbal_maxdiff": args.globalmaxdiff,
+                "local_maxdiff": args.localmaxdiff, "shortcs": args.cs != "long"})
+    if args.maxdivergence is not None:
+        opt["maxdivergence"] = args.maxdivergence
+    if args.globalpenalty is not None:
+        opt["golbal_skipcost"] = args.globalpenalty
+    if args.localpenalty is not None:
+        opt["local_skipcost"] = args.localpenalty
+    if args.markunbalancetra:
+        opt["markunbalancetra"] = True
+    if args.nodiscard:
+        opt["nodiscard"] = True
+    return opt
+
+
+def batches(paths, want_comments, batch_bases):
+    cur, n = [], 0
+    for path in paths:
+        for rec in align.read_fastx(path, read_comment=want_comments):
+            cur.append(rec)
+            n += len(rec[1])
+            if n >= batch_bases:
+                yield cur
+                cur, n = [], 0
+    if cur:
+        yield cur
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    if args.o != "-":
+        if not args.o.endswith(".sam"):
+            sys.exit("output path must end in .sam (BAM goes through samtools in the reference; not mirrored) or be '-'")
+        if os.path.isfile(args.o) and not args.force:
+            sys.exit("output file exists (use --force)")
+    opt = options_from(args)
+    ref = [(r[0], r[1].upper()) for r in align.read_fastx(args.ref)]
+    index = align.Index(ref, w=args.w, k=args.k, device=args.device)
+    al = align.Aligner(index, opt, args.mode, host_threads=args.t)
+    contig2seq = {n: s for n, s in ref}
+    contig2iloc = {n: i for i, (n, _) in enumerate(ref)}
+    out = sys.stdout if args.o == "-" else open(args.o, "w")
+    try:
+        out.write(sam.header_text([(n, len(s)) for n, s in ref]))
+        pending = None
+
+        def collect(p):
+            handle, recs_in = p
+            rec_off, recs, cig = al.wait(handle)
+            for i, rec in enumerate(recs_in):
+                rows = al.rows_of(rec[0], recs[rec_off[i]:rec_off[i + 1]], cig)
+                if not rows:
+                    continue
+                qual = None if (args.Q or len(rec) < 3) else rec[2]
+                try:
+                    if args.copycomments:
+                        lines = sam.get_bam_dict_str_comments(rows, rec[1].upper(), qual, rec[3] if len(rec) > 3 else None, contig2iloc,
+                                                              contig2seq, opt["md"], opt["shortcs"], opt["cigar2cg"],
+                                                              opt["markunbalancetra"], opt)
+                    else:
+                        lines = sam.get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
+                                                     opt["cigar2cg"], opt["markunbalancetra"], opt)
+                except Exception:          # the reference's worker swallows the read (clrnano:24116-24125)
+                    continue
+                out.write("\n".join(lines) + "\n")
+
+        for batch in batches(args.read, args.copycomments, args.batch_bases):
+            enc = [r[1].upper().encode() for r in batch]
+            off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+            nxt = (al.submit_packed(b"".join(enc), off), batch)
+            if pending is not None:
+                collect(pending)
+            pending = nxt
+        if pending is not None:
+            collect(pending)
+    finally:
+        if out is not sys.stdout:
+            out.close()
+        index.close()
+
+
+if __name__ == "__main__":
+    main()

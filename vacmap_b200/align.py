@@ -228,6 +228,15 @@ class Aligner:
         -> (rec_off int64[n+1], records structured array, cigar uint32 array)."""
         return self.wait(self.submit_packed(seq_cat, seq_off, resident=resident))
 
+    def rows_of(self, rid, recs, cig):
+        """`onemapinfolist` rows (clrnano:20760) of one read from its slice of the record array."""
+        rows = []
+        for r in recs:
+            ops = cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]]
+            rows.append(Record(rid, self.index.names[r["contig"]], "+" if r["strand"] == 1 else "-", int(r["q_st"]),
+                               int(r["q_en"]), int(r["r_st"]), int(r["r_en"]), int(r["mapq"]), cigar_string(ops)))
+        return rows
+
     def align_batch(self, reads):
         """reads: list of (readid, sequence).  -> list (per read) of lists of Record."""
         enc = [s.upper().encode() for _, s in reads]
@@ -235,14 +244,18 @@ class Aligner:
         for i, e in enumerate(enc):
             off[i + 1] = off[i] + len(e)
         rec_off, recs, cig = self.align_packed(b"".join(enc), off)
+        return [self.rows_of(rid, recs[rec_off[i]:rec_off[i + 1]], cig) for i, (rid, _) in enumerate(reads)]
+
+    def sam_lines(self, reads, quals=None):
+        """SAM text of a batch: per read, the lines `get_bam_dict_str` (clrnano:20841) writes for its records."""
+        from . import sam
+        o = self.option
+        contig2seq = {n: self.index.seq(n) for n in self.index.names}
+        contig2iloc = {n: i for i, n in enumerate(self.index.names)}
         out = []
-        for i, (rid, _) in enumerate(reads):
-            rows = []
-            for r in recs[rec_off[i]:rec_off[i + 1]]:
-                ops = cig[r["cigar_off"]:r["cigar_off"] + r["cigar_len"]]
-                rows.append(Record(rid, self.index.names[r["contig"]], "+" if r["strand"] == 1 else "-", int(r["q_st"]),
-                                   int(r["q_en"]), int(r["r_st"]), int(r["r_en"]), int(r["mapq"]), cigar_string(ops)))
-            out.append(rows)
+        for i, ((rid, seq), rows) in enumerate(zip(reads, self.align_batch(reads))):
+            out.append(sam.get_bam_dict_str(rows, seq.upper(), quals[i] if quals else None, contig2iloc, contig2seq, o["md"],
+                                            o["shortcs"], o["cigar2cg"], o["markunbalancetra"], o) if rows else [])
         return out
 
 

@@ -1,0 +1,301 @@
+"""SAM record text for the alignments of one read.
+
+Host mirror of the reference's emitter for the per-read path (``mammap_clrnano.py``):
+``get_bam_dict_str`` (:20841-21021), ``get_bam_dict_str_comments`` (:21022-), ``reassign_mapq``
+(:11661-11707), ``mergecigar_`` (:4773-4796), ``mergecigar_md_`` / ``get_MD_CSshort`` / ``get_MD_CSlong``
+(:19012-19148), ``P_alignmentstring`` (:5391-5424) and ``output_functions.nm_from_cigar`` (:300-349).
+Same argument meaning, same text -- including the quirks SURVEY Appendix A lists (tag order = dict
+insertion order RG, [CG], SA, NM, MD, cs; MD / cs empty unless the CIGAR uses ``=`` / ``X``; NM under
+``--H`` computed at the reference's offsets; ``n_cigar`` counting numbers AND letters).  The per-base Python
+loops of the reference (NM over ``M`` runs, reverse complement) are numpy comparisons here.
+"""
+import re
+
+import numpy as np
+
+_CIGAR_RE = re.compile(r"(\d+)([MIDNSHP=X])")
+_COMP = bytes.maketrans(b"ACGTUNacgtun", b"TGCAANtgcaan")
+
+
+def reverse_complement(seq):
+    """``str(Bio.Seq.Seq(seq).reverse_complement())`` for the alphabet the hot path sees (ACGTN, either case)."""
+    return seq.encode().translate(_COMP)[::-1].decode()
+
+
+def sort_by_length(x):            # :66
+    return x[4] - x[3]
+
+
+def reassign_mapq(onemapinfolist):
+    """:11661-11707 -- MAPQ 0 for records off the "main" reference-ordered path (quirk A11)."""
+    g_list = [0]
+    n = len(onemapinfolist)
+    while g_list[-1] < n - 1:
+        iloc = g_list[-1]
+        test_iloc = iloc
+        b = onemapinfolist[iloc]
+        b_contig, b_q_st, b_q_en, b_r_st, b_r_en = b[1], b[3], b[4], b[5], b[6]
+        hit = False
+        while test_iloc + 1 < n:
+            test_iloc += 1
+            t = onemapinfolist[test_iloc]
+            if t[1] != b_contig:
+                continue
+            if t[2] == "+":
+                refgap = t[5] - b_r_en
+            else:
+                refgap = b_r_st - t[6]
+            if abs(refgap) > 100000:
+                continue
+            if refgap < 10:
+                g_list.append(test_iloc)
+                hit = True
+                break
+        if not hit:
+            g_list.append(iloc + 1)
+    keep = set(g_list)
+    out = []
+    for iloc, rec in enumerate(onemapinfolist):
+        rec = list(rec)
+        if iloc not in keep:
+            rec[7] = 0
+        out.append(rec)
+    return out
+
+
+def mergecigar_(cigarstring):
+    """:4773-4796 -- adjacent runs of the same op merged; returns the flat [number, op, number, op ...] list."""
+    oplist = []
+    preop = None
+    for num, op in _CIGAR_RE.findall(cigarstring):
+        if op == preop:
+            oplist[-2] = str(int(oplist[-2]) + int(num))
+        else:
+            oplist.append(str(int(num)))
+            oplist.append(op)
+            preop = op
+    return oplist
+
+
+def _codes(s):
+    return np.frombuffer(s.upper().encode(), dtype=np.uint8)
+
+
+def nm_from_cigar(cigar_string, query_seq, ref_seq):
+    """output_functions.py:300-349 -- mismatches in M + I + D + X; S advances the query, H does not (quirk A8)."""
+    q, r = _codes(query_seq), _codes(ref_seq)
+    nm = q_pos = r_pos = 0
+    for num, op in _CIGAR_RE.findall(cigar_string):
+        n = int(num)
+        if op == "M":
+            a, b = q[q_pos:q_pos + n], r[r_pos:r_pos + n]
+            if len(a) != n or len(b) != n:
+                raise IndexError("string index out of range")      # the reference's per-base loop raises here
+            nm += int(np.count_nonzero(a != b))
+            q_pos += n
+            r_pos += n
+        elif op == "I":
+            nm += n
+            q_pos += n
+        elif op == "D":
+            nm += n
+            r_pos += n
+        elif op == "N":
+            r_pos += n
+        elif op == "S":
+            q_pos += n
+        elif op == "=":
+            q_pos += n
+            r_pos += n
+        elif op == "X":
+            nm += n
+            q_pos += n
+            r_pos += n
+    return nm
+
+
+def md_cs(oplist, target, query, shortcs=True):
+    """get_MD_CSshort / get_MD_CSlong (:19012-19112): MD and cs from an =/X CIGAR; ('', '') at the first M."""
+    md, cs = [], []
+    refloc = readloc = 0
+    preop = ""
+    equal_value = 0
+    for i in range(1, len(oplist), 2):
+        value = int(oplist[i - 1])
+        op = oplist[i]
+        if op == "X":
+            if equal_value > 0:
+                md.append(str(equal_value))
+            elif preop == "D":
+                md.append("0")
+            md.append(target[refloc])
+            cs.append("*" + (target[refloc] + query[readloc]).lower())
+            for j in range(1, value):
+                md.append("0" + target[refloc + j])
+                cs.append("*" + (target[refloc + j] + query[readloc + j]).lower())
+            refloc += value
+            readloc += value
+            equal_value = 0
+        elif op == "=":
+            if shortcs:
+                cs.append(":" + oplist[i - 1])
+            else:
+                cs.append("=" + target[refloc:refloc + value].upper())
+            refloc += value
+            readloc += value
+            equal_value += value
+        elif op == "D":
+            if equal_value > 0:
+                md.append(str(equal_value))
+            elif preop == "X":
+                md.append("0")
+            md.append("^" + target[refloc:refloc + value])
+            cs.append("-" + target[refloc:refloc + value].lower())
+            refloc += value
+            equal_value = 0
+        elif op == "I":
+            cs.append("+" + query[readloc:readloc + value].lower())
+            readloc += value
+            continue
+        elif op in ("S", "H"):
+            continue
+        else:
+            return "", ""
+        preop = op
+    if equal_value > 0:
+        md.append(str(equal_value))
+    return "".join(md), "".join(cs)
+
+
+_FIXED = {"QNAME": 0, "FLAG": 1, "RNAME": 2, "POS": 3, "MAPQ": 4, "CIGAR": 5, "RNEXT": 6, "PNEXT": 7, "TLEN": 8, "SEQ": 9,
+          "QUAL": 10}
+
+
+def _tag(tag, value):
+    code = "i" if type(value) is int else "f" if type(value) is float else "Z"
+    return tag + ":" + code + ":" + str(value)
+
+
+def alignment_string(infodict, comments=None, with_comments=False):
+    """P_alignmentstring (:5391-5424) / P_alignmentstring_comments (:20686-20730)."""
+    infolist = ["*", "4", "*", "0", "255", "*", "*", "0", "0", "*", "*"]
+    tags = {"QNAME", "FLAG", "RNAME", "POS", "MAPQ", "CIGAR", "RNEXT", "PNEXT", "TLEN", "SEQ", "QUAL", "SA", "NM", "MD", "cs"}
+    for key, value in infodict.items():
+        if key in _FIXED:
+            infolist[_FIXED[key]] = value
+        else:
+            infolist.append(_tag(key, value))
+            tags.add(key)
+    if with_comments and isinstance(comments, str):
+        for onecomment in comments.split("\t"):
+            info = onecomment.split(":")
+            if len(info) == 3 and len(info[0]) == 2 and info[0] not in tags and info[1] in ("A", "i", "f", "Z", "H", "B"):
+                infolist.append(onecomment)
+                tags.add(info[0])
+    return "\t".join(infolist)
+
+
+def _fake_cigar(item, qlen, clipsyb):
+    top = str(item[3]) + clipsyb if item[3] > 0 else ""
+    tail = str(qlen - item[4]) + clipsyb if (qlen - item[4]) > 0 else ""
+    diff = item[4] - item[3] - item[6] + item[5]
+    if diff > 0:
+        body = str(item[6] - item[5]) + "M" + str(diff) + "I"
+    elif diff < 0:
+        body = str(item[4] - item[3]) + "M" + str(abs(diff)) + "D"
+    else:
+        body = str(item[4] - item[3]) + "M"
+    return top + body + tail
+
+
+def get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option,
+                     comments=None, with_comments=False):
+    """:20841-21021 -- SAM lines of one read's ``onemapinfolist`` rows
+    ``(readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar)``; longest query span first = primary
+    (stable sort then reverse: among equal spans the later row wins, quirk A12)."""
+    if markunbalancetra:
+        mapinfo = reassign_mapq(mapinfo)
+    else:
+        mapinfo = [list(x) for x in mapinfo]
+    hardclip = option["H"]
+    rc_query = reverse_complement(query)
+    mapinfo.sort(key=sort_by_length)
+    mapinfo = mapinfo[::-1]
+    fakecigar = option["fakecigar"]
+    clipsyb = "H" if hardclip else "S"
+    nms, mds, css, n_cigars, fakes = [], [], [], [], []
+    for item in mapinfo:
+        oriented = query if item[2] == "+" else rc_query
+        target = contig2seq[item[1]][item[5]:item[6]]
+        if not md:
+            oplist = mergecigar_(item[-1])
+            item[-1] = "".join(oplist)
+            nms.append(nm_from_cigar(item[8], oriented, target))
+            mds.append(None)
+            css.append(None)
+        else:
+            tmp_query = oriented[item[3]:item[4]]
+            oplist = mergecigar_(item[-1])
+            mdstring, csstring = md_cs(oplist, target, tmp_query, shortcs)
+            item[-1] = "".join(oplist)
+            nms.append(nm_from_cigar(item[-1], tmp_query, target))
+            mds.append(mdstring)
+            css.append(csstring)
+        n_cigars.append(len(oplist))
+        fakes.append(_fake_cigar(item, len(query), clipsyb) if fakecigar else None)
+    have_qual = qual is not None and len(qual) == len(query)
+    rc_qual = qual[::-1] if have_qual else None
+    out = []
+    for iloc, primary in enumerate(mapinfo):
+        d = {}
+        if "rg-id" in option:
+            d["RG"] = option["rg-id"]
+        d["QNAME"] = primary[0]
+        d["RNAME"] = primary[1]
+        base_value = 0 if iloc == 0 else 2048
+        d["FLAG"] = str(base_value if primary[2] == "+" else 16 + base_value)
+        d["POS"] = str(primary[5] + 1)
+        if n_cigars[iloc] > 65535 and cigar2cg:
+            d["CG"] = primary[8]
+        else:
+            d["CIGAR"] = primary[8]
+        if len(mapinfo) > 1:
+            sa = []
+            for t, item in enumerate(mapinfo):
+                if t == iloc:
+                    continue
+                sa.append("".join((item[1], ",", str(item[5] + 1), ",", item[2], ",", fakes[t] if fakecigar else item[8], ",",
+                                   str(item[7]), ",", str(nms[t]) + ";")))
+            d["SA"] = "".join(sa)
+        d["MAPQ"] = str(primary[7])
+        seq, q = (query, qual) if primary[2] == "+" else (rc_query, rc_qual)
+        if not hardclip:
+            d["SEQ"] = seq
+            if have_qual:
+                d["QUAL"] = q
+        else:
+            d["SEQ"] = seq[primary[3]:primary[4]]
+            if have_qual:
+                d["QUAL"] = q[primary[3]:primary[4]]
+        d["NM"] = nms[iloc]
+        if md:
+            d["MD"] = mds[iloc]
+            d["cs"] = css[iloc]
+        out.append(alignment_string(d, comments, with_comments))
+    return out
+
+
+def get_bam_dict_str_comments(mapinfo, query, qual, comments, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra,
+                              option):
+    """:21022- -- as above, with the FASTQ comment's well-formed SAM tags copied over (``--copycomments``)."""
+    return get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option,
+                            comments=comments, with_comments=True)
+
+
+def header_text(contigs, rg_id=None):
+    """``@HD VN:1.0`` + one ``@SQ`` per contig, as ``create_header`` (:70-83) hands to pysam; ``contigs`` = [(name, length)]."""
+    lines = ["@HD\tVN:1.0"]
+    lines += ["@SQ\tSN:%s\tLN:%d" % (n, ln) for n, ln in contigs]
+    if rg_id is not None:
+        lines.append("@RG\tID:%s" % rg_id)
+    return "\n".join(lines) + "\n"
