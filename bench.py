@@ -164,7 +164,9 @@ def run_reference(args):
 
 
 KERNEL_BYTES_NOTE = {
-    "k_fill": "B = sum(q+t) sequence bytes + q*t direction bytes (traceback matrix exceeds SMEM) per fill segment",
+    "k_fill": "B = sum(q+t) sequence bytes + q*t direction bytes (written once; the traceback re-reads only the path) + 4 B per CIGAR op",
+    "k_ed_upper": "B = sum(q+t) sequence bytes (every base is read once, by the gap DP or by the anchor check)",
+    "k_seed": "B = read bytes + 16 B per anchor out",
     "k_edit_distance": "B = sum(q+t) sequence bytes (bit-vector state stays in registers/SMEM)",
     "k_reseed_hits": "B = read bytes x2 strands + 8 B per hit written (x2 launches: count + fill)",
     "k_reseed_merge": "B = 8 B per hit read + 16 B per anchor out",
@@ -211,6 +213,11 @@ def main():
 
     # reads shard across ranks (no data-path collective): weak scaling, fixed work per GPU
     ref, reads, cat, off = make_workload(args.reads, rank)
+    if dist is not None:
+        # the one-time collective of the design: the reference goes out from rank 0 over NCCL, every rank then
+        # builds its own index replica in its own HBM
+        from vacmap_b200 import shard
+        ref = shard.broadcast_reference(ref if rank == 0 else None)
     ctx = vb._lib.Context(local_rank)
     ix = vb.Index(ref, w=10, k=15, ctx=ctx)
     al = vb.Aligner(ix, vb.default_option("H"), "H", workers=args.workers, chunk_reads=args.chunk)
@@ -268,21 +275,29 @@ def main():
     e2e_wall = time.perf_counter() - t0
     d2h = recs.nbytes + cig.nbytes + rec_off.nbytes
 
+    # ---- roofline leg: one lock-step pass (one worker, one stream), so every kernel is timed alone by the CUDA
+    # events the library records on its launching stream; the pipelined legs above overlap kernels of several
+    # workers, which stretches their individual durations ----
+    solo = {}
+    if rank == 0:
+        al1 = vb.Aligner(ix, vb.default_option("H"), "H", workers=1)
+        for _ in range(2):
+            al1.align_packed(cat, off, resident=True)
+            solo = dict(al1.last_stage_ms)
+
     t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
     tot = torch.tensor([aligned, aligned_e2e, len(recs)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        # final gather of the alignment records on rank 0 (fixed-size rows; CIGAR arenas stay per rank)
-        n_local = torch.tensor([len(recs)], dtype=torch.int64, device="cuda")
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, n_local)
-        mx = int(max(int(s.item()) for s in sizes))
-        payload = torch.zeros((mx, vb.align.RECORD_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
-        if len(recs):
-            payload[:len(recs)] = torch.from_numpy(recs.view(np.uint8).reshape(len(recs), -1)).cuda()
-        gathered = [torch.zeros_like(payload) for _ in range(world)] if rank == 0 else None
-        dist.gather(payload, gathered, dst=0)
+        # final gather of the alignment records (rows + CIGAR arena) on rank 0, global read order
+        tg = time.perf_counter()
+        gathered = shard.gather_records(rec_off, recs, cig)
+        gather_ms = 1000 * (time.perf_counter() - tg)
+        if rank == 0:
+            assert len(gathered[1]) == int(tot[2].item())
+    else:
+        gather_ms = 0.0
     wall_max, e2e_max = [float(x) for x in t.cpu()]
     aligned_all, aligned_e2e_all, nrec_all = [float(x) for x in tot.cpu()]
 
@@ -291,26 +306,37 @@ def main():
         e2e = aligned_e2e_all / e2e_max / 1e9
         peak, peak_src = peaks()
         per_step = {k: v / args.steps for k, v in stage.items()}
-        kern = {k: v for k, v in per_step.items() if k.startswith("k_") or k.endswith("_kernels")}
+        kern = {k: v for k, v in solo.items() if k.startswith("k_") or k.endswith("_kernels")}
         top = max(kern, key=kern.get) if kern else None
-        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_ed_cells",
+        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_ed_cells", "n_ed_upper_jobs",
                                                       "n_reseed_hits", "n_chain_anchors")}
-        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_cells"],
-                     "k_edit_distance": 2.0 * bases,
-                     "k_reseed_hits": 2 * (2.0 * bases) + 8.0 * counts["n_reseed_hits"],
+        n_ops = float(len(cig))
+        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_cells"] + 4.0 * n_ops,
+                     "k_edit_distance": 2.0 * bases, "k_ed_upper": 2.0 * bases,
+                     "k_reseed_hits": 2.0 * bases + 8.0 * counts["n_reseed_hits"],
                      "k_reseed_merge": 8.0 * counts["n_reseed_hits"] + 16.0 * counts["n_reseed_hits"] / 4,
                      "chain_local_kernels": 28.0 * counts["n_chain_anchors"], "chain_global_kernels": 28.0 * counts["n_chain_anchors"],
-                     "k_extend": 0.0}
+                     "k_seed": 1.0 * bases + 16.0 * counts["n_chain_anchors"], "k_extend": 0.0}
         roof = None
         if top:
             secs = kern[top] / 1000.0
             achieved = alg_bytes.get(top, 0.0) / secs / 1e9 if secs > 0 else 0.0
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
+            if os.path.exists(tp):
+                tj = json.load(open(tp)).get(top)
+                if tj:      # DRAM bytes per unit of work from the committed `ncu --set full` capture, scaled to this launch
+                    traffic = tj["dram_bytes_per_unit"] * counts.get(tj["unit_count"], 0.0)
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "kernel_ms_per_step": kern[top],
-                    "bytes_per_step": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
+                    "frac": achieved / peak, "traffic": traffic, "kernel_ms": kern[top],
+                    "kernel_ms_in_pipeline_per_step": per_step.get(top),
+                    "timing": "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
+                              "'launch' = the kernel's launches of one step (one per capacity class)",
+                    "bytes": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
                     "gcups": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
-                    "note": "integer DP wavefront: compute/latency-bound, not HBM-bound (SURVEY 8d); the HBM fraction is "
-                            "reported because north_star asks for it"}
+                    "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
+                    "note": "integer DP wavefront: bound by the ALU pipe (ncu: ~80 % ALU, ~30 % DRAM), not by HBM "
+                            "(SURVEY 8d); the HBM fraction is reported because north_star asks for it"}
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
@@ -323,7 +349,7 @@ def main():
                                          "the timed region"},
                 "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": len(cat) + off.nbytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "host_cores_busy": round(cpu_busy, 2), "host_cores": os.cpu_count(),
-                "records_per_step": nrec_all,
+                "records_per_step": nrec_all, "gather_ms": round(gather_ms, 2),
                 "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
                 "work_per_step": counts,
                 "roofline": roof, "clocks": clocks}
