@@ -308,8 +308,8 @@ def main():
         per_step = {k: v / args.steps for k, v in stage.items()}
         kern = {k: v for k, v in solo.items() if k.startswith("k_") or k.endswith("_kernels")}
         top = max(kern, key=kern.get) if kern else None
-        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_ed_cells", "n_ed_upper_jobs",
-                                                      "n_reseed_hits", "n_chain_anchors")}
+        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_fill_band_jobs", "n_fill_band_redo",
+                                                      "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors")}
         n_ops = float(len(cig))
         alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_cells"] + 4.0 * n_ops,
                      "k_edit_distance": 2.0 * bases, "k_ed_upper": 2.0 * bases,

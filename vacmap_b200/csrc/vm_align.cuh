@@ -86,10 +86,33 @@ struct VmFillPlan {
     std::vector<VmFillLaunch> launches;
     size_t dir_words = 0, band_words = 0;   // scratch needed (uint32 words), shared by the launches
 };
-void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan, int host_threads = 1);
+// only_mask != nullptr: plan only the jobs j with only_mask[j] != 0
+void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan, int host_threads = 1,
+                  const uint8_t *only_mask = nullptr);
 // counters_dev: one zeroed int per launch.  The CIGAR ops of job j end up in dense_out[results[j].x .. + results[j].y)
 // (results: uint2 per job, zero-initialised by the caller; dense_count: zeroed 64-bit bump allocator;
 // cigar_scratch: per-job room of tlen + qlen + 2 ops at J.out_off).  Returns the number of kernel launches.
 int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs_dev, const VmFillPair *pairs_dev, VmSeqSources src, int eqx,
                    uint32_t *dir_scratch, uint32_t *band_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
                    unsigned long long *dense_count, void *results, cudaStream_t stream);
+
+// ---- banded global fill with an optimality certificate (vm_fillb.cu) ----
+#define VM_FB_MAXC 8
+// two jobs sharing a warp and a band of diagonals [kmin, kmax] (b = -1: no partner)
+struct VmFillBandPair { int32_t a, b, kmin, kmax; };
+struct VmFillBandLaunch {
+    int C, pair_begin, pair_end, blocks;      // C register slots per lane: at most 32 * C band rows per anti-diagonal
+    long long dir_words_per_warp;
+};
+struct VmFillBandPlan {
+    std::vector<VmFillBandPair> pairs;
+    std::vector<VmFillBandLaunch> launches;
+    size_t dir_words = 0;
+};
+// false: the job is left to the full-matrix kernel (too small to gain, or too long for the staging)
+bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax);
+void vm_fillb_plan(const VmAlnJobDev *jobs_host, const int *ids, int n_ids, int sm_count, VmFillBandPlan &plan);
+// as vm_fill_launch; a job whose certificate fails gets results[j] = (0xffffffff, 0) and must be re-run unbanded
+int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs_dev, const VmFillBandPair *pairs_dev, VmSeqSources src, int eqx,
+                    uint32_t *dir_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
+                    unsigned long long *dense_count, void *results, cudaStream_t stream);

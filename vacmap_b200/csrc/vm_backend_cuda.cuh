@@ -118,11 +118,12 @@ public:
     bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
-    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0;
+    double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0, fill_band_jobs_ = 0,
+           fill_band_redo_ = 0;
     void reset_counters()
     {
         timer.ms.clear();
-        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = 0;
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = fill_band_jobs_ = fill_band_redo_ = 0;
     }
 
     // device time of a group of launches, CUDA events on the ctx stream
@@ -706,35 +707,91 @@ public:
             fill_bases_ += bases;
             fill_jobs_ += nj;
         }
+        // Jobs the banded kernel can take (with its optimality certificate) and the rest for the full-matrix kernel
+        static const bool no_band = getenv("VM_FILL_NO_BAND") != nullptr;      // debug / A-B switch
+        std::vector<int> band_ids;
+        std::vector<uint8_t> full_mask((size_t)nj, 1);
         {
             WallTimer w2(this, "h_fill_plan");
-            vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads);
+            if (!no_band) {
+                for (int j = 0; j < nj; ++j) {
+                    int kmin, kmax;
+                    if (J[j].t.len > 0 && J[j].q.len > 0 && vm_fillb_own_band(J[j].t.len, J[j].q.len, kmin, kmax)) {
+                        band_ids.push_back(j);
+                        full_mask[j] = 0;
+                    }
+                }
+            }
+            vm_fillb_plan(J, band_ids.data(), (int)band_ids.size(), c_->sm_count > 0 ? c_->sm_count : 148, bplan_);
+            vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());
         }
-        BE_OK(d_dir_.ensure(plan_.dir_words * 4 + 64));
+        const size_t n_launch = plan_.launches.size() + bplan_.launches.size();
+        BE_OK(d_dir_.ensure(std::max(plan_.dir_words, bplan_.dir_words) * 4 + 64));
         BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
         BE_OK(d_cig_.ensure((size_t)out_off * 4 + 64));
         BE_OK(d_cigd_.ensure((size_t)out_off * 4 + 64));
         BE_OK(d_seg_.ensure((size_t)nj * 8 + 64));
-        BE_OK(d_pairs_.ensure(plan_.pairs.size() * sizeof(VmFillPair) + plan_.launches.size() * 4 + 64));
-        // [pairs | dense counter (8 bytes, 8-aligned) | one launch counter each]
-        unsigned long long *d_count = (unsigned long long *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
+        BE_OK(d_pairs_.ensure(plan_.pairs.size() * sizeof(VmFillPair) + bplan_.pairs.size() * sizeof(VmFillBandPair) + n_launch * 4 + 128));
+        // [full pairs | band pairs | dense counter (8 bytes, 8-aligned) | one launch counter each]
+        VmFillBandPair *d_bpairs = (VmFillBandPair *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
+        unsigned long long *d_count = (unsigned long long *)(d_bpairs + bplan_.pairs.size());
         int *d_ctr = (int *)(d_count + 1);
         BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
         if (!plan_.pairs.empty())
             BE_OK(cudaMemcpyAsync(d_pairs_.p, plan_.pairs.data(), plan_.pairs.size() * sizeof(VmFillPair), cudaMemcpyHostToDevice,
                                   c_->stream));
-        BE_OK(cudaMemsetAsync(d_count, 0, 8 + plan_.launches.size() * 4 + 4, c_->stream));
+        if (!bplan_.pairs.empty())
+            BE_OK(cudaMemcpyAsync(d_bpairs, bplan_.pairs.data(), bplan_.pairs.size() * sizeof(VmFillBandPair), cudaMemcpyHostToDevice,
+                                  c_->stream));
+        BE_OK(cudaMemsetAsync(d_count, 0, 8 + n_launch * 4 + 4, c_->stream));
         BE_OK(cudaMemsetAsync(d_seg_.p, 0, (size_t)nj * 8, c_->stream));
-        KTimer kt(this, "k_fill");
-        c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
-                                       d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(),
-                                       d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
-        kt.stop();
-        WallTimer w3(this, "h_fill_post");
-        // per job (offset, length) into the dense CIGAR arena the kernel filled, then one dense D2H
         BE_OK(h_misc_.ensure((size_t)nj * 8 + 64));
         unsigned long long *h_count = h_misc_.as<unsigned long long>();
         uint32_t *h_res = (uint32_t *)(h_count + 1);
+        {
+            KTimer kt(this, "k_fill");
+            // the direction scratch is shared: the banded launches run first, the full-matrix ones after them on the
+            // same stream
+            c_->launches += vm_fillb_launch(bplan_, jobs_.as<VmAlnJobDev>(), d_bpairs, sources(), eqx ? 1 : 0, d_dir_.as<uint32_t>(),
+                                            d_ctr + plan_.launches.size(), d_cig_.as<uint32_t>(), d_cigd_.as<uint32_t>(), d_count,
+                                            d_seg_.p, c_->stream);
+            c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
+                                           d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(),
+                                           d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
+            kt.stop();
+        }
+        if (!band_ids.empty()) {
+            // jobs whose certificate failed: once more, in the full-matrix kernel
+            BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(cudaStreamSynchronize(c_->stream));
+            BE_OK(cudaGetLastError());
+            std::fill(full_mask.begin(), full_mask.end(), 0);
+            int n_redo = 0;
+            for (int j : band_ids)
+                if (h_res[2 * j] == 0xffffffffu) { full_mask[j] = 1; ++n_redo; }
+            fill_band_jobs_ += (double)band_ids.size();
+            fill_band_redo_ += n_redo;
+            if (n_redo) {
+                vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());
+                BE_OK(d_dir_.ensure(plan_.dir_words * 4 + 64));
+                BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
+                BE_OK(d_pairs_.ensure(plan_.pairs.size() * sizeof(VmFillPair) + plan_.launches.size() * 4 + 128));
+                int *d_ctr2 = (int *)(d_pairs_.as<VmFillPair>() + plan_.pairs.size());
+                BE_OK(cudaMemcpyAsync(d_pairs_.p, plan_.pairs.data(), plan_.pairs.size() * sizeof(VmFillPair), cudaMemcpyHostToDevice,
+                                      c_->stream));
+                BE_OK(cudaMemsetAsync(d_ctr2, 0, plan_.launches.size() * 4 + 4, c_->stream));
+                BE_OK(d_nh_.ensure(64));
+                BE_OK(cudaMemcpyAsync(d_nh_.p, d_count, 8, cudaMemcpyDeviceToDevice, c_->stream));   // the counter moves with us
+                d_count = d_nh_.as<unsigned long long>();
+                KTimer kt(this, "k_fill");
+                c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
+                                               d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr2, d_cig_.as<uint32_t>(),
+                                               d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
+                kt.stop();
+            }
+        }
+        WallTimer w3(this, "h_fill_post");
+        // per job (offset, length) into the dense CIGAR arena the kernel filled, then one dense D2H
         BE_OK(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaStreamSynchronize(c_->stream));
@@ -757,6 +814,7 @@ private:
     VmDevBuf reads_fwd_, reads_rc_, read_off_, jobs_, d_wlo_, d_whi_, d_gx_, d_gy_, d_nh_, d_hits_, d_tab_, d_order_, d_rout_,
         d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_, d_msegs_;
     VmFillPlan plan_;
+    VmFillBandPlan bplan_;
     Extracted gx_, lx_;
     VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;

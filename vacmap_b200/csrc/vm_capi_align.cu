@@ -106,7 +106,8 @@ struct vm_job {
     int64_t chunks_left = 0;
     std::string err;
     StageTimer timer;
-    double fill_cells = 0, fill_bases = 0, fill_jobs = 0, ed_cells = 0, ed_upper = 0, reseed_hits = 0, chain_anchors = 0;
+    double fill_cells = 0, fill_bases = 0, fill_jobs = 0, ed_cells = 0, ed_upper = 0, reseed_hits = 0, chain_anchors = 0, band_jobs = 0,
+           band_redo = 0;
     int64_t launches = 0;
     std::chrono::steady_clock::time_point t0, t_done;
 };
@@ -120,6 +121,8 @@ void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::strin
     job->fill_cells += wb.fill_cells_; job->fill_bases += wb.fill_bases_; job->fill_jobs += wb.fill_jobs_;
     job->ed_cells += wb.ed_cells_; job->ed_upper += wb.ed_upper_jobs_; job->reseed_hits += wb.reseed_hits_;
     job->chain_anchors += wb.chain_anchors_;
+    job->band_jobs += wb.fill_band_jobs_;
+    job->band_redo += wb.fill_band_redo_;
     job->launches += launches;
     if (!err.empty() && job->err.empty()) job->err = err;
     if (--job->chunks_left == 0) {
@@ -352,6 +355,8 @@ int vm_align_wait(vm_job *job, vm_result **out)
     tm.add("n_fill_cells", job->fill_cells);
     tm.add("n_fill_bases", job->fill_bases);
     tm.add("n_fill_jobs", job->fill_jobs);
+    tm.add("n_fill_band_jobs", job->band_jobs);
+    tm.add("n_fill_band_redo", job->band_redo);
     tm.add("n_ed_cells", job->ed_cells);
     tm.add("n_ed_upper_jobs", job->ed_upper);
     tm.add("n_reseed_hits", job->reseed_hits);

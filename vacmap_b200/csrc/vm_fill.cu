@@ -18,74 +18,13 @@
 //    reused by the next pair of the persistent warp, so the traceback reads mostly hit L2.
 //  * Traceback: two walker lanes (one per job) run on 32-step x R-row tiles the whole warp stages into shared
 //    memory with one round trip, instead of one dependent global load per path cell.
-#include "vm_align.cuh"
+#include "vm_fill_cell.cuh"
 #include "vm_hostpool.hpp"
 #include <algorithm>
 #include <cstdlib>
 #include <cuda_fp16.h>
 
 namespace {
-
-struct VmGapPar2 {
-    int match, mismatch, q1, e1, q2, e2;
-};
-__host__ __device__ constexpr VmGapPar2 vm_fill_par() { return VmGapPar2{2, -4, 4, 2, 24, 1}; }
-
-// H on the boundary row / column after `len` gap bases (0 for len == 0)
-__device__ __forceinline__ int vm_hb(int len)
-{
-    constexpr VmGapPar2 g = vm_fill_par();
-    if (len <= 0) return 0;
-    const int a = -(g.q1 + g.e1 * len), b = -(g.q2 + g.e2 * len);
-    return a > b ? a : b;
-}
-
-__device__ __forceinline__ __half2 vm_h2(unsigned bits) { return *reinterpret_cast<__half2 *>(&bits); }
-__device__ __forceinline__ unsigned vm_u32(__half2 h) { return *reinterpret_cast<unsigned *>(&h); }
-__device__ __forceinline__ __half2 vm_h2i(int v) { return __half2half2(__int2half_rn(v)); }
-#define VM_H2C(x) __floats2half2_rn((float)(x), (float)(x))
-
-// fp16 bit pattern of a base code; N (and padding) is NaN so that both the ordered == and the ordered != test
-// fail and the substitution score becomes 0
-__device__ __forceinline__ unsigned vm_code_half(int c)
-{
-    return c == 0 ? 0x0000u : c == 1 ? 0x3c00u : c == 2 ? 0x4000u : c == 3 ? 0x4200u : 0x7fffu;
-}
-
-// One cell for both jobs.  in: v = v(i-1,j), x1/x2 = x(i-1,j) from the cell above; u/y1/y2 = from the cell to the
-// left.  out: the same quantities for (i,j), and the direction bits of job A in byte 0 / job B in byte 2.
-__device__ __forceinline__ void vm_cell2(__half2 tc, __half2 qc, __half2 &v, __half2 &x1, __half2 &x2, __half2 &u, __half2 &y1,
-                                         __half2 &y2, unsigned &dir)
-{
-    constexpr VmGapPar2 g = vm_fill_par();
-    const unsigned eqm = __heq2_mask(tc, qc);
-    const __half2 ne1 = __hne2(tc, qc);
-    __half2 z = __hfma2(ne1, VM_H2C(g.mismatch), vm_h2(eqm & (g.match == 2 ? 0x40004000u : 0u)));
-    const __half2 a = __hadd2(x1, v), b = __hadd2(y1, u), a2 = __hadd2(x2, v), b2 = __hadd2(y2, u);
-    unsigned m, dl;
-    m = __hgt2_mask(a, z);  z = __hmax2(z, a);  dl = m & 0x00010001u;
-    m = __hgt2_mask(b, z);  z = __hmax2(z, b);  dl = (dl & ~m) | (m & 0x00020002u);
-    m = __hgt2_mask(a2, z); z = __hmax2(z, a2); dl = (dl & ~m) | (m & 0x00030003u);
-    m = __hgt2_mask(b2, z); z = __hmax2(z, b2); dl = (dl & ~m) | (m & 0x00040004u);
-    const __half2 un = __hsub2(z, v), vn = __hsub2(z, u);
-    const __half2 one = VM_H2C(1), zero = VM_H2C(0);
-    const __half2 t1 = __hsub2(VM_H2C(g.q1), z);          // -(z - q1)
-    const __half2 ap = __hfma2_relu(one, a, t1), bp = __hfma2_relu(one, b, t1);
-    const __half2 t2 = __hsub2(VM_H2C(g.q2), z);
-    const __half2 a2p = __hfma2_relu(one, a2, t2), b2p = __hfma2_relu(one, b2, t2);
-    unsigned d = dl | (eqm & 0x00800080u);
-    d |= __hgt2_mask(ap, zero) & 0x00080008u;
-    d |= __hgt2_mask(bp, zero) & 0x00100010u;
-    d |= __hgt2_mask(a2p, zero) & 0x00200020u;
-    d |= __hgt2_mask(b2p, zero) & 0x00400040u;
-    x1 = __hsub2(ap, VM_H2C(g.q1 + g.e1));
-    y1 = __hsub2(bp, VM_H2C(g.q1 + g.e1));
-    x2 = __hsub2(a2p, VM_H2C(g.q2 + g.e2));
-    y2 = __hsub2(b2p, VM_H2C(g.q2 + g.e2));
-    u = un;
-    v = vn;
-    dir = d;
-}
 
 template <int R, bool MB>
 __global__ void __launch_bounds__(128) vm_fill_kernel(VmAlnJobDev *jobs, const VmFillPair *__restrict__ pairs, int pair_begin,
@@ -314,7 +253,7 @@ int vm_fill_blocks_per_sm(int R, bool mb)
 // rc = 9 beyond (R = 16, several bands); column class by qlen (<= 512, <= 4096, longer) so that one very long
 // query does not size the scratch of every resident warp.  Inside a class jobs are ordered by qlen and paired
 // with their neighbour: both halves of the half2 registers do useful work for (nearly) the whole sweep.
-void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, int host_threads)
+void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, int host_threads, const uint8_t *only_mask)
 {
     plan.pairs.clear();
     plan.launches.clear();
@@ -322,7 +261,7 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, 
     constexpr int NCLS = 27, NB = 1024, NKEY = NCLS * NB;
     auto key_of = [&](int j) {
         const int tl = J[j].t.len, ql = J[j].q.len;
-        if (tl <= 0 || ql <= 0) return -1;
+        if (tl <= 0 || ql <= 0 || (only_mask && !only_mask[j])) return -1;
         const int rc = tl <= 512 ? (tl + 63) / 64 : 9;
         const int qc = ql <= 512 ? 0 : ql <= 4096 ? 1 : 2;
         const int cls = (rc - 1) * 3 + qc;

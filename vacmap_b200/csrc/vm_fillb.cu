@@ -1,0 +1,414 @@
+// Banded global dual-affine fill with an optimality certificate: the same alignment (score, tie order, CIGAR) as
+// the full-matrix kernel of vm_fill.cu -- mp.k_cigar(target, query, 2, -4, 4, 2, 24, 1, bw=-1, zdropvalue=-1, eqx)
+// at mammap_clrnano.py:21554, 21598 -- for roughly half the cells.
+//
+// Why it is exact.  Only the diagonals k = j - i in [kmin, kmax] are computed; a cell whose upper (left) neighbour
+// lies outside sees -infinity there.  The traced path has the banded optimum S.  A path that touches a diagonal
+// above kmax needs nI >= kmax + 1 inserted bases and nI - D deleted ones to come back (D = qlen - tlen), so it
+// scores at most 2 (qlen - nI) - g(nI) - g(nI - D), g(n) = min(q1 + e1 n, q2 + e2 n); symmetrically below kmin.
+// If S is strictly above both bounds, no path leaving the band reaches S: every cell of the traced path has the
+// same value and the same winning predecessor as in the full matrix (a better or tying prefix through the outside
+// would, joined with the path's suffix, be an outside path scoring >= S), so the direction walk is identical.
+// Jobs that fail the test are reported as such and the host re-runs them in the full-matrix kernel.
+//
+// Layout.  Anti-diagonal wavefront: at step r the band holds at most 32*C rows t (cells (t, r - t)); row t lives in
+// lane (t / C) % 32, register slot t % C, and the slot moves on to row t + 32*C when t leaves the band.  u / y
+// (differences towards the left neighbour) stay in the row's registers, v / x (towards the upper neighbour) are
+// read from the slot above -- slot c - 1 of the same lane, or slot C - 1 of the previous lane through three
+// shuffles per step.  A slot that is not computing publishes (v, x) = (0, -inf), which is exactly what a cell on
+// the band's upper edge must see.  Two jobs share a warp, one per half of every half2 register (as in vm_fill.cu);
+// they share the band geometry (the union of their bands), cells beyond a job's own matrix are never read back.
+// Direction bytes go to the warp's scratch as [step][word][lane] (one 128-byte line per store instruction); the
+// traceback stages 32-step tiles of the few lanes it can reach into shared memory, compares the bases itself
+// (both sequences are staged in shared memory as fp16 codes) and sums the path's score for the certificate.
+#include "vm_fill_cell.cuh"
+#include <algorithm>
+
+namespace {
+
+#define VM_FB_CAP 768          // longest target / query the banded kernel stages in shared memory
+#define VM_FB_NEG (-1000)      // "-infinity" of the difference recurrences (exact in fp16)
+
+__device__ __forceinline__ int vm_gapcost(int n)
+{
+    constexpr VmGapPar2 g = vm_fill_par();
+    const int a = g.q1 + g.e1 * n, b = g.q2 + g.e2 * n;
+    return a < b ? a : b;
+}
+
+// upper bound on the score of any path of a (tlen x qlen) job that leaves the band [kmin, kmax]
+__device__ __forceinline__ int vm_outside_bound(int tlen, int qlen, int kmin, int kmax)
+{
+    const int D = qlen - tlen;
+    int best = -0x3fffffff;
+    const int nI = kmax + 1;
+    if (nI <= qlen && nI - D >= 1 && nI - D <= tlen) best = 2 * (qlen - nI) - vm_gapcost(nI) - vm_gapcost(nI - D);
+    const int nD = -kmin + 1;
+    if (nD <= tlen && nD + D >= 1 && nD + D <= qlen) {
+        const int b = 2 * (tlen - nD) - vm_gapcost(nD) - vm_gapcost(nD + D);
+        if (b > best) best = b;
+    }
+    return best;
+}
+
+template <int C>
+__global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
+                                                       int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
+                                                       long long dir_words_per_warp, int *counter, uint32_t *cigar_out,
+                                                       uint32_t *dense_out, unsigned long long *dense_count, uint2 *results)
+{
+    constexpr VmGapPar2 g = vm_fill_par();
+    constexpr int CW = (C + 1) / 2;                               // direction words per lane and step
+    constexpr int NL = (31 / C + 2) < 32 ? (31 / C + 2) : 32;     // lanes a 32-row tile can touch
+    constexpr int TW = NL * CW;                                   // tile words per step
+    extern __shared__ uint32_t vm_fb_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *sT = vm_fb_smem + (size_t)warp * (2 * VM_FB_CAP + 2 * 32 * TW);
+    uint32_t *sQ = sT + VM_FB_CAP;
+    uint32_t *tile = sQ + VM_FB_CAP;                              // [2][32][TW]
+    const long long gw = (long long)blockIdx.x * 4 + warp;
+    uint32_t *dir = dir_all + gw * dir_words_per_warp;
+    const __half2 neg2 = VM_H2C(VM_FB_NEG), zero2 = VM_H2C(0);
+    const __half2 open1 = VM_H2C(-(g.q1 + g.e1)), open2 = VM_H2C(-(g.q2 + g.e2));
+    for (;;) {
+        int p = 0;
+        if (lane == 0) p = pair_begin + atomicAdd(counter, 1);
+        p = __shfl_sync(VM_FULL, p, 0);
+        if (p >= pair_end) break;
+        const VmFillBandPair pr = pairs[p];
+        const bool hasB = pr.b >= 0;
+        VmAlnJobDev &JA = jobs[pr.a];
+        VmAlnJobDev &JB = jobs[hasB ? pr.b : pr.a];
+        const VmSeqView TA = vm_view(S, JA.t, JA.read), QA = vm_view(S, JA.q, JA.read);
+        const VmSeqView TB = vm_view(S, JB.t, JB.read), QB = vm_view(S, JB.q, JB.read);
+        const int tA = TA.len, qA = QA.len, tB = hasB ? TB.len : 0, qB = hasB ? QB.len : 0;
+        const int tlen = tA > tB ? tA : tB, qlen = qA > qB ? qA : qB;
+        const int kmin = pr.kmin, kmax = pr.kmax;
+        // ---------------- stage both sequences as fp16 code pairs (A low half, B high half) ----------------
+        __syncwarp();
+        for (int t = lane; t < tlen; t += 32)
+            sT[t] = vm_code_half(t < tA ? vm_at(TA, t) : 4) | vm_code_half(t < tB ? vm_at(TB, t) : 4) << 16;
+        for (int q = lane; q < qlen; q += 32)
+            sQ[q] = vm_code_half(q < qA ? vm_at(QA, q) : 4) | vm_code_half(q < qB ? vm_at(QB, q) : 4) << 16;
+        __syncwarp();
+        // ---------------- forward pass over the anti-diagonals ----------------
+        int row[C];
+        __half2 tc[C], u[C], y1[C], y2[C], v[C], x1[C], x2[C];
+        auto init_row = [&](int c, int t) {
+            // the row's first cell is in column 0 (real boundary) or on the band's lower edge (nothing to its left)
+            row[c] = t;
+            tc[c] = vm_h2(t < tlen ? sT[t] : 0x7fff7fffu);
+            if (t + kmin <= 0) {
+                u[c] = vm_h2i(vm_hb(t + 1) - vm_hb(t));
+                y1[c] = open1;
+                y2[c] = open2;
+            } else {
+                u[c] = zero2;
+                y1[c] = neg2;
+                y2[c] = neg2;
+            }
+        };
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            init_row(c, lane * C + c);
+            v[c] = zero2; x1[c] = neg2; x2[c] = neg2;
+        }
+        const int nsteps = tlen + qlen - 1;
+        for (int r = 0; r < nsteps; ++r) {
+            int tlo = r - (qlen - 1);
+            const int e = r - kmax;                       // ceil((r - kmax) / 2)
+            const int tk = e > 0 ? (e + 1) >> 1 : 0;
+            if (tlo < tk) tlo = tk;
+            if (tlo < 0) tlo = 0;
+            int thi = r < tlen - 1 ? r : tlen - 1;
+            const int f = r - kmin;                       // floor((r - kmin) / 2), r - kmin >= 0 always
+            if ((f >> 1) < thi) thi = f >> 1;
+            // what the slot above holds from the previous step: slot C-1 of the previous lane for slot 0
+            __half2 inV = __shfl_sync(VM_FULL, v[C - 1], (lane + 31) & 31);
+            __half2 inX1 = __shfl_sync(VM_FULL, x1[C - 1], (lane + 31) & 31);
+            __half2 inX2 = __shfl_sync(VM_FULL, x2[C - 1], (lane + 31) & 31);
+            unsigned d[C];
+#pragma unroll
+            for (int c = C - 1; c >= 0; --c) {
+                if (row[c] < tlo) init_row(c, row[c] + 32 * C);
+                const int t = row[c];
+                d[c] = 0u;
+                if (t <= thi) {
+                    const int j = r - t;
+                    __half2 cv, cx1, cx2;
+                    if (c > 0) { cv = v[c - 1]; cx1 = x1[c - 1]; cx2 = x2[c - 1]; }
+                    else { cv = inV; cx1 = inX1; cx2 = inX2; }
+                    if (t == 0) {                          // real boundary row
+                        cv = vm_h2i(vm_hb(j + 1) - vm_hb(j));
+                        cx1 = open1;
+                        cx2 = open2;
+                    }
+                    const __half2 qc = vm_h2(sQ[j]);
+                    vm_cell2(tc[c], qc, cv, cx1, cx2, u[c], y1[c], y2[c], d[c]);
+                    v[c] = cv; x1[c] = cx1; x2[c] = cx2;
+                }
+            }
+            // slots that did not compute this step publish (0, -inf); done after the reads above
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (row[c] > thi) { v[c] = zero2; x1[c] = neg2; x2[c] = neg2; }
+            uint32_t *dst = dir + (long long)r * (CW * 32) + lane;
+#pragma unroll
+            for (int m = 0; m < CW; ++m) {
+                const unsigned lo = d[2 * m], hi = (2 * m + 1 < C) ? d[(2 * m + 1 < C) ? 2 * m + 1 : 0] : 0u;
+                dst[m * 32] = __byte_perm(lo, hi, 0x6420);           // [A even, B even, A odd, B odd]
+            }
+        }
+        __syncwarp();
+        // ---------------- traceback (ksw_backtrack, left-aligned): lane 0 walks job A, lane 1 job B ----------------
+        const int w = lane & 1;
+        const int tw = w ? tB : tA, qw = w ? qB : qA;
+        const bool walker = lane < 2 && tw > 0 && qw > 0;
+        uint32_t *out = cigar_out + (w ? JB.out_off : JA.out_off);
+        int i = tw - 1, j = qw - 1, state = 0, n = 0, score = 0;
+        unsigned cur_op = 0, cur_len = 0;
+        const int sh = w * 16;
+        for (;;) {
+            const bool need = walker && i >= 0 && j >= 0;
+            const unsigned needmask = __ballot_sync(VM_FULL, need) & 3u;
+            if (!needmask) break;
+#pragma unroll
+            for (int ws = 0; ws < 2; ++ws) {
+                const int ii = __shfl_sync(VM_FULL, i, ws), jj = __shfl_sync(VM_FULL, j, ws);
+                if (needmask >> ws & 1u) {
+                    const int rr = ii + jj - lane;                    // this lane stages one anti-diagonal of the tile
+                    const int row_lo = ii > 31 ? ii - 31 : 0;
+                    const int lane_lo = (row_lo / C) & 31;
+                    if (rr >= 0) {
+                        const uint32_t *src = dir + (long long)rr * (CW * 32);
+                        uint32_t *tl = tile + ((size_t)ws * 32 + lane) * TW;
+#pragma unroll
+                        for (int x = 0; x < NL; ++x)
+#pragma unroll
+                            for (int m = 0; m < CW; ++m) tl[x * CW + m] = src[m * 32 + ((lane_lo + x) & 31)];
+                    }
+                }
+            }
+            __syncwarp();
+            if (need) {
+                const int r_hi = i + j, row_lo = i > 31 ? i - 31 : 0, blk_lo = row_lo / C;
+                const uint32_t *tl = tile + (size_t)w * 32 * TW;
+                while (i >= 0 && j >= 0) {
+                    const int back = r_hi - (i + j);
+                    if (back >= 32 || i < row_lo) break;
+                    const int c = i % C;
+                    const unsigned tmp = (tl[back * TW + (i / C - blk_lo) * CW + (c >> 1)] >> (((c & 1) * 2 + w) * 8)) & 0xffu;
+                    if (state == 0) state = tmp & 7;
+                    else if (!((tmp >> (state + 2)) & 1)) state = 0;
+                    if (state == 0) state = tmp & 7;
+                    unsigned op;
+                    if (state == 0) {
+                        const unsigned a = (sT[i] >> sh) & 0xffffu, b = (sQ[j] >> sh) & 0xffffu;
+                        const bool same = a == b;
+                        if (a != 0x7fffu && b != 0x7fffu) score += same ? g.match : g.mismatch;
+                        op = eqx ? (same ? 7u : 8u) : 0u;
+                        --i; --j;
+                    } else if (state == 1 || state == 3) { op = 2; --i; }
+                    else { op = 1; --j; }
+                    if (op == cur_op) ++cur_len;
+                    else {
+                        if (cur_len) {
+                            out[n++] = cur_len << 4 | cur_op;
+                            if (cur_op == 1u || cur_op == 2u) score -= vm_gapcost((int)cur_len);
+                        }
+                        cur_op = op;
+                        cur_len = 1;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        bool certified = true;
+        if (walker) {
+            if (i >= 0) {
+                if (cur_len && cur_op == 2u) cur_len += (unsigned)(i + 1);
+                else {
+                    if (cur_len) { out[n++] = cur_len << 4 | cur_op; if (cur_op == 1u) score -= vm_gapcost((int)cur_len); }
+                    cur_op = 2u;
+                    cur_len = (unsigned)(i + 1);
+                }
+            }
+            if (j >= 0) {
+                if (cur_len && cur_op == 1u) cur_len += (unsigned)(j + 1);
+                else {
+                    if (cur_len) { out[n++] = cur_len << 4 | cur_op; if (cur_op == 2u) score -= vm_gapcost((int)cur_len); }
+                    cur_op = 1u;
+                    cur_len = (unsigned)(j + 1);
+                }
+            }
+            if (cur_len) {
+                out[n++] = cur_len << 4 | cur_op;
+                if (cur_op == 1u || cur_op == 2u) score -= vm_gapcost((int)cur_len);
+            }
+            certified = score > vm_outside_bound(tw, qw, kmin, kmax);
+        }
+        __syncwarp();
+        // ops were pushed end to start: claim room in the dense CIGAR arena and copy them over flipped, all lanes helping
+#pragma unroll
+        for (int ws = 0; ws < 2; ++ws) {
+            if (ws == 1 && !hasB) break;
+            const int ok = __shfl_sync(VM_FULL, certified ? 1 : 0, ws);
+            const int nn = ok ? __shfl_sync(VM_FULL, walker ? n : 0, ws) : 0;
+            unsigned long long base = 0;
+            if (lane == 0 && nn > 0) base = atomicAdd(dense_count, (unsigned long long)nn);
+            base = __shfl_sync(VM_FULL, base, 0);
+            const uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
+            for (int x = lane; x < nn; x += 32) dense_out[base + x] = o[nn - 1 - x];
+            if (lane == 0) results[ws ? pr.b : pr.a] = ok ? make_uint2((unsigned)base, (unsigned)nn) : make_uint2(0xffffffffu, 0u);
+        }
+        __syncwarp();
+    }
+}
+
+template <int C>
+size_t vm_fillb_smem()
+{
+    constexpr int CW = (C + 1) / 2;
+    constexpr int NL = (31 / C + 2) < 32 ? (31 / C + 2) : 32;
+    return (size_t)4 * (2 * VM_FB_CAP + 2 * 32 * NL * CW) * sizeof(uint32_t);
+}
+
+template <int C>
+int vm_fillb_occupancy()
+{
+    vm_smem_optin(vm_fillb_kernel<C>);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vm_fillb_kernel<C>, 128, vm_fillb_smem<C>()) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+
+int vm_fillb_blocks_per_sm(int C)
+{
+    switch (C) {
+    case 1: return vm_fillb_occupancy<1>();
+    case 2: return vm_fillb_occupancy<2>();
+    case 3: return vm_fillb_occupancy<3>();
+    case 4: return vm_fillb_occupancy<4>();
+    case 5: return vm_fillb_occupancy<5>();
+    case 6: return vm_fillb_occupancy<6>();
+    case 7: return vm_fillb_occupancy<7>();
+    default: return vm_fillb_occupancy<8>();
+    }
+}
+
+} // namespace
+
+// The band a job gets on its own: half-width w around its corridor [min(0, D), max(0, D)], wide enough that a read
+// with ~10 % errors certifies with margin; jobs too small to gain, or too long for the shared-memory staging, are
+// left to the full-matrix kernel.
+bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax)
+{
+    const int mn = tlen < qlen ? tlen : qlen, mx = tlen > qlen ? tlen : qlen;
+    if (mn < 96 || mx > VM_FB_CAP) return false;
+    const int D = qlen - tlen;
+    int w = (int)(0.17 * mn) + 6;
+    if (w < 24) w = 24;
+    kmin = (D < 0 ? D : 0) - w;
+    kmax = (D > 0 ? D : 0) + w;
+    return ((kmax - kmin) / 2 + 1 + 31) / 32 <= VM_FB_MAXC;
+}
+
+// Pairs of jobs with (nearly) the same band: class key (slots C, D / 16), ordered by query length inside a class.
+void vm_fillb_plan(const VmAlnJobDev *J, const int *ids, int n_ids, int sm_count, VmFillBandPlan &plan)
+{
+    plan.pairs.clear();
+    plan.launches.clear();
+    plan.dir_words = 0;
+    struct Key { int c, dbucket, ql, id, kmin, kmax; };
+    std::vector<Key> keys;
+    keys.reserve((size_t)n_ids);
+    for (int x = 0; x < n_ids; ++x) {
+        const int j = ids[x];
+        Key k;
+        vm_fillb_own_band(J[j].t.len, J[j].q.len, k.kmin, k.kmax);
+        k.c = ((k.kmax - k.kmin) / 2 + 1 + 31) / 32;
+        k.dbucket = (J[j].q.len - J[j].t.len + 4096) >> 3;
+        k.ql = J[j].q.len;
+        k.id = j;
+        keys.push_back(k);
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
+        if (a.c != b.c) return a.c < b.c;
+        if (a.dbucket != b.dbucket) return a.dbucket < b.dbucket;
+        if (a.ql != b.ql) return a.ql < b.ql;
+        return a.id < b.id;
+    });
+    // pair neighbours; a pair's band is the union of its jobs' bands, which may need one slot more
+    std::vector<std::vector<VmFillBandPair>> by_c(VM_FB_MAXC + 2);
+    std::vector<int> max_steps(VM_FB_MAXC + 2, 0);
+    size_t x = 0;
+    while (x < keys.size()) {
+        VmFillBandPair pr;
+        pr.a = keys[x].id;
+        pr.b = -1;
+        pr.kmin = keys[x].kmin;
+        pr.kmax = keys[x].kmax;
+        int steps = J[pr.a].t.len + J[pr.a].q.len;
+        size_t used = 1;
+        if (x + 1 < keys.size() && keys[x + 1].c == keys[x].c) {
+            const int kmin = std::min(pr.kmin, keys[x + 1].kmin), kmax = std::max(pr.kmax, keys[x + 1].kmax);
+            if (((kmax - kmin) / 2 + 1 + 31) / 32 <= VM_FB_MAXC) {
+                pr.b = keys[x + 1].id;
+                pr.kmin = kmin;
+                pr.kmax = kmax;
+                steps = std::max(J[pr.a].t.len, J[pr.b].t.len) + std::max(J[pr.a].q.len, J[pr.b].q.len);
+                used = 2;
+            }
+        }
+        const int rows = (pr.kmax - pr.kmin) / 2 + 1;
+        const int c = (rows + 31) / 32;
+        // widen the band to the capacity of its slot class: free rows, more margin for the certificate
+        const int spare = 32 * c - rows;
+        pr.kmin -= spare;
+        pr.kmax += spare;
+        by_c[(size_t)c].push_back(pr);
+        max_steps[(size_t)c] = std::max(max_steps[(size_t)c], steps);
+        x += used;
+    }
+    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+        if (by_c[(size_t)c].empty()) continue;
+        VmFillBandLaunch L;
+        L.C = c;
+        L.pair_begin = (int)plan.pairs.size();
+        plan.pairs.insert(plan.pairs.end(), by_c[(size_t)c].begin(), by_c[(size_t)c].end());
+        L.pair_end = (int)plan.pairs.size();
+        L.dir_words_per_warp = (long long)max_steps[(size_t)c] * ((c + 1) / 2) * 32;
+        const int n_pairs = L.pair_end - L.pair_begin;
+        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
+        plan.dir_words = std::max(plan.dir_words, (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp));
+        plan.launches.push_back(L);
+    }
+}
+
+int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs, const VmFillBandPair *pairs, VmSeqSources src, int eqx, uint32_t *dir,
+                    int *counters, uint32_t *cigar_scratch, uint32_t *dense_out, unsigned long long *dense_count, void *results,
+                    cudaStream_t stream)
+{
+    int n = 0;
+    for (size_t li = 0; li < plan.launches.size(); ++li) {
+        const VmFillBandLaunch &L = plan.launches[li];
+        int *ctr = counters + li;
+#define VM_FILLB_GO(CC)                                                                                                  \
+    vm_fillb_kernel<CC><<<L.blocks, 128, vm_fillb_smem<CC>(), stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir, \
+                                                                        L.dir_words_per_warp, ctr, cigar_scratch, dense_out, \
+                                                                        dense_count, (uint2 *)results)
+        switch (L.C) {
+        case 1: VM_FILLB_GO(1); break;
+        case 2: VM_FILLB_GO(2); break;
+        case 3: VM_FILLB_GO(3); break;
+        case 4: VM_FILLB_GO(4); break;
+        case 5: VM_FILLB_GO(5); break;
+        case 6: VM_FILLB_GO(6); break;
+        case 7: VM_FILLB_GO(7); break;
+        default: VM_FILLB_GO(8); break;
+        }
+#undef VM_FILLB_GO
+        ++n;
+    }
+    return n;
+}
