@@ -111,7 +111,8 @@ struct VmFillBandPlan {
 };
 // false: the job is left to the full-matrix kernel (too small to gain, or too long for the staging)
 bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax);
-void vm_fillb_plan(const VmAlnJobDev *jobs_host, const int *ids, int n_ids, int sm_count, VmFillBandPlan &plan);
+// plans every job the banded kernel can take and clears its full_mask entry
+void vm_fillb_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, int host_threads, VmFillBandPlan &plan, uint8_t *full_mask);
 // as vm_fill_launch; a job whose certificate fails gets results[j] = (0xffffffff, 0) and must be re-run unbanded
 int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs_dev, const VmFillBandPair *pairs_dev, VmSeqSources src, int eqx,
                     uint32_t *dir_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,

@@ -15,6 +15,7 @@
 #include "vm_extract.cuh"
 #include "vm_pipeline.hpp"
 #include <chrono>
+#include <ctime>
 #include <map>
 #include <mutex>
 
@@ -145,13 +146,22 @@ public:
             Timeline::get().add(be, name, w0, std::chrono::steady_clock::now());
         }
     };
+    static double process_cpu_ms()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts);
+        return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+    }
+    // wall time of a stage, plus ("cpu_<name>") the CPU time the whole process burnt meanwhile -- in a lock-step
+    // run (one worker) that is the stage's own host cost on all threads
     struct WallTimer {
-        CudaBackend *be; const char *name; std::chrono::steady_clock::time_point t0;
-        WallTimer(CudaBackend *b, const char *n) : be(b), name(n), t0(std::chrono::steady_clock::now()) {}
+        CudaBackend *be; const char *name; std::chrono::steady_clock::time_point t0; double c0;
+        WallTimer(CudaBackend *b, const char *n) : be(b), name(n), t0(std::chrono::steady_clock::now()), c0(process_cpu_ms()) {}
         ~WallTimer()
         {
             const auto t1 = std::chrono::steady_clock::now();
             be->timer.add(name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+            be->timer.add((std::string("cpu_") + name).c_str(), process_cpu_ms() - c0);
             Timeline::get().add(be, name, t0, t1);
         }
     };
@@ -709,20 +719,11 @@ public:
         }
         // Jobs the banded kernel can take (with its optimality certificate) and the rest for the full-matrix kernel
         static const bool no_band = getenv("VM_FILL_NO_BAND") != nullptr;      // debug / A-B switch
-        std::vector<int> band_ids;
         std::vector<uint8_t> full_mask((size_t)nj, 1);
         {
             WallTimer w2(this, "h_fill_plan");
-            if (!no_band) {
-                for (int j = 0; j < nj; ++j) {
-                    int kmin, kmax;
-                    if (J[j].t.len > 0 && J[j].q.len > 0 && vm_fillb_own_band(J[j].t.len, J[j].q.len, kmin, kmax)) {
-                        band_ids.push_back(j);
-                        full_mask[j] = 0;
-                    }
-                }
-            }
-            vm_fillb_plan(J, band_ids.data(), (int)band_ids.size(), c_->sm_count > 0 ? c_->sm_count : 148, bplan_);
+            if (!no_band) vm_fillb_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, host_threads, bplan_, full_mask.data());
+            else { bplan_.pairs.clear(); bplan_.launches.clear(); bplan_.dir_words = 0; }
             vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());
         }
         const size_t n_launch = plan_.launches.size() + bplan_.launches.size();
@@ -760,16 +761,18 @@ public:
                                            d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
             kt.stop();
         }
-        if (!band_ids.empty()) {
+        if (!bplan_.pairs.empty()) {
             // jobs whose certificate failed: once more, in the full-matrix kernel
             BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
             BE_OK(cudaStreamSynchronize(c_->stream));
             BE_OK(cudaGetLastError());
-            std::fill(full_mask.begin(), full_mask.end(), 0);
-            int n_redo = 0;
-            for (int j : band_ids)
-                if (h_res[2 * j] == 0xffffffffu) { full_mask[j] = 1; ++n_redo; }
-            fill_band_jobs_ += (double)band_ids.size();
+            int n_redo = 0, n_band = 0;
+            for (int j = 0; j < nj; ++j) {
+                n_band += full_mask[j] == 0;
+                full_mask[j] = h_res[2 * j] == 0xffffffffu;
+                n_redo += full_mask[j];
+            }
+            fill_band_jobs_ += (double)n_band;
             fill_band_redo_ += n_redo;
             if (n_redo) {
                 vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());

@@ -148,6 +148,7 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
             Timeline::get().add(&wb, nm, t1 - std::chrono::duration_cast<std::chrono::steady_clock::duration>(
                                                   std::chrono::duration<double, std::milli>(ms)), t1);
         };
+        drv.on_cpu = [&wb](const char *nm, double ms) { wb.timer.add((std::string("cpu_") + nm).c_str(), ms); };
         const int64_t r0 = job->bounds[(size_t)ci], nr = job->bounds[(size_t)ci + 1] - r0;
         ReadBatch sb;
         sb.n = nr;
@@ -264,15 +265,15 @@ int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int
         CudaBackend &be = *(CudaBackend *)c->backend;
         be.set_index(h);
         be.reads_resident = resident != 0;
-        int workers = p->workers > 0 ? p->workers : 6;
-        const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + workers - 1) / workers);
-        if (n_reads <= chunk) workers = 1;
-        // equal chunks, a whole number of rounds per worker (every chunk pays the same fixed chain of launch and
-        // synchronisation latencies: fewer, larger chunks win, and a ragged last round would leave workers idle)
+        // `workers` = size of the pool; a job is cut into equal chunks of ~chunk_reads (default: a sixth of the job, at
+        // least 512 reads -- every chunk pays the same fixed chain of launch and synchronisation latencies, so fewer,
+        // larger chunks win).  With more workers than chunks per job, the chunks of the next job run beside them.
+        int workers = p->workers > 0 ? p->workers : 8;
+        const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 5) / 6);
+        if (n_reads <= chunk || workers == 1) workers = 1;
         job->bounds.assign(1, 0);
         if (workers > 1) {
-            const int64_t rounds = std::max<int64_t>(1, (n_reads + chunk * workers - 1) / (chunk * workers));
-            const int64_t parts = rounds * workers;
+            const int64_t parts = (n_reads + chunk - 1) / chunk;
             for (int64_t i = 1; i <= parts; ++i) {
                 const int64_t e = n_reads * i / parts;
                 if (e > job->bounds.back()) job->bounds.push_back(e);

@@ -22,6 +22,7 @@
 // traceback stages 32-step tiles of the few lanes it can reach into shared memory, compares the bases itself
 // (both sequences are staged in shared memory as fp16 codes) and sums the path's score for the certificate.
 #include "vm_fill_cell.cuh"
+#include "vm_hostpool.hpp"
 #include <algorithm>
 
 namespace {
@@ -51,6 +52,15 @@ __device__ __forceinline__ int vm_outside_bound(int tlen, int qlen, int kmin, in
     return best;
 }
 
+// H(-1, n) - H(-1, n - 1) of the boundary row / column, n = index + 1: the gap pieces cross at 20 bases
+// (4 + 2 n <= 24 + n), so the step is -(q1 + e1) for the first base, -e1 up to there and -e2 beyond
+__device__ __forceinline__ __half2 vm_boundary_step(int index)
+{
+    constexpr VmGapPar2 g = vm_fill_par();
+    static_assert(g.q1 == 4 && g.e1 == 2 && g.q2 == 24 && g.e2 == 1, "boundary steps are folded for these penalties");
+    return index == 0 ? VM_H2C(-(g.q1 + g.e1)) : index < 20 ? VM_H2C(-g.e1) : VM_H2C(-g.e2);
+}
+
 template <int C>
 __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
                                                        int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
@@ -69,7 +79,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
     const long long gw = (long long)blockIdx.x * 4 + warp;
     uint32_t *dir = dir_all + gw * dir_words_per_warp;
     const __half2 neg2 = VM_H2C(VM_FB_NEG), zero2 = VM_H2C(0);
-    const __half2 open1 = VM_H2C(-(g.q1 + g.e1)), open2 = VM_H2C(-(g.q2 + g.e2));
+    const __half2 open1 = VM_H2C(-(g.q1 + g.e1)), open2 = VM_H2C(-(g.q2 + g.e2)), ext2 = VM_H2C(-g.e2);
     for (;;) {
         int p = 0;
         if (lane == 0) p = pair_begin + atomicAdd(counter, 1);
@@ -98,15 +108,10 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             // the row's first cell is in column 0 (real boundary) or on the band's lower edge (nothing to its left)
             row[c] = t;
             tc[c] = vm_h2(t < tlen ? sT[t] : 0x7fff7fffu);
-            if (t + kmin <= 0) {
-                u[c] = vm_h2i(vm_hb(t + 1) - vm_hb(t));
-                y1[c] = open1;
-                y2[c] = open2;
-            } else {
-                u[c] = zero2;
-                y1[c] = neg2;
-                y2[c] = neg2;
-            }
+            const bool edge = t + kmin > 0;
+            u[c] = edge ? zero2 : vm_boundary_step(t);
+            y1[c] = edge ? neg2 : open1;
+            y2[c] = edge ? neg2 : open2;
         };
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -130,7 +135,17 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             unsigned d[C];
 #pragma unroll
             for (int c = C - 1; c >= 0; --c) {
-                if (row[c] < tlo) init_row(c, row[c] + 32 * C);
+                if (row[c] < tlo) {
+                    // the slot moves on to the row one period further down; its first cell is on the band's lower edge,
+                    // or (bands reaching far below the main diagonal) in column 0, more than 20 rows down the boundary
+                    const int t = row[c] + 32 * C;
+                    row[c] = t;
+                    tc[c] = vm_h2(t < tlen ? sT[t] : 0x7fff7fffu);
+                    const bool edge = t + kmin > 0;
+                    u[c] = edge ? zero2 : ext2;
+                    y1[c] = edge ? neg2 : open1;
+                    y2[c] = edge ? neg2 : open2;
+                }
                 const int t = row[c];
                 d[c] = 0u;
                 if (t <= thi) {
@@ -138,8 +153,8 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
                     __half2 cv, cx1, cx2;
                     if (c > 0) { cv = v[c - 1]; cx1 = x1[c - 1]; cx2 = x2[c - 1]; }
                     else { cv = inV; cx1 = inX1; cx2 = inX2; }
-                    if (t == 0) {                          // real boundary row
-                        cv = vm_h2i(vm_hb(j + 1) - vm_hb(j));
+                    if (c == 0 && t == 0) {                // real boundary row (row 0 lives in lane 0, slot 0)
+                        cv = vm_boundary_step(j);
                         cx1 = open1;
                         cx2 = open2;
                     }
@@ -306,77 +321,122 @@ bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax)
     const int mn = tlen < qlen ? tlen : qlen, mx = tlen > qlen ? tlen : qlen;
     if (mn < 96 || mx > VM_FB_CAP) return false;
     const int D = qlen - tlen;
-    int w = (int)(0.17 * mn) + 6;
+    // a read at ~10 % error scores ~1.3 per base, a path leaving the band at most 2 (mn - w) - 2 (24 + w): this w
+    // leaves ~0.15 per base of margin; the planner then widens the band to the capacity of its slot class
+    int w = (int)(0.2125 * mn) - 12;
     if (w < 24) w = 24;
     kmin = (D < 0 ? D : 0) - w;
     kmax = (D > 0 ? D : 0) + w;
     return ((kmax - kmin) / 2 + 1 + 31) / 32 <= VM_FB_MAXC;
 }
 
-// Pairs of jobs with (nearly) the same band: class key (slots C, D / 16), ordered by query length inside a class.
-void vm_fillb_plan(const VmAlnJobDev *J, const int *ids, int n_ids, int sm_count, VmFillBandPlan &plan)
+// Pairs of jobs with (nearly) the same band.  Jobs are bucketed by (slots C of their own band, D / 8, qlen / 4) with a
+// parallel stable counting sort, neighbours in that order share a warp; a pair's band is the union of its jobs'
+// bands, widened to the capacity of its slot class.  full_mask[j] is cleared for every job planned here.
+void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads, VmFillBandPlan &plan, uint8_t *full_mask)
 {
     plan.pairs.clear();
     plan.launches.clear();
     plan.dir_words = 0;
-    struct Key { int c, dbucket, ql, id, kmin, kmax; };
-    std::vector<Key> keys;
-    keys.reserve((size_t)n_ids);
-    for (int x = 0; x < n_ids; ++x) {
-        const int j = ids[x];
-        Key k;
-        vm_fillb_own_band(J[j].t.len, J[j].q.len, k.kmin, k.kmax);
-        k.c = ((k.kmax - k.kmin) / 2 + 1 + 31) / 32;
-        k.dbucket = (J[j].q.len - J[j].t.len + 4096) >> 3;
-        k.ql = J[j].q.len;
-        k.id = j;
-        keys.push_back(k);
-    }
-    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
-        if (a.c != b.c) return a.c < b.c;
-        if (a.dbucket != b.dbucket) return a.dbucket < b.dbucket;
-        if (a.ql != b.ql) return a.ql < b.ql;
-        return a.id < b.id;
-    });
-    // pair neighbours; a pair's band is the union of its jobs' bands, which may need one slot more
-    std::vector<std::vector<VmFillBandPair>> by_c(VM_FB_MAXC + 2);
-    std::vector<int> max_steps(VM_FB_MAXC + 2, 0);
-    size_t x = 0;
-    while (x < keys.size()) {
-        VmFillBandPair pr;
-        pr.a = keys[x].id;
-        pr.b = -1;
-        pr.kmin = keys[x].kmin;
-        pr.kmax = keys[x].kmax;
-        int steps = J[pr.a].t.len + J[pr.a].q.len;
-        size_t used = 1;
-        if (x + 1 < keys.size() && keys[x + 1].c == keys[x].c) {
-            const int kmin = std::min(pr.kmin, keys[x + 1].kmin), kmax = std::max(pr.kmax, keys[x + 1].kmax);
-            if (((kmax - kmin) / 2 + 1 + 31) / 32 <= VM_FB_MAXC) {
-                pr.b = keys[x + 1].id;
-                pr.kmin = kmin;
-                pr.kmax = kmax;
-                steps = std::max(J[pr.a].t.len, J[pr.b].t.len) + std::max(J[pr.a].q.len, J[pr.b].q.len);
-                used = 2;
-            }
+    constexpr int ND = 256, NQ = VM_FB_CAP / 8 + 1, NKEY = VM_FB_MAXC * ND * NQ;     // D / 8 in [-128, 128) covers |D| < 1024
+    const int T = std::max(1, std::min(std::min(host_threads, 8), nj / 8192 + 1));
+    std::vector<int32_t> keys((size_t)nj);
+    std::vector<std::vector<int32_t>> hist((size_t)T, std::vector<int32_t>((size_t)NKEY, 0));
+    auto slice = [&](int t, int &lo, int &hi) { lo = (int)((long long)nj * t / T); hi = (int)((long long)nj * (t + 1) / T); };
+    vmp::parallel_for(T, T, [&](int64_t t) {
+        int lo, hi;
+        slice((int)t, lo, hi);
+        std::vector<int32_t> &h = hist[(size_t)t];
+        for (int j = lo; j < hi; ++j) {
+            int kmin, kmax;
+            keys[j] = -1;
+            if (J[j].t.len <= 0 || J[j].q.len <= 0 || !vm_fillb_own_band(J[j].t.len, J[j].q.len, kmin, kmax)) continue;
+            const int c = ((kmax - kmin) / 2 + 1 + 31) / 32;
+            int db = ((J[j].q.len - J[j].t.len) >> 3) + ND / 2;
+            db = db < 0 ? 0 : db >= ND ? ND - 1 : db;
+            keys[j] = ((c - 1) * ND + db) * NQ + (J[j].q.len >> 3);
+            ++h[(size_t)keys[j]];
+            full_mask[j] = 0;
         }
-        const int rows = (pr.kmax - pr.kmin) / 2 + 1;
-        const int c = (rows + 31) / 32;
-        // widen the band to the capacity of its slot class: free rows, more margin for the certificate
-        const int spare = 32 * c - rows;
-        pr.kmin -= spare;
-        pr.kmax += spare;
-        by_c[(size_t)c].push_back(pr);
-        max_steps[(size_t)c] = std::max(max_steps[(size_t)c], steps);
-        x += used;
+    }, 1);
+    int32_t n_live = 0;
+    int32_t class_lo[VM_FB_MAXC + 2];
+    for (int k = 0; k < NKEY; ++k) {
+        if (k % (ND * NQ) == 0) class_lo[k / (ND * NQ) + 1] = n_live;     // first position of slot class c = k / (ND NQ) + 1
+        for (int t = 0; t < T; ++t) {
+            const int32_t cnt = hist[(size_t)t][(size_t)k];
+            hist[(size_t)t][(size_t)k] = n_live;
+            n_live += cnt;
+        }
+    }
+    class_lo[VM_FB_MAXC + 1] = n_live;
+    std::vector<int32_t> order((size_t)n_live);
+    vmp::parallel_for(T, T, [&](int64_t t) {
+        int lo, hi;
+        slice((int)t, lo, hi);
+        std::vector<int32_t> &pos = hist[(size_t)t];
+        for (int j = lo; j < hi; ++j)
+            if (keys[j] >= 0) order[(size_t)pos[(size_t)keys[j]]++] = j;
+    }, 1);
+    // neighbours of the same slot class share a warp (the widest class runs its jobs alone: a union could need a
+    // ninth slot); every pair is built independently, then bucketed by the slot class of its union
+    struct Tmp { VmFillBandPair pr; int c, steps; };
+    std::vector<int64_t> pair_lo(VM_FB_MAXC + 2, 0);
+    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+        const int64_t n = class_lo[c + 1] - class_lo[c];
+        pair_lo[c + 1] = pair_lo[c] + (c < VM_FB_MAXC ? (n + 1) / 2 : n);
+    }
+    std::vector<Tmp> tmp((size_t)pair_lo[VM_FB_MAXC + 1]);
+    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+        const int64_t np = pair_lo[c + 1] - pair_lo[c];
+        const int lo = class_lo[c], hi = class_lo[c + 1];
+        const bool alone = c == VM_FB_MAXC;
+        vmp::parallel_for(np, host_threads, [&](int64_t p) {
+            Tmp &t = tmp[(size_t)(pair_lo[c] + p)];
+            const int xa = alone ? lo + (int)p : lo + 2 * (int)p, xb = alone ? hi : xa + 1;
+            VmFillBandPair &pr = t.pr;
+            pr.a = order[(size_t)xa];
+            pr.b = xb < hi ? order[(size_t)xb] : -1;
+            vm_fillb_own_band(J[pr.a].t.len, J[pr.a].q.len, pr.kmin, pr.kmax);
+            t.steps = J[pr.a].t.len + J[pr.a].q.len;
+            if (pr.b >= 0) {
+                int bmin, bmax;
+                vm_fillb_own_band(J[pr.b].t.len, J[pr.b].q.len, bmin, bmax);
+                pr.kmin = std::min(pr.kmin, bmin);
+                pr.kmax = std::max(pr.kmax, bmax);
+                t.steps = std::max(J[pr.a].t.len, J[pr.b].t.len) + std::max(J[pr.a].q.len, J[pr.b].q.len);
+            }
+            const int rows = (pr.kmax - pr.kmin) / 2 + 1;
+            t.c = (rows + 31) / 32;
+            if (t.c > VM_FB_MAXC) {          // cannot happen for neighbours of one bucket; if it does, the full-matrix kernel takes them
+                full_mask[pr.a] = 1;
+                if (pr.b >= 0) full_mask[pr.b] = 1;
+                t.c = 0;
+                return;
+            }
+            // widen the band to the capacity of its slot class: free rows, more margin for the certificate
+            const int spare = 32 * t.c - rows;
+            pr.kmin -= spare;
+            pr.kmax += spare;
+        }, 4096);
+    }
+    std::vector<int64_t> cnt(VM_FB_MAXC + 2, 0), at(VM_FB_MAXC + 2, 0);
+    std::vector<int> max_steps(VM_FB_MAXC + 2, 0);
+    for (const Tmp &t : tmp) { ++cnt[(size_t)t.c]; max_steps[(size_t)t.c] = std::max(max_steps[(size_t)t.c], t.steps); }
+    cnt[0] = 0;
+    for (int c = 1; c <= VM_FB_MAXC; ++c) at[c + 1] = at[c] + cnt[c];
+    plan.pairs.resize((size_t)at[VM_FB_MAXC + 1]);
+    {
+        std::vector<int64_t> pos(at);
+        for (const Tmp &t : tmp)
+            if (t.c > 0) plan.pairs[(size_t)pos[(size_t)t.c]++] = t.pr;
     }
     for (int c = 1; c <= VM_FB_MAXC; ++c) {
-        if (by_c[(size_t)c].empty()) continue;
+        if (cnt[c] == 0) continue;
         VmFillBandLaunch L;
         L.C = c;
-        L.pair_begin = (int)plan.pairs.size();
-        plan.pairs.insert(plan.pairs.end(), by_c[(size_t)c].begin(), by_c[(size_t)c].end());
-        L.pair_end = (int)plan.pairs.size();
+        L.pair_begin = (int)at[c];
+        L.pair_end = (int)at[c + 1];
         L.dir_words_per_warp = (long long)max_steps[(size_t)c] * ((c + 1) / 2) * 32;
         const int n_pairs = L.pair_end - L.pair_begin;
         L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fillb_blocks_per_sm(c)));

@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <cmath>
+#include <ctime>
 #include <chrono>
 #include <functional>
 #include <thread>
@@ -131,12 +132,20 @@ public:
 
     // optional wall-clock accounting of the host glue phases (name, milliseconds)
     std::function<void(const char *, double)> on_time;
+    static double process_cpu_ms()
+    {
+        timespec ts;
+        clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts);
+        return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+    }
+    std::function<void(const char *, double)> on_cpu;     // (phase, process CPU milliseconds burnt during it)
     struct Phase {
-        Driver *d; const char *name; std::chrono::steady_clock::time_point t0;
-        Phase(Driver *d_, const char *n) : d(d_), name(n), t0(std::chrono::steady_clock::now()) {}
+        Driver *d; const char *name; std::chrono::steady_clock::time_point t0; double c0;
+        Phase(Driver *d_, const char *n) : d(d_), name(n), t0(std::chrono::steady_clock::now()), c0(process_cpu_ms()) {}
         ~Phase()
         {
             if (d->on_time) d->on_time(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            if (d->on_cpu) d->on_cpu(name, process_cpu_ms() - c0);
         }
     };
 
