@@ -6,7 +6,7 @@ timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --reads 2000 --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-bash tests/gpu/ncu_full.sh fill vm_fill_kernel 12
+bash tests/gpu/ncu_full.sh fill "vm_fillb_kernel|vm_fill_kernel" 14
 bash tests/gpu/ncu_full.sh edupper vm_ed_upper_kernel 1
 bash tests/gpu/ncu_full.sh reseed "vm_reseed" 2
 bash tests/gpu/ncu_full.sh chain "vm_chain_exact" 3

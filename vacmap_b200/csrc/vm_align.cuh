@@ -92,9 +92,14 @@ void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFill
 // counters_dev: one zeroed int per launch.  The CIGAR ops of job j end up in dense_out[results[j].x .. + results[j].y)
 // (results: uint2 per job, zero-initialised by the caller; dense_count: zeroed 64-bit bump allocator;
 // cigar_scratch: per-job room of tlen + qlen + 2 ops at J.out_off).  Returns the number of kernel launches.
+// Launches of fewer than VM_FILL_SMALL_BLOCKS blocks go round-robin (*side_rr) to the `side` streams (the caller
+// orders them against main_stream with events); *dir_cursor / *band_cursor: words of the scratch arenas already
+// handed to earlier launches (every launch gets its own slice).
+#define VM_FILL_SMALL_BLOCKS 64
 int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs_dev, const VmFillPair *pairs_dev, VmSeqSources src, int eqx,
                    uint32_t *dir_scratch, uint32_t *band_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
-                   unsigned long long *dense_count, void *results, cudaStream_t stream);
+                   unsigned long long *dense_count, void *results, cudaStream_t main_stream, const cudaStream_t *side, int n_side,
+                   int *side_rr, size_t *dir_cursor, size_t *band_cursor);
 
 // ---- banded global fill with an optimality certificate (vm_fillb.cu) ----
 #define VM_FB_MAXC 8
@@ -116,4 +121,5 @@ void vm_fillb_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, int h
 // as vm_fill_launch; a job whose certificate fails gets results[j] = (0xffffffff, 0) and must be re-run unbanded
 int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs_dev, const VmFillBandPair *pairs_dev, VmSeqSources src, int eqx,
                     uint32_t *dir_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
-                    unsigned long long *dense_count, void *results, cudaStream_t stream);
+                    unsigned long long *dense_count, void *results, cudaStream_t main_stream, const cudaStream_t *side, int n_side,
+                    int *side_rr, size_t *dir_cursor);

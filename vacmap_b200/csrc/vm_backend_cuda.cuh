@@ -104,6 +104,11 @@ public:
     CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih) {}
     ~CudaBackend() override
     {
+        for (int i = 0; i < 3; ++i) {
+            if (side_[i]) cudaStreamDestroy(side_[i]);
+            if (side_done_[i]) cudaEventDestroy(side_done_[i]);
+        }
+        if (side_go_) cudaEventDestroy(side_go_);
         seed_.release();
         gx_.release();
         lx_.release();
@@ -523,6 +528,28 @@ public:
         extract(false, n, dense, xids, 0.0, lx_, out);
     }
 
+    // side streams of this backend (created on first use), ordered against the main stream with events
+    static const int kSide = 3;
+    void side_fork()
+    {
+        if (!side_[0]) {
+            for (int i = 0; i < kSide; ++i) {
+                BE_OK(cudaStreamCreateWithFlags(&side_[i], cudaStreamNonBlocking));
+                BE_OK(cudaEventCreateWithFlags(&side_done_[i], cudaEventDisableTiming));
+            }
+            BE_OK(cudaEventCreateWithFlags(&side_go_, cudaEventDisableTiming));
+        }
+        BE_OK(cudaEventRecord(side_go_, c_->stream));
+        for (int i = 0; i < kSide; ++i) BE_OK(cudaStreamWaitEvent(side_[i], side_go_, 0));
+    }
+    void side_join()
+    {
+        for (int i = 0; i < kSide; ++i) {
+            BE_OK(cudaEventRecord(side_done_[i], side_[i]));
+            BE_OK(cudaStreamWaitEvent(c_->stream, side_done_[i], 0));
+        }
+    }
+
     static VmSeqSpec spec(const vmg::SeqRef &s)
     {
         VmSeqSpec d;
@@ -727,7 +754,7 @@ public:
             vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());
         }
         const size_t n_launch = plan_.launches.size() + bplan_.launches.size();
-        BE_OK(d_dir_.ensure(std::max(plan_.dir_words, bplan_.dir_words) * 4 + 64));
+        BE_OK(d_dir_.ensure((plan_.dir_words + bplan_.dir_words) * 4 + 64));
         BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
         BE_OK(d_cig_.ensure((size_t)out_off * 4 + 64));
         BE_OK(d_cigd_.ensure((size_t)out_off * 4 + 64));
@@ -751,14 +778,18 @@ public:
         uint32_t *h_res = (uint32_t *)(h_count + 1);
         {
             KTimer kt(this, "k_fill");
-            // the direction scratch is shared: the banded launches run first, the full-matrix ones after them on the
-            // same stream
+            // launches that fill the device run on the worker's stream, the small ones (rare job classes, one warp's
+            // latency deep) beside them on side streams: fork after the uploads, join before the read-back
+            side_fork();
+            int rr = 0;
+            size_t dir_cur = 0, band_cur = 0;
             c_->launches += vm_fillb_launch(bplan_, jobs_.as<VmAlnJobDev>(), d_bpairs, sources(), eqx ? 1 : 0, d_dir_.as<uint32_t>(),
                                             d_ctr + plan_.launches.size(), d_cig_.as<uint32_t>(), d_cigd_.as<uint32_t>(), d_count,
-                                            d_seg_.p, c_->stream);
+                                            d_seg_.p, c_->stream, side_, kSide, &rr, &dir_cur);
             c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
                                            d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr, d_cig_.as<uint32_t>(),
-                                           d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
+                                           d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream, side_, kSide, &rr, &dir_cur, &band_cur);
+            side_join();
             kt.stop();
         }
         if (!bplan_.pairs.empty()) {
@@ -787,9 +818,11 @@ public:
                 BE_OK(cudaMemcpyAsync(d_nh_.p, d_count, 8, cudaMemcpyDeviceToDevice, c_->stream));   // the counter moves with us
                 d_count = d_nh_.as<unsigned long long>();
                 KTimer kt(this, "k_fill");
+                int rr = 0;
+                size_t dir_cur = 0, band_cur = 0;
                 c_->launches += vm_fill_launch(plan_, jobs_.as<VmAlnJobDev>(), d_pairs_.as<VmFillPair>(), sources(), eqx ? 1 : 0,
                                                d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr2, d_cig_.as<uint32_t>(),
-                                               d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream);
+                                               d_cigd_.as<uint32_t>(), d_count, d_seg_.p, c_->stream, nullptr, 0, &rr, &dir_cur, &band_cur);
                 kt.stop();
             }
         }
@@ -818,6 +851,8 @@ private:
         d_dense_, d_seg_, d_dir_, d_sc_, d_cig_, d_cigd_, d_pairs_, d_msegs_;
     VmFillPlan plan_;
     VmFillBandPlan bplan_;
+    cudaStream_t side_[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t side_done_[3] = {nullptr, nullptr, nullptr}, side_go_ = nullptr;
     Extracted gx_, lx_;
     VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;

@@ -336,20 +336,29 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, 
         const long long fit = (long long)(mem_cap_words / (size_t)(4 * L.dir_words_per_warp));
         blocks = std::max<long long>(1, std::min(blocks, std::max<long long>(fit, 1)));
         L.blocks = (int)blocks;
-        plan.dir_words = std::max(plan.dir_words, (size_t)(blocks * 4 * L.dir_words_per_warp));
-        plan.band_words = std::max(plan.band_words, (size_t)(blocks * 4 * L.band_words_per_warp));
+        plan.dir_words += (size_t)(blocks * 4 * L.dir_words_per_warp);          // every launch has its own slice
+        plan.band_words += (size_t)(blocks * 4 * L.band_words_per_warp);
         plan.launches.push_back(L);
     }
 }
 
 int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs, const VmFillPair *pairs, VmSeqSources src, int eqx, uint32_t *dir,
                    uint32_t *band, int *counters, uint32_t *cigar_out, uint32_t *dense_out, unsigned long long *dense_count,
-                   void *results, cudaStream_t stream)
+                   void *results, cudaStream_t main_stream, const cudaStream_t *side, int n_side, int *side_rr, size_t *dir_cursor,
+                   size_t *band_cursor)
 {
     int n = 0;
+    uint32_t *const dir0 = dir, *const band0 = band;
     for (size_t li = 0; li < plan.launches.size(); ++li) {
         const VmFillLaunch &L = plan.launches[li];
         int *ctr = counters + li;
+        // see vm_fillb_launch: small launches on side streams, one scratch slice per launch
+        const bool small = n_side > 0 && L.blocks < VM_FILL_SMALL_BLOCKS;
+        cudaStream_t stream = small ? side[(*side_rr)++ % n_side] : main_stream;
+        dir = dir0 + *dir_cursor;
+        band = band0 + *band_cursor;
+        *dir_cursor += (size_t)L.blocks * 4 * (size_t)L.dir_words_per_warp;
+        *band_cursor += (size_t)L.blocks * 4 * (size_t)L.band_words_per_warp;
 #define VM_FILL_GO(RR, MBB)                                                                                           \
     vm_fill_kernel<RR, MBB><<<L.blocks, 128, 0, stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir,       \
                                                            L.dir_words_per_warp, band, L.band_words_per_warp, ctr, cigar_out,      \

@@ -440,19 +440,27 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
         L.dir_words_per_warp = (long long)max_steps[(size_t)c] * ((c + 1) / 2) * 32;
         const int n_pairs = L.pair_end - L.pair_begin;
         L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
-        plan.dir_words = std::max(plan.dir_words, (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp));
+        plan.dir_words += (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp);      // every launch has its own slice
         plan.launches.push_back(L);
     }
 }
 
 int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs, const VmFillBandPair *pairs, VmSeqSources src, int eqx, uint32_t *dir,
                     int *counters, uint32_t *cigar_scratch, uint32_t *dense_out, unsigned long long *dense_count, void *results,
-                    cudaStream_t stream)
+                    cudaStream_t main_stream, const cudaStream_t *side, int n_side, int *side_rr, size_t *dir_cursor)
 {
     int n = 0;
     for (size_t li = 0; li < plan.launches.size(); ++li) {
         const VmFillBandLaunch &L = plan.launches[li];
         int *ctr = counters + li;
+        // launches of a few blocks (rare job classes) are one warp's latency deep: they go to side streams, beside
+        // the launches that fill the device; every launch gets its own slice of the direction scratch
+        const bool small = n_side > 0 && L.blocks < VM_FILL_SMALL_BLOCKS;
+        cudaStream_t stream = small ? side[(*side_rr)++ % n_side] : main_stream;
+        uint32_t *dir_l = dir + *dir_cursor;
+        *dir_cursor += (size_t)L.blocks * 4 * (size_t)L.dir_words_per_warp;
+        uint32_t *dir_save = dir;
+        dir = dir_l;
 #define VM_FILLB_GO(CC)                                                                                                  \
     vm_fillb_kernel<CC><<<L.blocks, 128, vm_fillb_smem<CC>(), stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir, \
                                                                         L.dir_words_per_warp, ctr, cigar_scratch, dense_out, \
@@ -468,6 +476,7 @@ int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs, const VmFillB
         default: VM_FILLB_GO(8); break;
         }
 #undef VM_FILLB_GO
+        dir = dir_save;
         ++n;
     }
     return n;
