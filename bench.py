@@ -164,7 +164,8 @@ def run_reference(args):
 
 
 KERNEL_BYTES_NOTE = {
-    "k_fill": "B = sum(q+t) sequence bytes + q*t direction bytes (written once; the traceback re-reads only the path) + 4 B per CIGAR op",
+    "k_fill": "B = sum(q+t) sequence bytes + the direction bytes of the cells inside the certified band (n_fill_dir_bytes: one "
+              "128-byte line per step and direction word, written once; the traceback re-reads only the path) + 4 B per CIGAR op",
     "k_ed_upper": "B = sum(q+t) sequence bytes (every base is read once, by the gap DP or by the anchor check)",
     "k_seed": "B = read bytes + 16 B per anchor out",
     "k_edit_distance": "B = sum(q+t) sequence bytes (bit-vector state stays in registers/SMEM)",
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workers", type=int, default=0, help="sub-batches in flight per GPU (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="reads per sub-batch (0 = automatic)")
+    ap.add_argument("--ahead", type=int, default=2, help="steps submitted ahead of the one being collected")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -235,21 +237,26 @@ def main():
     aligned = 0
     t0 = time.perf_counter()
     cpu0 = time.process_time()
-    # steps are submitted one ahead (vm_align_submit / vm_align_wait): while step s drains, step s + 1 is already
-    # seeding, as a stream of super-batches would; every step's work completes inside the timed region
-    pending = None
+    # steps are submitted ahead of their collection (vm_align_submit / vm_align_wait, `--ahead` jobs in flight): while
+    # step s drains, the next ones are already seeding, as a stream of super-batches would; every step's work
+    # completes inside the timed region
+    from collections import deque
+    inflight = deque()
+
+    def collect():
+        nonlocal aligned, rec_off, recs, cig
+        rec_off, recs, cig = al.wait(inflight.popleft())
+        for k, v in al.last_stage_ms.items():
+            stage[k] = stage.get(k, 0.0) + v
+        aligned += int(np.diff(off)[np.diff(rec_off) > 0].sum())
+
+    rec_off = recs = cig = None
     for _ in range(args.steps):
-        nxt = al.submit_packed(cat, off, resident=True)
-        if pending is not None:
-            rec_off, recs, cig = al.wait(pending)
-            for k, v in al.last_stage_ms.items():
-                stage[k] = stage.get(k, 0.0) + v
-            aligned += int(np.diff(off)[np.diff(rec_off) > 0].sum())
-        pending = nxt
-    rec_off, recs, cig = al.wait(pending)
-    for k, v in al.last_stage_ms.items():
-        stage[k] = stage.get(k, 0.0) + v
-    aligned += int(np.diff(off)[np.diff(rec_off) > 0].sum())
+        inflight.append(al.submit_packed(cat, off, resident=True))
+        if len(inflight) > args.ahead:
+            collect()
+    while inflight:
+        collect()
     barrier()
     wall = time.perf_counter() - t0
     cpu_busy = (time.process_time() - cpu0) / max(wall, 1e-9)      # host cores kept busy by this rank
@@ -262,15 +269,14 @@ def main():
     barrier()
     t0 = time.perf_counter()
     aligned_e2e = 0
-    pending = None
     for _ in range(args.steps):
-        nxt = al.submit_packed(cat, off)                 # host reads in ...
-        if pending is not None:
-            rec_off, recs, cig = al.wait(pending)        # ... host records out
+        inflight.append(al.submit_packed(cat, off))      # host reads in ...
+        if len(inflight) > args.ahead:
+            rec_off, recs, cig = al.wait(inflight.popleft())     # ... host records out
             aligned_e2e += int(np.diff(off)[np.diff(rec_off) > 0].sum())
-        pending = nxt
-    rec_off, recs, cig = al.wait(pending)
-    aligned_e2e += int(np.diff(off)[np.diff(rec_off) > 0].sum())
+    while inflight:
+        rec_off, recs, cig = al.wait(inflight.popleft())
+        aligned_e2e += int(np.diff(off)[np.diff(rec_off) > 0].sum())
     barrier()
     e2e_wall = time.perf_counter() - t0
     d2h = recs.nbytes + cig.nbytes + rec_off.nbytes
@@ -308,10 +314,10 @@ def main():
         per_step = {k: v / args.steps for k, v in stage.items()}
         kern = {k: v for k, v in solo.items() if k.startswith("k_") or k.endswith("_kernels")}
         top = max(kern, key=kern.get) if kern else None
-        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_fill_band_jobs", "n_fill_band_redo",
+        counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_fill_band_jobs", "n_fill_band_redo", "n_fill_dir_bytes",
                                                       "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors")}
         n_ops = float(len(cig))
-        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_cells"] + 4.0 * n_ops,
+        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_dir_bytes"] + 4.0 * n_ops,
                      "k_edit_distance": 2.0 * bases, "k_ed_upper": 2.0 * bases,
                      "k_reseed_hits": 2.0 * bases + 8.0 * counts["n_reseed_hits"],
                      "k_reseed_merge": 8.0 * counts["n_reseed_hits"] + 16.0 * counts["n_reseed_hits"] / 4,
@@ -333,9 +339,9 @@ def main():
                     "timing": "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
                               "'launch' = the kernel's launches of one step (one per capacity class)",
                     "bytes": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
-                    "gcups": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
+                    "gcups_full_matrix_equivalent": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
                     "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
-                    "note": "integer DP wavefront: bound by the ALU pipe (ncu: ~80 % ALU, ~30 % DRAM), not by HBM "
+                    "note": "integer DP wavefront: issue / ALU-pipe bound (ncu: issue 72 %, ALU 61 %, DRAM 11 %), not HBM bound "
                             "(SURVEY 8d); the HBM fraction is reported because north_star asks for it"}
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
@@ -345,8 +351,8 @@ def main():
                            "l2": "per-step working set (reads 2x%.0f MB + anchors, hits, direction matrices >1 GB) exceeds "
                                  "the 126 MB L2" % (bases / 1e6),
                            "sharding": "reads split across ranks, index replicated per GPU, records gathered on rank 0",
-                           "pipelining": "steps submitted one ahead (vm_align_submit / vm_align_wait), all K steps complete inside "
-                                         "the timed region"},
+                           "pipelining": "steps submitted %d ahead of their collection (vm_align_submit / vm_align_wait), all K "
+                                         "steps complete inside the timed region" % args.ahead},
                 "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": len(cat) + off.nbytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "host_cores_busy": round(cpu_busy, 2), "host_cores": os.cpu_count(),
                 "records_per_step": nrec_all, "gather_ms": round(gather_ms, 2),

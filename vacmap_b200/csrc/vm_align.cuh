@@ -84,7 +84,8 @@ struct VmFillLaunch {
 struct VmFillPlan {
     std::vector<VmFillPair> pairs;
     std::vector<VmFillLaunch> launches;
-    size_t dir_words = 0, band_words = 0;   // scratch needed (uint32 words), shared by the launches
+    size_t dir_words = 0, band_words = 0;   // scratch needed (uint32 words), one slice per launch
+    double dir_bytes = 0;                   // direction bytes the launches will store (the kernel's dominant traffic)
 };
 // only_mask != nullptr: plan only the jobs j with only_mask[j] != 0
 void vm_fill_plan(const VmAlnJobDev *jobs_host, int n_jobs, int sm_count, VmFillPlan &plan, int host_threads = 1,
@@ -113,6 +114,7 @@ struct VmFillBandPlan {
     std::vector<VmFillBandPair> pairs;
     std::vector<VmFillBandLaunch> launches;
     size_t dir_words = 0;
+    double dir_bytes = 0;                   // direction bytes the launches will store
 };
 // false: the job is left to the full-matrix kernel (too small to gain, or too long for the staging)
 bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax);

@@ -29,7 +29,7 @@ int vm_ctx_create(int device, vm_ctx **out)
         delete c;
         return VM_ERR_CUDA;
     }
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventCreateWithFlags(&c->ev[i], cudaEventBlockingSync);
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
     return VM_OK;
@@ -39,7 +39,7 @@ void vm_ctx_destroy(vm_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    vm_stream_sync(c->stream);
     if (c->pool && c->pool_free) c->pool_free(c->pool);
     c->pool = nullptr;
     for (vm_ctx *k : c->kids) vm_ctx_destroy(k);
@@ -74,7 +74,7 @@ int vm_set_tables(vm_ctx *c, const float *extra, int64_t n_extra, const float *r
                                   cudaMemcpyHostToDevice, c->stream));
     VM_CUDA_OK(c, cudaMemcpyAsync(c->log2cache.p, log2cache, n_log2cache * sizeof(double),
                                   cudaMemcpyHostToDevice, c->stream));
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, vm_stream_sync(c->stream));
     c->n_extra = n_extra;
     c->n_readgapcost = n_readgapcost;
     c->n_log2cache = n_log2cache;
@@ -149,7 +149,7 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
         A.n_rg = (int)rg.size();
     }
     // the staging vectors above are pageable: make sure the copies are done before they go away
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, vm_stream_sync(c->stream));
     A.anchors = s.sorted.as<VmAnchor>();
     A.off = s.off_dev.as<int64_t>();
     A.cnt = s.cnt_dev.as<int32_t>();
@@ -240,7 +240,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     if (may_bail) {
         s.gmax_host.resize(cnt.size());
         VM_CUDA_OK(c, cudaMemcpyAsync(s.gmax_host.data(), s.gmax.p, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        VM_CUDA_OK(c, vm_stream_sync(c->stream));
         for (int t = 0; t < n_exact; ++t)
             if (s.gmax_host[ids_host[t]] < 0) fast_ids.push_back(ids_host[t]);
     }
@@ -258,10 +258,10 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         VM_CUDA_OK(c, cudaMemcpyAsync(fids_dev, fast_ids.data(), fast_ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->launches += vm_launch_chain_fast(prm.variant, A, prm.fast_t, fids_dev, (int)fast_ids.size(),
                                             s.fast_scratch.as<long long>(), s.fast_off.as<int64_t>(), c->stream);
-        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));   // soff / fast_ids are stack-lifetime staging
+        VM_CUDA_OK(c, vm_stream_sync(c->stream));   // soff / fast_ids are stack-lifetime staging
     }
     VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, vm_stream_sync(c->stream));
     VM_CUDA_OK(c, cudaGetLastError());
     if (ms4) {
         ms4[0] = 0;
@@ -291,7 +291,7 @@ int vm_chain_prepare(vm_ctx *c, int64_t n_reads, int64_t span, const std::vector
         VM_CUDA_OK(c, cudaMemcpyAsync(s.off_dev.p, start.data(), (size_t)n_reads * 8, cudaMemcpyHostToDevice, c->stream));
         VM_CUDA_OK(c, cudaMemcpyAsync(s.cnt_dev.p, cnt.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, c->stream));
         VM_CUDA_OK(c, cudaMemsetAsync(s.gmax.p, 0xff, (size_t)n_reads * 8, c->stream));   // -1: not chained
-        VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        VM_CUDA_OK(c, vm_stream_sync(c->stream));
     }
     return VM_OK;
 }
@@ -333,7 +333,7 @@ int vm_chain_global_upload(vm_ctx *c, const vm_chain_params *prm, int64_t n_read
     if (rc != VM_OK) return rc;
     if (s.total > 0)
         VM_CUDA_OK(c, cudaMemcpyAsync(s.rows.p, anchors, (size_t)s.total * 32, cudaMemcpyHostToDevice, c->stream));
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, vm_stream_sync(c->stream));
     s.loaded = true;
     return VM_OK;
 }
@@ -382,7 +382,7 @@ int vm_chain_global_download(vm_ctx *c, int64_t *sorted, double *S, int32_t *P, 
     }
     if (g_max_index && s.n_reads > 0)
         VM_CUDA_OK(c, cudaMemcpyAsync(g_max_index, s.gmax.p, (size_t)s.n_reads * 8, cudaMemcpyDeviceToHost, c->stream));
-    VM_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    VM_CUDA_OK(c, vm_stream_sync(c->stream));
     if (used_fast && s.n_reads > 0) memcpy(used_fast, s.used_fast.data(), (size_t)s.n_reads * 4);
     return VM_OK;
 }

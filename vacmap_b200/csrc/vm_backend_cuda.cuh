@@ -125,11 +125,11 @@ public:
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
     double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0, fill_band_jobs_ = 0,
-           fill_band_redo_ = 0;
+           fill_band_redo_ = 0, fill_dir_bytes_ = 0;
     void reset_counters()
     {
         timer.ms.clear();
-        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = fill_band_jobs_ = fill_band_redo_ = 0;
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = fill_band_jobs_ = fill_band_redo_ = fill_dir_bytes_ = 0;
     }
 
     // device time of a group of launches, CUDA events on the ctx stream
@@ -137,7 +137,7 @@ public:
         CudaBackend *be; const char *name; cudaEvent_t a, b; std::chrono::steady_clock::time_point w0;
         KTimer(CudaBackend *be_, const char *n) : be(be_), name(n), w0(std::chrono::steady_clock::now())
         {
-            cudaEventCreate(&a); cudaEventCreate(&b);
+            cudaEventCreateWithFlags(&a, cudaEventBlockingSync); cudaEventCreateWithFlags(&b, cudaEventBlockingSync);
             cudaEventRecord(a, be->c_->stream);
         }
         void stop()
@@ -193,7 +193,7 @@ public:
                                                                                       (int)b.n, (int64_t)total, reads_rc_.as<uint8_t>());
             c_->launches += 1;
         }
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
     }
 
     // reads [r0, r0 + n) of a batch another backend of this device already holds in HBM (device-to-device)
@@ -209,7 +209,7 @@ public:
         BE_OK(cudaMemcpyAsync(reads_fwd_.p, src.reads_fwd_.as<uint8_t>() + base, total, cudaMemcpyDeviceToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(reads_rc_.p, src.reads_rc_.as<uint8_t>() + base, total, cudaMemcpyDeviceToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(read_off_.p, off_host_.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         reads_resident = true;
     }
 
@@ -329,7 +329,7 @@ public:
         BE_OK(X.h_rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
         BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 16, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaMemcpyAsync(X.h_rec.p, X.rec.p, (size_t)n * sizeof(VmExtractRec), cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
         const size_t na = (size_t)X.h_counters.as<unsigned long long>()[0], nc = (size_t)X.h_counters.as<unsigned long long>()[1];
         BE_OK(X.h_anc.ensure(std::max<size_t>(na, 1) * 16));
@@ -342,7 +342,7 @@ public:
             if (nc) BE_OK(cudaMemcpyAsync(X.h_len.p, X.len.p, nc * 4, cudaMemcpyDeviceToHost, c_->stream));
             if (nc) BE_OK(cudaMemcpyAsync(X.h_score.p, X.score.p, nc * 8, cudaMemcpyDeviceToHost, c_->stream));
         }
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         out.rec = X.h_rec.as<ExtractRec>();
         out.x_anc = X.h_anc.as<Anc32>();
         out.x_S = X.h_S.as<double>();
@@ -426,7 +426,7 @@ public:
         }
         std::vector<int32_t> n_hits((size_t)nj);
         BE_OK(cudaMemcpyAsync(n_hits.data(), d_n_hits, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         {
             // jobs that overflowed their capacity: exact room at the end of the hit buffer, second launch
             std::vector<int> redo;
@@ -445,7 +445,7 @@ public:
                 BE_OK(bigger.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
                 BE_OK(cudaMemcpyAsync(bigger.p, d_hits_.p, (size_t)RJ[0].hit_off * vm_reseed_hit_bytes(), cudaMemcpyDeviceToDevice,
                                       c_->stream));
-                BE_OK(cudaStreamSynchronize(c_->stream));
+                BE_OK(vm_stream_sync(c_->stream));
                 d_hits_.release();
                 d_hits_ = bigger;
                 BE_OK(d_seg_.ensure(RJ.size() * (sizeof(VmReseedJobDev) + 4) + 64));
@@ -482,7 +482,7 @@ public:
         }
         std::vector<int32_t> n_out((size_t)nj);
         BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         // concatenate the jobs of each read into one dense anchor list on the device
         std::vector<int64_t> seg(2 * (size_t)nj);   // [src_off | dst_off]
         int64_t dense = 0;
@@ -627,7 +627,7 @@ public:
             c_->launches += vm_launch_ed_upper(jobs_.as<VmAlnJobDev>(), d_seg_.as<int>(), nu, d_msegs_.p, sources(), c_->stream);
             kt.stop();
             BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaStreamSynchronize(c_->stream));
+            BE_OK(vm_stream_sync(c_->stream));
             BE_OK(cudaGetLastError());
             bound.assign((size_t)nj, -1);
             for (int t = 0; t < nu; ++t) {
@@ -691,7 +691,7 @@ public:
                                                 c_->stream);
         kt.stop();
         BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
         for (int j = 0; j < nj; ++j) jobs[which[j]].dist = J[j].result0;
     }
@@ -713,7 +713,7 @@ public:
         c_->launches += vm_launch_extend(jobs_.as<VmAlnJobDev>(), nj, sources(), c_->stream);
         kt.stop();
         BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nj * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
         for (int j = 0; j < nj; ++j) { jobs[j].job.q_e = (int32_t)J[j].result0; jobs[j].job.t_e = (int32_t)J[j].result1; }
     }
@@ -753,6 +753,7 @@ public:
             else { bplan_.pairs.clear(); bplan_.launches.clear(); bplan_.dir_words = 0; }
             vm_fill_plan(J, nj, c_->sm_count > 0 ? c_->sm_count : 148, plan_, host_threads, full_mask.data());
         }
+        fill_dir_bytes_ += plan_.dir_bytes + bplan_.dir_bytes;
         const size_t n_launch = plan_.launches.size() + bplan_.launches.size();
         BE_OK(d_dir_.ensure((plan_.dir_words + bplan_.dir_words) * 4 + 64));
         BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
@@ -795,7 +796,7 @@ public:
         if (!bplan_.pairs.empty()) {
             // jobs whose certificate failed: once more, in the full-matrix kernel
             BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
-            BE_OK(cudaStreamSynchronize(c_->stream));
+            BE_OK(vm_stream_sync(c_->stream));
             BE_OK(cudaGetLastError());
             int n_redo = 0, n_band = 0;
             for (int j = 0; j < nj; ++j) {
@@ -830,7 +831,7 @@ public:
         // per job (offset, length) into the dense CIGAR arena the kernel filled, then one dense D2H
         BE_OK(cudaMemcpyAsync(h_count, d_count, 8, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaMemcpyAsync(h_res, d_seg_.p, (size_t)nj * 8, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
         const size_t dense = (size_t)*h_count;
         BE_OK(h_cig_.ensure(std::max<size_t>(dense, 1) * 4));
@@ -839,7 +840,7 @@ public:
             jobs[j].cig_off = h_res[2 * j];
             jobs[j].cig_len = (int32_t)h_res[2 * j + 1];
         }, 4096);
-        BE_OK(cudaStreamSynchronize(c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
         return h_cig_.as<uint32_t>();
     }
 

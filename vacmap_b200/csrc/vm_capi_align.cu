@@ -107,7 +107,7 @@ struct vm_job {
     std::string err;
     StageTimer timer;
     double fill_cells = 0, fill_bases = 0, fill_jobs = 0, ed_cells = 0, ed_upper = 0, reseed_hits = 0, chain_anchors = 0, band_jobs = 0,
-           band_redo = 0;
+           band_redo = 0, dir_bytes = 0;
     int64_t launches = 0;
     std::chrono::steady_clock::time_point t0, t_done;
 };
@@ -123,6 +123,7 @@ void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::strin
     job->chain_anchors += wb.chain_anchors_;
     job->band_jobs += wb.fill_band_jobs_;
     job->band_redo += wb.fill_band_redo_;
+    job->dir_bytes += wb.fill_dir_bytes_;
     job->launches += launches;
     if (!err.empty() && job->err.empty()) job->err = err;
     if (--job->chunks_left == 0) {
@@ -358,6 +359,7 @@ int vm_align_wait(vm_job *job, vm_result **out)
     tm.add("n_fill_jobs", job->fill_jobs);
     tm.add("n_fill_band_jobs", job->band_jobs);
     tm.add("n_fill_band_redo", job->band_redo);
+    tm.add("n_fill_dir_bytes", job->dir_bytes);
     tm.add("n_ed_cells", job->ed_cells);
     tm.add("n_ed_upper_jobs", job->ed_upper);
     tm.add("n_reseed_hits", job->reseed_hits);

@@ -35,6 +35,21 @@ struct VmError {
         }                                                                            \
     } while (0)
 
+// Wait for a stream without burning a host core: the default cudaStreamSynchronize spins, and with several worker
+// threads waiting on their kernels at any moment that costs whole cores the host glue needs.  One blocking-sync
+// event per host thread.
+static inline cudaError_t vm_stream_sync(cudaStream_t stream)
+{
+    thread_local cudaEvent_t ev = nullptr;
+    if (!ev) {
+        const cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) { ev = nullptr; return e; }
+    }
+    const cudaError_t e = cudaEventRecord(ev, stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev);
+}
+
 // Let a kernel use all opt-in dynamic shared memory.  The value is the same on every call, so concurrent
 // worker threads launching the same kernel with different sizes cannot lower each other's limit.
 template <typename F>

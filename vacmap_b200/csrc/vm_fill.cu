@@ -258,6 +258,7 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, 
     plan.pairs.clear();
     plan.launches.clear();
     plan.dir_words = plan.band_words = 0;
+    plan.dir_bytes = 0;
     constexpr int NCLS = 27, NB = 1024, NKEY = NCLS * NB;
     auto key_of = [&](int j) {
         const int tl = J[j].t.len, ql = J[j].q.len;
@@ -323,6 +324,12 @@ void vm_fill_plan(const VmAlnJobDev *J, int nj, int sm_count, VmFillPlan &plan, 
         for (int x = lo; x < hi; ++x) {
             max_q = std::max(max_q, J[order[x]].q.len);
             max_t = std::max(max_t, J[order[x]].t.len);
+        }
+        for (int x = lo; x < hi; x += 2) {
+            const int tl = std::max(J[order[x]].t.len, x + 1 < hi ? J[order[x + 1]].t.len : 0);
+            const int ql = std::max(J[order[x]].q.len, x + 1 < hi ? J[order[x + 1]].q.len : 0);
+            const int rows_pb = 32 * (rc == 9 ? 16 : 2 * rc);
+            plan.dir_bytes += (double)((tl + rows_pb - 1) / rows_pb) * (ql + 31) * (rows_pb / 64) * 128.0;
         }
         L.pair_end = (int)plan.pairs.size();
         const int rows = 32 * L.R;

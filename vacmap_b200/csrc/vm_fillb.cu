@@ -338,6 +338,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
     plan.pairs.clear();
     plan.launches.clear();
     plan.dir_words = 0;
+    plan.dir_bytes = 0;
     constexpr int ND = 256, NQ = VM_FB_CAP / 8 + 1, NKEY = VM_FB_MAXC * ND * NQ;     // D / 8 in [-128, 128) covers |D| < 1024
     const int T = std::max(1, std::min(std::min(host_threads, 8), nj / 8192 + 1));
     std::vector<int32_t> keys((size_t)nj);
@@ -422,7 +423,11 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
     }
     std::vector<int64_t> cnt(VM_FB_MAXC + 2, 0), at(VM_FB_MAXC + 2, 0);
     std::vector<int> max_steps(VM_FB_MAXC + 2, 0);
-    for (const Tmp &t : tmp) { ++cnt[(size_t)t.c]; max_steps[(size_t)t.c] = std::max(max_steps[(size_t)t.c], t.steps); }
+    for (const Tmp &t : tmp) {
+        ++cnt[(size_t)t.c];
+        max_steps[(size_t)t.c] = std::max(max_steps[(size_t)t.c], t.steps);
+        plan.dir_bytes += (double)t.steps * ((t.c + 1) / 2) * 128.0;
+    }
     cnt[0] = 0;
     for (int c = 1; c <= VM_FB_MAXC; ++c) at[c + 1] = at[c] + cnt[c];
     plan.pairs.resize((size_t)at[VM_FB_MAXC + 1]);

@@ -346,7 +346,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
         SEED_OK(B.chunk_off.ensure((size_t)(n + 1) * 8 + 64));
         SEED_OK(B.chunk_cnt.ensure((size_t)n_chunks * 4 + 64));
         SEED_OK(cudaMemcpyAsync(B.chunk_off.p, chunk_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
-        SEED_OK(cudaStreamSynchronize(stream));
+        SEED_OK(vm_stream_sync(stream));
         if (n_chunks > 0)
             vm_sketch_chunk_kernel<<<(unsigned)((n_chunks + 63) / 64), 64, 0, stream>>>(
                 reads_dev, off_dev, B.chunk_off.as<int64_t>(), n, n_chunks, ix.w, ix.k, B.mz_hash.as<uint64_t>(),
@@ -361,7 +361,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     *launches += 2;
     std::vector<int32_t> n_anchor(n);
     SEED_OK(cudaMemcpyAsync(n_anchor.data(), B.n_anchor.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    SEED_OK(cudaStreamSynchronize(stream));
+    SEED_OK(vm_stream_sync(stream));
     std::vector<int64_t> t_off(n + 1, 0);
     for (int r = 0; r < n; ++r) {
         a_off_host[r + 1] = a_off_host[r] + n_anchor[r];
@@ -382,7 +382,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     if (t_off[n] > 0) {
         vm_cl_init_kernel<<<(unsigned)((t_off[n] + 255) / 256), 256, 0, stream>>>(B.table.as<VmClSlot>(), t_off[n]);
         *launches += 1;
-        SEED_OK(cudaStreamSynchronize(stream));   // a_off / t_off staging vectors are about to go out of scope
+        SEED_OK(vm_stream_sync(stream));   // a_off / t_off staging vectors are about to go out of scope
     }
     vm_seed_expand_kernel<<<n, 32, 0, stream>>>(ix, off_dev, B.mz_posz.as<uint32_t>(), B.n_mz.as<int32_t>(),
                                                 B.mz_start.as<uint32_t>(), B.mz_cnt.as<uint32_t>(), B.mz_aoff.as<uint32_t>(),
@@ -393,7 +393,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     *launches += 2;
     SEED_OK(cudaMemcpyAsync(n_out.data(), B.n_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
     SEED_OK(cudaMemcpyAsync(need_rev.data(), B.need_rev.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    SEED_OK(cudaStreamSynchronize(stream));
+    SEED_OK(vm_stream_sync(stream));
     SEED_OK(cudaGetLastError());
 #undef SEED_OK
     return 0;
