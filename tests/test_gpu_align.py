@@ -87,3 +87,42 @@ def test_banded_edit_distance_is_exact_inside_the_band(gpu_ctx):
                 assert g == d, (len(t), len(q), d, k, g)
             else:
                 assert g > k, (len(t), len(q), d, k, g)
+
+
+def test_banded_fill_certificate_and_fallback(gpu_ctx):
+    """Pairs inside the banded kernel's size range (96..768) whose optimum hugs or leaves the band: unrelated
+    sequences, heavy divergence, a large insertion / deletion, tandem shifts.  Whether the certificate holds or
+    the pair falls back to the full-matrix kernel, the CIGAR must be the oracle's (full-matrix) CIGAR."""
+    from vacmap_b200.align import pairs_batch
+    rng = np.random.default_rng(35)
+    ts, qs = [], []
+    for i in range(160):
+        n = int(rng.integers(100, 700))
+        t = synth.random_seq(rng, n)
+        kind = i % 8
+        if kind == 0:
+            q = synth.random_seq(rng, int(rng.integers(100, 700)))                     # unrelated
+        elif kind == 1:
+            q = synth.mutate(rng, t, 0.30)                                             # very divergent
+        elif kind == 2:
+            p = int(rng.integers(10, n - 10))
+            q = np.concatenate([t[:p], synth.random_seq(rng, int(rng.integers(40, 300))), t[p:]])[:760]   # big insertion
+        elif kind == 3:
+            p = int(rng.integers(10, n // 2))
+            q = np.concatenate([t[:p], t[p + int(rng.integers(40, n // 2)):]])          # big deletion
+        elif kind == 4:
+            k = int(rng.integers(5, 60))
+            q = np.concatenate([t[k:], t[:k]])                                         # rotation: shifted diagonal
+        elif kind == 5:
+            q = synth.mutate(rng, t, 0.10)
+            q[rng.integers(0, len(q), size=len(q) // 15)] = ord("N")                    # N runs
+        else:
+            q = synth.mutate(rng, t, float(rng.choice([0.02, 0.10, 0.15, 0.20])))
+        if len(q) < 96:
+            q = np.concatenate([q, synth.random_seq(rng, 96)])
+        ts.append(t.tobytes().decode())
+        qs.append(q.tobytes().decode())
+    for eqx in (False, True):
+        got = pairs_batch("fill", ts, qs, eqx=eqx, ctx=gpu_ctx)
+        for t, q, g in zip(ts, qs, got):
+            assert g == oracle.k_cigar(t, q, 2, -4, 4, 2, 24, 1, -1, -1, eqx)[0], (len(t), len(q))
