@@ -73,3 +73,24 @@ def test_long_read_and_divergent_reads(gpu_ctx):
     reads = long_read + [("del6k", deleted)] + noisy
     assert _check(vb, gpu_ctx, ref, reads) >= 3
     assert _check(vb, gpu_ctx, ref, noisy, mode="S") >= 1
+
+
+def test_a_read_that_cannot_be_processed_is_dropped_alone(gpu_ctx, monkeypatch):
+    """The reference's worker loses only the read that raised (`except Exception: continue`, clrnano:24116-24125).
+    VM_TEST_FAIL_LEN injects a failure for reads of one length: that read comes back without records, every other
+    read of the batch -- same chunk or not -- is unaffected."""
+    import vacmap_b200 as vb
+    ref = synth.make_reference(71, 200000)
+    reads = synth.make_reads(ref, 72, 9, read_len=5000, err=0.08)
+    bad = ("bad", reads[0][1][:4321])
+    batch = reads[:4] + [bad] + reads[4:]
+    opt = vb.default_option("H")
+    ix = vb.Index(ref, ctx=gpu_ctx)
+    want = vb.Aligner(ix, opt, "H", workers=1).align_batch(batch)
+    assert want[4]                                   # it maps when nothing is injected
+    monkeypatch.setenv("VM_TEST_FAIL_LEN", "4321")
+    for workers, chunk in ((1, 0), (3, 4)):
+        got = vb.Aligner(ix, opt, "H", workers=workers, chunk_reads=chunk).align_batch(batch)
+        assert got[4] == []
+        assert got[:4] == want[:4] and got[5:] == want[5:]
+    ix.close()

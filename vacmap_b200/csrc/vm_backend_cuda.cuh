@@ -231,6 +231,11 @@ public:
                     std::vector<char> &need_reverse, ChainOut &out) override
     {
         WallTimer wt(this, "seed_chain");
+        if (const char *inj = getenv("VM_TEST_FAIL_LEN")) {      // test hook: a read of this length cannot be processed
+            const int64_t bad = atoll(inj);
+            for (int64_t r = 0; r < b.n; ++r)
+                if (b.len(r) == bad) throw std::runtime_error("injected failure (VM_TEST_FAIL_LEN)");
+        }
         upload_reads(b);
         std::vector<int32_t> n_out, nrev;
         std::vector<int64_t> a_off;

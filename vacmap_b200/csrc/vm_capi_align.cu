@@ -160,8 +160,32 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
             else wb.reads_resident = false;
         }
         BatchResult sr;
-        drv.align_batch(sb, sr);
-        for (int64_t i = 0; i < nr; ++i) job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+        try {
+            drv.align_batch(sb, sr);
+            for (int64_t i = 0; i < nr; ++i) job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+        } catch (const std::exception &e) {
+            // Something in this chunk could not be processed (e.g. a read beyond a kernel's size limits).  The reference
+            // loses only the offending read (`except Exception: continue`, clrnano:24116-24125): redo the chunk one
+            // read at a time and leave the reads that fail again without records.
+            if (nr <= 1 || cudaGetLastError() != cudaSuccess) throw;
+            int64_t dropped = 0;
+            for (int64_t i = 0; i < nr; ++i) {
+                ReadBatch one;
+                one.n = 1;
+                one.seq = job->seqs;
+                one.off = job->seq_off + r0 + i;
+                wb.reads_resident = false;
+                try {
+                    BatchResult s1;
+                    drv.align_batch(one, s1);
+                    job->br.records[(size_t)(r0 + i)].swap(s1.records[0]);
+                } catch (const std::exception &) {
+                    if (cudaGetLastError() != cudaSuccess) throw;
+                    ++dropped;
+                }
+            }
+            wb.timer.add("n_reads_dropped_on_error", (double)dropped);
+        }
     } catch (const std::exception &e) {
         err = e.what();
         if (err.empty()) err = "error";
