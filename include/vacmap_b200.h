@@ -110,6 +110,19 @@ int vm_chain_global_download(vm_ctx *ctx, int64_t *sorted, double *S, int32_t *P
 /* per-kernel device time of the last run (ms): [pack, sort, dp_exact, dp_fast] */
 int vm_chain_global_times(vm_ctx *ctx, float *ms4);
 
+/*
+ * Stage-level local chaining (parity tests).  Replaces get_optimal_chain_..._fine_list (variant 1,
+ * clrnano:27305-27528), _fine_list_mismatch (variant 2, :28250-28476) and, with force_fast, their _fast twins
+ * (:26938-27303, :27891-28248); without it the exact DP falls back to _fast as the reference does (:27380-27384).
+ * presorted != 0: `anchors` are already ordered by read end (what the functions take); else they are sorted like
+ * np.argsort(x + len) at :28585.  Outputs per read: score[r] = g_max_scores, the chain in path[path_off[r] ..
+ * path_off[r+1]) as int64 rows, trimmed like :27508-27527, in ASCENDING read order (the reference's list reversed);
+ * `path` needs room for off[n_reads] rows.
+ */
+int vm_chain_local_batch(vm_ctx *ctx, const vm_chain_params *prm, int32_t presorted, int32_t force_fast, int64_t n_reads,
+                         const int64_t *anchors, const int64_t *off, const int32_t *read_len, double *score, int64_t *path,
+                         int64_t *path_off, int32_t *used_fast);
+
 /* ------------------------------------------------------------------------
  * Reference index.  Replaces `vacmap_index.Aligner(path, w=, k=)` (vacmap:344; a minimap2
  * .mmi built by `minimap2 -d`, vacmap:329-336) and its accessors `.k`, `.seq_offset`

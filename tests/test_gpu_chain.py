@@ -114,3 +114,40 @@ def test_full_size_properties(gpu_ctx):
         j = i % len(base)
         if i >= len(base):
             assert (r.S == res[j].S).all() and (r.P == res[j].P).all() and (r.S_arg == res[j].S_arg).all()
+
+
+def test_golden_local(gpu_ctx):
+    """Local DPs through vm_chain_local_batch vs what the REFERENCE's own numba functions returned for the same sorted
+    anchors (tests/golden/chain.npz): _fine_list / _fine_list_mismatch (modes H and L parameters), exact score and the
+    trimmed path; the _fast twins' score; and, on unsorted input, the oracle after the replayed argsort."""
+    import vacmap_b200 as vb
+    n = int(G["l_count"])
+    al = [G["l_%d_a" % ci].astype(np.int64) for ci in range(n)]
+    Ls = [int((a[:, 0] + a[:, 3]).max()) + 1 for a in al]
+    for tag, var, sk, mg in (("fl", 1, 40.0, 99), ("flm", 2, 40.0, 99), ("fl59", 1, 59.0, 50)):
+        prm = vb.ChainParams(kmersize=9, skipcost=sk, maxdiff=30, maxgap=mg, variant=var)
+        res = vb.chain_local_batch(al, Ls, prm, presorted=True, ctx=gpu_ctx)
+        for ci, r in enumerate(res):
+            assert r.score == float(G["l_%d_%s_score" % (ci, tag)]), (tag, ci)
+            want = G["l_%d_%s_path" % (ci, tag)].astype(np.int64).reshape(-1, 4)[::-1]      # the reference lists it descending
+            assert r.path.shape == want.shape and (r.path == want).all(), (tag, ci)
+            assert not r.used_fast
+    for tag, var in (("flf", 1), ("flmf", 2)):
+        prm = vb.ChainParams(kmersize=9, skipcost=40.0, maxdiff=30, maxgap=99, variant=var)
+        res = vb.chain_local_batch(al, Ls, prm, presorted=True, force_fast=True, ctx=gpu_ctx)
+        for ci, r in enumerate(res):
+            assert r.used_fast and r.score == float(G["l_%d_%s_score" % (ci, tag)]), (tag, ci)
+            want = G["l_%d_%s_path" % (ci, tag)].astype(np.int64).reshape(-1, 4)[::-1]
+            assert r.path.shape == want.shape and (r.path == want).all(), (tag, ci)
+    # unsorted input: the library's own argsort (numba quicksort replay on x + len), then the oracle on that order
+    rng = np.random.default_rng(12)
+    raw = [a[rng.permutation(len(a))] for a in al] + [np.zeros((0, 4), np.int64)]
+    prm = vb.ChainParams(kmersize=9, skipcost=40.0, maxdiff=30, maxgap=99, variant=1)
+    res = vb.chain_local_batch(raw, Ls + [100], prm, presorted=False, ctx=gpu_ctx)
+    for a, r in zip(raw, res):
+        if len(a) == 0:
+            assert len(r.path) == 0
+            continue
+        srt = a[oracle.argsort_i64(a[:, 0] + a[:, 3])]
+        sc, path, S, P, used_fast = oracle.chain_local(srt, 9, 1, 40.0, 30, 99)
+        assert r.score == sc and (r.path == np.asarray(path, np.int64).reshape(-1, 4)[::-1]).all()

@@ -7,8 +7,8 @@ missing.
 """
 from . import _lib  # noqa: F401
 from .tables import score_tables  # noqa: F401
-from .chain import ChainParams, chain_global_batch, GlobalChainer  # noqa: F401
+from .chain import ChainParams, chain_global_batch, chain_local_batch, GlobalChainer  # noqa: F401
 from .align import Index, Aligner, Record, default_option, read_fastx  # noqa: F401
 
-__all__ = ["score_tables", "ChainParams", "chain_global_batch", "GlobalChainer", "Index", "Aligner", "Record",
+__all__ = ["score_tables", "ChainParams", "chain_global_batch", "chain_local_batch", "GlobalChainer", "Index", "Aligner", "Record",
            "default_option", "read_fastx"]

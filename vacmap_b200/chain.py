@@ -98,3 +98,28 @@ def chain_global_batch(anchor_list, read_lens, params=None, ctx=None, device=0):
     ch.upload(anchor_list, read_lens)
     ch.run()
     return ch.download()
+
+
+LocalChainResult = collections.namedtuple("LocalChainResult", "score path used_fast")
+
+
+def chain_local_batch(anchor_list, read_lens, params, presorted=True, force_fast=False, ctx=None, device=0):
+    """Stage-level local chaining (``vm_chain_local_batch``): what ``get_optimal_chain_..._fine_list`` (variant 1),
+    ``_fine_list_mismatch`` (variant 2) or their ``_fast`` twins return for each read's int64[n,4] anchors --
+    ``(g_max_scores, path)`` -- with the path in ASCENDING read order (the reference's list reversed)."""
+    L = _lib.load()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_chain_local_batch.argtypes = [vp, ctypes.POINTER(_lib.ChainParamsC), i32, i32, i64, vp, vp, vp, vp, vp, vp, vp]
+    ctx = ctx or _lib.default_context(device)
+    rows, off = _ragged(anchor_list)
+    n = len(anchor_list)
+    rl = np.ascontiguousarray(read_lens, dtype=np.int32)
+    score = np.zeros(n, np.float64)
+    path = np.zeros((max(int(off[-1]), 1), 4), np.int64)
+    path_off = np.zeros(n + 1, np.int64)
+    used_fast = np.zeros(n, np.int32)
+    pc = params.c()
+    _lib.check(ctx.h, L.vm_chain_local_batch(ctx.h, ctypes.byref(pc), int(presorted), int(force_fast), n, _lib.ptr(rows),
+                                             _lib.ptr(off), _lib.ptr(rl), _lib.ptr(score), _lib.ptr(path), _lib.ptr(path_off),
+                                             _lib.ptr(used_fast)))
+    return [LocalChainResult(float(score[i]), path[path_off[i]:path_off[i + 1]].copy(), int(used_fast[i])) for i in range(n)]

@@ -177,7 +177,8 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
 // the integer score of a chain of read r (sizes the fast DP's per-score counters).
 int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch, const std::vector<int64_t> &start,
                   const std::vector<int32_t> &cnt, const std::vector<int32_t> &read_len, const std::vector<int32_t> &cnt_len,
-                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4)
+                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4,
+                  bool presorted, bool force_fast)
 {
     (void)start;
     VmChainState &s = c->chain;
@@ -192,7 +193,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         const int64_t n = cnt[r];
         if (n <= 0) continue;
         // hit2work_1 :23570 -- n / read_len > 5 goes straight to the fast DP (global only)
-        if (!by_end && (double)n / (double)read_len[r] > 5.0) { fast_ids.push_back(r); continue; }
+        if (force_fast || (!by_end && (double)n / (double)read_len[r] > 5.0)) { fast_ids.push_back(r); continue; }
         int k = 0;
         while (k < kNumCaps && n > kCaps[k]) ++k;
         cls[k].push_back(r);
@@ -214,7 +215,14 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
 
     cudaEvent_t *ev = c->ev;
     VM_CUDA_OK(c, cudaEventRecord(ev[1], c->stream));
-    for (int k = 0; k <= kNumCaps; ++k) {
+    if (presorted) {
+        // stage-level entry with anchors already in DP order (the reference functions take sorted input): no argsort
+        int64_t span = 0;
+        for (size_t r = 0; r < cnt.size(); ++r) span = std::max<int64_t>(span, start[r] + cnt[r]);
+        if (span > 0)
+            VM_CUDA_OK(c, cudaMemcpyAsync(s.sorted.p, d_anch, (size_t)span * sizeof(VmAnchor), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    for (int k = 0; k <= kNumCaps && !presorted; ++k) {
         const int n_k = cls_start[k + 1] - cls_start[k];
         if (n_k == 0) continue;
         const bool smem = k < kNumCaps && kCaps[k] <= VM_SORT_SMEM_CAP;
@@ -223,7 +231,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
                                               s.perm.as<int32_t>(), s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(),
                                               sorted_rows_dev, c->stream);
     }
-    if (!fast_ids.empty())
+    if (!fast_ids.empty() && !presorted)
         c->launches += vm_launch_sort_anchors(d_anch, s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(), s.ids.as<int>() + n_exact,
                                               (int)fast_ids.size(), 0, false, by_end ? 1 : 0, s.perm.as<int32_t>(),
                                               s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(), sorted_rows_dev, c->stream);

@@ -295,6 +295,7 @@ public:
         BE_OK(X.counters.ensure(64));
         BE_OK(x_tmp_anc_.ensure(T * 16));
         BE_OK(x_ids_.ensure(ids.size() * 4 + 64));
+        if (!global) BE_OK(X.score.ensure((size_t)(n + 1) * 8));
         if (global) {
             BE_OK(X.S.ensure(T * 8));
             BE_OK(X.len.ensure(T * 4));
@@ -326,7 +327,7 @@ public:
                                                          x_tmp_score_.as<double>(), O, c_->stream);
             else
                 c_->launches += vm_launch_extract_local(x_ids_.as<int>(), (int)ids.size(), s.off_dev.as<int64_t>(), s.cnt_dev.as<int32_t>(),
-                                                        s.sorted.as<VmAnchor>(), s.P.as<int32_t>(), s.gmax.as<int64_t>(),
+                                                        s.sorted.as<VmAnchor>(), s.S.as<double>(), s.P.as<int32_t>(), s.gmax.as<int64_t>(),
                                                         x_tmp_anc_.as<VmAnchor>(), O, c_->stream);
             kt.stop();
         }
@@ -346,6 +347,10 @@ public:
             if (na) BE_OK(cudaMemcpyAsync(X.h_S.p, X.S.p, na * 8, cudaMemcpyDeviceToHost, c_->stream));
             if (nc) BE_OK(cudaMemcpyAsync(X.h_len.p, X.len.p, nc * 4, cudaMemcpyDeviceToHost, c_->stream));
             if (nc) BE_OK(cudaMemcpyAsync(X.h_score.p, X.score.p, nc * 8, cudaMemcpyDeviceToHost, c_->stream));
+        }
+        if (!global && want_local_score_) {
+            BE_OK(X.h_score.ensure((size_t)(n + 1) * 8));
+            BE_OK(cudaMemcpyAsync(X.h_score.p, X.score.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
         }
         BE_OK(vm_stream_sync(c_->stream));
         out.rec = X.h_rec.as<ExtractRec>();
@@ -553,6 +558,46 @@ public:
             BE_OK(cudaEventRecord(side_done_[i], side_[i]));
             BE_OK(cudaStreamWaitEvent(c_->stream, side_done_[i], 0));
         }
+    }
+
+    // Stage-level local chaining (parity tests): anchors as int64 rows, already in the DP's order when
+    // `presorted` (the reference functions take sorted input); the exact DP with its own fall-back, or the _fast
+    // variant outright.  Per read: the best chain's score and its trimmed path in ASCENDING read order.
+    void chain_local_stage(const vm_chain_params &prm, bool presorted, bool force_fast, int64_t n, const int64_t *rows,
+                           const int64_t *off, const int32_t *read_len, ChainOut &out, std::vector<double> &score,
+                           std::vector<int32_t> &used_fast)
+    {
+        const int64_t total = off[n];
+        std::vector<VmAnchor> h((size_t)std::max<int64_t>(total, 1));
+        for (int64_t t = 0; t < total; ++t) {
+            h[(size_t)t].x = (int32_t)rows[4 * t];
+            h[(size_t)t].y = (uint32_t)rows[4 * t + 1];
+            h[(size_t)t].s = (int32_t)rows[4 * t + 2];
+            h[(size_t)t].l = (int32_t)rows[4 * t + 3];
+        }
+        BE_OK(d_dense_.ensure(h.size() * sizeof(VmAnchor)));
+        BE_OK(cudaMemcpyAsync(d_dense_.p, h.data(), (size_t)total * sizeof(VmAnchor), cudaMemcpyHostToDevice, c_->stream));
+        out = ChainOut();
+        out.start.assign(off, off + n);
+        out.cnt.resize((size_t)n);
+        out.gmax.assign((size_t)n, -1);
+        std::vector<int32_t> rl((size_t)n);
+        std::vector<int> ids;
+        for (int64_t r = 0; r < n; ++r) {
+            out.cnt[(size_t)r] = (int32_t)(off[r + 1] - off[r]);
+            rl[(size_t)r] = read_len[r] + 64;
+            if (out.cnt[(size_t)r] > 0) ids.push_back((int)r);
+        }
+        if (vm_chain_prepare(c_, n, total, out.start, out.cnt, false) != VM_OK) throw std::runtime_error("chain: " + c_->err);
+        used_fast.assign((size_t)n, 0);
+        float ms4[4] = {0, 0, 0, 0};
+        if (vm_chain_core(c_, prm, d_dense_.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, &used_fast, ms4, presorted,
+                          force_fast) != VM_OK)
+            throw std::runtime_error("chain: " + c_->err);
+        want_local_score_ = true;
+        extract(false, n, total, ids, 0.0, lx_, out);
+        want_local_score_ = false;
+        score.assign(lx_.h_score.as<double>(), lx_.h_score.as<double>() + n);
     }
 
     static VmSeqSpec spec(const vmg::SeqRef &s)
@@ -860,6 +905,7 @@ private:
     cudaStream_t side_[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t side_done_[3] = {nullptr, nullptr, nullptr}, side_go_ = nullptr;
     Extracted gx_, lx_;
+    bool want_local_score_ = false;
     VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;
     std::vector<int64_t> off_host_;

@@ -487,6 +487,52 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
     return VM_OK;
 }
 
+// Stage-level local chaining: the reference's get_optimal_chain_..._fine_list (variant 1, clrnano:27305-27528),
+// _fine_list_mismatch (variant 2, :28250-28476) or their _fast twins (force_fast) on anchors given as int64 rows
+// (readpos, refpos, strand, len); presorted != 0: rows are already ordered by read end as the functions expect,
+// else the library sorts them as the caller does (np.argsort(x + len), :28585).  Per read r: score[r] (g_max_scores)
+// and the chain -- trimmed like :27508-27527, ASCENDING read order (the reference returns it descending) -- in
+// path[path_off[r] .. path_off[r+1]) as int64 rows; used_fast[r] = 1 when a _fast variant produced it.
+int vm_chain_local_batch(vm_ctx *c, const vm_chain_params *prm, int32_t presorted, int32_t force_fast, int64_t n_reads,
+                         const int64_t *anchors, const int64_t *off, const int32_t *read_len, double *score, int64_t *path,
+                         int64_t *path_off, int32_t *used_fast)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!prm || n_reads < 0 || !off || !score || !path_off || (n_reads > 0 && !read_len) || (prm->variant != 1 && prm->variant != 2)) {
+        c->err = "bad argument";
+        return VM_ERR_ARG;
+    }
+    if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, nullptr);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        ChainOut out;
+        std::vector<double> sc;
+        std::vector<int32_t> uf;
+        be.chain_local_stage(*prm, presorted != 0, force_fast != 0, n_reads, anchors, off, read_len, out, sc, uf);
+        path_off[0] = 0;
+        for (int64_t r = 0; r < n_reads; ++r) {
+            const ExtractRec &x = out.rec[r];
+            score[r] = x.n_anc > 0 ? sc[(size_t)r] : 0.0;
+            if (used_fast) used_fast[r] = uf[(size_t)r];
+            for (int32_t t = 0; t < x.n_anc && path; ++t) {
+                const Anc32 &a = out.x_anc[x.anc_off + t];
+                int64_t *o = path + 4 * (path_off[r] + t);
+                o[0] = a.x; o[1] = (int64_t)a.y; o[2] = a.s; o[3] = a.l;
+            }
+            path_off[r + 1] = path_off[r] + x.n_anc;
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
 // Stage-level seeding: what `index_object.map(seq, check_num, mid_occ=-1)` followed by
 // get_reversed_chain_numpy_rough returns per read.  rows: int64[cap][4]; row_off[n_reads+1] receives
 // the ragged offsets; returns VM_ERR_NOMEM (with row_off filled) when cap is too small.

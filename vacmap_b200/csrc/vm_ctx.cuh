@@ -101,4 +101,5 @@ int vm_chain_prepare(vm_ctx *c, int64_t n_reads, int64_t span, const std::vector
                      bool want_rows);
 int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch, const std::vector<int64_t> &start,
                   const std::vector<int32_t> &cnt, const std::vector<int32_t> &read_len, const std::vector<int32_t> &cnt_len,
-                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4);
+                  const std::vector<int> &ids, int64_t *sorted_rows_dev, std::vector<int32_t> *used_fast, float *ms4,
+                  bool presorted = false, bool force_fast = false);

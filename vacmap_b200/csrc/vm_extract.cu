@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(64) vm_extract_global_kernel(const int *__rest
 // ---- local stage: the best chain, overlapping anchors trimmed, ASCENDING read order ----
 __global__ void __launch_bounds__(64) vm_extract_local_kernel(const int *__restrict__ ids, int n_ids, const int64_t *__restrict__ off,
                                                               const int32_t *__restrict__ cnt, const VmAnchor *__restrict__ a_all,
-                                                              const int32_t *__restrict__ P_all, const int64_t *__restrict__ gmax,
-                                                              VmAnchor *tmp_anc, VmExtractOut out)
+                                                              const double *__restrict__ S_all, const int32_t *__restrict__ P_all,
+                                                              const int64_t *__restrict__ gmax, VmAnchor *tmp_anc, VmExtractOut out)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_ids) return;
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(64) vm_extract_local_kernel(const int *__restr
     rec.n_anc = k;
     rec.n_chains = 1;
     rec.anc_off = (long long)atomicAdd(out.n_anc_total, (unsigned long long)k);
+    if (out.chain_score) out.chain_score[r] = S_all[o + g];       // g_max_scores of the local DP (:27506)
     for (int x = 0; x < k; ++x) out.anc[rec.anc_off + x] = ta[k - 1 - x];
     out.rec[r] = rec;
 }
@@ -141,9 +142,10 @@ int vm_launch_extract_global(const int *ids_dev, int n_ids, const int64_t *off, 
 }
 
 int vm_launch_extract_local(const int *ids_dev, int n_ids, const int64_t *off, const int32_t *cnt, const VmAnchor *sorted,
-                            const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out, cudaStream_t stream)
+                            const double *S, const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out,
+                            cudaStream_t stream)
 {
     if (n_ids <= 0) return 0;
-    vm_extract_local_kernel<<<(n_ids + 63) / 64, 64, 0, stream>>>(ids_dev, n_ids, off, cnt, sorted, P, gmax, tmp_anc, out);
+    vm_extract_local_kernel<<<(n_ids + 63) / 64, 64, 0, stream>>>(ids_dev, n_ids, off, cnt, sorted, S, P, gmax, tmp_anc, out);
     return 1;
 }

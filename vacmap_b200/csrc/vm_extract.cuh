@@ -16,7 +16,7 @@ struct VmExtractOut {
                                           //        local: the trimmed best chain in ASCENDING read order
     double *S;                            // global: S of every anchor of the primary chain (0 for the others)
     int32_t *chain_len;                   // global: anchors per chain, discovery order (primary first)
-    double *chain_score;                  // global: score per chain
+    double *chain_score;                  // global: score per chain; local: [n_reads] score of the best chain (or null)
     unsigned long long *n_anc_total;      // bump allocators, zeroed by the host
     unsigned long long *n_chain_total;
 };
@@ -26,4 +26,5 @@ int vm_launch_extract_global(const int *ids_dev, int n_ids, const int64_t *off, 
                              uint8_t *used_zeroed, VmAnchor *tmp_anc, double *tmp_S, int32_t *tmp_len, double *tmp_score,
                              const VmExtractOut &out, cudaStream_t stream);
 int vm_launch_extract_local(const int *ids_dev, int n_ids, const int64_t *off, const int32_t *cnt, const VmAnchor *sorted,
-                            const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out, cudaStream_t stream);
+                            const double *S, const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out,
+                            cudaStream_t stream);
