@@ -210,6 +210,18 @@ int vm_align_resident(vm_ctx *ctx, vm_index_handle *index, const vm_align_params
 int vm_seed_batch_rows(vm_ctx *ctx, vm_index_handle *index, int32_t check_num, int64_t n_reads, const char *seqs,
                        const int64_t *seq_off, int64_t *rows, int64_t cap, int64_t *row_off, int32_t *need_reverse);
 
+/* Stage-level local re-seeding: the 9-mer scan + same-diagonal merge of get_localmap_..._guide_1 (clrnano:23138-23344)
+ * for guide jobs built by the caller (window construction :23095-23136 is host glue).  Job j: read job_read[j], given
+ * already oriented (its `testseq`); read positions [readstart[j], readend[j]); reference windows
+ * win_lo / win_hi[win_off[j] .. win_off[j+1]) as GLOBAL [lo, hi) in insertion order; guide points gx / gy[g_off[j] ..
+ * g_off[j+1]) sorted by read position.  Output: the anchors, in the reference's emission order, as int64 rows
+ * (readpos, refpos_global, strand, len) in rows[row_off[j] .. row_off[j+1]); VM_ERR_NOMEM (row_off filled) when `cap`
+ * rows are not enough. */
+int vm_local_reseed_batch(vm_ctx *ctx, vm_index_handle *index, int64_t n_reads, const char *seqs, const int64_t *seq_off,
+                          int64_t n_jobs, const int32_t *job_read, const int32_t *readstart, const int32_t *readend,
+                          const int64_t *win_off, const int64_t *win_lo, const int64_t *win_hi, const int64_t *g_off,
+                          const int32_t *gx, const int64_t *gy, int64_t *rows, int64_t cap, int64_t *row_off);
+
 /* Stage-level entry point of the base-level kernels on raw sequence pairs (parity tests).
  * kind 0: edlib.align(query, target, task='distance') (clrnano:19251)        -> out0[j] = distance
  * kind 3: as kind 0, computed inside the band |i - j| <= out1[j] (out1 is an INPUT): out0[j] = the exact distance

@@ -54,3 +54,42 @@ def test_seeding_other_kw(gpu_ctx):
         ix, ox = vb.Index(ref, w=w, k=k, ctx=gpu_ctx), oracle.Index(ref, w=w, k=k)
         check(ix, ox, reads, 100)
         ix.close()
+
+
+def test_local_reseeding_matches_oracle(gpu_ctx):
+    """Stage-level local re-seeding (vm_local_reseed_batch): for the guide chains the oracle pipeline selects on real
+    reads (SVs, both strands, two contigs), the anchors of every guide job -- windows and guide points built by the
+    oracle's restatement of :23095-23136 -- must equal orc_local_reseed's, in the reference's emission order."""
+    import vacmap_b200 as vb
+    from vacmap_b200.align import local_reseed_batch
+    ref = synth.make_reference(45, 400000, n_contigs=2, repeat_frac=0.10)
+    reads = synth.make_reads(ref, 46, 14, read_len=8000, err=0.10, sv_frac=0.5)
+    ox = oracle.Index(ref)
+    ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+    opt = vb.default_option("S")           # mode S re-seeds every secondary chain
+    oriented, jobs, want = [], [], []
+    for rid, seq in reads:
+        seq = seq.upper()
+        L = len(seq)
+        mapq, scores, path_list = pl.decode_hit(ox, seq, L, ox.k, opt, "S")
+        if scores == 0.0:
+            continue
+        rc_seq = pl.revcomp(seq)
+        if scores < 0.0:
+            seq, rc_seq = rc_seq, seq
+        chains = [np.array(p, dtype=np.int64) for p in path_list]
+        chains = pl.drop_somechains(pl.merge_chain(chains))
+        ri = len(oriented)
+        oriented.append(seq)
+        for ch in chains:
+            wins, raw = pl.guide_windows(ch, ctg)
+            readstart = max(0, int(raw[0][0]) - 7000)
+            readend = min(L - 9 + 1, int(raw[-1][0]) + 7000)
+            jobs.append((ri, wins, raw, readstart, readend))
+            want.append(oracle.local_reseed_scan(ctg, wins, raw, seq, rc_seq, 9, readstart, readend))
+    assert len(jobs) >= 10 and sum(len(w) for w in want) > 5000
+    ix = vb.Index(ref, ctx=gpu_ctx)
+    got = local_reseed_batch(ix, oriented, jobs)
+    for (ri, wins, raw, a, b), g, w in zip(jobs, got, want):
+        assert g.shape == w.shape and (g == w).all(), (ri, len(wins), len(raw))
+    ix.close()

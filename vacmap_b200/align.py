@@ -319,3 +319,37 @@ def seed_batch(index, reads, check_num=100):
         _lib.check(index.ctx.h, rc)
         break
     return [(rows[row_off[i]:row_off[i + 1]].copy(), bool(nrev[i])) for i in range(len(reads))]
+
+
+def local_reseed_batch(index, reads, jobs):
+    """Stage-level local re-seeding (``vm_local_reseed_batch``).  reads: oriented sequences; jobs: list of
+    ``(read_index, windows [(lo, hi) global], guides int64[m, >=2] sorted by read position, readstart, readend)``.
+    -> per job, int64[n, 4] anchors in the reference's emission order."""
+    L = _lib.load()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_local_reseed_batch.argtypes = [vp, vp, i64, vp, vp, i64] + [vp] * 9 + [vp, i64, vp]
+    enc = [s.upper().encode() for s in reads]
+    off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+    nj = len(jobs)
+    job_read = np.array([j[0] for j in jobs], np.int32)
+    rs = np.array([j[3] for j in jobs], np.int32)
+    re_ = np.array([j[4] for j in jobs], np.int32)
+    win_off = np.concatenate([[0], np.cumsum([len(j[1]) for j in jobs])]).astype(np.int64)
+    g_off = np.concatenate([[0], np.cumsum([len(j[2]) for j in jobs])]).astype(np.int64)
+    wl = np.array([w[0] for j in jobs for w in j[1]] or [0], np.int64)
+    wh = np.array([w[1] for j in jobs for w in j[1]] or [0], np.int64)
+    gx = np.concatenate([np.asarray(j[2])[:, 0] for j in jobs] or [np.zeros(0)]).astype(np.int32)
+    gy = np.concatenate([np.asarray(j[2])[:, 1] for j in jobs] or [np.zeros(0)]).astype(np.int64)
+    cap = max(4096, 4 * int(off[-1]))
+    ctx = index.ctx
+    while True:
+        rows = np.zeros((cap, 4), np.int64)
+        row_off = np.zeros(nj + 1, np.int64)
+        rc = L.vm_local_reseed_batch(ctx.h, index.h, len(reads), b"".join(enc), _lib.ptr(off), nj, _lib.ptr(job_read), _lib.ptr(rs),
+                                     _lib.ptr(re_), _lib.ptr(win_off), _lib.ptr(wl), _lib.ptr(wh), _lib.ptr(g_off), _lib.ptr(gx),
+                                     _lib.ptr(gy), _lib.ptr(rows), cap, _lib.ptr(row_off))
+        if rc == -4:      # VM_ERR_NOMEM: row_off is filled, retry with enough room
+            cap = int(row_off[-1]) + 16
+            continue
+        _lib.check(ctx.h, rc)
+        return [rows[row_off[j]:row_off[j + 1]].copy() for j in range(nj)]

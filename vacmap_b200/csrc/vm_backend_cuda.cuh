@@ -360,21 +360,14 @@ public:
         out.x_score = X.h_score.as<double>();
     }
 
-    // ---- local re-seeding + local chaining ----
-    void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
-                      const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
-                      ChainOut &out) override
+    // local 9-mer re-seeding of every guide job (hits + same-diagonal merge): afterwards job j's anchors are
+    // d_rout_[2 * J[j].dense_off .. + n_out[j]) on the device
+    void reseed_device(const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs, std::vector<VmReseedJobDev> &J,
+                       std::vector<int32_t> &n_out, int32_t *&d_n_out)
     {
-        WallTimer wt(this, "reseed_chain");
-        const int64_t n = b.n;
         const int nj = (int)jobs.size();
-        out = ChainOut();
-        out.start.assign((size_t)n, 0);
-        out.cnt.assign((size_t)n, 0);
-        out.gmax.assign((size_t)n, -1);
-        if (nj == 0) return;
         WallTimer *hs = new WallTimer(this, "h_reseed_stage");
-        std::vector<VmReseedJobDev> J((size_t)nj);
+        J.assign((size_t)nj, VmReseedJobDev());
         std::vector<int64_t> w_off((size_t)nj + 1, 0), g_off((size_t)nj + 1, 0);
         for (int j = 0; j < nj; ++j) {
             w_off[j + 1] = w_off[j] + (int64_t)jobs[j].job.win_lo.size();
@@ -424,7 +417,8 @@ public:
         BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_gx_.p, gx, n_g * 4, cudaMemcpyHostToDevice, c_->stream));
         BE_OK(cudaMemcpyAsync(d_gy_.p, gy, n_g * 8, cudaMemcpyHostToDevice, c_->stream));
-        int32_t *d_n_hits = d_nh_.as<int32_t>(), *d_n_out = d_nh_.as<int32_t>() + nj;
+        int32_t *d_n_hits = d_nh_.as<int32_t>();
+        d_n_out = d_nh_.as<int32_t>() + nj;
         const VmIndexDev &ix = ih_->ix->dev;
         delete hs;
         {
@@ -490,9 +484,49 @@ public:
                                                    d_order_.as<int32_t>(), d_rout_.as<VmAnchor>(), d_n_out, c_->stream);
             kt.stop();
         }
-        std::vector<int32_t> n_out((size_t)nj);
+        n_out.assign((size_t)nj, 0);
         BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(vm_stream_sync(c_->stream));
+    }
+
+    // stage-level: the anchors of every guide job on the host (parity tests)
+    void reseed_only(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                     std::vector<VmAnchor> &flat, std::vector<int64_t> &job_off)
+    {
+        upload_reads(b);
+        std::vector<VmReseedJobDev> J;
+        std::vector<int32_t> n_out;
+        int32_t *d_n_out = nullptr;
+        const int nj = (int)jobs.size();
+        job_off.assign((size_t)nj + 1, 0);
+        if (nj == 0) { flat.clear(); return; }
+        reseed_device(need_reverse, jobs, J, n_out, d_n_out);
+        for (int j = 0; j < nj; ++j) job_off[(size_t)j + 1] = job_off[(size_t)j] + n_out[(size_t)j];
+        flat.resize((size_t)job_off[(size_t)nj]);
+        for (int j = 0; j < nj; ++j)
+            if (n_out[(size_t)j] > 0)
+                BE_OK(cudaMemcpyAsync(flat.data() + job_off[(size_t)j], d_rout_.as<VmAnchor>() + 2 * J[(size_t)j].dense_off,
+                                      (size_t)n_out[(size_t)j] * sizeof(VmAnchor), cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
+    }
+
+    // ---- local re-seeding + local chaining ----
+    void reseed_chain(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<GuideJobRef> &jobs,
+                      const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                      ChainOut &out) override
+    {
+        WallTimer wt(this, "reseed_chain");
+        const int64_t n = b.n;
+        const int nj = (int)jobs.size();
+        out = ChainOut();
+        out.start.assign((size_t)n, 0);
+        out.cnt.assign((size_t)n, 0);
+        out.gmax.assign((size_t)n, -1);
+        if (nj == 0) return;
+        std::vector<VmReseedJobDev> J;
+        std::vector<int32_t> n_out;
+        int32_t *d_n_out = nullptr;
+        reseed_device(need_reverse, jobs, J, n_out, d_n_out);
         // concatenate the jobs of each read into one dense anchor list on the device
         std::vector<int64_t> seg(2 * (size_t)nj);   // [src_off | dst_off]
         int64_t dense = 0;

@@ -487,6 +487,62 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
     return VM_OK;
 }
 
+// Stage-level local re-seeding: the scan + same-diagonal merge of get_localmap_..._guide_1 (clrnano:23138-23344)
+// for jobs whose windows and guide chain the caller built (window construction :23095-23136 is host glue).
+// Job j: read job_read[j] (given already oriented: its testseq), read positions [readstart[j], readend[j]),
+// reference windows win_lo/win_hi[win_off[j] .. win_off[j+1]) (GLOBAL [lo, hi), insertion order), guide points
+// gx/gy[g_off[j] .. g_off[j+1]) sorted by read position.  Output: the anchors in the reference's emission order
+// as int64 rows in rows[row_off[j] .. row_off[j+1]); VM_ERR_NOMEM (row_off filled) when `cap` rows are too few.
+int vm_local_reseed_batch(vm_ctx *c, vm_index_handle *h, int64_t n_reads, const char *seqs, const int64_t *seq_off, int64_t n_jobs,
+                          const int32_t *job_read, const int32_t *readstart, const int32_t *readend, const int64_t *win_off,
+                          const int64_t *win_lo, const int64_t *win_hi, const int64_t *g_off, const int32_t *gx, const int64_t *gy,
+                          int64_t *rows, int64_t cap, int64_t *row_off)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!h || n_reads < 0 || n_jobs < 0 || !seq_off || !row_off || (n_jobs > 0 && (!job_read || !readstart || !readend || !win_off || !g_off))) {
+        c->err = "bad argument";
+        return VM_ERR_ARG;
+    }
+    cudaSetDevice(c->device);
+    try {
+        if (!c->backend) {
+            c->backend = new CudaBackend(c, h);
+            c->backend_free = [](void *p) { delete (CudaBackend *)p; };
+        }
+        CudaBackend &be = *(CudaBackend *)c->backend;
+        be.set_index(h);
+        be.reads_resident = false;
+        ReadBatch b;
+        b.n = n_reads; b.seq = seqs; b.off = seq_off;
+        std::vector<GuideJobRef> jobs((size_t)n_jobs);
+        for (int64_t j = 0; j < n_jobs; ++j) {
+            if (job_read[j] < 0 || job_read[j] >= n_reads) { c->err = "bad job_read"; return VM_ERR_ARG; }
+            jobs[(size_t)j].read = job_read[j];
+            vmg::GuideJob &g = jobs[(size_t)j].job;
+            g.readstart = readstart[j];
+            g.readend = readend[j];
+            g.win_lo.assign(win_lo + win_off[j], win_lo + win_off[j + 1]);
+            g.win_hi.assign(win_hi + win_off[j], win_hi + win_off[j + 1]);
+            g.gx.assign(gx + g_off[j], gx + g_off[j + 1]);
+            g.gy.assign(gy + g_off[j], gy + g_off[j + 1]);
+        }
+        std::vector<char> need_reverse((size_t)n_reads, 0);
+        std::vector<VmAnchor> flat;
+        std::vector<int64_t> job_off;
+        be.reseed_only(b, need_reverse, jobs, flat, job_off);
+        for (int64_t j = 0; j <= n_jobs; ++j) row_off[j] = job_off[(size_t)j];
+        if (row_off[n_jobs] > cap) { c->err = "row buffer too small"; return VM_ERR_NOMEM; }
+        for (size_t t = 0; t < flat.size(); ++t) {
+            int64_t *o = rows + 4 * t;
+            o[0] = flat[t].x; o[1] = (int64_t)flat[t].y; o[2] = flat[t].s; o[3] = flat[t].l;
+        }
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        return VM_ERR_CUDA;
+    }
+    return VM_OK;
+}
+
 // Stage-level local chaining: the reference's get_optimal_chain_..._fine_list (variant 1, clrnano:27305-27528),
 // _fine_list_mismatch (variant 2, :28250-28476) or their _fast twins (force_fast) on anchors given as int64 rows
 // (readpos, refpos, strand, len); presorted != 0: rows are already ordered by read end as the functions expect,
