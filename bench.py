@@ -195,6 +195,11 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
+    # one process per GPU: every rank gets its share of the host cores for the glue (pool size is read at load time)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    if local_world > 1:
+        os.environ.setdefault("VM_HOST_THREADS", str(max(2, (os.cpu_count() or 1) // local_world)))
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # NCCL's version banner goes to stdout; this script prints one JSON line there
     import torch
     import vacmap_b200 as vb
 

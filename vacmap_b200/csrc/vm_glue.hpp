@@ -328,8 +328,14 @@ static void hit2work_chains(std::vector<Path> &path_list, std::vector<double> &s
     }
     out.ok = true;
     out.score = scores_list[0];
-    out.guides.push_back(path_list[0]);
-    for (const Path *p : secondary) out.guides.push_back(*p);
+    out.guides.reserve(1 + secondary.size());
+    {   // path_list is not used after this: the chains move into the result
+        std::vector<Path> sec;
+        sec.reserve(secondary.size());
+        for (const Path *p : secondary) sec.push_back(std::move(*const_cast<Path *>(p)));
+        out.guides.push_back(std::move(path_list[0]));
+        for (Path &p : sec) out.guides.push_back(std::move(p));
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -337,7 +343,8 @@ static void hit2work_chains(std::vector<Path> &path_list, std::vector<double> &s
 // ---------------------------------------------------------------------------
 static void merge_chain(std::vector<Path> &chains)
 {
-    std::vector<Path> rest(chains.begin() + 1, chains.end());
+    if (chains.size() <= 1) return;
+    std::vector<Path> rest(std::make_move_iterator(chains.begin() + 1), std::make_move_iterator(chains.end()));
     if (!rest.empty()) {
         std::vector<int64_t> keys, order;
         for (const Path &c : rest) keys.push_back(c.back().x);
@@ -404,12 +411,13 @@ static void drop_somechains(std::vector<Path> &chains)
             if (item.s == 1) c0[ci]++; else c1[ci]++;
         }
     std::vector<Path> out;
-    out.push_back(chains[0]);
+    out.reserve(chains.size());
+    out.push_back(std::move(chains[0]));
     for (size_t ci = 0; ci < m; ++ci) {
         const bool keep = (sc0[ci] > sc1[ci] && c0[ci] > c1[ci]) || (sc0[ci] < sc1[ci] && c0[ci] < c1[ci]);
-        const Path &ch = chains[ci + 1];
+        Path &ch = chains[ci + 1];
         if ((!keep && distance[ci] < 500) || (ch.front().x - ch.back().x) < 100) continue;
-        out.push_back(ch);
+        out.push_back(std::move(ch));
     }
     chains.swap(out);
 }
@@ -424,7 +432,8 @@ static size_t select_guides(std::vector<Path> &chains, const ModeConst &mc)
     for (const Path &c : chains) keys.push_back(1.0 / (double)c.size());
     argsort_replay<double>(keys.data(), (int64_t)keys.size(), order);
     std::vector<Path> t;
-    for (int64_t i : order) t.push_back(chains[i]);
+    t.reserve(chains.size());
+    for (int64_t i : order) t.push_back(std::move(chains[i]));
     chains.swap(t);
     size_t used = 1;
     int count = 2;
@@ -556,6 +565,7 @@ static void rebuild_chain_break(const Contigs &ctg, const Path &raw, int64_t lar
     al.clear();
     Anc pre = raw[0];
     al.push_back(Path{pre});
+    al.back().reserve(raw.size());
     for (size_t i = 1; i < raw.size(); ++i) {
         const Anc &now = raw[i];
         if (pre.s == now.s) {
@@ -577,6 +587,7 @@ static void rebuild_chain_break(const Contigs &ctg, const Path &raw, int64_t lar
             if ((b.back().x + b.back().l - b.front().x) < small_alignment) al.pop_back();
         }
         al.push_back(Path{now});
+        al.back().reserve(raw.size() - i);
         pre = now;
     }
     if (al.back().size() == 1) al.pop_back();

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <deque>
 #include <exception>
 #include <functional>
@@ -20,7 +21,12 @@ class HostPool {
 public:
     static HostPool &get()
     {
-        static HostPool pool((int)std::max(1u, std::thread::hardware_concurrency()));
+        // VM_HOST_THREADS: share of the host this process may use (one process per GPU on a multi-GPU box)
+        static HostPool pool([] {
+            const char *e = getenv("VM_HOST_THREADS");
+            const int n = e ? atoi(e) : 0;
+            return n > 0 ? n : (int)std::max(1u, std::thread::hardware_concurrency());
+        }());
         return pool;
     }
     int size() const { return (int)threads_.size() + 1; }

@@ -264,6 +264,7 @@ private:
             s.recs.clear();
             s.filtered = false;
             try {
+                segj[t].reserve(s.asc.size());
                 vmg::rebuild_chain_break(ctg_, s.asc, opt_.local_maxdiff, s.al);
                 for (size_t i = 0; i < s.al.size(); ++i) {
                     EdJob j;
