@@ -1033,8 +1033,11 @@ static int64_t cigar_query_len(const std::vector<uint32_t> &c)
     return n;
 }
 
-// kept[i]: anchors of sub-alignment i after split_alignment; cig[i]: concatenated fill ops of it
-static void make_records(const AlnList &kept, const std::vector<std::vector<uint32_t>> &cig, int mapq, int64_t L,
+// a run of CIGAR ops inside a kernel's output array
+struct OpSpan { const uint32_t *p; int32_t n; };
+
+// kept[i]: anchors of sub-alignment i after split_alignment; cig[i]: the fill segments' ops of it, in order
+static void make_records(const AlnList &kept, const std::vector<std::vector<OpSpan>> &cig, int mapq, int64_t L,
                          const Contigs &ctg, bool need_reverse, bool hardclip, std::vector<Record> &out)
 {
     out.clear();
@@ -1060,8 +1063,11 @@ static void make_records(const AlnList &kept, const std::vector<std::vector<uint
             r.r_en = al.back().y + al.back().l - bias;
             r.strand = need_reverse ? 1 : -1;
         }
+        size_t n_ops = 3;
+        for (const OpSpan &sp : cig[i]) n_ops += (size_t)sp.n;
+        r.cigar.reserve(n_ops);
         if (r.q_st > 0) r.cigar.push_back((uint32_t)r.q_st << 4 | clip);
-        r.cigar.insert(r.cigar.end(), cig[i].begin(), cig[i].end());
+        for (const OpSpan &sp : cig[i]) r.cigar.insert(r.cigar.end(), sp.p, sp.p + sp.n);
         if (tailM > 0) r.cigar.push_back((uint32_t)tailM << 4 | 0u);
         if (L - r.q_en > 0) r.cigar.push_back((uint32_t)(L - r.q_en) << 4 | clip);
         const int64_t want = hardclip ? (r.q_en - r.q_st) : L;

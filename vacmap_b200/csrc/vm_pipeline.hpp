@@ -96,6 +96,23 @@ struct Backend {
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
 };
 
+// Thread time spent in the parts of the host glue, summed over the pool's threads ("t_<name>" stage entries):
+// where the host cores go inside a phase.
+enum SubPart { SP_H2W = 0, SP_GUIDES, SP_GUIDEJOB, SP_REBUILD, SP_QT, SP_SEGS, SP_MERGE, SP_FIXINV, SP_SPLIT, SP_FILLJOBS, SP_CIGCAT,
+               SP_RECORDS, SP_TRACE, SP_COUNT };
+static const char *const kSubPartName[SP_COUNT] = {"t_hit2work", "t_select_guides", "t_guide_job", "t_rebuild_break", "t_query_target",
+                                                   "t_match_segments", "t_merge_conjacent", "t_fix_simple_inv", "t_split_alignment",
+                                                   "t_fill_jobs", "t_cigar_concat", "t_make_records", "t_traceback_copy"};
+struct SubTimes {
+    std::atomic<int64_t> ns[SP_COUNT];
+    SubTimes() { for (auto &x : ns) x.store(0); }
+};
+struct SubScope {
+    SubTimes &st; int part; std::chrono::steady_clock::time_point t0;
+    SubScope(SubTimes &s, int p) : st(s), part(p), t0(std::chrono::steady_clock::now()) {}
+    ~SubScope() { st.ns[part].fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(), std::memory_order_relaxed); }
+};
+
 struct ReadState {
     bool alive = false;
     bool need_reverse = false;
@@ -170,18 +187,25 @@ public:
             if (m <= 2) return;                       // decode_hit :23986 -- <= 2 anchors: unmapped
             const int64_t o = g.start[r];
             vmg::GlobalResult gr;
-            if (g.rec) {
-                const ExtractRec &x = g.rec[r];
-                vmg::hit2work_extracted(g.x_anc + x.anc_off, g.x_S + x.anc_off, g.x_len + x.meta_off, g.x_score + x.meta_off,
-                                        x.n_chains, read_len[r], gr);
-            } else vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
+            {
+                SubScope sc(sub_, SP_H2W);
+                if (g.rec) {
+                    const ExtractRec &x = g.rec[r];
+                    vmg::hit2work_extracted(g.x_anc + x.anc_off, g.x_S + x.anc_off, g.x_len + x.meta_off, g.x_score + x.meta_off,
+                                            x.n_chains, read_len[r], gr);
+                } else vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
+            }
             if (!gr.ok) return;
             ReadState &s = st[r];
             s.alive = true;
             s.need_reverse = need_rev[r] != 0;
             s.mapq = gr.mapq;
             s.guides.swap(gr.guides);
-            s.n_guides_used = vmg::select_guides(s.guides, opt_.mode);
+            {
+                SubScope sc(sub_, SP_GUIDES);
+                s.n_guides_used = vmg::select_guides(s.guides, opt_.mode);
+            }
+            SubScope sc(sub_, SP_GUIDEJOB);
             for (size_t gi = 0; gi < s.n_guides_used; ++gi) {
                 GuideJobRef j;
                 j.read = (int32_t)r;
@@ -207,6 +231,7 @@ public:
         // ---- 4-5. local re-seeding + local chaining (fused on the device) ----
         ChainOut lc;
         be_.reseed_chain(b, need_rev, all_gjobs, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
+        lc_ = &lc;
 
         // ---- 6. traceback, then extend_func as a staged state machine ----
         ph = new Phase(this, "g_traceback");
@@ -215,12 +240,14 @@ public:
             if (!s.alive) return;
             if (lc.cnt[r] == 0) { s.alive = false; return; }   // np.array([]) indexing raises in the reference
             const int64_t o = lc.start[r];
+            SubScope sc(sub_, SP_TRACE);
             if (lc.rec) {
-                const ExtractRec &x = lc.rec[r];
-                s.asc.resize((size_t)x.n_anc);
-                for (int32_t t = 0; t < x.n_anc; ++t) s.asc[(size_t)t] = vmg::widen(lc.x_anc[x.anc_off + t]);
-            } else vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
-            if (s.asc.size() <= 1) s.alive = false;
+                // the path was extracted on the device; it is widened where it is consumed (rebuild_chain_break)
+                if (lc.rec[r].n_anc <= 1) s.alive = false;
+            } else {
+                vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
+                if (s.asc.size() <= 1) s.alive = false;
+            }
             s.nofilter = opt_.nodiscard;
         });
         delete ph;
@@ -238,6 +265,9 @@ public:
             }
         }
         if (!again.empty()) extend_pass(b, read_len, st, again);
+        lc_ = nullptr;
+        if (on_time)
+            for (int p = 0; p < SP_COUNT; ++p) on_time(kSubPartName[p], 1e-6 * (double)sub_.ns[p].exchange(0));
         {
             Phase p2(this, "g_finish");
             parallel_for(n, threads_, [&](int64_t r) {
@@ -264,14 +294,30 @@ private:
             s.recs.clear();
             s.filtered = false;
             try {
-                segj[t].reserve(s.asc.size());
-                vmg::rebuild_chain_break(ctg_, s.asc, opt_.local_maxdiff, s.al);
+                const Path *asc = &s.asc;
+                thread_local Path widened;
+                if (lc_ && lc_->rec) {
+                    SubScope sc(sub_, SP_TRACE);
+                    const ExtractRec &x = lc_->rec[r];
+                    widened.resize((size_t)x.n_anc);
+                    for (int32_t k = 0; k < x.n_anc; ++k) widened[(size_t)k] = vmg::widen(lc_->x_anc[x.anc_off + k]);
+                    asc = &widened;
+                }
+                segj[t].reserve(asc->size());
+                {
+                    SubScope sc(sub_, SP_REBUILD);
+                    vmg::rebuild_chain_break(ctg_, *asc, opt_.local_maxdiff, s.al);
+                }
                 for (size_t i = 0; i < s.al.size(); ++i) {
                     EdJob j;
                     j.read = (int32_t)r;
-                    vmg::query_target(s.al[i].front(), s.al[i].back(), read_len[r], ctg_, j.b, j.a);
+                    {
+                        SubScope sc(sub_, SP_QT);
+                        vmg::query_target(s.al[i].front(), s.al[i].back(), read_len[r], ctg_, j.b, j.a);
+                    }
                     if (std::min(j.a.len(), j.b.len()) == 0) throw vmg::ReadDropped("division by zero");
                     j.seg_off = (int64_t)segj[t].size();
+                    SubScope sc(sub_, SP_SEGS);
                     j.seg_n = vmg::match_segments(s.al[i], j.a.len(), j.b.len(), segj[t], 128) ? (int32_t)(segj[t].size() - (size_t)j.seg_off) : 0;
                     orient(j.a, s.need_reverse);
                     orient(j.b, s.need_reverse);
@@ -326,15 +372,23 @@ private:
             ReadState &s = st[r];
             if (!s.alive) return;
             try {
-                vmg::merge_conjacent(s.al, ctg_);
+                {
+                    SubScope sc(sub_, SP_MERGE);
+                    vmg::merge_conjacent(s.al, ctg_);
+                }
                 if (s.al.size() > 2) {
+                    SubScope sc(sub_, SP_FIXINV);
                     std::string oriented = oriented_read(b, r, s.need_reverse);
                     vmg::fix_simple_inv(s.al, ctg_, oriented.data(), read_len[r]);
                 }
                 s.kept.assign(s.al.size(), Path());
                 s.fills.clear();
-                for (size_t i = 0; i < s.al.size(); ++i)
-                    vmg::split_alignment(s.al[i], (int)i, read_len[r], ctg_, s.kept[i], s.fills);
+                {
+                    SubScope sc(sub_, SP_SPLIT);
+                    for (size_t i = 0; i < s.al.size(); ++i)
+                        vmg::split_alignment(s.al[i], (int)i, read_len[r], ctg_, s.kept[i], s.fills);
+                }
+                SubScope sc(sub_, SP_FILLJOBS);
                 for (vmg::FillJob &f : s.fills) {
                     FillJobRef j;
                     j.read = (int32_t)r;
@@ -356,11 +410,13 @@ private:
             const int64_t r = ids[t];
             ReadState &s = st[r];
             if (!s.alive) return;
-            std::vector<std::vector<uint32_t>> cig(s.al.size());
-            for (int64_t q = f_start[t]; q < f_start[t + 1]; ++q) {
-                std::vector<uint32_t> &dst = cig[fills[q].job.aln];
-                dst.insert(dst.end(), cig_ops + fills[q].cig_off, cig_ops + fills[q].cig_off + fills[q].cig_len);
+            std::vector<std::vector<vmg::OpSpan>> cig(s.al.size());
+            {
+                SubScope sc(sub_, SP_CIGCAT);
+                for (int64_t q = f_start[t]; q < f_start[t + 1]; ++q)
+                    cig[fills[q].job.aln].push_back(vmg::OpSpan{cig_ops + fills[q].cig_off, fills[q].cig_len});
             }
+            SubScope sc(sub_, SP_RECORDS);
             try {
                 vmg::make_records(s.kept, cig, s.mapq, read_len[r], ctg_, s.need_reverse, opt_.hardclip, s.recs);
             } catch (const vmg::ReadDropped &) { s.alive = false; s.recs.clear(); }
@@ -431,6 +487,8 @@ private:
         return rc;
     }
 
+    SubTimes sub_;
+    const ChainOut *lc_ = nullptr;     // local-stage result of the batch in flight (valid during align_batch)
     Backend &be_;
     const vmg::Contigs &ctg_;
     vmg::Options opt_;
