@@ -171,7 +171,7 @@ struct OracleBackend : public Backend {
         out.adopt_stores();
     }
 
-    void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const std::vector<vmg::MatchSeg> &) override
+    void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const vmg::MatchSeg *, size_t) override
     {
         for (EdJob &j : jobs) {
             const std::string x = materialize(b, j.read, j.a), y = materialize(b, j.read, j.b);

@@ -665,7 +665,13 @@ public:
     // Divergence filter distances.  Jobs that come with their chain's match segments are first bounded from
     // above by the alignment through those segments (vm_ed_upper_kernel); a bound within the job's band settles
     // the filter, so only the jobs it leaves open (none on typical reads) run the exact banded kernel.
-    void edit_distance(const ReadBatch &, std::vector<EdJob> &jobs, const std::vector<vmg::MatchSeg> &segs) override
+    vmg::MatchSeg *seg_staging(size_t n_segs) override
+    {
+        BE_OK(h_segs_.ensure(n_segs * sizeof(vmg::MatchSeg) + 64));
+        return h_segs_.as<vmg::MatchSeg>();
+    }
+
+    void edit_distance(const ReadBatch &, std::vector<EdJob> &jobs, const vmg::MatchSeg *segs, size_t n_segs) override
     {
         WallTimer wt(this, "edit_distance");
         const int nj = (int)jobs.size();
@@ -691,20 +697,15 @@ public:
                 J[t].n_out = e.seg_n;
             }, 1024);
             static_assert(sizeof(vmg::MatchSeg) == 12, "match segment layout");
-            BE_OK(d_msegs_.ensure(segs.size() * sizeof(vmg::MatchSeg) + 64));
+            BE_OK(d_msegs_.ensure(n_segs * sizeof(vmg::MatchSeg) + 64));
             BE_OK(d_seg_.ensure((size_t)nu * 4 + 64));
             std::vector<int> ids((size_t)nu);
             for (int t = 0; t < nu; ++t) ids[t] = t;
-            BE_OK(h_segs_.ensure(segs.size() * sizeof(vmg::MatchSeg) + 64));
-            {
-                const int64_t blk = 1 << 16, nb = ((int64_t)segs.size() + blk - 1) / blk;
-                vmg::MatchSeg *dst = h_segs_.as<vmg::MatchSeg>();
-                parallel_for(nb, host_threads, [&](int64_t b) {
-                    const int64_t lo = b * blk, hi = std::min<int64_t>((int64_t)segs.size(), lo + blk);
-                    memcpy(dst + lo, segs.data() + lo, (size_t)(hi - lo) * sizeof(vmg::MatchSeg));
-                }, 1);
+            if (segs != h_segs_.as<vmg::MatchSeg>()) {      // a caller that did not use seg_staging()
+                BE_OK(h_segs_.ensure(n_segs * sizeof(vmg::MatchSeg) + 64));
+                memcpy(h_segs_.p, segs, n_segs * sizeof(vmg::MatchSeg));
             }
-            BE_OK(cudaMemcpyAsync(d_msegs_.p, h_segs_.p, segs.size() * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
+            BE_OK(cudaMemcpyAsync(d_msegs_.p, h_segs_.p, n_segs * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
             KTimer kt(this, "k_ed_upper");

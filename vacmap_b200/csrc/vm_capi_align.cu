@@ -454,7 +454,7 @@ int vm_pairs_batch(vm_ctx *c, int32_t kind, int32_t eqx, int64_t n_pairs, const 
                 jobs[j].b = ref_of(t_off[j], t_off[j + 1]);
                 jobs[j].band = kind == 3 ? out1[j] : -1;
             }
-            be.edit_distance(b, jobs, std::vector<vmg::MatchSeg>());
+            be.edit_distance(b, jobs, nullptr, 0);
             for (int64_t j = 0; j < n_pairs; ++j) out0[j] = jobs[j].dist;
         } else if (kind == 1) {
             std::vector<ExtJobRef> jobs((size_t)n_pairs);

@@ -253,15 +253,23 @@ static void hit2work_chains(std::vector<Path> &path_list, std::vector<double> &s
     // 100-bp read-bin sets as sorted unique vectors (the reference's Python sets are only ever
     // intersected and counted, :23672-23694)
     auto binset = [&](const Path &p, std::vector<int64_t> &s) {
+        // chains come in descending read order: walking them backwards gives the bins already sorted
         s.clear();
         s.reserve(p.size());
-        for (const Anc &v : p) s.push_back(v.x / bin_size);
-        std::sort(s.begin(), s.end());
-        s.erase(std::unique(s.begin(), s.end()), s.end());
+        bool sorted = true;
+        for (size_t i = p.size(); i-- > 0;) {
+            const int64_t b = p[i].x / bin_size;
+            if (!s.empty() && b < s.back()) sorted = false;
+            if (s.empty() || b != s.back()) s.push_back(b);
+        }
+        if (!sorted) {
+            std::sort(s.begin(), s.end());
+            s.erase(std::unique(s.begin(), s.end()), s.end());
+        }
     };
     std::vector<std::vector<int64_t>> prim_sets(1);
     std::vector<std::vector<double>> prim_scores;
-    binset(path_list[order[0]], prim_sets[0]);
+    if (order.size() > 1) binset(path_list[order[0]], prim_sets[0]);      // only ever compared with other chains
     prim_scores.push_back({scores_list[order[0]]});
     std::vector<int64_t> b;
     for (size_t oi = 1; oi < order.size(); ++oi) {
@@ -455,14 +463,14 @@ struct GuideJob {
     int32_t readstart = 0, readend = 0;
 };
 
-static void windows_of(const std::vector<Anc> &raw_by_y, int64_t readgap, const Contigs &ctg, bool split_contigs,
+static void windows_of(const int64_t *ys, size_t n, int64_t readgap, const Contigs &ctg, bool split_contigs,
                        std::vector<std::pair<int64_t, int64_t>> &se)
 {
     se.clear();
-    se.push_back({raw_by_y[0].y, raw_by_y[0].y});
-    int cur = ctg.cid(raw_by_y[0].y);
-    for (size_t i = 1; i < raw_by_y.size(); ++i) {
-        const int64_t y = raw_by_y[i].y;
+    se.push_back({ys[0], ys[0]});
+    int cur = ctg.cid(ys[0]);
+    for (size_t i = 1; i < n; ++i) {
+        const int64_t y = ys[i];
         if ((y - se.back().second) < readgap && (!split_contigs || cur == ctg.cid(y))) se.back().second = y;
         else {
             if (se.back().first == se.back().second) se.pop_back();
@@ -503,24 +511,43 @@ static void make_guide_job(const Path &chain, int64_t L, int k, const Contigs &c
         if (d > readgap) readgap = d;
     }
     readgap = std::max<int64_t>(readgap + 1000, 5000);
-    std::vector<int64_t> keys(chain.size()), order;
-    for (size_t i = 0; i < chain.size(); ++i) keys[i] = chain[i].y;
-    argsort_replay<int64_t>(keys.data(), (int64_t)keys.size(), order);
-    std::vector<Anc> by_y(chain.size());
-    for (size_t i = 0; i < chain.size(); ++i) by_y[i] = chain[order[i]];
-    std::vector<std::pair<int64_t, int64_t>> se;
-    windows_of(by_y, readgap, ctg, false, se);
-    if (windows_to_ranges(se, ctg, look_span, job)) {
-        windows_of(by_y, readgap, ctg, true, se);
-        windows_to_ranges(se, ctg, look_span, job);
+    const size_t n = chain.size();
+    // Common case: read positions strictly descending (every chain out of the DP) and reference positions strictly
+    // monotone.  Then both argsorts (:23103 by reference position, :23183 by read position) have a single possible
+    // result and the guide points are the chain in ascending read order -- no permutation to replay.
+    bool x_desc = true, y_asc = true, y_desc = true;
+    for (size_t i = 1; i < n; ++i) {
+        if (!(chain[i].x < chain[i - 1].x)) x_desc = false;
+        if (!(chain[i - 1].y < chain[i].y)) y_asc = false;
+        if (!(chain[i].y < chain[i - 1].y)) y_desc = false;
     }
-    for (size_t i = 0; i < by_y.size(); ++i) keys[i] = by_y[i].x;
-    argsort_replay<int64_t>(keys.data(), (int64_t)keys.size(), order);
-    job.gx.resize(chain.size());
-    job.gy.resize(chain.size());
-    for (size_t i = 0; i < chain.size(); ++i) {
-        job.gx[i] = (int32_t)by_y[order[i]].x;
-        job.gy[i] = by_y[order[i]].y;
+    std::vector<int64_t> ys(n);
+    std::vector<std::pair<int64_t, int64_t>> se;
+    job.gx.resize(n);
+    job.gy.resize(n);
+    if (n >= 1 && x_desc && (y_asc || y_desc)) {
+        for (size_t i = 0; i < n; ++i) {
+            ys[i] = y_asc ? chain[i].y : chain[n - 1 - i].y;
+            job.gx[i] = (int32_t)chain[n - 1 - i].x;
+            job.gy[i] = chain[n - 1 - i].y;
+        }
+    } else {
+        std::vector<int64_t> keys(n), order;
+        for (size_t i = 0; i < n; ++i) keys[i] = chain[i].y;
+        argsort_replay<int64_t>(keys.data(), (int64_t)n, order);
+        std::vector<Anc> by_y(n);
+        for (size_t i = 0; i < n; ++i) { by_y[i] = chain[order[i]]; ys[i] = by_y[i].y; }
+        for (size_t i = 0; i < n; ++i) keys[i] = by_y[i].x;
+        argsort_replay<int64_t>(keys.data(), (int64_t)n, order);
+        for (size_t i = 0; i < n; ++i) {
+            job.gx[i] = (int32_t)by_y[order[i]].x;
+            job.gy[i] = by_y[order[i]].y;
+        }
+    }
+    windows_of(ys.data(), n, readgap, ctg, false, se);
+    if (windows_to_ranges(se, ctg, look_span, job)) {
+        windows_of(ys.data(), n, readgap, ctg, true, se);
+        windows_to_ranges(se, ctg, look_span, job);
     }
     job.readstart = (int32_t)std::max<int64_t>(0, (int64_t)job.gx.front() - look_span);
     job.readend = (int32_t)std::min<int64_t>(L - k + 1, (int64_t)job.gx.back() + look_span);

@@ -14,6 +14,7 @@
 #include <memory>
 #include <mutex>
 #include <cmath>
+#include <cstring>
 #include <ctime>
 #include <chrono>
 #include <functional>
@@ -90,7 +91,9 @@ struct Backend {
                               const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
                               ChainOut &out) = 0;
     // a = query, b = target of get_query_target_for_cigar; segs: exact-match segments the jobs refer to
-    virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const std::vector<vmg::MatchSeg> &segs) = 0;
+    virtual void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const vmg::MatchSeg *segs, size_t n_segs) = 0;
+    // optional: memory the backend wants the match segments written to (page-locked staging); nullptr = none
+    virtual vmg::MatchSeg *seg_staging(size_t n_segs) { (void)n_segs; return nullptr; }
     virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
     // sets cig_off / cig_len of every job; the returned array stays valid until the next fill()
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
@@ -327,15 +330,19 @@ private:
             } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); segj[t].clear(); }
         });
         std::vector<EdJob> ed;
-        std::vector<int64_t> ed_start, seg_start;
-        std::vector<vmg::MatchSeg> segs;
+        std::vector<int64_t> ed_start, seg_start((size_t)m + 1, 0);
+        std::vector<vmg::MatchSeg> segs_own;
         parallel_concat(edj, threads_, ed, ed_start);
-        parallel_concat(segj, threads_, segs, seg_start);
+        for (int64_t t = 0; t < m; ++t) seg_start[t + 1] = seg_start[t] + (int64_t)segj[t].size();
+        const size_t n_segs = (size_t)seg_start[m];
+        vmg::MatchSeg *segs = be_.seg_staging(n_segs);       // straight into the backend's staging when it has one
+        if (!segs) { segs_own.resize(n_segs); segs = segs_own.data(); }
         parallel_for(m, threads_, [&](int64_t t) {
+            if (!segj[t].empty()) memcpy(segs + seg_start[t], segj[t].data(), segj[t].size() * sizeof(vmg::MatchSeg));
             for (int64_t q = ed_start[t]; q < ed_start[t + 1]; ++q) ed[q].seg_off += seg_start[t];
-        }, 256);
+        }, 64);
         delete ph;
-        be_.edit_distance(b, ed, segs);
+        be_.edit_distance(b, ed, segs, n_segs);
         ph = new Phase(this, "g_ext_edges");
         parallel_for(m, threads_, [&](int64_t t) {
             ReadState &s = st[ids[t]];
