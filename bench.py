@@ -28,6 +28,19 @@ REF_LEN = 5_000_000
 WORKLOAD = "10k synthetic ONT reads (15 kb, 10% err) vs 5 Mb reference, -mode H, 1xB200 (BASELINE configs[1])"
 
 
+_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -152,7 +165,7 @@ def run_reference(args):
         vals.append(v)
         t_all += dt
     v = float(np.mean(vals))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "aligned_gbp_per_s", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
@@ -160,7 +173,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
                          "sample": "%d reads of the workload per step; oracle port (C stages + Python glue), %d processes"
                                    % (sample, cores)},
-        "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 KERNEL_BYTES_NOTE = {
@@ -190,6 +203,12 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="reads per sub-batch (0 = automatic)")
     ap.add_argument("--ahead", type=int, default=2, help="steps submitted ahead of the one being collected")
     args = ap.parse_args()
+    # stdout carries exactly one line, the JSON: everything else that writes to fd 1 while the run lasts (NCCL's
+    # version banner, library chatter) is sent to stderr, and the line goes out through the saved descriptor
+    global _STDOUT
+    sys.stdout.flush()
+    _STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -371,7 +390,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
                                     "sample": "%d reads of the workload, oracle port (C stages + Python glue), %d processes, "
                                               "%.1f s" % (sample, cores, dt)}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
