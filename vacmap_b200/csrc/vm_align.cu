@@ -283,6 +283,57 @@ __device__ __forceinline__ int vm_gap_distance(const VmSeqView &Q, int q0, int m
     return score;
 }
 
+// Match segments of a job from the anchors of its sub-alignment (device copy of vmg::match_segments, vm_glue.hpp):
+// the anchors of job j are anc[J.dir_off .. + J.n_out) in ascending read order; the segments replace them in
+// segs[J.dir_off ..) and J.n_out becomes their number (0: no bound possible -- a query gap beyond the 128 bases the
+// gap DP holds in registers, or mixed strands -- the exact kernel will take the job).
+__global__ void __launch_bounds__(128) vm_match_segments_kernel(VmAlnJobDev *jobs, int n_jobs, const VmAnchor *__restrict__ anc,
+                                                                VmMatchSeg *segs, int max_qgap)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_jobs) return;
+    VmAlnJobDev &J = jobs[t];
+    const int n = J.n_out;
+    const VmAnchor *A = anc + J.dir_off;
+    VmMatchSeg *out = segs + J.dir_off;
+    const long long qlen = J.q.len, tlen = J.t.len;
+    int m = 0;
+    bool ok = n >= 2;
+    if (ok) {
+        const VmAnchor pre = A[0], now = A[n - 1];
+        const bool fwd = pre.s == 1;
+        long long cq = 0, ct = 0;
+        for (int k = 0; k < n && ok; ++k) {
+            const VmAnchor a = fwd ? A[k] : A[n - 1 - k];
+            if (a.s != pre.s) { ok = false; break; }
+            long long q = fwd ? (long long)a.x - pre.x : (long long)now.x - a.x - a.l;
+            long long tt = fwd ? (long long)a.y - (long long)pre.y : (long long)a.y - ((long long)now.y + now.l);
+            long long l = a.l;
+            long long d = cq - q > ct - tt ? cq - q : ct - tt;
+            if (d < 0) d = 0;
+            q += d; tt += d; l -= d;
+            if (l > qlen - q) l = qlen - q;
+            if (l > tlen - tt) l = tlen - tt;
+            if (l <= 0) continue;
+            if (q - cq > max_qgap) { ok = false; break; }
+            VmMatchSeg sg;
+            sg.q = (int32_t)q; sg.t = (int32_t)tt; sg.l = (int32_t)l;
+            out[m++] = sg;
+            cq = q + l;
+            ct = tt + l;
+        }
+        if (ok && qlen - cq > max_qgap) ok = false;
+    }
+    J.n_out = ok ? m : -1;
+}
+
+int vm_launch_match_segments(VmAlnJobDev *jobs, int n_jobs, const VmAnchor *anc_dev, void *segs_dev, cudaStream_t stream)
+{
+    if (n_jobs <= 0) return 0;
+    vm_match_segments_kernel<<<(n_jobs + 127) / 128, 128, 0, stream>>>(jobs, n_jobs, anc_dev, (VmMatchSeg *)segs_dev, 128);
+    return 1;
+}
+
 __global__ void __launch_bounds__(128) vm_ed_upper_kernel(VmAlnJobDev *jobs, const int *__restrict__ job_ids, int n_jobs,
                                                           const VmMatchSeg *__restrict__ segs, VmSeqSources S)
 {
@@ -292,6 +343,7 @@ __global__ void __launch_bounds__(128) vm_ed_upper_kernel(VmAlnJobDev *jobs, con
     const VmSeqView Q = vm_view(S, J.q, J.read), T = vm_view(S, J.t, J.read);
     const VmMatchSeg *sg = segs + J.dir_off;
     const int n = J.n_out;
+    if (n < 0) { if (lane == 0) J.result0 = 1LL << 40; return; }      // no segments: no bound
     long long cost = 0;
     for (int i = lane; i <= n; i += 32) {
         int cq = 0, ct = 0;

@@ -71,6 +71,8 @@ int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *cl
                             cudaStream_t stream);
 // upper bound of the distance through the job's match segments (J.dir_off / J.n_out into segs_dev, 12-byte {q, t, l})
 int vm_launch_ed_upper(VmAlnJobDev *jobs, const int *ids_dev, int n_jobs, const void *segs_dev, VmSeqSources src, cudaStream_t stream);
+// derive the match segments of every job from its sub-alignment's anchors on the device (anc_dev[J.dir_off .. + J.n_out))
+int vm_launch_match_segments(VmAlnJobDev *jobs, int n_jobs, const VmAnchor *anc_dev, void *segs_dev, cudaStream_t stream);
 int vm_launch_extend(VmAlnJobDev *jobs, int n_jobs, VmSeqSources src, cudaStream_t stream);
 
 // ---- global fill (vm_fill.cu) ----

@@ -112,7 +112,7 @@ public:
         seed_.release();
         gx_.release();
         lx_.release();
-        { VmDevBuf *xb[] = {&x_ids_, &x_used_, &x_tmp_anc_, &x_tmp_S_, &x_tmp_len_, &x_tmp_score_}; for (VmDevBuf *x : xb) x->release(); }
+        { VmDevBuf *xb[] = {&x_ids_, &x_used_, &x_tmp_anc_, &x_tmp_S_, &x_tmp_len_, &x_tmp_score_, &d_ctg_}; for (VmDevBuf *x : xb) x->release(); }
         VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
                          &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_, &d_msegs_};
         for (VmDevBuf *x : b) x->release();
@@ -276,11 +276,15 @@ public:
     struct Extracted {
         VmDevBuf rec, anc, S, len, score, counters;
         VmPinnedBuf h_rec, h_anc, h_S, h_len, h_score, h_counters;
+        // local stage: rebuild_chain_break on the device
+        VmDevBuf al_rec, al_anc, al_len;
+        VmPinnedBuf h_al_rec, h_al_anc, h_al_len;
+        size_t al_n_anc = 0;
         void release()
         {
-            VmDevBuf *d[] = {&rec, &anc, &S, &len, &score, &counters};
+            VmDevBuf *d[] = {&rec, &anc, &S, &len, &score, &counters, &al_rec, &al_anc, &al_len};
             for (VmDevBuf *x : d) x->release();
-            VmPinnedBuf *h[] = {&h_rec, &h_anc, &h_S, &h_len, &h_score, &h_counters};
+            VmPinnedBuf *h[] = {&h_rec, &h_anc, &h_S, &h_len, &h_score, &h_counters, &h_al_rec, &h_al_anc, &h_al_len};
             for (VmPinnedBuf *x : h) x->release();
         }
     };
@@ -331,9 +335,31 @@ public:
                                                         x_tmp_anc_.as<VmAnchor>(), O, c_->stream);
             kt.stop();
         }
+        const bool rebuild = !global && rebuild_large_cost_ >= 0 && ih_ != nullptr;
+        if (rebuild) {
+            static_assert(sizeof(RebuildRec) == sizeof(VmRebuildRec), "rebuild record layout");
+            BE_OK(X.al_rec.ensure((size_t)(n + 1) * sizeof(VmRebuildRec)));
+            BE_OK(X.al_anc.ensure(T * 16));
+            BE_OK(X.al_len.ensure(T * 4));
+            BE_OK(x_tmp_len_.ensure(T * 4));
+            BE_OK(x_tmp_S_.ensure(T * 16));          // second anchor scratch (the extract kernel's is still being read)
+            BE_OK(cudaMemsetAsync(X.al_rec.p, 0, (size_t)(n + 1) * sizeof(VmRebuildRec), c_->stream));
+            upload_contig_starts();
+            VmRebuildOut R;
+            R.rec = X.al_rec.as<VmRebuildRec>();
+            R.anc = X.al_anc.as<VmAnchor>();
+            R.len = X.al_len.as<int32_t>();
+            R.n_anc_total = X.counters.as<unsigned long long>() + 2;
+            R.n_len_total = X.counters.as<unsigned long long>() + 3;
+            KTimer kt(this, "k_rebuild");
+            c_->launches += vm_launch_rebuild(x_ids_.as<int>(), (int)ids.size(), s.off_dev.as<int64_t>(), X.rec.as<VmExtractRec>(),
+                                              X.anc.as<VmAnchor>(), d_ctg_.as<int64_t>(), n_ctg_dev_, rebuild_large_cost_, 50,
+                                              x_tmp_S_.as<VmAnchor>(), x_tmp_len_.as<int32_t>(), R, c_->stream);
+            kt.stop();
+        }
         BE_OK(X.h_counters.ensure(64));
         BE_OK(X.h_rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
-        BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 16, cudaMemcpyDeviceToHost, c_->stream));
+        BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 32, cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(cudaMemcpyAsync(X.h_rec.p, X.rec.p, (size_t)n * sizeof(VmExtractRec), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
@@ -352,7 +378,22 @@ public:
             BE_OK(X.h_score.ensure((size_t)(n + 1) * 8));
             BE_OK(cudaMemcpyAsync(X.h_score.p, X.score.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c_->stream));
         }
+        if (rebuild) {
+            const size_t ra = (size_t)X.h_counters.as<unsigned long long>()[2], rl = (size_t)X.h_counters.as<unsigned long long>()[3];
+            X.al_n_anc = ra;
+            BE_OK(X.h_al_rec.ensure((size_t)(n + 1) * sizeof(VmRebuildRec)));
+            BE_OK(X.h_al_anc.ensure(std::max<size_t>(ra, 1) * 16));
+            BE_OK(X.h_al_len.ensure(std::max<size_t>(rl, 1) * 4));
+            BE_OK(cudaMemcpyAsync(X.h_al_rec.p, X.al_rec.p, (size_t)n * sizeof(VmRebuildRec), cudaMemcpyDeviceToHost, c_->stream));
+            if (ra) BE_OK(cudaMemcpyAsync(X.h_al_anc.p, X.al_anc.p, ra * 16, cudaMemcpyDeviceToHost, c_->stream));
+            if (rl) BE_OK(cudaMemcpyAsync(X.h_al_len.p, X.al_len.p, rl * 4, cudaMemcpyDeviceToHost, c_->stream));
+        }
         BE_OK(vm_stream_sync(c_->stream));
+        if (rebuild) {
+            out.al_rec = X.h_al_rec.as<RebuildRec>();
+            out.al_anc = X.h_al_anc.as<Anc32>();
+            out.al_len = X.h_al_len.as<int32_t>();
+        }
         out.rec = X.h_rec.as<ExtractRec>();
         out.x_anc = X.h_anc.as<Anc32>();
         out.x_S = X.h_S.as<double>();
@@ -569,7 +610,21 @@ public:
         std::vector<int> xids;
         for (int64_t r = 0; r < n; ++r)
             if (variant[r] != 0 && out.cnt[r] > 0) xids.push_back((int)r);
+        rebuild_large_cost_ = maxdiff;        // rebuild_chain_break's large_cost is the local maxdiff (:19243)
         extract(false, n, dense, xids, 0.0, lx_, out);
+        rebuild_large_cost_ = -1;
+    }
+
+    // contig start offsets on the device (pos2contig for the rebuild kernel), refreshed when the index changes
+    void upload_contig_starts()
+    {
+        if (d_ctg_for_ == ih_) return;
+        const std::vector<int64_t> &st = ih_->ctg.start;
+        BE_OK(d_ctg_.ensure(st.size() * 8 + 64));
+        BE_OK(cudaMemcpyAsync(d_ctg_.p, st.data(), st.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
+        n_ctg_dev_ = (int)st.size();
+        d_ctg_for_ = ih_;
     }
 
     // side streams of this backend (created on first use), ordered against the main stream with events
@@ -679,8 +734,9 @@ public:
         const bool check = getenv("VM_ED_CHECK") != nullptr;   // debug: also run the exact kernel and compare
         std::vector<int> open_jobs;
         std::vector<int> ub;
+        bool on_device = false;
         for (int j = 0; j < nj; ++j) {
-            if (jobs[j].seg_n > 0 && jobs[j].band >= 0) ub.push_back(j);
+            if (jobs[j].seg_n > 0 && jobs[j].band >= 0) { ub.push_back(j); on_device = on_device || jobs[j].segs_on_device; }
             else open_jobs.push_back(j);
         }
         std::vector<int64_t> bound;
@@ -697,18 +753,21 @@ public:
                 J[t].n_out = e.seg_n;
             }, 1024);
             static_assert(sizeof(vmg::MatchSeg) == 12, "match segment layout");
-            BE_OK(d_msegs_.ensure(n_segs * sizeof(vmg::MatchSeg) + 64));
+            BE_OK(d_msegs_.ensure(std::max(n_segs, on_device ? lx_.al_n_anc : (size_t)0) * sizeof(vmg::MatchSeg) + 64));
             BE_OK(d_seg_.ensure((size_t)nu * 4 + 64));
             std::vector<int> ids((size_t)nu);
             for (int t = 0; t < nu; ++t) ids[t] = t;
-            if (segs != h_segs_.as<vmg::MatchSeg>()) {      // a caller that did not use seg_staging()
+            if (!on_device && segs != h_segs_.as<vmg::MatchSeg>()) {      // a caller that did not use seg_staging()
                 BE_OK(h_segs_.ensure(n_segs * sizeof(vmg::MatchSeg) + 64));
                 memcpy(h_segs_.p, segs, n_segs * sizeof(vmg::MatchSeg));
             }
-            BE_OK(cudaMemcpyAsync(d_msegs_.p, h_segs_.p, n_segs * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
+            if (!on_device)
+                BE_OK(cudaMemcpyAsync(d_msegs_.p, h_segs_.p, n_segs * sizeof(vmg::MatchSeg), cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(d_seg_.p, ids.data(), (size_t)nu * 4, cudaMemcpyHostToDevice, c_->stream));
             BE_OK(cudaMemcpyAsync(jobs_.p, J, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyHostToDevice, c_->stream));
             KTimer kt(this, "k_ed_upper");
+            if (on_device)      // the segments are derived from the sub-alignments' anchors the rebuild kernel left in HBM
+                c_->launches += vm_launch_match_segments(jobs_.as<VmAlnJobDev>(), nu, lx_.al_anc.as<VmAnchor>(), d_msegs_.p, c_->stream);
             c_->launches += vm_launch_ed_upper(jobs_.as<VmAlnJobDev>(), d_seg_.as<int>(), nu, d_msegs_.p, sources(), c_->stream);
             kt.stop();
             BE_OK(cudaMemcpyAsync(J, jobs_.p, (size_t)nu * sizeof(VmAlnJobDev), cudaMemcpyDeviceToHost, c_->stream));
@@ -941,6 +1000,10 @@ private:
     cudaEvent_t side_done_[3] = {nullptr, nullptr, nullptr}, side_go_ = nullptr;
     Extracted gx_, lx_;
     bool want_local_score_ = false;
+    int rebuild_large_cost_ = -1;          // >= 0 while the local extraction should also rebuild the sub-alignments
+    VmDevBuf d_ctg_;
+    int n_ctg_dev_ = 0;
+    const vm_index_handle *d_ctg_for_ = nullptr;
     VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
     VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;
     std::vector<int64_t> off_host_;

@@ -149,3 +149,85 @@ int vm_launch_extract_local(const int *ids_dev, int n_ids, const int64_t *off, c
     vm_extract_local_kernel<<<(n_ids + 63) / 64, 64, 0, stream>>>(ids_dev, n_ids, off, cnt, sorted, S, P, gmax, tmp_anc, out);
     return 1;
 }
+
+// ---- rebuild_chain_break (:23437-23484) on the extracted local path: colinear sub-alignments ----
+// pos2contig (:51-59): last contig whose start <= pos (the first one if pos precedes all)
+__device__ __forceinline__ int vm_cid(const int64_t *__restrict__ starts, int n, long long pos)
+{
+    int lo = 0, hi = n;           // first index with starts[i] > pos
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (starts[mid] <= pos) lo = mid + 1; else hi = mid;
+    }
+    return lo > 0 ? lo - 1 : 0;
+}
+
+__global__ void __launch_bounds__(64) vm_rebuild_kernel(const int *__restrict__ ids, int n_ids, const int64_t *__restrict__ off,
+                                                        const VmExtractRec *__restrict__ rec, const VmAnchor *__restrict__ path_all,
+                                                        const int64_t *__restrict__ ctg_start, int n_ctg, int large_cost,
+                                                        int small_alignment, VmAnchor *tmp_anc, int32_t *tmp_len, VmRebuildOut out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ids) return;
+    const int r = ids[t];
+    VmRebuildRec rr;
+    rr.anc_off = 0; rr.len_off = 0; rr.n_anc = 0; rr.n_al = 0;
+    const int n = rec[r].n_anc;
+    if (n <= 1) { out.rec[r] = rr; return; }
+    const VmAnchor *raw = path_all + rec[r].anc_off;       // ascending read order
+    VmAnchor *oa = tmp_anc + off[r];                         // scratch: the read's slice of the anchor arena
+    int32_t *ol = tmp_len + off[r];
+    int k = 0, na = 0, cur = 0;                              // anchors written, sub-alignments closed, length of the open one
+    VmAnchor pre = raw[0];
+    oa[k++] = pre;
+    cur = 1;
+    for (int i = 1; i < n; ++i) {
+        const VmAnchor now = raw[i];
+        if (pre.s == now.s) {
+            const long long readgap = (long long)now.x - pre.x - pre.l;
+            const long long refgap = pre.s == 1 ? (long long)now.y - (long long)pre.y - pre.l : (long long)pre.y - (long long)now.y - now.l;
+            long long d = readgap - refgap;
+            if (d < 0) d = -d;
+            if (d <= large_cost && refgap >= -20 && readgap < 100 &&
+                vm_cid(ctg_start, n_ctg, (long long)pre.y) == vm_cid(ctg_start, n_ctg, (long long)now.y)) {
+                if (refgap >= 0 || readgap > 20) { oa[k++] = now; ++cur; pre = now; }
+                continue;                                    // small negative refgap with readgap <= 20: the anchor is dropped
+            }
+        }
+        // break: close the open sub-alignment
+        if (cur == 1) { --k; cur = 0; }                      // singleton: dropped
+        else { ol[na++] = cur; cur = 0; }
+        if (na > 0) {                                        // the (new) last one must span >= small_alignment read bases
+            const int len = ol[na - 1];
+            if (oa[k - 1].x + oa[k - 1].l - oa[k - len].x < small_alignment) { k -= len; --na; }
+        }
+        oa[k++] = now;
+        cur = 1;
+        pre = now;
+    }
+    if (cur == 1) { --k; cur = 0; }
+    else if (cur > 1) { ol[na++] = cur; cur = 0; }
+    if (na > 0) {
+        const int len = ol[na - 1];
+        if (oa[k - 1].x + oa[k - 1].l - oa[k - len].x < small_alignment) { k -= len; --na; }
+    }
+    rr.n_anc = k;
+    rr.n_al = na;
+    if (na > 0) {
+        rr.anc_off = (long long)atomicAdd(out.n_anc_total, (unsigned long long)k);
+        rr.len_off = (long long)atomicAdd(out.n_len_total, (unsigned long long)na);
+        for (int x = 0; x < k; ++x) out.anc[rr.anc_off + x] = oa[x];
+        for (int x = 0; x < na; ++x) out.len[rr.len_off + x] = ol[x];
+    }
+    out.rec[r] = rr;
+}
+
+int vm_launch_rebuild(const int *ids_dev, int n_ids, const int64_t *off, const VmExtractRec *rec, const VmAnchor *path,
+                      const int64_t *ctg_start_dev, int n_ctg, int large_cost, int small_alignment, VmAnchor *tmp_anc, int32_t *tmp_len,
+                      const VmRebuildOut &out, cudaStream_t stream)
+{
+    if (n_ids <= 0) return 0;
+    vm_rebuild_kernel<<<(n_ids + 63) / 64, 64, 0, stream>>>(ids_dev, n_ids, off, rec, path, ctg_start_dev, n_ctg, large_cost,
+                                                           small_alignment, tmp_anc, tmp_len, out);
+    return 1;
+}

@@ -28,3 +28,21 @@ int vm_launch_extract_global(const int *ids_dev, int n_ids, const int64_t *off, 
 int vm_launch_extract_local(const int *ids_dev, int n_ids, const int64_t *off, const int32_t *cnt, const VmAnchor *sorted,
                             const double *S, const int32_t *P, const int64_t *gmax, VmAnchor *tmp_anc, const VmExtractOut &out,
                             cudaStream_t stream);
+
+// rebuild_chain_break on the device: per read, the colinear sub-alignments of its local path
+struct VmRebuildRec {
+    long long anc_off;    // into VmRebuildOut::anc: the anchors of all its sub-alignments, back to back
+    long long len_off;    // into VmRebuildOut::len: anchors per sub-alignment
+    int32_t n_anc;
+    int32_t n_al;         // 0: the reference raises here (no sub-alignment left) -> the read has no records
+};
+struct VmRebuildOut {
+    VmRebuildRec *rec;                    // [n_reads]
+    VmAnchor *anc;
+    int32_t *len;
+    unsigned long long *n_anc_total;      // bump allocators, zeroed by the host
+    unsigned long long *n_len_total;
+};
+int vm_launch_rebuild(const int *ids_dev, int n_ids, const int64_t *off, const VmExtractRec *rec, const VmAnchor *path,
+                      const int64_t *ctg_start_dev, int n_ctg, int large_cost, int small_alignment, VmAnchor *tmp_anc, int32_t *tmp_len,
+                      const VmRebuildOut &out, cudaStream_t stream);

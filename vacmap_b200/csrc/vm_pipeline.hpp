@@ -42,6 +42,12 @@ struct ExtractRec {
     int32_t n_anc, n_chains;
 };
 
+// where a read's device-rebuilt sub-alignments sit in ChainOut::al_* (layout of VmRebuildRec, vm_extract.cuh)
+struct RebuildRec {
+    long long anc_off, len_off;
+    int32_t n_anc, n_al;
+};
+
 struct ChainOut {
     std::vector<int64_t> start;
     std::vector<int32_t> cnt;
@@ -58,6 +64,12 @@ struct ChainOut {
     const double *x_S = nullptr;
     const int32_t *x_len = nullptr;
     const double *x_score = nullptr;
+    // Local stage only, when the backend also ran rebuild_chain_break (:23437-23484) on the path: per read its
+    // colinear sub-alignments (anchors back to back in al_anc, anchors per sub-alignment in al_len).  The same
+    // anchors stay on the device; EdJob::seg_off then counts in that device array (al_rec[r].anc_off + ...).
+    const RebuildRec *al_rec = nullptr;
+    const Anc32 *al_anc = nullptr;
+    const int32_t *al_len = nullptr;
     std::vector<Anc32> sorted_store;
     std::vector<double> S_store;
     std::vector<int32_t> P_store, A_store;
@@ -71,7 +83,10 @@ struct GuideJobRef { int32_t read; vmg::GuideJob job; };
 // band: half-width k of the Ukkonen band (-1 = none); dist is exact when <= band, else only known to be > band
 // seg_off/seg_n: exact-match segments of the job inside the array handed to Backend::edit_distance (seg_n = 0:
 // none); with them a backend may return in `dist` any upper bound of the distance that is <= band
-struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; int64_t band = -1; int64_t seg_off = 0; int32_t seg_n = 0; };
+// segs_on_device: seg_off / seg_n address the sub-alignment's ANCHORS in the backend's device copy (ChainOut::al_anc)
+// and the backend derives the segments there
+struct EdJob { int32_t read; vmg::SeqRef a, b; int64_t dist = 0; int64_t band = -1; int64_t seg_off = 0; int32_t seg_n = 0;
+               bool segs_on_device = false; };
 struct ExtJobRef { int32_t read; vmg::ExtJob job; };
 // CIGAR ops of a fill job: cig[cig_off .. cig_off + cig_len) of the array Backend::fill hands back
 struct FillJobRef { int32_t read; vmg::FillJob job; int64_t cig_off = 0; int32_t cig_len = 0; };
@@ -257,7 +272,9 @@ public:
         std::vector<int64_t> todo;
         for (int64_t r = 0; r < n; ++r)
             if (st[r].alive) todo.push_back(r);
+        first_pass_ = true;
         extend_pass(b, read_len, st, todo);
+        first_pass_ = false;     // the rare second pass rebuilds on the host (the device copy has served its jobs)
         // second pass (:24079-24080): paired large indels after a filtered sub-alignment
         std::vector<int64_t> again;
         for (int64_t r : todo) {
@@ -297,6 +314,33 @@ private:
             s.recs.clear();
             s.filtered = false;
             try {
+                if (first_pass_ && lc_ && lc_->al_rec) {
+                    // sub-alignments rebuilt on the device: widen them, the match segments are derived there too
+                    SubScope sc(sub_, SP_TRACE);
+                    const RebuildRec &x = lc_->al_rec[r];
+                    if (x.n_al == 0) throw vmg::ReadDropped("rebuild_chain_break: empty");
+                    s.al.assign((size_t)x.n_al, Path());
+                    long long ao = x.anc_off;
+                    for (int32_t i = 0; i < x.n_al; ++i) {
+                        const int32_t len = lc_->al_len[x.len_off + i];
+                        Path &p = s.al[(size_t)i];
+                        p.resize((size_t)len);
+                        for (int32_t k = 0; k < len; ++k) p[(size_t)k] = vmg::widen(lc_->al_anc[ao + k]);
+                        EdJob j;
+                        j.read = (int32_t)r;
+                        vmg::query_target(p.front(), p.back(), read_len[r], ctg_, j.b, j.a);
+                        if (std::min(j.a.len(), j.b.len()) == 0) throw vmg::ReadDropped("division by zero");
+                        j.seg_off = ao;
+                        j.seg_n = len;
+                        j.segs_on_device = true;
+                        orient(j.a, s.need_reverse);
+                        orient(j.b, s.need_reverse);
+                        j.band = divergence_band(std::min(j.a.len(), j.b.len()));
+                        edj[t].push_back(j);
+                        ao += len;
+                    }
+                    return;
+                }
                 const Path *asc = &s.asc;
                 thread_local Path widened;
                 if (lc_ && lc_->rec) {
@@ -495,6 +539,7 @@ private:
     }
 
     SubTimes sub_;
+    bool first_pass_ = false;
     const ChainOut *lc_ = nullptr;     // local-stage result of the batch in flight (valid during align_batch)
     Backend &be_;
     const vmg::Contigs &ctg_;
