@@ -8,6 +8,7 @@
 import collections
 import ctypes
 import gzip
+import weakref
 
 import numpy as np
 
@@ -202,6 +203,7 @@ class Aligner:
         res = ctypes.c_void_p()
         ctx = self.index.ctx
         _lib.check(ctx.h, L.vm_align_wait(job, ctypes.byref(res)))
+        keep = False
         try:
             nrec, nops = L.vm_result_num_records(res), L.vm_result_num_cigar_ops(res)
             off = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_offsets(res), ctypes.POINTER(ctypes.c_int64)),
@@ -212,15 +214,20 @@ class Aligner:
                 recs = raw.view(RECORD_DTYPE).copy()
             else:
                 recs = np.zeros(0, dtype=RECORD_DTYPE)
-            if nops:
-                cig = np.ctypeslib.as_array(ctypes.cast(L.vm_result_cigar(res), ctypes.POINTER(ctypes.c_uint32)),
-                                            shape=(nops,)).copy()
-            else:
-                cig = np.zeros(0, dtype=np.uint32)
             txt = (L.vm_result_stage_times(res) or b"").decode()
             self.last_stage_ms = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in txt.split(";") if "=" in kv}
+            if nops:
+                # the CIGAR arena (the bulk of the result) is not copied: the array views the library's memory,
+                # which is released when the last view of it is gone
+                buf = (ctypes.c_uint32 * nops).from_address(L.vm_result_cigar(res))
+                weakref.finalize(buf, L.vm_result_free, res)
+                keep = True
+                cig = np.frombuffer(buf, dtype=np.uint32)
+            else:
+                cig = np.zeros(0, dtype=np.uint32)
         finally:
-            L.vm_result_free(res)
+            if not keep:
+                L.vm_result_free(res)
         return off, recs, cig
 
     def align_packed(self, seq_cat, seq_off, resident=False):

@@ -341,7 +341,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
     plan.dir_bytes = 0;
     constexpr int ND = 256, NQ = VM_FB_CAP / 8 + 1, NKEY = VM_FB_MAXC * ND * NQ;     // D / 8 in [-128, 128) covers |D| < 1024
     const int T = std::max(1, std::min(std::min(host_threads, 8), nj / 8192 + 1));
-    std::vector<int32_t> keys((size_t)nj);
+    std::vector<int32_t> keys((size_t)nj), bmin((size_t)nj), bmax((size_t)nj);      // key and own band of every job
     std::vector<std::vector<int32_t>> hist((size_t)T, std::vector<int32_t>((size_t)NKEY, 0));
     auto slice = [&](int t, int &lo, int &hi) { lo = (int)((long long)nj * t / T); hi = (int)((long long)nj * (t + 1) / T); };
     vmp::parallel_for(T, T, [&](int64_t t) {
@@ -352,6 +352,8 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
             int kmin, kmax;
             keys[j] = -1;
             if (J[j].t.len <= 0 || J[j].q.len <= 0 || !vm_fillb_own_band(J[j].t.len, J[j].q.len, kmin, kmax)) continue;
+            bmin[j] = kmin;
+            bmax[j] = kmax;
             const int c = ((kmax - kmin) / 2 + 1 + 31) / 32;
             int db = ((J[j].q.len - J[j].t.len) >> 3) + ND / 2;
             db = db < 0 ? 0 : db >= ND ? ND - 1 : db;
@@ -398,13 +400,12 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
             VmFillBandPair &pr = t.pr;
             pr.a = order[(size_t)xa];
             pr.b = xb < hi ? order[(size_t)xb] : -1;
-            vm_fillb_own_band(J[pr.a].t.len, J[pr.a].q.len, pr.kmin, pr.kmax);
+            pr.kmin = bmin[(size_t)pr.a];
+            pr.kmax = bmax[(size_t)pr.a];
             t.steps = J[pr.a].t.len + J[pr.a].q.len;
             if (pr.b >= 0) {
-                int bmin, bmax;
-                vm_fillb_own_band(J[pr.b].t.len, J[pr.b].q.len, bmin, bmax);
-                pr.kmin = std::min(pr.kmin, bmin);
-                pr.kmax = std::max(pr.kmax, bmax);
+                pr.kmin = std::min(pr.kmin, bmin[(size_t)pr.b]);
+                pr.kmax = std::max(pr.kmax, bmax[(size_t)pr.b]);
                 t.steps = std::max(J[pr.a].t.len, J[pr.b].t.len) + std::max(J[pr.a].q.len, J[pr.b].q.len);
             }
             const int rows = (pr.kmax - pr.kmin) / 2 + 1;
