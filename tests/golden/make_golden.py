@@ -131,6 +131,14 @@ def gen_e2e():
     ref3 = synth.make_reference(3, 600000, n_contigs=2)
     reads3 = synth.make_reads(ref3, 12, 8, read_len=15000, err=0.10, sv_frac=0.3)
     case("synth600k_2ctg_H", ref3, reads3, "H")
+    # more of the option / mode space, all from the reference's own code: hard clips with the approximate SA CIGAR,
+    # mode L (mammap_ccs) on HiFi-like reads, mode S (mammap_sensitive) on reads with nested SVs
+    case("synth300k_H_hardclip_fakecigar", ref2, reads2[:8], "H", H=True, fakecigar=True)
+    reads4 = synth.make_reads(ref2, 13, 8, read_len=6000, err=0.005, ratio=(1, 1, 1), sv_frac=0.5)
+    case("synth300k_L", ref2, reads4, "L")
+    case("synth300k_L_eqx_md_longcs", ref2, reads4[:4], "L", eqx=True, md=True, shortcs=False)
+    reads5 = synth.make_reads(ref2, 14, 8, read_len=6000, err=0.10, sv_frac=0.8)
+    case("synth300k_S", ref2, reads5, "S")
     with gzip.open(os.path.join(HERE, "e2e.json.gz"), "wt") as f:
         json.dump(out, f)
     print("e2e.json.gz:", os.path.getsize(os.path.join(HERE, "e2e.json.gz")), "bytes")

@@ -20,11 +20,21 @@ def case_inputs(name):
     if name.startswith("testdata"):
         ref = [(n, s) for n, s, _ in shim.read_fastx(os.path.join(td, "reference.fasta.gz"))]
         reads = [(r[0], r[1]) for r in shim.read_fastx(os.path.join(td, "read.fasta.gz"))]
+    elif name.startswith("synth300k_L"):
+        ref = synth.make_reference(1, 300000)
+        reads = synth.make_reads(ref, 13, 8, read_len=6000, err=0.005, ratio=(1, 1, 1), sv_frac=0.5)
+        if name.endswith("longcs"):
+            reads = reads[:4]
+    elif name == "synth300k_S":
+        ref = synth.make_reference(1, 300000)
+        reads = synth.make_reads(ref, 14, 8, read_len=6000, err=0.10, sv_frac=0.8)
     elif name.startswith("synth300k"):
         ref = synth.make_reference(1, 300000)
         reads = synth.make_reads(ref, 11, 16, read_len=6000, err=0.10, sv_frac=0.5)
         if name.endswith("eqx"):
             reads = reads[:6]
+        if name.endswith("fakecigar"):
+            reads = reads[:8]
     elif name.startswith("synth600k"):
         ref = synth.make_reference(3, 600000, n_contigs=2)
         reads = synth.make_reads(ref, 12, 8, read_len=15000, err=0.10, sv_frac=0.3)
