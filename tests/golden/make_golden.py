@@ -150,3 +150,37 @@ if __name__ == "__main__":
         gen_chain()
     if "e2e" in what:
         gen_e2e()
+
+
+def gen_sam_comments():
+    """SAM text with FASTQ comments and base qualities (get_bam_dict_str_comments, --copycomments) from the reference's
+    own emitter, fed with the records already pinned in e2e.json.gz -> tests/golden/sam_comments.json.gz."""
+    import gzip
+    import json
+    import refrun
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_oracle_e2e import case_inputs
+    e2e = json.load(gzip.open(os.path.join(HERE, "e2e.json.gz"), "rt"))
+    out = {"cases": []}
+    comments = "XA:i:5\tNM:i:7\tab:Z:hello there\tbad\tzz:Q:1\tRG:Z:other\tXB:f:1.5"
+    for name in ("testdata_H_eqx_md", "synth300k_H", "synth300k_H_hardclip_fakecigar"):
+        case = [c for c in e2e["cases"] if c["name"] == name][0]
+        ref, reads = case_inputs(name)
+        R = refrun.ReferenceRunner(ref, mode=case["mode"], **case["opt"])
+        lines = []
+        for (rid, seq), recs in zip(reads, case["records"]):
+            if not recs:
+                lines.append([])
+                continue
+            qual = "".join(chr(33 + (i * 7) % 40) for i in range(len(seq)))
+            lines.append(R.mod.get_bam_dict_str_comments([tuple(r) for r in recs], seq.upper(), qual, comments, R.contig2iloc,
+                                                         R.contig2seq, R.option["md"], R.option["shortcs"], R.option["cigar2cg"],
+                                                         R.option["markunbalancetra"], R.option))
+        out["cases"].append({"name": name, "comments": comments, "sam": lines})
+        print(name, sum(len(x) for x in lines), "lines")
+    with gzip.open(os.path.join(HERE, "sam_comments.json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
+if __name__ == "__main__" and "samcomments" in sys.argv[1:]:
+    gen_sam_comments()
