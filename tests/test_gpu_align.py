@@ -35,6 +35,14 @@ def test_fill_cigars_match_oracle(gpu_ctx):
     t2, q2 = pairs(rng, 12, 500, 1400)          # targets beyond one 256-row band
     ts += t2 + ["A", "ACGT", "ACGTNNACGT", "TTTTTTTTTT"]
     qs += q2 + ["ACGTACGT", "A", "ACGTNNACGA", "TTTTT"]
+    # the common case in bulk, so that every slot class (two pairs per warp up to 64 band rows, one beyond) sees
+    # full warps, a half-empty last warp and partners of unequal length
+    for i in range(523):
+        n = int(rng.integers(96, 760))
+        t = synth.random_seq(rng, n)
+        q = synth.mutate(rng, t, float(rng.choice([0.05, 0.10, 0.12])))[:760]
+        ts.append(t.tobytes().decode())
+        qs.append(q.tobytes().decode())
     for eqx in (False, True):
         got = pairs_batch("fill", ts, qs, eqx=eqx, ctx=gpu_ctx)
         for t, q, g in zip(ts, qs, got):
@@ -120,6 +128,14 @@ def test_banded_fill_certificate_and_fallback(gpu_ctx):
             q = synth.mutate(rng, t, float(rng.choice([0.02, 0.10, 0.15, 0.20])))
         if len(q) < 96:
             q = np.concatenate([q, synth.random_seq(rng, 96)])
+        ts.append(t.tobytes().decode())
+        qs.append(q.tobytes().decode())
+    # the common case in bulk, so that every slot class (two pairs per warp up to 64 band rows, one beyond) sees
+    # full warps, a half-empty last warp and partners of unequal length
+    for i in range(523):
+        n = int(rng.integers(96, 760))
+        t = synth.random_seq(rng, n)
+        q = synth.mutate(rng, t, float(rng.choice([0.05, 0.10, 0.12])))[:760]
         ts.append(t.tobytes().decode())
         qs.append(q.tobytes().decode())
     for eqx in (False, True):

@@ -32,6 +32,14 @@ __device__ __forceinline__ unsigned vm_code_half(int c)
     return c == 0 ? 0x0000u : c == 1 ? 0x3c00u : c == 2 ? 0x4000u : c == 3 ? 0x4200u : 0x7fffu;
 }
 
+// The same codes, high byte only (their low bytes are zero; N = 0x7f00 is still a NaN): two jobs in 16 bits of
+// shared memory, spread to the half2 operand with one byte permute
+__device__ __forceinline__ unsigned vm_code_byte(int c)
+{
+    return c == 0 ? 0x00u : c == 1 ? 0x3cu : c == 2 ? 0x40u : c == 3 ? 0x42u : 0x7fu;
+}
+__device__ __forceinline__ __half2 vm_codes_half2(unsigned two_bytes) { return vm_h2(__byte_perm(two_bytes, 0u, 0x1404)); }
+
 // One cell for both jobs.  in: v = v(i-1,j), x1/x2 = x(i-1,j) from the cell above; u/y1/y2 = from the cell to the
 // left.  out: the same quantities for (i,j), and the direction bits of job A in byte 0 / job B in byte 2.
 __device__ __forceinline__ void vm_cell2(__half2 tc, __half2 qc, __half2 &v, __half2 &x1, __half2 &x2, __half2 &u, __half2 &y1,

@@ -27,7 +27,8 @@
 
 namespace {
 
-#define VM_FB_CAP 768          // longest target / query the banded kernel stages in shared memory
+#define VM_FB_CAP 768          // longest target / query the banded kernel stages in shared memory (whole-warp pairs)
+#define VM_FB_CAP2 512         // ... of the half-warp pairs
 #define VM_FB_NEG (-1000)      // "-infinity" of the difference recurrences (exact in fp16)
 
 __device__ __forceinline__ int vm_gapcost(int n)
@@ -61,45 +62,58 @@ __device__ __forceinline__ __half2 vm_boundary_step(int index)
     return index == 0 ? VM_H2C(-(g.q1 + g.e1)) : index < 20 ? VM_H2C(-g.e1) : VM_H2C(-g.e2);
 }
 
-template <int C>
+// G pairs of jobs per warp (G = 1: 32 lanes per pair, G = 2: 16), C register slots per lane: the band of a pair holds
+// at most (32 / G) * C rows per anti-diagonal.  The half-warp classes fit the common 200..350-base segments (their
+// bands need 40..60 rows) into 48 or 64 rows instead of 64 or 96, and share the per-step bookkeeping between four jobs.
+template <int C, int G>
 __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
                                                        int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
                                                        long long dir_words_per_warp, int *counter, uint32_t *cigar_out,
                                                        uint32_t *dense_out, unsigned long long *dense_count, uint2 *results)
 {
     constexpr VmGapPar2 g = vm_fill_par();
+    constexpr int LJ = 32 / G;                                    // lanes of one pair
+    constexpr int CAP = G == 1 ? VM_FB_CAP : VM_FB_CAP2;          // longest sequence staged
     constexpr int CW = (C + 1) / 2;                               // direction words per lane and step
-    constexpr int NL = (31 / C + 2) < 32 ? (31 / C + 2) : 32;     // lanes a 32-row tile can touch
+    constexpr int TS = LJ;                                        // traceback tile: TS steps x TS rows
+    constexpr int NL = ((TS - 1) / C + 2) < LJ ? ((TS - 1) / C + 2) : LJ;     // lanes a TS-row tile can touch
     constexpr int TW = NL * CW;                                   // tile words per step
+    constexpr int GROUP_WORDS = CAP + 2 * TS * TW;                // [T codes u16 | Q codes u16 | two tiles]
     extern __shared__ uint32_t vm_fb_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *sT = vm_fb_smem + (size_t)warp * (2 * VM_FB_CAP + 2 * 32 * TW);
-    uint32_t *sQ = sT + VM_FB_CAP;
-    uint32_t *tile = sQ + VM_FB_CAP;                              // [2][32][TW]
+    const int grp = lane / LJ, gl = lane % LJ;
+    uint32_t *gbase = vm_fb_smem + ((size_t)warp * G + grp) * GROUP_WORDS;
+    uint16_t *sT = reinterpret_cast<uint16_t *>(gbase);           // high byte of the fp16 code: job A low byte, B high
+    uint16_t *sQ = sT + CAP;
+    uint32_t *tile = gbase + CAP;                                 // [2][TS][TW]
     const long long gw = (long long)blockIdx.x * 4 + warp;
     uint32_t *dir = dir_all + gw * dir_words_per_warp;
     const __half2 neg2 = VM_H2C(VM_FB_NEG), zero2 = VM_H2C(0);
     const __half2 open1 = VM_H2C(-(g.q1 + g.e1)), open2 = VM_H2C(-(g.q2 + g.e2)), ext2 = VM_H2C(-g.e2);
     for (;;) {
         int p = 0;
-        if (lane == 0) p = pair_begin + atomicAdd(counter, 1);
+        if (lane == 0) p = pair_begin + atomicAdd(counter, G);
         p = __shfl_sync(VM_FULL, p, 0);
         if (p >= pair_end) break;
-        const VmFillBandPair pr = pairs[p];
+        p += grp;
+        const bool live = p < pair_end;                           // the last warp's second half may have no pair
+        VmFillBandPair pr;
+        if (live) pr = pairs[p];
+        else { pr.a = -1; pr.b = -1; pr.kmin = 0; pr.kmax = 0; }
         const bool hasB = pr.b >= 0;
-        VmAlnJobDev &JA = jobs[pr.a];
-        VmAlnJobDev &JB = jobs[hasB ? pr.b : pr.a];
+        VmAlnJobDev &JA = jobs[live ? pr.a : 0];
+        VmAlnJobDev &JB = jobs[hasB ? pr.b : (live ? pr.a : 0)];
         const VmSeqView TA = vm_view(S, JA.t, JA.read), QA = vm_view(S, JA.q, JA.read);
         const VmSeqView TB = vm_view(S, JB.t, JB.read), QB = vm_view(S, JB.q, JB.read);
-        const int tA = TA.len, qA = QA.len, tB = hasB ? TB.len : 0, qB = hasB ? QB.len : 0;
+        const int tA = live ? TA.len : 0, qA = live ? QA.len : 0, tB = hasB ? TB.len : 0, qB = hasB ? QB.len : 0;
         const int tlen = tA > tB ? tA : tB, qlen = qA > qB ? qA : qB;
         const int kmin = pr.kmin, kmax = pr.kmax;
-        // ---------------- stage both sequences as fp16 code pairs (A low half, B high half) ----------------
+        // ---------------- stage both sequences as fp16 code bytes (A low byte, B high byte) ----------------
         __syncwarp();
-        for (int t = lane; t < tlen; t += 32)
-            sT[t] = vm_code_half(t < tA ? vm_at(TA, t) : 4) | vm_code_half(t < tB ? vm_at(TB, t) : 4) << 16;
-        for (int q = lane; q < qlen; q += 32)
-            sQ[q] = vm_code_half(q < qA ? vm_at(QA, q) : 4) | vm_code_half(q < qB ? vm_at(QB, q) : 4) << 16;
+        for (int t = gl; t < tlen; t += LJ)
+            sT[t] = (uint16_t)(vm_code_byte(t < tA ? vm_at(TA, t) : 4) | vm_code_byte(t < tB ? vm_at(TB, t) : 4) << 8);
+        for (int q = gl; q < qlen; q += LJ)
+            sQ[q] = (uint16_t)(vm_code_byte(q < qA ? vm_at(QA, q) : 4) | vm_code_byte(q < qB ? vm_at(QB, q) : 4) << 8);
         __syncwarp();
         // ---------------- forward pass over the anti-diagonals ----------------
         int row[C];
@@ -107,7 +121,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
         auto init_row = [&](int c, int t) {
             // the row's first cell is in column 0 (real boundary) or on the band's lower edge (nothing to its left)
             row[c] = t;
-            tc[c] = vm_h2(t < tlen ? sT[t] : 0x7fff7fffu);
+            tc[c] = vm_codes_half2(t < tlen ? sT[t] : 0x7f7fu);
             const bool edge = t + kmin > 0;
             u[c] = edge ? zero2 : vm_boundary_step(t);
             y1[c] = edge ? neg2 : open1;
@@ -115,10 +129,14 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
         };
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            init_row(c, lane * C + c);
+            init_row(c, gl * C + c);
             v[c] = zero2; x1[c] = neg2; x2[c] = neg2;
         }
-        const int nsteps = tlen + qlen - 1;
+        int nsteps = tlen + qlen - 1;
+        if (G == 2) {                                             // both halves run to the longer pair's last step
+            const int other = __shfl_xor_sync(VM_FULL, nsteps, 16);
+            nsteps = nsteps > other ? nsteps : other;
+        }
         for (int r = 0; r < nsteps; ++r) {
             int tlo = r - (qlen - 1);
             const int e = r - kmax;                       // ceil((r - kmax) / 2)
@@ -129,18 +147,18 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             const int f = r - kmin;                       // floor((r - kmin) / 2), r - kmin >= 0 always
             if ((f >> 1) < thi) thi = f >> 1;
             // what the slot above holds from the previous step: slot C-1 of the previous lane for slot 0
-            __half2 inV = __shfl_sync(VM_FULL, v[C - 1], (lane + 31) & 31);
-            __half2 inX1 = __shfl_sync(VM_FULL, x1[C - 1], (lane + 31) & 31);
-            __half2 inX2 = __shfl_sync(VM_FULL, x2[C - 1], (lane + 31) & 31);
+            __half2 inV = __shfl_sync(VM_FULL, v[C - 1], (gl + LJ - 1) & (LJ - 1), LJ);
+            __half2 inX1 = __shfl_sync(VM_FULL, x1[C - 1], (gl + LJ - 1) & (LJ - 1), LJ);
+            __half2 inX2 = __shfl_sync(VM_FULL, x2[C - 1], (gl + LJ - 1) & (LJ - 1), LJ);
             unsigned d[C];
 #pragma unroll
             for (int c = C - 1; c >= 0; --c) {
                 if (row[c] < tlo) {
                     // the slot moves on to the row one period further down; its first cell is on the band's lower edge,
                     // or (bands reaching far below the main diagonal) in column 0, more than 20 rows down the boundary
-                    const int t = row[c] + 32 * C;
+                    const int t = row[c] + LJ * C;
                     row[c] = t;
-                    tc[c] = vm_h2(t < tlen ? sT[t] : 0x7fff7fffu);
+                    tc[c] = vm_codes_half2(t < tlen ? sT[t] : 0x7f7fu);
                     const bool edge = t + kmin > 0;
                     u[c] = edge ? zero2 : ext2;
                     y1[c] = edge ? neg2 : open1;
@@ -158,7 +176,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
                         cx1 = open1;
                         cx2 = open2;
                     }
-                    const __half2 qc = vm_h2(sQ[j]);
+                    const __half2 qc = vm_codes_half2(sQ[j]);
                     vm_cell2(tc[c], qc, cv, cx1, cx2, u[c], y1[c], y2[c], d[c]);
                     v[c] = cv; x1[c] = cx1; x2[c] = cx2;
                 }
@@ -175,42 +193,43 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             }
         }
         __syncwarp();
-        // ---------------- traceback (ksw_backtrack, left-aligned): lane 0 walks job A, lane 1 job B ----------------
-        const int w = lane & 1;
+        // ---------------- traceback (ksw_backtrack, left-aligned): lane 0 of the pair walks job A, lane 1 job B ----------------
+        const int w = gl & 1;
         const int tw = w ? tB : tA, qw = w ? qB : qA;
-        const bool walker = lane < 2 && tw > 0 && qw > 0;
+        const bool walker = gl < 2 && tw > 0 && qw > 0;
         uint32_t *out = cigar_out + (w ? JB.out_off : JA.out_off);
         int i = tw - 1, j = qw - 1, state = 0, n = 0, score = 0;
         unsigned cur_op = 0, cur_len = 0;
-        const int sh = w * 16;
+        const int sh = w * 8;
         for (;;) {
             const bool need = walker && i >= 0 && j >= 0;
-            const unsigned needmask = __ballot_sync(VM_FULL, need) & 3u;
-            if (!needmask) break;
+            const unsigned ball = __ballot_sync(VM_FULL, need);
+            if (!ball) break;
+            const unsigned needmask = (ball >> (grp * LJ)) & 3u;
 #pragma unroll
             for (int ws = 0; ws < 2; ++ws) {
-                const int ii = __shfl_sync(VM_FULL, i, ws), jj = __shfl_sync(VM_FULL, j, ws);
+                const int ii = __shfl_sync(VM_FULL, i, ws, LJ), jj = __shfl_sync(VM_FULL, j, ws, LJ);
                 if (needmask >> ws & 1u) {
-                    const int rr = ii + jj - lane;                    // this lane stages one anti-diagonal of the tile
-                    const int row_lo = ii > 31 ? ii - 31 : 0;
-                    const int lane_lo = (row_lo / C) & 31;
+                    const int rr = ii + jj - gl;                      // this lane stages one anti-diagonal of the tile
+                    const int row_lo = ii > TS - 1 ? ii - (TS - 1) : 0;
+                    const int lane_lo = (row_lo / C) & (LJ - 1);
                     if (rr >= 0) {
-                        const uint32_t *src = dir + (long long)rr * (CW * 32);
-                        uint32_t *tl = tile + ((size_t)ws * 32 + lane) * TW;
+                        const uint32_t *src = dir + (long long)rr * (CW * 32) + grp * LJ;
+                        uint32_t *tl = tile + ((size_t)ws * TS + gl) * TW;
 #pragma unroll
                         for (int x = 0; x < NL; ++x)
 #pragma unroll
-                            for (int m = 0; m < CW; ++m) tl[x * CW + m] = src[m * 32 + ((lane_lo + x) & 31)];
+                            for (int m = 0; m < CW; ++m) tl[x * CW + m] = src[m * 32 + ((lane_lo + x) & (LJ - 1))];
                     }
                 }
             }
             __syncwarp();
             if (need) {
-                const int r_hi = i + j, row_lo = i > 31 ? i - 31 : 0, blk_lo = row_lo / C;
-                const uint32_t *tl = tile + (size_t)w * 32 * TW;
+                const int r_hi = i + j, row_lo = i > TS - 1 ? i - (TS - 1) : 0, blk_lo = row_lo / C;
+                const uint32_t *tl = tile + (size_t)w * TS * TW;
                 while (i >= 0 && j >= 0) {
                     const int back = r_hi - (i + j);
-                    if (back >= 32 || i < row_lo) break;
+                    if (back >= TS || i < row_lo) break;
                     const int c = i % C;
                     const unsigned tmp = (tl[back * TW + (i / C - blk_lo) * CW + (c >> 1)] >> (((c & 1) * 2 + w) * 8)) & 0xffu;
                     if (state == 0) state = tmp & 7;
@@ -218,9 +237,9 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
                     if (state == 0) state = tmp & 7;
                     unsigned op;
                     if (state == 0) {
-                        const unsigned a = (sT[i] >> sh) & 0xffffu, b = (sQ[j] >> sh) & 0xffffu;
+                        const unsigned a = (sT[i] >> sh) & 0xffu, b = (sQ[j] >> sh) & 0xffu;
                         const bool same = a == b;
-                        if (a != 0x7fffu && b != 0x7fffu) score += same ? g.match : g.mismatch;
+                        if (a != 0x7fu && b != 0x7fu) score += same ? g.match : g.mismatch;
                         op = eqx ? (same ? 7u : 8u) : 0u;
                         --i; --j;
                     } else if (state == 1 || state == 3) { op = 2; --i; }
@@ -263,52 +282,75 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             certified = score > vm_outside_bound(tw, qw, kmin, kmax);
         }
         __syncwarp();
-        // ops were pushed end to start: claim room in the dense CIGAR arena and copy them over flipped, all lanes helping
+        // ops were pushed end to start: claim room in the dense CIGAR arena and copy them over flipped, the pair's lanes helping
 #pragma unroll
         for (int ws = 0; ws < 2; ++ws) {
-            if (ws == 1 && !hasB) break;
-            const int ok = __shfl_sync(VM_FULL, certified ? 1 : 0, ws);
-            const int nn = ok ? __shfl_sync(VM_FULL, walker ? n : 0, ws) : 0;
+            const int ok = __shfl_sync(VM_FULL, certified ? 1 : 0, ws, LJ);
+            const int nw = __shfl_sync(VM_FULL, walker ? n : 0, ws, LJ);
+            const int nn = ok ? nw : 0;
+            const int jid = ws ? pr.b : pr.a;                        // -1: no such job in this pair
             unsigned long long base = 0;
-            if (lane == 0 && nn > 0) base = atomicAdd(dense_count, (unsigned long long)nn);
-            base = __shfl_sync(VM_FULL, base, 0);
-            const uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
-            for (int x = lane; x < nn; x += 32) dense_out[base + x] = o[nn - 1 - x];
-            if (lane == 0) results[ws ? pr.b : pr.a] = ok ? make_uint2((unsigned)base, (unsigned)nn) : make_uint2(0xffffffffu, 0u);
+            if (gl == 0 && nn > 0) base = atomicAdd(dense_count, (unsigned long long)nn);
+            base = __shfl_sync(VM_FULL, base, 0, LJ);
+            if (jid >= 0) {
+                const uint32_t *o = cigar_out + (ws ? JB.out_off : JA.out_off);
+                for (int x = gl; x < nn; x += LJ) dense_out[base + x] = o[nn - 1 - x];
+                if (gl == 0) results[jid] = ok ? make_uint2((unsigned)base, (unsigned)nn) : make_uint2(0xffffffffu, 0u);
+            }
         }
         __syncwarp();
     }
 }
 
-template <int C>
+template <int C, int G>
 size_t vm_fillb_smem()
 {
-    constexpr int CW = (C + 1) / 2;
-    constexpr int NL = (31 / C + 2) < 32 ? (31 / C + 2) : 32;
-    return (size_t)4 * (2 * VM_FB_CAP + 2 * 32 * NL * CW) * sizeof(uint32_t);
+    constexpr int LJ = 32 / G, CAP = G == 1 ? VM_FB_CAP : VM_FB_CAP2, CW = (C + 1) / 2;
+    constexpr int NL = ((LJ - 1) / C + 2) < LJ ? ((LJ - 1) / C + 2) : LJ;
+    return (size_t)4 * G * (CAP + 2 * LJ * NL * CW) * sizeof(uint32_t);
 }
 
-template <int C>
+template <int C, int G>
 int vm_fillb_occupancy()
 {
-    vm_smem_optin(vm_fillb_kernel<C>);
+    vm_smem_optin(vm_fillb_kernel<C, G>);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vm_fillb_kernel<C>, 128, vm_fillb_smem<C>()) != cudaSuccess || nb < 1) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, vm_fillb_kernel<C, G>, 128, vm_fillb_smem<C, G>()) != cudaSuccess || nb < 1) nb = 1;
     return nb;
 }
 
-int vm_fillb_blocks_per_sm(int C)
+// Slot classes by band rows per anti-diagonal: half-warp pairs up to 64 rows, whole-warp pairs beyond
+struct VmFbClass { int G, C; };
+constexpr VmFbClass VM_FB_CLASS[VM_FB_NCLASS + 1] = {{0, 0}, {2, 2}, {2, 3}, {2, 4}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {1, 8}};
+inline int vm_fb_rows(int k) { return 32 / VM_FB_CLASS[k].G * VM_FB_CLASS[k].C; }
+// smallest class that holds `rows` band rows and sequences of up to `mx` bases (0: none)
+inline int vm_fb_class_of(int rows, int mx)
 {
-    switch (C) {
-    case 1: return vm_fillb_occupancy<1>();
-    case 2: return vm_fillb_occupancy<2>();
-    case 3: return vm_fillb_occupancy<3>();
-    case 4: return vm_fillb_occupancy<4>();
-    case 5: return vm_fillb_occupancy<5>();
-    case 6: return vm_fillb_occupancy<6>();
-    case 7: return vm_fillb_occupancy<7>();
-    default: return vm_fillb_occupancy<8>();
+    for (int k = 1; k <= VM_FB_NCLASS; ++k)
+        if (rows <= vm_fb_rows(k) && (VM_FB_CLASS[k].G == 1 || mx <= VM_FB_CAP2)) return k;
+    return 0;
+}
+
+#define VM_FB_DISPATCH(K, WHAT)                 \
+    switch (K) {                                \
+    case 1: WHAT(2, 2); break;                  \
+    case 2: WHAT(3, 2); break;                  \
+    case 3: WHAT(4, 2); break;                  \
+    case 4: WHAT(3, 1); break;                  \
+    case 5: WHAT(4, 1); break;                  \
+    case 6: WHAT(5, 1); break;                  \
+    case 7: WHAT(6, 1); break;                  \
+    case 8: WHAT(7, 1); break;                  \
+    default: WHAT(8, 1); break;                 \
     }
+
+int vm_fillb_blocks_per_sm(int k)
+{
+    int nb = 1;
+#define VM_FB_OCC(CC, GG) nb = vm_fillb_occupancy<CC, GG>()
+    VM_FB_DISPATCH(k, VM_FB_OCC)
+#undef VM_FB_OCC
+    return nb;
 }
 
 } // namespace
@@ -327,10 +369,10 @@ bool vm_fillb_own_band(int tlen, int qlen, int &kmin, int &kmax)
     if (w < 24) w = 24;
     kmin = (D < 0 ? D : 0) - w;
     kmax = (D > 0 ? D : 0) + w;
-    return ((kmax - kmin) / 2 + 1 + 31) / 32 <= VM_FB_MAXC;
+    return vm_fb_class_of((kmax - kmin) / 2 + 1, mx) > 0;
 }
 
-// Pairs of jobs with (nearly) the same band.  Jobs are bucketed by (slots C of their own band, D / 8, qlen / 4) with a
+// Pairs of jobs with (nearly) the same band.  Jobs are bucketed by (slot class of their own band, D / 8, qlen / 8) with a
 // parallel stable counting sort, neighbours in that order share a warp; a pair's band is the union of its jobs'
 // bands, widened to the capacity of its slot class.  full_mask[j] is cleared for every job planned here.
 void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads, VmFillBandPlan &plan, uint8_t *full_mask)
@@ -339,7 +381,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
     plan.launches.clear();
     plan.dir_words = 0;
     plan.dir_bytes = 0;
-    constexpr int ND = 256, NQ = VM_FB_CAP / 8 + 1, NKEY = VM_FB_MAXC * ND * NQ;     // D / 8 in [-128, 128) covers |D| < 1024
+    constexpr int ND = 256, NQ = VM_FB_CAP / 8 + 1, NKEY = VM_FB_NCLASS * ND * NQ;     // D / 8 in [-128, 128) covers |D| < 1024
     const int T = std::max(1, std::min(std::min(host_threads, 8), nj / 8192 + 1));
     std::vector<int32_t> keys((size_t)nj), bmin((size_t)nj), bmax((size_t)nj);      // key and own band of every job
     std::vector<std::vector<int32_t>> hist((size_t)T, std::vector<int32_t>((size_t)NKEY, 0));
@@ -354,7 +396,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
             if (J[j].t.len <= 0 || J[j].q.len <= 0 || !vm_fillb_own_band(J[j].t.len, J[j].q.len, kmin, kmax)) continue;
             bmin[j] = kmin;
             bmax[j] = kmax;
-            const int c = ((kmax - kmin) / 2 + 1 + 31) / 32;
+            const int c = vm_fb_class_of((kmax - kmin) / 2 + 1, std::max(J[j].t.len, J[j].q.len));
             int db = ((J[j].q.len - J[j].t.len) >> 3) + ND / 2;
             db = db < 0 ? 0 : db >= ND ? ND - 1 : db;
             keys[j] = ((c - 1) * ND + db) * NQ + (J[j].q.len >> 3);
@@ -363,7 +405,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
         }
     }, 1);
     int32_t n_live = 0;
-    int32_t class_lo[VM_FB_MAXC + 2];
+    int32_t class_lo[VM_FB_NCLASS + 2];
     for (int k = 0; k < NKEY; ++k) {
         if (k % (ND * NQ) == 0) class_lo[k / (ND * NQ) + 1] = n_live;     // first position of slot class c = k / (ND NQ) + 1
         for (int t = 0; t < T; ++t) {
@@ -372,7 +414,7 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
             n_live += cnt;
         }
     }
-    class_lo[VM_FB_MAXC + 1] = n_live;
+    class_lo[VM_FB_NCLASS + 1] = n_live;
     std::vector<int32_t> order((size_t)n_live);
     vmp::parallel_for(T, T, [&](int64_t t) {
         int lo, hi;
@@ -384,16 +426,16 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
     // neighbours of the same slot class share a warp (the widest class runs its jobs alone: a union could need a
     // ninth slot); every pair is built independently, then bucketed by the slot class of its union
     struct Tmp { VmFillBandPair pr; int c, steps; };
-    std::vector<int64_t> pair_lo(VM_FB_MAXC + 2, 0);
-    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+    std::vector<int64_t> pair_lo(VM_FB_NCLASS + 2, 0);
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) {
         const int64_t n = class_lo[c + 1] - class_lo[c];
-        pair_lo[c + 1] = pair_lo[c] + (c < VM_FB_MAXC ? (n + 1) / 2 : n);
+        pair_lo[c + 1] = pair_lo[c] + (c < VM_FB_NCLASS ? (n + 1) / 2 : n);
     }
-    std::vector<Tmp> tmp((size_t)pair_lo[VM_FB_MAXC + 1]);
-    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+    std::vector<Tmp> tmp((size_t)pair_lo[VM_FB_NCLASS + 1]);
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) {
         const int64_t np = pair_lo[c + 1] - pair_lo[c];
         const int lo = class_lo[c], hi = class_lo[c + 1];
-        const bool alone = c == VM_FB_MAXC;
+        const bool alone = c == VM_FB_NCLASS;
         vmp::parallel_for(np, host_threads, [&](int64_t p) {
             Tmp &t = tmp[(size_t)(pair_lo[c] + p)];
             const int xa = alone ? lo + (int)p : lo + 2 * (int)p, xb = alone ? hi : xa + 1;
@@ -403,49 +445,51 @@ void vm_fillb_plan(const VmAlnJobDev *J, int nj, int sm_count, int host_threads,
             pr.kmin = bmin[(size_t)pr.a];
             pr.kmax = bmax[(size_t)pr.a];
             t.steps = J[pr.a].t.len + J[pr.a].q.len;
+            int mx = std::max(J[pr.a].t.len, J[pr.a].q.len);
             if (pr.b >= 0) {
+                mx = std::max(mx, std::max(J[pr.b].t.len, J[pr.b].q.len));
                 pr.kmin = std::min(pr.kmin, bmin[(size_t)pr.b]);
                 pr.kmax = std::max(pr.kmax, bmax[(size_t)pr.b]);
                 t.steps = std::max(J[pr.a].t.len, J[pr.b].t.len) + std::max(J[pr.a].q.len, J[pr.b].q.len);
             }
             const int rows = (pr.kmax - pr.kmin) / 2 + 1;
-            t.c = (rows + 31) / 32;
-            if (t.c > VM_FB_MAXC) {          // cannot happen for neighbours of one bucket; if it does, the full-matrix kernel takes them
+            t.c = vm_fb_class_of(rows, mx);
+            if (t.c == 0) {          // cannot happen for neighbours of one bucket; if it does, the full-matrix kernel takes them
                 full_mask[pr.a] = 1;
                 if (pr.b >= 0) full_mask[pr.b] = 1;
-                t.c = 0;
                 return;
             }
             // widen the band to the capacity of its slot class: free rows, more margin for the certificate
-            const int spare = 32 * t.c - rows;
+            const int spare = vm_fb_rows(t.c) - rows;
             pr.kmin -= spare;
             pr.kmax += spare;
         }, 4096);
     }
-    std::vector<int64_t> cnt(VM_FB_MAXC + 2, 0), at(VM_FB_MAXC + 2, 0);
-    std::vector<int> max_steps(VM_FB_MAXC + 2, 0);
+    std::vector<int64_t> cnt(VM_FB_NCLASS + 2, 0), at(VM_FB_NCLASS + 2, 0);
+    std::vector<int> max_steps(VM_FB_NCLASS + 2, 0);
     for (const Tmp &t : tmp) {
         ++cnt[(size_t)t.c];
         max_steps[(size_t)t.c] = std::max(max_steps[(size_t)t.c], t.steps);
-        plan.dir_bytes += (double)t.steps * ((t.c + 1) / 2) * 128.0;
+        if (t.c > 0) plan.dir_bytes += (double)t.steps * ((VM_FB_CLASS[t.c].C + 1) / 2) * 128.0 / VM_FB_CLASS[t.c].G;
     }
     cnt[0] = 0;
-    for (int c = 1; c <= VM_FB_MAXC; ++c) at[c + 1] = at[c] + cnt[c];
-    plan.pairs.resize((size_t)at[VM_FB_MAXC + 1]);
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) at[c + 1] = at[c] + cnt[c];
+    plan.pairs.resize((size_t)at[VM_FB_NCLASS + 1]);
     {
         std::vector<int64_t> pos(at);
         for (const Tmp &t : tmp)
             if (t.c > 0) plan.pairs[(size_t)pos[(size_t)t.c]++] = t.pr;
     }
-    for (int c = 1; c <= VM_FB_MAXC; ++c) {
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) {
         if (cnt[c] == 0) continue;
         VmFillBandLaunch L;
-        L.C = c;
+        L.cls = c;
         L.pair_begin = (int)at[c];
         L.pair_end = (int)at[c + 1];
-        L.dir_words_per_warp = (long long)max_steps[(size_t)c] * ((c + 1) / 2) * 32;
+        L.dir_words_per_warp = (long long)max_steps[(size_t)c] * ((VM_FB_CLASS[c].C + 1) / 2) * 32;
         const int n_pairs = L.pair_end - L.pair_begin;
-        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
+        const int per_block = 4 * VM_FB_CLASS[c].G;
+        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + per_block - 1) / per_block, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
         plan.dir_words += (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp);      // every launch has its own slice
         plan.launches.push_back(L);
     }
@@ -467,20 +511,11 @@ int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs, const VmFillB
         *dir_cursor += (size_t)L.blocks * 4 * (size_t)L.dir_words_per_warp;
         uint32_t *dir_save = dir;
         dir = dir_l;
-#define VM_FILLB_GO(CC)                                                                                                  \
-    vm_fillb_kernel<CC><<<L.blocks, 128, vm_fillb_smem<CC>(), stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir, \
-                                                                        L.dir_words_per_warp, ctr, cigar_scratch, dense_out, \
-                                                                        dense_count, (uint2 *)results)
-        switch (L.C) {
-        case 1: VM_FILLB_GO(1); break;
-        case 2: VM_FILLB_GO(2); break;
-        case 3: VM_FILLB_GO(3); break;
-        case 4: VM_FILLB_GO(4); break;
-        case 5: VM_FILLB_GO(5); break;
-        case 6: VM_FILLB_GO(6); break;
-        case 7: VM_FILLB_GO(7); break;
-        default: VM_FILLB_GO(8); break;
-        }
+#define VM_FILLB_GO(CC, GG)                                                                                                        \
+    vm_fillb_kernel<CC, GG><<<L.blocks, 128, vm_fillb_smem<CC, GG>(), stream>>>(jobs, pairs, L.pair_begin, L.pair_end, src, eqx, dir, \
+                                                                                L.dir_words_per_warp, ctr, cigar_scratch,          \
+                                                                                dense_out, dense_count, (uint2 *)results)
+        VM_FB_DISPATCH(L.cls, VM_FILLB_GO)
 #undef VM_FILLB_GO
         dir = dir_save;
         ++n;
