@@ -105,7 +105,7 @@ int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs_dev, const VmFillPa
                    int *side_rr, size_t *dir_cursor, size_t *band_cursor);
 
 // ---- banded global fill with an optimality certificate (vm_fillb.cu) ----
-#define VM_FB_NCLASS 9        // slot classes (vm_fillb.cu: VM_FB_CLASS), by band rows per anti-diagonal
+#define VM_FB_NCLASS 12       // slot classes (vm_fillb.cu: VM_FB_CLASS), by band rows per anti-diagonal
 // two jobs sharing a warp and a band of diagonals [kmin, kmax] (b = -1: no partner)
 struct VmFillBandPair { int32_t a, b, kmin, kmax; };
 struct VmFillBandLaunch {

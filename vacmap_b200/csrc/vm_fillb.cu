@@ -29,6 +29,7 @@ namespace {
 
 #define VM_FB_CAP 768          // longest target / query the banded kernel stages in shared memory (whole-warp pairs)
 #define VM_FB_CAP2 512         // ... of the half-warp pairs
+#define VM_FB_CAP4 384         // ... of the quarter-warp pairs
 #define VM_FB_NEG (-1000)      // "-infinity" of the difference recurrences (exact in fp16)
 
 __device__ __forceinline__ int vm_gapcost(int n)
@@ -62,9 +63,12 @@ __device__ __forceinline__ __half2 vm_boundary_step(int index)
     return index == 0 ? VM_H2C(-(g.q1 + g.e1)) : index < 20 ? VM_H2C(-g.e1) : VM_H2C(-g.e2);
 }
 
-// G pairs of jobs per warp (G = 1: 32 lanes per pair, G = 2: 16), C register slots per lane: the band of a pair holds
-// at most (32 / G) * C rows per anti-diagonal.  The half-warp classes fit the common 200..350-base segments (their
-// bands need 40..60 rows) into 48 or 64 rows instead of 64 or 96, and share the per-step bookkeeping between four jobs.
+__host__ __device__ constexpr int vm_fb_cap(int G) { return G == 1 ? VM_FB_CAP : G == 2 ? VM_FB_CAP2 : VM_FB_CAP4; }
+
+// G pairs of jobs per warp (32 / G lanes per pair), C register slots per lane: the band of a pair holds at most
+// (32 / G) * C rows per anti-diagonal.  The quarter-warp classes fit the common 200..350-base segments (their bands
+// need 40..60 rows) into 48, 56 or 64 rows instead of 64 or 96, and share the per-step bookkeeping (bounds, three
+// shuffles, the store, the loop) between eight jobs.
 template <int C, int G>
 __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
                                                        int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
 {
     constexpr VmGapPar2 g = vm_fill_par();
     constexpr int LJ = 32 / G;                                    // lanes of one pair
-    constexpr int CAP = G == 1 ? VM_FB_CAP : VM_FB_CAP2;          // longest sequence staged
+    constexpr int CAP = vm_fb_cap(G);                             // longest sequence staged
     constexpr int CW = (C + 1) / 2;                               // direction words per lane and step
     constexpr int TS = LJ;                                        // traceback tile: TS steps x TS rows
     constexpr int NL = ((TS - 1) / C + 2) < LJ ? ((TS - 1) / C + 2) : LJ;     // lanes a TS-row tile can touch
@@ -133,8 +137,9 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
             v[c] = zero2; x1[c] = neg2; x2[c] = neg2;
         }
         int nsteps = tlen + qlen - 1;
-        if (G == 2) {                                             // both halves run to the longer pair's last step
-            const int other = __shfl_xor_sync(VM_FULL, nsteps, 16);
+#pragma unroll
+        for (int o = LJ; o < 32; o <<= 1) {                       // every group runs to the longest pair's last step
+            const int other = __shfl_xor_sync(VM_FULL, nsteps, o);
             nsteps = nsteps > other ? nsteps : other;
         }
         for (int r = 0; r < nsteps; ++r) {
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
 template <int C, int G>
 size_t vm_fillb_smem()
 {
-    constexpr int LJ = 32 / G, CAP = G == 1 ? VM_FB_CAP : VM_FB_CAP2, CW = (C + 1) / 2;
+    constexpr int LJ = 32 / G, CAP = vm_fb_cap(G), CW = (C + 1) / 2;
     constexpr int NL = ((LJ - 1) / C + 2) < LJ ? ((LJ - 1) / C + 2) : LJ;
     return (size_t)4 * G * (CAP + 2 * LJ * NL * CW) * sizeof(uint32_t);
 }
@@ -319,28 +324,33 @@ int vm_fillb_occupancy()
     return nb;
 }
 
-// Slot classes by band rows per anti-diagonal: half-warp pairs up to 64 rows, whole-warp pairs beyond
+// Slot classes by band rows per anti-diagonal: quarter-warp pairs up to 64 rows, half-warp pairs up to 96, whole-warp
+// pairs beyond (and for sequences longer than the narrower groups stage)
 struct VmFbClass { int G, C; };
-constexpr VmFbClass VM_FB_CLASS[VM_FB_NCLASS + 1] = {{0, 0}, {2, 2}, {2, 3}, {2, 4}, {1, 3}, {1, 4}, {1, 5}, {1, 6}, {1, 7}, {1, 8}};
+constexpr VmFbClass VM_FB_CLASS[VM_FB_NCLASS + 1] = {{0, 0}, {4, 4}, {4, 6}, {4, 7}, {4, 8}, {2, 5}, {2, 6}, {1, 3},
+                                                     {1, 4}, {1, 5}, {1, 6}, {1, 7}, {1, 8}};
 inline int vm_fb_rows(int k) { return 32 / VM_FB_CLASS[k].G * VM_FB_CLASS[k].C; }
 // smallest class that holds `rows` band rows and sequences of up to `mx` bases (0: none)
 inline int vm_fb_class_of(int rows, int mx)
 {
     for (int k = 1; k <= VM_FB_NCLASS; ++k)
-        if (rows <= vm_fb_rows(k) && (VM_FB_CLASS[k].G == 1 || mx <= VM_FB_CAP2)) return k;
+        if (rows <= vm_fb_rows(k) && mx <= vm_fb_cap(VM_FB_CLASS[k].G)) return k;
     return 0;
 }
 
 #define VM_FB_DISPATCH(K, WHAT)                 \
     switch (K) {                                \
-    case 1: WHAT(2, 2); break;                  \
-    case 2: WHAT(3, 2); break;                  \
-    case 3: WHAT(4, 2); break;                  \
-    case 4: WHAT(3, 1); break;                  \
-    case 5: WHAT(4, 1); break;                  \
-    case 6: WHAT(5, 1); break;                  \
-    case 7: WHAT(6, 1); break;                  \
-    case 8: WHAT(7, 1); break;                  \
+    case 1: WHAT(4, 4); break;                  \
+    case 2: WHAT(6, 4); break;                  \
+    case 3: WHAT(7, 4); break;                  \
+    case 4: WHAT(8, 4); break;                  \
+    case 5: WHAT(5, 2); break;                  \
+    case 6: WHAT(6, 2); break;                  \
+    case 7: WHAT(3, 1); break;                  \
+    case 8: WHAT(4, 1); break;                  \
+    case 9: WHAT(5, 1); break;                  \
+    case 10: WHAT(6, 1); break;                 \
+    case 11: WHAT(7, 1); break;                 \
     default: WHAT(8, 1); break;                 \
     }
 
