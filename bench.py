@@ -365,7 +365,7 @@ def main():
                     "bytes": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
                     "gcups_full_matrix_equivalent": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
                     "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
-                    "note": "integer DP wavefront: issue / ALU-pipe bound (ncu: issue 72 %, ALU 61 %, DRAM 11 %), not HBM bound "
+                    "note": "integer DP wavefront: issue / ALU-pipe bound (ncu, 48-row class: issue 71 %, ALU 67 %, DRAM 15 %), not HBM bound "
                             "(SURVEY 8d); the HBM fraction is reported because north_star asks for it"}
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
