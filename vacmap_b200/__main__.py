@@ -57,9 +57,15 @@ def options_from(args):
 
 
 def batches(paths, want_comments, batch_bases):
+    """Reads of all input files in order, cut into batches of ~batch_bases; a read name seen before is skipped
+    (the reference's `unique_set`, vacmap:428-476)."""
     cur, n = [], 0
+    seen = set()
     for path in paths:
         for rec in align.read_fastx(path, read_comment=want_comments):
+            if rec[0] in seen:
+                continue
+            seen.add(rec[0])
             cur.append(rec)
             n += len(rec[1])
             if n >= batch_bases:
