@@ -1,0 +1,77 @@
+"""asm mode, first brick: the batch loop around the linked global DP.
+
+TEST INFRASTRUCTURE, like the rest of oracle/.  Restates `assembly_get_readmap_DP_test`'s first round
+(mammap_asm.py:23218-23290): anchors arrive in batches sorted by read position; after every batch the anchors within
+`skipcost + 56` of the best score are carried over (scores rebased to end at 1000 + ..., back-pointers negated =
+"index into the previous batch") and the final chain is traced back through the saved batches.  The DP itself is
+`oracle.chain_linked_d_all` (pinned by tests/golden/asm_linked.json.gz); this loop is the build's restatement of
+inline reference code and is pinned through the same fixture's `path` entries, produced by running the reference's own
+njit function inside a transcription of that loop (tests/golden/make_golden.py::gen_asm_linked).
+The `_d_fast_all` fall-back after an opcount bail-out (:23246-23247) is not restated yet: NotImplementedError.
+"""
+import numpy as np
+
+import oracle
+
+
+def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None):
+    """batches: iterable of int64[m,4] anchor arrays, each sorted by read position.  Returns the chain as a list of
+    (readpos, refpos, strand, len) in DESCENDING read order (as the reference's `path`), [] if it has <= 1 anchors.
+    dp: the linked DP to call (default: the oracle's C restatement) -- the golden generator passes the reference's."""
+    if dp is None:
+        def dp(gs, gi, pS, pP, prl, a):
+            g, S, P, A, _ = oracle.chain_linked_d_all(gs, gi, pS, pP, prl, a, kmersize, skipcost, maxdiff, maxgap)
+            return g, S, P, A
+    g_max_scores, g_max_index = 0, 0
+    pre_S = np.zeros(0, np.float64)
+    pre_P = np.zeros(0, np.int32)
+    pre_info = np.zeros((0, 4), np.int64)
+    saved = []
+    pre_g = None
+    for one in batches:
+        one = np.asarray(one, dtype=np.int64).reshape(-1, 4)
+        if len(one) == 0:
+            continue
+        if len(pre_info) != 0:
+            linked = np.concatenate((pre_info, one))
+            prereadloc = max(0, int(pre_info[:, 0].max()))           # :23234-23237
+        else:
+            linked = one
+            prereadloc = int(one[0][0])
+        pre_g, S, P, S_arg = dp(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, linked)
+        if pre_g == -1:
+            raise NotImplementedError("opcount bail-out: linked _d_fast_all is not restated yet")
+        if P[pre_g] < 0:
+            continue
+        g_max_scores = S[S_arg[-1]]
+        lowest = g_max_scores - skipcost - 36 - 20
+        sliceiloc = len(S) - 1
+        if sliceiloc > 0:
+            while lowest < S[S_arg[sliceiloc]]:
+                sliceiloc -= 1
+                if sliceiloc == 0:
+                    break
+            sliceiloc = max(sliceiloc, 0)
+        else:
+            raise Exception("ERROR: ")
+        sel = S_arg[sliceiloc:]
+        pre_S = S[sel] - S[S_arg[sliceiloc]] + 1000
+        pre_P = (-P[sel]).astype(np.int32)
+        pre_info = linked[sel]
+        g_max_index = len(pre_S) - 1
+        g_max_scores = pre_S[-1]
+        saved.append((linked, P))
+    path = []
+    g = pre_g
+    for linked, P in reversed(saved):
+        take = g
+        path.append(tuple(int(v) for v in linked[take]))
+        while True:
+            if P[take] < 0:
+                break
+            take = P[take]
+            path.append(tuple(int(v) for v in linked[take]))
+        g = abs(int(P[take]))
+    if len(path) <= 1:
+        return []
+    return path

@@ -226,6 +226,118 @@ done:
     return ret;
 }
 
+/*
+ * asm mode (mammap_asm.py), SURVEY 8f-1: pairwise gap geometry of the linked DPs (`21795-21824`).  Same shape as
+ * pair_gaps above, but the older formulas: no +-1 on opposite strands, overlap handled through the non-overlapping
+ * length of anchor i.
+ */
+static inline void pair_gaps_asm(const int64_t *ai, const int64_t *aj,
+                                 int64_t *bonus, int64_t *readgap, int64_t *refgap)
+{
+    int64_t rg = ai[0] - aj[0] - aj[3];
+    if (rg < 0) {
+        int64_t nos = ai[0] - aj[0];
+        *bonus = ai[0] + ai[3] - aj[0] - aj[3];
+        *readgap = 0;
+        if (ai[2] == aj[2]) {
+            if (ai[2] == 1) *refgap = ai[1] - aj[1] - nos;
+            else *refgap = aj[1] + aj[3] - nos - ai[1] - ai[3];
+        } else {
+            if (aj[2] == -1) *refgap = ai[1] + aj[3] - nos - aj[1];
+            else *refgap = ai[1] + ai[3] - aj[1] - nos;
+        }
+    } else {
+        *bonus = ai[3];
+        *readgap = rg;
+        if (ai[2] == aj[2]) {
+            if (ai[2] == 1) *refgap = ai[1] - aj[1] - aj[3];
+            else *refgap = aj[1] - ai[1] - ai[3];
+        } else {
+            if (aj[2] == -1) *refgap = ai[1] - aj[1];
+            else *refgap = ai[1] + ai[3] - aj[1] - aj[3];
+        }
+    }
+}
+
+/*
+ * asm mode, global DP with carry-in: linked_get_optimal_chain_..._fine_list_d_all (mammap_asm.py `21687-21871`).
+ * a: int64[n][4] = the anchors carried over from the previous batch (pre_n of them, in ascending score order)
+ * followed by this batch's anchors sorted by read position.  pre_n > 0: S / P of the first pre_n anchors are the
+ * carried (rebased) scores and negated back-pointers, g_max_scores / g_max_index / prereadloc come from the caller
+ * and only S_arg[0] = 0 is in the test space until the read position first advances (`21713-21718`).  pre_n == 0:
+ * the plain start (`21720-21729`).  No coverage term; the scan stops at the first S_j <= best - l_i (`21777`).
+ * Returns g_max_index, or -1 on the opcount bail-out (`21754`).
+ */
+int64_t orc_chain_linked_d_all(const int64_t *a, int64_t n, int64_t pre_n, const double *pre_S, const int32_t *pre_P,
+                               double g_max_scores, int64_t g_max_index, int64_t prereadloc, int kmersize,
+                               double skipcost, int64_t maxdiff, int64_t maxgap, const orc_tables *tb, int64_t max_factor,
+                               double *S, int32_t *P, int32_t *S_arg, int64_t *opcount_out)
+{
+    double *gapcost_list = (double *)malloc(sizeof(double) * (size_t)(maxdiff + 1));
+    orc_gapcost_table(kmersize, (int)maxdiff, 0, gapcost_list);
+    int64_t testspace_en = 1, pre_size;
+    S_arg[0] = 0;
+    if (pre_n > 0) {
+        memcpy(S, pre_S, sizeof(double) * (size_t)pre_n);
+        memcpy(P, pre_P, sizeof(int32_t) * (size_t)pre_n);
+        pre_size = pre_n;
+    } else {
+        S[0] = (double)a[3];
+        P[0] = NOPRE;
+        g_max_scores = (double)a[3];
+        g_max_index = 0;
+        prereadloc = a[0];
+        pre_size = 1;
+    }
+    int64_t opcount = 0;
+    int64_t ret = 0;
+    for (int64_t i = pre_size; i < n; ++i) {
+        const int64_t *ai = a + i * 4;
+        double max_scores = (double)ai[3];
+        int64_t pre_index = NOPRE;
+        if (prereadloc < ai[0]) {
+            if (((double)opcount / (double)i) > (double)max_factor) { ret = -1; goto done; }
+            for (int64_t k = testspace_en; k < i; ++k) {
+                int64_t loc = insertpoint_score(S, S[k], k, S_arg);
+                memmove(S_arg + loc + 1, S_arg + loc, sizeof(int32_t) * (size_t)(k - loc));
+                S_arg[loc] = (int32_t)k;
+            }
+            testspace_en = i;
+            prereadloc = ai[0];
+        }
+        for (int64_t q = testspace_en - 1; q >= 0; --q) {
+            int64_t j = S_arg[q];
+            if (S[j] > (max_scores - (double)ai[3])) {
+                ++opcount;
+                int64_t bonus, readgap, refgap;
+                pair_gaps_asm(ai, a + j * 4, &bonus, &readgap, &refgap);
+                int64_t gapcost = llabs(readgap - refgap);
+                double t;
+                if (ai[2] == a[j * 4 + 2] && refgap >= 0 && readgap <= maxgap && gapcost <= maxdiff) {
+                    t = S[j] + (double)bonus - gapcost_list[gapcost];
+                } else {
+                    if (gapcost > tb->extra_size) gapcost = tb->extra_size;
+                    t = S[j] - skipcost + (double)bonus - (double)tb->extra[gapcost];
+                }
+                if (t > max_scores) { max_scores = t; pre_index = j; }
+            } else break;
+        }
+        S[i] = max_scores;
+        P[i] = (int32_t)pre_index;
+        if (max_scores > g_max_scores) { g_max_scores = max_scores; g_max_index = i; }
+    }
+    for (int64_t k = testspace_en; k < n; ++k) {
+        int64_t loc = insertpoint_score(S, S[k], k, S_arg);
+        memmove(S_arg + loc + 1, S_arg + loc, sizeof(int32_t) * (size_t)(k - loc));
+        S_arg[loc] = (int32_t)k;
+    }
+    ret = g_max_index;
+done:
+    if (opcount_out) *opcount_out = opcount;
+    free(gapcost_list);
+    return ret;
+}
+
 /* insertpoint_score_distance `17200-17226` */
 static int64_t insertpoint_score_distance(const int64_t *Si, int64_t target, int64_t k,
                                           const int32_t *arg, int64_t tdist, const int64_t *dist)

@@ -92,6 +92,71 @@ def gen_chain():
     print("chain.npz:", os.path.getsize(os.path.join(HERE, "chain.npz")), "bytes")
 
 
+def gen_asm_linked():
+    """asm mode: the reference's linked global DP with carry-in, run batch after batch inside the
+    first-round loop of `assembly_get_readmap_DP_test` (oracle/asm.py transcribes that inline loop; the DP called
+    here is the reference's own njit function) -> tests/golden/asm_linked.npz."""
+    import numba
+    import oracle.asm as oasm
+    m = refimport.load_mode("asm")
+    dall = getattr(m, "linked_" + P + "_d_all")
+
+    @numba.njit
+    def nb_argsort(a):
+        return np.argsort(a)
+
+    rng = np.random.default_rng(20261018)
+    out = {}
+    flows = []
+    for t in range(7):
+        if t == 0:
+            a = synth.anchors_tieheavy(rng, n=600)
+        elif t == 1:
+            a = synth.anchors_global(rng, n_true=40, n_noise=0)
+        else:
+            a = synth.anchors_global(rng, n_true=int(rng.integers(200, 900)), n_noise=int(rng.integers(0, 1200)))
+        a = a[nb_argsort(a[:, 0])].astype(np.int64)
+        nb = int(rng.integers(2, 6)) if t != 1 else 1
+        cuts = sorted(set(int(c) for c in rng.integers(1, len(a) - 1, size=nb - 1))) if nb > 1 else []
+        # a batch boundary never splits a run of equal read positions (batches are read-position slices, asm:22415-22441)
+        def slide(c):
+            while c < len(a) and a[c][0] == a[c - 1][0]:
+                c += 1
+            return c
+        cuts = sorted(set(c for c in map(slide, cuts) if c < len(a)))
+        flows.append(np.split(a, cuts))
+    # an empty batch in the middle, and a flow whose first batch is a single anchor (P[g] < 0: nothing carried)
+    flows.append([flows[2][0], np.zeros((0, 4), np.int64)] + flows[2][1:])
+    flows.append([flows[3][0][:1]] + [flows[3][0][1:]] + flows[3][1:])
+    for fi, batches in enumerate(flows):
+        rec = []
+
+        def dp(gs, gi, pS, pP, prl, lk, rec=rec):
+            g, S, Pp, A, _ = dall(gs, gi, pS, pP, prl, lk, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
+            rec.append((np.array([gs, gi, prl], dtype=np.float64), pS.copy(), pP.copy(), lk.copy(), int(g), S.copy(), Pp.copy(),
+                        A.copy()))
+            return g, S, Pp, A
+
+        path = oasm.first_round_path(batches, 15, 40., 50, 1000, dp=dp)
+        out["f%d_nb" % fi] = np.array(len(batches))
+        for bi, b in enumerate(batches):
+            out["f%d_b%d" % (fi, bi)] = b.astype(np.int32) if (len(b) == 0 or b.max() < 2**31) else b
+        out["f%d_calls" % fi] = np.array(len(rec))
+        for ci, (hd, pS, pP, lk, g, S, Pp, A) in enumerate(rec):
+            out["f%d_c%d_head" % (fi, ci)] = hd
+            out["f%d_c%d_preS" % (fi, ci)] = pS
+            out["f%d_c%d_preP" % (fi, ci)] = pP
+            out["f%d_c%d_g" % (fi, ci)] = np.array(g)
+            out["f%d_c%d_S" % (fi, ci)] = S
+            out["f%d_c%d_P" % (fi, ci)] = Pp
+            out["f%d_c%d_A" % (fi, ci)] = A
+        out["f%d_path" % fi] = np.array(path, dtype=np.int64).reshape(-1, 4)
+        print("flow", fi, "batches", [len(b) for b in batches], "calls", len(rec), "path", len(path))
+    out["n_flows"] = np.array(len(flows))
+    np.savez_compressed(os.path.join(HERE, "asm_linked.npz"), **out)
+    print("asm_linked.npz:", os.path.getsize(os.path.join(HERE, "asm_linked.npz")), "bytes")
+
+
 def gen_e2e():
     """End-to-end records from the reference's own get_readmap_DP_test / get_bam_dict_str run over the
     oracle's vacmap_index / edlib shim.  Inputs are regenerated from seeds (tests/synth.py) except the
@@ -150,6 +215,8 @@ if __name__ == "__main__":
         gen_chain()
     if "e2e" in what:
         gen_e2e()
+    if "asm" in what:
+        gen_asm_linked()
 
 
 def gen_sam_comments():

@@ -1,0 +1,44 @@
+"""asm mode, first brick: the oracle's linked global DP with carry-in and the batch loop around it
+against the reference's own njit function (tests/golden/asm_linked.npz, made by tests/golden/make_golden.py asm)."""
+import os
+
+import numpy as np
+
+import oracle
+import oracle.asm as oasm
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_linked.npz"))
+
+
+def test_linked_dp_calls_match_reference_bit_for_bit():
+    n_calls = n_carry = 0
+    for fi in range(int(G["n_flows"])):
+        batches = [G["f%d_b%d" % (fi, bi)].astype(np.int64).reshape(-1, 4) for bi in range(int(G["f%d_nb" % fi]))]
+        seen = []
+
+        def dp(gs, gi, pS, pP, prl, lk, seen=seen, fi=fi):
+            ci = len(seen)
+            head = G["f%d_c%d_head" % (fi, ci)]
+            assert (float(gs), float(gi), float(prl)) == tuple(head), (fi, ci)
+            assert np.array_equal(pS, G["f%d_c%d_preS" % (fi, ci)]) and np.array_equal(pP, G["f%d_c%d_preP" % (fi, ci)]), (fi, ci)
+            g, S, P, A, _ = oracle.chain_linked_d_all(gs, gi, pS, pP, prl, lk, 15, 40., 50, 1000)
+            assert g == int(G["f%d_c%d_g" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(S, G["f%d_c%d_S" % (fi, ci)]), (fi, ci)          # float64, exact
+            assert np.array_equal(P, G["f%d_c%d_P" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(A, G["f%d_c%d_A" % (fi, ci)]), (fi, ci)
+            seen.append(len(pS))
+            return g, S, P, A
+
+        path = oasm.first_round_path(batches, 15, 40., 50, 1000, dp=dp)
+        assert len(seen) == int(G["f%d_calls" % fi])
+        assert np.array_equal(np.array(path, dtype=np.int64).reshape(-1, 4), G["f%d_path" % fi]), fi
+        n_calls += len(seen)
+        n_carry += sum(1 for s in seen if s > 0)
+    assert n_calls >= 20 and n_carry >= 10
+
+
+def test_default_dp_is_the_oracle_and_short_chains_give_nothing():
+    batches = [G["f2_b%d" % bi].astype(np.int64) for bi in range(int(G["f2_nb"]))]
+    assert np.array_equal(np.array(oasm.first_round_path(batches, 15, 40., 50, 1000)), G["f2_path"])
+    assert oasm.first_round_path([np.array([[5, 100, 1, 15]])], 15, 40., 50, 1000) == []
+    assert oasm.first_round_path([], 15, 40., 50, 1000) == []
