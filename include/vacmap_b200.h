@@ -72,7 +72,7 @@ typedef struct vm_chain_params {
     int32_t max_factor;   /* 1000 (:19367) opcount bail-out of the exact global DP */
     int32_t fast_t;       /* 5: bucket size above which the fast DP probes one member */
     int32_t large_readgap;/* 30 (:28587) multi-chain local DP */
-    int32_t variant;      /* 0 global _d_all; 1 local _fine_list; 2 local _fine_list_mismatch */
+    int32_t variant;      /* 0 global _d_all; 1 local _fine_list; 2 local _fine_list_mismatch; 3 asm linked _d_all (set by vm_chain_linked_batch) */
 } vm_chain_params;
 
 /*
@@ -109,6 +109,23 @@ int vm_chain_global_download(vm_ctx *ctx, int64_t *sorted, double *S, int32_t *P
                              int64_t *g_max_index, int32_t *used_fast);
 /* per-kernel device time of the last run (ms): [pack, sort, dp_exact, dp_fast] */
 int vm_chain_global_times(vm_ctx *ctx, float *ms4);
+
+/*
+ * asm mode: the linked global DP with carry-in, one job per (contig, anchor batch).
+ * Replaces linked_get_optimal_chain_..._fine_list_d_all(g_max_scores, g_max_index, pre_S, pre_P, prereadloc,
+ * one_mapinfo, kmersize, skipcost, maxdiff, maxgap) (mammap_asm.py:21687-21871) as called from
+ * assembly_get_readmap_DP_test (:23244).
+ *   anchors  int64[total][4]: per job the pre_n[j] anchors carried over from the previous batch followed by this
+ *            batch's anchors sorted by read position (`linked_one_mapinfo`, :23232) -- already in DP order
+ *   off      int64[n_jobs+1]; pre_n int32[n_jobs] (0: plain start, :21720-21729)
+ *   head     float64[n_jobs][3] = g_max_scores, g_max_index, prereadloc of the call (ignored when pre_n == 0)
+ *   S, P     IN: the first pre_n[j] entries of every job hold pre_S / pre_P; OUT: all of S, P (int32, -9999999 = start)
+ *   S_arg    OUT int32[total]; g_max_index OUT int64[n_jobs], -1 = opcount bail-out (:21754; the caller then runs
+ *            the _d_fast_all twin, not part of this entry point yet)
+ */
+int vm_chain_linked_batch(vm_ctx *ctx, const vm_chain_params *prm, int64_t n_jobs, const int64_t *anchors, const int64_t *off,
+                          const int32_t *pre_n, const double *head, double *S, int32_t *P, int32_t *S_arg,
+                          int64_t *g_max_index);
 
 /*
  * Stage-level local chaining (parity tests).  Replaces get_optimal_chain_..._fine_list (variant 1,

@@ -8,7 +8,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 4; }
+int vm_abi_version(void) { return 5; }
 
 int vm_ctx_create(int device, vm_ctx **out)
 {
@@ -131,7 +131,7 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
     if (c->n_extra == 0) { c->err = "vm_set_tables must be called first"; return VM_ERR_STATE; }
     if (p.maxdiff + 1 > VM_GCL_MAX) { c->err = "maxdiff too large"; return VM_ERR_ARG; }
     std::vector<double> gcl;
-    vm_host_gapcost(p.kmersize, p.maxdiff, p.variant != 0, gcl);
+    vm_host_gapcost(p.kmersize, p.maxdiff, p.variant == 1 || p.variant == 2, gcl);
     VM_CUDA_OK(c, s.gcl.ensure(gcl.size() * sizeof(double)));
     VM_CUDA_OK(c, cudaMemcpyAsync(s.gcl.p, gcl.data(), gcl.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     A.rgcost = nullptr;
@@ -167,6 +167,8 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
     A.maxdiff = p.maxdiff;
     A.maxgap = p.maxgap;
     A.max_factor = p.max_factor;
+    A.pre_n = s.pre_n_dev.as<int32_t>();
+    A.head = s.head_dev.as<double>();
     return VM_OK;
 }
 
@@ -185,7 +187,8 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     VmChainArgs A;
     int rc = vm_chain_args(c, s, prm, A);
     if (rc != VM_OK) return rc;
-    const bool by_end = prm.variant != 0;
+    const bool by_end = prm.variant == 1 || prm.variant == 2;
+    const bool linked = prm.variant == 3;      // asm mode: no fast fall-back here, a bail-out is reported as g_max_index -1
     std::vector<std::vector<int>> cls(kNumCaps + 1);
     std::vector<int> fast_ids;
     bool may_bail = false;
@@ -193,12 +196,12 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         const int64_t n = cnt[r];
         if (n <= 0) continue;
         // hit2work_1 :23570 -- n / read_len > 5 goes straight to the fast DP (global only)
-        if (force_fast || (!by_end && (double)n / (double)read_len[r] > 5.0)) { fast_ids.push_back(r); continue; }
+        if (!linked && (force_fast || (!by_end && (double)n / (double)read_len[r] > 5.0))) { fast_ids.push_back(r); continue; }
         int k = 0;
         while (k < kNumCaps && n > kCaps[k]) ++k;
         cls[k].push_back(r);
         // global: opcount/i > 1000 needs i > 2000; local: opcount > 100000 needs n(n-1)/2 > 100000
-        if (by_end ? n > 440 : n > 2000) may_bail = true;
+        if (!linked && (by_end ? n > 440 : n > 2000)) may_bail = true;
     }
     std::vector<int> ids_host;
     std::vector<int> cls_start(kNumCaps + 2, 0);
@@ -404,6 +407,39 @@ int vm_chain_global_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_reads
     rc = vm_chain_global_run(c, kernel_ms);
     if (rc != VM_OK) return rc;
     return vm_chain_global_download(c, sorted, S, P, S_arg, g_max_index, used_fast);
+}
+
+int vm_chain_linked_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_jobs, const int64_t *anchors, const int64_t *off,
+                          const int32_t *pre_n, const double *head, double *S, int32_t *P, int32_t *S_arg, int64_t *g_max_index)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!prm || !off || n_jobs < 0 || (n_jobs > 0 && (!pre_n || !head || !S || !P))) { c->err = "bad argument"; return VM_ERR_ARG; }
+    vm_chain_params p = *prm;
+    p.variant = 3;
+    for (int64_t r = 0; r < n_jobs; ++r)
+        if (pre_n[r] < 0 || pre_n[r] > off[r + 1] - off[r]) { c->err = "pre_n out of range"; return VM_ERR_ARG; }
+    // jobs never take the n / read_len > 5 short cut of hit2work_1 (that rule belongs to the per-read path)
+    std::vector<int32_t> rl((size_t)std::max<int64_t>(n_jobs, 1), INT32_MAX / 2);
+    int rc = vm_chain_global_upload(c, &p, n_jobs, anchors, off, rl.data());
+    if (rc != VM_OK) return rc;
+    VmChainState &s = c->chain;
+    const size_t T = (size_t)s.total;
+    VM_CUDA_OK(c, s.pre_n_dev.ensure((size_t)(n_jobs + 1) * 4));
+    VM_CUDA_OK(c, s.head_dev.ensure((size_t)(n_jobs + 1) * 24));
+    if (n_jobs > 0) {
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.pre_n_dev.p, pre_n, (size_t)n_jobs * 4, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.head_dev.p, head, (size_t)n_jobs * 24, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (T > 0) {      // the carried scores / negated back-pointers sit in front of every job's S / P
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.S.p, S, T * 8, cudaMemcpyHostToDevice, c->stream));
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.P.p, P, T * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<int> ids((size_t)n_jobs);
+    for (int64_t r = 0; r < n_jobs; ++r) ids[(size_t)r] = (int)r;
+    c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
+    rc = vm_chain_core(c, p, s.anch.as<VmAnchor>(), s.off, s.cnt, s.read_len, s.cnt_len, ids, nullptr, nullptr, s.ms, true, false);
+    if (rc != VM_OK) return rc;
+    return vm_chain_global_download(c, nullptr, S, P, S_arg, g_max_index, nullptr);
 }
 
 } // extern "C"

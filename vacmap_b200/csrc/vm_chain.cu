@@ -125,19 +125,21 @@ template <int VARIANT>
 __device__ __forceinline__ double vm_pair_score(const VmScoreCtx &c, const VmAnchor &ai, const VmAnchor &aj,
                                                 double Sj, bool &skip)
 {
+    constexpr bool GLOBAL = VARIANT == 0 || VARIANT == 3;      // 3: asm mode's linked global DP (mammap_asm.py:21687-21871)
     int bonus, readgap;
     long long refgap;
-    vm_pair_gaps(ai, aj, bonus, readgap, refgap);
+    if (VARIANT == 3) vm_pair_gaps_asm(ai, aj, bonus, readgap, refgap);
+    else vm_pair_gaps(ai, aj, bonus, readgap, refgap);
     skip = false;
-    if (VARIANT != 0 && (ai.x - aj.x - aj.l) < 0 && bonus <= 0) { skip = true; return -CUDART_INF; }
+    if (!GLOBAL && (ai.x - aj.x - aj.l) < 0 && bonus <= 0) { skip = true; return -CUDART_INF; }
     long long gapcost = vm_llabs((long long)readgap - refgap);
     if (ai.s == aj.s && refgap >= 0 && readgap <= c.maxgap && gapcost <= (long long)c.maxdiff) {
         double t = Sj + (double)bonus;
         t = t - c.gcl[gapcost];
-        if (VARIANT != 0) t = t - (double)c.rgl[readgap];
+        if (!GLOBAL) t = t - (double)c.rgl[readgap];
         return t;
     }
-    if (VARIANT == 0) {
+    if (GLOBAL) {
         if (gapcost > c.extra_size) gapcost = c.extra_size;
         double t = Sj - c.skipcost;
         t = t + (double)bonus;
@@ -260,8 +262,10 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
         S = A.S + base;
         arg = A.S_arg + base;
     }
+    constexpr bool GLOBAL = VARIANT == 0 || VARIANT == 3;
+    constexpr int INS = VARIANT == 3 ? 0 : VARIANT;             // S_arg insertion rule (insertpoint_score for both global DPs)
     for (int t = lane; t <= A.maxdiff && t < VM_GCL_MAX; t += 32) gcl[t] = A.gapcost_list[t];
-    if (VARIANT != 0)
+    if (!GLOBAL)
         for (int t = lane; t < A.n_rg && t < VM_RGL_MAX; t += 32) rgl[t] = A.rgcost[t];
     __syncwarp();
     if (n <= 0) {
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
 
     int32_t *P = A.P + base;
     const VmAnchor a0 = a[0];
-    int prekey = VARIANT == 0 ? a0.x : a0.x + a0.l;
+    int prekey = GLOBAL ? a0.x : a0.x + a0.l;
     if (VARIANT == 0) {
         // coverage of the first read position (:24865-24876): run length, capped at 20
         const bool eq = lane < n && a[lane].x == a0.x;
@@ -287,24 +291,36 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
         c.maxdiff = A.maxdiff - run > 10 ? A.maxdiff - run : 10;
     }
     int testspace_en = 1;
-    if (lane == 0) { arg[0] = 0; S[0] = (double)a0.l; P[0] = VM_NOPRE; }
-    __syncwarp();
     double g_max_scores = (double)a0.l;
     int g_max_index = 0;
+    int i_first = 1;
+    const int pre_n = VARIANT == 3 ? A.pre_n[rid] : 0;
+    if (pre_n > 0) {
+        // carried anchors in front of the batch (:21713-21718): their scores / negated back-pointers are already in
+        // S / P, only the first of them is in the test space until the read position first advances
+        if (SMEM)
+            for (int t = lane; t < pre_n; t += 32) S[t] = A.S[base + t];
+        if (lane == 0) arg[0] = 0;
+        g_max_scores = A.head[3 * rid];
+        g_max_index = (int)A.head[3 * rid + 1];
+        prekey = (int)A.head[3 * rid + 2];
+        i_first = pre_n;
+    } else if (lane == 0) { arg[0] = 0; S[0] = (double)a0.l; P[0] = VM_NOPRE; }
+    __syncwarp();
     long long opcount = 0;
     long long result = 0;
     bool bailed = false;
 
-    for (int i = 1; i < n; ++i) {
+    for (int i = i_first; i < n; ++i) {
         const VmAnchor ai = a[i];
-        const int key = VARIANT == 0 ? ai.x : ai.x + ai.l;
+        const int key = GLOBAL ? ai.x : ai.x + ai.l;
         if (prekey < key) {
-            if (VARIANT == 0) {
+            if (GLOBAL) {
                 if (((double)opcount / (double)i) > (double)A.max_factor) { bailed = true; result = -1; break; }
             } else {
                 if (opcount > 100000 && ((double)opcount / (double)prekey) > 1000.0) { bailed = true; result = -2; break; }
             }
-            for (int k = testspace_en; k < i; ++k) vm_insert_one<VARIANT>(S, arg, k, lane);
+            for (int k = testspace_en; k < i; ++k) vm_insert_one<INS>(S, arg, k, lane);
             testspace_en = i;
             if (VARIANT == 0) {
                 const bool eq = (i + lane) < n && a[i + lane].x == ai.x;
@@ -341,7 +357,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
             double exc = __shfl_up_sync(VM_FULL, inc, 1);
             if (lane == 0 || !(exc > max_scores)) exc = max_scores;
             bool brk;
-            if (VARIANT == 0) brk = valid && !(Sj > (exc - li));   // :24949 / else break :25003
+            if (GLOBAL) brk = valid && !(Sj > (exc - li));         // :24949 / else break :25003
             else brk = valid && (Sj < (exc - li));                 // :27413
             const unsigned bm = __ballot_sync(VM_FULL, brk);
             const unsigned vm = __ballot_sync(VM_FULL, valid);
@@ -349,7 +365,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
             int first = bm ? (__ffs(bm) - 1) : nvalid;
             // lanes at/after the break are never evaluated
             if (lane >= first) t = -CUDART_INF;
-            if (VARIANT == 0) opcount += first;                      // counted inside the if (:24951)
+            if (GLOBAL) opcount += first;                            // counted inside the if (:24951)
             else opcount += bm ? first + 1 : nvalid;                 // counted before the test (:27410)
             // arg-max, lowest lane (= first visited) wins ties
             double bt = t;
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
         if (max_scores > g_max_scores) { g_max_scores = max_scores; g_max_index = i; }
     }
     if (!bailed) {
-        for (int k = testspace_en; k < n; ++k) vm_insert_one<VARIANT>(S, arg, k, lane);
+        for (int k = testspace_en; k < n; ++k) vm_insert_one<INS>(S, arg, k, lane);
         result = g_max_index;
         if (SMEM) {
             double *So = A.S + base;
@@ -402,6 +418,7 @@ int vm_launch_chain_exact(int variant, const VmChainArgs &args, const int *read_
     switch (variant) {
     case 0: return vm_launch_exact_v<0>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     case 1: return vm_launch_exact_v<1>(args, read_ids_dev, n_ids, cap, use_smem, stream);
+    case 3: return vm_launch_exact_v<3>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     default: return vm_launch_exact_v<2>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     }
 }

@@ -41,6 +41,10 @@ struct VmChainArgs {
     int maxdiff;
     int maxgap;
     int max_factor;
+    // variant 3 (asm mode, linked global DP): per read the number of carried anchors in front of the batch (their S / P
+    // already in S / P), and head[3 r .. 3 r + 3) = carried g_max_scores, g_max_index, prereadloc (mammap_asm.py:21713)
+    const int32_t *pre_n;
+    const double *head;
 };
 
 int vm_launch_chain_exact(int variant, const VmChainArgs &args, const int *read_ids_dev, int n_ids,

@@ -95,4 +95,35 @@ __device__ __forceinline__ void vm_pair_gaps(const VmAnchor &ai, const VmAnchor 
     }
 }
 
+// asm mode (mammap_asm.py:21795-21824): the linked DPs' older gap geometry -- no +-1 between opposite strands,
+// overlaps handled through the non-overlapping length of anchor i
+__device__ __forceinline__ void vm_pair_gaps_asm(const VmAnchor &ai, const VmAnchor &aj,
+                                                 int &bonus, int &readgap, long long &refgap)
+{
+    const int rg = ai.x - aj.x - aj.l;
+    const long long yi = (long long)ai.y, yj = (long long)aj.y;
+    if (rg < 0) {
+        const long long nos = ai.x - aj.x;
+        bonus = ai.x + ai.l - aj.x - aj.l;
+        readgap = 0;
+        if (ai.s == aj.s) {
+            if (ai.s == 1) refgap = yi - yj - nos;
+            else refgap = yj + aj.l - nos - yi - ai.l;
+        } else {
+            if (aj.s == -1) refgap = yi + aj.l - nos - yj;
+            else refgap = yi + ai.l - yj - nos;
+        }
+    } else {
+        bonus = ai.l;
+        readgap = rg;
+        if (ai.s == aj.s) {
+            if (ai.s == 1) refgap = yi - yj - aj.l;
+            else refgap = yj - yi - ai.l;
+        } else {
+            if (aj.s == -1) refgap = yi - yj;
+            else refgap = yi + ai.l - yj - aj.l;
+        }
+    }
+}
+
 __device__ __forceinline__ long long vm_llabs(long long v) { return v < 0 ? -v : v; }

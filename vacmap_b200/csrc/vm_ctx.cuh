@@ -67,7 +67,7 @@ struct VmChainState {
     std::vector<int32_t> read_len, cnt_len;
     std::vector<int64_t> gmax_host;
     VmDevBuf rows, off_dev, cnt_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
-        fast_scratch, fast_off, sort_scratch;
+        fast_scratch, fast_off, sort_scratch, pre_n_dev, head_dev;      // pre_n / head: carried prefix of the linked DP (variant 3)
     std::vector<int32_t> used_fast;
     float ms[4] = {0, 0, 0, 0};
 };
