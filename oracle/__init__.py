@@ -61,6 +61,8 @@ def _declare(L):
     L.orc_chain_global_d_all.argtypes = [vp, i64, i32, dbl, i64, i64, vp, i64, vp, vp, vp, vp]
     L.orc_chain_linked_d_all.restype = i64
     L.orc_chain_linked_d_all.argtypes = [vp, i64, i64, vp, vp, dbl, i64, i64, i32, dbl, i64, i64, vp, i64, vp, vp, vp, vp]
+    L.orc_chain_linked_fast.restype = i64
+    L.orc_chain_linked_fast.argtypes = [vp, i64, i64, vp, vp, dbl, i64, i64, i32, dbl, i64, i64, i64, vp, vp, vp, vp]
     L.orc_chain_fast.restype = i64
     L.orc_chain_fast.argtypes = [vp, i64, i32, i32, dbl, i64, i64, i64, vp, vp, vp, vp, vp]
     L.orc_chain_local.restype = i64
@@ -149,6 +151,22 @@ def chain_linked_d_all(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, a, k
                                      float(g_max_scores), int(g_max_index), int(prereadloc), kmersize, float(skipcost), maxdiff,
                                      maxgap, ctypes.addressof(t["struct"]), max_factor, _p(S), _p(P), _p(A), _p(op))
     return g, S, P, A, int(op[0])
+
+
+def chain_linked_fast(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, a, kmersize, skipcost, maxdiff, maxgap, fast_t=5):
+    """asm mode: `linked_..._fine_list_d_fast_all` (mammap_asm.py:21872).  Returns (g_max_index, S, P, S_arg_i)."""
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    pre_S = np.ascontiguousarray(pre_S, dtype=np.float64)
+    pre_P = np.ascontiguousarray(pre_P, dtype=np.int32)
+    n = len(a)
+    S = np.zeros(n, np.float64)
+    P = np.zeros(n, np.int32)
+    A = np.zeros(n, np.int32)
+    t = tables()
+    g = lib().orc_chain_linked_fast(_p(a), n, len(pre_S), _p(pre_S) if len(pre_S) else None, _p(pre_P) if len(pre_P) else None,
+                                    float(g_max_scores), int(g_max_index), int(prereadloc), kmersize, float(skipcost), maxdiff,
+                                    maxgap, fast_t, ctypes.addressof(t["struct"]), _p(S), _p(P), _p(A))
+    return g, S, P, A
 
 
 def chain_fast(a, kmersize, variant, skipcost, maxdiff, maxgap, fast_t=5, large_readgap=30):

@@ -7,21 +7,25 @@ TEST INFRASTRUCTURE, like the rest of oracle/.  Restates `assembly_get_readmap_D
 `oracle.chain_linked_d_all` (pinned by tests/golden/asm_linked.json.gz); this loop is the build's restatement of
 inline reference code and is pinned through the same fixture's `path` entries, produced by running the reference's own
 njit function inside a transcription of that loop (tests/golden/make_golden.py::gen_asm_linked).
-The `_d_fast_all` fall-back after an opcount bail-out (:23246-23247) is not restated yet: NotImplementedError.
+After an opcount bail-out the heuristic twin `_d_fast_all` takes over (:23246-23247; `oracle.chain_linked_fast`).
 """
 import numpy as np
 
 import oracle
 
 
-def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None):
+def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None, dp_fast=None):
     """batches: iterable of int64[m,4] anchor arrays, each sorted by read position.  Returns the chain as a list of
     (readpos, refpos, strand, len) in DESCENDING read order (as the reference's `path`), [] if it has <= 1 anchors.
-    dp: the linked DP to call (default: the oracle's C restatement) -- the golden generator passes the reference's."""
+    dp / dp_fast: the linked DPs to call (default: the oracle's C restatements) -- the golden generator passes the
+    reference's."""
     if dp is None:
         def dp(gs, gi, pS, pP, prl, a):
             g, S, P, A, _ = oracle.chain_linked_d_all(gs, gi, pS, pP, prl, a, kmersize, skipcost, maxdiff, maxgap)
             return g, S, P, A
+    if dp_fast is None:
+        def dp_fast(gs, gi, pS, pP, prl, a):
+            return oracle.chain_linked_fast(gs, gi, pS, pP, prl, a, kmersize, skipcost, maxdiff, maxgap)
     g_max_scores, g_max_index = 0, 0
     pre_S = np.zeros(0, np.float64)
     pre_P = np.zeros(0, np.int32)
@@ -39,8 +43,8 @@ def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None)
             linked = one
             prereadloc = int(one[0][0])
         pre_g, S, P, S_arg = dp(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, linked)
-        if pre_g == -1:
-            raise NotImplementedError("opcount bail-out: linked _d_fast_all is not restated yet")
+        if pre_g == -1:                                              # opcount bail-out -> the heuristic twin (:23246-23247)
+            pre_g, S, P, S_arg = dp_fast(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, linked)
         if P[pre_g] < 0:
             continue
         g_max_scores = S[S_arg[-1]]

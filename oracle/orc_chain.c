@@ -534,6 +534,115 @@ int64_t orc_chain_fast(const int64_t *a, int64_t n, int kmersize, int variant,
     return g_max_index;
 }
 
+/*
+ * asm mode, heuristic twin of the linked DP: linked_..._fine_list_d_fast_all (mammap_asm.py `21872-22158`), taken
+ * when the exact one bails out (`23246-23247`).  As orc_chain_fast(variant 0) above, with the asm gap geometry, no
+ * coverage term, and the carried prefix: S_i[:pre_n] = int64(pre_S), only S_arg_i[0] = 0 / S_i_count[S_i[0]] = 1
+ * in the test space and max_score_i = S_i[0] (`21906-21914`; the plain start keeps the reference's max_score_i = 0).
+ */
+int64_t orc_chain_linked_fast(const int64_t *a, int64_t n, int64_t pre_n, const double *pre_S, const int32_t *pre_P,
+                              double g_max_scores, int64_t g_max_index, int64_t prereadloc, int kmersize,
+                              double skipcost, int64_t maxdiff, int64_t maxgap, int64_t fast_t, const orc_tables *tb,
+                              double *S, int32_t *P, int32_t *S_arg_i)
+{
+    double *gapcost_list = (double *)malloc(sizeof(double) * (size_t)(maxdiff + 1));
+    orc_gapcost_table(kmersize, (int)maxdiff, 0, gapcost_list);
+    int64_t lastpos = a[(n - 1) * 4];
+    int64_t *target = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t *Si = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t readlength = lastpos + 1000;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t *ai = a + i * 4;
+        if (ai[2] == 1) target[i] = ai[1] - ai[0] + readlength;
+        else target[i] = -(ai[1] + ai[0] + readlength);
+    }
+    /* S_i_count is lastpos + 50 long in the reference and indexed by integer score: head-room as in orc_chain_fast */
+    int64_t cnt_size = lastpos + 50;
+    {
+        int64_t tot = 64;
+        for (int64_t i = 0; i < n; ++i) tot += a[i * 4 + 3];
+        int64_t carried = 0;
+        for (int64_t i = 0; i < pre_n; ++i)
+            if ((int64_t)pre_S[i] > carried) carried = (int64_t)pre_S[i];
+        tot += carried;
+        if (tot > cnt_size) cnt_size = tot;
+    }
+    int64_t *Sicount = (int64_t *)calloc((size_t)cnt_size, sizeof(int64_t));
+    int64_t testspace_en_i = 1, pre_size, max_score_i;
+    S_arg_i[0] = 0;
+    if (pre_n > 0) {
+        for (int64_t i = 0; i < pre_n; ++i) { S[i] = pre_S[i]; Si[i] = (int64_t)pre_S[i]; P[i] = pre_P[i]; }
+        pre_size = pre_n;
+        Sicount[Si[0]] = 1;
+        max_score_i = Si[0];
+    } else {
+        S[0] = (double)a[3]; Si[0] = a[3]; P[0] = NOPRE;
+        pre_size = 1;
+        g_max_scores = (double)a[3];
+        g_max_index = 0;
+        prereadloc = a[0];
+        Sicount[a[3]] = 1;
+        max_score_i = 0;
+    }
+    for (int64_t i = pre_size; i < n; ++i) {
+        const int64_t *ai = a + i * 4;
+        P[i] = NOPRE;
+        double max_scores = (double)ai[3];
+        int64_t pre_index = NOPRE;
+        if (prereadloc < ai[0]) {
+            for (int64_t k = testspace_en_i; k < i; ++k) {
+                Sicount[Si[k]] += 1;
+                if (Si[k] > max_score_i) max_score_i = Si[k];
+                int64_t loc = insertpoint_score_distance(Si, Si[k], k, S_arg_i, target[k], target);
+                memmove(S_arg_i + loc + 1, S_arg_i + loc, sizeof(int32_t) * (size_t)(k - loc));
+                S_arg_i[loc] = (int32_t)k;
+            }
+            testspace_en_i = i;
+            prereadloc = ai[0];
+        }
+        int64_t c_score_i = max_score_i;
+        int64_t st_loc = testspace_en_i, en_loc = testspace_en_i;
+        int64_t f_kmersize = ai[3] + 1;
+        while ((double)c_score_i > (max_scores - (double)f_kmersize)) {
+            int64_t now_count = Sicount[c_score_i];
+            if (now_count == 0) { --c_score_i; continue; }
+            st_loc = en_loc - now_count;
+            int64_t q_hi = en_loc - 1, q_lo = st_loc;
+            if (now_count > fast_t) q_hi = q_lo = closest2targetdistance(target[i], target, S_arg_i, st_loc, en_loc);
+            for (int64_t q = q_hi; q >= q_lo; --q) {
+                int64_t j = S_arg_i[q];
+                const int64_t *aj = a + j * 4;
+                int64_t bonus, readgap, refgap;
+                pair_gaps_asm(ai, aj, &bonus, &readgap, &refgap);
+                int64_t gapcost = llabs(readgap - refgap);
+                double t;
+                if (ai[2] == aj[2] && refgap >= 0 && readgap <= maxgap && gapcost <= maxdiff) {
+                    t = S[j] + (double)bonus - gapcost_list[gapcost];
+                } else {
+                    if (gapcost > tb->extra_size) gapcost = tb->extra_size;
+                    t = S[j] - skipcost + (double)bonus - (double)tb->extra[gapcost];
+                }
+                if (t > max_scores) { max_scores = t; pre_index = j; }
+            }
+            en_loc = st_loc;
+            --c_score_i;
+        }
+        S[i] = max_scores;
+        Si[i] = (int64_t)max_scores;
+        P[i] = (int32_t)pre_index;
+        if (max_scores > g_max_scores) { g_max_scores = max_scores; g_max_index = i; }
+    }
+    for (int64_t k = testspace_en_i; k < n; ++k) {
+        Sicount[Si[k]] += 1;
+        if (Si[k] > max_score_i) max_score_i = Si[k];
+        int64_t loc = insertpoint_score_distance(Si, Si[k], k, S_arg_i, target[k], target);
+        memmove(S_arg_i + loc + 1, S_arg_i + loc, sizeof(int32_t) * (size_t)(k - loc));
+        S_arg_i[loc] = (int32_t)k;
+    }
+    free(gapcost_list); free(target); free(Si); free(Sicount);
+    return g_max_index;
+}
+
 /* smallorequal2target_1d_point `13229-13264` (last index with S <= target, -1 if none) */
 static int64_t smallorequal(const double *arr, double target, int64_t n, const int64_t *point)
 {

@@ -100,6 +100,7 @@ def gen_asm_linked():
     import oracle.asm as oasm
     m = refimport.load_mode("asm")
     dall = getattr(m, "linked_" + P + "_d_all")
+    dfast = getattr(m, "linked_" + P + "_d_fast_all")
 
     @numba.njit
     def nb_argsort(a):
@@ -128,6 +129,15 @@ def gen_asm_linked():
     # an empty batch in the middle, and a flow whose first batch is a single anchor (P[g] < 0: nothing carried)
     flows.append([flows[2][0], np.zeros((0, 4), np.int64)] + flows[2][1:])
     flows.append([flows[3][0][:1]] + [flows[3][0][1:]] + flows[3][1:])
+    # a noise-only batch after a normal one: the exact DP bails out on opcount (:21754) and the loop falls back to
+    # the heuristic twin with the carried prefix (:23246-23247); then a normal batch again
+    noise = synth.anchors_global(rng, n_true=0, n_noise=3200, repeats=False)
+    noise = noise[nb_argsort(noise[:, 0])].astype(np.int64)
+    shift = int(flows[5][0][:, 0].max()) + 1
+    noise[:, 0] += shift
+    tail = flows[5][1].copy()
+    tail[:, 0] += int(noise[:, 0].max()) + 1
+    flows.append([flows[5][0], noise, tail])
     for fi, batches in enumerate(flows):
         rec = []
 
@@ -137,12 +147,25 @@ def gen_asm_linked():
                         A.copy()))
             return g, S, Pp, A
 
-        path = oasm.first_round_path(batches, 15, 40., 50, 1000, dp=dp)
+        def dpf(gs, gi, pS, pP, prl, lk, rec=rec):
+            g, S, Pp, A = dfast(gs, gi, pS, pP, prl, lk, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
+            rec[-1] = rec[-1] + (int(g), S.copy(), Pp.copy(), A.copy())
+            return g, S, Pp, A
+
+        path = oasm.first_round_path(batches, 15, 40., 50, 1000, dp=dp, dp_fast=dpf)
         out["f%d_nb" % fi] = np.array(len(batches))
         for bi, b in enumerate(batches):
             out["f%d_b%d" % (fi, bi)] = b.astype(np.int32) if (len(b) == 0 or b.max() < 2**31) else b
         out["f%d_calls" % fi] = np.array(len(rec))
-        for ci, (hd, pS, pP, lk, g, S, Pp, A) in enumerate(rec):
+        for ci, r in enumerate(rec):
+            hd, pS, pP, lk, g, S, Pp, A = r[:8]
+            # the heuristic twin on the same arguments: what the loop used after a bail-out, else run here
+            fg, fS, fP, fA = r[8:] if len(r) > 8 else dfast(hd[0] if len(pS) else 0, int(hd[1]) if len(pS) else 0, pS, pP, int(hd[2]),
+                                                            lk, kmersize=15, skipcost=40., maxdiff=50, maxgap=1000)
+            out["f%d_c%d_fg" % (fi, ci)] = np.array(int(fg))
+            out["f%d_c%d_fS" % (fi, ci)] = fS
+            out["f%d_c%d_fP" % (fi, ci)] = fP
+            out["f%d_c%d_fA" % (fi, ci)] = fA
             out["f%d_c%d_head" % (fi, ci)] = hd
             out["f%d_c%d_preS" % (fi, ci)] = pS
             out["f%d_c%d_preP" % (fi, ci)] = pP

@@ -172,11 +172,12 @@ def test_asm_linked_dp_matches_reference_and_oracle(gpu_ctx):
             ci = len(seen)
             r = chain_linked_batch([(gs, gi, pS, pP, prl, lk)], prm, ctx=gpu_ctx)[0]
             assert r.g_max_index == int(G["f%d_c%d_g" % (fi, ci)]), (fi, ci)
-            assert np.array_equal(r.S, G["f%d_c%d_S" % (fi, ci)]), (fi, ci)
-            assert np.array_equal(r.P, G["f%d_c%d_P" % (fi, ci)]), (fi, ci)
-            assert np.array_equal(r.S_arg, G["f%d_c%d_A" % (fi, ci)]), (fi, ci)
-            jobs.append((gs, gi, pS.copy(), pP.copy(), prl, lk.copy()))
-            want.append(r)
+            if r.g_max_index >= 0:          # -1: opcount bail-out (the loop then takes the oracle's heuristic twin)
+                assert np.array_equal(r.S, G["f%d_c%d_S" % (fi, ci)]), (fi, ci)
+                assert np.array_equal(r.P, G["f%d_c%d_P" % (fi, ci)]), (fi, ci)
+                assert np.array_equal(r.S_arg, G["f%d_c%d_A" % (fi, ci)]), (fi, ci)
+                jobs.append((gs, gi, pS.copy(), pP.copy(), prl, lk.copy()))
+                want.append(r)
             seen.append(1)
             return r.g_max_index, r.S, r.P, r.S_arg
 
