@@ -120,12 +120,14 @@ int vm_chain_global_times(vm_ctx *ctx, float *ms4);
  *   off      int64[n_jobs+1]; pre_n int32[n_jobs] (0: plain start, :21720-21729)
  *   head     float64[n_jobs][3] = g_max_scores, g_max_index, prereadloc of the call (ignored when pre_n == 0)
  *   S, P     IN: the first pre_n[j] entries of every job hold pre_S / pre_P; OUT: all of S, P (int32, -9999999 = start)
- *   S_arg    OUT int32[total]; g_max_index OUT int64[n_jobs], -1 = opcount bail-out (:21754; the caller then runs
- *            the _d_fast_all twin, not part of this entry point yet)
+ *   S_arg    OUT int32[total]; g_max_index OUT int64[n_jobs]
+ *   used_fast OUT int32[n_jobs] (optional): 1 where the exact DP bailed out on opcount (:21754) and the result is the
+ *            heuristic twin's, linked_..._fine_list_d_fast_all (:21872-22158) on the same arguments -- the caller's
+ *            fall-back at :23246-23247 (S_arg is then its S_arg_i)
  */
 int vm_chain_linked_batch(vm_ctx *ctx, const vm_chain_params *prm, int64_t n_jobs, const int64_t *anchors, const int64_t *off,
                           const int32_t *pre_n, const double *head, double *S, int32_t *P, int32_t *S_arg,
-                          int64_t *g_max_index);
+                          int64_t *g_max_index, int32_t *used_fast);
 
 /*
  * Stage-level local chaining (parity tests).  Replaces get_optimal_chain_..._fine_list (variant 1,

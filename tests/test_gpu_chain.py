@@ -163,7 +163,7 @@ def test_asm_linked_dp_matches_reference_and_oracle(gpu_ctx):
     from vacmap_b200.chain import ChainParams, chain_linked_batch
     G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_linked.npz"))
     prm = ChainParams(kmersize=15, skipcost=40.0, maxdiff=50, maxgap=1000)
-    jobs, want = [], []
+    jobs, want, n_fast = [], [], []
     for fi in range(int(G["n_flows"])):
         batches = [G["f%d_b%d" % (fi, bi)].astype(np.int64).reshape(-1, 4) for bi in range(int(G["f%d_nb" % fi]))]
         seen = []
@@ -171,20 +171,26 @@ def test_asm_linked_dp_matches_reference_and_oracle(gpu_ctx):
         def dp(gs, gi, pS, pP, prl, lk, seen=seen, fi=fi):
             ci = len(seen)
             r = chain_linked_batch([(gs, gi, pS, pP, prl, lk)], prm, ctx=gpu_ctx)[0]
-            assert r.g_max_index == int(G["f%d_c%d_g" % (fi, ci)]), (fi, ci)
-            if r.g_max_index >= 0:          # -1: opcount bail-out (the loop then takes the oracle's heuristic twin)
-                assert np.array_equal(r.S, G["f%d_c%d_S" % (fi, ci)]), (fi, ci)
-                assert np.array_equal(r.P, G["f%d_c%d_P" % (fi, ci)]), (fi, ci)
-                assert np.array_equal(r.S_arg, G["f%d_c%d_A" % (fi, ci)]), (fi, ci)
-                jobs.append((gs, gi, pS.copy(), pP.copy(), prl, lk.copy()))
-                want.append(r)
+            # where the reference's exact DP bails out on opcount its caller takes the heuristic twin: so does the entry point
+            tag = "f" if int(G["f%d_c%d_g" % (fi, ci)]) == -1 else ""
+            assert r.used_fast == (1 if tag else 0), (fi, ci)
+            n_fast.append(r.used_fast)
+            assert r.g_max_index == int(G["f%d_c%d_%sg" % (fi, ci, tag)]), (fi, ci)
+            assert np.array_equal(r.S, G["f%d_c%d_%sS" % (fi, ci, tag)]), (fi, ci)
+            assert np.array_equal(r.P, G["f%d_c%d_%sP" % (fi, ci, tag)]), (fi, ci)
+            assert np.array_equal(r.S_arg, G["f%d_c%d_%sA" % (fi, ci, tag)]), (fi, ci)
+            jobs.append((gs, gi, pS.copy(), pP.copy(), prl, lk.copy()))
+            want.append(r)
             seen.append(1)
             return r.g_max_index, r.S, r.P, r.S_arg
 
         path = oasm.first_round_path(batches, 15, 40., 50, 1000, dp=dp)
         assert np.array_equal(np.array(path, dtype=np.int64).reshape(-1, 4), G["f%d_path" % fi]), fi
-    assert len(jobs) >= 20
+    assert len(jobs) >= 20 and sum(n_fast) >= 1
     for r, w, j in zip(chain_linked_batch(jobs, prm, ctx=gpu_ctx), want, jobs):
         assert r.g_max_index == w.g_max_index and np.array_equal(r.S, w.S) and np.array_equal(r.P, w.P) and np.array_equal(r.S_arg, w.S_arg)
-        o = oracle.chain_linked_d_all(j[0], j[1], j[2], j[3], j[4], j[5], 15, 40., 50, 1000)
+        if r.used_fast:
+            o = oracle.chain_linked_fast(j[0], j[1], j[2], j[3], j[4], j[5], 15, 40., 50, 1000)
+        else:
+            o = oracle.chain_linked_d_all(j[0], j[1], j[2], j[3], j[4], j[5], 15, 40., 50, 1000)
         assert o[0] == r.g_max_index and np.array_equal(o[1], r.S) and np.array_equal(o[2], r.P) and np.array_equal(o[3], r.S_arg)

@@ -125,7 +125,7 @@ def chain_local_batch(anchor_list, read_lens, params, presorted=True, force_fast
     return [LocalChainResult(float(score[i]), path[path_off[i]:path_off[i + 1]].copy(), int(used_fast[i])) for i in range(n)]
 
 
-LinkedChainResult = collections.namedtuple("LinkedChainResult", "g_max_index S P S_arg")
+LinkedChainResult = collections.namedtuple("LinkedChainResult", "g_max_index S P S_arg used_fast")
 
 
 def chain_linked_batch(jobs, params=None, ctx=None, device=0):
@@ -133,10 +133,11 @@ def chain_linked_batch(jobs, params=None, ctx=None, device=0):
     argument list of ``linked_get_optimal_chain_..._fine_list_d_all`` (mammap_asm.py:21687):
     ``(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, one_mapinfo)`` with ``one_mapinfo`` int64[n,4] = the
     ``len(pre_S)`` carried anchors followed by the batch sorted by read position.  Returns what the function returns
-    per job: ``(g_max_index | -1, S, P, S_arg)``."""
+    per job, ``(g_max_index, S, P, S_arg)`` -- or, where it bails out on opcount (``used_fast``), what its caller's
+    fall-back ``..._d_fast_all`` returns on the same arguments (:23246-23247)."""
     L = _lib.load()
     vp, i64 = ctypes.c_void_p, ctypes.c_int64
-    L.vm_chain_linked_batch.argtypes = [vp, ctypes.POINTER(_lib.ChainParamsC), i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.vm_chain_linked_batch.argtypes = [vp, ctypes.POINTER(_lib.ChainParamsC), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     ctx = ctx or _lib.default_context(device)
     params = params or ChainParams()
     rows, off = _ragged([j[5] for j in jobs])
@@ -152,8 +153,9 @@ def chain_linked_batch(jobs, params=None, ctx=None, device=0):
         P[off[i]:off[i] + len(pP)] = pP
     A = np.zeros(max(total, 1), np.int32)
     g = np.zeros(max(n, 1), np.int64)
+    uf = np.zeros(max(n, 1), np.int32)
     pc = params.c()
     _lib.check(ctx.h, L.vm_chain_linked_batch(ctx.h, ctypes.byref(pc), n, _lib.ptr(rows), _lib.ptr(off), _lib.ptr(pre_n),
-                                              _lib.ptr(head), _lib.ptr(S), _lib.ptr(P), _lib.ptr(A), _lib.ptr(g)))
-    return [LinkedChainResult(int(g[i]), S[off[i]:off[i + 1]].copy(), P[off[i]:off[i + 1]].copy(), A[off[i]:off[i + 1]].copy())
-            for i in range(n)]
+                                              _lib.ptr(head), _lib.ptr(S), _lib.ptr(P), _lib.ptr(A), _lib.ptr(g), _lib.ptr(uf)))
+    return [LinkedChainResult(int(g[i]), S[off[i]:off[i + 1]].copy(), P[off[i]:off[i + 1]].copy(), A[off[i]:off[i + 1]].copy(),
+                              int(uf[i])) for i in range(n)]

@@ -188,7 +188,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     int rc = vm_chain_args(c, s, prm, A);
     if (rc != VM_OK) return rc;
     const bool by_end = prm.variant == 1 || prm.variant == 2;
-    const bool linked = prm.variant == 3;      // asm mode: no fast fall-back here, a bail-out is reported as g_max_index -1
+    const bool linked = prm.variant == 3;      // asm mode: jobs, not reads -- no n / read_len short cut to the fast DP
     std::vector<std::vector<int>> cls(kNumCaps + 1);
     std::vector<int> fast_ids;
     bool may_bail = false;
@@ -201,7 +201,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         while (k < kNumCaps && n > kCaps[k]) ++k;
         cls[k].push_back(r);
         // global: opcount/i > 1000 needs i > 2000; local: opcount > 100000 needs n(n-1)/2 > 100000
-        if (!linked && (by_end ? n > 440 : n > 2000)) may_bail = true;
+        if (by_end ? n > 440 : n > 2000) may_bail = true;
     }
     std::vector<int> ids_host;
     std::vector<int> cls_start(kNumCaps + 2, 0);
@@ -410,7 +410,8 @@ int vm_chain_global_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_reads
 }
 
 int vm_chain_linked_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_jobs, const int64_t *anchors, const int64_t *off,
-                          const int32_t *pre_n, const double *head, double *S, int32_t *P, int32_t *S_arg, int64_t *g_max_index)
+                          const int32_t *pre_n, const double *head, double *S, int32_t *P, int32_t *S_arg, int64_t *g_max_index,
+                          int32_t *used_fast)
 {
     if (!c) return VM_ERR_ARG;
     if (!prm || !off || n_jobs < 0 || (n_jobs > 0 && (!pre_n || !head || !S || !P))) { c->err = "bad argument"; return VM_ERR_ARG; }
@@ -418,8 +419,16 @@ int vm_chain_linked_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_jobs,
     p.variant = 3;
     for (int64_t r = 0; r < n_jobs; ++r)
         if (pre_n[r] < 0 || pre_n[r] > off[r + 1] - off[r]) { c->err = "pre_n out of range"; return VM_ERR_ARG; }
-    // jobs never take the n / read_len > 5 short cut of hit2work_1 (that rule belongs to the per-read path)
-    std::vector<int32_t> rl((size_t)std::max<int64_t>(n_jobs, 1), INT32_MAX / 2);
+    // "read length" of a job = what sizes the fast DP's per-score counters: the largest chain score it can reach
+    // (carried scores + the read span of its anchors)
+    std::vector<int32_t> rl((size_t)std::max<int64_t>(n_jobs, 1), 0);
+    for (int64_t r = 0; r < n_jobs; ++r) {
+        double carried = 0;
+        for (int64_t t = 0; t < pre_n[r]; ++t) carried = std::max(carried, S[off[r] + t]);
+        int64_t span = 0;
+        for (int64_t t = off[r]; t < off[r + 1]; ++t) span = std::max(span, anchors[t * 4] + anchors[t * 4 + 3]);
+        rl[(size_t)r] = (int32_t)std::min<double>((double)span + carried + 1064.0, (double)(INT32_MAX - 256));
+    }
     int rc = vm_chain_global_upload(c, &p, n_jobs, anchors, off, rl.data());
     if (rc != VM_OK) return rc;
     VmChainState &s = c->chain;
@@ -437,9 +446,10 @@ int vm_chain_linked_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_jobs,
     std::vector<int> ids((size_t)n_jobs);
     for (int64_t r = 0; r < n_jobs; ++r) ids[(size_t)r] = (int)r;
     c->launches += vm_launch_pack(s.rows.as<int64_t>(), s.anch.as<VmAnchor>(), s.total, c->stream);
-    rc = vm_chain_core(c, p, s.anch.as<VmAnchor>(), s.off, s.cnt, s.read_len, s.cnt_len, ids, nullptr, nullptr, s.ms, true, false);
+    s.used_fast.assign((size_t)n_jobs, 0);
+    rc = vm_chain_core(c, p, s.anch.as<VmAnchor>(), s.off, s.cnt, s.read_len, s.cnt_len, ids, nullptr, &s.used_fast, s.ms, true, false);
     if (rc != VM_OK) return rc;
-    return vm_chain_global_download(c, nullptr, S, P, S_arg, g_max_index, nullptr);
+    return vm_chain_global_download(c, nullptr, S, P, S_arg, g_max_index, used_fast);
 }
 
 } // extern "C"

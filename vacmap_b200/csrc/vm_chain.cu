@@ -496,8 +496,9 @@ __global__ void __launch_bounds__(32) vm_chain_fast_kernel(VmChainArgs A, int fa
     const VmAnchor *__restrict__ a = A.anchors + base;
     double *gcl = (double *)vm_smem;
     float *rgl = (float *)(gcl + VM_GCL_MAX);
+    constexpr bool GLOBAL = VARIANT == 0 || VARIANT == 3;      // 3: asm mode's linked twin (mammap_asm.py:21872-22158)
     for (int t = lane; t <= A.maxdiff && t < VM_GCL_MAX; t += 32) gcl[t] = A.gapcost_list[t];
-    if (VARIANT != 0)
+    if (!GLOBAL)
         for (int t = lane; t < A.n_rg && t < VM_RGL_MAX; t += 32) rgl[t] = A.rgcost[t];
     __syncwarp();
     if (n <= 0) {
@@ -529,22 +530,37 @@ __global__ void __launch_bounds__(32) vm_chain_fast_kernel(VmChainArgs A, int fa
     __syncwarp();
 
     const VmAnchor a0 = a[0];
-    int prekey = VARIANT == 0 ? a0.x : a0.x + a0.l;
+    int prekey = GLOBAL ? a0.x : a0.x + a0.l;
     int testspace_en_i = 1;
-    if (lane == 0) {
+    double g_max_scores = (double)a0.l;
+    int g_max_index = 0;
+    long long max_score_i = 0;
+    int i_first = 1;
+    const int pre_n = VARIANT == 3 ? A.pre_n[rid] : 0;
+    if (pre_n > 0) {
+        // carried prefix (:21903-21914): S / P already hold pre_S / pre_P; only its first anchor is in the test space
+        for (int t = lane; t < pre_n; t += 32) Si[t] = (long long)S[t];
+        __syncwarp();
+        max_score_i = Si[0];
+        if (lane == 0) {
+            arg[0] = 0;
+            if (max_score_i >= 0 && max_score_i < cnt_size) count[max_score_i] = 1;
+        }
+        g_max_scores = A.head[3 * rid];
+        g_max_index = (int)A.head[3 * rid + 1];
+        prekey = (int)A.head[3 * rid + 2];
+        i_first = pre_n;
+    } else if (lane == 0) {
         arg[0] = 0; S[0] = (double)a0.l; Si[0] = a0.l; P[0] = VM_NOPRE;
         if (a0.l < cnt_size) count[a0.l] = 1;
     }
     __syncwarp();
-    double g_max_scores = (double)a0.l;
-    int g_max_index = 0;
-    long long max_score_i = 0;
 
-    for (int i = 1; i < n; ++i) {
+    for (int i = i_first; i < n; ++i) {
         const VmAnchor ai = a[i];
         double max_scores = (double)ai.l;
         int pre_index = VM_NOPRE;
-        const int key = VARIANT == 0 ? ai.x : ai.x + ai.l;
+        const int key = GLOBAL ? ai.x : ai.x + ai.l;
         if (prekey < key) {
             for (int k = testspace_en_i; k < i; ++k) {
                 const long long sk = Si[k];
@@ -609,6 +625,7 @@ int vm_launch_chain_fast(int variant, const VmChainArgs &args, int fast_t, const
     switch (variant) {
     case 0: vm_chain_fast_kernel<0><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
     case 1: vm_chain_fast_kernel<1><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
+    case 3: vm_chain_fast_kernel<3><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
     default: vm_chain_fast_kernel<2><<<n_ids, 32, smem, stream>>>(args, fast_t, read_ids_dev, scratch_i64, scratch_off); break;
     }
     return 1;
