@@ -60,7 +60,7 @@ def _declare(L):
     L.orc_chain_global_d_all.restype = i64
     L.orc_chain_global_d_all.argtypes = [vp, i64, i32, dbl, i64, i64, vp, i64, vp, vp, vp, vp]
     L.orc_chain_linked_d_all.restype = i64
-    L.orc_chain_linked_d_all.argtypes = [vp, i64, i64, vp, vp, dbl, i64, i64, i32, dbl, i64, i64, vp, i64, vp, vp, vp, vp]
+    L.orc_chain_linked_d_all.argtypes = [vp, i64, i64, vp, vp, dbl, i64, i64, i32, dbl, i64, i64, vp, i64, vp, vp, vp, vp, vp]
     L.orc_chain_linked_fast.restype = i64
     L.orc_chain_linked_fast.argtypes = [vp, i64, i64, vp, vp, dbl, i64, i64, i32, dbl, i64, i64, i64, vp, vp, vp, vp]
     L.orc_chain_fast.restype = i64
@@ -134,10 +134,24 @@ def chain_global_d_all(a, kmersize, skipcost, maxdiff, maxgap, max_factor=1000):
     return g, S, P, A, int(op[0])
 
 
+_ASM_RG = None
+
+
+def asm_readgapcost():
+    """asm mode's readgapcost_list (mammap_asm.py:16536-16538): float32[100], 0.1 log2(r) -- not clrnano's log2(r + 1)."""
+    global _ASM_RG
+    if _ASM_RG is None:
+        _ASM_RG = np.zeros(100, dtype=np.float32)
+        for r in range(1, 100):
+            _ASM_RG[r] = 0.1 * np.log2(r)
+    return _ASM_RG
+
+
 def chain_linked_d_all(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, a, kmersize, skipcost, maxdiff, maxgap,
-                       max_factor=1000):
-    """asm mode: `linked_..._fine_list_d_all` (mammap_asm.py:21687).  a: int64[n,4] = carried anchors (len(pre_S) of
-    them) + this batch sorted by read position.  Returns (g_max_index | -1, S, P, S_arg, opcount)."""
+                       max_factor=1000, local=False):
+    """asm mode: `linked_..._fine_list_d_all` (mammap_asm.py:21687), or with local=True its second-round twin
+    `linked_..._fine_list_all` (:21505).  a: int64[n,4] = carried anchors (len(pre_S) of them) + this batch sorted by
+    read position.  Returns (g_max_index | -1, S, P, S_arg, opcount)."""
     a = np.ascontiguousarray(a, dtype=np.int64)
     pre_S = np.ascontiguousarray(pre_S, dtype=np.float64)
     pre_P = np.ascontiguousarray(pre_P, dtype=np.int32)
@@ -149,7 +163,8 @@ def chain_linked_d_all(g_max_scores, g_max_index, pre_S, pre_P, prereadloc, a, k
     t = tables()
     g = lib().orc_chain_linked_d_all(_p(a), n, len(pre_S), _p(pre_S) if len(pre_S) else None, _p(pre_P) if len(pre_P) else None,
                                      float(g_max_scores), int(g_max_index), int(prereadloc), kmersize, float(skipcost), maxdiff,
-                                     maxgap, ctypes.addressof(t["struct"]), max_factor, _p(S), _p(P), _p(A), _p(op))
+                                     maxgap, ctypes.addressof(t["struct"]), max_factor, _p(asm_readgapcost()) if local else None,
+                                     _p(S), _p(P), _p(A), _p(op))
     return g, S, P, A, int(op[0])
 
 

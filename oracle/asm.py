@@ -14,6 +14,33 @@ import numpy as np
 import oracle
 
 
+def second_round_path(batches, kmersize, skipcost, maxdiff, maxgap=99, dp=None):
+    """Second round (mammap_asm.py:23306-23404): the same batch loop over the re-seeded local anchors with
+    `linked_..._fine_list_all` (no bail-out, no fall-back), then the overlap trimming of :23393-23402 (an anchor
+    reaching into its successor is cut back to the successor's start; the comparison runs against the UNtrimmed
+    neighbour) and the reversal to ASCENDING read order that `ass_extend_func` takes.  [] if <= 1 anchors."""
+    if dp is None:
+        def dp(gs, gi, pS, pP, prl, a):
+            g, S, P, A, _ = oracle.chain_linked_d_all(gs, gi, pS, pP, prl, a, kmersize, skipcost, maxdiff, maxgap, local=True)
+            return g, S, P, A
+
+    def never(*_):
+        raise AssertionError("the second-round DP has no bail-out")
+    path = first_round_path(batches, kmersize, skipcost, maxdiff, maxgap, dp=dp, dp_fast=never)
+    if not path:
+        return []
+    pre = path[0]
+    for t in range(1, len(path)):
+        now = path[t]
+        if not pre[0] >= now[0] + now[3]:
+            if now[2] == 1:
+                path[t] = (now[0], now[1], now[2], pre[0] - now[0])
+            else:
+                path[t] = (now[0], now[1] + now[3] - pre[0] + now[0], now[2], pre[0] - now[0])
+        pre = now
+    return path[::-1]
+
+
 def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None, dp_fast=None):
     """batches: iterable of int64[m,4] anchor arrays, each sorted by read position.  Returns the chain as a list of
     (readpos, refpos, strand, len) in DESCENDING read order (as the reference's `path`), [] if it has <= 1 anchors.

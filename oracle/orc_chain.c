@@ -267,11 +267,14 @@ static inline void pair_gaps_asm(const int64_t *ai, const int64_t *aj,
  * and only S_arg[0] = 0 is in the test space until the read position first advances (`21713-21718`).  pre_n == 0:
  * the plain start (`21720-21729`).  No coverage term; the scan stops at the first S_j <= best - l_i (`21777`).
  * Returns g_max_index, or -1 on the opcount bail-out (`21754`).
+ * rgcost != NULL: the second-round twin linked_..._fine_list_all (`21505-21686`) instead -- the same loop, anchors
+ * still ordered by read START, colinear pairs also pay readgapcost_list[readgap] (asm's table, `16536-16538`:
+ * 0.1 log2(r), float32[100]) and there is no bail-out.
  */
 int64_t orc_chain_linked_d_all(const int64_t *a, int64_t n, int64_t pre_n, const double *pre_S, const int32_t *pre_P,
                                double g_max_scores, int64_t g_max_index, int64_t prereadloc, int kmersize,
                                double skipcost, int64_t maxdiff, int64_t maxgap, const orc_tables *tb, int64_t max_factor,
-                               double *S, int32_t *P, int32_t *S_arg, int64_t *opcount_out)
+                               const float *rgcost, double *S, int32_t *P, int32_t *S_arg, int64_t *opcount_out)
 {
     double *gapcost_list = (double *)malloc(sizeof(double) * (size_t)(maxdiff + 1));
     orc_gapcost_table(kmersize, (int)maxdiff, 0, gapcost_list);
@@ -296,7 +299,7 @@ int64_t orc_chain_linked_d_all(const int64_t *a, int64_t n, int64_t pre_n, const
         double max_scores = (double)ai[3];
         int64_t pre_index = NOPRE;
         if (prereadloc < ai[0]) {
-            if (((double)opcount / (double)i) > (double)max_factor) { ret = -1; goto done; }
+            if (!rgcost && ((double)opcount / (double)i) > (double)max_factor) { ret = -1; goto done; }
             for (int64_t k = testspace_en; k < i; ++k) {
                 int64_t loc = insertpoint_score(S, S[k], k, S_arg);
                 memmove(S_arg + loc + 1, S_arg + loc, sizeof(int32_t) * (size_t)(k - loc));
@@ -315,6 +318,7 @@ int64_t orc_chain_linked_d_all(const int64_t *a, int64_t n, int64_t pre_n, const
                 double t;
                 if (ai[2] == a[j * 4 + 2] && refgap >= 0 && readgap <= maxgap && gapcost <= maxdiff) {
                     t = S[j] + (double)bonus - gapcost_list[gapcost];
+                    if (rgcost) t = t - (double)rgcost[readgap];
                 } else {
                     if (gapcost > tb->extra_size) gapcost = tb->extra_size;
                     t = S[j] - skipcost + (double)bonus - (double)tb->extra[gapcost];

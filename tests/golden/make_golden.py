@@ -176,6 +176,52 @@ def gen_asm_linked():
         out["f%d_path" % fi] = np.array(path, dtype=np.int64).reshape(-1, 4)
         print("flow", fi, "batches", [len(b) for b in batches], "calls", len(rec), "path", len(path))
     out["n_flows"] = np.array(len(flows))
+    # --- second round: linked_..._fine_list_all over local (k = 9) anchors, sorted by read start ---
+    dloc = getattr(m, "linked_" + P + "_all")
+    lflows = []
+    for t in range(6):
+        if t == 0:
+            a = synth.anchors_tieheavy(rng, n=500, k=9)
+        else:
+            a = synth.anchors_local(rng, n_true=int(rng.integers(100, 900)), n_noise=int(rng.integers(0, 300)), multi=(t % 2 == 0))
+        a = a[nb_argsort(a[:, 0])].astype(np.int64)
+        nb = int(rng.integers(1, 5))
+        cuts = sorted(set(int(c) for c in rng.integers(1, len(a) - 1, size=nb - 1))) if nb > 1 else []
+
+        def slide(c):
+            while c < len(a) and a[c][0] == a[c - 1][0]:
+                c += 1
+            return c
+        cuts = sorted(set(c for c in map(slide, cuts) if c < len(a)))
+        lflows.append(np.split(a, cuts))
+    for fi, batches in enumerate(lflows):
+        rec = []
+
+        def dpl(gs, gi, pS, pP, prl, lk, rec=rec):
+            g, S, Pp, A, _ = dloc(gs, gi, pS, pP, prl, lk, kmersize=9, skipcost=30., maxdiff=30, maxgap=99)
+            rec.append((int(g), S.copy(), Pp.copy(), A.copy()))
+            return g, S, Pp, A
+
+        try:
+            path = oasm.second_round_path(batches, 9, 30., 30, 99, dp=dpl)
+            out["l%d_err" % fi] = np.array(0)
+        except IndexError:
+            # a chain that STARTS in a carried anchor: pre_P = -(-9999999) is followed as an index by the traceback
+            # (:23380-23385) -- the reference raises here too and the contig yields nothing
+            path = []
+            out["l%d_err" % fi] = np.array(1)
+        out["l%d_nb" % fi] = np.array(len(batches))
+        for bi, b in enumerate(batches):
+            out["l%d_b%d" % (fi, bi)] = b.astype(np.int32) if (len(b) == 0 or b.max() < 2**31) else b
+        out["l%d_calls" % fi] = np.array(len(rec))
+        for ci, (g, S, Pp, A) in enumerate(rec):
+            out["l%d_c%d_g" % (fi, ci)] = np.array(g)
+            out["l%d_c%d_S" % (fi, ci)] = S
+            out["l%d_c%d_P" % (fi, ci)] = Pp
+            out["l%d_c%d_A" % (fi, ci)] = A
+        out["l%d_path" % fi] = np.array(path, dtype=np.int64).reshape(-1, 4)
+        print("local flow", fi, "batches", [len(b) for b in batches], "calls", len(rec), "path", len(path))
+    out["n_lflows"] = np.array(len(lflows))
     np.savez_compressed(os.path.join(HERE, "asm_linked.npz"), **out)
     print("asm_linked.npz:", os.path.getsize(os.path.join(HERE, "asm_linked.npz")), "bytes")
 

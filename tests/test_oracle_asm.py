@@ -51,3 +51,40 @@ def test_default_dp_is_the_oracle_and_short_chains_give_nothing():
     assert np.array_equal(np.array(oasm.first_round_path(batches, 15, 40., 50, 1000)), G["f2_path"])
     assert oasm.first_round_path([np.array([[5, 100, 1, 15]])], 15, 40., 50, 1000) == []
     assert oasm.first_round_path([], 15, 40., 50, 1000) == []
+
+
+def test_second_round_linked_dp_matches_reference():
+    """`linked_..._fine_list_all` (local anchors, asm's own read-gap table, no bail-out) call by call, and the trimmed
+    ascending path of the second-round loop (the trimming itself is the build's restatement of inline code)."""
+    n_calls = n_err = 0
+    for fi in range(int(G["n_lflows"])):
+        batches = [G["l%d_b%d" % (fi, bi)].astype(np.int64).reshape(-1, 4) for bi in range(int(G["l%d_nb" % fi]))]
+        seen = []
+
+        def dp(gs, gi, pS, pP, prl, lk, seen=seen, fi=fi):
+            ci = len(seen)
+            g, S, P, A, _ = oracle.chain_linked_d_all(gs, gi, pS, pP, prl, lk, 9, 30., 30, 99, local=True)
+            assert g == int(G["l%d_c%d_g" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(S, G["l%d_c%d_S" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(P, G["l%d_c%d_P" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(A, G["l%d_c%d_A" % (fi, ci)]), (fi, ci)
+            seen.append(1)
+            return g, S, P, A
+
+        if int(G["l%d_err" % fi]):
+            # a chain starting in a carried anchor: its negated "no predecessor" mark is followed as an index
+            # (:23380-23385) and the reference raises -- so must the restatement
+            import pytest
+            with pytest.raises(IndexError):
+                oasm.second_round_path(batches, 9, 30., 30, 99, dp=dp)
+            n_err += 1
+            n_calls += len(seen)
+            continue
+        path = oasm.second_round_path(batches, 9, 30., 30, 99, dp=dp)
+        assert len(seen) == int(G["l%d_calls" % fi])
+        want = G["l%d_path" % fi]
+        assert np.array_equal(np.array(path, dtype=np.int64).reshape(-1, 4), want), fi
+        if len(want) > 1:           # ascending, and no anchor reaches past its successor's start
+            assert (np.diff(want[:, 0]) >= 0).all() and (want[:-1, 0] + want[:-1, 3] <= want[1:, 0]).all()
+        n_calls += len(seen)
+    assert n_calls >= 10
