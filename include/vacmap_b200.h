@@ -72,7 +72,7 @@ typedef struct vm_chain_params {
     int32_t max_factor;   /* 1000 (:19367) opcount bail-out of the exact global DP */
     int32_t fast_t;       /* 5: bucket size above which the fast DP probes one member */
     int32_t large_readgap;/* 30 (:28587) multi-chain local DP */
-    int32_t variant;      /* 0 global _d_all; 1 local _fine_list; 2 local _fine_list_mismatch; 3 asm linked _d_all (set by vm_chain_linked_batch) */
+    int32_t variant;      /* 0 global _d_all; 1 local _fine_list; 2 local _fine_list_mismatch; 3 / 4 asm linked _d_all / _all (vm_chain_linked_batch) */
 } vm_chain_params;
 
 /*
@@ -121,6 +121,8 @@ int vm_chain_global_times(vm_ctx *ctx, float *ms4);
  *   head     float64[n_jobs][3] = g_max_scores, g_max_index, prereadloc of the call (ignored when pre_n == 0)
  *   S, P     IN: the first pre_n[j] entries of every job hold pre_S / pre_P; OUT: all of S, P (int32, -9999999 = start)
  *   S_arg    OUT int32[total]; g_max_index OUT int64[n_jobs]
+ * prm->variant == 4 selects the second-round twin linked_..._fine_list_all (:21505-21686, called at :23343): same
+ * arguments and carry, asm's read-gap cost on colinear pairs, no bail-out; any other value the first-round DP.
  *   used_fast OUT int32[n_jobs] (optional): 1 where the exact DP bailed out on opcount (:21754) and the result is the
  *            heuristic twin's, linked_..._fine_list_d_fast_all (:21872-22158) on the same arguments -- the caller's
  *            fall-back at :23246-23247 (S_arg is then its S_arg_i)

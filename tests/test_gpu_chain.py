@@ -194,3 +194,36 @@ def test_asm_linked_dp_matches_reference_and_oracle(gpu_ctx):
         else:
             o = oracle.chain_linked_d_all(j[0], j[1], j[2], j[3], j[4], j[5], 15, 40., 50, 1000)
         assert o[0] == r.g_max_index and np.array_equal(o[1], r.S) and np.array_equal(o[2], r.P) and np.array_equal(o[3], r.S_arg)
+
+
+def test_asm_linked_second_round_dp_matches_reference(gpu_ctx):
+    """vm_chain_linked_batch with variant 4 == the reference's linked_..._fine_list_all on the golden second-round
+    flows (local anchors, asm's read-gap table, carried prefixes), call by call through the oracle's loop."""
+    import os
+    import oracle.asm as oasm
+    from vacmap_b200.chain import ChainParams, chain_linked_batch
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_linked.npz"))
+    prm = ChainParams(kmersize=9, skipcost=30.0, maxdiff=30, maxgap=99, variant=4)
+    n_calls = 0
+    for fi in range(int(G["n_lflows"])):
+        batches = [G["l%d_b%d" % (fi, bi)].astype(np.int64).reshape(-1, 4) for bi in range(int(G["l%d_nb" % fi]))]
+        seen = []
+
+        def dp(gs, gi, pS, pP, prl, lk, seen=seen, fi=fi):
+            ci = len(seen)
+            r = chain_linked_batch([(gs, gi, pS, pP, prl, lk)], prm, ctx=gpu_ctx)[0]
+            assert r.used_fast == 0 and r.g_max_index == int(G["l%d_c%d_g" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(r.S, G["l%d_c%d_S" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(r.P, G["l%d_c%d_P" % (fi, ci)]), (fi, ci)
+            assert np.array_equal(r.S_arg, G["l%d_c%d_A" % (fi, ci)]), (fi, ci)
+            seen.append(1)
+            return r.g_max_index, r.S, r.P, r.S_arg
+
+        if int(G["l%d_err" % fi]):
+            with pytest.raises(IndexError):
+                oasm.second_round_path(batches, 9, 30., 30, 99, dp=dp)
+        else:
+            path = oasm.second_round_path(batches, 9, 30., 30, 99, dp=dp)
+            assert np.array_equal(np.array(path, dtype=np.int64).reshape(-1, 4), G["l%d_path" % fi]), fi
+        n_calls += len(seen)
+    assert n_calls >= 10

@@ -140,6 +140,15 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
     if (p.variant == 1) {
         A.rgcost = c->readgapcost.as<float>();
         A.n_rg = (int)c->n_readgapcost;
+    } else if (p.variant == 4) {
+        // asm mode's own readgapcost_list (mammap_asm.py:16536-16538): float32[100], 0.1 log2(r)
+        if (p.maxgap + 1 > 100) { c->err = "maxgap too large for the linked local DP"; return VM_ERR_ARG; }
+        rg.assign(100, 0.0f);
+        for (int r = 1; r < 100; ++r) rg[(size_t)r] = (float)(0.1 * std::log2((double)r));
+        VM_CUDA_OK(c, s.rgl.ensure(rg.size() * sizeof(float)));
+        VM_CUDA_OK(c, cudaMemcpyAsync(s.rgl.p, rg.data(), rg.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        A.rgcost = s.rgl.as<float>();
+        A.n_rg = (int)rg.size();
     } else if (p.variant == 2) {
         if (p.maxgap + 1 > VM_RGL_MAX) { c->err = "maxgap too large for the local DP"; return VM_ERR_ARG; }
         vm_host_large_readgap(p.maxgap, p.large_readgap, rg);
@@ -188,7 +197,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     int rc = vm_chain_args(c, s, prm, A);
     if (rc != VM_OK) return rc;
     const bool by_end = prm.variant == 1 || prm.variant == 2;
-    const bool linked = prm.variant == 3;      // asm mode: jobs, not reads -- no n / read_len short cut to the fast DP
+    const bool linked = prm.variant >= 3;      // asm mode: jobs, not reads -- no n / read_len short cut to the fast DP
     std::vector<std::vector<int>> cls(kNumCaps + 1);
     std::vector<int> fast_ids;
     bool may_bail = false;
@@ -201,7 +210,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         while (k < kNumCaps && n > kCaps[k]) ++k;
         cls[k].push_back(r);
         // global: opcount/i > 1000 needs i > 2000; local: opcount > 100000 needs n(n-1)/2 > 100000
-        if (by_end ? n > 440 : n > 2000) may_bail = true;
+        if (prm.variant != 4 && (by_end ? n > 440 : n > 2000)) may_bail = true;      // variant 4 never bails out
     }
     std::vector<int> ids_host;
     std::vector<int> cls_start(kNumCaps + 2, 0);
@@ -416,7 +425,7 @@ int vm_chain_linked_batch(vm_ctx *c, const vm_chain_params *prm, int64_t n_jobs,
     if (!c) return VM_ERR_ARG;
     if (!prm || !off || n_jobs < 0 || (n_jobs > 0 && (!pre_n || !head || !S || !P))) { c->err = "bad argument"; return VM_ERR_ARG; }
     vm_chain_params p = *prm;
-    p.variant = 3;
+    p.variant = prm->variant == 4 ? 4 : 3;      // 4: the second-round twin linked_..._fine_list_all (:21505-21686)
     for (int64_t r = 0; r < n_jobs; ++r)
         if (pre_n[r] < 0 || pre_n[r] > off[r + 1] - off[r]) { c->err = "pre_n out of range"; return VM_ERR_ARG; }
     // "read length" of a job = what sizes the fast DP's per-score counters: the largest chain score it can reach

@@ -125,10 +125,13 @@ template <int VARIANT>
 __device__ __forceinline__ double vm_pair_score(const VmScoreCtx &c, const VmAnchor &ai, const VmAnchor &aj,
                                                 double Sj, bool &skip)
 {
-    constexpr bool GLOBAL = VARIANT == 0 || VARIANT == 3;      // 3: asm mode's linked global DP (mammap_asm.py:21687-21871)
+    // 3 / 4: asm mode's linked DPs (mammap_asm.py:21687-21871 first round; :21505-21686 second round = the same
+    // with a read-gap cost on colinear pairs)
+    constexpr bool GLOBAL = VARIANT == 0 || VARIANT >= 3;
+    constexpr bool READGAP = VARIANT == 1 || VARIANT == 2 || VARIANT == 4;
     int bonus, readgap;
     long long refgap;
-    if (VARIANT == 3) vm_pair_gaps_asm(ai, aj, bonus, readgap, refgap);
+    if (VARIANT >= 3) vm_pair_gaps_asm(ai, aj, bonus, readgap, refgap);
     else vm_pair_gaps(ai, aj, bonus, readgap, refgap);
     skip = false;
     if (!GLOBAL && (ai.x - aj.x - aj.l) < 0 && bonus <= 0) { skip = true; return -CUDART_INF; }
@@ -136,7 +139,7 @@ __device__ __forceinline__ double vm_pair_score(const VmScoreCtx &c, const VmAnc
     if (ai.s == aj.s && refgap >= 0 && readgap <= c.maxgap && gapcost <= (long long)c.maxdiff) {
         double t = Sj + (double)bonus;
         t = t - c.gcl[gapcost];
-        if (!GLOBAL) t = t - (double)c.rgl[readgap];
+        if (READGAP) t = t - (double)c.rgl[readgap];
         return t;
     }
     if (GLOBAL) {
@@ -262,10 +265,10 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
         S = A.S + base;
         arg = A.S_arg + base;
     }
-    constexpr bool GLOBAL = VARIANT == 0 || VARIANT == 3;
-    constexpr int INS = VARIANT == 3 ? 0 : VARIANT;             // S_arg insertion rule (insertpoint_score for both global DPs)
+    constexpr bool GLOBAL = VARIANT == 0 || VARIANT >= 3;
+    constexpr int INS = VARIANT >= 3 ? 0 : VARIANT;             // S_arg insertion rule (insertpoint_score for the read-start ordered DPs)
     for (int t = lane; t <= A.maxdiff && t < VM_GCL_MAX; t += 32) gcl[t] = A.gapcost_list[t];
-    if (!GLOBAL)
+    if (VARIANT == 1 || VARIANT == 2 || VARIANT == 4)
         for (int t = lane; t < A.n_rg && t < VM_RGL_MAX; t += 32) rgl[t] = A.rgcost[t];
     __syncwarp();
     if (n <= 0) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
     double g_max_scores = (double)a0.l;
     int g_max_index = 0;
     int i_first = 1;
-    const int pre_n = VARIANT == 3 ? A.pre_n[rid] : 0;
+    const int pre_n = VARIANT >= 3 ? A.pre_n[rid] : 0;
     if (pre_n > 0) {
         // carried anchors in front of the batch (:21713-21718): their scores / negated back-pointers are already in
         // S / P, only the first of them is in the test space until the read position first advances
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
         const int key = GLOBAL ? ai.x : ai.x + ai.l;
         if (prekey < key) {
             if (GLOBAL) {
-                if (((double)opcount / (double)i) > (double)A.max_factor) { bailed = true; result = -1; break; }
+                // (the second-round linked DP, variant 4, has no bail-out)
+                if (VARIANT != 4 && ((double)opcount / (double)i) > (double)A.max_factor) { bailed = true; result = -1; break; }
             } else {
                 if (opcount > 100000 && ((double)opcount / (double)prekey) > 1000.0) { bailed = true; result = -2; break; }
             }
@@ -419,6 +423,7 @@ int vm_launch_chain_exact(int variant, const VmChainArgs &args, const int *read_
     case 0: return vm_launch_exact_v<0>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     case 1: return vm_launch_exact_v<1>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     case 3: return vm_launch_exact_v<3>(args, read_ids_dev, n_ids, cap, use_smem, stream);
+    case 4: return vm_launch_exact_v<4>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     default: return vm_launch_exact_v<2>(args, read_ids_dev, n_ids, cap, use_smem, stream);
     }
 }
