@@ -106,3 +106,43 @@ def first_round_path(batches, kmersize, skipcost, maxdiff, maxgap=1000, dp=None,
     if len(path) <= 1:
         return []
     return path
+
+
+def collect_second_round_anchors(r_st, r_en, raw, seq, rc_seq, ctg, k=9):
+    """Re-seeding between the rounds (mammap_asm.py:22478-22755): 9-mers of the read positions [r_st, r_en - k) looked
+    up in the reference windows around the first-round anchors `raw` (int64[m,4]; windows as in guide_1 but with a
+    2000-base margin), guide-proximity filter and same-diagonal merge as guide_1, then sorted by read position with
+    numba's argsort, twice (:22754-22755).  Built from the pieces of the per-read oracle (oracle/pipeline.py,
+    orc_reseed.c): the scan itself is the same code path."""
+    import oracle.pipeline as pl
+    raw = np.ascontiguousarray(raw, dtype=np.int64)
+    wins, raw_x = pl.guide_windows(raw, ctg, look_span=2000)
+    rows = oracle.local_reseed_scan(ctg, wins, raw_x, seq, rc_seq, k, int(r_st), int(r_en) - k)
+    if len(rows) == 0:
+        return rows
+    rows = rows[oracle.argsort_i64(rows[:, 0])]
+    return rows[oracle.argsort_i64(rows[:, 0])]
+
+
+def yield_second_mapinfo(raw, seq, rc_seq, ctg, k=9, batch=100000):
+    """Batches of second-round anchors along the first-round path `raw` (ascending, int64[m,4]) --
+    mammap_asm.py:22444-22476: a batch ends at a path anchor whose successor starts further right, once it reaches
+    `batch` bases past the batch start and holds more than 300 path anchors; every batch is re-seeded with 20 path
+    anchors of context on both sides."""
+    raw = np.ascontiguousarray(raw, dtype=np.int64)
+    n = len(raw)
+    st_read = st_path = iloc_path = 0
+    for now in raw[1:]:
+        iloc_path += 1
+        if iloc_path == n - 1 or (iloc_path < n - 1 and raw[iloc_path + 1][0] > raw[iloc_path][0]):
+            if now[0] + now[3] > st_read + batch and iloc_path - st_path > 300:
+                en_read = int(raw[iloc_path][0])
+                rows = collect_second_round_anchors(st_read, en_read, raw[max(0, st_path - 20):min(iloc_path + 20, n)], seq, rc_seq, ctg, k)
+                if len(rows) > 0:
+                    yield rows
+                st_path = iloc_path + 1
+                st_read = en_read
+    if st_read < len(seq):
+        rows = collect_second_round_anchors(st_read, len(seq), raw[max(0, st_path - 20):min(iloc_path + 20, n)], seq, rc_seq, ctg, k)
+        if len(rows) > 0:
+            yield rows

@@ -226,6 +226,48 @@ def gen_asm_linked():
     print("asm_linked.npz:", os.path.getsize(os.path.join(HERE, "asm_linked.npz")), "bytes")
 
 
+def asm_reseed_inputs():
+    """Seeded inputs of the asm re-seeding fixture (shared with tests/test_oracle_asm.py): a 2-contig reference and
+    one 60 kb 'contig read' with an inversion and a deletion, 1 % divergence."""
+    ref = synth.make_reference(77, 240000, n_contigs=2)
+    rng = np.random.default_rng(78)
+    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[20000:82000].copy()
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    parts = [src[:20000], comp[src[20000:26000]][::-1], src[26000:40000], src[43000:]]      # INV 6 kb, DEL 3 kb
+    read = synth.mutate(rng, np.concatenate(parts), 0.01)
+    return ref, read.tobytes().decode()
+
+
+def gen_asm_reseed():
+    """asm mode: the reference's yield_second_mapinfo / collect_second_round_anchors (mammap_asm.py:22444-22755) on a
+    first-round path computed by the oracle -> tests/golden/asm_reseed.npz."""
+    import oracle
+    import oracle.asm as oasm
+    import oracle.pipeline as pl
+    import refrun
+    ref, read = asm_reseed_inputs()
+    R = refrun.ReferenceRunner(ref, mode="asm")
+    ox = oracle.Index(ref)
+    a = np.array(ox.map(read, -1, -1), dtype=np.int64)
+    a = a[oracle.argsort_i64(a[:, 0])]
+    path = oasm.first_round_path([a], 15, 40., 50, 1000)
+    raw = np.array(path[::-1], dtype=np.int64)
+    from vacmap_b200.sam import reverse_complement
+    rc = reverse_complement(read)
+    out = {"raw": raw}
+    for bi, batch in enumerate((8000, 20000, 100000)):
+        got = [np.asarray(x) for x in R.mod.yield_second_mapinfo(raw, read, rc, R.contig2start, R.contig2seq, 9, batch)]
+        out["n_%d" % bi] = np.array(len(got))
+        out["batch_%d" % bi] = np.array(batch)
+        for ci, x in enumerate(got):
+            out["b%d_%d" % (bi, ci)] = x.astype(np.int64)
+        print("batch", batch, "->", [len(x) for x in got])
+    np.savez_compressed(os.path.join(HERE, "asm_reseed.npz"), **out)
+    print("asm_reseed.npz:", os.path.getsize(os.path.join(HERE, "asm_reseed.npz")), "bytes")
+
+
 def gen_e2e():
     """End-to-end records from the reference's own get_readmap_DP_test / get_bam_dict_str run over the
     oracle's vacmap_index / edlib shim.  Inputs are regenerated from seeds (tests/synth.py) except the
@@ -286,6 +328,8 @@ if __name__ == "__main__":
         gen_e2e()
     if "asm" in what:
         gen_asm_linked()
+    if "asmseed" in what:
+        gen_asm_reseed()
 
 
 def gen_sam_comments():

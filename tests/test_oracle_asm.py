@@ -88,3 +88,44 @@ def test_second_round_linked_dp_matches_reference():
             assert (np.diff(want[:, 0]) >= 0).all() and (want[:-1, 0] + want[:-1, 3] <= want[1:, 0]).all()
         n_calls += len(seen)
     assert n_calls >= 10
+
+
+def test_second_round_reseeding_matches_reference():
+    """`yield_second_mapinfo` / `collect_second_round_anchors` (mammap_asm.py:22444-22755) restated over the per-read
+    oracle's window / scan pieces == the reference's own functions on a 60 kb contig read with an inversion and a
+    deletion (tests/golden/asm_reseed.npz), for three batch sizes: same batches, same anchors, same order."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import oracle.pipeline as pl
+    from vacmap_b200.sam import reverse_complement
+    import synth
+    R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_reseed.npz"))
+    # the generator's seeded inputs (tests/golden/make_golden.py::asm_reseed_inputs), rebuilt here without the reference
+    ref = synth.make_reference(77, 240000, n_contigs=2)
+    rng = np.random.default_rng(78)
+    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[20000:82000].copy()
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    parts = [src[:20000], comp[src[20000:26000]][::-1], src[26000:40000], src[43000:]]
+    read = synth.mutate(rng, np.concatenate(parts), 0.01).tobytes().decode()
+    # the first-round path the fixture was made from is itself reproduced by the oracle
+    ox = oracle.Index(ref)
+    a = np.array(ox.map(read, -1, -1), dtype=np.int64)
+    a = a[oracle.argsort_i64(a[:, 0])]
+    raw = np.array(oasm.first_round_path([a], 15, 40., 50, 1000)[::-1], dtype=np.int64)
+    assert np.array_equal(raw, R["raw"])
+    ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+    rc = reverse_complement(read)
+    n_anchor = 0
+    for bi in range(3):
+        got = list(oasm.yield_second_mapinfo(raw, read, rc, ctg, 9, int(R["batch_%d" % bi])))
+        assert len(got) == int(R["n_%d" % bi]), bi
+        for ci, x in enumerate(got):
+            assert np.array_equal(x, R["b%d_%d" % (bi, ci)]), (bi, ci)
+            n_anchor += len(x)
+    assert n_anchor > 10000
+    # and the second-round chain over those batches covers the read on both strands (the inversion)
+    path = oasm.second_round_path(got, 9, 30., 30, 99)
+    strands = {p[2] for p in path}
+    assert strands == {1, -1} and path[0][0] < 200 and path[-1][0] > len(read) - 300
