@@ -268,6 +268,50 @@ def gen_asm_reseed():
     print("asm_reseed.npz:", os.path.getsize(os.path.join(HERE, "asm_reseed.npz")), "bytes")
 
 
+def asm_e2e_inputs():
+    """Seeded inputs of the asm end-to-end fixture: a 1.3 Mb 2-contig reference and one 520 kb contig read cut from it
+    with a 4 kb inversion, a 2.5 kb deletion, a 1.2 kb insertion and 0.5 % divergence."""
+    ref = synth.make_reference(91, 1300000, n_contigs=2)
+    rng = np.random.default_rng(92)
+    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[40000:563700].copy()
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    parts = [src[:150000], comp[src[150000:154000]][::-1], src[154000:300000], src[302500:420000],
+             synth.random_seq(rng, 1200), src[420000:]]
+    read = synth.mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1))
+    return ref, read.tobytes().decode()
+
+
+def gen_asm_e2e():
+    """asm mode end to end: the reference's assembly_get_readmap_DP_test (mammap_asm.py:23204) over the oracle
+    natives on a 520 kb contig read -> tests/golden/asm_e2e.json.gz (onemapinfolist rows)."""
+    import gzip
+    import json
+    import tempfile
+    import time
+    import refrun
+    from vacmap_b200.sam import reverse_complement
+    ref, read = asm_e2e_inputs()
+    assert len(read) >= 500000
+    out = {"cases": []}
+    for eqx in (False, True):
+        R = refrun.ReferenceRunner(ref, mode="asm", eqx=eqx)
+        wd = tempfile.mkdtemp() + "/w/"
+        t0 = time.time()
+        recs = R.mod.assembly_get_readmap_DP_test(wd, "ctgread", read, reverse_complement(read), len(read), R.aligner,
+                                                  R.mod.pos2contig, R.contig2start, R.contig2seq, R.index2contig, R.option)
+        recs = [list(r) for r in recs]
+        for r in recs:
+            for i in (3, 4, 5, 6, 7):
+                r[i] = int(r[i])
+        print("eqx", eqx, len(recs), "records", [(r[2], r[3], r[4], r[5], r[6]) for r in recs], round(time.time() - t0, 1), "s")
+        out["cases"].append({"eqx": eqx, "records": recs})
+    with gzip.open(os.path.join(HERE, "asm_e2e.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("asm_e2e.json.gz:", os.path.getsize(os.path.join(HERE, "asm_e2e.json.gz")), "bytes")
+
+
 def gen_e2e():
     """End-to-end records from the reference's own get_readmap_DP_test / get_bam_dict_str run over the
     oracle's vacmap_index / edlib shim.  Inputs are regenerated from seeds (tests/synth.py) except the
@@ -330,6 +374,8 @@ if __name__ == "__main__":
         gen_asm_linked()
     if "asmseed" in what:
         gen_asm_reseed()
+    if "asme2e" in what:
+        gen_asm_e2e()
 
 
 def gen_sam_comments():

@@ -129,3 +129,32 @@ def test_second_round_reseeding_matches_reference():
     path = oasm.second_round_path(got, 9, 30., 30, 99)
     strands = {p[2] for p in path}
     assert strands == {1, -1} and path[0][0] < 200 and path[-1][0] > len(read) - 300
+
+
+def test_asm_end_to_end_matches_reference():
+    """`oracle.asm.assembly_align` (both rounds, re-seeding, asm's own rebuild / inversion fix / split + link_cigar,
+    record assembly) == the reference's assembly_get_readmap_DP_test on a 520 kb contig read with an inversion, a
+    deletion and an insertion (tests/golden/asm_e2e.json.gz): same rows, same CIGARs, with and without --eqx."""
+    import gzip
+    import json
+    import oracle.pipeline as pl
+    import synth
+    import test_oracle_e2e  # noqa: F401  (default options live next to the per-read fixtures)
+    E = json.load(gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_e2e.json.gz"), "rt"))
+    ref = synth.make_reference(91, 1300000, n_contigs=2)
+    rng = np.random.default_rng(92)
+    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[40000:563700].copy()
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    parts = [src[:150000], comp[src[150000:154000]][::-1], src[154000:300000], src[302500:420000],
+             synth.random_seq(rng, 1200), src[420000:]]
+    read = synth.mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1)).tobytes().decode()
+    ox = oracle.Index(ref)
+    ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+    for case in E["cases"]:
+        opt = {"eqx": case["eqx"], "H": False, "golbal_skipcost": 30., "golbal_maxdiff": 50, "local_skipcost": 30.,
+               "local_maxdiff": 30, "local_kmersize": 9}
+        got = oasm.assembly_align("ctgread", read, ox, ctg, opt)
+        assert [list(r) for r in got] == case["records"], case["eqx"]
+    assert len(E["cases"][0]["records"]) == 3
