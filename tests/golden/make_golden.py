@@ -312,6 +312,29 @@ def gen_asm_e2e():
     print("asm_e2e.json.gz:", os.path.getsize(os.path.join(HERE, "asm_e2e.json.gz")), "bytes")
 
 
+def gen_asm_link():
+    """link_cigar (mammap_asm.py:22366-22410, njit) on random CIGAR pairs -> tests/golden/asm_link_cigar.json."""
+    import json
+    m = refimport.load_mode("asm")
+    rng = np.random.default_rng(5)
+
+    def rnd():
+        n = int(rng.integers(1, 5))
+        ops, last = [], ""
+        for _ in range(n):
+            op = str(rng.choice([c for c in "=XIDM" if c != last]))
+            last = op
+            ops.append(str(int(rng.choice([1, 7, 10, 99, 100, 1234, 20000]))) + op)
+        return "".join(ops)
+    rows = []
+    for _ in range(300):
+        a, b = rnd(), rnd()
+        rows.append([a, b, str(m.link_cigar(a, b))])
+    with open(os.path.join(HERE, "asm_link_cigar.json"), "w") as f:
+        json.dump(rows, f)
+    print("asm_link_cigar.json", len(rows), "pairs,", sum(1 for r in rows if r[2] != r[0] + r[1]), "merged")
+
+
 def gen_e2e():
     """End-to-end records from the reference's own get_readmap_DP_test / get_bam_dict_str run over the
     oracle's vacmap_index / edlib shim.  Inputs are regenerated from seeds (tests/synth.py) except the
@@ -376,6 +399,8 @@ if __name__ == "__main__":
         gen_asm_reseed()
     if "asme2e" in what:
         gen_asm_e2e()
+    if "asmlink" in what:
+        gen_asm_link()
 
 
 def gen_sam_comments():

@@ -158,3 +158,11 @@ def test_asm_end_to_end_matches_reference():
         got = oasm.assembly_align("ctgread", read, ox, ctg, opt)
         assert [list(r) for r in got] == case["records"], case["eqx"]
     assert len(E["cases"][0]["records"]) == 3
+
+
+def test_link_cigar_matches_reference():
+    import json
+    rows = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_link_cigar.json")))
+    assert len(rows) == 300 and any(r[2] != r[0] + r[1] for r in rows)
+    for a, b, want in rows:
+        assert oasm.link_cigar(a, b) == want, (a, b)
