@@ -23,9 +23,12 @@ def _carry(S, P, S_arg, linked, skipcost):
     at = len(S) - 1
     if at <= 0:
         raise Exception("ERROR: ")
-    # first position (from the top) whose score is not above `lowest`; S[S_arg] ascends, so a binary search finds it
+    # the reference walks down from the top while the score is above `lowest` (and never tests position 0): the last
+    # position whose score is not above it.  No binary search: after a bail-out S_arg is the heuristic DP's order
+    # (integer score, then diagonal), which is not monotone in S inside an integer bucket.
     order = S[S_arg]
-    at = max(int(np.searchsorted(order, lowest, side="right")) - 1, 0)
+    below = np.flatnonzero(order <= lowest)
+    at = int(below[-1]) if len(below) else 0
     sel = S_arg[at:]
     return S[sel] - order[at] + 1000, (-P[sel]).astype(np.int32), linked[sel]
 
