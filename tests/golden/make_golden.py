@@ -269,18 +269,7 @@ def gen_asm_reseed():
 
 
 def asm_e2e_inputs():
-    """Seeded inputs of the asm end-to-end fixture: a 1.3 Mb 2-contig reference and one 520 kb contig read cut from it
-    with a 4 kb inversion, a 2.5 kb deletion, a 1.2 kb insertion and 0.5 % divergence."""
-    ref = synth.make_reference(91, 1300000, n_contigs=2)
-    rng = np.random.default_rng(92)
-    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[40000:563700].copy()
-    comp = np.zeros(256, np.uint8)
-    for x, y in zip(b"ACGT", b"TGCA"):
-        comp[x] = y
-    parts = [src[:150000], comp[src[150000:154000]][::-1], src[154000:300000], src[302500:420000],
-             synth.random_seq(rng, 1200), src[420000:]]
-    read = synth.mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1))
-    return ref, read.tobytes().decode()
+    return synth.asm_e2e_inputs()
 
 
 def gen_asm_e2e():
@@ -333,6 +322,55 @@ def gen_asm_link():
     with open(os.path.join(HERE, "asm_link_cigar.json"), "w") as f:
         json.dump(rows, f)
     print("asm_link_cigar.json", len(rows), "pairs,", sum(1 for r in rows if r[2] != r[0] + r[1]), "merged")
+
+
+def squash_sam_line(line):
+    """SEQ / QUAL of a 520 kb contig read do not belong in a fixture: replaced by length + sha1."""
+    import hashlib
+    f = line.split("\t")
+    for i in (9, 10):
+        if len(f[i]) > 64:
+            f[i] = "%d:%s" % (len(f[i]), hashlib.sha1(f[i].encode()).hexdigest())
+    return "\t".join(f)
+
+
+def gen_asm_sam():
+    """asm mode's SAM emitter iterator_get_bam_dict_str (mammap_asm.py:22757-22941) on the records of asm_e2e.json.gz
+    (plus a MAPQ 1 / 0 variant for the primary rule) -> tests/golden/asm_sam.json.gz."""
+    import gzip
+    import json
+    import refrun
+    E = json.load(gzip.open(os.path.join(HERE, "asm_e2e.json.gz"), "rt"))
+    ref, read = asm_e2e_inputs()
+    R = refrun.ReferenceRunner(ref, mode="asm")
+    qual = "".join(chr(33 + (i * 11) % 41) for i in range(len(read)))
+    out = []
+    variants = [
+        dict(eqx=False, md=False, H=False, fakecigar=False, mapq=None, qual=False),
+        dict(eqx=True, md=True, H=False, fakecigar=False, mapq=None, qual=True),
+        dict(eqx=True, md=True, H=True, fakecigar=True, mapq=None, qual=True, shortcs=False),
+        dict(eqx=False, md=False, H=True, fakecigar=False, mapq=[1, 60, 0], qual=False),
+    ]
+    for v in variants:
+        recs = [list(r) for r in [c for c in E["cases"] if c["eqx"] == v["eqx"]][0]["records"]]
+        if v["mapq"]:
+            # longest record MAPQ 1 -> the second longest becomes primary; a MAPQ 0 record is written as 1
+            order = sorted(range(len(recs)), key=lambda i: recs[i][4] - recs[i][3])[::-1]
+            for rank, i in enumerate(order):
+                recs[i][7] = v["mapq"][rank]
+        if v["H"]:
+            # the rows were assembled with soft clips: re-clip for the hard-clip variant
+            for r in recs:
+                r[8] = r[8].replace("S", "H")
+        opt = dict(R.option)
+        opt.update({"H": v["H"], "fakecigar": v["fakecigar"]})
+        lines = list(R.mod.iterator_get_bam_dict_str([tuple(r) for r in recs], read.upper(), qual if v["qual"] else None,
+                                                     R.contig2iloc, R.contig2seq, v["md"], v.get("shortcs", True), False, False, opt))
+        out.append({"variant": v, "records": recs, "sam": [squash_sam_line(x) for x in lines]})
+        print(v, len(lines), "lines", [x.split("\t")[1] + ":" + x.split("\t")[4] for x in lines])
+    with gzip.open(os.path.join(HERE, "asm_sam.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("asm_sam.json.gz:", os.path.getsize(os.path.join(HERE, "asm_sam.json.gz")), "bytes")
 
 
 def gen_e2e():
@@ -401,6 +439,8 @@ if __name__ == "__main__":
         gen_asm_e2e()
     if "asmlink" in what:
         gen_asm_link()
+    if "asmsam" in what:
+        gen_asm_sam()
 
 
 def gen_sam_comments():

@@ -166,3 +166,19 @@ def make_reads(contigs, seed, n_reads, read_len=15000, err=0.10, ratio=(4, 3, 3)
         seg = mutate(rng, seg, err, ratio)
         reads.append(("read_%d" % i, seg.tobytes().decode()))
     return reads
+
+
+def asm_e2e_inputs():
+    """The asm end-to-end fixture's inputs (tests/golden/make_golden.py::asm_e2e_inputs, same seeds): a 1.3 Mb 2-contig
+    reference and one 520 kb contig read cut from it with a 4 kb inversion, a 2.5 kb deletion, a 1.2 kb insertion and
+    0.5 % divergence."""
+    ref = make_reference(91, 1300000, n_contigs=2)
+    rng = np.random.default_rng(92)
+    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[40000:563700].copy()
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGT", b"TGCA"):
+        comp[x] = y
+    parts = [src[:150000], comp[src[150000:154000]][::-1], src[154000:300000], src[302500:420000],
+             random_seq(rng, 1200), src[420000:]]
+    read = mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1))
+    return ref, read.tobytes().decode()

@@ -141,15 +141,7 @@ def test_asm_end_to_end_matches_reference():
     import synth
     import test_oracle_e2e  # noqa: F401  (default options live next to the per-read fixtures)
     E = json.load(gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_e2e.json.gz"), "rt"))
-    ref = synth.make_reference(91, 1300000, n_contigs=2)
-    rng = np.random.default_rng(92)
-    src = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)[40000:563700].copy()
-    comp = np.zeros(256, np.uint8)
-    for x, y in zip(b"ACGT", b"TGCA"):
-        comp[x] = y
-    parts = [src[:150000], comp[src[150000:154000]][::-1], src[154000:300000], src[302500:420000],
-             synth.random_seq(rng, 1200), src[420000:]]
-    read = synth.mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1)).tobytes().decode()
+    ref, read = synth.asm_e2e_inputs()
     ox = oracle.Index(ref)
     ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
     for case in E["cases"]:

@@ -208,8 +208,28 @@ def _fake_cigar(item, qlen, clipsyb):
     return top + body + tail
 
 
+def mergecigar_nm_(cigarstring):
+    """asm mode (mammap_asm.py:23126-23155): mergecigar_ plus NM = the X / D / I lengths -- counted only where a run
+    STARTS (the length merged into a preceding run of the same op is not added; quirk kept)."""
+    oplist, edit = [], 0
+    preop, prenum = "0", 0
+    for num, op in _CIGAR_RE.findall(cigarstring):
+        n = int(num)
+        if op == preop:
+            prenum += n
+            oplist[-2] = str(prenum)
+        else:
+            prenum = n
+            oplist.append(str(n))
+            oplist.append(op)
+            if op in "XDI":
+                edit += n
+            preop = op
+    return oplist, edit
+
+
 def get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option,
-                     comments=None, with_comments=False):
+                     comments=None, with_comments=False, asm=False):
     """:20841-21021 -- SAM lines of one read's ``onemapinfolist`` rows
     ``(readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar)``; longest query span first = primary
     (stable sort then reverse: among equal spans the later row wins, quirk A12)."""
@@ -228,17 +248,17 @@ def get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs,
         oriented = query if item[2] == "+" else rc_query
         target = contig2seq[item[1]][item[5]:item[6]]
         if not md:
-            oplist = mergecigar_(item[-1])
+            oplist, edit = mergecigar_nm_(item[-1]) if asm else (mergecigar_(item[-1]), None)
             item[-1] = "".join(oplist)
-            nms.append(nm_from_cigar(item[8], oriented, target))
+            nms.append(edit if asm else nm_from_cigar(item[8], oriented, target))
             mds.append(None)
             css.append(None)
         else:
             tmp_query = oriented[item[3]:item[4]]
-            oplist = mergecigar_(item[-1])
+            oplist, edit = mergecigar_nm_(item[-1]) if asm else (mergecigar_(item[-1]), None)
             mdstring, csstring = md_cs(oplist, target, tmp_query, shortcs)
             item[-1] = "".join(oplist)
-            nms.append(nm_from_cigar(item[-1], tmp_query, target))
+            nms.append(edit if asm else nm_from_cigar(item[-1], tmp_query, target))
             mds.append(mdstring)
             css.append(csstring)
         n_cigars.append(len(oplist))
@@ -246,13 +266,17 @@ def get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs,
     have_qual = qual is not None and len(qual) == len(query)
     rc_qual = qual[::-1] if have_qual else None
     out = []
+    # asm mode (:22838-22841, :22873-22887): the second-longest record is primary when the longest has MAPQ 1 and it
+    # has not; MAPQ is written as 60 (anything non-zero) or 1
+    primary_iloc = 1 if (asm and len(mapinfo) > 1 and mapinfo[0][7] == 1 and mapinfo[1][7] != 1) else 0
+    mq_of = (lambda v: 60 if v != 0 else 1) if asm else (lambda v: v)
     for iloc, primary in enumerate(mapinfo):
         d = {}
         if "rg-id" in option:
             d["RG"] = option["rg-id"]
         d["QNAME"] = primary[0]
         d["RNAME"] = primary[1]
-        base_value = 0 if iloc == 0 else 2048
+        base_value = 0 if iloc == primary_iloc else 2048
         d["FLAG"] = str(base_value if primary[2] == "+" else 16 + base_value)
         d["POS"] = str(primary[5] + 1)
         if n_cigars[iloc] > 65535 and cigar2cg:
@@ -265,9 +289,9 @@ def get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs,
                 if t == iloc:
                     continue
                 sa.append("".join((item[1], ",", str(item[5] + 1), ",", item[2], ",", fakes[t] if fakecigar else item[8], ",",
-                                   str(item[7]), ",", str(nms[t]) + ";")))
+                                   str(mq_of(item[7])), ",", str(nms[t]) + ";")))
             d["SA"] = "".join(sa)
-        d["MAPQ"] = str(primary[7])
+        d["MAPQ"] = str(mq_of(primary[7]))
         seq, q = (query, qual) if primary[2] == "+" else (rc_query, rc_qual)
         if not hardclip:
             d["SEQ"] = seq
@@ -290,6 +314,14 @@ def get_bam_dict_str_comments(mapinfo, query, qual, comments, contig2iloc, conti
     """:21022- -- as above, with the FASTQ comment's well-formed SAM tags copied over (``--copycomments``)."""
     return get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option,
                             comments=comments, with_comments=True)
+
+
+def iterator_get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option):
+    """asm mode's emitter (mammap_asm.py:22757-22941): as get_bam_dict_str with NM taken from the CIGAR alone
+    (`mergecigar_n_nm` / `mergecigar_md_cs_nm`), the primary-record rule and the 60 / 1 MAPQ of that mode; a generator
+    like the reference's."""
+    yield from get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md, shortcs, cigar2cg, markunbalancetra, option,
+                                asm=True)
 
 
 def header_text(contigs, rg_id=None):
