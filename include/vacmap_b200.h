@@ -257,7 +257,27 @@ int64_t vm_result_num_cigar_ops(vm_result *r);
 const int64_t *vm_result_read_offsets(vm_result *r);   /* [n_reads+1] into the record array */
 const vm_record *vm_result_records(vm_result *r);
 const uint32_t *vm_result_cigar(vm_result *r);         /* BAM encoding len<<4|op, ops MIDNSHP=X */
-const char *vm_result_stage_times(vm_result *r);       /* "stage=ms;..." wall milliseconds per stage */
+const char *vm_result_stage_times(vm_result *r);       /* "stage=ms;..." wall milliseconds per stage, "n_*" work counts, "c_*" branch counts */
+/* Per-read status [n_reads]: why a read has the records it has.  The reference emits nothing for a read in several
+ * distinguishable situations (SURVEY 8b "error convention"); they are told apart here instead of being merged into
+ * "zero records":
+ *   VM_READ_OK          >= 1 record
+ *   VM_READ_FEW_ANCHORS <= 2 seed anchors (decode_hit, clrnano:23986-23988)
+ *   VM_READ_LOW_SCORE   best global chain not above the mode's threshold (hit2work_1, clrnano:23650, 23711-23734)
+ *   VM_READ_SHORT_LOCAL local chain of <= 1 anchor (clrnano:24067-24068)
+ *   VM_READ_DROPPED     the reference raises inside the read and its worker swallows the exception
+ *                       (clrnano:24116-24125): "Failed to compute CIGAR" (21559-21569), Cigar length check
+ *                       (20779-20786), empty sub-alignment list, division by zero in the divergence filter
+ *   VM_READ_NO_RECORDS  extend_func produced no record (clrnano:24075-24076)
+ *   VM_READ_FAILED      the library could not process the read (beyond a kernel's size limits); no counterpart */
+#define VM_READ_OK 0
+#define VM_READ_FEW_ANCHORS 1
+#define VM_READ_LOW_SCORE 2
+#define VM_READ_SHORT_LOCAL 3
+#define VM_READ_DROPPED 4
+#define VM_READ_NO_RECORDS 5
+#define VM_READ_FAILED 6
+const int32_t *vm_result_read_status(vm_result *r);
 void vm_result_free(vm_result *r);
 
 #ifdef __cplusplus

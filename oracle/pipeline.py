@@ -191,14 +191,21 @@ def hit2work(a, L, kmersize, skipcost, maxdiff, maxgap, accept, bin_size=100, ov
     return path_list, mapq, scores_list, secondary, fast
 
 
-def decode_hit(index, seq, L, kmersize, opt, mode):
+def _bump(stats, key, by=1):
+    if stats is not None:
+        stats[key] = stats.get(key, 0) + by
+
+
+def decode_hit(index, seq, L, kmersize, opt, mode, stats=None):
     """decode_hit :23981-24020 -> (mapq, signed score, return_path_list)"""
     a = index.map(seq, check_num=opt["c"], mid_occ=-1)
     need_reverse, a = reverse_rough(a, L)
     if len(a) <= 2:
         return 0, 0.0, []
-    path_list, mapq, scores_list, secondary, _ = hit2work(
+    path_list, mapq, scores_list, secondary, fast = hit2work(
         a, L, kmersize, opt["golbal_skipcost"], opt["golbal_maxdiff"], 1000, MODE_CONST[mode]["accept"])
+    if fast:
+        _bump(stats, "fast_global")
     if len(path_list) == 0:
         return 0, 0.0, []
     ret = [path_list[0]] + list(secondary)
@@ -449,7 +456,7 @@ def drop_somechains(chains):
     return out
 
 
-def local_stage(path_list, seq, rc_seq, ctg, opt, mode):
+def local_stage(path_list, seq, rc_seq, ctg, opt, mode, stats=None):
     """get_localmap_multi_all_forDP_inv_guide_list :28479-28589 -> (score, path descending)"""
     mc = MODE_CONST[mode]
     chains = [np.array(p, dtype=np.int64) for p in path_list]
@@ -469,6 +476,7 @@ def local_stage(path_list, seq, rc_seq, ctg, opt, mode):
     a = a[oracle.argsort_i64(a[:, 0] + a[:, 3])]
     skip = opt["local_skipcost"]
     if len(chains) > 1:
+        _bump(stats, "mismatch_dp")
         if mc["clamp40"]:
             skip = min(skip, 40)
         sc, path, _, _, _ = oracle.chain_local(a, 9, 2, skip, opt["local_maxdiff"], mc["local_maxgap"], 30)
@@ -875,7 +883,7 @@ def paired_indel(cigars, indelsize=30):
     return False
 
 
-def extend_func(raw, readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, nofilter):
+def extend_func(raw, readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, nofilter, stats=None):
     """extend_func :19238-19303 -> (onemapinfolist, filtered)"""
     al = rebuild_chain_break(ctg, raw, opt["local_maxdiff"])
     i = 0
@@ -896,11 +904,19 @@ def extend_func(raw, readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, nofil
         while iloc < len(al) - 2:
             if not drop_misplaced(al, iloc):
                 iloc += 1
+            else:
+                _bump(stats, "drop_misplaced")
     if len(al) < n0:
         filtered = True
         extend_edge(seq, L, al, ctg)
+    n1 = len(al)
     merge_conjacent(al, ctg)
+    if len(al) != n1:
+        _bump(stats, "merge_conjacent", n1 - len(al))
+    before = [list(x) for x in al]
     fix_simple_inv(al, ctg, seq)
+    if [list(x) for x in al] != before:
+        _bump(stats, "fix_simple_inv")
     new_al, cigarlist = [], []
     for a in al:
         na, cg = split_alignment(a, seq, rc_seq, L, ctg, opt["eqx"])
@@ -909,27 +925,29 @@ def extend_func(raw, readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, nofil
     return onemapinfolist(new_al, cigarlist, readid, mapq, L, ctg, need_reverse, opt["H"]), filtered
 
 
-def align_read(readid, seq, index, ctg, opt, mode="H"):
+def align_read(readid, seq, index, ctg, opt, mode="H", stats=None):
     """get_readmap_DP_test :24023-24084 -> list of 9-tuples (possibly empty)"""
     seq = seq.upper()
     L = len(seq)
     rc_seq = revcomp(seq)
     try:
-        mapq, scores, path_list = decode_hit(index, seq, L, index.k, opt, mode)
+        mapq, scores, path_list = decode_hit(index, seq, L, index.k, opt, mode, stats)
         if scores == 0.0:
             return []
         need_reverse = scores < 0.0
         if need_reverse:
             seq, rc_seq = rc_seq, seq
-        sc, raw = local_stage(path_list, seq, rc_seq, ctg, opt, mode)
+        sc, raw = local_stage(path_list, seq, rc_seq, ctg, opt, mode, stats)
         if len(raw) <= 1:
             return []
         asc = raw[::-1]
-        recs, filtered = extend_func(list(asc), readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, opt["nodiscard"])
+        recs, filtered = extend_func(list(asc), readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, opt["nodiscard"], stats)
         if len(recs) == 0:
             return []
         if (not opt["nodiscard"]) and filtered and paired_indel([r[-1] for r in recs]):
-            recs, filtered = extend_func(list(asc), readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, True)
+            _bump(stats, "second_pass")
+            recs, filtered = extend_func(list(asc), readid, mapq, seq, rc_seq, L, ctg, need_reverse, opt, True, stats)
         return recs
     except (ReadDropped, ZeroDivisionError, IndexError):
+        _bump(stats, "dropped")
         return []

@@ -93,3 +93,31 @@ def test_local_reseeding_matches_oracle(gpu_ctx):
     for (ri, wins, raw, a, b), g, w in zip(jobs, got, want):
         assert g.shape == w.shape and (g == w).all(), (ri, len(wins), len(raw))
     ix.close()
+
+
+def test_local_reseeding_matches_reference_guide_1(gpu_ctx):
+    """Stage golden from the REFERENCE's own get_localmap_multi_all_forDP_inv_guide_1 (clrnano:23069-23345, run in the
+    build container, tests/golden/guide1.npz): vm_local_reseed_batch must hand back the same anchors in the same order
+    for the same guide chains (windows built by the oracle's restatement of :23095-23136, the host glue's job)."""
+    import guide1_cases
+    import vacmap_b200 as vb
+    from vacmap_b200.align import local_reseed_batch
+    by_case = {}
+    for j in guide1_cases.jobs():
+        by_case.setdefault(j["case"], []).append(j)
+    n = 0
+    for name, js in by_case.items():
+        ctg = pl.Contigs([c for c, _ in js[0]["ref"]], [s for _, s in js[0]["ref"]])
+        k, w = (15, 10)
+        ix = vb.Index(js[0]["ref"], w=w, k=k, ctx=gpu_ctx)
+        oriented, jobs = [], []
+        for j in js:
+            wins, raw = pl.guide_windows(j["chain"], ctg)
+            oriented.append(j["seq"])
+            jobs.append((len(oriented) - 1, wins, raw, j["range"][0], j["range"][1]))
+        got = local_reseed_batch(ix, oriented, jobs)
+        for j, g in zip(js, got):
+            assert g.shape == j["out"].shape and (g == j["out"]).all()
+            n += len(g)
+        ix.close()
+    assert n > 10000

@@ -34,3 +34,11 @@ def test_batches_skip_repeated_names_and_cut_by_bases(tmp_path):
     assert [[r[0] for r in b] for b in bs] == [["r1", "r2"], ["r3"]]          # second r1 and second r2 dropped
     assert bs[0][0][1] == "ACGTACGTAC" and bs[1][0][1] == "GGGGGGGG"
     assert [len(r) for b in list(batches([str(p1)], True, 1 << 30)) for r in b] == [4, 4]
+
+
+def test_fastq_record_with_empty_sequence_keeps_the_next_record_intact(tmp_path):
+    """kseq (behind mp.fastx_read, vacmap:445): a trimmed-to-nothing record is a zero-length read; the record
+    after it must come through whole (the header was taken for the quality string)."""
+    p = tmp_path / "e.fastq"
+    p.write_text("@r1\n\n+\n\n@r2\nACGT\n+\nIIII\n@r3\n+\n@r4\nGG\n+\n@>\n")
+    assert list(align.read_fastx(str(p))) == [("r1", "", None), ("r2", "ACGT", "IIII"), ("r3", "", None), ("r4", "GG", "@>")]

@@ -12,6 +12,21 @@ import numpy as np
 from . import align, sam
 
 
+RG_FLAGS = ("ID", "SM", "LB", "PL", "DS", "DT", "PU", "PI", "PG", "CN", "FO", "KS", "PM", "BC")
+
+
+def rg_metadata(args):
+    """collect_rg_metadata (vacmap:62-74) + the default group {"ID": "1", "SM": "sample"} (vacmap:214-218)."""
+    rg = {}
+    for f in RG_FLAGS:
+        v = getattr(args, "rg_" + f.lower(), None)
+        if v is not None:
+            rg[f] = str(v)
+    if rg and "ID" not in rg:
+        sys.exit("The --rg-id option is required when any other --rg-* option is supplied.")
+    return rg or {"ID": "1", "SM": "sample"}
+
+
 def build_parser():
     p = argparse.ArgumentParser(prog="vacmap_b200", description="VACmap per-read alignment path on B200 (CUDA)")
     p.add_argument("-ref", required=True)
@@ -31,7 +46,9 @@ def build_parser():
     for f in ("eqx", "MD", "L", "markunbalancetra", "nodiscard", "copycomments", "H", "fakecigar", "Q"):
         p.add_argument("--" + f, action="store_true")
     p.add_argument("--cs", nargs="?", const="short", default=None)
-    p.add_argument("--rg-id", dest="rg_id", default="1")
+    p.add_argument("--rg-id", dest="rg_id", default=None)
+    for f in RG_FLAGS[1:]:      # the other @RG fields of vacmap:134-150 (need --rg-id, vacmap:72-73)
+        p.add_argument("--rg-" + f.lower(), dest="rg_" + f.lower(), default=None)
     p.add_argument("--batch-bases", type=int, default=150_000_000, help="bases per super-batch")
     p.add_argument("--device", type=int, default=0)
     return p
@@ -41,7 +58,7 @@ def options_from(args):
     """The `pdict` of vacmap:177-296 (mode defaults, `golbal_` spelling and all)."""
     opt = align.default_option(args.mode)
     opt.update({"c": args.c, "eqx": args.eqx, "md": args.MD, "cigar2cg": args.L, "copycomments": args.copycomments, "H": args.H,
-                "fakecigar": args.fakecigar, "Q": args.Q, "rg-id": args.rg_id, "golbal_maxdiff": args.globalmaxdiff,
+                "fakecigar": args.fakecigar, "Q": args.Q, "rg-id": rg_metadata(args)["ID"], "golbal_maxdiff": args.globalmaxdiff,
                 "local_maxdiff": args.localmaxdiff, "shortcs": args.cs != "long"})
     if args.maxdivergence is not None:
         opt["maxdivergence"] = args.maxdivergence
@@ -86,11 +103,13 @@ def main(argv=None):
     ref = [(r[0], r[1].upper()) for r in align.read_fastx(args.ref)]
     index = align.Index(ref, w=args.w, k=args.k, device=args.device)
     al = align.Aligner(index, opt, args.mode, host_threads=args.t)
-    contig2seq = {n: s for n, s in ref}
+    # the reference takes contig2seq from index.seq() (vacmap:363): non-ACGT bases are N there
+    contig2seq = {n: index.seq(n) for n, _ in ref}
     contig2iloc = {n: i for i, (n, _) in enumerate(ref)}
     out = sys.stdout if args.o == "-" else open(args.o, "w")
     try:
-        out.write(sam.header_text([(n, len(s)) for n, s in ref]))
+        out.write(sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
+                                  command_line=" ".join(sys.argv if argv is None else ["vacmap_b200"] + list(argv))))
         pending = None
 
         def collect(p):

@@ -55,28 +55,37 @@ def default_option(mode="H", **over):
 
 
 def read_fastx(path, read_comment=False):
-    """FASTA / FASTQ(.gz) reader with the `vacmap_index.fastx_read` tuple contract (vacmap:445)."""
+    """FASTA / FASTQ(.gz) reader with the `vacmap_index.fastx_read` tuple contract (vacmap:445; kseq behind it):
+    multi-line records, a FASTQ record's quality runs until it is as long as the sequence -- so a record with an
+    EMPTY sequence (common after trimming) is a zero-length read followed by an intact next record."""
     op = gzip.open if str(path).endswith(".gz") else open
     with op(path, "rt") as f:
         name, comment, seq, qual, mode = None, None, [], [], None
+        nseq = nqual = 0
         for line in f:
             line = line.rstrip("\r\n")
+            if mode == "qual":
+                # inside a quality string nothing is a header: '@' and '>' are quality characters
+                qual.append(line)
+                nqual += len(line)
+                if nqual >= nseq:
+                    mode = "fq_done"
+                continue
             if not line:
                 continue
-            if line[0] in ">@" and mode != "qual":
+            if line[0] in ">@":
                 if name is not None:
                     yield _rec(name, comment, seq, qual, read_comment)
                 hdr = line[1:].split(None, 1)
                 name, comment = (hdr[0] if hdr else ""), (hdr[1] if len(hdr) > 1 else None)
                 seq, qual, mode = [], [], ("fa" if line[0] == ">" else "fq")
+                nseq = nqual = 0
             elif line[0] == "+" and mode == "fq":
-                mode = "qual"
-            elif mode == "qual":
-                qual.append(line)
-                if sum(map(len, qual)) >= sum(map(len, seq)):
-                    mode = "fq_done"
-            else:
+                # an empty sequence has an empty quality: the record is complete at once
+                mode = "qual" if nseq > 0 else "fq_done"
+            elif mode in ("fa", "fq"):
                 seq.append(line)
+                nseq += len(line)
         if name is not None:
             yield _rec(name, comment, seq, qual, read_comment)
 
@@ -109,6 +118,8 @@ def _declare(L):
         getattr(L, f).restype = vp
     L.vm_result_stage_times.argtypes = [vp]
     L.vm_result_stage_times.restype = ctypes.c_char_p
+    L.vm_result_read_status.argtypes = [vp]
+    L.vm_result_read_status.restype = vp
     L.vm_result_free.argtypes = [vp]
     L.vm_result_free.restype = None
     L._align_declared = True
@@ -175,6 +186,7 @@ class Aligner:
                                    o["golbal_maxdiff"], o["local_maxdiff"], o["c"], int(o["eqx"]), int(o["H"]),
                                    int(o["nodiscard"]), mc["max_guides"], mc["local_maxgap"], mc["clamp40"], host_threads, workers, chunk_reads)
         self.last_stage_ms = {}
+        self.last_status = np.zeros(0, np.int32)     # per-read VM_READ_* codes of the last collected batch
 
     def upload_reads(self, seq_cat, seq_off):
         """Put a packed batch in HBM ahead of `align_packed(..., resident=True)` (device-resident timing)."""
@@ -214,6 +226,8 @@ class Aligner:
                 recs = raw.view(RECORD_DTYPE).copy()
             else:
                 recs = np.zeros(0, dtype=RECORD_DTYPE)
+            self.last_status = np.ctypeslib.as_array(ctypes.cast(L.vm_result_read_status(res), ctypes.POINTER(ctypes.c_int32)),
+                                                     shape=(n,)).copy() if n else np.zeros(0, np.int32)
             txt = (L.vm_result_stage_times(res) or b"").decode()
             self.last_stage_ms = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in txt.split(";") if "=" in kv}
             if nops:

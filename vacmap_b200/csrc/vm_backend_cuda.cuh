@@ -265,7 +265,8 @@ public:
         vm_chain_params prm{kmersize, skipcost, maxdiff, maxgap, 1000, 5, 30, 0};
         if (vm_chain_prepare(c_, n, span, out.start, out.cnt, false) != VM_OK) throw std::runtime_error("chain: " + c_->err);
         float ms4[4] = {0, 0, 0, 0};
-        if (vm_chain_core(c_, prm, seed_.out.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, nullptr, ms4) != VM_OK)
+        out.used_fast.assign((size_t)n, 0);
+        if (vm_chain_core(c_, prm, seed_.out.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, &out.used_fast, ms4) != VM_OK)
             throw std::runtime_error("chain: " + c_->err);
         timer.add("chain_global_kernels", ms4[1] + ms4[2] + ms4[3]);
         // chains extracted on the device: only what hit2work_1 keeps goes to the host
@@ -599,10 +600,11 @@ public:
             rl[r] = (int32_t)std::min<int64_t>(b.len(r) + 64, INT32_MAX - 128);
             if (variant[r] != 0 && out.cnt[r] > 0) groups[{variant[r], skipcost[r]}].push_back((int)r);
         }
+        out.used_fast.assign((size_t)n, 0);
         for (auto &g : groups) {
             vm_chain_params prm{9, g.first.second, maxdiff, maxgap, 1000, 5, 30, g.first.first};
             float ms4[4] = {0, 0, 0, 0};
-            if (vm_chain_core(c_, prm, d_dense_.as<VmAnchor>(), out.start, out.cnt, rl, rl, g.second, nullptr, nullptr, ms4) != VM_OK)
+            if (vm_chain_core(c_, prm, d_dense_.as<VmAnchor>(), out.start, out.cnt, rl, rl, g.second, nullptr, &out.used_fast, ms4) != VM_OK)
                 throw std::runtime_error("chain: " + c_->err);
             timer.add("chain_local_kernels", ms4[1] + ms4[2] + ms4[3]);
         }

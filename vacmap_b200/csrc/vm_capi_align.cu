@@ -8,6 +8,7 @@ struct vm_result {
     std::vector<int64_t> rec_off;        // per read
     std::vector<vm_record> recs;
     std::vector<uint32_t> cigar;
+    std::vector<int32_t> status;         // per read (ReadStatus)
     std::vector<double> stage_ms;
     std::vector<std::string> stage_names;
     std::string stage_text;
@@ -162,7 +163,11 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
         BatchResult sr;
         try {
             drv.align_batch(sb, sr);
-            for (int64_t i = 0; i < nr; ++i) job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+            for (int64_t i = 0; i < nr; ++i) {
+                job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
+                job->br.status[(size_t)(r0 + i)] = sr.status[(size_t)i];
+            }
+            for (int k = 0; k < BC_COUNT; ++k) wb.timer.add(kBranchName[k], (double)sr.branch[k]);
         } catch (const std::exception &e) {
             // Something in this chunk could not be processed (e.g. a read beyond a kernel's size limits).  The reference
             // loses only the offending read (`except Exception: continue`, clrnano:24116-24125): redo the chunk one
@@ -179,8 +184,11 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
                     BatchResult s1;
                     drv.align_batch(one, s1);
                     job->br.records[(size_t)(r0 + i)].swap(s1.records[0]);
+                    job->br.status[(size_t)(r0 + i)] = s1.status[0];
+                    for (int k = 0; k < BC_COUNT; ++k) wb.timer.add(kBranchName[k], (double)s1.branch[k]);
                 } catch (const std::exception &) {
                     if (cudaGetLastError() != cudaSuccess) throw;
+                    job->br.status[(size_t)(r0 + i)] = RS_FAILED;
                     ++dropped;
                 }
             }
@@ -307,6 +315,7 @@ int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int
         job->workers = workers;
         job->chunks_left = (int64_t)job->bounds.size() - 1;
         job->br.records.assign((size_t)n_reads, {});
+        job->br.status.assign((size_t)n_reads, RS_OK);
         job->t0 = std::chrono::steady_clock::now();
         if (workers <= 1) {
             // lock-step: the whole batch on the context's own backend, in the calling thread
@@ -359,6 +368,7 @@ int vm_align_wait(vm_job *job, vm_result **out)
     }
     res->recs.resize((size_t)res->rec_off[n_reads]);
     res->cigar.resize((size_t)cig_off[n_reads]);
+    res->status.swap(br.status);
     parallel_for(n_reads, job->threads, [&](int64_t r) {
         int64_t ri = res->rec_off[r], co = cig_off[r];
         for (const vmg::Record &rec : br.records[r]) {
@@ -664,6 +674,7 @@ const int64_t *vm_result_read_offsets(vm_result *r) { return r ? r->rec_off.data
 const vm_record *vm_result_records(vm_result *r) { return r ? r->recs.data() : nullptr; }
 const uint32_t *vm_result_cigar(vm_result *r) { return r ? r->cigar.data() : nullptr; }
 const char *vm_result_stage_times(vm_result *r) { return r ? r->stage_text.c_str() : ""; }
+const int32_t *vm_result_read_status(vm_result *r) { return r ? r->status.data() : nullptr; }
 void vm_result_free(vm_result *r) { delete r; }
 
 } // extern "C"

@@ -903,9 +903,11 @@ static void merge_conjacent(AlnList &al, const Contigs &ctg)
 }
 
 // fix_simple_inv :24226-24312.  `read` = oriented read (upper-case), ctg.seq = reference.
-static void fix_simple_inv(AlnList &al, const Contigs &ctg, const char *read, int64_t L)
+// Returns whether a breakpoint was re-cut.
+static bool fix_simple_inv(AlnList &al, const Contigs &ctg, const char *read, int64_t L)
 {
-    if (al.size() <= 2) return;
+    if (al.size() <= 2) return false;
+    bool changed = false;
     size_t iloc = 0;
     while (iloc + 2 < al.size()) {
         Path &A = al[iloc], &B = al[iloc + 1], &C = al[iloc + 2];
@@ -933,6 +935,7 @@ static void fix_simple_inv(AlnList &al, const Contigs &ctg, const char *read, in
                             if (cc != read[qlo + t]) same = false;
                         }
                         if (same) {
+                            changed = true;
                             const int64_t bias = refen_0 - refst_1;
                             C[0] = Anc{readst_2 - bias, refst_2 - bias + bias0, 1, 0};
                             const Anc ins{readst_2 - bias, refen_0 + bias0, -1, 0};
@@ -951,6 +954,7 @@ static void fix_simple_inv(AlnList &al, const Contigs &ctg, const char *read, in
                         for (int64_t t = 0; same && t < rhi - rlo; ++t)
                             if (ctg.seq[rlo + t] != read[qlo + t]) same = false;
                         if (same) {
+                            changed = true;
                             A.back() = Anc{readen_0 - refen_0 + refst_1, refst_1 + bias0, 1, 0};
                             const Anc ins{readen_0 - refen_0 + refst_1, refen_1 + refen_0 - refst_1 + bias0, -1, 0};
                             for (;;) {
@@ -966,6 +970,7 @@ static void fix_simple_inv(AlnList &al, const Contigs &ctg, const char *read, in
         }
         ++iloc;
     }
+    return changed;
 }
 
 struct FillJob {     // one global dual-affine fill (k_cigar 2,-4,4,2,24,1 bw -1 zdrop -1)

@@ -52,6 +52,7 @@ struct ChainOut {
     std::vector<int64_t> start;
     std::vector<int32_t> cnt;
     std::vector<int64_t> gmax;      // g_max_index per read (-1: not chained)
+    std::vector<int32_t> used_fast; // per read, 1 when a heuristic _fast DP produced the result (empty: not reported)
     const Anc32 *sorted = nullptr;  // anchors after the argsort
     const double *S = nullptr;      // global stage only
     const int32_t *P = nullptr;
@@ -133,6 +134,7 @@ struct SubScope {
 
 struct ReadState {
     bool alive = false;
+    bool dropped = false;           // the reference raises on this read (ReadDropped)
     bool need_reverse = false;
     int mapq = 0;
     std::vector<Path> guides;
@@ -149,8 +151,28 @@ struct ReadState {
     std::vector<vmg::Record> recs;
 };
 
+// Why a read has the records it has (vm_result_read_status): the reference's "emit nothing" cases, told apart.
+enum ReadStatus {
+    RS_OK = 0,            // >= 1 record
+    RS_FEW_ANCHORS = 1,   // <= 2 seed anchors after the cluster filter (decode_hit :23986-23988)
+    RS_LOW_SCORE = 2,     // best global chain not above the mode's threshold (hit2work_1 :23650, :23711-23734)
+    RS_SHORT_LOCAL = 3,   // local chain of <= 1 anchor (:24067-24068)
+    RS_DROPPED = 4,       // the reference raises inside the read and its worker swallows it (:24116-24125):
+                          // empty rebuild_chain_break, "Failed to compute CIGAR" (:21559-21569), Cigar length check (:20779-20786), ...
+    RS_NO_RECORDS = 5,    // extend_func returned no record (:24075-24076)
+    RS_FAILED = 6         // the library could not process the read (size limits); the reference has no counterpart
+};
+
+// Branches of the reference's per-read driver a batch went through (how often), for the parity tests' coverage claims
+enum BranchCounter { BC_FAST_GLOBAL = 0, BC_MISMATCH_DP, BC_FAST_LOCAL, BC_DROP_MISPLACED, BC_MERGE_CONJACENT, BC_FIX_SIMPLE_INV,
+                     BC_SECOND_PASS, BC_COUNT };
+static const char *const kBranchName[BC_COUNT] = {"c_fast_global", "c_mismatch_dp", "c_fast_local", "c_drop_misplaced",
+                                                  "c_merge_conjacent", "c_fix_simple_inv", "c_second_pass"};
+
 struct BatchResult {
     std::vector<std::vector<vmg::Record>> records;   // per read, in the reference's emission order
+    std::vector<int32_t> status;                     // ReadStatus per read
+    int64_t branch[BC_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 // map the oriented sequences of the per-read driver onto the stored orientations:
@@ -188,6 +210,8 @@ public:
     {
         const int64_t n = b.n;
         res.records.assign((size_t)n, {});
+        res.status.assign((size_t)n, RS_OK);
+        for (auto &x : bc_) x.store(0);
         std::vector<ReadState> st((size_t)n);
         std::vector<int64_t> read_len((size_t)n);
         for (int64_t r = 0; r < n; ++r) read_len[r] = b.len(r);
@@ -202,7 +226,8 @@ public:
         Phase *ph = new Phase(this, "g_hit2work");
         parallel_for(n, threads_, [&](int64_t r) {
             const int64_t m = g.cnt[r];
-            if (m <= 2) return;                       // decode_hit :23986 -- <= 2 anchors: unmapped
+            if (m <= 2) { res.status[r] = RS_FEW_ANCHORS; return; }     // decode_hit :23986 -- <= 2 anchors: unmapped
+            if (!g.used_fast.empty() && g.used_fast[r]) bc_[BC_FAST_GLOBAL].fetch_add(1, std::memory_order_relaxed);
             const int64_t o = g.start[r];
             vmg::GlobalResult gr;
             {
@@ -213,7 +238,7 @@ public:
                                             x.n_chains, read_len[r], gr);
                 } else vmg::hit2work(g.sorted + o, g.S + o, g.P + o, g.S_arg + o, m, g.gmax[r], read_len[r], opt_.mode.accept, gr);
             }
-            if (!gr.ok) return;
+            if (!gr.ok) { res.status[r] = RS_LOW_SCORE; return; }
             ReadState &s = st[r];
             s.alive = true;
             s.need_reverse = need_rev[r] != 0;
@@ -240,6 +265,7 @@ public:
             if (!st[r].alive) continue;
             if (st[r].guides.size() > 1) {
                 variant[r] = 2;
+                bc_[BC_MISMATCH_DP].fetch_add(1, std::memory_order_relaxed);
                 if (opt_.mode.clamp40) skip[r] = std::min(skip[r], 40.0);
             } else variant[r] = 1;
         }
@@ -256,7 +282,8 @@ public:
         parallel_for(n, threads_, [&](int64_t r) {
             ReadState &s = st[r];
             if (!s.alive) return;
-            if (lc.cnt[r] == 0) { s.alive = false; return; }   // np.array([]) indexing raises in the reference
+            if (!lc.used_fast.empty() && lc.used_fast[r]) bc_[BC_FAST_LOCAL].fetch_add(1, std::memory_order_relaxed);
+            if (lc.cnt[r] == 0) { s.alive = false; res.status[r] = RS_DROPPED; return; }   // np.array([]) indexing raises in the reference
             const int64_t o = lc.start[r];
             SubScope sc(sub_, SP_TRACE);
             if (lc.rec) {
@@ -266,6 +293,7 @@ public:
                 vmg::local_traceback(lc.sorted + o, lc.P + o, lc.gmax[r], s.asc);
                 if (s.asc.size() <= 1) s.alive = false;
             }
+            if (!s.alive) res.status[r] = RS_SHORT_LOCAL;
             s.nofilter = opt_.nodiscard;
         });
         delete ph;
@@ -282,6 +310,7 @@ public:
             if (s.alive && !s.recs.empty() && !opt_.nodiscard && s.filtered && vmg::paired_indel(s.recs)) {
                 s.nofilter = true;
                 again.push_back(r);
+                bc_[BC_SECOND_PASS].fetch_add(1, std::memory_order_relaxed);
             }
         }
         if (!again.empty()) extend_pass(b, read_len, st, again);
@@ -292,9 +321,11 @@ public:
             Phase p2(this, "g_finish");
             parallel_for(n, threads_, [&](int64_t r) {
                 if (st[r].alive) res.records[r].swap(st[r].recs);
+                else if (res.status[r] == RS_OK) res.status[r] = st[r].dropped ? RS_DROPPED : RS_NO_RECORDS;
                 st[r] = ReadState();     // the per-read state is torn down by the pool, not serially
             }, 64);
             st.clear();
+            for (int i = 0; i < BC_COUNT; ++i) res.branch[i] = bc_[i].load();
         }
     }
 
@@ -371,7 +402,7 @@ private:
                     j.band = divergence_band(std::min(j.a.len(), j.b.len()));
                     edj[t].push_back(j);
                 }
-            } catch (const vmg::ReadDropped &) { s.alive = false; edj[t].clear(); segj[t].clear(); }
+            } catch (const vmg::ReadDropped &) { s.alive = false; s.dropped = true; edj[t].clear(); segj[t].clear(); }
         });
         std::vector<EdJob> ed;
         std::vector<int64_t> ed_start, seg_start((size_t)m + 1, 0);
@@ -408,8 +439,10 @@ private:
             s.n0 = s.al.size();
             if (s.al.size() > 2 && !s.nofilter) {
                 size_t iloc = 0;
-                while (iloc + 2 < s.al.size())
+                while (iloc + 2 < s.al.size()) {
                     if (!vmg::drop_misplaced(s.al, iloc)) ++iloc;
+                    else bc_[BC_DROP_MISPLACED].fetch_add(1, std::memory_order_relaxed);
+                }
             }
             if (s.al.size() < s.n0) { s.filtered = true; changed.push_back(ids[t]); }
         }
@@ -425,12 +458,14 @@ private:
             try {
                 {
                     SubScope sc(sub_, SP_MERGE);
+                    const size_t before = s.al.size();
                     vmg::merge_conjacent(s.al, ctg_);
+                    if (s.al.size() != before) bc_[BC_MERGE_CONJACENT].fetch_add((int64_t)(before - s.al.size()), std::memory_order_relaxed);
                 }
                 if (s.al.size() > 2) {
                     SubScope sc(sub_, SP_FIXINV);
                     std::string oriented = oriented_read(b, r, s.need_reverse);
-                    vmg::fix_simple_inv(s.al, ctg_, oriented.data(), read_len[r]);
+                    if (vmg::fix_simple_inv(s.al, ctg_, oriented.data(), read_len[r])) bc_[BC_FIX_SIMPLE_INV].fetch_add(1, std::memory_order_relaxed);
                 }
                 s.kept.assign(s.al.size(), Path());
                 s.fills.clear();
@@ -448,7 +483,7 @@ private:
                     orient(j.job.query, s.need_reverse);
                     fj[t].push_back(std::move(j));
                 }
-            } catch (const vmg::ReadDropped &) { s.alive = false; fj[t].clear(); }
+            } catch (const vmg::ReadDropped &) { s.alive = false; s.dropped = true; fj[t].clear(); }
         });
         std::vector<FillJobRef> fills;
         std::vector<int64_t> f_start;
@@ -470,7 +505,7 @@ private:
             SubScope sc(sub_, SP_RECORDS);
             try {
                 vmg::make_records(s.kept, cig, s.mapq, read_len[r], ctg_, s.need_reverse, opt_.hardclip, s.recs);
-            } catch (const vmg::ReadDropped &) { s.alive = false; s.recs.clear(); }
+            } catch (const vmg::ReadDropped &) { s.alive = false; s.dropped = true; s.recs.clear(); }
             if (s.recs.empty()) s.alive = false;
         });
     }
@@ -539,6 +574,7 @@ private:
     }
 
     SubTimes sub_;
+    std::atomic<int64_t> bc_[BC_COUNT];
     bool first_pass_ = false;
     const ChainOut *lc_ = nullptr;     // local-stage result of the batch in flight (valid during align_batch)
     Backend &be_;

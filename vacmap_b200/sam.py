@@ -14,11 +14,12 @@ import re
 import numpy as np
 
 _CIGAR_RE = re.compile(r"(\d+)([MIDNSHP=X])")
-_COMP = bytes.maketrans(b"ACGTUNacgtun", b"TGCAANtgcaan")
+# Bio.Seq's ambiguous DNA complement table (IUPAC codes, both cases; U -> A)
+_COMP = bytes.maketrans(b"ACGTUNRYKMBVDHSWacgtunrykmbvdhsw", b"TGCAANYRMKVBHDSWtgcaanyrmkvbhdsw")
 
 
 def reverse_complement(seq):
-    """``str(Bio.Seq.Seq(seq).reverse_complement())`` for the alphabet the hot path sees (ACGTN, either case)."""
+    """``str(Bio.Seq.Seq(seq).reverse_complement())``, IUPAC ambiguity codes included."""
     return seq.encode().translate(_COMP)[::-1].decode()
 
 
@@ -324,10 +325,24 @@ def iterator_get_bam_dict_str(mapinfo, query, qual, contig2iloc, contig2seq, md,
                                 asm=True)
 
 
-def header_text(contigs, rg_id=None):
-    """``@HD VN:1.0`` + one ``@SQ`` per contig, as ``create_header`` (:70-83) hands to pysam; ``contigs`` = [(name, length)]."""
+# field order of pysam's AlignmentHeader.from_dict (libcalignmentfile.pyx VALID_HEADER_ORDER), which the reference's
+# writer uses to print its header dict (output_functions.py:66-76); pysam is absent here, so this order is restated
+RG_ORDER = ("ID", "CN", "SM", "LB", "PU", "PI", "DT", "DS", "PL", "FO", "KS", "PG", "PM", "BC")
+PG_ORDER = ("PN", "ID", "VN", "PP", "DS", "CL")
+
+
+def header_text(contigs, rg=None, command_line=None, version="1.0.2"):
+    """The header the reference hands to pysam (vacmap:353-370): ``@HD VN:1.0``, one ``@SQ`` per contig, the read
+    group every record's RG:Z tag points to (default ``{"ID": "1", "SM": "sample"}``, vacmap:214-218) and the
+    ``@PG`` line; ``contigs`` = [(name, length)], ``rg`` = dict of @RG fields (None: the default group)."""
+    if rg is None:
+        rg = {"ID": "1", "SM": "sample"}
+    elif not isinstance(rg, dict):
+        rg = {"ID": str(rg), "SM": "sample"}
     lines = ["@HD\tVN:1.0"]
     lines += ["@SQ\tSN:%s\tLN:%d" % (n, ln) for n, ln in contigs]
-    if rg_id is not None:
-        lines.append("@RG\tID:%s" % rg_id)
+    keys = [k for k in RG_ORDER if k in rg] + [k for k in rg if k not in RG_ORDER]
+    lines.append("@RG\t" + "\t".join("%s:%s" % (k, rg[k]) for k in keys))
+    pg = {"ID": "VACmap", "PN": "VACmap", "VN": version, "CL": command_line if command_line is not None else ""}
+    lines.append("@PG\t" + "\t".join("%s:%s" % (k, pg[k]) for k in PG_ORDER if k in pg))
     return "\n".join(lines) + "\n"
