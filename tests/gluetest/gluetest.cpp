@@ -2,9 +2,11 @@
 // on a CPU-only box with the ORACLE's C stage functions standing in for the CUDA kernels, so the
 // glue can be checked against the reference-generated golden records without a GPU.
 #include "../../vacmap_b200/csrc/vm_pipeline.hpp"
+#include "../../vacmap_b200/csrc/vm_dgrun.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <memory>
 
 extern "C" {
 // oracle/orc_*.c
@@ -41,11 +43,141 @@ static std::string revcomp(const std::string &s)
     return r;
 }
 
+struct OracleBackend;
+
+// Execution policy of vm_dgrun.hpp for the CPU harness: the per-read functors run in plain loops, the hot loops are
+// the oracle's C natives (exact edit distance, k_cigar extension and fill).
+struct OracleExec {
+    typedef std::vector<char> Buf;
+    typedef std::vector<char> HostBuf;
+    static constexpr bool kBoundsAreUpper = false;
+    OracleBackend *be = nullptr;
+    int fill_slot = 0;
+    std::vector<uint32_t> ops_[2];
+    static void release(Buf &b) { Buf().swap(b); }
+    static void release_host(HostBuf &b) { HostBuf().swap(b); }
+    template <typename T> T *ensure(Buf &b, size_t n) { if (b.size() < n * sizeof(T) + 64) b.resize(n * sizeof(T) + 64); return (T *)b.data(); }
+    template <typename T> T *host(HostBuf &b, size_t n) { return ensure<T>(b, n); }
+    void zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+    void to_host(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+    void to_exec(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+    void sync() {}
+    template <typename F> void per_item(int64_t n, const F &f) { for (int64_t t = 0; t < n; ++t) f(t); }
+    struct Ext {
+        OracleBackend *be;
+        int32_t read;
+        void operator()(const vmd::Spec &t, const vmd::Spec &q, int32_t &q_e, int32_t &t_e);
+    };
+    template <typename F> void per_item_warp(int64_t n, const F &f)
+    {
+        Ext ext{be, 0};
+        for (int64_t t = 0; t < n; ++t) f(t, ext, true);
+    }
+    template <typename F> void per_ids_write(const int32_t *ids, int64_t n, const F &f) { for (int64_t t = 0; t < n; ++t) f.run(ids[t], 0, 1); }
+    void ed_bounds(vmd::Job *jobs, int64_t n, const vmd::A32 *);
+    void ed_exact(vmd::Job *, const int32_t *, int64_t) {}
+    void fill(vmd::Job *jobs, int64_t nj, int64_t, bool eqx, vmd::U2 *res, const uint32_t **ops);
+};
+
 struct OracleBackend : public Backend {
     void *index;
     const orc_tables *tb;
     const char *ref;
+    bool device_ext = false;             // GT_DEVICE_GLUE: run extend_func through vm_dgrun.hpp / vm_dglue.hpp
+    const vmg::Contigs *ctg = nullptr;
+    const ChainOut *last_lc = nullptr;
+    const ReadBatch *cur = nullptr;
+    std::string fwd_all, rc_all;
+    OracleExec exec;
+    std::unique_ptr<vmd::BackHalf<OracleExec>> back;
     OracleBackend(void *ix, const orc_tables *t, const char *r) : index(ix), tb(t), ref(r) {}
+
+    std::string materialize_spec(const vmd::Spec &s, int read) const
+    {
+        std::string out;
+        if (s.src == 0) out.assign(ref + s.lo, (size_t)s.len);
+        else out = (s.src == 1 ? fwd_all : rc_all).substr((size_t)(cur->off[read] - cur->off[0] + s.lo), (size_t)s.len);
+        if (s.comp)
+            for (char &c : out) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+        if (s.reverse) std::reverse(out.begin(), out.end());
+        return out;
+    }
+
+    bool has_device_extension() const override { return device_ext; }
+    bool extend_device(const ReadBatch &b, const std::vector<int32_t> &ids, const std::vector<char> &need_reverse,
+                       const std::vector<int32_t> &mapq, const vmg::Options &opt, std::vector<int32_t> &status, FlatRecords &out) override
+    {
+        if (!device_ext) return false;
+        const int64_t n = b.n;
+        cur = &b;
+        fwd_all.assign(b.seq + b.off[0], (size_t)(b.off[n] - b.off[0]));
+        rc_all.resize(fwd_all.size());
+        std::vector<int64_t> off((size_t)n + 1);
+        for (int64_t r = 0; r <= n; ++r) off[(size_t)r] = b.off[r] - b.off[0];
+        for (int64_t r = 0; r < n; ++r) {
+            const std::string rc = revcomp(fwd_all.substr((size_t)off[(size_t)r], (size_t)(off[(size_t)r + 1] - off[(size_t)r])));
+            memcpy(&rc_all[(size_t)off[(size_t)r]], rc.data(), rc.size());
+        }
+        // what the device kernels would have left behind: the extracted local chain and its rebuilt sub-alignments
+        const ChainOut &lc = *last_lc;
+        std::vector<vmd::ExtractRec> xrec((size_t)n);
+        std::vector<vmd::RebuildRec> rrec((size_t)n);
+        std::vector<vmd::A32> al_anc;
+        std::vector<int32_t> al_len, cnt((size_t)n), nrev((size_t)n), mq(mapq);
+        std::vector<vmg::AlnList> als((size_t)n);
+        for (int64_t r = 0; r < n; ++r) {
+            memset(&xrec[(size_t)r], 0, sizeof(vmd::ExtractRec));
+            memset(&rrec[(size_t)r], 0, sizeof(vmd::RebuildRec));
+            cnt[(size_t)r] = lc.cnt[(size_t)r];
+            nrev[(size_t)r] = need_reverse[(size_t)r] ? 1 : 0;
+            if (lc.cnt[(size_t)r] <= 0 || lc.gmax[(size_t)r] < 0) continue;
+            Path asc;
+            vmg::local_traceback(lc.sorted + lc.start[(size_t)r], lc.P + lc.start[(size_t)r], lc.gmax[(size_t)r], asc);
+            xrec[(size_t)r].n_anc = (int32_t)asc.size();
+            xrec[(size_t)r].n_chains = 1;
+            if (asc.size() <= 1) continue;
+            try { vmg::rebuild_chain_break(*ctg, asc, opt.local_maxdiff, als[(size_t)r]); } catch (const vmg::ReadDropped &) { als[(size_t)r].clear(); }
+        }
+        // the rebuild kernel claims its anchor room and its length room from two independent counters, in whatever order the
+        // threads arrive: here the lengths are laid out in read order and the anchors in REVERSE read order, so that nothing
+        // downstream can rely on the two offsets growing together
+        for (int64_t r = 0; r < n; ++r) {
+            rrec[(size_t)r].len_off = (long long)al_len.size();
+            rrec[(size_t)r].n_al = (int32_t)als[(size_t)r].size();
+            for (const Path &p : als[(size_t)r]) al_len.push_back((int32_t)p.size());
+        }
+        for (int64_t r = n - 1; r >= 0; --r) {
+            rrec[(size_t)r].anc_off = (long long)al_anc.size();
+            for (const Path &p : als[(size_t)r])
+                for (const Anc &a : p) al_anc.push_back(vmd::A32{(int32_t)a.x, (uint32_t)a.y, a.s, a.l});
+            rrec[(size_t)r].n_anc = (int32_t)(al_anc.size() - (size_t)rrec[(size_t)r].anc_off);
+        }
+        al_anc.push_back(vmd::A32{0, 0, 0, 0});
+        al_len.push_back(0);
+        vmd::BackInput in;
+        in.n_reads = n;
+        in.read_off = off.data();
+        in.reads_fwd = (const uint8_t *)fwd_all.data();
+        in.reads_rc = (const uint8_t *)rc_all.data();
+        in.ref = (const uint8_t *)ref;
+        in.ctg.start = ctg->start.data(); in.ctg.len = ctg->len.data(); in.ctg.n = (int32_t)ctg->start.size();
+        in.need_reverse = nrev.data();
+        in.mapq = mq.data();
+        in.local_cnt = cnt.data();
+        in.xrec = xrec.data(); in.rrec = rrec.data(); in.al_anc = al_anc.data(); in.al_len = al_len.data();
+        in.NA = (int64_t)al_len.size() - 1; in.NT = (int64_t)al_anc.size() - 1;
+        in.total_bases = off[(size_t)n];
+        vmd::BackParams p;
+        p.maxdivergence = opt.maxdivergence; p.eqx = opt.eqx; p.hardclip = opt.hardclip; p.nodiscard = opt.nodiscard;
+        exec.be = this;
+        if (!back) back.reset(new vmd::BackHalf<OracleExec>(exec));
+        vmd::BackResult br;
+        back->run(in, p, ids, status, br);
+        out.rec_off.swap(br.rec_off);
+        out.recs = br.recs; out.cigar = br.cigar; out.n_rec = br.n_rec; out.n_ops = br.n_ops;
+        for (int k = 0; k < vmd::CT_COUNT; ++k) out.counters[k] = br.counters[k];
+        return true;
+    }
 
     std::string materialize(const ReadBatch &b, int read, const vmg::SeqRef &s) const
     {
@@ -87,6 +219,7 @@ struct OracleBackend : public Backend {
     {
         out = ChainOut();
         out.start.assign((size_t)b.n, 0); out.cnt.assign((size_t)b.n, 0); out.gmax.assign((size_t)b.n, -1);
+        out.used_fast.assign((size_t)b.n, 0);
         need_reverse.assign((size_t)b.n, 0);
         for (int64_t r = 0; r < b.n; ++r) {
             const int64_t L = b.len(r);
@@ -118,7 +251,10 @@ struct OracleBackend : public Backend {
             if (n > 0) {
                 const bool fast = (double)n / (double)L > 5.0;
                 if (!fast) g = orc_chain_global_d_all(srows.data(), n, kmersize, skipcost, maxdiff, maxgap, tb, 1000, S.data(), P.data(), A.data(), nullptr);
-                if (fast || g == -1) g = orc_chain_fast(srows.data(), n, kmersize, 0, skipcost, maxdiff, maxgap, 5, tb, nullptr, S.data(), P.data(), A.data());
+                if (fast || g == -1) {
+                    g = orc_chain_fast(srows.data(), n, kmersize, 0, skipcost, maxdiff, maxgap, 5, tb, nullptr, S.data(), P.data(), A.data());
+                    if (n > 2) out.used_fast[(size_t)r] = 1;
+                }
             }
             put(out, r, srt, S, P, A, g);
         }
@@ -169,6 +305,7 @@ struct OracleBackend : public Backend {
             put(out, r, srt, S, P, A32, g);
         }
         out.adopt_stores();
+        last_lc = &out;
     }
 
     void edit_distance(const ReadBatch &b, std::vector<EdJob> &jobs, const vmg::MatchSeg *, size_t) override
@@ -208,6 +345,46 @@ struct OracleBackend : public Backend {
     }
 };
 
+void OracleExec::Ext::operator()(const vmd::Spec &t, const vmd::Spec &q, int32_t &q_e, int32_t &t_e)
+{
+    const std::string ts = be->materialize_spec(t, read), qs = be->materialize_spec(q, read);
+    orc_kc_result res;
+    std::vector<uint32_t> cig(ts.size() + qs.size() + 4);
+    orc_k_cigar(ts.data(), (int32_t)ts.size(), qs.data(), (int32_t)qs.size(), 2, -4, 4, 4, 4, 4, 100, 50, 0, cig.data(), (int32_t)cig.size(), &res);
+    q_e = res.q_e;
+    t_e = res.t_e;
+}
+
+void OracleExec::ed_bounds(vmd::Job *jobs, int64_t n, const vmd::A32 *)
+{
+    for (int64_t j = 0; j < n; ++j) {
+        vmd::Job &J = jobs[j];
+        if (J.t.len <= 0 || J.q.len <= 0) continue;
+        const std::string x = be->materialize_spec(J.q, J.read), y = be->materialize_spec(J.t, J.read);
+        J.result0 = orc_edit_distance(x.data(), (int64_t)x.size(), y.data(), (int64_t)y.size());
+    }
+}
+
+void OracleExec::fill(vmd::Job *jobs, int64_t nj, int64_t, bool eqx, vmd::U2 *res, const uint32_t **ops)
+{
+    std::vector<uint32_t> &O = ops_[fill_slot];
+    O.clear();
+    for (int64_t j = 0; j < nj; ++j) {
+        vmd::Job &J = jobs[j];
+        res[j].x = (uint32_t)O.size();
+        res[j].y = 0;
+        if (J.t.len <= 0 || J.q.len <= 0) continue;
+        const std::string t = be->materialize_spec(J.t, J.read), q = be->materialize_spec(J.q, J.read);
+        orc_kc_result r;
+        std::vector<uint32_t> cig(t.size() + q.size() + 4);
+        orc_k_cigar(t.data(), (int32_t)t.size(), q.data(), (int32_t)q.size(), 2, -4, 4, 2, 24, 1, -1, -1, eqx ? 1 : 0, cig.data(), (int32_t)cig.size(), &r);
+        res[j].y = (uint32_t)r.n_cigar;
+        O.insert(O.end(), cig.begin(), cig.begin() + r.n_cigar);
+    }
+    O.push_back(0);
+    *ops = O.data();
+}
+
 extern "C" {
 
 struct gt_options {
@@ -230,6 +407,8 @@ int64_t gt_align_batch(void *orc_index, const orc_tables *tb, const char *ref, c
     opt.eqx = o->eqx; opt.hardclip = o->hardclip; opt.nodiscard = o->nodiscard;
     opt.mode = vmg::ModeConst{o->accept, o->max_guides, o->local_maxgap, o->clamp40 != 0};
     OracleBackend be(orc_index, tb, ref);
+    be.ctg = &ctg;
+    be.device_ext = getenv("GT_DEVICE_GLUE") != nullptr;
     Driver drv(be, ctg, opt, o->kmersize, o->threads);
     std::map<std::string, double> phase_ms;
     if (getenv("GT_TIMES")) drv.on_time = [&](const char *nm, double ms) { phase_ms[nm] += ms; };
@@ -239,6 +418,30 @@ int64_t gt_align_batch(void *orc_index, const orc_tables *tb, const char *ref, c
     drv.align_batch(b, res);
     for (auto &kv : phase_ms) fprintf(stderr, "GT_TIME %s %.3f\n", kv.first.c_str(), kv.second);
     int64_t nrec = 0, ncig = 0;
+    if (const char *cf = getenv("GT_COUNTERS")) {
+        FILE *f = fopen(cf, "w");
+        if (f) {
+            for (int k = 0; k < BC_COUNT; ++k) fprintf(f, "%s %lld\n", kBranchName[k], (long long)res.branch[k]);
+            for (int64_t r = 0; r < n_reads; ++r) fprintf(f, "status %lld %d\n", (long long)r, (int)res.status[(size_t)r]);
+            fclose(f);
+        }
+    }
+    if (res.flat) {
+        for (int64_t r = 0; r < n_reads; ++r)
+            for (int64_t q = res.fr.rec_off[(size_t)r]; q < res.fr.rec_off[(size_t)r + 1]; ++q) {
+                const vmd::Rec &rec = res.fr.recs[q];
+                if (nrec < rec_cap && ncig + rec.cigar_len <= cigar_cap) {
+                    int64_t *row = rec_rows + nrec * 9;
+                    row[0] = r; row[1] = rec.contig; row[2] = rec.strand; row[3] = rec.q_st; row[4] = rec.q_en;
+                    row[5] = rec.r_st; row[6] = rec.r_en; row[7] = rec.mapq; row[8] = rec.cigar_len;
+                    memcpy(cigar + ncig, res.fr.cigar + rec.cigar_off, (size_t)rec.cigar_len * 4);
+                }
+                ++nrec;
+                ncig += rec.cigar_len;
+            }
+        *n_cigar_out = ncig;
+        return nrec;
+    }
     for (int64_t r = 0; r < n_reads; ++r)
         for (const vmg::Record &rec : res.records[r]) {
             if (nrec < rec_cap && ncig + (int64_t)rec.cigar.size() <= cigar_cap) {

@@ -69,7 +69,8 @@ extern const int VM_ED_CLASS_G[VM_ED_NCLASS];
 int vm_ed_slots(int m, int n, long long band);
 int vm_launch_edit_distance(VmAlnJobDev *jobs, const int *ids_dev, const int *class_start, const int *class_words, VmSeqSources src,
                             cudaStream_t stream);
-// upper bound of the distance through the job's match segments (J.dir_off / J.n_out into segs_dev, 12-byte {q, t, l})
+// upper bound of the distance through the job's match segments (J.dir_off / J.n_out into segs_dev, 12-byte {q, t, l});
+// ids_dev == nullptr: jobs 0 .. n_jobs - 1
 int vm_launch_ed_upper(VmAlnJobDev *jobs, const int *ids_dev, int n_jobs, const void *segs_dev, VmSeqSources src, cudaStream_t stream);
 // derive the match segments of every job from its sub-alignment's anchors on the device (anc_dev[J.dir_off .. + J.n_out))
 int vm_launch_match_segments(VmAlnJobDev *jobs, int n_jobs, const VmAnchor *anc_dev, void *segs_dev, cudaStream_t stream);
@@ -127,3 +128,42 @@ int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs_dev, const VmF
                     uint32_t *dir_scratch, int *counters_dev, uint32_t *cigar_scratch, uint32_t *dense_out,
                     unsigned long long *dense_count, void *results, cudaStream_t main_stream, const cudaStream_t *side, int n_side,
                     int *side_rr, size_t *dir_cursor);
+
+// ---- the same plans made on the device (the jobs never visit the host) ----
+#include "vm_ctx.cuh"
+struct VmFbTable {          // per slot class 1..VM_FB_NCLASS of the banded kernel
+    int32_t cnt[16], at[16], max_steps[16];
+    unsigned long long sum_steps[16];
+    int32_t n_live, n_pairs;
+};
+struct VmFfTable {          // per capacity class 0..26 of the full-matrix kernel
+    int32_t n[32], pair_begin[32], max_q[32], max_t[32];
+    int32_t n_live, n_pairs;
+    double dir_bytes;
+};
+struct VmFillPlanBufs {
+    VmDevBuf keys, bmin, bmax, start, cursor, order, tpairs, keys2, start2, cursor2, order2, small;
+    VmPinnedBuf table;
+    void release()
+    {
+        VmDevBuf *d[] = {&keys, &bmin, &bmax, &start, &cursor, &order, &tpairs, &keys2, &start2, &cursor2, &order2, &small};
+        for (VmDevBuf *x : d) x->release();
+        table.release();
+    }
+};
+// Asynchronous part: plans every job the banded kernel can take.  pairs_out_dev (room for n_jobs pairs) receives the
+// pairs bucketed by slot class; full_mask_dev[j] = 1 for valid jobs left to the full-matrix kernel; B.table (pinned host,
+// a VmFbTable) is valid once the stream is synchronised.  Returns the number of kernel launches, < 0 on a CUDA error.
+int vm_fillb_plan_dev(const VmAlnJobDev *jobs_dev, int n_jobs, VmFillPlanBufs &B, VmFillBandPair *pairs_out_dev, uint8_t *full_mask_dev,
+                      cudaStream_t stream);
+// launches of the plan from the table (pairs stay on the device: plan.pairs is left empty)
+void vm_fillb_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillBandPlan &plan);
+// Full-matrix kernel, jobs with only_mask_dev[j] != 0: pairs_out_dev gets the pairs by capacity class, B.table a VmFfTable.
+int vm_fill_plan_dev(const VmAlnJobDev *jobs_dev, int n_jobs, const uint8_t *only_mask_dev, VmFillPlanBufs &B, VmFillPair *pairs_out_dev,
+                     cudaStream_t stream);
+void vm_fill_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillPlan &plan);
+// sum over the valid jobs of tlen * qlen (cells) and tlen + qlen (bases), added to the two device doubles
+int vm_launch_fill_stats(const VmAlnJobDev *jobs_dev, int n_jobs, double *cells_dev, double *bases_dev, cudaStream_t stream);
+// mask_dev[j] = 1 for the jobs whose banded certificate failed (results[j].x == 0xffffffff), 0 otherwise; their number is
+// added to *count_dev
+int vm_launch_fill_redo_mask(const void *results_dev, int n_jobs, uint8_t *mask_dev, unsigned long long *count_dev, cudaStream_t stream);

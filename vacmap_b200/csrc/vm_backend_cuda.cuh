@@ -14,6 +14,7 @@
 #include "vm_align.cuh"
 #include "vm_extract.cuh"
 #include "vm_pipeline.hpp"
+#include "vm_dglue.cuh"
 #include <chrono>
 #include <ctime>
 #include <map>
@@ -101,7 +102,10 @@ struct Timeline {
 
 class CudaBackend : public Backend {
 public:
-    CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih) {}
+    CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih)
+    {
+        device_extension = getenv("VM_HOST_GLUE") == nullptr;      // A/B switch: the vector-based host glue of round 1
+    }
     ~CudaBackend() override
     {
         for (int i = 0; i < 3; ++i) {
@@ -116,12 +120,17 @@ public:
         VmDevBuf *b[] = {&reads_fwd_, &reads_rc_, &read_off_, &jobs_, &d_wlo_, &d_whi_, &d_gx_, &d_gy_, &d_nh_, &d_hits_, &d_tab_,
                          &d_order_, &d_rout_, &d_dense_, &d_seg_, &d_dir_, &d_sc_, &d_cig_, &d_cigd_, &d_pairs_, &d_msegs_};
         for (VmDevBuf *x : b) x->release();
+        { VmDevBuf *xb[] = {&dx_nrev_, &d_mask_, &d_fstats_, &d_cigd2_}; for (VmDevBuf *x : xb) x->release(); }
+        bplanbufs_.release();
+        fplanbufs_.release();
+        back_.reset();
         VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_, &h_gx_, &h_gy_,
                             &h_segs_};
         for (VmPinnedBuf *x : p) x->release();
     }
     StageTimer timer;
     bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
+    bool device_extension = true;   // extend_func's glue runs on the device (extend_device); false: the host glue of vm_glue.hpp
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
     double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0, fill_band_jobs_ = 0,
@@ -280,7 +289,7 @@ public:
         // local stage: rebuild_chain_break on the device
         VmDevBuf al_rec, al_anc, al_len;
         VmPinnedBuf h_al_rec, h_al_anc, h_al_len;
-        size_t al_n_anc = 0;
+        size_t al_n_anc = 0, al_n_al = 0;
         void release()
         {
             VmDevBuf *d[] = {&rec, &anc, &S, &len, &score, &counters, &al_rec, &al_anc, &al_len};
@@ -361,6 +370,14 @@ public:
         BE_OK(X.h_counters.ensure(64));
         BE_OK(X.h_rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
         BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 32, cudaMemcpyDeviceToHost, c_->stream));
+        if (!global && device_extension && rebuild) {
+            // the extension stage runs on the device (extend_device): only the totals cross PCIe
+            BE_OK(vm_stream_sync(c_->stream));
+            BE_OK(cudaGetLastError());
+            X.al_n_anc = (size_t)X.h_counters.as<unsigned long long>()[2];
+            X.al_n_al = (size_t)X.h_counters.as<unsigned long long>()[3];
+            return;
+        }
         BE_OK(cudaMemcpyAsync(X.h_rec.p, X.rec.p, (size_t)n * sizeof(VmExtractRec), cudaMemcpyDeviceToHost, c_->stream));
         BE_OK(vm_stream_sync(c_->stream));
         BE_OK(cudaGetLastError());
@@ -382,6 +399,7 @@ public:
         if (rebuild) {
             const size_t ra = (size_t)X.h_counters.as<unsigned long long>()[2], rl = (size_t)X.h_counters.as<unsigned long long>()[3];
             X.al_n_anc = ra;
+            X.al_n_al = rl;
             BE_OK(X.h_al_rec.ensure((size_t)(n + 1) * sizeof(VmRebuildRec)));
             BE_OK(X.h_al_anc.ensure(std::max<size_t>(ra, 1) * 16));
             BE_OK(X.h_al_len.ensure(std::max<size_t>(rl, 1) * 4));
@@ -620,6 +638,8 @@ public:
     // contig start offsets on the device (pos2contig for the rebuild kernel), refreshed when the index changes
     void upload_contig_starts()
     {
+        upload_contig_table();
+        return;
         if (d_ctg_for_ == ih_) return;
         const std::vector<int64_t> &st = ih_->ctg.start;
         BE_OK(d_ctg_.ensure(st.size() * 8 + 64));
@@ -990,7 +1010,279 @@ public:
         return h_cig_.as<uint32_t>();
     }
 
+    // =========================================================================================================
+    // The extension stage with its glue on the device (vm_dgrun.hpp / vm_dglue.hpp): CudaExec is the execution
+    // policy that runs the per-read functors as kernels on this backend's stream and the hot loops on the kernels
+    // this backend already owns (divergence-filter bounds, exact banded distance, fill with device-side planning).
+    // =========================================================================================================
+    struct CudaExec {
+        typedef VmDevBuf Buf;
+        typedef VmPinnedBuf HostBuf;
+        static constexpr bool kBoundsAreUpper = true;
+        static void release(Buf &b) { b.release(); }
+        static void release_host(HostBuf &b) { b.release(); }
+        template <typename T> T *host(HostBuf &b, size_t n)
+        {
+            BE_OK(b.ensure(n * sizeof(T) + 64));
+            return b.as<T>();
+        }
+        CudaBackend *be;
+        template <typename T> T *ensure(Buf &b, size_t n)
+        {
+            BE_OK(b.ensure(n * sizeof(T) + 64));
+            return b.as<T>();
+        }
+        void zero(void *p, size_t bytes) { if (bytes) BE_OK(cudaMemsetAsync(p, 0, bytes, be->c_->stream)); }
+        void to_host(void *dst, const void *src, size_t bytes) { if (bytes) BE_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, be->c_->stream)); }
+        void to_exec(void *dst, const void *src, size_t bytes) { if (bytes) BE_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, be->c_->stream)); }
+        void sync()
+        {
+            BE_OK(vm_stream_sync(be->c_->stream));
+            BE_OK(cudaGetLastError());
+        }
+        template <typename F> void per_item(int64_t n, const F &f)
+        {
+            if (n <= 0) return;
+            vm_dg_item_kernel<F><<<(unsigned)((n + 63) / 64), 64, 0, be->c_->stream>>>(n, f);
+            be->c_->launches += 1;
+        }
+        template <typename F> void per_item_warp(int64_t n, const F &f)
+        {
+            if (n <= 0) return;
+            KTimer kt(be, "k_extend");
+            vm_dg_warp_kernel<F><<<(unsigned)((n + 3) / 4), 128, 0, be->c_->stream>>>(n, f, be->sources());
+            be->c_->launches += 1;
+            kt.stop();
+        }
+        template <typename F> void per_ids_write(const int32_t *ids, int64_t n, const F &f)
+        {
+            if (n <= 0) return;
+            vm_dg_write_kernel<F><<<(unsigned)((n + 3) / 4), 128, 0, be->c_->stream>>>(ids, n, f);
+            be->c_->launches += 1;
+        }
+        void ed_bounds(vmd::Job *jobs, int64_t n, const vmd::A32 *al_anc)
+        {
+            if (n <= 0) return;
+            BE_OK(be->d_msegs_.ensure(std::max<size_t>(be->lx_.al_n_anc, 1) * sizeof(vmg::MatchSeg) + 64));
+            KTimer kt(be, "k_ed_upper");
+            be->c_->launches += vm_launch_match_segments((VmAlnJobDev *)jobs, (int)n, (const VmAnchor *)al_anc, be->d_msegs_.p, be->c_->stream);
+            be->c_->launches += vm_launch_ed_upper((VmAlnJobDev *)jobs, nullptr, (int)n, be->d_msegs_.p, be->sources(), be->c_->stream);
+            kt.stop();
+            be->ed_upper_jobs_ += (double)n;
+        }
+        // the jobs the bound left open: exact banded distance (host-planned by register class, as the stage-level path)
+        void ed_exact(vmd::Job *jobs, const int32_t *open, int64_t n_open)
+        {
+            std::vector<int32_t> ids((size_t)n_open);
+            to_host(ids.data(), open, (size_t)n_open * 4);
+            sync();
+            std::vector<VmAlnJobDev> J((size_t)n_open);
+            for (int64_t i = 0; i < n_open; ++i) to_host(&J[(size_t)i], (VmAlnJobDev *)jobs + ids[(size_t)i], sizeof(VmAlnJobDev));
+            sync();
+            std::vector<EdJob> ed((size_t)n_open);
+            std::vector<int> which((size_t)n_open);
+            for (int64_t i = 0; i < n_open; ++i) {
+                const VmAlnJobDev &j = J[(size_t)i];
+                EdJob &e = ed[(size_t)i];
+                e.read = j.read;
+                e.a.src = j.q.src; e.a.lo = j.q.lo; e.a.hi = j.q.lo + j.q.len; e.a.reverse = j.q.reverse; e.a.comp = j.q.comp;
+                e.b.src = j.t.src; e.b.lo = j.t.lo; e.b.hi = j.t.lo + j.t.len; e.b.reverse = j.t.reverse; e.b.comp = j.t.comp;
+                e.band = j.out_off;
+                which[(size_t)i] = (int)i;
+            }
+            be->ed_exact(ed, which);
+            for (int64_t i = 0; i < n_open; ++i) {
+                int64_t d = ed[(size_t)i].dist;
+                to_exec(&((VmAlnJobDev *)jobs + ids[(size_t)i])->result0, &d, 8);
+                sync();      // `d` is a stack variable
+            }
+        }
+        void fill(vmd::Job *jobs, int64_t nj, int64_t scratch_words, bool eqx, vmd::U2 *res, const uint32_t **ops)
+        {
+            *ops = be->fill_device((VmAlnJobDev *)jobs, (int)nj, scratch_words, eqx, (uint2 *)res, fill_slot);
+        }
+        int fill_slot = 0;       // pass 1 / pass 2 keep their dense CIGAR arenas apart
+    };
+
+    // per-job statistics of a fill batch, summed on the device
+    struct FillStats { double cells, bases; unsigned long long n_band, n_redo; };
+
+    // Global fill of device-resident jobs, planned on the device.  results[j] = (offset, length) of job j's ops in the
+    // returned dense arena (valid until the next fill_device call with the same slot).
+    const uint32_t *fill_device(VmAlnJobDev *jobs, int nj, int64_t scratch_words, bool eqx, uint2 *results, int slot)
+    {
+        WallTimer wt(this, "fill");
+        VmDevBuf &dense = slot ? d_cigd2_ : d_cigd_;
+        const int sms = c_->sm_count > 0 ? c_->sm_count : 148;
+        BE_OK(d_cig_.ensure((size_t)scratch_words * 4 + 64));
+        BE_OK(dense.ensure((size_t)scratch_words * 4 + 64));
+        BE_OK(d_mask_.ensure((size_t)nj + 64));
+        BE_OK(d_pairs_.ensure((size_t)nj * (sizeof(VmFillPair) + sizeof(VmFillBandPair)) + 4096));
+        BE_OK(d_fstats_.ensure(256));
+        VmFillPair *d_fpairs = d_pairs_.as<VmFillPair>();
+        VmFillBandPair *d_bpairs = (VmFillBandPair *)(d_fpairs + nj);
+        unsigned long long *d_count = (unsigned long long *)d_fstats_.p;       // [dense count | FillStats | launch counters]
+        FillStats *d_stats = (FillStats *)(d_count + 1);
+        int *d_ctr = (int *)(d_stats + 1);
+        static const bool no_band = getenv("VM_FILL_NO_BAND") != nullptr;
+        {
+            WallTimer w2(this, "h_fill_plan");
+            BE_OK(cudaMemsetAsync(d_fstats_.p, 0, 256, c_->stream));
+            BE_OK(cudaMemsetAsync(results, 0, (size_t)nj * 8, c_->stream));
+            int nl;
+            if (!no_band) {
+                nl = vm_fillb_plan_dev(jobs, nj, bplanbufs_, d_bpairs, d_mask_.as<uint8_t>(), c_->stream);
+                if (nl < 0) throw std::runtime_error("fill plan (banded): CUDA error");
+                c_->launches += nl;
+            } else BE_OK(cudaMemsetAsync(d_mask_.p, 1, (size_t)nj, c_->stream));
+            nl = vm_fill_plan_dev(jobs, nj, d_mask_.as<uint8_t>(), fplanbufs_, d_fpairs, c_->stream);
+            if (nl < 0) throw std::runtime_error("fill plan: CUDA error");
+            c_->launches += nl + vm_launch_fill_stats(jobs, nj, &d_stats->cells, &d_stats->bases, c_->stream);
+            BE_OK(vm_stream_sync(c_->stream));
+            BE_OK(cudaGetLastError());
+            if (!no_band) vm_fillb_plan_finish(bplanbufs_, sms, bplan_);
+            else { bplan_.pairs.clear(); bplan_.launches.clear(); bplan_.dir_words = 0; bplan_.dir_bytes = 0; }
+            vm_fill_plan_finish(fplanbufs_, sms, plan_);
+        }
+        fill_dir_bytes_ += plan_.dir_bytes + bplan_.dir_bytes;
+        fill_jobs_ += nj;
+        if (plan_.launches.size() + bplan_.launches.size() > 40) throw std::runtime_error("fill: too many launch classes");
+        if (getenv("VM_DEBUG_MEM")) {
+            size_t fr = 0, tot = 0;
+            cudaMemGetInfo(&fr, &tot);
+            fprintf(stderr, "[fill_device] nj=%d scratch_words=%lld band dir_words=%zu (%zu launches) full dir_words=%zu band_words=%zu (%zu launches) free=%.1f GB of %.1f\n",
+                    nj, (long long)scratch_words, bplan_.dir_words, bplan_.launches.size(), plan_.dir_words, plan_.band_words, plan_.launches.size(),
+                    fr / 1e9, tot / 1e9);
+            for (const VmFillBandLaunch &L : bplan_.launches)
+                fprintf(stderr, "   band cls %d pairs %d blocks %d words/warp %lld\n", L.cls, L.pair_end - L.pair_begin, L.blocks, L.dir_words_per_warp);
+            for (const VmFillLaunch &L : plan_.launches)
+                fprintf(stderr, "   full R %d mb %d pairs %d blocks %d words/warp %lld band/warp %lld\n", L.R, L.multiband, L.pair_end - L.pair_begin, L.blocks,
+                        L.dir_words_per_warp, L.band_words_per_warp);
+        }
+        BE_OK(d_dir_.ensure((plan_.dir_words + bplan_.dir_words) * 4 + 64));
+        BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
+        {
+            KTimer kt(this, "k_fill");
+            side_fork();
+            int rr = 0;
+            size_t dir_cur = 0, band_cur = 0;
+            c_->launches += vm_fillb_launch(bplan_, jobs, d_bpairs, sources(), eqx ? 1 : 0, d_dir_.as<uint32_t>(), d_ctr + plan_.launches.size(),
+                                            d_cig_.as<uint32_t>(), dense.as<uint32_t>(), d_count, results, c_->stream, side_, kSide, &rr, &dir_cur);
+            c_->launches += vm_fill_launch(plan_, jobs, d_fpairs, sources(), eqx ? 1 : 0, d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr,
+                                           d_cig_.as<uint32_t>(), dense.as<uint32_t>(), d_count, results, c_->stream, side_, kSide, &rr, &dir_cur,
+                                           &band_cur);
+            side_join();
+            kt.stop();
+        }
+        BE_OK(h_misc_.ensure(256));
+        FillStats *h_stats = h_misc_.as<FillStats>();
+        if (!bplan_.launches.empty()) {
+            // jobs whose certificate failed: once more, in the full-matrix kernel
+            c_->launches += vm_launch_fill_redo_mask(results, nj, d_mask_.as<uint8_t>(), &d_stats->n_redo, c_->stream);
+            BE_OK(cudaMemcpyAsync(h_stats, d_stats, sizeof(FillStats), cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(vm_stream_sync(c_->stream));
+            BE_OK(cudaGetLastError());
+            fill_band_jobs_ += (double)bplanbufs_.table.as<VmFbTable>()->n_live;
+            fill_band_redo_ += (double)h_stats->n_redo;
+            if (h_stats->n_redo) {
+                int nl = vm_fill_plan_dev(jobs, nj, d_mask_.as<uint8_t>(), fplanbufs_, d_fpairs, c_->stream);
+                if (nl < 0) throw std::runtime_error("fill plan: CUDA error");
+                c_->launches += nl;
+                BE_OK(vm_stream_sync(c_->stream));
+                vm_fill_plan_finish(fplanbufs_, sms, plan_);
+                BE_OK(d_dir_.ensure(plan_.dir_words * 4 + 64));
+                BE_OK(d_sc_.ensure(plan_.band_words * 4 + 64));
+                BE_OK(cudaMemsetAsync(d_ctr, 0, 160, c_->stream));
+                KTimer kt(this, "k_fill");
+                int rr = 0;
+                size_t dir_cur = 0, band_cur = 0;
+                c_->launches += vm_fill_launch(plan_, jobs, d_fpairs, sources(), eqx ? 1 : 0, d_dir_.as<uint32_t>(), d_sc_.as<uint32_t>(), d_ctr,
+                                               d_cig_.as<uint32_t>(), dense.as<uint32_t>(), d_count, results, c_->stream, nullptr, 0, &rr, &dir_cur,
+                                               &band_cur);
+                kt.stop();
+            }
+        } else {
+            BE_OK(cudaMemcpyAsync(h_stats, d_stats, sizeof(FillStats), cudaMemcpyDeviceToHost, c_->stream));
+            BE_OK(vm_stream_sync(c_->stream));
+        }
+        fill_cells_ += h_stats->cells;
+        fill_bases_ += h_stats->bases;
+        return dense.as<uint32_t>();
+    }
+
+    bool has_device_extension() const override { return device_extension; }
+
+    // extend_func (+ second pass) for every read of `ids` (the reads that came out of the local stage), on the device
+    bool extend_device(const ReadBatch &b, const std::vector<int32_t> &ids, const std::vector<char> &need_reverse,
+                       const std::vector<int32_t> &mapq, const vmg::Options &opt, std::vector<int32_t> &status, FlatRecords &out) override
+    {
+        if (!device_extension) return false;
+        WallTimer wt(this, "extend_device");
+        const int64_t n = b.n;
+        VmChainState &cs = c_->chain;
+        upload_contig_table();
+        BE_OK(dx_nrev_.ensure((size_t)n * 8 + 64));
+        int32_t *d_nrev = dx_nrev_.as<int32_t>(), *d_mapq = d_nrev + n;
+        std::vector<int32_t> tmp(2 * (size_t)n);
+        for (int64_t r = 0; r < n; ++r) { tmp[(size_t)r] = need_reverse[(size_t)r] ? 1 : 0; tmp[(size_t)(n + r)] = mapq[(size_t)r]; }
+        BE_OK(cudaMemcpyAsync(d_nrev, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));       // tmp is pageable and goes out of scope
+        vmd::BackInput in;
+        in.n_reads = n;
+        in.read_off = read_off_.as<int64_t>();
+        in.reads_fwd = reads_fwd_.as<uint8_t>();
+        in.reads_rc = reads_rc_.as<uint8_t>();
+        in.ref = ih_->ix->dev.ref;
+        in.ctg.start = d_ctg_.as<int64_t>();
+        in.ctg.len = d_ctg_.as<int64_t>() + n_ctg_dev_;
+        in.ctg.n = n_ctg_dev_;
+        in.need_reverse = d_nrev;
+        in.mapq = d_mapq;
+        in.local_cnt = cs.cnt_dev.as<int32_t>();
+        in.xrec = (const vmd::ExtractRec *)lx_.rec.p;
+        in.rrec = (const vmd::RebuildRec *)lx_.al_rec.p;
+        in.al_anc = (const vmd::A32 *)lx_.al_anc.p;
+        in.al_len = lx_.al_len.as<int32_t>();
+        in.NA = (int64_t)lx_.al_n_al;
+        in.NT = (int64_t)lx_.al_n_anc;
+        in.total_bases = b.off[n] - b.off[0];
+        vmd::BackParams p;
+        p.maxdivergence = opt.maxdivergence;
+        p.eqx = opt.eqx; p.hardclip = opt.hardclip; p.nodiscard = opt.nodiscard;
+        if (!back_) back_.reset(new vmd::BackHalf<CudaExec>(exec_));
+        exec_.be = this;
+        vmd::BackResult br;
+        back_->run(in, p, ids, status, br);
+        out.rec_off.swap(br.rec_off);
+        out.recs = br.recs;
+        out.cigar = br.cigar;
+        out.n_rec = br.n_rec;
+        out.n_ops = br.n_ops;
+        for (int k = 0; k < vmd::CT_COUNT; ++k) out.counters[k] = br.counters[k];
+        return true;
+    }
+
+    // contig starts and lengths on the device: [starts | lens]
+    void upload_contig_table()
+    {
+        if (d_ctg_for_ == ih_ && d_ctg_has_len_) return;
+        const std::vector<int64_t> &st = ih_->ctg.start, &ln = ih_->ctg.len;
+        std::vector<int64_t> both(st);
+        both.insert(both.end(), ln.begin(), ln.end());
+        BE_OK(d_ctg_.ensure(both.size() * 8 + 64));
+        BE_OK(cudaMemcpyAsync(d_ctg_.p, both.data(), both.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
+        n_ctg_dev_ = (int)st.size();
+        d_ctg_for_ = ih_;
+        d_ctg_has_len_ = true;
+    }
+
 private:
+    CudaExec exec_{nullptr};
+    std::unique_ptr<vmd::BackHalf<CudaExec>> back_;
+    VmDevBuf dx_nrev_, d_mask_, d_fstats_, d_cigd2_;
+    VmFillPlanBufs bplanbufs_, fplanbufs_;
+    bool d_ctg_has_len_ = false;
     vm_ctx *c_;
     vm_index_handle *ih_;
     VmSeedBufs seed_;

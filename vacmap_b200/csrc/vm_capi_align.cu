@@ -102,6 +102,9 @@ struct vm_job {
     const int64_t *seq_off = nullptr;
     std::vector<int64_t> bounds;
     BatchResult br;
+    // chunks whose records came back as flat arrays (device-resident extension stage): copies owned by the job
+    struct FlatChunk { bool used = false; std::vector<int64_t> rec_off; std::vector<vm_record> recs; std::vector<uint32_t> cigar; };
+    std::vector<FlatChunk> flat;
     std::mutex mu;
     std::condition_variable cv;
     int64_t chunks_left = 0;
@@ -163,6 +166,25 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
         BatchResult sr;
         try {
             drv.align_batch(sb, sr);
+            if (sr.flat) {
+                // the backend's page-locked result buffers are reused by its next chunk: copy out now
+                vm_job::FlatChunk &fc = job->flat[(size_t)ci];
+                fc.used = true;
+                fc.rec_off.swap(sr.fr.rec_off);
+                static_assert(sizeof(vm_record) == sizeof(vmd::Rec), "record layout");
+                fc.recs.resize((size_t)sr.fr.n_rec);
+                fc.cigar.resize((size_t)sr.fr.n_ops);
+                if (sr.fr.n_rec) memcpy(fc.recs.data(), sr.fr.recs, (size_t)sr.fr.n_rec * sizeof(vm_record));
+                if (sr.fr.n_ops) {
+                    // a few large memcpys: shared between the pool's threads
+                    const int64_t parts = std::max<int64_t>(1, std::min<int64_t>(8, sr.fr.n_ops >> 20));
+                    parallel_for(parts, job->threads, [&](int64_t k) {
+                        const int64_t lo = sr.fr.n_ops * k / parts, hi = sr.fr.n_ops * (k + 1) / parts;
+                        memcpy(fc.cigar.data() + lo, sr.fr.cigar + lo, (size_t)(hi - lo) * 4);
+                    }, 1);
+                }
+                for (int64_t i = 0; i < nr; ++i) job->br.status[(size_t)(r0 + i)] = sr.status[(size_t)i];
+            } else
             for (int64_t i = 0; i < nr; ++i) {
                 job->br.records[(size_t)(r0 + i)].swap(sr.records[(size_t)i]);
                 job->br.status[(size_t)(r0 + i)] = sr.status[(size_t)i];
@@ -183,6 +205,19 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
                 try {
                     BatchResult s1;
                     drv.align_batch(one, s1);
+                    if (s1.flat) {
+                        // one read: back to per-read records
+                        std::vector<vmg::Record> &dst = job->br.records[(size_t)(r0 + i)];
+                        dst.clear();
+                        for (int64_t q = 0; q < s1.fr.n_rec; ++q) {
+                            const vmd::Rec &x = s1.fr.recs[q];
+                            vmg::Record rec;
+                            rec.contig = x.contig; rec.strand = x.strand; rec.q_st = x.q_st; rec.q_en = x.q_en; rec.r_st = x.r_st;
+                            rec.r_en = x.r_en; rec.mapq = x.mapq;
+                            rec.cigar.assign(s1.fr.cigar + x.cigar_off, s1.fr.cigar + x.cigar_off + x.cigar_len);
+                            dst.push_back(std::move(rec));
+                        }
+                    } else
                     job->br.records[(size_t)(r0 + i)].swap(s1.records[0]);
                     job->br.status[(size_t)(r0 + i)] = s1.status[0];
                     for (int k = 0; k < BC_COUNT; ++k) wb.timer.add(kBranchName[k], (double)s1.branch[k]);
@@ -316,6 +351,7 @@ int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int
         job->chunks_left = (int64_t)job->bounds.size() - 1;
         job->br.records.assign((size_t)n_reads, {});
         job->br.status.assign((size_t)n_reads, RS_OK);
+        job->flat.assign(job->bounds.size() - 1, vm_job::FlatChunk());
         job->t0 = std::chrono::steady_clock::now();
         if (workers <= 1) {
             // lock-step: the whole batch on the context's own backend, in the calling thread
@@ -357,20 +393,50 @@ int vm_align_wait(vm_job *job, vm_result **out)
     vm_result *res = new vm_result();
     const double total = std::chrono::duration<double, std::milli>(job->t_done - job->t0).count();
     auto t1 = std::chrono::steady_clock::now();
-    // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel
+    // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel.  A read's records are either in
+    // its chunk's flat arrays (device-resident extension stage) or, per read, in br.records (host glue, single-read redo)
+    const int64_t n_chunks = (int64_t)job->bounds.size() - 1;
+    std::vector<int32_t> chunk_of((size_t)n_reads, 0);
+    for (int64_t ci = 0; ci < n_chunks; ++ci)
+        for (int64_t r = job->bounds[(size_t)ci]; r < job->bounds[(size_t)ci + 1]; ++r) chunk_of[(size_t)r] = (int32_t)ci;
+    auto flat_of = [&](int64_t r, int64_t &lo, int64_t &hi) -> const vm_job::FlatChunk * {
+        const vm_job::FlatChunk &fc = job->flat[(size_t)chunk_of[(size_t)r]];
+        if (!fc.used || !br.records[(size_t)r].empty()) return nullptr;
+        const int64_t i = r - job->bounds[(size_t)chunk_of[(size_t)r]];
+        lo = fc.rec_off[(size_t)i]; hi = fc.rec_off[(size_t)i + 1];
+        return &fc;
+    };
     res->rec_off.assign((size_t)n_reads + 1, 0);
     std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
     for (int64_t r = 0; r < n_reads; ++r) {
-        int64_t ops = 0;
-        for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
-        res->rec_off[r + 1] = res->rec_off[r] + (int64_t)br.records[r].size();
+        int64_t ops = 0, nrec = 0, lo = 0, hi = 0;
+        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
+            nrec = hi - lo;
+            if (nrec > 0) ops = fc->recs[(size_t)hi - 1].cigar_off + fc->recs[(size_t)hi - 1].cigar_len - fc->recs[(size_t)lo].cigar_off;
+        } else {
+            for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
+            nrec = (int64_t)br.records[r].size();
+        }
+        res->rec_off[r + 1] = res->rec_off[r] + nrec;
         cig_off[r + 1] = cig_off[r] + ops;
     }
     res->recs.resize((size_t)res->rec_off[n_reads]);
     res->cigar.resize((size_t)cig_off[n_reads]);
     res->status.swap(br.status);
     parallel_for(n_reads, job->threads, [&](int64_t r) {
-        int64_t ri = res->rec_off[r], co = cig_off[r];
+        int64_t ri = res->rec_off[r], co = cig_off[r], lo = 0, hi = 0;
+        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
+            if (hi <= lo) return;
+            // a read's records and CIGARs are contiguous in its chunk's arrays
+            const int64_t c0 = fc->recs[(size_t)lo].cigar_off;
+            for (int64_t q = lo; q < hi; ++q) {
+                vm_record o = fc->recs[(size_t)q];
+                o.cigar_off = co + (o.cigar_off - c0);
+                res->recs[(size_t)ri++] = o;
+            }
+            memcpy(res->cigar.data() + co, fc->cigar.data() + c0, (size_t)(cig_off[r + 1] - co) * 4);
+            return;
+        }
         for (const vmg::Record &rec : br.records[r]) {
             vm_record &o = res->recs[(size_t)ri++];
             o.contig = rec.contig;

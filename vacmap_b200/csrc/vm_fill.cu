@@ -386,3 +386,154 @@ int vm_fill_launch(const VmFillPlan &plan, VmAlnJobDev *jobs, const VmFillPair *
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same plan made on the device (vm_fill_plan above is the host version the stage-level entry points use).
+// ---------------------------------------------------------------------------------------------------------------
+#include "vm_devsort.cuh"
+
+namespace {
+
+constexpr int FF_NCLS = 27, FF_NB = 1024, FF_NKEY = FF_NCLS * FF_NB;
+struct FfSmall { VmFfTable tab; };
+
+__global__ void vm_ffp_key_kernel(const VmAlnJobDev *__restrict__ J, int nj, const uint8_t *__restrict__ only_mask, int32_t *keys, FfSmall *sm)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    const int tl = J[j].t.len, ql = J[j].q.len;
+    int key = -1;
+    if (tl > 0 && ql > 0 && (!only_mask || only_mask[j])) {
+        const int rc = tl <= 512 ? (tl + 63) / 64 : 9;
+        const int qc = ql <= 512 ? 0 : ql <= 4096 ? 1 : 2;
+        const int cls = (rc - 1) * 3 + qc;
+        const int b = qc == 0 ? ql >> 1 : qc == 1 ? ql >> 3 : min(ql >> 8, FF_NB - 1);
+        key = cls * FF_NB + b;
+        atomicMax(&sm->tab.max_q[cls], ql);
+        atomicMax(&sm->tab.max_t[cls], tl);
+    }
+    keys[j] = key;
+}
+
+__global__ void vm_ffp_bounds_kernel(const int32_t *__restrict__ start, FfSmall *sm)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int pb = 0;
+    for (int c = 0; c < FF_NCLS; ++c) {
+        const int n = start[(c + 1) * FF_NB] - start[c * FF_NB];
+        sm->tab.n[c] = n;
+        sm->tab.pair_begin[c] = pb;
+        pb += (n + 1) / 2;
+    }
+    sm->tab.n_live = start[FF_NKEY];
+    sm->tab.n_pairs = pb;
+}
+
+__global__ void vm_ffp_pair_kernel(const VmAlnJobDev *__restrict__ J, int nj, const int32_t *__restrict__ keys, const int32_t *__restrict__ order,
+                                   const int32_t *__restrict__ start, FfSmall *sm, VmFillPair *pairs_out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nj || x >= start[FF_NKEY]) return;
+    const int a = order[x];
+    const int cls = keys[a] / FF_NB;
+    const int lo = start[cls * FF_NB], hi = start[(cls + 1) * FF_NB];
+    const int rel = x - lo;
+    if (rel & 1) return;
+    VmFillPair pr;
+    pr.a = a;
+    pr.b = x + 1 < hi ? order[x + 1] : -1;
+    pairs_out[sm->tab.pair_begin[cls] + rel / 2] = pr;
+    const int rc = cls / 3 + 1;
+    const int tl = max(J[a].t.len, pr.b >= 0 ? J[pr.b].t.len : 0), ql = max(J[a].q.len, pr.b >= 0 ? J[pr.b].q.len : 0);
+    const int rows_pb = 32 * (rc == 9 ? 16 : 2 * rc);
+    atomicAdd(&sm->tab.dir_bytes, (double)((tl + rows_pb - 1) / rows_pb) * (ql + 31) * (rows_pb / 64) * 128.0);
+}
+
+} // namespace
+
+int vm_fill_plan_dev(const VmAlnJobDev *J, int nj, const uint8_t *only_mask, VmFillPlanBufs &B, VmFillPair *pairs_out, cudaStream_t stream)
+{
+    if (nj <= 0) return 0;
+    const size_t n = (size_t)nj;
+    if (B.keys.ensure(n * 4) || B.order.ensure(n * 4) || B.start.ensure(((size_t)FF_NKEY + 1) * 4) || B.cursor.ensure((size_t)FF_NKEY * 4) ||
+        B.small.ensure(sizeof(FfSmall) + 1024) || B.table.ensure(sizeof(VmFbTable) + sizeof(VmFfTable) + 64))
+        return -1;
+    FfSmall *sm = B.small.as<FfSmall>();
+    const int nb = (nj + 127) / 128;
+    cudaMemsetAsync(sm, 0, sizeof(FfSmall), stream);
+    vm_ffp_key_kernel<<<nb, 128, 0, stream>>>(J, nj, only_mask, B.keys.as<int32_t>(), sm);
+    int launches = 1 + vm_bucket_sort(B.keys.as<int32_t>(), nj, FF_NKEY, B.start.as<int32_t>(), B.cursor.as<int32_t>(), B.order.as<int32_t>(), stream);
+    vm_ffp_bounds_kernel<<<1, 32, 0, stream>>>(B.start.as<int32_t>(), sm);
+    vm_ffp_pair_kernel<<<nb, 128, 0, stream>>>(J, nj, B.keys.as<int32_t>(), B.order.as<int32_t>(), B.start.as<int32_t>(), sm, pairs_out);
+    launches += 2;
+    if (cudaMemcpyAsync(B.table.p, &sm->tab, sizeof(VmFfTable), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return -1;
+    return launches;
+}
+
+void vm_fill_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillPlan &plan)
+{
+    plan.pairs.clear();
+    plan.launches.clear();
+    plan.dir_words = plan.band_words = 0;
+    const VmFfTable &T = *B.table.as<VmFfTable>();
+    plan.dir_bytes = T.dir_bytes;
+    const size_t mem_cap_words = (size_t)6 << 28;
+    for (int cls = 0; cls < FF_NCLS; ++cls) {
+        if (T.n[cls] <= 0) continue;
+        const int rc = cls / 3 + 1;
+        VmFillLaunch L;
+        L.multiband = rc == 9;
+        L.R = L.multiband ? 16 : 2 * rc;
+        L.pair_begin = T.pair_begin[cls];
+        L.pair_end = T.pair_begin[cls] + (T.n[cls] + 1) / 2;
+        const int rows = 32 * L.R;
+        const long long nbands = L.multiband ? (T.max_t[cls] + rows - 1) / rows : 1;
+        L.dir_words_per_warp = nbands * ((long long)T.max_q[cls] + 32) * (L.R / 2) * 32;
+        L.band_words_per_warp = L.multiband ? 3LL * T.max_q[cls] + 32 : 0;
+        const int n_pairs = L.pair_end - L.pair_begin;
+        long long blocks = std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0));
+        const long long fit = (long long)(mem_cap_words / (size_t)(4 * L.dir_words_per_warp));
+        blocks = std::max<long long>(1, std::min(blocks, std::max<long long>(fit, 1)));
+        L.blocks = (int)blocks;
+        plan.dir_words += (size_t)(blocks * 4 * L.dir_words_per_warp);
+        plan.band_words += (size_t)(blocks * 4 * L.band_words_per_warp);
+        plan.launches.push_back(L);
+    }
+}
+
+namespace {
+
+__global__ void vm_fill_stats_kernel(const VmAlnJobDev *__restrict__ J, int nj, double *cells, double *bases)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    double c = 0, b = 0;
+    if (j < nj && J[j].t.len > 0 && J[j].q.len > 0) { c = (double)J[j].t.len * (double)J[j].q.len; b = (double)J[j].t.len + (double)J[j].q.len; }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) { c += __shfl_xor_sync(VM_FULL, c, d); b += __shfl_xor_sync(VM_FULL, b, d); }
+    if ((threadIdx.x & 31) == 0 && c > 0) { atomicAdd(cells, c); atomicAdd(bases, b); }
+}
+
+__global__ void vm_fill_redo_mask_kernel(const uint2 *__restrict__ results, int nj, uint8_t *mask, unsigned long long *count)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    const bool redo = results[j].x == 0xffffffffu;
+    mask[j] = redo ? 1 : 0;
+    if (redo) atomicAdd(count, 1ULL);
+}
+
+} // namespace
+
+int vm_launch_fill_stats(const VmAlnJobDev *jobs, int nj, double *cells, double *bases, cudaStream_t stream)
+{
+    if (nj <= 0) return 0;
+    vm_fill_stats_kernel<<<(nj + 255) / 256, 256, 0, stream>>>(jobs, nj, cells, bases);
+    return 1;
+}
+
+int vm_launch_fill_redo_mask(const void *results, int nj, uint8_t *mask, unsigned long long *count, cudaStream_t stream)
+{
+    if (nj <= 0) return 0;
+    vm_fill_redo_mask_kernel<<<(nj + 255) / 256, 256, 0, stream>>>((const uint2 *)results, nj, mask, count);
+    return 1;
+}

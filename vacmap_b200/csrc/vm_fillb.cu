@@ -532,3 +532,189 @@ int vm_fillb_launch(const VmFillBandPlan &plan, VmAlnJobDev *jobs, const VmFillB
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// The same plan made on the device (vm_fillb_plan above is the host version the stage-level entry points use).
+// ---------------------------------------------------------------------------------------------------------------
+#include "vm_devsort.cuh"
+
+namespace {
+
+constexpr int FB_ND = 256, FB_NQ = VM_FB_CAP / 8 + 1, FB_NKEY = VM_FB_NCLASS * FB_ND * FB_NQ;
+constexpr int FB_NB2 = 4096, FB_NKEY2 = (VM_FB_NCLASS + 1) * FB_NB2;
+
+__host__ __device__ inline int fb_rows_d(int k)
+{
+    const int G = k <= 4 ? 4 : k <= 6 ? 2 : 1;
+    const int C = k == 1 ? 4 : k == 2 ? 6 : k == 3 ? 7 : k == 4 ? 8 : k == 5 ? 5 : k == 6 ? 6 : k - 4;      // 7..12 -> 3..8
+    return 32 / G * C;
+}
+__host__ __device__ inline int fb_cap_d(int k) { return k <= 4 ? VM_FB_CAP4 : k <= 6 ? VM_FB_CAP2 : VM_FB_CAP; }
+__host__ __device__ inline int fb_class_of_d(int rows, int mx)
+{
+    for (int k = 1; k <= VM_FB_NCLASS; ++k)
+        if (rows <= fb_rows_d(k) && mx <= fb_cap_d(k)) return k;
+    return 0;
+}
+__device__ inline bool fb_own_band_d(int tlen, int qlen, int &kmin, int &kmax)
+{
+    const int mn = tlen < qlen ? tlen : qlen, mx = tlen > qlen ? tlen : qlen;
+    if (mn < 96 || mx > VM_FB_CAP) return false;
+    const int D = qlen - tlen;
+    int w = (int)(0.2125 * mn) - 12;
+    if (w < 24) w = 24;
+    kmin = (D < 0 ? D : 0) - w;
+    kmax = (D > 0 ? D : 0) + w;
+    return fb_class_of_d((kmax - kmin) / 2 + 1, mx) > 0;
+}
+
+struct FbSmall { int32_t class_lo[16], pair_lo[16]; VmFbTable tab; };
+
+__global__ void vm_fbp_key_kernel(const VmAlnJobDev *__restrict__ J, int nj, int32_t *keys, int32_t *bmin, int32_t *bmax, uint8_t *full_mask)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nj) return;
+    const int tl = J[j].t.len, ql = J[j].q.len;
+    int key = -1;
+    uint8_t full = 0;
+    if (tl > 0 && ql > 0) {
+        int kmin, kmax;
+        if (fb_own_band_d(tl, ql, kmin, kmax)) {
+            bmin[j] = kmin;
+            bmax[j] = kmax;
+            const int c = fb_class_of_d((kmax - kmin) / 2 + 1, tl > ql ? tl : ql);
+            int db = ((ql - tl) >> 3) + FB_ND / 2;
+            db = db < 0 ? 0 : db >= FB_ND ? FB_ND - 1 : db;
+            key = ((c - 1) * FB_ND + db) * FB_NQ + (ql >> 3);
+        } else full = 1;
+    }
+    keys[j] = key;
+    full_mask[j] = full;
+}
+
+__global__ void vm_fbp_bounds_kernel(const int32_t *__restrict__ start, FbSmall *sm)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) sm->class_lo[c] = start[(c - 1) * FB_ND * FB_NQ];
+    sm->class_lo[VM_FB_NCLASS + 1] = start[FB_NKEY];
+    sm->pair_lo[1] = 0;
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) {
+        const int n = sm->class_lo[c + 1] - sm->class_lo[c];
+        sm->pair_lo[c + 1] = sm->pair_lo[c] + (c < VM_FB_NCLASS ? (n + 1) / 2 : n);
+    }
+    for (int c = 0; c < 16; ++c) { sm->tab.cnt[c] = 0; sm->tab.at[c] = 0; sm->tab.max_steps[c] = 0; sm->tab.sum_steps[c] = 0ULL; }
+    sm->tab.n_live = sm->class_lo[VM_FB_NCLASS + 1];
+    sm->tab.n_pairs = 0;
+}
+
+// neighbours of the same slot class share a warp; a pair's band is the union of its jobs' bands, widened to the capacity
+// of the union's slot class
+__global__ void vm_fbp_pair_kernel(const VmAlnJobDev *__restrict__ J, int n_slots_max, const int32_t *__restrict__ order,
+                                   const int32_t *__restrict__ bmin, const int32_t *__restrict__ bmax, FbSmall *sm, VmFillBandPair *tpairs,
+                                   int32_t *keys2, uint8_t *full_mask)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_slots_max) return;
+    const int n_slots = sm->pair_lo[VM_FB_NCLASS + 1];
+    if (p >= n_slots) { keys2[p] = -1; return; }
+    int c = 1;
+    while (c < VM_FB_NCLASS && p >= sm->pair_lo[c + 1]) ++c;
+    const int lo = sm->class_lo[c], hi = sm->class_lo[c + 1];
+    const bool alone = c == VM_FB_NCLASS;
+    const int rel = p - sm->pair_lo[c];
+    const int xa = alone ? lo + rel : lo + 2 * rel, xb = alone ? hi : xa + 1;
+    VmFillBandPair pr;
+    pr.a = order[xa];
+    pr.b = xb < hi ? order[xb] : -1;
+    pr.kmin = bmin[pr.a];
+    pr.kmax = bmax[pr.a];
+    int steps = J[pr.a].t.len + J[pr.a].q.len;
+    int mx = max(J[pr.a].t.len, J[pr.a].q.len);
+    if (pr.b >= 0) {
+        mx = max(mx, max(J[pr.b].t.len, J[pr.b].q.len));
+        pr.kmin = min(pr.kmin, bmin[pr.b]);
+        pr.kmax = max(pr.kmax, bmax[pr.b]);
+        steps = max(J[pr.a].t.len, J[pr.b].t.len) + max(J[pr.a].q.len, J[pr.b].q.len);
+    }
+    const int rows = (pr.kmax - pr.kmin) / 2 + 1;
+    const int tc = fb_class_of_d(rows, mx);
+    if (tc == 0) {      // cannot happen for neighbours of one bucket; if it does, the full-matrix kernel takes them
+        full_mask[pr.a] = 1;
+        if (pr.b >= 0) full_mask[pr.b] = 1;
+        keys2[p] = -1;
+        return;
+    }
+    const int spare = fb_rows_d(tc) - rows;
+    pr.kmin -= spare;
+    pr.kmax += spare;
+    tpairs[p] = pr;
+    // second bucket sort: by the union's class, then coarsely by position so that neighbours stay neighbours
+    keys2[p] = tc * FB_NB2 + (int)((long long)p * FB_NB2 / n_slots);
+    atomicMax(&sm->tab.max_steps[tc], steps);
+    atomicAdd(&sm->tab.sum_steps[tc], (unsigned long long)steps);
+}
+
+__global__ void vm_fbp_place_kernel(int n_slots_max, const int32_t *__restrict__ order2, const int32_t *__restrict__ start2,
+                                    const VmFillBandPair *__restrict__ tpairs, VmFillBandPair *pairs_out, FbSmall *sm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = start2[FB_NKEY2];
+    if (i == 0) {
+        for (int c = 1; c <= VM_FB_NCLASS; ++c) {
+            sm->tab.at[c] = start2[c * FB_NB2];
+            sm->tab.cnt[c] = start2[(c + 1) * FB_NB2] - start2[c * FB_NB2];
+        }
+        sm->tab.n_pairs = n;
+    }
+    if (i >= n_slots_max || i >= n) return;
+    pairs_out[i] = tpairs[order2[i]];
+}
+
+} // namespace
+
+int vm_fillb_plan_dev(const VmAlnJobDev *J, int nj, VmFillPlanBufs &B, VmFillBandPair *pairs_out, uint8_t *full_mask, cudaStream_t stream)
+{
+    if (nj <= 0) return 0;
+    const size_t n = (size_t)nj;
+    if (B.keys.ensure(n * 4) || B.bmin.ensure(n * 4) || B.bmax.ensure(n * 4) || B.order.ensure(n * 4) || B.tpairs.ensure(n * sizeof(VmFillBandPair)) ||
+        B.keys2.ensure(n * 4) || B.order2.ensure(n * 4) || B.start.ensure(((size_t)FB_NKEY + 1) * 4) || B.cursor.ensure((size_t)FB_NKEY * 4) ||
+        B.start2.ensure(((size_t)FB_NKEY2 + 1) * 4) || B.cursor2.ensure((size_t)FB_NKEY2 * 4) || B.small.ensure(sizeof(FbSmall) + 1024) ||
+        B.table.ensure(sizeof(VmFbTable) + sizeof(VmFfTable) + 64))
+        return -1;
+    int launches = 0;
+    const int nb = (nj + 127) / 128;
+    FbSmall *sm = B.small.as<FbSmall>();
+    vm_fbp_key_kernel<<<nb, 128, 0, stream>>>(J, nj, B.keys.as<int32_t>(), B.bmin.as<int32_t>(), B.bmax.as<int32_t>(), full_mask);
+    launches += 1 + vm_bucket_sort(B.keys.as<int32_t>(), nj, FB_NKEY, B.start.as<int32_t>(), B.cursor.as<int32_t>(), B.order.as<int32_t>(), stream);
+    vm_fbp_bounds_kernel<<<1, 32, 0, stream>>>(B.start.as<int32_t>(), sm);
+    vm_fbp_pair_kernel<<<nb, 128, 0, stream>>>(J, nj, B.order.as<int32_t>(), B.bmin.as<int32_t>(), B.bmax.as<int32_t>(), sm,
+                                               B.tpairs.as<VmFillBandPair>(), B.keys2.as<int32_t>(), full_mask);
+    launches += 2 + vm_bucket_sort(B.keys2.as<int32_t>(), nj, FB_NKEY2, B.start2.as<int32_t>(), B.cursor2.as<int32_t>(), B.order2.as<int32_t>(), stream);
+    vm_fbp_place_kernel<<<nb, 128, 0, stream>>>(nj, B.order2.as<int32_t>(), B.start2.as<int32_t>(), B.tpairs.as<VmFillBandPair>(), pairs_out, sm);
+    ++launches;
+    if (cudaMemcpyAsync(B.table.p, &sm->tab, sizeof(VmFbTable), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return -1;
+    return launches;
+}
+
+void vm_fillb_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillBandPlan &plan)
+{
+    plan.pairs.clear();
+    plan.launches.clear();
+    plan.dir_words = 0;
+    plan.dir_bytes = 0;
+    const VmFbTable &T = *B.table.as<VmFbTable>();
+    for (int c = 1; c <= VM_FB_NCLASS; ++c) {
+        if (T.cnt[c] <= 0) continue;
+        plan.dir_bytes += (double)T.sum_steps[c] * ((VM_FB_CLASS[c].C + 1) / 2) * 128.0 / VM_FB_CLASS[c].G;
+        VmFillBandLaunch L;
+        L.cls = c;
+        L.pair_begin = T.at[c];
+        L.pair_end = T.at[c] + T.cnt[c];
+        L.dir_words_per_warp = (long long)T.max_steps[c] * ((VM_FB_CLASS[c].C + 1) / 2) * 32;
+        const int n_pairs = T.cnt[c];
+        const int per_block = 4 * VM_FB_CLASS[c].G;
+        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + per_block - 1) / per_block, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
+        plan.dir_words += (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp);
+        plan.launches.push_back(L);
+    }
+}

@@ -7,6 +7,7 @@
 // (tests/gluetest); the product only ever instantiates the CUDA backend (vm_backend_cuda.cu).
 #pragma once
 #include "vm_glue.hpp"
+#include "vm_dglue.hpp"
 #include "vm_hostpool.hpp"
 #include <atomic>
 #include <condition_variable>
@@ -92,6 +93,16 @@ struct ExtJobRef { int32_t read; vmg::ExtJob job; };
 // CIGAR ops of a fill job: cig[cig_off .. cig_off + cig_len) of the array Backend::fill hands back
 struct FillJobRef { int32_t read; vmg::FillJob job; int64_t cig_off = 0; int32_t cig_len = 0; };
 
+// Records of a chunk as flat arrays (what a backend that runs the extension stage itself hands back): recs / cigar
+// point into backend-owned host memory, valid until the backend's next extend_device call.
+struct FlatRecords {
+    std::vector<int64_t> rec_off;          // [n_reads + 1]
+    const vmd::Rec *recs = nullptr;        // == vm_record; cigar_off counts inside `cigar`
+    const uint32_t *cigar = nullptr;
+    int64_t n_rec = 0, n_ops = 0;
+    int64_t counters[vmd::CT_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 // The hot loops.  Every method processes the jobs of a whole batch; consecutive hot loops whose
 // hand-over needs no host decision are fused so the data never leaves the device in between.
 struct Backend {
@@ -113,6 +124,16 @@ struct Backend {
     virtual void extend(const ReadBatch &b, std::vector<ExtJobRef> &jobs) = 0;
     // sets cig_off / cig_len of every job; the returned array stays valid until the next fill()
     virtual const uint32_t *fill(const ReadBatch &b, bool eqx, std::vector<FillJobRef> &jobs) = 0;
+    // Optional: the whole of extend_func (:19238-19303) and the second pass (:24079-24080) for the reads `ids` that came
+    // out of reseed_chain, on the backend's side (nothing of the local stage has to visit the host then).  status: per
+    // read, in / out (ReadStatus).  false: not supported, the driver runs the host glue.
+    virtual bool extend_device(const ReadBatch &b, const std::vector<int32_t> &ids, const std::vector<char> &need_reverse,
+                               const std::vector<int32_t> &mapq, const vmg::Options &opt, std::vector<int32_t> &status, FlatRecords &out)
+    {
+        (void)b; (void)ids; (void)need_reverse; (void)mapq; (void)opt; (void)status; (void)out;
+        return false;
+    }
+    virtual bool has_device_extension() const { return false; }
 };
 
 // Thread time spent in the parts of the host glue, summed over the pool's threads ("t_<name>" stage entries):
@@ -170,6 +191,8 @@ static const char *const kBranchName[BC_COUNT] = {"c_fast_global", "c_mismatch_d
                                                   "c_merge_conjacent", "c_fix_simple_inv", "c_second_pass"};
 
 struct BatchResult {
+    bool flat = false;                               // true: the records are in `fr` (flat arrays), `records` is unused
+    FlatRecords fr;
     std::vector<std::vector<vmg::Record>> records;   // per read, in the reference's emission order
     std::vector<int32_t> status;                     // ReadStatus per read
     int64_t branch[BC_COUNT] = {0, 0, 0, 0, 0, 0, 0};
@@ -276,6 +299,30 @@ public:
         ChainOut lc;
         be_.reseed_chain(b, need_rev, all_gjobs, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
         lc_ = &lc;
+        if (be_.has_device_extension()) {
+            // ---- 6'. extend_func and the second pass with their glue on the device: the host only launches ----
+            std::vector<int32_t> ids, mapq((size_t)n, 0);
+            for (int64_t r = 0; r < n; ++r)
+                if (st[r].alive) { ids.push_back((int32_t)r); mapq[(size_t)r] = st[r].mapq; }
+            for (int64_t r = 0; r < n; ++r)
+                if (!lc.used_fast.empty() && lc.used_fast[r]) bc_[BC_FAST_LOCAL].fetch_add(1, std::memory_order_relaxed);
+            if (be_.extend_device(b, ids, need_rev, mapq, opt_, res.status, res.fr)) {
+                res.flat = true;
+                res.records.clear();
+                lc_ = nullptr;
+                bc_[BC_DROP_MISPLACED].fetch_add(res.fr.counters[vmd::CT_DROP_MISPLACED]);
+                bc_[BC_MERGE_CONJACENT].fetch_add(res.fr.counters[vmd::CT_MERGE_CONJACENT]);
+                bc_[BC_FIX_SIMPLE_INV].fetch_add(res.fr.counters[vmd::CT_FIX_SIMPLE_INV]);
+                bc_[BC_SECOND_PASS].fetch_add(res.fr.counters[vmd::CT_SECOND_PASS]);
+                if (on_time)
+                    for (int p = 0; p < SP_COUNT; ++p) on_time(kSubPartName[p], 1e-6 * (double)sub_.ns[p].exchange(0));
+                Phase p2(this, "g_finish");
+                parallel_for(n, threads_, [&](int64_t r) { st[r] = ReadState(); }, 64);
+                st.clear();
+                for (int i = 0; i < BC_COUNT; ++i) res.branch[i] = bc_[i].load();
+                return;
+            }
+        }
 
         // ---- 6. traceback, then extend_func as a staged state machine ----
         ph = new Phase(this, "g_traceback");

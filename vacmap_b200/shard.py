@@ -48,56 +48,89 @@ def broadcast_bytes(payload, src=0):
 
 
 def broadcast_reference(ref, src=0):
-    """ref = [(name, sequence)] on `src` (anything elsewhere) -> the same list on every rank."""
+    """ref = [(name, sequence)] on `src` (anything elsewhere) -> the same list on every rank.  The sequences travel as
+    one uint8 tensor (no Python string joins of a multi-gigabase reference); see `broadcast_index` for shipping the
+    BUILT index instead."""
     if dist.get_rank() == src:
         names = "\n".join(n for n, _ in ref).encode()
-        lens = np.array([len(s) for _, s in ref], dtype=np.int64).tobytes()
-        seqs = "".join(s for _, s in ref).encode()
+        lens = np.array([len(s) for _, s in ref], dtype=np.int64)
+        cat = np.empty(int(lens.sum()), dtype=np.uint8)
+        o = 0
+        for (_, sq), ln in zip(ref, lens):
+            cat[o:o + ln] = np.frombuffer(sq.encode() if isinstance(sq, str) else sq, dtype=np.uint8)
+            o += int(ln)
     else:
-        names = lens = seqs = b""
+        names, lens, cat = b"", np.zeros(0, np.int64), np.zeros(0, np.uint8)
     names = broadcast_bytes(names, src).decode().split("\n")
-    lens = np.frombuffer(broadcast_bytes(lens, src), dtype=np.int64)
-    seqs = broadcast_bytes(seqs, src).decode()
+    lens = np.frombuffer(broadcast_bytes(lens.tobytes(), src), dtype=np.int64)
+    cat = broadcast_array(cat, src)
     out, o = [], 0
     for n, ln in zip(names, lens):
-        out.append((n, seqs[o:o + int(ln)]))
+        out.append((n, cat[o:o + int(ln)].tobytes().decode()))
         o += int(ln)
     return out
 
 
-def _gather_array(arr, dst):
-    """Variable-length gather of a 1-D contiguous array (as bytes) on `dst`: list of per-rank arrays there, None elsewhere."""
+def broadcast_array(arr, src=0):
+    """Broadcast a 1-D numpy array (dtype known on every rank from `arr.dtype`) from `src`; returns the array."""
     dev = _device()
-    world, rank = dist.get_world_size(), dist.get_rank()
-    raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([raw.size], dtype=torch.int64, device=dev))
-    sizes = [int(s.item()) for s in sizes]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    if raw.size:
-        pad[:raw.size] = torch.from_numpy(raw.copy()).to(dev)
-    bufs = [torch.zeros(mx, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst)
-    if rank != dst:
-        return None
-    return [b[:sz].cpu().numpy().view(arr.dtype) for b, sz in zip(bufs, sizes)]
+    rank = dist.get_rank()
+    n = torch.tensor([arr.size if rank == src else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src=src)
+    if rank == src:
+        buf = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
+    else:
+        buf = torch.empty(int(n.item()) * arr.dtype.itemsize, dtype=torch.uint8, device=dev)
+    dist.broadcast(buf, src=src)
+    return arr if rank == src else buf.cpu().numpy().view(arr.dtype)
 
 
 def gather_records(rec_off, recs, cig, dst=0):
     """Per-rank results of `Aligner.align_packed` for the rank's block of reads -> on `dst`, the results of the whole
-    super-batch in global read order (rec_off over all reads, records with cigar_off rebased, one CIGAR arena)."""
-    parts = [_gather_array(np.diff(rec_off).astype(np.int64), dst), _gather_array(recs, dst), _gather_array(cig, dst)]
-    if dist.get_rank() != dst:
+    super-batch in global read order (rec_off over all reads, records with cigar_off rebased, one CIGAR arena).
+    One all_gather of the three sizes, then every rank's arrays go straight into their slices of the destination's
+    buffers (unpadded point-to-point sends; nothing is padded to the largest rank)."""
+    dev = _device()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = np.diff(rec_off).astype(np.int64)
+    mine = [np.ascontiguousarray(counts).view(np.uint8).reshape(-1), np.ascontiguousarray(recs).view(np.uint8).reshape(-1),
+            np.ascontiguousarray(cig).view(np.uint8).reshape(-1)]
+    sizes = torch.zeros((world, 3), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, torch.tensor([[a.size for a in mine]], dtype=torch.int64, device=dev))
+    sizes = sizes.cpu().numpy()
+    if rank != dst:
+        ops = []
+        for a in mine:
+            if a.size:
+                ops.append(dist.P2POp(dist.isend, torch.from_numpy(a).to(dev, non_blocking=True), dst))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
         return None
-    counts, rec_parts, cig_parts = parts
-    # rebase CIGAR offsets rank by rank
-    out_recs, shift = [], 0
-    for r, c in zip(rec_parts, cig_parts):
-        r = r.copy()
-        r["cigar_off"] += shift
-        shift += len(c)
-        out_recs.append(r)
-    all_counts = np.concatenate(counts) if counts else np.zeros(0, np.int64)
+    total = sizes.sum(axis=0)
+    bufs = [torch.empty(int(total[k]), dtype=torch.uint8, device=dev) for k in range(3)]
+    start = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(sizes, axis=0)])
+    ops = []
+    for r in range(world):
+        for k in range(3):
+            n = int(sizes[r, k])
+            if n == 0:
+                continue
+            sl = bufs[k][int(start[r, k]):int(start[r, k]) + n]
+            if r == dst:
+                sl.copy_(torch.from_numpy(mine[k]).to(dev, non_blocking=True))
+            else:
+                ops.append(dist.P2POp(dist.irecv, sl, r))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    all_counts = bufs[0].cpu().numpy().view(np.int64)
+    out_recs = bufs[1].cpu().numpy().view(recs.dtype).copy()
+    out_cig = bufs[2].cpu().numpy().view(cig.dtype)
+    # rebase the CIGAR offsets rank by rank
+    rec_start = start[:, 1] // max(recs.dtype.itemsize, 1)
+    cig_start = start[:, 2] // max(cig.dtype.itemsize, 1)
+    for r in range(world):
+        out_recs["cigar_off"][int(rec_start[r]):int(rec_start[r + 1])] += int(cig_start[r])
     off = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
-    return off, np.concatenate(out_recs), np.concatenate(cig_parts)
+    return off, out_recs, out_cig
