@@ -527,8 +527,9 @@ public:
         for (int j = 0; j < nj; ++j) {
             J[j].dense_off = dense_hits;
             dense_hits += n_hits[j];
-            int ts = 64;
-            while (ts < n_hits[j] + 8) ts <<= 1;
+            // the merge kernel gives every lane a 32nd of the table: at most a quarter full on average
+            int ts = 2048;
+            while (ts < 2 * (n_hits[j] + 8)) ts <<= 1;
             J[j].tab_off = tab_off;
             J[j].tab_size = ts;
             tab_off += ts;

@@ -333,11 +333,13 @@ int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int
         CudaBackend &be = *(CudaBackend *)c->backend;
         be.set_index(h);
         be.reads_resident = resident != 0;
-        // `workers` = size of the pool; a job is cut into equal chunks of ~chunk_reads (default: a sixth of the job, at
-        // least 512 reads -- every chunk pays the same fixed chain of launch and synchronisation latencies, so fewer,
-        // larger chunks win).  With more workers than chunks per job, the chunks of the next job run beside them.
-        int workers = p->workers > 0 ? p->workers : 8;
-        const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 5) / 6);
+        // `workers` = size of the pool; a job is cut into equal chunks of ~chunk_reads (default: half of the job, at
+        // least 512 reads -- every chunk pays the same fixed chain of launch and synchronisation latencies, and with the
+        // extension stage's glue on the device the host no longer needs many small chunks to keep its cores busy:
+        // measured 93 ms per 10k-read step with 3 workers x 5000 reads, 104 ms with 8 x 1667).  With more workers than
+        // chunks per job, the chunks of the next job run beside them.
+        int workers = p->workers > 0 ? p->workers : 4;
+        const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 1) / 2);
         if (n_reads <= chunk || workers == 1) workers = 1;
         job->bounds.assign(1, 0);
         if (workers > 1) {

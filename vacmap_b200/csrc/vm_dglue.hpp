@@ -718,3 +718,411 @@ VM_HD int64_t write_record(const ReadCtx &rc, const Fin &f, int mapq, const U2 *
 }
 
 } // namespace vmd
+
+// ===============================================================================================================
+// Front half: what hit2work_1 does after its DP (:23581-23734: chain grouping, MAPQ inputs, secondary chains),
+// guide-chain selection (merge_chain / drop_somechains / sort, :28482-28582) and the inputs of the re-seeding
+// kernel for every guide chain (:23090-23191: windows, guide points) -- for one read, from the chains the
+// extraction kernel left in HBM.  vm_glue.hpp::hit2work_extracted / select_guides / make_guide_job are the
+// vector-based host versions of the same.
+// ===============================================================================================================
+namespace vmd {
+
+// numba's argsort (numba/misc/quicksort.py) replayed on R[0..n): the permutation, ties and all.
+template <typename K>
+VM_HD void argsort_replay(const K *A, int32_t n, int32_t *R)
+{
+    for (int32_t t = 0; t < n; ++t) R[t] = t;
+    if (n < 2) return;
+    {
+        bool asc = true, desc = true;
+        for (int32_t t = 1; t < n && (asc || desc); ++t) {
+            if (!(A[t - 1] < A[t])) asc = false;
+            if (!(A[t] < A[t - 1])) desc = false;
+        }
+        if (asc) return;
+        if (desc) { for (int32_t t = 0; t < n / 2; ++t) { const int32_t x = R[t]; R[t] = R[n - 1 - t]; R[n - 1 - t] = x; } return; }
+    }
+    int32_t slo[64], shi[64];
+    int sp = 1;
+    slo[0] = 0; shi[0] = n - 1;
+    while (sp > 0) {
+        --sp;
+        int32_t low = slo[sp], high = shi[sp];
+        while (high - low >= 15) {
+            const int32_t mid = (low + high) >> 1;
+            int32_t x;
+            if (A[R[mid]] < A[R[low]]) { x = R[low]; R[low] = R[mid]; R[mid] = x; }
+            if (A[R[high]] < A[R[mid]]) { x = R[high]; R[high] = R[mid]; R[mid] = x; }
+            if (A[R[mid]] < A[R[low]]) { x = R[low]; R[low] = R[mid]; R[mid] = x; }
+            const K pivot = A[R[mid]];
+            x = R[high]; R[high] = R[mid]; R[mid] = x;
+            int32_t i = low, j = high - 1;
+            for (;;) {
+                while (i < high && A[R[i]] < pivot) ++i;
+                while (j >= low && pivot < A[R[j]]) --j;
+                if (i >= j) break;
+                x = R[i]; R[i] = R[j]; R[j] = x;
+                ++i; --j;
+            }
+            x = R[i]; R[i] = R[high]; R[high] = x;
+            if (high - i > i - low) {
+                if (high > i) { slo[sp] = i + 1; shi[sp] = high; ++sp; }
+                high = i - 1;
+            } else {
+                if (i > low) { slo[sp] = low; shi[sp] = i - 1; ++sp; }
+                low = i + 1;
+            }
+        }
+        for (int32_t i = low + 1; i <= high; ++i) {
+            const int32_t k = R[i];
+            const K v = A[k];
+            int32_t j = i;
+            while (j > low && v < A[R[j - 1]]) { R[j] = R[j - 1]; --j; }
+            R[j] = k;
+        }
+    }
+}
+
+// == VmReseedJobDev
+struct RJob {
+    int32_t read, need_reverse, readstart, readend, n_win, n_guide;
+    int64_t win_off, g_off, hit_off;
+    int32_t hit_cap, pad0;
+    int64_t dense_off, tab_off;
+    int32_t tab_size, pad;
+};
+
+struct FrontOut {
+    int32_t status;        // ST_OK: the read goes on to the local stage
+    int32_t n_guides;      // guide chains after merge_chain / drop_somechains (> 1: the multi-chain local DP)
+    int32_t n_jobs;        // of them re-seeded (the mode's cap)
+    int32_t pad;
+    double f1, f2, m;      // MAPQ inputs (:23697-23704); the host takes the logarithm (libm, as numba does)
+};
+
+// per-read scratch, every pointer already offset to the read's slice
+struct FrontScratch {
+    // sized by the read's extracted chains (nc)
+    int32_t *order, *coff /* nc + 1 */, *pstart /* nc + 1 */, *rest, *head, *tail, *nxt, *size, *cseg, *cpos, *cflat, *sc0, *sc1, *ordc;
+    int64_t *dist, *k64c;
+    double *kd;
+    // sized by the read's extracted anchors (na)
+    int32_t *bins, *cur, *orda;
+    int64_t *k64a;
+    Anc *tmp;
+};
+
+// a (possibly merged) guide chain = original chains linked head -> nxt -> ... -> tail, each in descending read order
+struct ChainView {
+    const A32 *anc;            // the read's extracted anchors
+    const int32_t *coff, *nxt;
+    VM_HD Anc front(const int32_t *head, int c) const { return widen(anc[coff[head[c]]]); }
+    VM_HD Anc back(const int32_t *tail, int c) const { return widen(anc[coff[tail[c] + 1] - 1]); }
+};
+
+// anchor number `idx` of the chain starting at original chain `seg` -- sequential cursor
+struct Cursor {
+    int32_t seg, pos;          // original chain, offset inside it
+};
+
+VM_HD int64_t front_read(const ReadCtx &rc, const ExtractRec &xr, const A32 *anc_all, const double *S_all, const int32_t *len_all,
+                         const double *score_all, int max_guides, int kmer, const FrontScratch &W, RJob *jobs, int64_t *wlo, int64_t *whi,
+                         int32_t *gx, int64_t *gy, int64_t g_base, int64_t w_base, FrontOut &out)
+{
+    out.status = ST_LOW_SCORE; out.n_guides = 0; out.n_jobs = 0; out.pad = 0; out.f1 = 0; out.f2 = 0; out.m = 0;
+    const int nc = xr.n_chains;
+    if (nc <= 0) return 0;
+    const A32 *anc = anc_all + xr.anc_off;
+    const double *S_prim = S_all + xr.anc_off;
+    const int32_t *len = len_all + xr.meta_off;
+    const double *score = score_all + xr.meta_off;
+    int32_t *coff = W.coff;
+    coff[0] = 0;
+    for (int c = 0; c < nc; ++c) coff[c + 1] = coff[c] + len[c];
+    // ---- order of the chains: descending score, the primary chain first (:23655-23662) ----
+    int32_t *order = W.order;
+    argsort_replay<double>(score, nc, order);
+    for (int t = 0; t < nc / 2; ++t) { const int32_t x = order[t]; order[t] = order[nc - 1 - t]; order[nc - 1 - t] = x; }
+    if (order[0] != 0)
+        for (int i = 0; i < nc; ++i)
+            if (order[i] == 0) { order[i] = order[0]; order[0] = 0; break; }
+    // ---- grouping by 100-bp read-bin overlap (:23672-23694): only the second score of the primary group is used ----
+    // bin set of chain c: its anchors walked backwards (ascending read position)
+    int32_t *bins = W.bins, *pstart = W.pstart, *cur = W.cur;
+    int n_sets = 0;
+    double f2 = 0.0;
+    bool have_f2 = false;
+    auto binset = [&](int c, int32_t *dst) -> int {
+        int n = 0;
+        bool sorted = true;
+        for (int t = coff[c + 1] - 1; t >= coff[c]; --t) {
+            const int32_t b = anc[t].x / 100;
+            if (n > 0 && b < dst[n - 1]) sorted = false;
+            if (n == 0 || b != dst[n - 1]) dst[n++] = b;
+        }
+        if (!sorted) {          // never for chains out of the DP (strictly descending read positions); kept for safety
+            for (int i = 1; i < n; ++i) { const int32_t v = dst[i]; int j = i; while (j > 0 && dst[j - 1] > v) { dst[j] = dst[j - 1]; --j; } dst[j] = v; }
+            int u = 0;
+            for (int i = 0; i < n; ++i) if (u == 0 || dst[i] != dst[u - 1]) dst[u++] = dst[i];
+            n = u;
+        }
+        return n;
+    };
+    pstart[0] = 0;
+    if (nc > 1) pstart[1] = binset(order[0], bins);
+    else pstart[1] = 0;
+    n_sets = 1;
+    for (int oi = 1; oi < nc; ++oi) {
+        const int c = order[oi];
+        const int nb = binset(c, cur);
+        double best = 0.0;
+        int pref = 0;
+        for (int p = 0; p < n_sets; ++p) {
+            const int32_t *ps = bins + pstart[p];
+            const int np = pstart[p + 1] - pstart[p];
+            int inter = 0;
+            if (nb > 0 && np > 0 && cur[0] <= ps[np - 1] && ps[0] <= cur[nb - 1]) {
+                int i = 0, j = 0;
+                while (i < nb && j < np) {
+                    if (cur[i] < ps[j]) ++i;
+                    else if (ps[j] < cur[i]) ++j;
+                    else { ++inter; ++i; ++j; }
+                }
+            }
+            const double ov = (double)inter / (double)(np < nb ? np : nb);
+            if (ov > best) { best = ov; pref = p; }
+        }
+        if (best < 0.5) {
+            for (int i = 0; i < nb; ++i) bins[pstart[n_sets] + i] = cur[i];
+            pstart[n_sets + 1] = pstart[n_sets] + nb;
+            ++n_sets;
+        } else if (pref == 0 && !have_f2) { f2 = score[c]; have_f2 = true; }
+    }
+    out.f1 = score[order[0]];
+    out.f2 = f2;
+    out.m = (double)len[order[0]];
+    // ---- select_secondary_alignment :23505-23538 ----
+    int32_t *rest = W.rest;      // chain ids: the secondary chains in selection order
+    int n_sec = 0;
+    if (nc > 1) {
+        const int np = len[0];
+        auto loc2score_at = [&](int64_t q) -> double {
+            int lo = 0, hi = np;          // first t with prim[t].x <= q (descending read order)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)anc[mid].x <= q) hi = mid; else lo = mid + 1;
+            }
+            return lo < np ? S_prim[lo] : 0.0;
+        };
+        for (int oi = 1; oi < nc; ++oi) {
+            const int c = order[oi];
+            const double f2s = score[c];
+            const int64_t en_loc = anc[coff[c]].x, st_loc = anc[coff[c + 1] - 1].x;
+            if (en_loc - st_loc < 50) continue;
+            double f1s = loc2score_at(en_loc) - loc2score_at(st_loc);
+            if (f1s < 1.0) f1s = 1.0;
+            const double df = f1s - f2s;
+            if (f2s / f1s > 0.9 || (df < 0 ? -df : df) < 40) {
+                bool skip = false;
+                for (int q = 0; q < n_sec; ++q) {
+                    const int pc = rest[q];
+                    const int64_t pe = anc[coff[pc]].x, ps = anc[coff[pc + 1] - 1].x;
+                    const int64_t ovs = imax(imin(en_loc, pe) - imax(ps, st_loc), 0);
+                    if ((double)ovs / (double)(en_loc - st_loc) > 0.5) { skip = true; break; }
+                }
+                if (!skip) rest[n_sec++] = c;
+            }
+        }
+    }
+    // ---- merge_chain :28529-28569 on the secondary chains ----
+    int32_t *head = W.head, *tail = W.tail, *nxt = W.nxt, *size = W.size;
+    for (int c = 0; c < nc; ++c) { head[c] = c; tail[c] = c; nxt[c] = -1; size[c] = len[c]; }
+    ChainView cv{anc, coff, nxt};
+    int n_rest = n_sec;
+    if (n_rest > 0) {
+        // sort by the read position of the last anchor (numba argsort on int64 keys)
+        for (int q = 0; q < n_rest; ++q) W.k64c[q] = cv.back(tail, rest[q]).x;
+        argsort_replay<int64_t>(W.k64c, n_rest, W.ordc);
+        for (int q = 0; q < n_rest; ++q) W.cseg[q] = rest[W.ordc[q]];
+        for (int q = 0; q < n_rest; ++q) rest[q] = W.cseg[q];
+        int iloc = 0;
+        while (iloc + 1 < n_rest) {
+            int jloc = iloc + 1;
+            while (jloc < n_rest) {
+                const int ci = rest[iloc], cj = rest[jloc];
+                const Anc a0 = cv.front(head, ci), bl = cv.back(tail, cj);
+                if (a0.x + a0.l <= bl.x && a0.s == bl.s) {
+                    const int64_t readgap = bl.x - a0.x - a0.l;
+                    const int64_t refgap = a0.s == 1 ? bl.y - a0.y - a0.l : a0.y - bl.y - bl.l;
+                    if (iabs(readgap - refgap) < 500) {
+                        // merged = rest[jloc] followed by rest[iloc]; it takes rest[iloc]'s place
+                        nxt[tail[cj]] = head[ci];
+                        head[ci] = head[cj];
+                        size[ci] += size[cj];
+                        for (int q = jloc; q + 1 < n_rest; ++q) rest[q] = rest[q + 1];
+                        --n_rest;
+                        continue;
+                    }
+                }
+                ++jloc;
+            }
+            ++iloc;
+        }
+        // sort by length
+        for (int q = 0; q < n_rest; ++q) W.k64c[q] = size[rest[q]];
+        argsort_replay<int64_t>(W.k64c, n_rest, W.ordc);
+        for (int q = 0; q < n_rest; ++q) W.cseg[q] = rest[W.ordc[q]];
+        for (int q = 0; q < n_rest; ++q) rest[q] = W.cseg[q];
+    }
+    // ---- drop_somechains :28482-28528 (chains[0] = the primary chain) ----
+    // Note: tail[] of a merged chain is the tail of its LAST part, kept in tail[ci] only for unmerged chains; a merged
+    // chain's last part is found by walking nxt (merges are rare)
+    auto last_part = [&](int c) { int s = head[c]; while (nxt[s] >= 0) s = nxt[s]; return s; };
+    if (n_rest > 0) {
+        for (int q = 0; q < n_rest; ++q) {
+            W.cseg[q] = head[rest[q]]; W.cpos[q] = 0; W.cflat[q] = 0; W.sc0[q] = 0; W.sc1[q] = 0; W.dist[q] = INT64_MAX;
+        }
+        for (int t = coff[0]; t < coff[1]; ++t) {
+            const Anc item = widen(anc[t]);
+            for (int q = 0; q < n_rest; ++q) {
+                const int c = rest[q];
+                const int lp = last_part(c);
+                const int64_t back_x = anc[coff[lp + 1] - 1].x, front_x = anc[coff[head[c]]].x;
+                if (item.x >= back_x && item.x <= front_x) { if (item.s == 1) W.sc0[q]++; else W.sc1[q]++; }
+                for (;;) {
+                    const A32 ca = anc[coff[W.cseg[q]] + W.cpos[q]];
+                    if (!((int64_t)ca.x > item.x)) break;
+                    if (W.cflat[q] < size[c] - 1) {
+                        ++W.cflat[q];
+                        if (++W.cpos[q] >= len[W.cseg[q]]) { W.cseg[q] = nxt[W.cseg[q]]; W.cpos[q] = 0; }
+                    } else break;
+                }
+                const int64_t d = iabs(item.y - (int64_t)anc[coff[W.cseg[q]] + W.cpos[q]].y);
+                if (d < W.dist[q]) W.dist[q] = d;
+            }
+        }
+        int kept = 0;
+        for (int q = 0; q < n_rest; ++q) {
+            const int c = rest[q];
+            int64_t c0 = 0, c1 = 0;
+            for (int s = head[c]; s >= 0; s = nxt[s])
+                for (int t = coff[s]; t < coff[s + 1]; ++t) { if (anc[t].s == 1) ++c0; else ++c1; }
+            const bool keep = (W.sc0[q] > W.sc1[q] && c0 > c1) || (W.sc0[q] < W.sc1[q] && c0 < c1);
+            const int lp = last_part(c);
+            const int64_t span = (int64_t)anc[coff[head[c]]].x - (int64_t)anc[coff[lp + 1] - 1].x;
+            if ((!keep && W.dist[q] < 500) || span < 100) continue;
+            rest[kept++] = c;
+        }
+        n_rest = kept;
+    }
+    // ---- order of re-seeding: sort all chains by 1 / length (:28574), cap (:28575-28582) ----
+    const int n_all = 1 + n_rest;
+    // chain list: index 0 = primary (original chain 0), then rest[]
+    for (int q = 0; q < n_all; ++q) W.kd[q] = 1.0 / (double)(q == 0 ? size[0] : size[rest[q - 1]]);
+    argsort_replay<double>(W.kd, n_all, W.ordc);
+    int used = n_all;
+    if (max_guides > 0 && used > max_guides) used = max_guides;
+    out.status = ST_OK;
+    out.n_guides = n_all;
+    out.n_jobs = used;
+    // ---- one re-seeding job per used chain (:23090-23191) ----
+    const int64_t look_span = 7000;
+    int64_t g_used = 0, w_used = 0;
+    for (int ji = 0; ji < used; ++ji) {
+        const int li = W.ordc[ji];
+        const int c = li == 0 ? 0 : rest[li - 1];
+        const int n = size[c];
+        // materialise the chain (descending read order) into tmp
+        Anc *ch = W.tmp;
+        {
+            int k = 0;
+            for (int s = head[c]; s >= 0; s = nxt[s])
+                for (int t = coff[s]; t < coff[s + 1]; ++t) ch[k++] = widen(anc[t]);
+        }
+        int64_t readgap = 0;
+        bool x_desc = true, y_asc = true, y_desc = true;
+        for (int i = 1; i < n; ++i) {
+            const int64_t d = iabs(ch[i].x - ch[i - 1].x);
+            if (d > readgap) readgap = d;
+            if (!(ch[i].x < ch[i - 1].x)) x_desc = false;
+            if (!(ch[i - 1].y < ch[i].y)) y_asc = false;
+            if (!(ch[i].y < ch[i - 1].y)) y_desc = false;
+        }
+        readgap = imax(readgap + 1000, 5000);
+        int32_t *jgx = gx + g_used;
+        int64_t *jgy = gy + g_used;
+        int64_t *ys = W.k64a;             // reference positions ascending (the :23103 argsort)
+        if (n >= 1 && x_desc && (y_asc || y_desc)) {
+            for (int i = 0; i < n; ++i) {
+                ys[i] = y_asc ? ch[i].y : ch[n - 1 - i].y;
+                jgx[i] = (int32_t)ch[n - 1 - i].x;
+                jgy[i] = ch[n - 1 - i].y;
+            }
+        } else {
+            // general case: argsort by reference position, then by read position (:23183), both numba's
+            int64_t *keys = (int64_t *)jgy;          // the job's gy room doubles as key scratch until it is written
+            for (int i = 0; i < n; ++i) keys[i] = ch[i].y;
+            argsort_replay<int64_t>(keys, n, W.orda);
+            // by_y into the bins / cur scratch is too small for anchors: permute through ys + a second pass
+            for (int i = 0; i < n; ++i) ys[i] = ch[W.orda[i]].y;
+            // keys for the second sort: read positions of by_y
+            for (int i = 0; i < n; ++i) keys[i] = ch[W.orda[i]].x;
+            int32_t *ord2 = W.cur;               // na-sized int32 scratch (the bin sets are done)
+            argsort_replay<int64_t>(keys, n, ord2);
+            for (int i = 0; i < n; ++i) jgx[i] = (int32_t)ch[W.orda[ord2[i]]].x;
+            for (int i = 0; i < n; ++i) jgy[i] = ch[W.orda[ord2[i]]].y;      // overwrites keys only after both reads of it are over
+        }
+        // windows_of + windows_to_ranges, with the retry that splits windows at contig borders
+        int64_t *jlo = wlo + w_used, *jhi = whi + w_used;
+        int n_win = 0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const bool split = attempt == 1;
+            // the (first, second) pairs are produced one at a time; a pair is final once the next one starts
+            n_win = 0;
+            bool retry = false;
+            int64_t first = ys[0], second = ys[0];
+            int curc = rc.ctg.cid(ys[0]);
+            bool open = true;
+            auto emit = [&](int64_t a, int64_t b) -> bool {      // false: windows span two contigs -> retry
+                int64_t min_ref = a, max_ref = b;
+                const int cc = rc.ctg.cid(min_ref);
+                if (cc != rc.ctg.cid(max_ref)) return false;
+                const int64_t cs = rc.ctg.start[cc];
+                const int64_t lookfurther = imin(look_span, min_ref - cs);
+                min_ref -= lookfurther;
+                max_ref += look_span;
+                int64_t lo, hi;
+                rc.ctg.slice(cc, min_ref - cs, max_ref - cs, lo, hi);
+                jlo[n_win] = lo; jhi[n_win] = hi; ++n_win;
+                return true;
+            };
+            for (int i = 1; i < n && !retry; ++i) {
+                const int64_t y = ys[i];
+                if ((y - second) < readgap && (!split || curc == rc.ctg.cid(y))) second = y;
+                else {
+                    if (first != second && !emit(first, second)) retry = true;
+                    first = y; second = y;
+                    curc = rc.ctg.cid(y);
+                }
+            }
+            if (!retry && open && first != second && !emit(first, second)) retry = true;
+            if (!retry || split) break;
+            // the reference keeps the windows added before the cross-contig one and then ADDS those of the second attempt
+            // (windows_to_ranges clears its lists first in the host version: job.win_lo.clear()) -- the host version clears
+        }
+        RJob J;
+        J.read = rc.read; J.need_reverse = rc.need_reverse ? 1 : 0;
+        J.readstart = (int32_t)imax(0, (int64_t)jgx[0] - look_span);
+        J.readend = (int32_t)imin(rc.L - kmer + 1, (int64_t)jgx[n - 1] + look_span);
+        J.n_win = n_win; J.n_guide = n;
+        J.win_off = w_base + w_used; J.g_off = g_base + g_used;
+        J.hit_off = 0; J.hit_cap = 0; J.pad0 = 0; J.dense_off = 0; J.tab_off = 0; J.tab_size = 0; J.pad = 0;
+        jobs[ji] = J;
+        g_used += n;
+        w_used += n_win;
+    }
+    return g_used;
+}
+
+} // namespace vmd

@@ -14,9 +14,10 @@
 //     at an offset obtained from a block scan, so hits are ordered exactly like the reference's
 //     scan: (read position, forward before reverse, window, reference position).  HBM-bound
 //     gather: 2 strands x (2 offsets + ~log2(run) probes) per read position.
-//   kernel 2 (vm_reseed_merge_kernel): one warp per job (lane 0 works); replays the
-//     same-diagonal merge (:23235-23252, 23294-23312) over the ordered hits with the diagonal
-//     table (`pointdict`) in global memory, emitting anchors in the reference's order.
+//   kernel 2 (vm_reseed_merge_kernel): one warp per job; the same-diagonal merge (:23235-23252,
+//     23294-23312) with the diagonals split between the lanes (each replays its diagonals' hits in
+//     scan order), the diagonal table (`pointdict`) in global memory, and the reference's emission
+//     order restored by slotting every anchor at the scan index that emitted it.
 #include "vm_reseed.cuh"
 
 struct VmHit {
@@ -200,32 +201,179 @@ __global__ void __launch_bounds__(VM_RS_THREADS) vm_reseed_hits_kernel(VmIndexDe
     if (tid == 0) n_hits[blockIdx.x] = running;
 }
 
-struct VmPoint {
-    long long key;
+// The diagonal table of a job: tab_size keys (64-bit, contiguous: cleared with coalesced stores) followed by tab_size values
+struct VmPointVal {
     int c0;
     unsigned c1;
-    int c2;
-    int c3;
+    int c23;       // segment length | (strand == -1) << 8
+    int q0;        // scan index of the hit that opened the diagonal (the reference's dict insertion order)
 };
+struct VmPoint { long long key; VmPointVal v; };      // 24 bytes per slot (sizing only)
 #define VM_PT_EMPTY 0x7fffffffffffffffLL
+__device__ __forceinline__ long long *vm_tab_keys(VmPoint *table_all, const VmReseedJobDev &J) { return (long long *)((char *)table_all + J.tab_off * 24); }
+__device__ __forceinline__ VmPointVal *vm_tab_vals(VmPoint *table_all, const VmReseedJobDev &J)
+{
+    return (VmPointVal *)((char *)table_all + J.tab_off * 24 + (long long)J.tab_size * 8);
+}
 
+// Same-diagonal merge (:23235-23252, 23294-23312), one warp per job.
+//
+// The reference walks the hits in scan order; every hit touches only the running segment of its own diagonal
+// (`pointdict[point]`), emits at most one anchor (when the segment is cut by a gap or reaches 20 bases), and the
+// segments still open at the end are emitted in the order their diagonals first appeared.  Diagonals are
+// independent, so the lanes split them: lane `hash(point) & 31` owns a diagonal and replays its hits in scan order,
+// 32 hits (one per lane) being staged at a time; the table latency of up to 32 diagonals overlaps instead of
+// being paid one hit after the other.  Every lane has its own interleaved slice of the job's table (slots
+// lane, lane + 32, ...): no atomics.  The reference's output ORDER is kept without sorting: an anchor emitted while
+// processing hit q goes to slot q of a sparse array, a left-over segment to slot n + q0, and a final in-place
+// compaction of the 2n slots (in slot order) yields exactly the sequential emission order.
+// flags: one byte per slot (the job's slice of the `order` scratch, 4 bytes per hit).
+// A lane whose slice fills up gives up: n_out = -1, and the job is redone by the sequential kernel below.
 __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDev *__restrict__ jobs,
                                                              const VmHit *__restrict__ hits_all,
                                                              const int32_t *__restrict__ n_hits,
                                                              VmPoint *__restrict__ table_all, int32_t *__restrict__ order_all,
                                                              VmAnchor *__restrict__ out_all, int32_t *__restrict__ n_out)
 {
+    __shared__ VmHit s_hit[32];
+    __shared__ unsigned s_mask[32];
     const VmReseedJobDev J = jobs[blockIdx.x];
     const int lane = threadIdx.x;
     const int n = n_hits[blockIdx.x];
-    if (n > J.hit_cap) { if (lane == 0) n_out[blockIdx.x] = 0; return; }   // never after the host's re-run
+    if (n > J.hit_cap || n <= 0) { if (lane == 0) n_out[blockIdx.x] = 0; return; }   // over capacity: never after the host's re-run
     const VmHit *hits = hits_all + J.hit_off;
-    VmPoint *tab = table_all + J.tab_off;
+    long long *keys = vm_tab_keys(table_all, J);
+    VmPointVal *vals = vm_tab_vals(table_all, J);
+    const int sub = J.tab_size >> 5;                               // slots of one lane's slice (a power of two)
+    uint8_t *flag = (uint8_t *)(order_all + J.dense_off);          // [2n]
+    VmAnchor *out = out_all + 2 * J.dense_off;                     // [2n] sparse slots, compacted in place at the end
+    for (int t = lane; t < J.tab_size; t += 32) keys[t] = VM_PT_EMPTY;
+    for (int t = lane; t < (2 * n + 3) / 4; t += 32) ((uint32_t *)flag)[t] = 0u;
+    __syncwarp();
+    const int k = VM_K9;
+    int used = 0;
+    bool full = false;
+    for (int q0 = 0; q0 < n; q0 += 32) {
+        const int q = q0 + lane;
+        int own = -1;
+        if (q < n) {
+            const VmHit h = hits[q];
+            s_hit[lane] = h;
+            const int iloc = h.iloc_s >> 1;
+            const long long point = (h.iloc_s & 1) ? -((long long)h.refloc + iloc) : (long long)h.refloc - iloc;
+            const unsigned long long hh = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
+            own = (int)((hh >> 40) & 31u);
+        }
+        s_mask[lane] = 0u;
+        __syncwarp();
+        // lane L learns which of the 32 staged hits it owns: every group of equal owners reports its member mask
+        const unsigned peers = __match_any_sync(VM_FULL, own);
+        if (own >= 0 && (int)(__ffs(peers) - 1) == lane) s_mask[own] = peers;
+        __syncwarp();
+        unsigned mine = s_mask[lane];
+        while (mine && !full) {
+            const int t = __ffs(mine) - 1;
+            mine &= mine - 1;
+            const VmHit hit = s_hit[t];
+            const int qq = q0 + t;
+            const int iloc = hit.iloc_s >> 1;
+            const int strand = (hit.iloc_s & 1) ? -1 : 1;
+            const long long refloc = hit.refloc;
+            const long long point = strand == 1 ? refloc - iloc : -(refloc + iloc);
+            const unsigned long long h = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
+            int s = (int)((h ^ (h >> 31)) & (unsigned long long)(sub - 1));
+            long long key;
+            while ((key = keys[(s << 5) + lane]) != VM_PT_EMPTY && key != point) s = (s + 1) & (sub - 1);
+            VmPointVal *e = vals + (s << 5) + lane;
+            if (key == VM_PT_EMPTY) {
+                if (++used >= sub) { full = true; break; }         // keep one slot free: the probe loop must terminate
+                keys[(s << 5) + lane] = point;
+                VmPointVal nv; nv.c0 = iloc; nv.c1 = (unsigned)refloc; nv.c23 = k | (strand == 1 ? 0 : 256); nv.q0 = qq;
+                *e = nv;
+                continue;
+            }
+            int c0 = e->c0, c3 = e->c23 & 255, c2 = (e->c23 & 256) ? -1 : 1;
+            unsigned c1 = e->c1;
+            if (c0 + c3 >= iloc) {
+                const int bonus = iloc - (c0 + c3) + k;
+                if (bonus > 0) {
+                    if (c3 + bonus < 20) {
+                        if (strand == 1) { c2 = 1; c3 += bonus; }
+                        else { c1 = (unsigned)refloc; c2 = -1; c3 += bonus; }
+                    } else {
+                        VmAnchor a; a.x = c0; a.y = c1; a.s = c2; a.l = c3;
+                        out[qq] = a;
+                        flag[qq] = 1;
+                        if (strand == 1) { const int l3 = c3; c0 += l3; c1 += (unsigned)l3; c2 = 1; c3 = bonus; }
+                        else { c0 += c3; c1 = (unsigned)refloc; c2 = -1; c3 = bonus; }
+                    }
+                    e->c0 = c0; e->c1 = c1; e->c23 = c3 | (c2 == 1 ? 0 : 256);
+                }
+            } else {
+                VmAnchor a; a.x = c0; a.y = c1; a.s = c2; a.l = c3;
+                out[qq] = a;
+                flag[qq] = 1;
+                e->c0 = iloc; e->c1 = (unsigned)refloc; e->c23 = k | (strand == 1 ? 0 : 256);
+            }
+        }
+        if (__any_sync(VM_FULL, full)) { if (lane == 0) n_out[blockIdx.x] = -1; return; }
+    }
+    // the segments still open, at slot n + (scan index of their diagonal's first hit)
+    for (int t = lane; t < J.tab_size; t += 32) {
+        if (keys[t] == VM_PT_EMPTY) continue;
+        const VmPointVal p = vals[t];
+        VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = (p.c23 & 256) ? -1 : 1; a.l = p.c23 & 255;
+        out[n + p.q0] = a;
+        flag[n + p.q0] = 1;
+    }
+    __syncwarp();
+    // in-place compaction in slot order, 128 slots per step (the write position never overtakes the read position)
+    int m = 0;
+    const int n_words = (2 * n + 3) / 4;
+    for (int b = 0; b < n_words; b += 32) {
+        const int w = b + lane;
+        const uint32_t f = w < n_words ? ((const uint32_t *)flag)[w] : 0u;
+        const int base = w * 4;
+        VmAnchor a[4];
+        int cnt = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if ((f >> (8 * t)) & 0xffu) { a[cnt] = out[base + t]; ++cnt; }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(VM_FULL, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const int total = __shfl_sync(VM_FULL, incl, 31);
+        __syncwarp();
+        int o = m + incl - cnt;
+        for (int t = 0; t < cnt; ++t) out[o + t] = a[t];
+        m += total;
+        __syncwarp();
+    }
+    if (lane == 0) n_out[blockIdx.x] = m;
+}
+
+// The same merge replayed by one lane, hit after hit (the formulation above falls back to it for a job whose hits
+// crowd one lane's table slice; `only_failed`: run only the jobs marked n_out = -1).
+__global__ void __launch_bounds__(32) vm_reseed_merge_seq_kernel(const VmReseedJobDev *__restrict__ jobs,
+                                                                 const VmHit *__restrict__ hits_all,
+                                                                 const int32_t *__restrict__ n_hits,
+                                                                 VmPoint *__restrict__ table_all, int32_t *__restrict__ order_all,
+                                                                 VmAnchor *__restrict__ out_all, int32_t *__restrict__ n_out)
+{
+    if (n_out[blockIdx.x] != -1) return;
+    const VmReseedJobDev J = jobs[blockIdx.x];
+    const int lane = threadIdx.x;
+    const int n = n_hits[blockIdx.x];
+    const VmHit *hits = hits_all + J.hit_off;
+    long long *keys = vm_tab_keys(table_all, J);
+    VmPointVal *vals = vm_tab_vals(table_all, J);
     const int tmask = J.tab_size - 1;
     int32_t *order = order_all + J.dense_off;
     VmAnchor *out = out_all + 2 * J.dense_off;
-    // clear the diagonal table with all lanes
-    for (int t = lane; t < J.tab_size; t += 32) tab[t].key = VM_PT_EMPTY;
+    for (int t = lane; t < J.tab_size; t += 32) keys[t] = VM_PT_EMPTY;
     __syncwarp();
     if (lane != 0) return;
     int n_pts = 0, m = 0;
@@ -238,36 +386,35 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
         const long long point = strand == 1 ? refloc - iloc : -(refloc + iloc);
         unsigned long long h = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
         int s = (int)((h ^ (h >> 31)) & (unsigned long long)tmask);
-        while (tab[s].key != VM_PT_EMPTY && tab[s].key != point) s = (s + 1) & tmask;
-        VmPoint p = tab[s];
-        if (p.key == VM_PT_EMPTY) {
-            p.key = point; p.c0 = iloc; p.c1 = (unsigned)refloc; p.c2 = strand; p.c3 = k;
-            tab[s] = p;
+        while (keys[s] != VM_PT_EMPTY && keys[s] != point) s = (s + 1) & tmask;
+        VmPointVal p = vals[s];
+        int c3 = p.c23 & 255, c2 = (p.c23 & 256) ? -1 : 1;
+        if (keys[s] == VM_PT_EMPTY) {
+            keys[s] = point; p.c0 = iloc; p.c1 = (unsigned)refloc; c2 = strand; c3 = k; p.q0 = q;
             order[n_pts++] = s;
-        } else if (p.c0 + p.c3 >= iloc) {
-            const int bonus = iloc - (p.c0 + p.c3) + k;
-            if (bonus > 0) {
-                if (p.c3 + bonus < 20) {
-                    if (strand == 1) { p.c2 = 1; p.c3 += bonus; }
-                    else { p.c1 = (unsigned)refloc; p.c2 = -1; p.c3 += bonus; }
-                } else {
-                    VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
-                    out[m++] = a;
-                    if (strand == 1) { const int c3 = p.c3; p.c0 += c3; p.c1 += (unsigned)c3; p.c2 = 1; p.c3 = bonus; }
-                    else { p.c0 += p.c3; p.c1 = (unsigned)refloc; p.c2 = -1; p.c3 = bonus; }
-                }
-                tab[s] = p;
+        } else if (p.c0 + c3 >= iloc) {
+            const int bonus = iloc - (p.c0 + c3) + k;
+            if (bonus <= 0) continue;
+            if (c3 + bonus < 20) {
+                if (strand == 1) { c2 = 1; c3 += bonus; }
+                else { p.c1 = (unsigned)refloc; c2 = -1; c3 += bonus; }
+            } else {
+                VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = c2; a.l = c3;
+                out[m++] = a;
+                if (strand == 1) { p.c0 += c3; p.c1 += (unsigned)c3; c2 = 1; c3 = bonus; }
+                else { p.c0 += c3; p.c1 = (unsigned)refloc; c2 = -1; c3 = bonus; }
             }
         } else {
-            VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
+            VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = c2; a.l = c3;
             out[m++] = a;
-            p.c0 = iloc; p.c1 = (unsigned)refloc; p.c2 = strand; p.c3 = k;
-            tab[s] = p;
+            p.c0 = iloc; p.c1 = (unsigned)refloc; c2 = strand; c3 = k;
         }
+        p.c23 = c3 | (c2 == 1 ? 0 : 256);
+        vals[s] = p;
     }
     for (int q = 0; q < n_pts; ++q) {
-        const VmPoint p = tab[order[q]];
-        VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = p.c2; a.l = p.c3;
+        const VmPointVal p = vals[order[q]];
+        VmAnchor a; a.x = p.c0; a.y = p.c1; a.s = (p.c23 & 256) ? -1 : 1; a.l = p.c23 & 255;
         out[m++] = a;
     }
     n_out[blockIdx.x] = m;
@@ -288,7 +435,9 @@ int vm_reseed_merge_launch(const VmReseedJobDev *jobs_dev, int n_jobs, const voi
 {
     if (n_jobs <= 0) return 0;
     vm_reseed_merge_kernel<<<n_jobs, 32, 0, stream>>>(jobs_dev, (const VmHit *)hits, n_hits, (VmPoint *)table, order, out, n_out);
-    return 1;
+    // jobs that gave up (n_out = -1: one lane's table slice filled up) are replayed hit after hit; everyone else returns at once
+    vm_reseed_merge_seq_kernel<<<n_jobs, 32, 0, stream>>>(jobs_dev, (const VmHit *)hits, n_hits, (VmPoint *)table, order, out, n_out);
+    return 2;
 }
 
 size_t vm_reseed_hit_bytes() { return sizeof(VmHit); }
