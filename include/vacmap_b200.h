@@ -157,6 +157,20 @@ typedef struct vm_index_handle vm_index_handle;
 int vm_index_create(vm_ctx *ctx, int32_t n_contigs, const char *const *names, const char *const *seqs,
                     const int64_t *lens, int32_t w, int32_t k, vm_index_handle **out);
 void vm_index_destroy(vm_index_handle *h);
+/* The index is built ON THE DEVICE (what `minimap2 -d` does for the reference, vacmap:324-344, plus the 9-mer position
+ * index of the local stage): chunk-parallel mm_sketch of the contigs, stable radix sort by hash, hash table by atomicCAS,
+ * 9-mer codes radix-sorted.  The three entry points below let one process build it and the others use it:
+ *   vm_index_arrays     the five device arrays of a built index (reference, hash table, occurrences, 9-mer positions,
+ *                       9-mer offsets: ptrs[5], bytes[5]) and eight scalars (meta[8]: n_keys, n_occ, n_kpos, ht_slots,
+ *                       mid_occ, w, k, reference length)
+ *   vm_index_adopt      an index over device arrays the CALLER owns (e.g. filled by an NCCL broadcast); they must outlive
+ *                       the handle
+ *   vm_index_minimizers the distinct minimizer hashes (ascending), their counts and their occurrences on the host -- what
+ *                       a minimap2 `.mmi` file stores (vacmap_b200/mmi.py writes it) */
+int vm_index_arrays(vm_index_handle *h, const void **ptrs, int64_t *bytes, int64_t *meta);
+int vm_index_adopt(vm_ctx *ctx, int32_t n_contigs, const char *const *names, const int64_t *lens, const void *const *ptrs,
+                   const int64_t *bytes, const int64_t *meta, vm_index_handle **out);
+int vm_index_minimizers(vm_index_handle *h, uint64_t *keys, int32_t *counts, uint64_t *occ);
 int vm_index_info(vm_index_handle *h, int32_t *k, int32_t *w, int32_t *n_contigs, int64_t *n_minimizers,
                   int64_t *n_keys, int32_t *mid_occ);
 /* contig i: name, global start offset (`seq_offset[i][2]`), length, pointer to its (library-owned) sequence */

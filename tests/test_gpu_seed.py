@@ -121,3 +121,48 @@ def test_local_reseeding_matches_reference_guide_1(gpu_ctx):
             n += len(g)
         ix.close()
     assert n > 10000
+
+
+def test_device_built_index_equals_host_built_index(gpu_ctx, monkeypatch, tmp_path):
+    """the index built on the device (chunk-parallel sketch of the contigs, stable radix sort, CAS hash table,
+    radix-sorted 9-mers) must be the index the single-threaded host build of round 1 makes: same keys, counts and
+    occurrence order, same default occurrence cap, same seeds and same records; and it survives a trip through a
+    minimap2 `.mmi` file (vacmap:324-344)."""
+    import vacmap_b200 as vb
+    from vacmap_b200 import mmi
+    from vacmap_b200.align import seed_batch
+    ref = synth.make_reference(5, 300000, n_contigs=3, repeat_frac=0.1)
+    ref.append(("withN", "ACGT" * 50 + "N" * 30 + "ACGTTGCA" * 40 + "nnnnacgtacgatcgatcgatcgatcgtagctagctagctagcatcgatcgatcga" * 5))
+    reads = synth.make_reads(ref[:3], 77, 12, read_len=5000, err=0.08, sv_frac=0.5)
+    ix = vb.Index(ref, w=10, k=15, ctx=gpu_ctx)
+    dev = ix.minimizers()
+    seeds = seed_batch(ix, [s for _, s in reads])
+    recs = vb.Aligner(ix, vb.default_option("H"), "H").align_batch(reads)
+    monkeypatch.setenv("VM_INDEX_HOST", "1")
+    ixh = vb.Index(ref, w=10, k=15, ctx=gpu_ctx)
+    monkeypatch.delenv("VM_INDEX_HOST")
+    host = ixh.minimizers()
+    assert (ix.n_keys, ix.n_minimizers, ix.mid_occ) == (ixh.n_keys, ixh.n_minimizers, ixh.mid_occ)
+    for a, b in zip(dev, host):
+        assert a.shape == b.shape and (a == b).all()
+    assert all(ix.seq(n) == ixh.seq(n) for n, _ in ref)
+    for (a, fa), (b, fb) in zip(seeds, seed_batch(ixh, [s for _, s in reads])):
+        assert fa == fb and a.shape == b.shape and (a == b).all()
+    assert recs == vb.Aligner(ixh, vb.default_option("H"), "H").align_batch(reads)
+    ox = oracle.Index(ref)
+    assert (ix.n_keys, ix.n_minimizers, ix.mid_occ) == (ox.n_keys, ox.n_occ, ox.mid_occ_default)
+    # through a .mmi file: what the writer stores is what the reader finds, and an index opened from it is the same index
+    p = str(tmp_path / "ref.fa.w10_k15.mmi")
+    ix.write_mmi(p)
+    m = mmi.read_mmi(p, with_minimizers=True)
+    assert m["names"] == [n for n, _ in ref] and m["seqs"] == [ix.seq(n) for n, _ in ref]
+    assert (m["keys"] == dev[0]).all() and (m["counts"] == dev[1]).all() and (m["occ"] == dev[2]).all()
+    ix2 = vb.Index(p, w=10, k=15, ctx=gpu_ctx)
+    assert (ix2.n_keys, ix2.n_minimizers, ix2.mid_occ) == (ix.n_keys, ix.n_minimizers, ix.mid_occ)
+    assert recs == vb.Aligner(ix2, vb.default_option("H"), "H").align_batch(reads)
+    # a second handle over the same device arrays (what a rank does with an index another rank broadcast)
+    arrs, meta = ix.arrays()
+    ix3 = vb.Index.adopt(ix.names, ix.lens, [p_ for p_, _ in arrs], [b_ for _, b_ in arrs], meta, ctx=gpu_ctx)
+    assert recs == vb.Aligner(ix3, vb.default_option("H"), "H").align_batch(reads)
+    for x in (ix3, ix2, ixh, ix):
+        x.close()

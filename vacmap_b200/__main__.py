@@ -2,7 +2,8 @@
 (`vacmap:95-296`) over the CUDA path, for the flags that reach the per-read alignment path and its SAM text.
 Reads stream through in super-batches (one vm_align_submit per batch, the next one submitted before the previous
 is collected); records of a batch are written in read order, a read that does not map writes nothing (quirk A2).
-Not mirrored: BAM output through samtools, `.mmi` index files, BAM input, `-mode R` and `-mode asm`."""
+`<ref>.w{w}_k{k}.mmi` index files are read and written in minimap2's format (vacmap_b200/mmi.py).
+Not mirrored: BAM output through samtools, BAM input, `-mode R` and `-mode asm`."""
 import argparse
 import os
 import sys
@@ -34,6 +35,7 @@ def build_parser():
     p.add_argument("-mode", required=True, choices=["H", "L", "S"])
     p.add_argument("-o", default="-")
     p.add_argument("--force", action="store_true")
+    p.add_argument("--nowriteindex", action="store_true", help="do not save the reference index (<ref>.w{w}_k{k}.mmi) for reuse")
     p.add_argument("-t", type=int, default=0, help="host glue threads (0 = all cores)")
     p.add_argument("-k", type=int, default=15)
     p.add_argument("-w", type=int, default=10)
@@ -100,8 +102,16 @@ def main(argv=None):
         if os.path.isfile(args.o) and not args.force:
             sys.exit("output file exists (use --force)")
     opt = options_from(args)
-    ref = [(r[0], r[1].upper()) for r in align.read_fastx(args.ref)]
-    index = align.Index(ref, w=args.w, k=args.k, device=args.device)
+    # vacmap:324-344 -- `<ref>.w{w}_k{k}.mmi` is used when it exists and written (minimap2's format) when it does not;
+    # here the index itself is always built on the GPU, the file carries the sequences
+    refpath = args.ref
+    index_name = "%s.w%d_k%d.mmi" % (refpath, args.w, args.k)
+    if not args.nowriteindex and os.path.isfile(index_name):
+        refpath = index_name
+    index = align.Index(refpath, w=args.w, k=args.k, device=args.device)
+    if not args.nowriteindex and refpath != index_name and not refpath.endswith("mmi"):
+        index.write_mmi(index_name)
+    ref = [(n, index.seq(n)) for n in index.names]
     al = align.Aligner(index, opt, args.mode, host_threads=args.t)
     # the reference takes contig2seq from index.seq() (vacmap:363): non-ACGT bases are N there
     contig2seq = {n: index.seq(n) for n, _ in ref}

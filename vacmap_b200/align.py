@@ -103,6 +103,9 @@ def _declare(L):
     L.vm_index_create.argtypes = [vp, i32, vp, vp, vp, i32, i32, ctypes.POINTER(vp)]
     L.vm_index_destroy.argtypes = [vp]
     L.vm_index_destroy.restype = None
+    L.vm_index_arrays.argtypes = [vp, vp, vp, vp]
+    L.vm_index_adopt.argtypes = [vp, i32, vp, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    L.vm_index_minimizers.argtypes = [vp, vp, vp, vp]
     L.vm_index_info.argtypes = [vp] + [vp] * 6
     L.vm_index_contig.argtypes = [vp, i32, vp, vp, vp, vp]
     L.vm_align_batch.argtypes = [vp, vp, ctypes.POINTER(AlignParamsC), i64, vp, vp, ctypes.POINTER(vp)]
@@ -129,11 +132,22 @@ class Index:
     """Reference index resident on one GPU: `.k`, `.w`, `.seq_offset`, `.seq(name)` as the reference uses them."""
 
     def __init__(self, ref, w=10, k=15, ctx=None, device=0):
-        """ref: path to a FASTA(.gz) or a list of (name, sequence)."""
+        """ref: path to a FASTA(.gz) or to a minimap2 `.mmi` (its sequences are used, the index itself is rebuilt on the
+        GPU, which is faster than reading it), or a list of (name, sequence)."""
         L = _lib.load()
         _declare(L)
         self.ctx = ctx or _lib.default_context(device)
-        contigs = [(n, s) for n, s, _ in read_fastx(ref)] if isinstance(ref, (str, bytes)) else list(ref)
+        if isinstance(ref, (str, bytes)):
+            from . import mmi
+            if mmi.is_mmi(ref):
+                m = mmi.read_mmi(ref)
+                if m["seqs"] is None:
+                    raise ValueError("%s was written without sequences (minimap2 --idx-no-seq)" % ref)
+                contigs = list(zip(m["names"], m["seqs"]))
+            else:
+                contigs = [(n, s) for n, s, _ in read_fastx(ref)]
+        else:
+            contigs = list(ref)
         self.k, self.w = int(k), int(w)
         self.names = [n for n, _ in contigs]
         enc = [s.encode() if isinstance(s, str) else bytes(s) for _, s in contigs]
@@ -144,12 +158,64 @@ class Index:
         h = ctypes.c_void_p()
         _lib.check(self.ctx.h, L.vm_index_create(self.ctx.h, n, names_c, seqs_c, _lib.ptr(lens), self.w, self.k,
                                                  ctypes.byref(h)))
+        self._finish(h, lens)
+
+    def _finish(self, h, lens):
+        L = _lib.load()
         self.h = h
-        self.lens = lens
-        self.starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
+        self.lens = np.asarray(lens, dtype=np.int64)
+        self.starts = np.concatenate([[0], np.cumsum(self.lens)[:-1]]).astype(np.int64)
         info = [ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()]
         L.vm_index_info(self.h, *[ctypes.byref(x) for x in info])
         self.n_minimizers, self.n_keys, self.mid_occ = info[3].value, info[4].value, info[5].value
+
+    def arrays(self):
+        """The built index as device arrays: ([(device pointer, bytes)] x 5, meta int64[8]) -- reference, hash table,
+        occurrences, 9-mer positions, 9-mer offsets (`vm_index_arrays`); what `adopt` takes on another rank."""
+        L = _lib.load()
+        ptrs = (ctypes.c_void_p * 5)()
+        nbytes = np.zeros(5, np.int64)
+        meta = np.zeros(8, np.int64)
+        _lib.check(self.ctx.h, L.vm_index_arrays(self.h, ptrs, _lib.ptr(nbytes), _lib.ptr(meta)))
+        return [(int(ptrs[i] or 0), int(nbytes[i])) for i in range(5)], meta
+
+    @classmethod
+    def adopt(cls, names, lens, ptrs, nbytes, meta, ctx=None, device=0, keep=None):
+        """An index over device arrays the caller owns (`vm_index_adopt`); `keep` = whatever must stay alive with it
+        (e.g. the torch tensors an NCCL broadcast filled)."""
+        L = _lib.load()
+        _declare(L)
+        self = cls.__new__(cls)
+        self.ctx = ctx or _lib.default_context(device)
+        self.names = list(names)
+        self.w, self.k = int(meta[5]), int(meta[6])
+        self._keep = keep
+        n = len(self.names)
+        names_c = (ctypes.c_char_p * n)(*[x.encode() for x in self.names])
+        lens = np.asarray(lens, dtype=np.int64)
+        p = (ctypes.c_void_p * 5)(*[int(x) for x in ptrs])
+        nb = np.asarray(nbytes, dtype=np.int64)
+        mt = np.asarray(meta, dtype=np.int64)
+        h = ctypes.c_void_p()
+        _lib.check(self.ctx.h, L.vm_index_adopt(self.ctx.h, n, names_c, _lib.ptr(lens), p, _lib.ptr(nb), _lib.ptr(mt), ctypes.byref(h)))
+        self._finish(h, lens)
+        return self
+
+    def minimizers(self):
+        """(distinct hashes ascending uint64[n_keys], counts int32[n_keys], occurrences uint64[n_minimizers] as global
+        last-base position << 1 | strand) -- what a `.mmi` stores."""
+        L = _lib.load()
+        keys = np.zeros(self.n_keys, np.uint64)
+        counts = np.zeros(self.n_keys, np.int32)
+        occ = np.zeros(self.n_minimizers, np.uint64)
+        _lib.check(self.ctx.h, L.vm_index_minimizers(self.h, _lib.ptr(keys), _lib.ptr(counts), _lib.ptr(occ)))
+        return keys, counts, occ
+
+    def write_mmi(self, path):
+        """Store the index as a minimap2 `.mmi` (`<ref>.w{w}_k{k}.mmi` is where the reference looks, vacmap:326)."""
+        from . import mmi
+        keys, counts, occ = self.minimizers()
+        mmi.write_mmi(path, self.names, [self.seq(n) for n in self.names], self.w, self.k, keys, counts, occ)
 
     @property
     def seq_offset(self):

@@ -8,7 +8,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 6; }
+int vm_abi_version(void) { return 7; }
 
 int vm_ctx_create(int device, vm_ctx **out)
 {

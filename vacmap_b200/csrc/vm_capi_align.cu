@@ -25,24 +25,45 @@ int vm_index_create(vm_ctx *c, int32_t n_contigs, const char *const *names, cons
         return VM_ERR_ARG;
     }
     cudaSetDevice(c->device);
-    std::vector<std::string> nm, sq;
-    for (int i = 0; i < n_contigs; ++i) {
-        nm.emplace_back(names[i]);
-        sq.emplace_back(seqs[i], (size_t)lens[i]);
-    }
-    vm_index_handle *h = new vm_index_handle();
-    h->ix = vm_index_build_host(nm, sq, w, k);
-    if ((int64_t)h->ix->ref.size() >= (1LL << 32) - 64) {
-        c->err = "reference longer than 2^32 bases is not supported";
-        vm_index_free(h->ix);
-        delete h;
-        return VM_ERR_ARG;
-    }
-    std::string err;
-    if (vm_index_upload(h->ix, err)) {
-        c->err = err;
-        vm_index_free(h->ix);
-        delete h;
+    int64_t total = 0;
+    for (int i = 0; i < n_contigs; ++i) total += lens[i];
+    if (total >= (1LL << 32) - 64) { c->err = "reference longer than 2^32 bases is not supported (global coordinates are 32-bit)"; return VM_ERR_ARG; }
+    vm_index_handle *h = nullptr;
+    try {
+        h = new vm_index_handle();
+        std::string err;
+        if (getenv("VM_INDEX_HOST")) {
+            // A/B switch: the single-threaded host build of round 1 (the device build must give the same index)
+            std::vector<std::string> nm, sq;
+            for (int i = 0; i < n_contigs; ++i) {
+                nm.emplace_back(names[i]);
+                sq.emplace_back(seqs[i], (size_t)lens[i]);
+            }
+            h->ix = vm_index_build_host(nm, sq, w, k);
+            if (vm_index_upload(h->ix, err)) throw std::runtime_error(err);
+        } else {
+            VmIndex *ix = new VmIndex();
+            h->ix = ix;
+            ix->w = w;
+            ix->k = k;
+            ix->ref.resize((size_t)total);
+            int64_t off = 0;
+            for (int i = 0; i < n_contigs; ++i) {
+                ix->names.emplace_back(names[i]);
+                ix->ctg_start.push_back(off);
+                ix->ctg_len.push_back(lens[i]);
+                if (lens[i]) memcpy(&ix->ref[(size_t)off], seqs[i], (size_t)lens[i]);
+                off += lens[i];
+            }
+            if (vm_index_build_device(ix, err)) throw std::runtime_error(err);
+        }
+    } catch (const std::bad_alloc &) {
+        c->err = "out of host memory while building the index";
+        if (h) { vm_index_free(h->ix); delete h; }
+        return VM_ERR_NOMEM;
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        if (h) { vm_index_free(h->ix); delete h; }
         return VM_ERR_CUDA;
     }
     h->ctg.names = h->ix->names;
@@ -51,6 +72,98 @@ int vm_index_create(vm_ctx *c, int32_t n_contigs, const char *const *names, cons
     h->ctg.seq = h->ix->ref.data();
     h->ctg.total = (int64_t)h->ix->ref.size();
     *out = h;
+    return VM_OK;
+}
+
+// The built index as five device arrays (reference, hash table, occurrences, 9-mer positions, 9-mer offsets) plus
+// eight scalars: what another rank needs to use the index without building it (vm_index_adopt).
+int vm_index_arrays(vm_index_handle *h, const void **ptrs, int64_t *bytes, int64_t *meta)
+{
+    if (!h || !ptrs || !bytes || !meta) return VM_ERR_ARG;
+    VmIndex *ix = h->ix;
+    ptrs[0] = ix->d_ref;  bytes[0] = (int64_t)ix->ref.size();
+    ptrs[1] = ix->d_ht;   bytes[1] = (int64_t)(ix->ht_slots * sizeof(VmHtSlot));
+    ptrs[2] = ix->d_occ;  bytes[2] = ix->n_occ * 8;
+    ptrs[3] = ix->d_kpos; bytes[3] = ix->n_kpos * 4;
+    ptrs[4] = ix->d_koff; bytes[4] = ((int64_t)VM_K9_KEYS + 1) * 8;
+    meta[0] = ix->n_keys; meta[1] = ix->n_occ; meta[2] = ix->n_kpos; meta[3] = (int64_t)ix->ht_slots; meta[4] = ix->mid_occ_default;
+    meta[5] = ix->w; meta[6] = ix->k; meta[7] = (int64_t)ix->ref.size();
+    return VM_OK;
+}
+
+// An index over device arrays the CALLER owns (e.g. received by an NCCL broadcast from the rank that built them): the
+// handle only borrows them; they must outlive it.  The normalised reference is copied back to the host for the glue.
+int vm_index_adopt(vm_ctx *c, int32_t n_contigs, const char *const *names, const int64_t *lens, const void *const *ptrs,
+                   const int64_t *bytes, const int64_t *meta, vm_index_handle **out)
+{
+    if (!c) return VM_ERR_ARG;
+    if (!out || n_contigs <= 0 || !names || !lens || !ptrs || !bytes || !meta) { c->err = "bad argument"; return VM_ERR_ARG; }
+    cudaSetDevice(c->device);
+    vm_index_handle *h = nullptr;
+    try {
+        h = new vm_index_handle();
+        VmIndex *ix = new VmIndex();
+        h->ix = ix;
+        ix->borrowed = true;
+        ix->w = (int)meta[5];
+        ix->k = (int)meta[6];
+        int64_t off = 0;
+        for (int i = 0; i < n_contigs; ++i) {
+            ix->names.emplace_back(names[i]);
+            ix->ctg_start.push_back(off);
+            ix->ctg_len.push_back(lens[i]);
+            off += lens[i];
+        }
+        if (off != meta[7] || bytes[0] != off) throw std::runtime_error("vm_index_adopt: contig lengths do not add up to the reference array");
+        ix->d_ref = (void *)ptrs[0]; ix->d_ht = (void *)ptrs[1]; ix->d_occ = (void *)ptrs[2]; ix->d_kpos = (void *)ptrs[3]; ix->d_koff = (void *)ptrs[4];
+        ix->n_keys = meta[0]; ix->n_occ = meta[1]; ix->n_kpos = meta[2]; ix->ht_slots = (uint64_t)meta[3]; ix->mid_occ_default = (int)meta[4];
+        ix->ref.resize((size_t)off);
+        if (off && cudaMemcpy(&ix->ref[0], ix->d_ref, (size_t)off, cudaMemcpyDeviceToHost) != cudaSuccess)
+            throw std::runtime_error("vm_index_adopt: cannot read the reference array");
+        ix->dev.ht = (const VmHtSlot *)ix->d_ht;
+        ix->dev.ht_mask = ix->ht_slots - 1;
+        ix->dev.occ = (const uint64_t *)ix->d_occ;
+        ix->dev.kpos = (const uint32_t *)ix->d_kpos;
+        ix->dev.koff = (const int64_t *)ix->d_koff;
+        ix->dev.ref = (const uint8_t *)ix->d_ref;
+        ix->dev.ref_len = off;
+        ix->dev.w = ix->w;
+        ix->dev.k = ix->k;
+        ix->dev.mid_occ = ix->mid_occ_default;
+    } catch (const std::exception &e) {
+        c->err = e.what();
+        if (h) { vm_index_free(h->ix); delete h; }
+        return VM_ERR_ARG;
+    }
+    h->ctg.names = h->ix->names;
+    h->ctg.start = h->ix->ctg_start;
+    h->ctg.len = h->ix->ctg_len;
+    h->ctg.seq = h->ix->ref.data();
+    h->ctg.total = (int64_t)h->ix->ref.size();
+    *out = h;
+    return VM_OK;
+}
+
+// The minimizer side of the index for the .mmi writer: the n_keys distinct hashes (ascending), their occurrence counts,
+// and the n_minimizers occurrences (global last-base position << 1 | strand) key after key, ascending inside a key.
+int vm_index_minimizers(vm_index_handle *h, uint64_t *keys, int32_t *counts, uint64_t *occ)
+{
+    if (!h || !keys || !counts || !occ) return VM_ERR_ARG;
+    VmIndex *ix = h->ix;
+    if (ix->d_ukeys && ix->d_ucnt) {
+        if (cudaMemcpy(keys, ix->d_ukeys, (size_t)ix->n_keys * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(counts, ix->d_ucnt, (size_t)ix->n_keys * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(occ, ix->d_occ, (size_t)ix->n_occ * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return VM_ERR_CUDA;
+        return VM_OK;
+    }
+    if (ix->ht.empty()) return VM_ERR_STATE;         // an adopted index keeps no key list
+    std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> ks;
+    for (const VmHtSlot &sl : ix->ht)
+        if (sl.key != VM_HT_EMPTY) ks.push_back({sl.key, {sl.start, sl.count}});
+    std::sort(ks.begin(), ks.end());
+    for (size_t i = 0; i < ks.size(); ++i) { keys[i] = ks[i].first; counts[i] = (int32_t)ks[i].second.second; }
+    memcpy(occ, ix->occ.data(), ix->occ.size() * 8);
     return VM_OK;
 }
 
@@ -68,7 +181,7 @@ int vm_index_info(vm_index_handle *h, int32_t *k, int32_t *w, int32_t *n_contigs
     if (k) *k = h->ix->k;
     if (w) *w = h->ix->w;
     if (n_contigs) *n_contigs = (int32_t)h->ix->names.size();
-    if (n_minimizers) *n_minimizers = (int64_t)h->ix->occ.size();
+    if (n_minimizers) *n_minimizers = h->ix->n_occ;
     if (n_keys) *n_keys = h->ix->n_keys;
     if (mid_occ) *mid_occ = h->ix->mid_occ_default;
     return VM_OK;

@@ -102,6 +102,9 @@ int vm_index_upload(VmIndex *ix, std::string &err)
     if (up(&ix->d_kpos, ix->kpos.data(), ix->kpos.size() * 4, err)) return -1;
     if (up(&ix->d_koff, ix->koff.data(), ix->koff.size() * 8, err)) return -1;
     if (up(&ix->d_ref, ix->ref.data(), ix->ref.size(), err)) return -1;
+    ix->ht_slots = ix->ht.size();
+    ix->n_occ = (int64_t)ix->occ.size();
+    ix->n_kpos = (int64_t)ix->kpos.size();
     ix->dev.ht = (const VmHtSlot *)ix->d_ht;
     ix->dev.ht_mask = ix->ht.size() - 1;
     ix->dev.occ = (const uint64_t *)ix->d_occ;
@@ -118,8 +121,9 @@ int vm_index_upload(VmIndex *ix, std::string &err)
 void vm_index_free(VmIndex *ix)
 {
     if (!ix) return;
-    void *p[] = {ix->d_ht, ix->d_occ, ix->d_kpos, ix->d_koff, ix->d_ref};
-    for (void *q : p)
-        if (q) cudaFree(q);
+    void *p[] = {ix->d_ht, ix->d_occ, ix->d_kpos, ix->d_koff, ix->d_ref, ix->d_ukeys, ix->d_ucnt};
+    if (!ix->borrowed)
+        for (void *q : p)
+            if (q) cudaFree(q);
     delete ix;
 }

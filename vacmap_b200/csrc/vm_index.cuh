@@ -44,8 +44,12 @@ struct VmIndex {
     std::vector<uint32_t> kpos;
     std::vector<int64_t> koff;
     int64_t n_keys = 0;
+    int64_t n_occ = 0, n_kpos = 0;         // minimizer occurrences, 9-mer positions
+    uint64_t ht_slots = 0;
     // device copies
     void *d_ht = nullptr, *d_occ = nullptr, *d_kpos = nullptr, *d_koff = nullptr, *d_ref = nullptr;
+    void *d_ukeys = nullptr, *d_ucnt = nullptr;      // device build: unique minimizer hashes (ascending) and their counts
+    bool borrowed = false;                 // the device arrays belong to the caller (vm_index_adopt)
     VmIndexDev dev{};
 };
 
@@ -167,5 +171,7 @@ __host__ __device__ inline void vm_sketch(const unsigned char *str, int64_t len,
 __host__ __device__ __forceinline__ int vm_code5(unsigned char c) { return vm_nt4(c); }
 
 VmIndex *vm_index_build_host(const std::vector<std::string> &names, const std::vector<std::string> &seqs, int w, int k);
+// the same index built on the device (vm_index_gpu.cu); ix->ref holds the raw concatenated sequence on entry
+int vm_index_build_device(VmIndex *ix, std::string &err);
 int vm_index_upload(VmIndex *ix, std::string &err);
 void vm_index_free(VmIndex *ix);

@@ -74,6 +74,17 @@ __global__ void vm_sketch_chunk_kernel(const uint8_t *__restrict__ reads, const 
     chunk_cnt[cid] = cnt;
 }
 
+// the same kernel for the contigs of a reference (vm_index_gpu.cu)
+int vm_sketch_chunk_size() { return VM_SK_CHUNK; }
+int vm_launch_sketch_chunks(const uint8_t *seq_dev, const int64_t *off_dev, const int64_t *chunk_off_dev, int n_seq, int64_t n_chunks, int w,
+                            int k, uint64_t *mz_hash, uint32_t *mz_posz, int32_t *chunk_cnt, cudaStream_t stream)
+{
+    if (n_chunks <= 0) return 0;
+    vm_sketch_chunk_kernel<<<(unsigned)((n_chunks + 127) / 128), 128, 0, stream>>>(seq_dev, off_dev, chunk_off_dev, n_seq, n_chunks, w, k, mz_hash,
+                                                                                  mz_posz, chunk_cnt);
+    return 1;
+}
+
 // compaction of the per-chunk outputs to the front of each read's slot range: one warp per read
 __global__ void __launch_bounds__(32) vm_sketch_compact_kernel(const int64_t *__restrict__ off, const int64_t *__restrict__ chunk_off,
                                                                const int32_t *__restrict__ chunk_cnt, uint64_t *__restrict__ mz_hash,

@@ -134,3 +134,40 @@ def gather_records(rec_off, recs, cig, dst=0):
         out_recs["cigar_off"][int(rec_start[r]):int(rec_start[r + 1])] += int(cig_start[r])
     off = np.concatenate([[0], np.cumsum(all_counts)]).astype(np.int64)
     return off, out_recs, out_cig
+
+
+def broadcast_index(index, src=0, ctx=None, device=None):
+    """The BUILT index from `src` to every rank over the backend's broadcast (NCCL: HBM to HBM over NVLink): the five
+    device arrays of `Index.arrays()` arrive in torch tensors on every other rank and are adopted there
+    (`Index.adopt`) -- nobody but `src` sketches, sorts or hashes anything.  `index` is ignored on the other ranks.
+    Needs the NCCL backend (the arrays live in device memory)."""
+    from .align import Index
+    rank = dist.get_rank()
+    dev = _device()
+    if dev.type != "cuda":
+        raise RuntimeError("broadcast_index moves device arrays: NCCL backend only")
+    if rank == src:
+        arrs, meta = index.arrays()
+        names = "\n".join(index.names).encode()
+        lens = np.asarray(index.lens, dtype=np.int64)
+        sizes = np.array([b for _, b in arrs], dtype=np.int64)
+    else:
+        arrs, meta, names, lens, sizes = None, np.zeros(8, np.int64), b"", np.zeros(0, np.int64), np.zeros(5, np.int64)
+    names = broadcast_bytes(names, src).decode().split("\n")
+    lens = np.frombuffer(broadcast_bytes(lens.tobytes(), src), dtype=np.int64)
+    meta = np.frombuffer(broadcast_bytes(meta.tobytes(), src), dtype=np.int64)
+    sizes = np.frombuffer(broadcast_bytes(sizes.tobytes(), src), dtype=np.int64)
+    tensors = []
+    for i in range(5):
+        t = torch.empty(int(sizes[i]) + 64, dtype=torch.uint8, device=dev)
+        if rank == src and sizes[i]:
+            import ctypes
+            ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(arrs[i][0]), ctypes.c_size_t(int(sizes[i])),
+                                                   ctypes.c_int(3))
+        dist.broadcast(t, src=src)
+        tensors.append(t)
+    if rank == src:
+        return index
+    torch.cuda.synchronize()
+    return Index.adopt(names, lens, [t.data_ptr() for t in tensors], sizes, meta, ctx=ctx, device=dev.index if device is None else device,
+                       keep=tensors)
