@@ -27,6 +27,22 @@ ERR = 0.10
 REF_LEN = 5_000_000
 WORKLOAD = "10k synthetic ONT reads (15 kb, 10% err) vs 5 Mb reference, -mode H, 1xB200 (BASELINE configs[1])"
 
+# The default run is BASELINE configs[1] (the configuration the metric is quoted on).  --workload cfg2 / cfg3 run the
+# other single-GPU-sized configurations per GPU (their bench lines are kept under profiles/, they are not the headline).
+WORKLOADS = {
+    "cfg1": dict(name=WORKLOAD, mode="H", k=15, w=10, ref_len=REF_LEN, ref_seed=1, n_contigs=1, read_len=READ_LEN, err=ERR, ratio=(4, 3, 3),
+                 reads=10000, read_seed=11, sv=False),
+    "cfg2": dict(name="synthetic HiFi reads (20 kb, 0.5% err) vs GRCh38-sized (3.1 Gb) reference, -mode L -k 19 -w 10 "
+                      "(BASELINE configs[2]; 7 500 reads = 150 Mbp per GPU per step)",
+                 mode="L", k=19, w=10, ref_len=3_100_000_000, ref_seed=2, n_contigs=62, read_len=20000, err=0.005, ratio=(1, 1, 1),
+                 reads=7500, read_seed=12, sv=False),
+    "cfg3": dict(name="10 kb reads (10% err) from donors with nested DEL/INS/INV/DUP/TRA events (vacsim grammar) vs 250 Mb "
+                      "reference, -mode S (BASELINE configs[3]; 10 000 reads per GPU per step)",
+                 mode="S", k=15, w=10, ref_len=250_000_000, ref_seed=3, n_contigs=5, read_len=10000, err=0.10, ratio=(4, 3, 3),
+                 reads=10000, read_seed=31, sv=True),
+}
+WL = WORKLOADS["cfg1"]
+
 
 _STDOUT = None
 
@@ -97,12 +113,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(n_reads, rank=0):
-    """BASELINE configs[1]: i.i.d. 5 Mb reference with 5 % diverged repeats (seed 1); 15 kb reads with
-    10 % i.i.d. errors (sub:ins:del 4:3:3), seed 11 + rank."""
+def make_workload(n_reads, rank=0, ref_only=False):
+    """The workload's synthetic inputs: i.i.d. reference with 5 % diverged repeats in 50 Mb contigs; reads with
+    i.i.d. errors, seed + rank; cfg3: every read's donor segment carries 1-20 adjacent events of vacsim's grammar."""
     import synth
-    ref = synth.make_reference(1, REF_LEN)
-    reads = synth.make_reads(ref, 11 + rank, n_reads, read_len=READ_LEN, err=ERR)
+    ref = synth.make_reference(WL["ref_seed"], WL["ref_len"], n_contigs=WL["n_contigs"])
+    if ref_only:
+        return ref
+    if WL["sv"]:
+        import bulk
+        rng = np.random.default_rng(WL["read_seed"] + rank)
+        arrs = [np.frombuffer(s.encode(), dtype=np.uint8) for _, s in ref]
+        reads = []
+        for i in range(n_reads):
+            a = arrs[int(rng.integers(0, len(arrs)))]
+            st = int(rng.integers(0, len(a) - WL["read_len"]))
+            seg = bulk.nested_sv(rng, a[st:st + WL["read_len"]].copy(), a, int(rng.integers(1, 21)))
+            if rng.random() < 0.5:
+                seg = synth._COMP[seg][::-1]
+            reads.append(("read_%d" % i, synth.mutate(rng, seg, WL["err"], WL["ratio"]).tobytes().decode()))
+    else:
+        reads = synth.make_reads(ref, WL["read_seed"] + rank, n_reads, read_len=WL["read_len"], err=WL["err"], ratio=WL["ratio"])
     enc = [s.encode() for _, s in reads]
     off = np.zeros(n_reads + 1, dtype=np.int64)
     for i, e in enumerate(enc):
@@ -120,17 +151,17 @@ def _cpu_init(ref):
     import oracle
     import oracle.pipeline as pl
     oracle.tables()
-    _CPU["ix"] = oracle.Index(ref, w=10, k=15)
+    _CPU["ix"] = oracle.Index(ref, w=WL["w"], k=WL["k"])
     _CPU["ctg"] = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
 
 
 def _cpu_work(chunk):
     import oracle.pipeline as pl
     import vacmap_b200.align as va
-    opt = va.default_option("H")
+    opt = va.default_option(WL["mode"])
     bases = 0
     for rid, seq in chunk:
-        if pl.align_read(rid, seq, _CPU["ix"], _CPU["ctg"], opt, "H"):
+        if pl.align_read(rid, seq, _CPU["ix"], _CPU["ctg"], opt, WL["mode"]):
             bases += len(seq)
     return bases
 
@@ -163,12 +194,28 @@ class CpuArm:
             self.pool.join()
 
 
+def cpu_inputs(sample, ref=None):
+    """Reference and reads of the bounded CPU sample.  For the GRCh38-sized workload the oracle's single-threaded index
+    build would take many minutes, so its sample is drawn from (and indexed over) the first 250 Mb of the same reference;
+    the per-read cost (chaining, extension) does not depend on the rest."""
+    import synth
+    if ref is None:
+        ref = make_workload(0, ref_only=True)
+    note = ""
+    if WL["ref_len"] > 1_000_000_000:
+        ref = ref[:5]
+        note = "; reference cut to its first 250 Mb for the CPU arm"
+    reads = synth.make_reads(ref, WL["read_seed"], sample, read_len=WL["read_len"], err=WL["err"], ratio=WL["ratio"]) if not WL["sv"] \
+        else make_workload(sample)[1]
+    return ref, reads, note
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cores = os.cpu_count() or 1
     sample = min(args.reads, args.cpu_sample)
-    ref, reads, _, _ = make_workload(sample)
+    ref, reads, _note = cpu_inputs(sample)
     arm = CpuArm(ref, cores)
     for _ in range(max(args.warmup, 1)):
         arm.run(reads[:max(cores * 8, 64)])
@@ -183,7 +230,7 @@ def run_reference(args):
         "impl": "reference", "metric": "aligned_gbp_per_s", "value": v, "unit": "Gbp/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_all / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_step": sample, "read_len": READ_LEN, "err": ERR, "ref_len": REF_LEN},
+        "config": {"workload": WL["name"], "reads_per_step": sample, "read_len": WL["read_len"], "err": WL["err"], "ref_len": WL["ref_len"]},
         "cpu_baseline": {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
                          "sample": "%d reads of the workload per step; oracle port (C stages + Python glue), %d persistent worker "
                                    "processes, warmed" % (sample, cores)},
@@ -210,13 +257,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10000, help="reads per GPU per step (configs[1]: 10k)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU per step (0 = the workload's: configs[1] 10k)")
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS), help="cfg1 = BASELINE configs[1] (the headline)")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="reads in the bounded CPU baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workers", type=int, default=0, help="sub-batches in flight per GPU (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="reads per sub-batch (0 = automatic)")
     ap.add_argument("--ahead", type=int, default=2, help="steps submitted ahead of the one being collected")
     args = ap.parse_args()
+    global WL
+    WL = WORKLOADS[args.workload]
+    if args.reads <= 0:
+        args.reads = WL["reads"]
     # stdout carries exactly one line, the JSON: everything else that writes to fd 1 while the run lasts (NCCL's
     # version banner, library chatter) is sent to stderr, and the line goes out through the saved descriptor
     global _STDOUT
@@ -254,13 +306,16 @@ def main():
     # reads shard across ranks (no data-path collective): weak scaling, fixed work per GPU
     ref, reads, cat, off = make_workload(args.reads, rank)
     if dist is not None:
-        # the one-time collective of the design: the reference goes out from rank 0 over NCCL, every rank then
-        # builds its own index replica in its own HBM
         from vacmap_b200 import shard
-        ref = shard.broadcast_reference(ref if rank == 0 else None)
     ctx = vb._lib.Context(local_rank)
-    ix = vb.Index(ref, w=10, k=15, ctx=ctx)
-    al = vb.Aligner(ix, vb.default_option("H"), "H", workers=args.workers, chunk_reads=args.chunk)
+    t_ix = time.perf_counter()
+    if dist is not None and os.environ.get("VM_BROADCAST_INDEX", "1") != "0":
+        # the index is built once, on rank 0's GPU, and the BUILT tables go out over NCCL (HBM to HBM)
+        ix = shard.broadcast_index(vb.Index(ref, w=WL["w"], k=WL["k"], ctx=ctx) if rank == 0 else None, ctx=ctx, device=local_rank)
+    else:
+        ix = vb.Index(ref, w=WL["w"], k=WL["k"], ctx=ctx)
+    index_s = time.perf_counter() - t_ix
+    al = vb.Aligner(ix, vb.default_option(WL["mode"]), WL["mode"], workers=args.workers, chunk_reads=args.chunk)
     bases = int(off[-1])
 
     # ---- device-resident: reads already in HBM when the timed region starts ----
@@ -331,11 +386,17 @@ def main():
     # events the library records on its launching stream; the pipelined legs above overlap kernels of several
     # workers, which stretches their individual durations ----
     solo = {}
+    solo_note = None
     if rank == 0:
-        al1 = vb.Aligner(ix, vb.default_option("H"), "H", workers=1)
-        for _ in range(2):
-            al1.align_packed(cat, off, resident=True)
-            solo = dict(al1.last_stage_ms)
+        al1 = vb.Aligner(ix, vb.default_option(WL["mode"]), WL["mode"], workers=1)
+        try:
+            for _ in range(2):
+                al1.align_packed(cat, off, resident=True)
+                solo = dict(al1.last_stage_ms)
+        except Exception as e:      # e.g. not enough HBM left for whole-batch arenas beside the workers' (GRCh38-sized index)
+            sys.stderr.write("lock-step roofline leg failed (%s): kernel times taken from the pipelined steps\n" % e)
+            solo = {k: v / args.steps for k, v in stage.items()}
+            solo_note = "kernel times from the pipelined steps (stretched by the overlap of the workers): the lock-step pass did not fit"
 
     t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
     tot = torch.tensor([aligned, aligned_e2e, len(recs)], dtype=torch.float64, device="cuda")
@@ -385,8 +446,8 @@ def main():
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "kernel_ms": kern[top],
                     "kernel_ms_in_pipeline_per_step": per_step.get(top),
-                    "timing": "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
-                              "'launch' = the kernel's launches of one step (one per capacity class)",
+                    "timing": solo_note or "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
+                                           "'launch' = the kernel's launches of one step (one per capacity class)",
                     "bytes": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
                     "gcups_full_matrix_equivalent": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
                     "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
@@ -395,11 +456,11 @@ def main():
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "reads_per_gpu_per_step": args.reads, "read_len": READ_LEN, "err": ERR,
-                           "ref_len": REF_LEN, "mode": "H", "k": 15, "w": 10,
+                "config": {"workload": WL["name"], "reads_per_gpu_per_step": args.reads, "read_len": WL["read_len"], "err": WL["err"],
+                           "ref_len": WL["ref_len"], "mode": WL["mode"], "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2),
                            "l2": "per-step working set (reads 2x%.0f MB + anchors, hits, direction matrices >1 GB) exceeds "
                                  "the 126 MB L2" % (bases / 1e6),
-                           "sharding": "reads split across ranks (no data-path collective); reference broadcast from rank 0 over NCCL; records "
+                           "sharding": "reads split across ranks (no data-path collective); index built on rank 0's GPU and broadcast as built tables over NCCL; records "
                                        "emitted per rank (SURVEY 8e) -- gather_ms = one warmed gather of a step's records to rank 0, optional",
                            "pipelining": "steps submitted %d ahead of their collection (vm_align_submit / vm_align_wait), all K "
                                          "steps complete inside the timed region" % args.ahead},
@@ -412,9 +473,10 @@ def main():
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             sample = min(args.reads, args.cpu_sample)
-            arm = CpuArm(ref, cores)
-            arm.run(reads[:max(cores * 8, 64)])
-            v, dt = arm.run(reads[:sample])
+            ref_c, reads_c, note = cpu_inputs(sample, ref)
+            arm = CpuArm(ref_c, cores)
+            arm.run(reads_c[:max(cores * 8, 64)])
+            v, dt = arm.run(reads_c[:sample])
             arm.close()
             line["cpu_baseline"] = {"value": v, "unit": "Gbp/s", "cores": cores, "kind": "port",
                                     "sample": "%d reads of the workload, oracle port (C stages + Python glue), %d persistent worker "

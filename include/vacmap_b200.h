@@ -171,6 +171,10 @@ int vm_index_arrays(vm_index_handle *h, const void **ptrs, int64_t *bytes, int64
 int vm_index_adopt(vm_ctx *ctx, int32_t n_contigs, const char *const *names, const int64_t *lens, const void *const *ptrs,
                    const int64_t *bytes, const int64_t *meta, vm_index_handle **out);
 int vm_index_minimizers(vm_index_handle *h, uint64_t *keys, int32_t *counts, uint64_t *occ);
+/* np.argsort as numba compiles it (numba/misc/quicksort.py: median-of-three quicksort, insertion sort below 15 elements)
+ * on int64 keys: order[n].  Host function; the Python mirrors of the reference's asm-mode code use it where the reference
+ * sorts inside njit functions (mammap_asm.py:22754-22755). */
+int vm_argsort_i64(const int64_t *keys, int64_t n, int64_t *order);
 int vm_index_info(vm_index_handle *h, int32_t *k, int32_t *w, int32_t *n_contigs, int64_t *n_minimizers,
                   int64_t *n_keys, int32_t *mid_occ);
 /* contig i: name, global start offset (`seq_offset[i][2]`), length, pointer to its (library-owned) sequence */

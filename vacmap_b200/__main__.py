@@ -32,7 +32,8 @@ def build_parser():
     p = argparse.ArgumentParser(prog="vacmap_b200", description="VACmap per-read alignment path on B200 (CUDA)")
     p.add_argument("-ref", required=True)
     p.add_argument("-read", required=True, nargs="+")
-    p.add_argument("-mode", required=True, choices=["H", "L", "S"])
+    p.add_argument("-mode", required=True, choices=["H", "L", "S", "asm"])
+    p.add_argument("-workdir", help="accepted for compatibility with the reference's `-mode asm` (nothing is spilled to disk here)")
     p.add_argument("-o", default="-")
     p.add_argument("--force", action="store_true")
     p.add_argument("--nowriteindex", action="store_true", help="do not save the reference index (<ref>.w{w}_k{k}.mmi) for reuse")
@@ -58,9 +59,11 @@ def build_parser():
 
 def options_from(args):
     """The `pdict` of vacmap:177-296 (mode defaults, `golbal_` spelling and all)."""
-    opt = align.default_option(args.mode)
-    opt.update({"c": args.c, "eqx": args.eqx, "md": args.MD, "cigar2cg": args.L, "copycomments": args.copycomments, "H": args.H,
-                "fakecigar": args.fakecigar, "Q": args.Q, "rg-id": rg_metadata(args)["ID"], "golbal_maxdiff": args.globalmaxdiff,
+    opt = align.default_option("S" if args.mode == "asm" else args.mode)
+    if args.mode == "asm":
+        opt["eqx"] = True                  # vacmap:243-244: asm mode forces --eqx
+    opt.update({"c": args.c, "eqx": args.eqx or args.mode == "asm", "md": args.MD, "cigar2cg": args.L, "copycomments": args.copycomments, "H": args.H,
+                "fakecigar": args.fakecigar, "Q": args.Q, "mode": args.mode, "rg-id": rg_metadata(args)["ID"], "golbal_maxdiff": args.globalmaxdiff,
                 "local_maxdiff": args.localmaxdiff, "shortcs": args.cs != "long"})
     if args.maxdivergence is not None:
         opt["maxdivergence"] = args.maxdivergence
@@ -120,6 +123,24 @@ def main(argv=None):
     try:
         out.write(sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
                                   command_line=" ".join(sys.argv if argv is None else ["vacmap_b200"] + list(argv))))
+        if args.mode == "asm":
+            # one contig at a time (the reference's asm workers, vacmap:394-397 -> assembly_get_readmap_DP_test) and the mode's
+            # own emitter (iterator_get_bam_dict_str, mammap_asm.py:22757-22941)
+            from . import asm
+            seen = set()
+            for path in args.read:
+                for rec in align.read_fastx(path):
+                    if rec[0] in seen:
+                        continue
+                    seen.add(rec[0])
+                    rows = asm.assembly_align(rec[0], rec[1], index, opt)
+                    if not rows:
+                        continue
+                    qual = None if (args.Q or len(rec) < 3) else rec[2]
+                    for line in sam.iterator_get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
+                                                              opt["cigar2cg"], opt["markunbalancetra"], opt):
+                        out.write(line + "\n")
+            return
         pending = None
 
         def collect(p):

@@ -122,8 +122,10 @@ static void vm_host_large_readgap(int maxgap, int large_readgap, std::vector<flo
     }
 }
 
-static const int kCaps[] = {256, 512, 1024, 2048, 4096, 8192, VM_CHAIN_SMEM_CAP};
-static const int kNumCaps = 7;
+// shared-memory capacity classes of the DP kernels (12 B per anchor): fine steps where the reads are (a 15 kb read has
+// 0.5-2 k anchors per DP), so that a class wastes little of the SM's shared memory and more reads are resident
+static const int kCaps[] = {128, 256, 384, 512, 768, 1024, 1536, 2048, 3072, 4096, 6144, 8192, VM_CHAIN_SMEM_CAP};
+static const int kNumCaps = 13;
 
 // Fill VmChainArgs from ctx + state (device pointers).
 static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, VmChainArgs &A)

@@ -427,6 +427,7 @@ public:
     {
         const int nj = (int)jobs.size();
         WallTimer *hs = new WallTimer(this, "h_reseed_stage");
+        const bool from_device = false;
         J.assign((size_t)nj, VmReseedJobDev());
         std::vector<int64_t> w_off((size_t)nj + 1, 0), g_off((size_t)nj + 1, 0);
         for (int j = 0; j < nj; ++j) {
@@ -457,26 +458,35 @@ public:
             std::copy(g.gx.begin(), g.gx.end(), gx + g_off[j]);
             std::copy(g.gy.begin(), g.gy.end(), gy + g_off[j]);
         }, 64);
+        BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
+        BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
+        BE_OK(d_gx_.ensure(n_g * 4 + 64));
+        BE_OK(d_gy_.ensure(n_g * 8 + 64));
+        BE_OK(cudaMemcpyAsync(d_wlo_.p, wlo.data(), wlo.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gx_.p, gx, n_g * 4, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(cudaMemcpyAsync(d_gy_.p, gy, n_g * 8, cudaMemcpyHostToDevice, c_->stream));
+        reseed_run(J, n_out, d_n_out, hs, from_device);
+    }
+
+    // The re-seeding kernels over the job slots J (host copy; windows and guide points already in d_wlo_ / d_whi_ / d_gx_ /
+    // d_gy_ on the device).  A slot with n_guide == 0 is empty.  hs: the staging timer to close before the kernels.
+    void reseed_run(std::vector<VmReseedJobDev> &J, std::vector<int32_t> &n_out, int32_t *&d_n_out, WallTimer *hs, bool from_device)
+    {
+        (void)from_device;
+        const int nj = (int)J.size();
         // one pass with room for 3 hits per read position; the rare job that needs more is re-run below
         int64_t hit_off = 0;
         for (int j = 0; j < nj; ++j) {
             const int64_t span = std::max<int64_t>(0, (int64_t)J[j].readend - J[j].readstart);
             J[j].hit_off = hit_off;
-            J[j].hit_cap = (int32_t)std::min<int64_t>(3 * span + 64, INT32_MAX);
+            J[j].hit_cap = J[j].n_guide > 0 ? (int32_t)std::min<int64_t>(3 * span + 64, INT32_MAX) : 0;
             hit_off += J[j].hit_cap;
         }
-        BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev)));
-        BE_OK(d_wlo_.ensure(wlo.size() * 8 + 64));
-        BE_OK(d_whi_.ensure(whi.size() * 8 + 64));
-        BE_OK(d_gx_.ensure(n_g * 4 + 64));
-        BE_OK(d_gy_.ensure(n_g * 8 + 64));
+        BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev) + 64));
         BE_OK(d_nh_.ensure((size_t)nj * 8 + 64));
         BE_OK(d_hits_.ensure((size_t)hit_off * vm_reseed_hit_bytes() + 64));
         BE_OK(cudaMemcpyAsync(jobs_.p, J.data(), J.size() * sizeof(VmReseedJobDev), cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_wlo_.p, wlo.data(), wlo.size() * 8, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_whi_.p, whi.data(), whi.size() * 8, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_gx_.p, gx, n_g * 4, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(cudaMemcpyAsync(d_gy_.p, gy, n_g * 8, cudaMemcpyHostToDevice, c_->stream));
         int32_t *d_n_hits = d_nh_.as<int32_t>();
         d_n_out = d_nh_.as<int32_t>() + nj;
         const VmIndexDev &ix = ih_->ix->dev;
@@ -528,7 +538,7 @@ public:
             J[j].dense_off = dense_hits;
             dense_hits += n_hits[j];
             // the merge kernel gives every lane a 32nd of the table: at most a quarter full on average
-            int ts = 2048;
+            int ts = J[j].n_guide > 0 ? 2048 : 32;      // an empty slot has no table
             while (ts < 2 * (n_hits[j] + 8)) ts <<= 1;
             J[j].tab_off = tab_off;
             J[j].tab_size = ts;
@@ -588,21 +598,37 @@ public:
         std::vector<int32_t> n_out;
         int32_t *d_n_out = nullptr;
         reseed_device(need_reverse, jobs, J, n_out, d_n_out);
-        // concatenate the jobs of each read into one dense anchor list on the device
-        std::vector<int64_t> seg(2 * (size_t)nj);   // [src_off | dst_off]
-        int64_t dense = 0;
+        // the jobs of a read are consecutive, reads in order
+        std::vector<int32_t> job_lo((size_t)n, 0), job_n((size_t)n, 0);
         {
             size_t q = 0;
             for (int64_t r = 0; r < n; ++r) {
-                out.start[r] = dense;
-                while (q < jobs.size() && jobs[q].read == r) {
-                    seg[q] = 2 * J[q].dense_off;
-                    seg[(size_t)nj + q] = dense;
-                    dense += n_out[q];
-                    ++q;
-                }
-                out.cnt[r] = variant[r] ? (int32_t)(dense - out.start[r]) : 0;
+                job_lo[(size_t)r] = (int32_t)q;
+                while (q < jobs.size() && jobs[q].read == r) ++q;
+                job_n[(size_t)r] = (int32_t)(q - (size_t)job_lo[(size_t)r]);
             }
+        }
+        reseed_chain_finish(b, J, n_out, d_n_out, job_lo, job_n, variant, skipcost, maxdiff, maxgap, out);
+    }
+
+    // concatenate the anchors of each read's jobs (slots [job_lo[r], job_lo[r] + job_n[r]) of J), chain them, trace back
+    void reseed_chain_finish(const ReadBatch &b, const std::vector<VmReseedJobDev> &J, const std::vector<int32_t> &n_out, int32_t *d_n_out,
+                             const std::vector<int32_t> &job_lo, const std::vector<int32_t> &job_n, const std::vector<int> &variant,
+                             const std::vector<double> &skipcost, int maxdiff, int maxgap, ChainOut &out)
+    {
+        const int64_t n = b.n;
+        const int nj = (int)J.size();
+        // one dense anchor list per read on the device
+        std::vector<int64_t> seg(2 * (size_t)nj, 0);   // [src_off | dst_off]
+        int64_t dense = 0;
+        for (int64_t r = 0; r < n; ++r) {
+            out.start[r] = dense;
+            for (int32_t q = job_lo[(size_t)r]; q < job_lo[(size_t)r] + job_n[(size_t)r]; ++q) {
+                seg[(size_t)q] = 2 * J[(size_t)q].dense_off;
+                seg[(size_t)nj + (size_t)q] = dense;
+                dense += n_out[(size_t)q];
+            }
+            out.cnt[r] = variant[r] ? (int32_t)(dense - out.start[r]) : 0;
         }
         BE_OK(d_dense_.ensure((size_t)std::max<int64_t>(dense, 1) * sizeof(VmAnchor)));
         BE_OK(d_seg_.ensure(seg.size() * 8 + 64));

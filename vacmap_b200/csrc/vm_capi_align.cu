@@ -144,6 +144,19 @@ int vm_index_adopt(vm_ctx *c, int32_t n_contigs, const char *const *names, const
     return VM_OK;
 }
 
+// numba's argsort (np.argsort inside njit code: numba/misc/quicksort.py) of int64 keys, ties and all -- the host mirrors of
+// the reference's Python need it wherever the reference sorts inside njit functions (mammap_asm.py:22754-22755, clrnano:23103)
+int vm_argsort_i64(const int64_t *keys, int64_t n, int64_t *order)
+{
+    if (n < 0 || (n > 0 && (!keys || !order))) return VM_ERR_ARG;
+    try {
+        std::vector<int64_t> R;
+        vmg::argsort_replay<int64_t>(keys, n, R);
+        if (n) memcpy(order, R.data(), (size_t)n * 8);
+    } catch (const std::exception &) { return VM_ERR_NOMEM; }
+    return VM_OK;
+}
+
 // The minimizer side of the index for the .mmi writer: the n_keys distinct hashes (ascending), their occurrence counts,
 // and the n_minimizers occurrences (global last-base position << 1 | strand) key after key, ascending inside a key.
 int vm_index_minimizers(vm_index_handle *h, uint64_t *keys, int32_t *counts, uint64_t *occ)

@@ -351,35 +351,60 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
                 const VmAnchor aj = a[j];
                 t = vm_pair_score<VARIANT>(c, ai, aj, Sj, skip);
             }
-            // running max the reference would hold just before visiting this lane's j
-            double inc = t;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double o = __shfl_up_sync(VM_FULL, inc, d);
-                if (lane >= d && o > inc) inc = o;
-            }
-            double exc = __shfl_up_sync(VM_FULL, inc, 1);
-            if (lane == 0 || !(exc > max_scores)) exc = max_scores;
-            bool brk;
-            if (GLOBAL) brk = valid && !(Sj > (exc - li));         // :24949 / else break :25003
-            else brk = valid && (Sj < (exc - li));                 // :27413
-            const unsigned bm = __ballot_sync(VM_FULL, brk);
+            // ---- break position and winner of the chunk ----
+            // The reference visits the lanes in order, keeps a running maximum `exc`, stops at the first lane whose S can
+            // no longer win (S <= exc - l_i), and the first strictly better candidate wins.  Fast path: one warp-wide
+            // arg-max (two REDUX on an order-preserving 64-bit key + a ballot).  With X = max(max_scores, M), M the
+            // chunk's maximum at lane bl, every lane behind bl has exc = X exactly and every lane has exc <= X, and S is
+            // non-increasing along the lanes -- so the lanes that stop under X form a suffix starting at first', and when
+            // first' > bl it is the reference's break position exactly (lanes before it do not stop even under X, lanes
+            // from it on see exc = X).  Only when the stop would fall at or before the winner is the exact running maximum
+            // needed (prefix-max ladder, as before).
+            unsigned long long ukey = (unsigned long long)__double_as_longlong(t);
+            ukey = (ukey >> 63) ? ~ukey : (ukey | 0x8000000000000000ULL);
+            const unsigned khi = (unsigned)(ukey >> 32), klo = (unsigned)ukey;
+            const unsigned mh = __reduce_max_sync(VM_FULL, khi);
+            const unsigned ml = __reduce_max_sync(VM_FULL, khi == mh ? klo : 0u);
+            const unsigned wmask = __ballot_sync(VM_FULL, khi == mh && klo == ml);
+            int bl = __ffs(wmask) - 1;                                // lowest lane attaining the maximum
+            unsigned long long mkey = (unsigned long long)mh << 32 | ml;
+            mkey = (mkey >> 63) ? (mkey & 0x7fffffffffffffffULL) : ~mkey;
+            double bt = __longlong_as_double((long long)mkey);
+            const double X = bt > max_scores ? bt : max_scores;
             const unsigned vm = __ballot_sync(VM_FULL, valid);
             const int nvalid = __popc(vm);
+            unsigned bm;
+            if (GLOBAL) bm = __ballot_sync(VM_FULL, valid && !(Sj > (X - li)));
+            else bm = __ballot_sync(VM_FULL, valid && (Sj < (X - li)));
             int first = bm ? (__ffs(bm) - 1) : nvalid;
-            // lanes at/after the break are never evaluated
-            if (lane >= first) t = -CUDART_INF;
+            if (first <= bl) {
+                // exact running max the reference would hold just before visiting each lane's j
+                double inc = t;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const double o = __shfl_up_sync(VM_FULL, inc, d);
+                    if (lane >= d && o > inc) inc = o;
+                }
+                double exc = __shfl_up_sync(VM_FULL, inc, 1);
+                if (lane == 0 || !(exc > max_scores)) exc = max_scores;
+                bool brk;
+                if (GLOBAL) brk = valid && !(Sj > (exc - li));         // :24949 / else break :25003
+                else brk = valid && (Sj < (exc - li));                 // :27413
+                bm = __ballot_sync(VM_FULL, brk);
+                first = bm ? (__ffs(bm) - 1) : nvalid;
+                // lanes at/after the break are never evaluated: arg-max over the lanes before it, lowest lane wins ties
+                double tt = lane >= first ? -CUDART_INF : t;
+                bt = tt;
+                bl = lane;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    const double ot = __shfl_xor_sync(VM_FULL, bt, d);
+                    const int ol = __shfl_xor_sync(VM_FULL, bl, d);
+                    if (ot > bt || (ot == bt && ol < bl)) { bt = ot; bl = ol; }
+                }
+            }
             if (GLOBAL) opcount += first;                            // counted inside the if (:24951)
             else opcount += bm ? first + 1 : nvalid;                 // counted before the test (:27410)
-            // arg-max, lowest lane (= first visited) wins ties
-            double bt = t;
-            int bl = lane;
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const double ot = __shfl_xor_sync(VM_FULL, bt, d);
-                const int ol = __shfl_xor_sync(VM_FULL, bl, d);
-                if (ot > bt || (ot == bt && ol < bl)) { bt = ot; bl = ol; }
-            }
             const int bj = __shfl_sync(VM_FULL, j, bl);
             if (bt > max_scores) { max_scores = bt; pre_index = bj; }
             if (bm) break;

@@ -136,6 +136,13 @@ def gather_records(rec_off, recs, cig, dst=0):
     return off, out_recs, out_cig
 
 
+class _DevView:
+    """Device memory owned by someone else, exposed through the CUDA array interface (1-D uint8)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 def broadcast_index(index, src=0, ctx=None, device=None):
     """The BUILT index from `src` to every rank over the backend's broadcast (NCCL: HBM to HBM over NVLink): the five
     device arrays of `Index.arrays()` arrive in torch tensors on every other rank and are adopted there
@@ -159,12 +166,13 @@ def broadcast_index(index, src=0, ctx=None, device=None):
     sizes = np.frombuffer(broadcast_bytes(sizes.tobytes(), src), dtype=np.int64)
     tensors = []
     for i in range(5):
-        t = torch.empty(int(sizes[i]) + 64, dtype=torch.uint8, device=dev)
-        if rank == src and sizes[i]:
-            import ctypes
-            ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(arrs[i][0]), ctypes.c_size_t(int(sizes[i])),
-                                                   ctypes.c_int(3))
-        dist.broadcast(t, src=src)
+        if rank == src:
+            # a zero-copy torch view of the library's device array (CUDA array interface): the source of the broadcast
+            t = torch.as_tensor(_DevView(arrs[i][0], int(sizes[i])), device=dev) if sizes[i] else torch.empty(0, dtype=torch.uint8, device=dev)
+        else:
+            t = torch.empty(int(sizes[i]), dtype=torch.uint8, device=dev)
+        if sizes[i]:
+            dist.broadcast(t, src=src)
         tensors.append(t)
     if rank == src:
         return index
