@@ -103,6 +103,130 @@ struct OracleBackend : public Backend {
         return out;
     }
 
+    // ---- front half through vm_dgrun.hpp / vm_dglue.hpp (what the CUDA kernels run), over a host copy of what the
+    // extraction kernel leaves behind ----
+    std::unique_ptr<vmd::FrontHalf<OracleExec>> front;
+    std::vector<vmd::RJob> fJ;
+    std::vector<vmd::ExtractRec> fx;
+    std::vector<int64_t> f_wlo, f_whi, f_gy;
+    std::vector<int32_t> f_gx;
+    bool has_device_front() const override { return device_ext; }
+
+    // vm_extract_global_kernel on the host: primary chain + residual chains with score > 40, discovery order
+    static void extract_global_host(const ChainOut &g, int64_t r, double accept, std::vector<vmd::A32> &anc, std::vector<double> &S_out,
+                                    std::vector<int32_t> &len, std::vector<double> &score, vmd::ExtractRec &rec)
+    {
+        memset(&rec, 0, sizeof(rec));
+        const int64_t n = g.cnt[(size_t)r], gm = g.gmax[(size_t)r];
+        if (n <= 0 || gm < 0) return;
+        const Anc32 *a = g.sorted + g.start[(size_t)r];
+        const double *S = g.S + g.start[(size_t)r];
+        const int32_t *P = g.P + g.start[(size_t)r], *A = g.S_arg + g.start[(size_t)r];
+        std::vector<char> used((size_t)n, 0);
+        std::vector<vmd::A32> ta;
+        std::vector<double> tS, tscore;
+        std::vector<int32_t> tlen;
+        bool hit = false;
+        {
+            int64_t take = gm;
+            used[(size_t)take] = 1;
+            const double sc = S[take];
+            for (;;) {
+                ta.push_back(vmd::A32{a[take].x, a[take].y, a[take].s, a[take].l});
+                tS.push_back(S[take]);
+                if (P[take] == vmg::kNoPre) break;
+                take = P[take];
+                used[(size_t)take] = 1;
+            }
+            if (sc > 40) { hit = true; tlen.push_back((int32_t)ta.size()); tscore.push_back(sc); }
+            else { ta.clear(); tS.clear(); }
+        }
+        const double scores = S[gm], max_scores = scores > 0 ? scores : 0;
+        if (!(hit && max_scores > accept)) return;
+        for (int64_t q = n - 1; q >= 0; --q) {
+            int64_t take = A[q];
+            if (used[(size_t)take]) continue;
+            const size_t k0 = ta.size();
+            used[(size_t)take] = 1;
+            double sc = S[take];
+            for (;;) {
+                ta.push_back(vmd::A32{a[take].x, a[take].y, a[take].s, a[take].l});
+                tS.push_back(0.0);
+                if (P[take] == vmg::kNoPre) break;
+                take = P[take];
+                if (used[(size_t)take]) { sc = sc - S[take]; break; }
+                used[(size_t)take] = 1;
+            }
+            if (sc > 40) { tlen.push_back((int32_t)(ta.size() - k0)); tscore.push_back(sc); }
+            else { ta.resize(k0); tS.resize(k0); }
+        }
+        rec.n_anc = (int32_t)ta.size();
+        rec.n_chains = (int32_t)tlen.size();
+        rec.anc_off = (long long)anc.size();
+        rec.meta_off = (long long)len.size();
+        anc.insert(anc.end(), ta.begin(), ta.end());
+        S_out.insert(S_out.end(), tS.begin(), tS.end());
+        len.insert(len.end(), tlen.begin(), tlen.end());
+        score.insert(score.end(), tscore.begin(), tscore.end());
+    }
+
+    double accept_ = 60.0;
+    bool front_device(const ReadBatch &b, const std::vector<char> &need_reverse, const ChainOut &g, int max_guides,
+                      std::vector<vmd::FrontOut> &fo) override
+    {
+        if (!device_ext) return false;
+        const int64_t n = b.n;
+        std::vector<vmd::ExtractRec> xrec((size_t)n);
+        std::vector<vmd::A32> anc;
+        std::vector<double> S, score;
+        std::vector<int32_t> len, ids, nrev((size_t)n);
+        std::vector<int64_t> off((size_t)n + 1);
+        // reads in REVERSE order: meta_off / anc_off must not be assumed to grow with the read index
+        for (int64_t r = n - 1; r >= 0; --r) extract_global_host(g, r, accept_, anc, S, len, score, xrec[(size_t)r]);
+        for (int64_t r = 0; r <= n; ++r) off[(size_t)r] = b.off[r] - b.off[0];
+        for (int64_t r = 0; r < n; ++r) {
+            nrev[(size_t)r] = need_reverse[(size_t)r] ? 1 : 0;
+            if (g.cnt[(size_t)r] > 2) ids.push_back((int32_t)r);
+        }
+        anc.push_back(vmd::A32{0, 0, 0, 0}); S.push_back(0); len.push_back(0); score.push_back(0);
+        vmd::FrontInput in;
+        in.n_reads = n; in.read_off = off.data();
+        in.ctg.start = ctg->start.data(); in.ctg.len = ctg->len.data(); in.ctg.n = (int32_t)ctg->start.size();
+        in.need_reverse = nrev.data();
+        in.xrec = xrec.data(); in.anc = anc.data(); in.S = S.data(); in.chain_len = len.data(); in.chain_score = score.data();
+        in.NA = (int64_t)anc.size() - 1; in.NC = (int64_t)len.size() - 1;
+        in.max_guides = max_guides; in.kmer = 9;
+        std::vector<vmd::RJob> jobs((size_t)in.NC + 1);
+        f_wlo.assign((size_t)in.NA + 1, 0); f_whi.assign((size_t)in.NA + 1, 0); f_gx.assign((size_t)in.NA + 1, 0); f_gy.assign((size_t)in.NA + 1, 0);
+        exec.be = this;
+        if (!front) front.reset(new vmd::FrontHalf<OracleExec>(exec));
+        front->run(in, ids, jobs.data(), f_wlo.data(), f_whi.data(), f_gx.data(), f_gy.data(), fo, fJ, fx);
+        return true;
+    }
+
+    void reseed_chain_front(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<vmd::FrontOut> &fo,
+                            const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                            ChainOut &out) override
+    {
+        // back to the job form of the host path, in read order, for the oracle's re-seeding
+        std::vector<GuideJobRef> jobs;
+        for (int64_t r = 0; r < b.n; ++r) {
+            if (variant[(size_t)r] == 0) continue;
+            for (int q = 0; q < fo[(size_t)r].n_jobs; ++q) {
+                const vmd::RJob &J = fJ[(size_t)(fx[(size_t)r].meta_off + q)];
+                GuideJobRef gj;
+                gj.read = (int32_t)r;
+                gj.job.readstart = J.readstart; gj.job.readend = J.readend;
+                gj.job.win_lo.assign(f_wlo.begin() + J.win_off, f_wlo.begin() + J.win_off + J.n_win);
+                gj.job.win_hi.assign(f_whi.begin() + J.win_off, f_whi.begin() + J.win_off + J.n_win);
+                gj.job.gx.assign(f_gx.begin() + J.g_off, f_gx.begin() + J.g_off + J.n_guide);
+                gj.job.gy.assign(f_gy.begin() + J.g_off, f_gy.begin() + J.g_off + J.n_guide);
+                jobs.push_back(std::move(gj));
+            }
+        }
+        reseed_chain(b, need_reverse, jobs, variant, skipcost, maxdiff, maxgap, out);
+    }
+
     bool has_device_extension() const override { return device_ext; }
     bool extend_device(const ReadBatch &b, const std::vector<int32_t> &ids, const std::vector<char> &need_reverse,
                        const std::vector<int32_t> &mapq, const vmg::Options &opt, std::vector<int32_t> &status, FlatRecords &out) override
@@ -408,6 +532,7 @@ int64_t gt_align_batch(void *orc_index, const orc_tables *tb, const char *ref, c
     opt.mode = vmg::ModeConst{o->accept, o->max_guides, o->local_maxgap, o->clamp40 != 0};
     OracleBackend be(orc_index, tb, ref);
     be.ctg = &ctg;
+    be.accept_ = o->accept;
     be.device_ext = getenv("GT_DEVICE_GLUE") != nullptr;
     Driver drv(be, ctg, opt, o->kmersize, o->threads);
     std::map<std::string, double> phase_ms;

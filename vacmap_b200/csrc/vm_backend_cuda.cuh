@@ -105,6 +105,7 @@ public:
     CudaBackend(vm_ctx *c, vm_index_handle *ih) : c_(c), ih_(ih)
     {
         device_extension = getenv("VM_HOST_GLUE") == nullptr;      // A/B switch: the vector-based host glue of round 1
+        device_front = device_extension && getenv("VM_HOST_FRONT") == nullptr;
     }
     ~CudaBackend() override
     {
@@ -124,6 +125,7 @@ public:
         bplanbufs_.release();
         fplanbufs_.release();
         back_.reset();
+        front_.reset();
         VmPinnedBuf *p[] = {&h_sorted_, &h_S_, &h_P_, &h_A_, &h_gmax_, &h_jobs_, &h_cig_, &h_lsorted_, &h_lP_, &h_lgmax_, &h_misc_, &h_gx_, &h_gy_,
                             &h_segs_};
         for (VmPinnedBuf *x : p) x->release();
@@ -131,6 +133,7 @@ public:
     StageTimer timer;
     bool reads_resident = false;    // vm_reads_upload already put this batch in HBM
     bool device_extension = true;   // extend_func's glue runs on the device (extend_device); false: the host glue of vm_glue.hpp
+    bool device_front = true;       // hit2work_1's bookkeeping, guide selection and re-seeding jobs on the device (front_device)
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
     double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0, fill_band_jobs_ = 0,
@@ -290,6 +293,7 @@ public:
         VmDevBuf al_rec, al_anc, al_len;
         VmPinnedBuf h_al_rec, h_al_anc, h_al_len;
         size_t al_n_anc = 0, al_n_al = 0;
+        size_t n_anc_total = 0, n_chain_total = 0;      // global stage: extracted anchors / chains of the chunk
         void release()
         {
             VmDevBuf *d[] = {&rec, &anc, &S, &len, &score, &counters, &al_rec, &al_anc, &al_len};
@@ -370,6 +374,14 @@ public:
         BE_OK(X.h_counters.ensure(64));
         BE_OK(X.h_rec.ensure((size_t)(n + 1) * sizeof(VmExtractRec)));
         BE_OK(cudaMemcpyAsync(X.h_counters.p, X.counters.p, 32, cudaMemcpyDeviceToHost, c_->stream));
+        if (global && device_front) {
+            // hit2work_1's bookkeeping runs on the device (front_device): only the totals cross PCIe
+            BE_OK(vm_stream_sync(c_->stream));
+            BE_OK(cudaGetLastError());
+            X.n_anc_total = (size_t)X.h_counters.as<unsigned long long>()[0];
+            X.n_chain_total = (size_t)X.h_counters.as<unsigned long long>()[1];
+            return;
+        }
         if (!global && device_extension && rebuild) {
             // the extension stage runs on the device (extend_device): only the totals cross PCIe
             BE_OK(vm_stream_sync(c_->stream));
@@ -1238,6 +1250,76 @@ public:
     }
 
     bool has_device_extension() const override { return device_extension; }
+    bool has_device_front() const override { return device_front; }
+
+    // hit2work_1's bookkeeping after the DP, guide selection and the re-seeding jobs of every read, on the device
+    bool front_device(const ReadBatch &b, const std::vector<char> &need_reverse, const ChainOut &g, int max_guides,
+                      std::vector<vmd::FrontOut> &fo) override
+    {
+        if (!device_front) return false;
+        WallTimer wt(this, "front_device");
+        static_assert(sizeof(vmd::RJob) == sizeof(VmReseedJobDev), "re-seeding job layout");
+        const int64_t n = b.n;
+        upload_contig_table();
+        std::vector<int32_t> ids, nrev((size_t)n);
+        for (int64_t r = 0; r < n; ++r) {
+            nrev[(size_t)r] = need_reverse[(size_t)r] ? 1 : 0;
+            if (g.cnt[(size_t)r] > 2) ids.push_back((int32_t)r);
+        }
+        const size_t NA = gx_.n_anc_total, NC = gx_.n_chain_total;
+        BE_OK(dx_nrev_.ensure((size_t)n * 8 + 64));
+        BE_OK(cudaMemcpyAsync(dx_nrev_.p, nrev.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c_->stream));
+        BE_OK(vm_stream_sync(c_->stream));
+        BE_OK(jobs_.ensure((NC + 1) * sizeof(VmReseedJobDev) + 64));
+        BE_OK(d_wlo_.ensure((NA + 1) * 8 + 64));
+        BE_OK(d_whi_.ensure((NA + 1) * 8 + 64));
+        BE_OK(d_gx_.ensure((NA + 1) * 4 + 64));
+        BE_OK(d_gy_.ensure((NA + 1) * 8 + 64));
+        vmd::FrontInput in;
+        in.n_reads = n;
+        in.read_off = read_off_.as<int64_t>();
+        in.ctg.start = d_ctg_.as<int64_t>();
+        in.ctg.len = d_ctg_.as<int64_t>() + n_ctg_dev_;
+        in.ctg.n = n_ctg_dev_;
+        in.need_reverse = dx_nrev_.as<int32_t>();
+        in.xrec = (const vmd::ExtractRec *)gx_.rec.p;
+        in.anc = (const vmd::A32 *)gx_.anc.p;
+        in.S = gx_.S.as<double>();
+        in.chain_len = gx_.len.as<int32_t>();
+        in.chain_score = gx_.score.as<double>();
+        in.NA = (int64_t)NA;
+        in.NC = (int64_t)NC;
+        in.max_guides = max_guides;
+        in.kmer = 9;
+        exec_.be = this;
+        if (!front_) front_.reset(new vmd::FrontHalf<CudaExec>(exec_));
+        front_->run(in, ids, (vmd::RJob *)jobs_.p, d_wlo_.as<int64_t>(), d_whi_.as<int64_t>(), d_gx_.as<int32_t>(), d_gy_.as<int64_t>(), fo,
+                    front_J_, front_xrec_);
+        return true;
+    }
+
+    void reseed_chain_front(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<vmd::FrontOut> &fo,
+                            const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                            ChainOut &out) override
+    {
+        (void)need_reverse;
+        WallTimer wt(this, "reseed_chain");
+        const int64_t n = b.n;
+        out = ChainOut();
+        out.start.assign((size_t)n, 0);
+        out.cnt.assign((size_t)n, 0);
+        out.gmax.assign((size_t)n, -1);
+        const size_t nj = front_J_.size();
+        if (nj == 0) return;
+        std::vector<VmReseedJobDev> J(nj);
+        memcpy(J.data(), front_J_.data(), nj * sizeof(VmReseedJobDev));
+        std::vector<int32_t> job_lo((size_t)n, 0), job_n((size_t)n, 0), n_out;
+        for (int64_t r = 0; r < n; ++r)
+            if (variant[(size_t)r] != 0) { job_lo[(size_t)r] = (int32_t)front_xrec_[(size_t)r].meta_off; job_n[(size_t)r] = fo[(size_t)r].n_jobs; }
+        int32_t *d_n_out = nullptr;
+        reseed_run(J, n_out, d_n_out, new WallTimer(this, "h_reseed_stage"), true);
+        reseed_chain_finish(b, J, n_out, d_n_out, job_lo, job_n, variant, skipcost, maxdiff, maxgap, out);
+    }
 
     // extend_func (+ second pass) for every read of `ids` (the reads that came out of the local stage), on the device
     bool extend_device(const ReadBatch &b, const std::vector<int32_t> &ids, const std::vector<char> &need_reverse,
@@ -1307,6 +1389,9 @@ public:
 private:
     CudaExec exec_{nullptr};
     std::unique_ptr<vmd::BackHalf<CudaExec>> back_;
+    std::unique_ptr<vmd::FrontHalf<CudaExec>> front_;
+    std::vector<vmd::RJob> front_J_;
+    std::vector<vmd::ExtractRec> front_xrec_;
     VmDevBuf dx_nrev_, d_mask_, d_fstats_, d_cigd2_;
     VmFillPlanBufs bplanbufs_, fplanbufs_;
     bool d_ctg_has_len_ = false;

@@ -244,7 +244,30 @@ __device__ __forceinline__ void vm_insert_one(const double *S, int32_t *arg, int
     __syncwarp();
 }
 
-template <int VARIANT, bool SMEM>
+// One bulk asynchronous copy (TMA engine, `cp.async.bulk`) of `bytes` (a multiple of 16) from global to this CTA's shared
+// memory, completion signalled on an mbarrier; issued by one thread, awaited by the whole warp.
+__device__ __forceinline__ void vm_bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *mbar, int lane)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst), bar = (unsigned)__cvta_generic_to_shared(mbar);
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gmem_src),
+                     "r"(bytes), "r"(bar)
+                     : "memory");
+    }
+    __syncwarp();
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+    }
+}
+
+// SMEM: 0 = S / S_arg in the (L2-resident) output arrays; 1 = S / S_arg in shared memory; 2 = the read's anchors too, staged
+// by one TMA bulk copy (the classes of the longest reads: a launch lasts as long as its slowest read, and every anchor of
+// that read otherwise pays an L1 / L2 round trip for a[i] and one for each predecessor a[j] on the dependent path)
+template <int VARIANT, int SMEM>
 __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const int *__restrict__ read_ids, int cap)
 {
     extern __shared__ __align__(16) unsigned char vm_smem[];
@@ -261,6 +284,12 @@ __global__ void __launch_bounds__(32) vm_chain_exact_kernel(VmChainArgs A, const
     if (SMEM) {
         S = (double *)(rgl + VM_RGL_MAX);
         arg = (int32_t *)(S + cap);
+        if (SMEM == 2 && n > 0) {
+            VmAnchor *sa = (VmAnchor *)(arg + cap);                       // 16-byte aligned: tables 1 KB, cap a multiple of 4
+            unsigned long long *mbar = (unsigned long long *)(sa + cap);
+            vm_bulk_load(sa, A.anchors + base, (unsigned)n * (unsigned)sizeof(VmAnchor), mbar, lane);
+            a = sa;
+        }
     } else {
         S = A.S + base;
         arg = A.S_arg + base;
@@ -430,13 +459,18 @@ static int vm_launch_exact_v(const VmChainArgs &args, const int *ids, int n_ids,
                              cudaStream_t stream)
 {
     if (n_ids <= 0) return 0;
-    if (use_smem) {
+    if (use_smem && cap >= VM_CHAIN_ANCHOR_SMEM_MIN && cap <= VM_CHAIN_ANCHOR_SMEM_MAX) {
+        // long reads: anchors staged in shared memory too (28 B per anchor + the mbarrier)
+        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 28 + 16;
+        vm_smem_optin(vm_chain_exact_kernel<VARIANT, 2>);
+        vm_chain_exact_kernel<VARIANT, 2><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+    } else if (use_smem) {
         size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 12;
-        vm_smem_optin(vm_chain_exact_kernel<VARIANT, true>);
-        vm_chain_exact_kernel<VARIANT, true><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+        vm_smem_optin(vm_chain_exact_kernel<VARIANT, 1>);
+        vm_chain_exact_kernel<VARIANT, 1><<<n_ids, 32, smem, stream>>>(args, ids, cap);
     } else {
         size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;
-        vm_chain_exact_kernel<VARIANT, false><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+        vm_chain_exact_kernel<VARIANT, 0><<<n_ids, 32, smem, stream>>>(args, ids, cap);
     }
     return 1;
 }

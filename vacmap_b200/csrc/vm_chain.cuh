@@ -18,6 +18,8 @@
 #include "vm_common.cuh"
 
 #define VM_CHAIN_SMEM_CAP 16384   // anchors; 12 B each -> 192 KB of the 227 KB
+#define VM_CHAIN_ANCHOR_SMEM_MIN 2048   // capacity classes from here up to ..._MAX stage the anchors in shared memory as well
+#define VM_CHAIN_ANCHOR_SMEM_MAX 6144   // 6144 * 28 B = 168 KB
 #define VM_GCL_MAX 64             // gapcost_list entries kept in smem (maxdiff+1 <= 64)
 #define VM_RGL_MAX 128            // read-gap cost entries kept in smem (maxgap+1 <= 128)
 

@@ -76,6 +76,10 @@ struct vm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    // side streams for launches that are one slow warp deep (the capacity classes of the chain kernels): run side by side
+    static const int kSide = 6;
+    cudaStream_t side[kSide] = {};
+    cudaEvent_t side_done[kSide] = {}, side_go = nullptr;
     std::string err;
     int64_t launches = 0;
     int sm_count = 0;

@@ -391,4 +391,106 @@ private:
     typename Exec::HostBuf h_recs_, h_cig_;
 };
 
+// ===============================================================================================================
+// Front half on the executor: hit2work_1's bookkeeping, guide selection and the re-seeding jobs of every read
+// (vm_dglue.hpp::front_read), one thread per read.  The job slots of a read are the slots of its extracted chains
+// (xrec.meta_off ...), its windows / guide points the slots of its extracted anchors (xrec.anc_off ...).
+// ===============================================================================================================
+struct FrontInput {
+    int64_t n_reads;
+    const int64_t *read_off;
+    Ctg ctg;
+    const int32_t *need_reverse;
+    const ExtractRec *xrec;          // global extraction of every read
+    const A32 *anc;
+    const double *S;
+    const int32_t *chain_len;
+    const double *chain_score;
+    int64_t NA, NC;                  // extracted anchors / chains of the chunk (host-known scalars)
+    int32_t max_guides, kmer;
+};
+
+struct FFront {
+    FrontInput in;
+    const int32_t *ids;
+    // scratch, unsliced: nc-sized arrays are indexed at meta_off, na-sized ones at anc_off
+    int32_t *order, *rest, *head, *tail, *nxt, *size, *cseg, *cpos, *cflat, *sc0, *sc1, *ordc;
+    int64_t *dist, *k64c;
+    double *kd;
+    int32_t *coff, *pstart, *bins, *cur, *orda;
+    int64_t *k64a;
+    Anc *tmp;
+    // outputs
+    RJob *jobs;
+    int64_t *wlo, *whi;
+    int32_t *gx;
+    int64_t *gy;
+    FrontOut *out;
+    VM_HD void operator()(int64_t t) const
+    {
+        const int32_t r = ids[t];
+        const ExtractRec xr = in.xrec[r];
+        ReadCtx rc;
+        rc.read = r; rc.L = in.read_off[r + 1] - in.read_off[r]; rc.need_reverse = in.need_reverse[r] != 0; rc.ctg = in.ctg;
+        FrontScratch W;
+        const long long c = xr.meta_off, a = xr.anc_off;
+        W.order = order + c; W.rest = rest + c; W.head = head + c; W.tail = tail + c; W.nxt = nxt + c; W.size = size + c;
+        W.cseg = cseg + c; W.cpos = cpos + c; W.cflat = cflat + c; W.sc0 = sc0 + c; W.sc1 = sc1 + c; W.ordc = ordc + c;
+        W.dist = dist + c; W.k64c = k64c + c; W.kd = kd + c;
+        W.coff = coff + a; W.pstart = pstart + a; W.bins = bins + a; W.cur = cur + a; W.orda = orda + a; W.k64a = k64a + a; W.tmp = tmp + a;
+        FrontOut o;
+        front_read(rc, xr, in.anc, in.S, in.chain_len, in.chain_score, in.max_guides, in.kmer, W, jobs + c, wlo + a, whi + a, gx + a, gy + a, a, a, o);
+        out[r] = o;
+    }
+};
+
+template <typename Exec>
+class FrontHalf {
+public:
+    explicit FrontHalf(Exec &ex) : ex_(ex) {}
+    ~FrontHalf()
+    {
+        for (auto *x : {&b_ids_, &b_i32c_, &b_i64c_, &b_f64c_, &b_i32a_, &b_i64a_, &b_tmp_, &b_out_}) Exec::release(*x);
+    }
+    // jobs / wlo / whi / gx / gy: executor arrays with room for NC jobs and NA windows / guide points (jobs zeroed here).
+    // fo: per read (only the entries of `ids_host` are meaningful); J: host copy of the NC job slots.
+    void run(const FrontInput &in, const std::vector<int32_t> &ids_host, RJob *jobs, int64_t *wlo, int64_t *whi, int32_t *gx, int64_t *gy,
+             std::vector<FrontOut> &fo, std::vector<RJob> &J, std::vector<ExtractRec> &xrec_host)
+    {
+        const int64_t n = in.n_reads;
+        const size_t NC = (size_t)in.NC + 1, NA = (size_t)in.NA + 1;
+        int32_t *ids = ex_.template ensure<int32_t>(b_ids_, ids_host.size() + 1);
+        int32_t *i32c = ex_.template ensure<int32_t>(b_i32c_, 12 * NC);
+        int64_t *i64c = ex_.template ensure<int64_t>(b_i64c_, 2 * NC);
+        double *f64c = ex_.template ensure<double>(b_f64c_, NC);
+        int32_t *i32a = ex_.template ensure<int32_t>(b_i32a_, 5 * NA);
+        int64_t *i64a = ex_.template ensure<int64_t>(b_i64a_, NA);
+        Anc *tmp = ex_.template ensure<Anc>(b_tmp_, NA);
+        FrontOut *out = ex_.template ensure<FrontOut>(b_out_, (size_t)n + 1);
+        ex_.to_exec(ids, ids_host.data(), ids_host.size() * 4);
+        ex_.zero(jobs, NC * sizeof(RJob));
+        ex_.zero(out, ((size_t)n + 1) * sizeof(FrontOut));
+        FFront f;
+        f.in = in; f.ids = ids;
+        f.order = i32c; f.rest = i32c + NC; f.head = i32c + 2 * NC; f.tail = i32c + 3 * NC; f.nxt = i32c + 4 * NC; f.size = i32c + 5 * NC;
+        f.cseg = i32c + 6 * NC; f.cpos = i32c + 7 * NC; f.cflat = i32c + 8 * NC; f.sc0 = i32c + 9 * NC; f.sc1 = i32c + 10 * NC; f.ordc = i32c + 11 * NC;
+        f.dist = i64c; f.k64c = i64c + NC; f.kd = f64c;
+        f.coff = i32a; f.pstart = i32a + NA; f.bins = i32a + 2 * NA; f.cur = i32a + 3 * NA; f.orda = i32a + 4 * NA;
+        f.k64a = i64a; f.tmp = tmp;
+        f.jobs = jobs; f.wlo = wlo; f.whi = whi; f.gx = gx; f.gy = gy; f.out = out;
+        ex_.per_item((int64_t)ids_host.size(), f);
+        fo.resize((size_t)n);
+        J.resize((size_t)in.NC);
+        xrec_host.resize((size_t)n);
+        ex_.to_host(fo.data(), out, (size_t)n * sizeof(FrontOut));
+        if (in.NC) ex_.to_host(J.data(), jobs, (size_t)in.NC * sizeof(RJob));
+        ex_.to_host(xrec_host.data(), in.xrec, (size_t)n * sizeof(ExtractRec));
+        ex_.sync();
+    }
+
+private:
+    Exec &ex_;
+    typename Exec::Buf b_ids_, b_i32c_, b_i64c_, b_f64c_, b_i32a_, b_i64a_, b_tmp_, b_out_;
+};
+
 } // namespace vmd

@@ -7,7 +7,7 @@
 // (tests/gluetest); the product only ever instantiates the CUDA backend (vm_backend_cuda.cu).
 #pragma once
 #include "vm_glue.hpp"
-#include "vm_dglue.hpp"
+#include "vm_dgrun.hpp"
 #include "vm_hostpool.hpp"
 #include <atomic>
 #include <condition_variable>
@@ -134,6 +134,23 @@ struct Backend {
         return false;
     }
     virtual bool has_device_extension() const { return false; }
+    // Optional: hit2work_1's bookkeeping after the DP, guide-chain selection and the re-seeding jobs (:23581-23734,
+    // :28482-28582, :23090-23191) on the backend's side, from the chains seed_chain extracted there.  fo[r]: what the
+    // driver still needs of read r (status, number of guide chains, MAPQ inputs).  The jobs stay with the backend;
+    // reseed_chain_front runs them.  false: not supported, the driver runs the host glue.
+    virtual bool has_device_front() const { return false; }
+    virtual bool front_device(const ReadBatch &b, const std::vector<char> &need_reverse, const ChainOut &g, int max_guides,
+                              std::vector<vmd::FrontOut> &fo)
+    {
+        (void)b; (void)need_reverse; (void)g; (void)max_guides; (void)fo;
+        return false;
+    }
+    virtual void reseed_chain_front(const ReadBatch &b, const std::vector<char> &need_reverse, const std::vector<vmd::FrontOut> &fo,
+                                    const std::vector<int> &variant, const std::vector<double> &skipcost, int maxdiff, int maxgap,
+                                    ChainOut &out)
+    {
+        (void)b; (void)need_reverse; (void)fo; (void)variant; (void)skipcost; (void)maxdiff; (void)maxgap; (void)out;
+    }
 };
 
 // Thread time spent in the parts of the host glue, summed over the pool's threads ("t_<name>" stage entries):
@@ -245,6 +262,34 @@ public:
         be_.seed_chain(b, opt_.check_num, k_, opt_.global_skipcost, opt_.global_maxdiff, 1000, opt_.mode.accept, need_rev, g);
 
         // ---- 3. hit2work bookkeeping + guide selection ----
+        std::vector<int> variant((size_t)n, 0);
+        std::vector<double> skip((size_t)n, opt_.local_skipcost);
+        ChainOut lc;
+        std::vector<vmd::FrontOut> fo;
+        if (be_.has_device_front() && be_.front_device(b, need_rev, g, opt_.mode.max_guides, fo)) {
+            // on the backend's side: the host only turns the per-read summary into flags
+            Phase ph3(this, "g_hit2work");
+            for (int64_t r = 0; r < n; ++r) {
+                if (g.cnt[r] <= 2) { res.status[r] = RS_FEW_ANCHORS; continue; }       // decode_hit :23986
+                if (!g.used_fast.empty() && g.used_fast[r]) bc_[BC_FAST_GLOBAL].fetch_add(1, std::memory_order_relaxed);
+                const vmd::FrontOut &f = fo[(size_t)r];
+                if (f.status != vmd::ST_OK) { res.status[r] = RS_LOW_SCORE; continue; }
+                ReadState &s = st[r];
+                s.alive = true;
+                s.need_reverse = need_rev[r] != 0;
+                // min(int(40*(1-f2/f1)*min(1, m/10)*np.log(f1)), 60)  (:23704); numba lowers np.log to libm log
+                double v = 40 * (1 - f.f2 / f.f1);
+                v = v * std::min(1.0, f.m / 10);
+                v = v * std::log(f.f1);
+                s.mapq = (int)std::min<int64_t>((int64_t)v, 60);
+                if (f.n_guides > 1) {
+                    variant[r] = 2;
+                    bc_[BC_MISMATCH_DP].fetch_add(1, std::memory_order_relaxed);
+                    if (opt_.mode.clamp40) skip[r] = std::min(skip[r], 40.0);
+                } else variant[r] = 1;
+            }
+            be_.reseed_chain_front(b, need_rev, fo, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
+        } else {
         std::vector<std::vector<GuideJobRef>> gjobs((size_t)n);
         Phase *ph = new Phase(this, "g_hit2work");
         parallel_for(n, threads_, [&](int64_t r) {
@@ -282,8 +327,6 @@ public:
         std::vector<GuideJobRef> all_gjobs;
         std::vector<int64_t> gj_start;
         parallel_concat(gjobs, threads_, all_gjobs, gj_start);
-        std::vector<int> variant((size_t)n, 0);
-        std::vector<double> skip((size_t)n, opt_.local_skipcost);
         for (int64_t r = 0; r < n; ++r) {
             if (!st[r].alive) continue;
             if (st[r].guides.size() > 1) {
@@ -296,8 +339,8 @@ public:
         delete ph;
 
         // ---- 4-5. local re-seeding + local chaining (fused on the device) ----
-        ChainOut lc;
         be_.reseed_chain(b, need_rev, all_gjobs, variant, skip, opt_.local_maxdiff, opt_.mode.local_maxgap, lc);
+        }
         lc_ = &lc;
         if (be_.has_device_extension()) {
             // ---- 6'. extend_func and the second pass with their glue on the device: the host only launches ----
@@ -325,7 +368,7 @@ public:
         }
 
         // ---- 6. traceback, then extend_func as a staged state machine ----
-        ph = new Phase(this, "g_traceback");
+        Phase *ph = new Phase(this, "g_traceback");
         parallel_for(n, threads_, [&](int64_t r) {
             ReadState &s = st[r];
             if (!s.alive) return;
