@@ -238,8 +238,9 @@ def run_reference(args):
 
 
 KERNEL_BYTES_NOTE = {
-    "k_fill": "B = sum(q+t) sequence bytes + the direction bytes of the cells inside the certified band (n_fill_dir_bytes: one "
-              "128-byte line per step and direction word, written once; the traceback re-reads only the path) + 4 B per CIGAR op",
+    "k_fill": "B = sum(q+t) sequence bytes + 4 B per CIGAR op (SURVEY 8d's compulsory terms); the direction bytes of the band cells "
+              "(one 128-byte line per step and direction word, written once, re-read along the path) exceed shared memory and "
+              "spill to HBM: reported apart as direction_spill_bytes / frac_with_direction_spill",
     "k_ed_upper": "B = sum(q+t) sequence bytes (every base is read once, by the gap DP or by the anchor check)",
     "k_seed": "B = read bytes + 16 B per anchor out",
     "k_edit_distance": "B = sum(q+t) sequence bytes (bit-vector state stays in registers/SMEM)",
@@ -425,34 +426,61 @@ def main():
         kern = {k: v for k, v in solo.items() if k.startswith("k_") or k.endswith("_kernels")}
         top = max(kern, key=kern.get) if kern else None
         counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_fill_band_jobs", "n_fill_band_redo", "n_fill_dir_bytes",
-                                                      "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors")}
+                                                      "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors", "n_chain_opcount")}
         n_ops = float(len(cig))
-        alg_bytes = {"k_fill": counts["n_fill_bases"] + counts["n_fill_dir_bytes"] + 4.0 * n_ops,
+        # ALGORITHMIC bytes per step: what the stage must move whatever the implementation
+        alg_bytes = {"k_fill": counts["n_fill_bases"] + 4.0 * n_ops,
                      "k_edit_distance": 2.0 * bases, "k_ed_upper": 2.0 * bases,
                      "k_reseed_hits": 2.0 * bases + 8.0 * counts["n_reseed_hits"],
                      "k_reseed_merge": 8.0 * counts["n_reseed_hits"] + 16.0 * counts["n_reseed_hits"] / 4,
                      "chain_local_kernels": 28.0 * counts["n_chain_anchors"], "chain_global_kernels": 28.0 * counts["n_chain_anchors"],
                      "k_seed": 1.0 * bases + 16.0 * counts["n_chain_anchors"], "k_extend": 0.0}
         roof = None
+        traffic_file = None
+        for name in ("r2_kernel_traffic.json", "r1_kernel_traffic.json"):
+            if os.path.exists(os.path.join(ROOT, "profiles", name)):
+                traffic_file = os.path.join(ROOT, "profiles", name)
+                break
+
+        def traffic_of(kernel):
+            if not traffic_file:
+                return None
+            tj = json.load(open(traffic_file)).get(kernel)
+            if not tj:      # DRAM bytes per unit of work from the committed `ncu --set full` capture, scaled to this launch
+                return None
+            return tj["dram_bytes_per_unit"] * counts.get(tj["unit_count"], 0.0)
         if top:
             secs = kern[top] / 1000.0
             achieved = alg_bytes.get(top, 0.0) / secs / 1e9 if secs > 0 else 0.0
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "r1_kernel_traffic.json")
-            if os.path.exists(tp):
-                tj = json.load(open(tp)).get(top)
-                if tj:      # DRAM bytes per unit of work from the committed `ncu --set full` capture, scaled to this launch
-                    traffic = tj["dram_bytes_per_unit"] * counts.get(tj["unit_count"], 0.0)
+            spill = counts["n_fill_dir_bytes"] if top == "k_fill" else 0.0
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "kernel_ms": kern[top],
+                    "frac": achieved / peak, "traffic": traffic_of(top), "kernel_ms": kern[top],
                     "kernel_ms_in_pipeline_per_step": per_step.get(top),
                     "timing": solo_note or "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
                                            "'launch' = the kernel's launches of one step (one per capacity class)",
                     "bytes": alg_bytes.get(top, 0.0), "bytes_formula": KERNEL_BYTES_NOTE.get(top, ""),
+                    "direction_spill_bytes": spill,
+                    "frac_with_direction_spill": ((alg_bytes.get(top, 0.0) + spill) / secs / 1e9 / peak) if secs > 0 else None,
                     "gcups_full_matrix_equivalent": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
                     "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
                     "note": "integer DP wavefront: issue / ALU-pipe bound (ncu, 48-row class: issue 71 %, ALU 67 %, DRAM 15 %), not HBM bound "
                             "(SURVEY 8d); the HBM fraction is reported because north_star asks for it"}
+        # the chaining kernels (the ones north_star names): both byte counts of SURVEY 8d
+        chain_ms = kern.get("chain_global_kernels", 0.0) + kern.get("chain_local_kernels", 0.0)
+        roof_chain = None
+        if chain_ms > 0:
+            b_chain = 28.0 * counts["n_chain_anchors"]
+            b_alg = 28.0 * counts["n_chain_opcount"] + b_chain
+            roof_chain = {"bound": "hbm", "kernel": "chain_global_kernels + chain_local_kernels (argsort replay + exact / fast DP)",
+                          "kernel_ms": chain_ms, "peak": peak, "unit": "GB/s",
+                          "B_chain": b_chain, "achieved": b_chain / (chain_ms / 1e3) / 1e9, "frac": b_chain / (chain_ms / 1e3) / 1e9 / peak,
+                          "B_chain_alg": b_alg, "achieved_alg": b_alg / (chain_ms / 1e3) / 1e9,
+                          "frac_alg": b_alg / (chain_ms / 1e3) / 1e9 / peak,
+                          "anchors": counts["n_chain_anchors"], "opcount": counts["n_chain_opcount"],
+                          "traffic": traffic_of("chain"),
+                          "note": "B_chain = 28 B per anchor (16 in + 8 S + 4 P), the compulsory bytes; B_chain_alg = opcount x 28 + 28 n, what the "
+                                  "reference's predecessor loop moves unstaged (opcount = its own counter, exact here).  The recurrence is serial "
+                                  "along the anchors of a read: latency-bound, a launch lasts as long as its slowest read (ncu)"}
         line = {"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
@@ -469,7 +497,7 @@ def main():
                 "records_per_step": nrec_all, "gather_ms": round(gather_ms, 2),
                 "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
                 "work_per_step": counts,
-                "roofline": roof, "clocks": clocks}
+                "roofline": roof, "roofline_chain": roof_chain, "clocks": clocks}
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             sample = min(args.reads, args.cpu_sample)

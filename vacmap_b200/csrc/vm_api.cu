@@ -90,18 +90,27 @@ int vm_set_tables(vm_ctx *c, const float *extra, int64_t n_extra, const float *r
 
 vm_ctx *vm_ctx_worker(vm_ctx *parent, int i)
 {
+    // the table never reallocates once workers hold pointers into it (a later submit may add workers while earlier
+    // ones are running): room for every worker a context can have is reserved with the first one
+    if (parent->kids.capacity() < 256) parent->kids.reserve(256);
+    if (i < 0 || i >= 256) return nullptr;
     while ((int)parent->kids.size() <= i) {
         vm_ctx *k = nullptr;
         if (vm_ctx_create(parent->device, &k) != VM_OK) return nullptr;
         parent->kids.push_back(k);
     }
     vm_ctx *k = parent->kids[i];
-    k->extra.alias(parent->extra);
-    k->readgapcost.alias(parent->readgapcost);
-    k->log2cache.alias(parent->log2cache);
-    k->n_extra = parent->n_extra;
-    k->n_readgapcost = parent->n_readgapcost;
-    k->n_log2cache = parent->n_log2cache;
+    // the score tables are aliases of the parent's; rewritten only when they changed (vm_set_tables reallocated them), so a
+    // worker that is in the middle of a chunk never sees its pointers touched by a concurrent submit
+    if (k->extra.p != parent->extra.p || k->readgapcost.p != parent->readgapcost.p || k->log2cache.p != parent->log2cache.p ||
+        k->n_extra != parent->n_extra) {
+        k->extra.alias(parent->extra);
+        k->readgapcost.alias(parent->readgapcost);
+        k->log2cache.alias(parent->log2cache);
+        k->n_extra = parent->n_extra;
+        k->n_readgapcost = parent->n_readgapcost;
+        k->n_log2cache = parent->n_log2cache;
+    }
     return k;
 }
 
@@ -164,8 +173,7 @@ static int vm_chain_args(vm_ctx *c, VmChainState &s, const vm_chain_params &p, V
         A.rgcost = s.rgl.as<float>();
         A.n_rg = (int)rg.size();
     }
-    // the staging vectors above are pageable: make sure the copies are done before they go away
-    VM_CUDA_OK(c, vm_stream_sync(c->stream));
+    // (the staging vectors above are pageable: cudaMemcpyAsync has staged them when it returns, no sync needed)
     A.anchors = s.sorted.as<VmAnchor>();
     A.off = s.off_dev.as<int64_t>();
     A.cnt = s.cnt_dev.as<int32_t>();
@@ -265,7 +273,8 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
                                                   s.perm.as<int32_t>(), s.sort_scratch.as<int32_t>(), s.sorted.as<VmAnchor>(),
                                                   sorted_rows_dev, st);
         }
-        const bool smem = k < kNumCaps;
+        static const int no_smem_below = getenv("VM_CHAIN_GLOBAL_BELOW") ? atoi(getenv("VM_CHAIN_GLOBAL_BELOW")) : 0;   // experiment knob
+        const bool smem = k < kNumCaps && !(kCaps[k] <= no_smem_below);
         c->launches += vm_launch_chain_exact(prm.variant, A, s.ids.as<int>() + cls_start[k], n_k, smem ? kCaps[k] : 0, smem, st);
     }
     if (!fast_ids.empty() && !presorted)
@@ -300,11 +309,15 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
         VM_CUDA_OK(c, cudaMemcpyAsync(fids_dev, fast_ids.data(), fast_ids.size() * 4, cudaMemcpyHostToDevice, c->stream));
         c->launches += vm_launch_chain_fast(prm.variant, A, prm.fast_t, fids_dev, (int)fast_ids.size(),
                                             s.fast_scratch.as<long long>(), s.fast_off.as<int64_t>(), c->stream);
-        VM_CUDA_OK(c, vm_stream_sync(c->stream));   // soff / fast_ids are stack-lifetime staging
     }
     VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
+    // the DPs' own count of predecessor evaluations (the reference's `opcount`): B_chain_alg of the roofline report
+    s.opcount_host.resize(cnt.size());
+    VM_CUDA_OK(c, cudaMemcpyAsync(s.opcount_host.data(), s.opcount.p, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     VM_CUDA_OK(c, vm_stream_sync(c->stream));
     VM_CUDA_OK(c, cudaGetLastError());
+    s.opcount_last = 0;
+    for (int t = 0; t < n_exact; ++t) s.opcount_last += (double)s.opcount_host[(size_t)ids_host[(size_t)t]];
     if (ms4) {
         ms4[0] = 0;
         for (int t = 1; t < 4; ++t) cudaEventElapsedTime(&ms4[t], ev[t], ev[t + 1]);

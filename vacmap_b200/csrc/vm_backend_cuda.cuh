@@ -137,11 +137,11 @@ public:
     int host_threads = 1;           // host threads this backend may use for staging loops
     void set_index(vm_index_handle *ih) { ih_ = ih; }
     double fill_cells_ = 0, fill_bases_ = 0, fill_jobs_ = 0, ed_cells_ = 0, reseed_hits_ = 0, chain_anchors_ = 0, ed_upper_jobs_ = 0, fill_band_jobs_ = 0,
-           fill_band_redo_ = 0, fill_dir_bytes_ = 0;
+           fill_band_redo_ = 0, fill_dir_bytes_ = 0, chain_opcount_ = 0;
     void reset_counters()
     {
         timer.ms.clear();
-        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = fill_band_jobs_ = fill_band_redo_ = fill_dir_bytes_ = 0;
+        fill_cells_ = fill_bases_ = fill_jobs_ = ed_cells_ = reseed_hits_ = chain_anchors_ = ed_upper_jobs_ = fill_band_jobs_ = fill_band_redo_ = fill_dir_bytes_ = chain_opcount_ = 0;
     }
 
     // device time of a group of launches, CUDA events on the ctx stream
@@ -281,6 +281,7 @@ public:
         if (vm_chain_core(c_, prm, seed_.out.as<VmAnchor>(), out.start, out.cnt, rl, rl, ids, nullptr, &out.used_fast, ms4) != VM_OK)
             throw std::runtime_error("chain: " + c_->err);
         timer.add("chain_global_kernels", ms4[1] + ms4[2] + ms4[3]);
+        chain_opcount_ += c_->chain.opcount_last;
         // chains extracted on the device: only what hit2work_1 keeps goes to the host
         extract(true, n, span, ids, accept, gx_, out);
     }
@@ -487,12 +488,14 @@ public:
     {
         (void)from_device;
         const int nj = (int)J.size();
-        // one pass with room for 3 hits per read position; the rare job that needs more is re-run below
+        // one pass with room for 1.5 hits per read position (measured: 0.2 on 15 kb ONT reads, 0.6 on 20 kb HiFi reads -- at 3
+        // per position the hit buffers of a GRCh38-sized HiFi chunk took 9 GB per worker); the rare job that needs more is
+        // re-run below with its exact count
         int64_t hit_off = 0;
         for (int j = 0; j < nj; ++j) {
             const int64_t span = std::max<int64_t>(0, (int64_t)J[j].readend - J[j].readstart);
             J[j].hit_off = hit_off;
-            J[j].hit_cap = J[j].n_guide > 0 ? (int32_t)std::min<int64_t>(3 * span + 64, INT32_MAX) : 0;
+            J[j].hit_cap = J[j].n_guide > 0 ? (int32_t)std::min<int64_t>(span + span / 2 + 64, INT32_MAX) : 0;
             hit_off += J[j].hit_cap;
         }
         BE_OK(jobs_.ensure(J.size() * sizeof(VmReseedJobDev) + 64));
@@ -549,9 +552,11 @@ public:
         for (int j = 0; j < nj; ++j) {
             J[j].dense_off = dense_hits;
             dense_hits += n_hits[j];
-            // the merge kernel gives every lane a 32nd of the table: at most a quarter full on average
-            int ts = J[j].n_guide > 0 ? 2048 : 32;      // an empty slot has no table
-            while (ts < 2 * (n_hits[j] + 8)) ts <<= 1;
+            // the merge kernel gives every lane a 32nd of the table; the diagonals are a fraction of the hits, so a table of
+            // the next power of two above the hit count is about a third full (a lane slice that does fill up sends the job to
+            // the sequential kernel)
+            int ts = J[j].n_guide > 0 ? 1024 : 32;      // an empty slot has no table
+            while (ts < n_hits[j] + 8) ts <<= 1;
             J[j].tab_off = tab_off;
             J[j].tab_size = ts;
             tab_off += ts;
@@ -664,6 +669,7 @@ public:
             if (vm_chain_core(c_, prm, d_dense_.as<VmAnchor>(), out.start, out.cnt, rl, rl, g.second, nullptr, &out.used_fast, ms4) != VM_OK)
                 throw std::runtime_error("chain: " + c_->err);
             timer.add("chain_local_kernels", ms4[1] + ms4[2] + ms4[3]);
+            chain_opcount_ += c_->chain.opcount_last;
         }
         // best chain of every read traced back (and trimmed) on the device
         std::vector<int> xids;
@@ -1268,8 +1274,7 @@ public:
         }
         const size_t NA = gx_.n_anc_total, NC = gx_.n_chain_total;
         BE_OK(dx_nrev_.ensure((size_t)n * 8 + 64));
-        BE_OK(cudaMemcpyAsync(dx_nrev_.p, nrev.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(vm_stream_sync(c_->stream));
+        BE_OK(cudaMemcpyAsync(dx_nrev_.p, nrev.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c_->stream));      // pageable: staged on return
         BE_OK(jobs_.ensure((NC + 1) * sizeof(VmReseedJobDev) + 64));
         BE_OK(d_wlo_.ensure((NA + 1) * 8 + 64));
         BE_OK(d_whi_.ensure((NA + 1) * 8 + 64));
@@ -1334,8 +1339,7 @@ public:
         int32_t *d_nrev = dx_nrev_.as<int32_t>(), *d_mapq = d_nrev + n;
         std::vector<int32_t> tmp(2 * (size_t)n);
         for (int64_t r = 0; r < n; ++r) { tmp[(size_t)r] = need_reverse[(size_t)r] ? 1 : 0; tmp[(size_t)(n + r)] = mapq[(size_t)r]; }
-        BE_OK(cudaMemcpyAsync(d_nrev, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, c_->stream));
-        BE_OK(vm_stream_sync(c_->stream));       // tmp is pageable and goes out of scope
+        BE_OK(cudaMemcpyAsync(d_nrev, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice, c_->stream));      // pageable: staged on return
         vmd::BackInput in;
         in.n_reads = n;
         in.read_off = read_off_.as<int64_t>();

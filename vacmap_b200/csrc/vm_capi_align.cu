@@ -237,7 +237,7 @@ struct vm_job {
     std::string err;
     StageTimer timer;
     double fill_cells = 0, fill_bases = 0, fill_jobs = 0, ed_cells = 0, ed_upper = 0, reseed_hits = 0, chain_anchors = 0, band_jobs = 0,
-           band_redo = 0, dir_bytes = 0;
+           band_redo = 0, dir_bytes = 0, chain_opcount = 0;
     int64_t launches = 0;
     std::chrono::steady_clock::time_point t0, t_done;
 };
@@ -251,6 +251,7 @@ void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::strin
     job->fill_cells += wb.fill_cells_; job->fill_bases += wb.fill_bases_; job->fill_jobs += wb.fill_jobs_;
     job->ed_cells += wb.ed_cells_; job->ed_upper += wb.ed_upper_jobs_; job->reseed_hits += wb.reseed_hits_;
     job->chain_anchors += wb.chain_anchors_;
+    job->chain_opcount += wb.chain_opcount_;
     job->band_jobs += wb.fill_band_jobs_;
     job->band_redo += wb.fill_band_redo_;
     job->dir_bytes += wb.fill_dir_bytes_;
@@ -391,7 +392,7 @@ struct AlignPool {
                 wc->backend = new CudaBackend(wc, h);
                 wc->backend_free = [](void *q) { delete (CudaBackend *)q; };
             }
-            threads.emplace_back([this, w] { loop(w); });
+            threads.emplace_back([this, w, wc] { loop(w, wc); });
         }
         for (int w = 0; w < (int)threads.size(); ++w) vm_ctx_worker(c, w);   // refresh the table aliases
         return true;
@@ -404,8 +405,9 @@ struct AlignPool {
         }
         cv.notify_all();
     }
-    void loop(int w)
+    void loop(int w, vm_ctx *wc)
     {
+        (void)w;
         for (;;) {
             std::pair<vm_job *, int64_t> task;
             {
@@ -415,7 +417,6 @@ struct AlignPool {
                 task = queue.front();
                 queue.pop_front();
             }
-            vm_ctx *wc = c->kids[(size_t)w];
             run_chunk(task.first, task.second, wc, *(CudaBackend *)wc->backend, (CudaBackend *)c->backend);
         }
     }
@@ -592,6 +593,7 @@ int vm_align_wait(vm_job *job, vm_result **out)
     tm.add("n_ed_upper_jobs", job->ed_upper);
     tm.add("n_reseed_hits", job->reseed_hits);
     tm.add("n_chain_anchors", job->chain_anchors);
+    tm.add("n_chain_opcount", job->chain_opcount);
     for (auto &kv : tm.ms) {
         res->stage_names.push_back(kv.first);
         res->stage_ms.push_back(kv.second);

@@ -69,6 +69,8 @@ struct VmChainState {
     VmDevBuf rows, off_dev, cnt_dev, anch, perm, sorted, sorted_rows, S, P, S_arg, gmax, opcount, ids, gcl, rgl,
         fast_scratch, fast_off, sort_scratch, pre_n_dev, head_dev;      // pre_n / head: carried prefix of the linked DP (variant 3)
     std::vector<int32_t> used_fast;
+    std::vector<int64_t> opcount_host;
+    double opcount_last = 0;             // predecessor evaluations of the last vm_chain_core call (the reference's `opcount`, summed)
     float ms[4] = {0, 0, 0, 0};
 };
 

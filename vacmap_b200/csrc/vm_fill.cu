@@ -491,7 +491,8 @@ void vm_fill_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillPlan &plan
         L.dir_words_per_warp = nbands * ((long long)T.max_q[cls] + 32) * (L.R / 2) * 32;
         L.band_words_per_warp = L.multiband ? 3LL * T.max_q[cls] + 32 : 0;
         const int n_pairs = L.pair_end - L.pair_begin;
-        long long blocks = std::min<long long>((n_pairs + 3) / 4, (long long)sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0));
+        static const double frac = getenv("VM_FILL_SM_FRAC") ? atof(getenv("VM_FILL_SM_FRAC")) : 1.0;   // experiment knob
+        long long blocks = std::min<long long>((n_pairs + 3) / 4, (long long)(frac * sm_count * vm_fill_blocks_per_sm(L.R, L.multiband != 0)));
         const long long fit = (long long)(mem_cap_words / (size_t)(4 * L.dir_words_per_warp));
         blocks = std::max<long long>(1, std::min(blocks, std::max<long long>(fit, 1)));
         L.blocks = (int)blocks;

@@ -713,7 +713,9 @@ void vm_fillb_plan_finish(const VmFillPlanBufs &B, int sm_count, VmFillBandPlan 
         L.dir_words_per_warp = (long long)T.max_steps[c] * ((VM_FB_CLASS[c].C + 1) / 2) * 32;
         const int n_pairs = T.cnt[c];
         const int per_block = 4 * VM_FB_CLASS[c].G;
-        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + per_block - 1) / per_block, (long long)sm_count * vm_fillb_blocks_per_sm(c)));
+        static const double frac = getenv("VM_FILL_SM_FRAC") ? atof(getenv("VM_FILL_SM_FRAC")) : 1.0;   // experiment knob
+        L.blocks = (int)std::max<long long>(1, std::min<long long>((n_pairs + per_block - 1) / per_block,
+                                                                   (long long)(frac * sm_count * vm_fillb_blocks_per_sm(c))));
         plan.dir_words += (size_t)((long long)L.blocks * 4 * L.dir_words_per_warp);
         plan.launches.push_back(L);
     }

@@ -356,8 +356,8 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
         const int64_t n_chunks = chunk_off[n];
         SEED_OK(B.chunk_off.ensure((size_t)(n + 1) * 8 + 64));
         SEED_OK(B.chunk_cnt.ensure((size_t)n_chunks * 4 + 64));
+        // (pageable source: cudaMemcpyAsync returns once it has been staged, so the vector may go out of scope -- no sync)
         SEED_OK(cudaMemcpyAsync(B.chunk_off.p, chunk_off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, stream));
-        SEED_OK(vm_stream_sync(stream));
         if (n_chunks > 0)
             vm_sketch_chunk_kernel<<<(unsigned)((n_chunks + 63) / 64), 64, 0, stream>>>(
                 reads_dev, off_dev, B.chunk_off.as<int64_t>(), n, n_chunks, ix.w, ix.k, B.mz_hash.as<uint64_t>(),
@@ -393,7 +393,6 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
     if (t_off[n] > 0) {
         vm_cl_init_kernel<<<(unsigned)((t_off[n] + 255) / 256), 256, 0, stream>>>(B.table.as<VmClSlot>(), t_off[n]);
         *launches += 1;
-        SEED_OK(vm_stream_sync(stream));   // a_off / t_off staging vectors are about to go out of scope
     }
     vm_seed_expand_kernel<<<n, 32, 0, stream>>>(ix, off_dev, B.mz_posz.as<uint32_t>(), B.n_mz.as<int32_t>(),
                                                 B.mz_start.as<uint32_t>(), B.mz_cnt.as<uint32_t>(), B.mz_aoff.as<uint32_t>(),
