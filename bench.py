@@ -70,8 +70,10 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_indices):
+        # one sampler process for all the job's GPUs (rank 0 runs it): eight nvidia-smi loops polling the driver at once
+        # are a measurable disturbance on the 4-vCPU-per-rank boxes
+        self.gpu, self.rows, self.proc = ",".join(str(g) for g in gpu_indices), [], None
 
     def start(self):
         try:
@@ -109,8 +111,13 @@ class ClockSampler:
                 for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
+        per_gpu = {}
+        for r in self.rows:
+            if len(r) >= 9 and num(r[1]) is not None:
+                per_gpu.setdefault(r[0], []).append(num(r[1]))
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "sm_mhz_per_gpu": {g: float(np.median(v)) for g, v in sorted(per_gpu.items())}}
 
 
 def make_workload(n_reads, rank=0, ref_only=False):
@@ -210,6 +217,59 @@ def cpu_inputs(sample, ref=None):
     return ref, reads, note
 
 
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.extend(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def pin_to_gpu_node(local_rank, local_world):
+    """Bind this rank to its slice of the cores of the NUMA node its GPU is attached to (sysfs; no-op when the
+    topology cannot be read).  Returns a one-line description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        nodes = []
+        for i in range(local_world):
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(i)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+            if len(bus.split(":")[0]) == 8:
+                bus = bus[4:]
+            try:
+                nodes.append(int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read()))
+            except OSError:
+                nodes.append(-1)
+        node = nodes[local_rank]
+        allowed = sorted(os.sched_getaffinity(0))
+        if node < 0:
+            cpus, peers = allowed, list(range(local_world))
+        else:
+            cpus = [c for c in _cpulist(open("/sys/devices/system/node/node%d/cpulist" % node).read()) if c in set(allowed)]
+            peers = [i for i in range(local_world) if nodes[i] == node]
+
+        def core_of(c):     # hyper-thread siblings next to each other, so that a slice is made of whole cores
+            try:
+                return min(_cpulist(open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c).read()))
+            except OSError:
+                return c
+        cpus.sort(key=lambda c: (core_of(c), c))
+        me = peers.index(local_rank)
+        per = len(cpus) // len(peers)
+        if per < 2:
+            return None
+        mine = cpus[me * per:(me + 1) * per]
+        os.sched_setaffinity(0, mine)
+        os.environ["VM_HOST_THREADS"] = str(max(2, min(int(os.environ.get("VM_HOST_THREADS", "64")), len(mine))))
+        return "rank bound to %d cores of NUMA node %d (its GPU's)" % (len(mine), node)
+    except Exception as e:      # no sysfs / nvml in this container: run unpinned
+        sys.stderr.write("pinning skipped: %s\n" % e)
+        return None
+
+
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
@@ -281,10 +341,14 @@ def main():
         return
     args.warmup = max(args.warmup, 3)
 
-    # one process per GPU: every rank gets its share of the host cores for the glue (pool size is read at load time)
+    # one process per GPU: every rank gets its share of the host cores for the glue (pool size is read at load time),
+    # and those cores are the ones of the NUMA node its GPU hangs off (staging copies stay on the near socket)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    pinning = None
     if local_world > 1:
         os.environ.setdefault("VM_HOST_THREADS", str(max(2, (os.cpu_count() or 1) // local_world)))
+        if os.environ.get("VM_BENCH_PIN", "1") != "0":
+            pinning = pin_to_gpu_node(int(os.environ.get("LOCAL_RANK", "0")), local_world)
     os.environ.setdefault("NCCL_DEBUG", "WARN")       # NCCL's version banner goes to stdout; this script prints one JSON line there
     import torch
     import vacmap_b200 as vb
@@ -330,9 +394,10 @@ def main():
             al.wait(warm.popleft())
     while warm:
         rec_off, recs, cig = al.wait(warm.popleft())
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(list(range(local_world))) if rank == 0 else None
     barrier()
-    sampler.start()
+    if sampler:
+        sampler.start()
     l0 = ctx.kernel_launches
     stage = {}
     aligned = 0
@@ -360,7 +425,7 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     cpu_busy = (time.process_time() - cpu0) / max(wall, 1e-9)      # host cores kept busy by this rank
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     launches = ctx.kernel_launches - l0
 
     # ---- end to end: host reads in, host records out, every step ----
@@ -426,7 +491,7 @@ def main():
         kern = {k: v for k, v in solo.items() if k.startswith("k_") or k.endswith("_kernels")}
         top = max(kern, key=kern.get) if kern else None
         counts = {k: per_step.get(k, 0.0) for k in ("n_fill_cells", "n_fill_bases", "n_fill_jobs", "n_fill_band_jobs", "n_fill_band_redo", "n_fill_dir_bytes",
-                                                      "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors", "n_chain_opcount")}
+                                                      "n_ed_cells", "n_ed_upper_jobs", "n_reseed_hits", "n_chain_anchors", "n_chain_opcount", "n_syncs")}
         n_ops = float(len(cig))
         # ALGORITHMIC bytes per step: what the stage must move whatever the implementation
         alg_bytes = {"k_fill": counts["n_fill_bases"] + 4.0 * n_ops,
@@ -485,7 +550,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
                 "config": {"workload": WL["name"], "reads_per_gpu_per_step": args.reads, "read_len": WL["read_len"], "err": WL["err"],
-                           "ref_len": WL["ref_len"], "mode": WL["mode"], "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2),
+                           "ref_len": WL["ref_len"], "mode": WL["mode"], "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2), "pinning": pinning,
                            "l2": "per-step working set (reads 2x%.0f MB + anchors, hits, direction matrices >1 GB) exceeds "
                                  "the 126 MB L2" % (bases / 1e6),
                            "sharding": "reads split across ranks (no data-path collective); index built on rank 0's GPU and broadcast as built tables over NCCL; records "

@@ -290,8 +290,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     // reads whose exact DP bailed out (opcount rule) join the fast list
     if (may_bail) {
         s.gmax_host.resize(cnt.size());
-        VM_CUDA_OK(c, cudaMemcpyAsync(s.gmax_host.data(), s.gmax.p, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-        VM_CUDA_OK(c, vm_stream_sync(c->stream));
+        VM_CUDA_OK(c, vm_d2h_sync(s.pin, s.gmax_host.data(), s.gmax.p, cnt.size() * 8, c->stream));
         for (int t = 0; t < n_exact; ++t)
             if (s.gmax_host[ids_host[t]] < 0) fast_ids.push_back(ids_host[t]);
     }
@@ -313,8 +312,7 @@ int vm_chain_core(vm_ctx *c, const vm_chain_params &prm, const VmAnchor *d_anch,
     VM_CUDA_OK(c, cudaEventRecord(ev[4], c->stream));
     // the DPs' own count of predecessor evaluations (the reference's `opcount`): B_chain_alg of the roofline report
     s.opcount_host.resize(cnt.size());
-    VM_CUDA_OK(c, cudaMemcpyAsync(s.opcount_host.data(), s.opcount.p, cnt.size() * 8, cudaMemcpyDeviceToHost, c->stream));
-    VM_CUDA_OK(c, vm_stream_sync(c->stream));
+    VM_CUDA_OK(c, vm_d2h_sync(s.pin, s.opcount_host.data(), s.opcount.p, cnt.size() * 8, c->stream));
     VM_CUDA_OK(c, cudaGetLastError());
     s.opcount_last = 0;
     for (int t = 0; t < n_exact; ++t) s.opcount_last += (double)s.opcount_host[(size_t)ids_host[(size_t)t]];

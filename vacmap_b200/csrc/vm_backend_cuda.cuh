@@ -514,8 +514,7 @@ public:
             kt.stop();
         }
         std::vector<int32_t> n_hits((size_t)nj);
-        BE_OK(cudaMemcpyAsync(n_hits.data(), d_n_hits, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(vm_stream_sync(c_->stream));
+        BE_OK(vm_d2h_sync(h_small_, n_hits.data(), d_n_hits, (size_t)nj * 4, c_->stream));
         {
             // jobs that overflowed their capacity: exact room at the end of the hit buffer, second launch
             std::vector<int> redo;
@@ -573,8 +572,7 @@ public:
             kt.stop();
         }
         n_out.assign((size_t)nj, 0);
-        BE_OK(cudaMemcpyAsync(n_out.data(), d_n_out, (size_t)nj * 4, cudaMemcpyDeviceToHost, c_->stream));
-        BE_OK(vm_stream_sync(c_->stream));
+        BE_OK(vm_d2h_sync(h_small_, n_out.data(), d_n_out, (size_t)nj * 4, c_->stream));
     }
 
     // stage-level: the anchors of every guide job on the host (parity tests)
@@ -1415,7 +1413,7 @@ private:
     int n_ctg_dev_ = 0;
     const vm_index_handle *d_ctg_for_ = nullptr;
     VmDevBuf x_ids_, x_used_, x_tmp_anc_, x_tmp_S_, x_tmp_len_, x_tmp_score_;
-    VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_;
+    VmPinnedBuf h_sorted_, h_S_, h_P_, h_A_, h_gmax_, h_jobs_, h_cig_, h_lsorted_, h_lP_, h_lgmax_, h_misc_, h_gx_, h_gy_, h_segs_, h_small_;
     std::vector<int64_t> off_host_;
 };
 

@@ -268,6 +268,7 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
 {
     std::string err;
     const int64_t l0 = wc->launches;
+    const VmSyncStats sync0 = vm_sync_stats();
     try {
         cudaSetDevice(job->c->device);
         wb.set_index(job->h);
@@ -360,6 +361,8 @@ void run_chunk(vm_job *job, int64_t ci, vm_ctx *wc, CudaBackend &wb, CudaBackend
         err = e.what();
         if (err.empty()) err = "error";
     }
+    wb.timer.add("w_sync_wait", 1e-6 * (double)(vm_sync_stats().ns - sync0.ns));      // this worker thread inside stream waits
+    wb.timer.add("n_syncs", (double)(vm_sync_stats().n - sync0.n));
     job_absorb(job, wb, wc->launches - l0, err);
 }
 

@@ -1,5 +1,8 @@
 // Shared device/host helpers for the vacmap_b200 CUDA library (sm_100a).
 #pragma once
+#include <chrono>
+#include <cstdlib>
+#include <sched.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,7 +41,20 @@ struct VmError {
 // Wait for a stream without burning a host core: the default cudaStreamSynchronize spins, and with several worker
 // threads waiting on their kernels at any moment that costs whole cores the host glue needs.  One blocking-sync
 // event per host thread.
+struct VmSyncStats { long long ns = 0, n = 0; };
+static inline VmSyncStats &vm_sync_stats() { thread_local VmSyncStats s; return s; }      // per host thread: time spent waiting, waits
+
+static inline cudaError_t vm_stream_sync_(cudaStream_t stream);
 static inline cudaError_t vm_stream_sync(cudaStream_t stream)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    const cudaError_t e = vm_stream_sync_(stream);
+    VmSyncStats &s = vm_sync_stats();
+    s.ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    s.n += 1;
+    return e;
+}
+static inline cudaError_t vm_stream_sync_(cudaStream_t stream)
 {
     thread_local cudaEvent_t ev = nullptr;
     if (!ev) {
@@ -47,6 +63,19 @@ static inline cudaError_t vm_stream_sync(cudaStream_t stream)
     }
     const cudaError_t e = cudaEventRecord(ev, stream);
     if (e != cudaSuccess) return e;
+    // VM_SYNC_SPIN_US: poll (yielding the core between polls) for that many microseconds before blocking -- a blocking
+    // wait is woken by an interrupt, which on a busy multi-GPU host can take far longer than the kernel waited for;
+    // 0 = block at once, negative = poll until done
+    static const long spin_us = getenv("VM_SYNC_SPIN_US") ? atol(getenv("VM_SYNC_SPIN_US")) : 0;
+    if (spin_us != 0) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            const cudaError_t q = cudaEventQuery(ev);
+            if (q != cudaErrorNotReady) return q;
+            if (spin_us > 0 && std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count() >= spin_us) break;
+            sched_yield();
+        }
+    }
     return cudaEventSynchronize(ev);
 }
 

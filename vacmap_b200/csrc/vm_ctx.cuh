@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/vacmap_b200.h"
 #include "vm_common.cuh"
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,23 @@ struct VmPinnedBuf {
     template <typename T> T *as() const { return (T *)p; }
 };
 
+// Device -> host through a page-locked bounce buffer, then a blocking wait.  A pageable destination would make the
+// driver wait for the stream itself -- spinning on a host core for as long as the kernels in front of the copy run.
+static inline cudaError_t vm_d2h_sync(VmPinnedBuf &pin, void *dst, const void *src, size_t bytes, cudaStream_t stream,
+                                      void *dst2 = nullptr, const void *src2 = nullptr, size_t bytes2 = 0)
+{
+    cudaError_t e = pin.ensure(bytes + bytes2 + 16);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpyAsync(pin.p, src, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && bytes2) e = cudaMemcpyAsync((char *)pin.p + bytes, src2, bytes2, cudaMemcpyDeviceToHost, stream);
+    if (e != cudaSuccess) return e;
+    e = vm_stream_sync(stream);
+    if (e != cudaSuccess) return e;
+    if (bytes) memcpy(dst, pin.p, bytes);
+    if (bytes2) memcpy(dst2, (char *)pin.p + bytes, bytes2);
+    return cudaSuccess;
+}
+
 // state of the chaining stage (stage-level upload / run / download, and the pipeline's device path)
 struct VmChainState {
     bool loaded = false;
@@ -70,6 +88,7 @@ struct VmChainState {
         fast_scratch, fast_off, sort_scratch, pre_n_dev, head_dev;      // pre_n / head: carried prefix of the linked DP (variant 3)
     std::vector<int32_t> used_fast;
     std::vector<int64_t> opcount_host;
+    VmPinnedBuf pin;                     // bounce buffer of the small per-read results read back between launches
     double opcount_last = 0;             // predecessor evaluations of the last vm_chain_core call (the reference's `opcount`, summed)
     float ms[4] = {0, 0, 0, 0};
 };

@@ -371,8 +371,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
                                                 B.n_anchor.as<int32_t>());
     *launches += 2;
     std::vector<int32_t> n_anchor(n);
-    SEED_OK(cudaMemcpyAsync(n_anchor.data(), B.n_anchor.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    SEED_OK(vm_stream_sync(stream));
+    SEED_OK(vm_d2h_sync(B.pin, n_anchor.data(), B.n_anchor.p, (size_t)n * 4, stream));
     std::vector<int64_t> t_off(n + 1, 0);
     for (int r = 0; r < n; ++r) {
         a_off_host[r + 1] = a_off_host[r] + n_anchor[r];
@@ -401,9 +400,7 @@ int vm_seed_batch(VmSeedBufs &B, const VmIndexDev &ix, const uint8_t *reads_dev,
                                                  check_num, B.table.as<VmClSlot>(), B.t_off.as<int64_t>(), B.compact.as<int>(),
                                                  B.out.as<VmAnchor>(), B.n_out.as<int32_t>(), B.need_rev.as<int32_t>());
     *launches += 2;
-    SEED_OK(cudaMemcpyAsync(n_out.data(), B.n_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    SEED_OK(cudaMemcpyAsync(need_rev.data(), B.need_rev.p, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
-    SEED_OK(vm_stream_sync(stream));
+    SEED_OK(vm_d2h_sync(B.pin, n_out.data(), B.n_out.p, (size_t)n * 4, stream, need_rev.data(), B.need_rev.p, (size_t)n * 4));
     SEED_OK(cudaGetLastError());
 #undef SEED_OK
     return 0;

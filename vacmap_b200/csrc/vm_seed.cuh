@@ -6,11 +6,13 @@
 struct VmSeedBufs {
     VmDevBuf mz_hash, mz_posz, mz_start, mz_cnt, mz_aoff, n_mz, n_anchor, n_out, need_rev, a_off, t_off, raw, out, table,
         compact, chunk_off, chunk_cnt;
+    VmPinnedBuf pin;      // bounce buffer of the per-read counts read back between launches
     void release()
     {
         VmDevBuf *b[] = {&mz_hash, &mz_posz, &mz_start, &mz_cnt, &mz_aoff, &n_mz, &n_anchor, &n_out, &need_rev, &a_off,
                          &t_off, &raw, &out, &table, &compact, &chunk_off, &chunk_cnt};
         for (VmDevBuf *x : b) x->release();
+        pin.release();
     }
 };
 
