@@ -49,6 +49,15 @@ void vm_ctx_destroy(vm_ctx *ctx);
 const char *vm_last_error(vm_ctx *ctx);
 /* Number of kernels launched by this ctx since creation (bench `gpu_launches`). */
 int64_t vm_kernel_launches(vm_ctx *ctx);
+/* Page-locked host memory for the read batches handed to vm_align_submit: the host-to-device copy of a sub-batch is
+ * then a DMA the worker's stream overlaps with the kernels of the other sub-batches; from pageable memory the driver
+ * stages it through the calling thread at memcpy speed.  vm_host_alloc / vm_host_free own the buffer (vm_host_free accepts ctx == NULL);
+ * vm_host_register / vm_host_unregister lock a buffer the caller owns (e.g. the read parser's).  No counterpart in the
+ * reference (its reads stay in Python strings, vacmap:391-420). */
+int vm_host_alloc(vm_ctx *ctx, int64_t bytes, void **out);
+int vm_host_free(vm_ctx *ctx, void *p);
+int vm_host_register(vm_ctx *ctx, void *p, int64_t bytes);
+int vm_host_unregister(vm_ctx *ctx, void *p);
 
 /*
  * Score tables.  The reference builds these with numpy at module import

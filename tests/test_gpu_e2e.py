@@ -123,3 +123,26 @@ def test_command_line_on_testdata(tmp_path):
     assert lines[0] == "@HD\tVN:1.0" and any(l.startswith("@SQ\tSN:") for l in lines)
     assert body == E2E["cases"][0]["sam"][0]
     assert sorted(l.split("\t")[1] for l in body) == ["16", "2048", "2048"]
+
+
+def test_pinned_host_reads_give_the_same_records(gpu_ctx):
+    """vm_host_alloc: a batch packed into page-locked memory (DMA upload per sub-batch) aligns like the same bytes
+    from pageable memory, several workers, two jobs in flight."""
+    import vacmap_b200 as vb
+    ref = synth.make_reference(31, 300000)
+    reads = synth.make_reads(ref, 32, 40, read_len=4000, err=0.10, sv_frac=0.3)
+    ix = vb.Index(ref, w=10, k=15, ctx=gpu_ctx)
+    al = vb.Aligner(ix, vb.default_option("H"), "H", workers=4, chunk_reads=10)
+    cat = b"".join(s.encode() for _, s in reads)
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for _, s in reads])
+    want = al.align_packed(cat, off)
+    pin = gpu_ctx.pinned_bytes(len(cat))
+    pin[:] = np.frombuffer(cat, dtype=np.uint8)
+    jobs = [al.submit_packed(pin, off) for _ in range(2)]
+    for j in jobs:
+        got = al.wait(j)
+        assert (got[0] == want[0]).all() and (got[1] == want[1]).all() and (got[2] == want[2]).all()
+    assert want[0][-1] > 0
+    del pin
+    ix.close()

@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(_HERE, "libvacmap_b200.so")
 
 VM_OK = 0
 NOPRE = -9999999
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _ERRS = {-1: "CUDA error", -2: "no CUDA device (vacmap_b200 has no CPU fallback)", -3: "bad argument",
          -4: "out of memory", -5: "bad call order"}
@@ -48,6 +48,10 @@ def load():
     L.vm_kernel_launches.argtypes = [vp]
     L.vm_kernel_launches.restype = i64
     L.vm_set_tables.argtypes = [vp, vp, i64, vp, i64, vp, i64]
+    L.vm_host_alloc.argtypes = [vp, i64, ctypes.POINTER(vp)]
+    L.vm_host_free.argtypes = [vp, vp]
+    L.vm_host_register.argtypes = [vp, vp, i64]
+    L.vm_host_unregister.argtypes = [vp, vp]
     L.vm_chain_global_batch.argtypes = [vp, ctypes.POINTER(ChainParamsC), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.vm_chain_global_upload.argtypes = [vp, ctypes.POINTER(ChainParamsC), i64, vp, vp, vp]
     L.vm_chain_global_run.argtypes = [vp, vp]
@@ -88,6 +92,18 @@ class Context:
     @property
     def kernel_launches(self):
         return int(load().vm_kernel_launches(self.h))
+
+    def pinned_bytes(self, n):
+        """uint8 array of n bytes in page-locked host memory (vm_host_alloc): a read batch packed into it is copied to
+        the device by DMA, overlapped with the other sub-batches' kernels.  Freed with the array."""
+        import weakref
+        import numpy as np
+        L = load()
+        p = ctypes.c_void_p()
+        check(self.h, L.vm_host_alloc(self.h, int(n), ctypes.byref(p)))
+        buf = (ctypes.c_uint8 * max(int(n), 1)).from_address(p.value)
+        weakref.finalize(buf, L.vm_host_free, None, p)
+        return np.frombuffer(buf, dtype=np.uint8)[:int(n)]
 
     def close(self):
         if getattr(self, "h", None):

@@ -269,8 +269,13 @@ class Aligner:
         n = len(seq_off) - 1
         job = ctypes.c_void_p()
         ctx = self.index.ctx
-        buf = (ctypes.c_char * len(seq_cat)).from_buffer_copy(seq_cat) if not isinstance(seq_cat, bytes) else seq_cat
-        _lib.check(ctx.h, L.vm_align_submit(ctx.h, self.index.h, ctypes.byref(self.params), n, buf, _lib.ptr(seq_off),
+        if isinstance(seq_cat, np.ndarray):      # e.g. Context.pinned_bytes: used in place (page-locked -> DMA upload)
+            if seq_cat.dtype != np.uint8 or not seq_cat.flags.c_contiguous:
+                raise ValueError("seq_cat: contiguous uint8 array or bytes")
+            buf, arg = seq_cat, _lib.ptr(seq_cat)
+        else:
+            buf = arg = seq_cat if isinstance(seq_cat, bytes) else bytes(seq_cat)
+        _lib.check(ctx.h, L.vm_align_submit(ctx.h, self.index.h, ctypes.byref(self.params), n, arg, _lib.ptr(seq_off),
                                             1 if resident else 0, ctypes.byref(job)))
         return (job, n, buf, seq_off)
 

@@ -8,7 +8,40 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 7; }
+int vm_abi_version(void) { return 8; }
+
+int vm_host_alloc(vm_ctx *c, int64_t bytes, void **out)
+{
+    if (!c || !out || bytes < 0) return VM_ERR_ARG;
+    *out = nullptr;
+    cudaSetDevice(c->device);
+    const cudaError_t e = cudaHostAlloc(out, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) { c->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); cudaGetLastError(); return VM_ERR_NOMEM; }
+    return VM_OK;
+}
+
+int vm_host_free(vm_ctx *c, void *p)
+{
+    // ctx may be NULL (a buffer outliving its context)
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); if (c) c->err = "cudaFreeHost failed"; return VM_ERR_CUDA; }
+    return VM_OK;
+}
+
+int vm_host_register(vm_ctx *c, void *p, int64_t bytes)
+{
+    if (!c || !p || bytes <= 0) return VM_ERR_ARG;
+    cudaSetDevice(c->device);
+    const cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { c->err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return VM_ERR_CUDA; }
+    return VM_OK;
+}
+
+int vm_host_unregister(vm_ctx *c, void *p)
+{
+    if (!c || !p) return VM_ERR_ARG;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); c->err = "cudaHostUnregister failed"; return VM_ERR_CUDA; }
+    return VM_OK;
+}
 
 int vm_ctx_create(int device, vm_ctx **out)
 {
