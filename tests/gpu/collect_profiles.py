@@ -1,0 +1,42 @@
+"""Build-box helper: copy the round's evidence from gpurun_out/ (scratch) into profiles/ (tracked) under a round prefix.
+usage: python tests/gpu/collect_profiles.py r2"""
+import json
+import os
+import shutil
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import ncu_summary  # noqa: E402
+from gpu import ncu_report  # noqa: E402,F401
+
+
+def main(prefix):
+    g, p = "gpurun_out", "profiles"
+    for src, dst in [("bench_default.json", "bench_default_10k.json"), ("bench_reference.json", "bench_reference_arm.json"),
+                     ("launches_bench.csv", "launches_bench_2000reads.csv")]:
+        if os.path.exists(os.path.join(g, src)):
+            shutil.copy(os.path.join(g, src), os.path.join(p, "%s_%s" % (prefix, dst)))
+    if os.path.exists(os.path.join(g, "launches_bench.csv")):
+        open(os.path.join(p, "%s_launches_bench_2000reads_summary.csv" % prefix), "w").write(
+            "\n".join(ncu_summary.summarise(os.path.join(g, "launches_bench.csv"))) + "\n")
+    full = {}
+    for tag in ("fill", "edupper", "reseed", "chain", "seed", "extract"):
+        rep = os.path.join(g, "prof_%s.ncu-rep" % tag)
+        if os.path.exists(rep):
+            full[tag] = ncu_report.summarise(rep)
+    if full:
+        json.dump(full, open(os.path.join(p, "%s_ncu_full_summary.json" % prefix), "w"), indent=1)
+        # DRAM traffic of the fill launches of the 2000-read pass (roofline.traffic is scaled from this)
+        rd = wr = 0.0
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for d in full.get("fill", []):
+            for k, v in d.items():
+                if k.startswith("rd["):
+                    rd += v * scale[k[3:-1]]
+                if k.startswith("wr["):
+                    wr += v * scale[k[3:-1]]
+        print("fill DRAM bytes in the capture: read %.3e write %.3e" % (rd, wr))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "r2")

@@ -3,7 +3,11 @@
 Reads stream through in super-batches (one vm_align_submit per batch, the next one submitted before the previous
 is collected); records of a batch are written in read order, a read that does not map writes nothing (quirk A2).
 `<ref>.w{w}_k{k}.mmi` index files are read and written in minimap2's format (vacmap_b200/mmi.py).
-Not mirrored: BAM output through samtools, BAM input, `-mode R` and `-mode asm`."""
+Several GPUs: launch one process per GPU (`python -m torch.distributed.run --nproc-per-node N -m vacmap_b200 ...`,
+the counterpart of the reference's `-t` worker processes, vacmap:391-420): rank 0 builds the index and broadcasts the
+built tables (NCCL), super-batches go round robin to the ranks, every rank writes its SAM text to a part file and
+rank 0 stitches the parts together in input order.
+Not mirrored: BAM output through samtools, BAM input, `-mode R`."""
 import argparse
 import os
 import sys
@@ -97,8 +101,41 @@ def batches(paths, want_comments, batch_bases):
         yield cur
 
 
+def stitch_parts(out, part_paths, sizes_per_rank):
+    """Rank 0's last step of a multi-GPU run: batch b was written by rank b % world as the (b // world)-th block of
+    its part file (`sizes_per_rank[r]` = byte length of each block); copy the blocks to `out` in batch order."""
+    world = len(part_paths)
+    files = [open(p, "rb") for p in part_paths]
+    try:
+        b = 0
+        while True:
+            r, i = b % world, b // world
+            if i >= len(sizes_per_rank[r]):
+                break
+            n = sizes_per_rank[r][i]
+            while n > 0:
+                buf = files[r].read(min(n, 1 << 24))
+                if not buf:
+                    raise IOError("part file %s is shorter than its block list" % part_paths[r])
+                out.write(buf)
+                n -= len(buf)
+            b += 1
+    finally:
+        for f in files:
+            f.close()
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    dist = None
+    if world > 1:
+        # one process per GPU (torchrun): this rank's device is its LOCAL_RANK
+        import torch
+        import torch.distributed as dist
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(args.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
     if args.o != "-":
         if not args.o.endswith(".sam"):
             sys.exit("output path must end in .sam (BAM goes through samtools in the reference; not mirrored) or be '-'")
@@ -111,17 +148,30 @@ def main(argv=None):
     index_name = "%s.w%d_k%d.mmi" % (refpath, args.w, args.k)
     if not args.nowriteindex and os.path.isfile(index_name):
         refpath = index_name
-    index = align.Index(refpath, w=args.w, k=args.k, device=args.device)
-    if not args.nowriteindex and refpath != index_name and not refpath.endswith("mmi"):
+    if dist is not None:
+        from . import shard
+        index = shard.broadcast_index(align.Index(refpath, w=args.w, k=args.k, device=args.device) if rank == 0 else None,
+                                      device=args.device)
+    else:
+        index = align.Index(refpath, w=args.w, k=args.k, device=args.device)
+    if rank == 0 and not args.nowriteindex and refpath != index_name and not refpath.endswith("mmi"):
         index.write_mmi(index_name)
     ref = [(n, index.seq(n)) for n in index.names]
     al = align.Aligner(index, opt, args.mode, host_threads=args.t)
     # the reference takes contig2seq from index.seq() (vacmap:363): non-ACGT bases are N there
     contig2seq = {n: index.seq(n) for n, _ in ref}
     contig2iloc = {n: i for i, (n, _) in enumerate(ref)}
-    out = sys.stdout if args.o == "-" else open(args.o, "w")
+    part_path = None
+    if dist is not None:
+        import tempfile
+        part_path = (args.o if args.o != "-" else os.path.join(tempfile.gettempdir(), "vacmap_b200.%s" % os.environ.get("MASTER_PORT", "0"))) + ".part%d" % rank
+        out = open(part_path, "w")
+    else:
+        out = sys.stdout if args.o == "-" else open(args.o, "w")
+    block_sizes = []      # multi-GPU: bytes of SAM text this rank wrote per batch it owned
     try:
-        out.write(sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
+        if rank == 0:
+            (out if dist is None else (sys.stdout if args.o == "-" else open(args.o, "w"))).write(sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
                                   command_line=" ".join(sys.argv if argv is None else ["vacmap_b200"] + list(argv))))
         if args.mode == "asm":
             # one contig at a time (the reference's asm workers, vacmap:394-397 -> assembly_get_readmap_DP_test) and the mode's

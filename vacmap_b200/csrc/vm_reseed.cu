@@ -253,6 +253,20 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
     const int k = VM_K9;
     int used = 0;
     bool full = false;
+    // The running segment of the diagonal this lane touched last stays in registers: consecutive hits of one diagonal
+    // (long exact stretches -- most of a HiFi read) cost no table round trip; it goes back to the table when the lane
+    // moves on to another diagonal and before the left-over pass.
+    long long cpoint = VM_PT_EMPTY;
+    int cslot = 0, c0 = 0, c2 = 1, c3 = 0;
+    unsigned c1 = 0;
+    bool dirty = false;
+    auto flush = [&]() {
+        if (dirty) {
+            VmPointVal *e = vals + cslot;
+            e->c0 = c0; e->c1 = c1; e->c23 = c3 | (c2 == 1 ? 0 : 256);
+            dirty = false;
+        }
+    };
     for (int q0 = 0; q0 < n; q0 += 32) {
         const int q = q0 + lane;
         int own = -1;
@@ -280,20 +294,26 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
             const int strand = (hit.iloc_s & 1) ? -1 : 1;
             const long long refloc = hit.refloc;
             const long long point = strand == 1 ? refloc - iloc : -(refloc + iloc);
-            const unsigned long long h = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
-            int s = (int)((h ^ (h >> 31)) & (unsigned long long)(sub - 1));
-            long long key;
-            while ((key = keys[(s << 5) + lane]) != VM_PT_EMPTY && key != point) s = (s + 1) & (sub - 1);
-            VmPointVal *e = vals + (s << 5) + lane;
-            if (key == VM_PT_EMPTY) {
-                if (++used >= sub) { full = true; break; }         // keep one slot free: the probe loop must terminate
-                keys[(s << 5) + lane] = point;
-                VmPointVal nv; nv.c0 = iloc; nv.c1 = (unsigned)refloc; nv.c23 = k | (strand == 1 ? 0 : 256); nv.q0 = qq;
-                *e = nv;
-                continue;
+            if (point != cpoint) {
+                // another diagonal of this lane: put the running segment back, fetch (or open) the new one
+                flush();
+                const unsigned long long h = (unsigned long long)point * 0x9E3779B97F4A7C15ULL;
+                int s = (int)((h ^ (h >> 31)) & (unsigned long long)(sub - 1));
+                long long key;
+                while ((key = keys[(s << 5) + lane]) != VM_PT_EMPTY && key != point) s = (s + 1) & (sub - 1);
+                cslot = (s << 5) + lane;
+                cpoint = point;
+                if (key == VM_PT_EMPTY) {
+                    if (++used >= sub) { full = true; break; }         // keep one slot free: the probe loop must terminate
+                    keys[cslot] = point;
+                    c0 = iloc; c1 = (unsigned)refloc; c2 = strand; c3 = k;
+                    VmPointVal nv; nv.c0 = c0; nv.c1 = c1; nv.c23 = k | (strand == 1 ? 0 : 256); nv.q0 = qq;
+                    vals[cslot] = nv;
+                    continue;
+                }
+                const VmPointVal pv = vals[cslot];
+                c0 = pv.c0; c1 = pv.c1; c3 = pv.c23 & 255; c2 = (pv.c23 & 256) ? -1 : 1;
             }
-            int c0 = e->c0, c3 = e->c23 & 255, c2 = (e->c23 & 256) ? -1 : 1;
-            unsigned c1 = e->c1;
             if (c0 + c3 >= iloc) {
                 const int bonus = iloc - (c0 + c3) + k;
                 if (bonus > 0) {
@@ -307,17 +327,20 @@ __global__ void __launch_bounds__(32) vm_reseed_merge_kernel(const VmReseedJobDe
                         if (strand == 1) { const int l3 = c3; c0 += l3; c1 += (unsigned)l3; c2 = 1; c3 = bonus; }
                         else { c0 += c3; c1 = (unsigned)refloc; c2 = -1; c3 = bonus; }
                     }
-                    e->c0 = c0; e->c1 = c1; e->c23 = c3 | (c2 == 1 ? 0 : 256);
+                    dirty = true;
                 }
             } else {
                 VmAnchor a; a.x = c0; a.y = c1; a.s = c2; a.l = c3;
                 out[qq] = a;
                 flag[qq] = 1;
-                e->c0 = iloc; e->c1 = (unsigned)refloc; e->c23 = k | (strand == 1 ? 0 : 256);
+                c0 = iloc; c1 = (unsigned)refloc; c2 = strand; c3 = k;
+                dirty = true;
             }
         }
         if (__any_sync(VM_FULL, full)) { if (lane == 0) n_out[blockIdx.x] = -1; return; }
     }
+    flush();
+    __syncwarp();
     // the segments still open, at slot n + (scan index of their diagonal's first hit)
     for (int t = lane; t < J.tab_size; t += 32) {
         if (keys[t] == VM_PT_EMPTY) continue;
