@@ -532,6 +532,9 @@ def main():
                     "frac_with_direction_spill": ((alg_bytes.get(top, 0.0) + spill) / secs / 1e9 / peak) if secs > 0 else None,
                     "gcups_full_matrix_equivalent": (counts["n_fill_cells"] / secs / 1e9) if top == "k_fill" and secs > 0 else None,
                     "all_kernels_ms": {k: round(v, 3) for k, v in sorted(kern.items())},
+                    # wall time of every stage of the lock-step pass (device-side glue kernels are inside front_device / extend_device)
+                    "lockstep_stage_ms": {k: round(v, 3) for k, v in sorted(solo.items())
+                                          if not k.startswith(("n_", "c_", "k_", "cpu_", "t_")) and not k.endswith("_kernels") and v >= 0.05},
                     "note": "integer DP wavefront: issue / ALU-pipe bound (ncu, 48-row class: issue 71 %, ALU 67 %, DRAM 15 %), not HBM bound "
                             "(SURVEY 8d); the HBM fraction is reported because north_star asks for it"}
         # the chaining kernels (the ones north_star names): both byte counts of SURVEY 8d

@@ -146,3 +146,54 @@ def test_pinned_host_reads_give_the_same_records(gpu_ctx):
     assert want[0][-1] > 0
     del pin
     ix.close()
+
+
+def test_command_line_on_two_gpus(tmp_path):
+    """One process per GPU (torchrun): index broadcast from rank 0, super-batches round robin, part files stitched in
+    input order -- the same SAM body as the single-GPU run."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import vacmap_b200.__main__ as cli
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = synth.make_reference(41, 300000)
+    reads = synth.make_reads(ref, 42, 24, read_len=3000, err=0.10, sv_frac=0.3)
+    (tmp_path / "ref.fa").write_text("".join(">%s\n%s\n" % (n, s) for n, s in ref))
+    (tmp_path / "reads.fa").write_text("".join(">%s\n%s\n" % (n, s) for n, s in reads))
+    common = ["-ref", str(tmp_path / "ref.fa"), "-read", str(tmp_path / "reads.fa"), "-mode", "H", "--nowriteindex", "--batch-bases", "9000"]
+    cli.main(common + ["-o", str(tmp_path / "one.sam")])
+    env = dict(os.environ, PYTHONPATH=root)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", "29731", "-m", "vacmap_b200"] + common + ["-o", str(tmp_path / "two.sam")], check=True, env=env, cwd=root,
+                   timeout=600)
+    body = lambda p: [l for l in p.read_text().splitlines() if not l.startswith("@PG")]
+    assert body(tmp_path / "two.sam") == body(tmp_path / "one.sam")
+    assert len(body(tmp_path / "one.sam")) > 20
+    assert not list(tmp_path.glob("*.part*"))
+
+
+def test_position_directory_of_long_9mer_runs(gpu_ctx, monkeypatch):
+    """A reference with skewed base composition gives 9-mers with hundreds to thousands of occurrences: their position
+    runs get a bucket directory (vm_index_build_buckets) and the local re-seeding's window search goes through it.
+    Records must equal those of an index built without the directory, and the oracle's."""
+    import vacmap_b200 as vb
+    rng = np.random.default_rng(77)
+    ref = [("chrA", np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, size=1_500_000, p=[0.46, 0.18, 0.18, 0.18])].tobytes().decode())]
+    reads = synth.make_reads(ref, 78, 12, read_len=6000, err=0.10, sv_frac=0.4)
+    opt = vb.default_option("H")
+    ix = vb.Index(ref, ctx=gpu_ctx)
+    got = vb.Aligner(ix, opt, "H", workers=1).align_batch(reads)
+    ix.close()
+    monkeypatch.setenv("VM_NO_KPOS_DIRECTORY", "1")
+    ix0 = vb.Index(ref, ctx=gpu_ctx)
+    plain = vb.Aligner(ix0, opt, "H", workers=1).align_batch(reads)
+    ix0.close()
+    assert got == plain and sum(len(g) for g in got) >= len(reads)
+    ox = oracle.Index(ref)
+    ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+    for (rid, seq), g in list(zip(reads, got))[:4]:
+        want = pl.align_read(rid, seq, ox, ctg, opt, "H")
+        assert [tuple(r) for r in g] == [tuple(w) for w in want], rid

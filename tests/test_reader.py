@@ -42,3 +42,21 @@ def test_fastq_record_with_empty_sequence_keeps_the_next_record_intact(tmp_path)
     p = tmp_path / "e.fastq"
     p.write_text("@r1\n\n+\n\n@r2\nACGT\n+\nIIII\n@r3\n+\n@r4\nGG\n+\n@>\n")
     assert list(align.read_fastx(str(p))) == [("r1", "", None), ("r2", "ACGT", "IIII"), ("r3", "", None), ("r4", "GG", "@>")]
+
+
+def test_stitch_parts_restores_batch_order(tmp_path):
+    """Multi-GPU command line: batch b is the (b // world)-th block of rank (b % world)'s part file."""
+    import io
+    from vacmap_b200.__main__ import stitch_parts
+    world = 3
+    blocks = [("batch%d\n" % b) * (b % 4) for b in range(10)]       # some batches write nothing
+    paths, sizes = [], []
+    for r in range(world):
+        mine = [blocks[b].encode() for b in range(r, 10, world)]
+        p = tmp_path / ("o.part%d" % r)
+        p.write_bytes(b"".join(mine))
+        paths.append(str(p))
+        sizes.append([len(m) for m in mine])
+    out = io.BytesIO()
+    stitch_parts(out, paths, sizes)
+    assert out.getvalue().decode() == "".join(blocks)

@@ -161,71 +161,105 @@ def main(argv=None):
     # the reference takes contig2seq from index.seq() (vacmap:363): non-ACGT bases are N there
     contig2seq = {n: index.seq(n) for n, _ in ref}
     contig2iloc = {n: i for i, (n, _) in enumerate(ref)}
+    header = sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
+                             command_line=" ".join(sys.argv if argv is None else ["vacmap_b200"] + list(argv)))
     part_path = None
     if dist is not None:
+        # this rank's SAM text goes to a part file next to the output (or in the temp directory for stdout)
         import tempfile
-        part_path = (args.o if args.o != "-" else os.path.join(tempfile.gettempdir(), "vacmap_b200.%s" % os.environ.get("MASTER_PORT", "0"))) + ".part%d" % rank
+        stem = args.o if args.o != "-" else os.path.join(tempfile.gettempdir(), "vacmap_b200.%s" % os.environ.get("MASTER_PORT", "0"))
+        part_path = "%s.part%d" % (stem, rank)
         out = open(part_path, "w")
     else:
         out = sys.stdout if args.o == "-" else open(args.o, "w")
-    block_sizes = []      # multi-GPU: bytes of SAM text this rank wrote per batch it owned
+        out.write(header)
+    block_sizes = []      # multi-GPU: bytes of SAM text per unit (super-batch, or contig in asm mode) this rank owned
+    mark = [0]
+
+    def end_block():
+        if dist is not None:
+            out.flush()
+            block_sizes.append(out.tell() - mark[0])
+            mark[0] = out.tell()
+
     try:
-        if rank == 0:
-            (out if dist is None else (sys.stdout if args.o == "-" else open(args.o, "w"))).write(sam.header_text([(n, len(s)) for n, s in ref], rg=rg_metadata(args),
-                                  command_line=" ".join(sys.argv if argv is None else ["vacmap_b200"] + list(argv))))
         if args.mode == "asm":
             # one contig at a time (the reference's asm workers, vacmap:394-397 -> assembly_get_readmap_DP_test) and the mode's
-            # own emitter (iterator_get_bam_dict_str, mammap_asm.py:22757-22941)
+            # own emitter (iterator_get_bam_dict_str, mammap_asm.py:22757-22941); several GPUs: contigs round robin
             from . import asm
             seen = set()
+            unit = 0
             for path in args.read:
                 for rec in align.read_fastx(path):
                     if rec[0] in seen:
                         continue
                     seen.add(rec[0])
+                    unit += 1
+                    if (unit - 1) % world != rank:
+                        continue
                     rows = asm.assembly_align(rec[0], rec[1], index, opt)
+                    if rows:
+                        qual = None if (args.Q or len(rec) < 3) else rec[2]
+                        for line in sam.iterator_get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
+                                                                  opt["cigar2cg"], opt["markunbalancetra"], opt):
+                            out.write(line + "\n")
+                    end_block()
+        else:
+            pending = None
+
+            def collect(p):
+                handle, recs_in = p
+                rec_off, recs, cig = al.wait(handle)
+                for i, rec in enumerate(recs_in):
+                    rows = al.rows_of(rec[0], recs[rec_off[i]:rec_off[i + 1]], cig)
                     if not rows:
                         continue
                     qual = None if (args.Q or len(rec) < 3) else rec[2]
-                    for line in sam.iterator_get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
-                                                              opt["cigar2cg"], opt["markunbalancetra"], opt):
-                        out.write(line + "\n")
-            return
-        pending = None
+                    try:
+                        if args.copycomments:
+                            lines = sam.get_bam_dict_str_comments(rows, rec[1].upper(), qual, rec[3] if len(rec) > 3 else None, contig2iloc,
+                                                                  contig2seq, opt["md"], opt["shortcs"], opt["cigar2cg"],
+                                                                  opt["markunbalancetra"], opt)
+                        else:
+                            lines = sam.get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
+                                                         opt["cigar2cg"], opt["markunbalancetra"], opt)
+                    except Exception:          # the reference's worker swallows the read (clrnano:24116-24125)
+                        continue
+                    out.write("\n".join(lines) + "\n")
+                end_block()
 
-        def collect(p):
-            handle, recs_in = p
-            rec_off, recs, cig = al.wait(handle)
-            for i, rec in enumerate(recs_in):
-                rows = al.rows_of(rec[0], recs[rec_off[i]:rec_off[i + 1]], cig)
-                if not rows:
+            # several GPUs: every rank parses the input (the read-name filter needs all names) and keeps every world-th batch
+            for bi, batch in enumerate(batches(args.read, args.copycomments, args.batch_bases)):
+                if bi % world != rank:
                     continue
-                qual = None if (args.Q or len(rec) < 3) else rec[2]
-                try:
-                    if args.copycomments:
-                        lines = sam.get_bam_dict_str_comments(rows, rec[1].upper(), qual, rec[3] if len(rec) > 3 else None, contig2iloc,
-                                                              contig2seq, opt["md"], opt["shortcs"], opt["cigar2cg"],
-                                                              opt["markunbalancetra"], opt)
-                    else:
-                        lines = sam.get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
-                                                     opt["cigar2cg"], opt["markunbalancetra"], opt)
-                except Exception:          # the reference's worker swallows the read (clrnano:24116-24125)
-                    continue
-                out.write("\n".join(lines) + "\n")
-
-        for batch in batches(args.read, args.copycomments, args.batch_bases):
-            enc = [r[1].upper().encode() for r in batch]
-            off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
-            nxt = (al.submit_packed(b"".join(enc), off), batch)
+                enc = [r[1].upper().encode() for r in batch]
+                off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
+                nxt = (al.submit_packed(b"".join(enc), off), batch)
+                if pending is not None:
+                    collect(pending)
+                pending = nxt
             if pending is not None:
                 collect(pending)
-            pending = nxt
-        if pending is not None:
-            collect(pending)
+        if dist is not None:
+            out.close()
+            sizes = [None] * world
+            dist.all_gather_object(sizes, block_sizes)      # doubles as the barrier: every part file is complete
+            if rank == 0:
+                final = sys.stdout.buffer if args.o == "-" else open(args.o, "wb")
+                try:
+                    final.write(header.encode())
+                    stitch_parts(final, ["%s.part%d" % (stem, r) for r in range(world)], sizes)
+                finally:
+                    if args.o != "-":
+                        final.close()
+            dist.barrier()
+            os.remove(part_path)
     finally:
-        if out is not sys.stdout:
+        if out is not sys.stdout and not out.closed:
             out.close()
         index.close()
+        if dist is not None:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -130,6 +130,8 @@ int vm_index_adopt(vm_ctx *c, int32_t n_contigs, const char *const *names, const
         ix->dev.w = ix->w;
         ix->dev.k = ix->k;
         ix->dev.mid_occ = ix->mid_occ_default;
+        std::string berr;
+        if (vm_index_build_buckets(ix, berr)) throw std::runtime_error(berr);
     } catch (const std::exception &e) {
         c->err = e.what();
         if (h) { vm_index_free(h->ix); delete h; }

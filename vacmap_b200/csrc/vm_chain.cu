@@ -459,18 +459,39 @@ static int vm_launch_exact_v(const VmChainArgs &args, const int *ids, int n_ids,
                              cudaStream_t stream)
 {
     if (n_ids <= 0) return 0;
-    if (use_smem && cap >= VM_CHAIN_ANCHOR_SMEM_MIN && cap <= VM_CHAIN_ANCHOR_SMEM_MAX) {
-        // long reads: anchors staged in shared memory too (28 B per anchor + the mbarrier)
-        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 28 + 16;
+    // Where S / S_arg (and the anchors) of a read live decides both the latency of one DP step and how many reads an SM
+    // holds (one warp per read): everything in shared memory is the fastest step but, for the long-read classes, leaves
+    // one or two warps per SM.  That is right for the handful of long reads of an ONT batch (the launch lasts as long
+    // as its slowest read) and wrong when the whole batch is long (HiFi, -k 19: every read has ~5 000 anchors; 148
+    // resident warps took 132 ms per 7 500 reads).  Pick the placement with the smallest estimated duration:
+    // waves of resident warps x relative step latency.
+    static const int n_sm = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+    static const int forced = getenv("VM_CHAIN_MODE") ? atoi(getenv("VM_CHAIN_MODE")) : -1;      // experiment knob
+    const size_t tables = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;
+    const size_t smem_of[3] = {tables, tables + (size_t)cap * 12, tables + (size_t)cap * 28 + 16};
+    const bool ok[3] = {true, use_smem, use_smem && cap >= VM_CHAIN_ANCHOR_SMEM_MIN && cap <= VM_CHAIN_ANCHOR_SMEM_MAX};
+    const double lat[3] = {2.2, 1.25, 1.0};
+    int mode = 0;
+    double best = 0;
+    for (int m = 0; m < 3; ++m) {
+        if (!ok[m]) continue;
+        size_t per_sm = (size_t)233472 / (smem_of[m] + 1024);
+        if (per_sm > 32) per_sm = 32;
+        if (per_sm < 1) per_sm = 1;
+        const double waves = (double)n_ids / (double)(per_sm * (size_t)n_sm);
+        const double t = (waves > 1.0 ? waves : 1.0) * lat[m];
+        if (m == 0 || t <= best) { best = t; mode = m; }
+    }
+    if (forced >= 0 && forced <= 2 && ok[forced]) mode = forced;
+    if (mode == 2) {
+        // anchors staged in shared memory too (28 B per anchor + the mbarrier)
         vm_smem_optin(vm_chain_exact_kernel<VARIANT, 2>);
-        vm_chain_exact_kernel<VARIANT, 2><<<n_ids, 32, smem, stream>>>(args, ids, cap);
-    } else if (use_smem) {
-        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4 + (size_t)cap * 12;
+        vm_chain_exact_kernel<VARIANT, 2><<<n_ids, 32, smem_of[2], stream>>>(args, ids, cap);
+    } else if (mode == 1) {
         vm_smem_optin(vm_chain_exact_kernel<VARIANT, 1>);
-        vm_chain_exact_kernel<VARIANT, 1><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+        vm_chain_exact_kernel<VARIANT, 1><<<n_ids, 32, smem_of[1], stream>>>(args, ids, cap);
     } else {
-        size_t smem = VM_GCL_MAX * 8 + VM_RGL_MAX * 4;
-        vm_chain_exact_kernel<VARIANT, 0><<<n_ids, 32, smem, stream>>>(args, ids, cap);
+        vm_chain_exact_kernel<VARIANT, 0><<<n_ids, 32, smem_of[0], stream>>>(args, ids, cap);
     }
     return 1;
 }

@@ -115,7 +115,7 @@ int vm_index_upload(VmIndex *ix, std::string &err)
     ix->dev.w = ix->w;
     ix->dev.k = ix->k;
     ix->dev.mid_occ = ix->mid_occ_default;
-    return 0;
+    return vm_index_build_buckets(ix, err);
 }
 
 void vm_index_free(VmIndex *ix)
@@ -125,5 +125,7 @@ void vm_index_free(VmIndex *ix)
     if (!ix->borrowed)
         for (void *q : p)
             if (q) cudaFree(q);
+    if (ix->d_krow) cudaFree(ix->d_krow);
+    if (ix->d_kbk) cudaFree(ix->d_kbk);
     delete ix;
 }

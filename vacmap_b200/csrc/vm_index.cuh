@@ -31,7 +31,35 @@ struct VmIndexDev {           // device pointers, passed to kernels by value
     int64_t ref_len;
     int32_t w, k;
     int32_t mid_occ;
+    // position directory of the long 9-mer runs (vm_index_build_buckets): krow[code] = row (or -1: short run, plain
+    // binary search); kbk[row * (kb_n + 1) + b] = lower_bound(b << kb_shift) inside the code's run, b = 0 .. kb_n
+    const int32_t *krow;
+    const uint32_t *kbk;
+    int32_t kb_shift, kb_n;
 };
+
+// first index in [b, e) of the code's position run with kpos >= lo (the window's start): a plain binary search over the
+// whole run costs log2(run) dependent HBM round trips -- 14 on a GRCh38-sized reference, where a 9-mer occurs ~12 000
+// times; with the directory it is one directory read and a search inside one position bucket (a sector or two)
+__device__ __forceinline__ int64_t vm_kpos_lower_bound(const VmIndexDev &ix, int code, int64_t b, int64_t e, long long lo)
+{
+    int64_t l = b, h = e;
+#ifdef __CUDA_ARCH__
+    const int row = ix.krow ? ix.krow[code] : -1;
+    if (row >= 0) {
+        long long bk = lo <= 0 ? 0 : (lo >> ix.kb_shift);
+        if (bk > ix.kb_n) bk = ix.kb_n;
+        const uint32_t *t = ix.kbk + (size_t)row * (size_t)(ix.kb_n + 1);
+        l = b + t[bk];
+        h = bk < ix.kb_n ? b + t[bk + 1] : e;
+    }
+#endif
+    while (l < h) {
+        const int64_t mid = (l + h) >> 1;
+        if ((long long)ix.kpos[mid] < lo) l = mid + 1; else h = mid;
+    }
+    return l;
+}
 
 struct VmIndex {
     int w = 10, k = 15;
@@ -49,6 +77,7 @@ struct VmIndex {
     // device copies
     void *d_ht = nullptr, *d_occ = nullptr, *d_kpos = nullptr, *d_koff = nullptr, *d_ref = nullptr;
     void *d_ukeys = nullptr, *d_ucnt = nullptr;      // device build: unique minimizer hashes (ascending) and their counts
+    void *d_krow = nullptr, *d_kbk = nullptr;        // position directory of the long 9-mer runs (always owned by the index)
     bool borrowed = false;                 // the device arrays belong to the caller (vm_index_adopt)
     VmIndexDev dev{};
 };
@@ -174,4 +203,6 @@ VmIndex *vm_index_build_host(const std::vector<std::string> &names, const std::v
 // the same index built on the device (vm_index_gpu.cu); ix->ref holds the raw concatenated sequence on entry
 int vm_index_build_device(VmIndex *ix, std::string &err);
 int vm_index_upload(VmIndex *ix, std::string &err);
+// position directory over ix->dev.kpos / koff (device arrays already in place); fills ix->dev.krow / kbk / kb_shift / kb_n
+int vm_index_build_buckets(VmIndex *ix, std::string &err);
 void vm_index_free(VmIndex *ix);

@@ -268,5 +268,71 @@ int vm_index_build_device(VmIndex *ix, std::string &err)
     ix->dev.w = w;
     ix->dev.k = k;
     ix->dev.mid_occ = ix->mid_occ_default;
+    return vm_index_build_buckets(ix, err);
+}
+
+// ---------------------------------------------------------------------------
+// Position directory of the long 9-mer runs.  One block per run: every entry whose bucket differs from its
+// predecessor's writes its index into the buckets in between (lower_bound of each bucket start), the tail is the
+// run length.
+// ---------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) ixg_bucket_kernel(const uint32_t *__restrict__ kpos, const int64_t *__restrict__ koff,
+                                                         const int32_t *__restrict__ row_code, int shift, int nb, uint32_t *__restrict__ kbk)
+{
+    const int code = row_code[blockIdx.x];
+    const int64_t b = koff[code];
+    const uint32_t len = (uint32_t)(koff[code + 1] - b);
+    uint32_t *t = kbk + (size_t)blockIdx.x * (size_t)(nb + 1);
+    const uint32_t *run = kpos + b;
+    for (uint32_t i = threadIdx.x; i <= len; i += blockDim.x) {
+        const int cur = i < len ? (int)(run[i] >> shift) : nb;            // past the end: every bucket left gets `len`
+        const int prev = i > 0 ? (int)(run[i - 1] >> shift) : -1;
+        for (int q = prev + 1; q <= cur; ++q) t[q] = i;
+    }
+}
+} // namespace
+
+#define VM_KB_MIN_RUN 128          // shorter runs: the plain binary search stays inside a few sectors anyway
+#define VM_KB_MAX_BUCKETS 2048
+#define VM_KB_MAX_BYTES (6ULL << 30)
+
+int vm_index_build_buckets(VmIndex *ix, std::string &err)
+{
+    ix->dev.krow = nullptr; ix->dev.kbk = nullptr; ix->dev.kb_shift = 0; ix->dev.kb_n = 0;
+    if (getenv("VM_NO_KPOS_DIRECTORY") || ix->dev.ref_len <= 0 || !ix->d_koff || !ix->d_kpos) return 0;
+    std::vector<int64_t> koff((size_t)VM_K9_KEYS + 1);
+    if (cudaMemcpy(koff.data(), ix->d_koff, koff.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { err = "position directory: cannot read koff"; return -1; }
+    std::vector<int32_t> krow((size_t)VM_K9_KEYS, -1), row_code;
+    for (int c = 0; c < VM_K9_KEYS; ++c)
+        if (koff[(size_t)c + 1] - koff[(size_t)c] >= VM_KB_MIN_RUN) { krow[(size_t)c] = (int32_t)row_code.size(); row_code.push_back(c); }
+    if (row_code.empty()) return 0;
+    int shift = 8;
+    while (((ix->dev.ref_len >> shift) + 1) > VM_KB_MAX_BUCKETS ||
+           (unsigned long long)row_code.size() * (unsigned long long)((ix->dev.ref_len >> shift) + 2) * 4ULL > VM_KB_MAX_BYTES) ++shift;
+    const int nb = (int)(ix->dev.ref_len >> shift) + 1;
+    void *d_codes = nullptr;
+    cudaError_t e = cudaMalloc(&ix->d_krow, krow.size() * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ix->d_kbk, row_code.size() * (size_t)(nb + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_codes, row_code.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(ix->d_krow, krow.data(), krow.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_codes, row_code.data(), row_code.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        ixg_bucket_kernel<<<(unsigned)row_code.size(), 256>>>((const uint32_t *)ix->d_kpos, (const int64_t *)ix->d_koff, (const int32_t *)d_codes, shift, nb,
+                                                              (uint32_t *)ix->d_kbk);
+        e = cudaDeviceSynchronize();
+    }
+    if (d_codes) cudaFree(d_codes);
+    if (e != cudaSuccess) {
+        // not enough memory for the directory: the plain search still works
+        cudaGetLastError();
+        if (ix->d_krow) { cudaFree(ix->d_krow); ix->d_krow = nullptr; }
+        if (ix->d_kbk) { cudaFree(ix->d_kbk); ix->d_kbk = nullptr; }
+        return 0;
+    }
+    ix->dev.krow = (const int32_t *)ix->d_krow;
+    ix->dev.kbk = (const uint32_t *)ix->d_kbk;
+    ix->dev.kb_shift = shift;
+    ix->dev.kb_n = nb;
     return 0;
 }

@@ -60,11 +60,7 @@ __device__ __forceinline__ void vm_probe(const VmIndexDev &ix, int code, const i
     if (b == e) return;
     for (int w = 0; w < n_win; ++w) {
         const long long lo = win_lo[w], hi = win_hi[w] - VM_K9;   // k-mer start must be <= hi
-        int64_t l = b, h = e;
-        while (l < h) {                       // lower_bound(lo)
-            const int64_t mid = (l + h) >> 1;
-            if ((long long)ix.kpos[mid] < lo) l = mid + 1; else h = mid;
-        }
+        int64_t l = vm_kpos_lower_bound(ix, code, b, e, lo);
         for (; l < e; ++l) {
             const long long refloc = ix.kpos[l];
             if (refloc > hi) break;
