@@ -35,7 +35,7 @@ WORKLOADS = {
     "cfg2": dict(name="synthetic HiFi reads (20 kb, 0.5% err) vs GRCh38-sized (3.1 Gb) reference, -mode L -k 19 -w 10 "
                       "(BASELINE configs[2]; 7 500 reads = 150 Mbp per GPU per step)",
                  mode="L", k=19, w=10, ref_len=3_100_000_000, ref_seed=2, n_contigs=62, read_len=20000, err=0.005, ratio=(1, 1, 1),
-                 reads=7500, read_seed=12, sv=False),
+                 reads=7500, read_seed=12, sv=False, workers=4, ahead=2),      # six workers' arenas + the 33 GB index + the lock-step leg do not fit
     "cfg3": dict(name="10 kb reads (10% err) from donors with nested DEL/INS/INV/DUP/TRA events (vacsim grammar) vs 250 Mb "
                       "reference, -mode S (BASELINE configs[3]; 10 000 reads per GPU per step)",
                  mode="S", k=15, w=10, ref_len=250_000_000, ref_seed=3, n_contigs=5, read_len=10000, err=0.10, ratio=(4, 3, 3),
@@ -324,12 +324,16 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workers", type=int, default=0, help="sub-batches in flight per GPU (0 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="reads per sub-batch (0 = automatic)")
-    ap.add_argument("--ahead", type=int, default=2, help="steps submitted ahead of the one being collected")
+    ap.add_argument("--ahead", type=int, default=0, help="steps submitted ahead of the one being collected (0 = the workload's: 3)")
     args = ap.parse_args()
     global WL
     WL = WORKLOADS[args.workload]
     if args.reads <= 0:
         args.reads = WL["reads"]
+    if args.ahead <= 0:
+        args.ahead = WL.get("ahead", 3)
+    if args.workers <= 0:
+        args.workers = WL.get("workers", 0)
     # stdout carries exactly one line, the JSON: everything else that writes to fd 1 while the run lasts (NCCL's
     # version banner, library chatter) is sent to stderr, and the line goes out through the saved descriptor
     global _STDOUT
@@ -451,22 +455,8 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t0
     d2h = recs.nbytes + cig.nbytes + rec_off.nbytes
-
-    # ---- roofline leg: one lock-step pass (one worker, one stream), so every kernel is timed alone by the CUDA
-    # events the library records on its launching stream; the pipelined legs above overlap kernels of several
-    # workers, which stretches their individual durations ----
-    solo = {}
-    solo_note = None
-    if rank == 0:
-        al1 = vb.Aligner(ix, vb.default_option(WL["mode"]), WL["mode"], workers=1)
-        try:
-            for _ in range(2):
-                al1.align_packed(cat, off, resident=True)
-                solo = dict(al1.last_stage_ms)
-        except Exception as e:      # e.g. not enough HBM left for whole-batch arenas beside the workers' (GRCh38-sized index)
-            sys.stderr.write("lock-step roofline leg failed (%s): kernel times taken from the pipelined steps\n" % e)
-            solo = {k: v / args.steps for k, v in stage.items()}
-            solo_note = "kernel times from the pipelined steps (stretched by the overlap of the workers): the lock-step pass did not fit"
+    free_b, total_b = torch.cuda.mem_get_info()
+    hbm_used_gb = round((total_b - free_b) / 1e9, 1)      # index + every worker's arenas, after both timed legs
 
     t = torch.tensor([wall, e2e_wall], dtype=torch.float64, device="cuda")
     tot = torch.tensor([aligned, aligned_e2e, len(recs)], dtype=torch.float64, device="cuda")
@@ -484,6 +474,22 @@ def main():
             assert len(gathered[1]) == int(tot[2].item())
     else:
         gather_ms = 0.0
+    # ---- roofline leg: one lock-step pass (one worker, one stream), so every kernel is timed alone by the CUDA
+    # events the library records on its launching stream; the pipelined legs above overlap kernels of several
+    # workers, which stretches their individual durations ----
+    solo = {}
+    solo_note = None
+    if rank == 0:
+        al1 = vb.Aligner(ix, vb.default_option(WL["mode"]), WL["mode"], workers=1)
+        try:
+            for _ in range(2):
+                al1.align_packed(cat, off, resident=True)
+                solo = dict(al1.last_stage_ms)
+        except Exception as e:      # e.g. not enough HBM left for whole-batch arenas beside the workers' (GRCh38-sized index)
+            sys.stderr.write("lock-step roofline leg failed (%s): kernel times taken from the pipelined steps\n" % e)
+            solo = {k: v / args.steps for k, v in stage.items()}
+            solo_note = "kernel times from the pipelined steps (stretched by the overlap of the workers): the lock-step pass did not fit"
+
     wall_max, e2e_max = [float(x) for x in t.cpu()]
     aligned_all, aligned_e2e_all, nrec_all = [float(x) for x in tot.cpu()]
 
@@ -557,7 +563,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32", "data": "synthetic",
                 "config": {"workload": WL["name"], "reads_per_gpu_per_step": args.reads, "read_len": WL["read_len"], "err": WL["err"],
-                           "ref_len": WL["ref_len"], "mode": WL["mode"], "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2), "pinning": pinning,
+                           "ref_len": WL["ref_len"], "mode": WL["mode"], "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2), "pinning": pinning, "hbm_used_gb": hbm_used_gb,
                            "l2": "per-step working set (reads 2x%.0f MB + anchors, hits, direction matrices >1 GB) exceeds "
                                  "the 126 MB L2" % (bases / 1e6),
                            "sharding": "reads split across ranks (no data-path collective); index built on rank 0's GPU and broadcast as built tables over NCCL; records "

@@ -469,8 +469,9 @@ int vm_align_submit(vm_ctx *c, vm_index_handle *h, const vm_align_params *p, int
         // least 512 reads -- every chunk pays the same fixed chain of launch and synchronisation latencies, and with the
         // extension stage's glue on the device the host no longer needs many small chunks to keep its cores busy:
         // measured 93 ms per 10k-read step with 3 workers x 5000 reads, 104 ms with 8 x 1667).  With more workers than
-        // chunks per job, the chunks of the next job run beside them.
-        int workers = p->workers > 0 ? p->workers : 4;
+        // chunks per job, the chunks of the next jobs run beside them: six workers over four jobs in flight measured
+        // 68.7-69.6 ms per step against 72-73 ms with four workers over three jobs (tests/gpu/ab_share.sh).
+        int workers = p->workers > 0 ? p->workers : 6;
         const int64_t chunk = p->chunk_reads > 0 ? p->chunk_reads : std::max<int64_t>(512, (n_reads + 1) / 2);
         if (n_reads <= chunk || workers == 1) workers = 1;
         job->bounds.assign(1, 0);

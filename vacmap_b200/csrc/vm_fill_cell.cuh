@@ -42,6 +42,9 @@ __device__ __forceinline__ __half2 vm_codes_half2(unsigned two_bytes) { return v
 
 // One cell for both jobs.  in: v = v(i-1,j), x1/x2 = x(i-1,j) from the cell above; u/y1/y2 = from the cell to the
 // left.  out: the same quantities for (i,j), and the direction bits of job A in byte 0 / job B in byte 2.
+// EQBIT: bit 7 = the bases are equal (the full-matrix kernel's traceback reads it; the banded kernel's compares the
+// staged bases itself and saves the instruction).
+template <bool EQBIT = true>
 __device__ __forceinline__ void vm_cell2(__half2 tc, __half2 qc, __half2 &v, __half2 &x1, __half2 &x2, __half2 &u, __half2 &y1,
                                          __half2 &y2, unsigned &dir)
 {
@@ -61,7 +64,7 @@ __device__ __forceinline__ void vm_cell2(__half2 tc, __half2 qc, __half2 &v, __h
     const __half2 ap = __hfma2_relu(one, a, t1), bp = __hfma2_relu(one, b, t1);
     const __half2 t2 = __hsub2(VM_H2C(g.q2), z);
     const __half2 a2p = __hfma2_relu(one, a2, t2), b2p = __hfma2_relu(one, b2, t2);
-    unsigned d = dl | (eqm & 0x00800080u);
+    unsigned d = EQBIT ? (dl | (eqm & 0x00800080u)) : dl;
     d |= __hgt2_mask(ap, zero) & 0x00080008u;
     d |= __hgt2_mask(bp, zero) & 0x00100010u;
     d |= __hgt2_mask(a2p, zero) & 0x00200020u;

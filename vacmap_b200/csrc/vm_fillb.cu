@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const 
                         cx2 = open2;
                     }
                     const __half2 qc = vm_codes_half2(sQ[j]);
-                    vm_cell2(tc[c], qc, cv, cx1, cx2, u[c], y1[c], y2[c], d[c]);
+                    vm_cell2<false>(tc[c], qc, cv, cx1, cx2, u[c], y1[c], y2[c], d[c]);
                     v[c] = cv; x1[c] = cx1; x2[c] = cx2;
                 }
             }
