@@ -7,20 +7,20 @@ WANT = [('Kernel Name', 'kernel'), ('gpu__time_duration.sum', 'ms'), ('dram__byt
         ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm%'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%'), ('launch__registers_per_thread', 'regs'),
-        ('launch__grid_size', 'grid'), ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
+        ('launch__grid_size', 'grid'), ('l1tex__t_sector_hit_rate.pct', 'l1hit%'), ('lts__t_sector_hit_rate.pct', 'l2hit%'), ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%'),
         ('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active', 'alu%'),
         ('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'fma%'),
         ('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'lsu%'), ('smsp__inst_executed.sum', 'inst'),
-        ('smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'st_long'),
-        ('smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio', 'st_short'),
-        ('smsp__average_warp_latency_issue_stalled_wait.ratio', 'st_wait'),
-        ('smsp__average_warp_latency_issue_stalled_barrier.ratio', 'st_bar'),
-        ('smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio', 'st_math'),
-        ('smsp__average_warp_latency_issue_stalled_not_selected.ratio', 'st_notsel'),
-        ('smsp__average_warp_latency_issue_stalled_lg_throttle.ratio', 'st_lg'),
-        ('smsp__average_warp_latency_issue_stalled_mio_throttle.ratio', 'st_mio'),
-        ('smsp__average_warp_latency_issue_stalled_branch_resolving.ratio', 'st_br'),
-        ('smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio', 'st_disp')]
+        ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'st_long'),
+        ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'st_short'),
+        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'st_wait'),
+        ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'st_bar'),
+        ('smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'st_math'),
+        ('smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'st_notsel'),
+        ('smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio', 'st_lg'),
+        ('smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio', 'st_mio'),
+        ('smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'st_br'),
+        ('smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio', 'st_disp')]
 
 
 def summarise(rep):
