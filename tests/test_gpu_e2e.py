@@ -197,3 +197,28 @@ def test_position_directory_of_long_9mer_runs(gpu_ctx, monkeypatch):
     for (rid, seq), g in list(zip(reads, got))[:4]:
         want = pl.align_read(rid, seq, ox, ctg, opt, "H")
         assert [tuple(r) for r in g] == [tuple(w) for w in want], rid
+
+
+def test_command_line_bam_in_bam_out(tmp_path):
+    """`-read reads.bam -o out.bam`: the unaligned-BAM input path (vacmap:439-466) and the BAM emitter carry the same three
+    alignments as the SAM run on testdata/ (README:124)."""
+    import gzip
+    import os
+    import shutil
+    import vacmap_b200.__main__ as cli
+    from vacmap_b200 import bam
+    td = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testdata")
+    for f in ("reference.fasta", "read.fasta"):
+        with gzip.open(os.path.join(td, f + ".gz"), "rb") as fi, open(tmp_path / f, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+    import vacmap_b200 as vb
+    reads = [(r[0], r[1]) for r in vb.read_fastx(str(tmp_path / "read.fasta"))]
+    w = bam.BamWriter(str(tmp_path / "reads.bam"), "@HD\tVN:1.0\tSO:unknown\n")
+    w.write_sam_lines(["%s\t4\t*\t0\t0\t*\t*\t0\t0\t%s\t*" % (n, s) for n, s in reads])
+    w.close()
+    cli.main(["-ref", str(tmp_path / "reference.fasta"), "-read", str(tmp_path / "reads.bam"), "-mode", "H", "--nowriteindex",
+              "-o", str(tmp_path / "out.bam")])
+    _, refs, recs = bam.read_bam_records(str(tmp_path / "out.bam"))
+    want = [l.split("\t") for l in E2E["cases"][0]["sam"][0]]
+    assert [(r["name"], r["flag"], refs[r["ref_id"]][0], r["pos"] + 1, r["mapq"], r["cigar"], r["seq"]) for r in recs] == \
+           [(f[0], int(f[1]), f[2], int(f[3]), int(f[4]), f[5], f[9]) for f in want]

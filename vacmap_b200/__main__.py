@@ -7,14 +7,15 @@ Several GPUs: launch one process per GPU (`python -m torch.distributed.run --npr
 the counterpart of the reference's `-t` worker processes, vacmap:391-420): rank 0 builds the index and broadcasts the
 built tables (NCCL), super-batches go round robin to the ranks, every rank writes its SAM text to a part file and
 rank 0 stitches the parts together in input order.
-Not mirrored: BAM output through samtools, BAM input, `-mode R`."""
+`-read x.bam` (unaligned BAM, as the reference reads it through pysam) and `-o out.bam` / `out.sorted.bam` (the reference
+pipes its SAM text into samtools) are handled by vacmap_b200/bam.py.  Not mirrored: `-mode R`."""
 import argparse
 import os
 import sys
 
 import numpy as np
 
-from . import align, sam
+from . import align, bam, sam
 
 
 RG_FLAGS = ("ID", "SM", "LB", "PL", "DS", "DT", "PU", "PI", "PG", "CN", "FO", "KS", "PM", "BC")
@@ -82,13 +83,44 @@ def options_from(args):
     return opt
 
 
+def read_records(path, want_comments=False):
+    """Records of one input file: FASTA / FASTQ (.gz) through the reader, `.bam` as the reference takes them from pysam
+    (vacmap:439-466)."""
+    if path.endswith(".bam"):
+        return bam.read_bam(path)
+    return align.read_fastx(path, read_comment=want_comments)
+
+
+class BamSink:
+    """File-like front of bam.BamWriter: takes the SAM text (str or bytes, in arbitrary pieces) the emitter writes."""
+
+    def __init__(self, path, header):
+        self.w = bam.BamWriter(path, header)
+        self.tail = ""
+        self.closed = False
+
+    def write(self, text):
+        if isinstance(text, bytes):
+            text = text.decode()
+        lines = (self.tail + text).split("\n")
+        self.tail = lines.pop()
+        self.w.write_sam_lines(lines)
+
+    def close(self):
+        if self.tail:
+            self.w.write_sam_lines([self.tail])
+            self.tail = ""
+        self.w.close()
+        self.closed = True
+
+
 def batches(paths, want_comments, batch_bases):
     """Reads of all input files in order, cut into batches of ~batch_bases; a read name seen before is skipped
     (the reference's `unique_set`, vacmap:428-476)."""
     cur, n = [], 0
     seen = set()
     for path in paths:
-        for rec in align.read_fastx(path, read_comment=want_comments):
+        for rec in read_records(path, want_comments):
             if rec[0] in seen:
                 continue
             seen.add(rec[0])
@@ -137,8 +169,8 @@ def main(argv=None):
         torch.cuda.set_device(args.device)
         dist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
     if args.o != "-":
-        if not args.o.endswith(".sam"):
-            sys.exit("output path must end in .sam (BAM goes through samtools in the reference; not mirrored) or be '-'")
+        if not args.o.endswith((".sam", ".bam")):
+            sys.exit("output path must end in .sam or .bam (sorted.bam: coordinate-sorted) or be '-'")
         if os.path.isfile(args.o) and not args.force:
             sys.exit("output file exists (use --force)")
     opt = options_from(args)
@@ -171,8 +203,11 @@ def main(argv=None):
         part_path = "%s.part%d" % (stem, rank)
         out = open(part_path, "w")
     else:
-        out = sys.stdout if args.o == "-" else open(args.o, "w")
-        out.write(header)
+        if args.o.endswith(".bam"):
+            out = BamSink(args.o, header)
+        else:
+            out = sys.stdout if args.o == "-" else open(args.o, "w")
+            out.write(header)
     block_sizes = []      # multi-GPU: bytes of SAM text per unit (super-batch, or contig in asm mode) this rank owned
     mark = [0]
 
@@ -190,7 +225,7 @@ def main(argv=None):
             seen = set()
             unit = 0
             for path in args.read:
-                for rec in align.read_fastx(path):
+                for rec in read_records(path):
                     if rec[0] in seen:
                         continue
                     seen.add(rec[0])
@@ -245,9 +280,10 @@ def main(argv=None):
             sizes = [None] * world
             dist.all_gather_object(sizes, block_sizes)      # doubles as the barrier: every part file is complete
             if rank == 0:
-                final = sys.stdout.buffer if args.o == "-" else open(args.o, "wb")
+                final = sys.stdout.buffer if args.o == "-" else (BamSink(args.o, header) if args.o.endswith(".bam") else open(args.o, "wb"))
                 try:
-                    final.write(header.encode())
+                    if not args.o.endswith(".bam"):
+                        final.write(header.encode())
                     stitch_parts(final, ["%s.part%d" % (stem, r) for r in range(world)], sizes)
                 finally:
                     if args.o != "-":
