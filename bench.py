@@ -40,6 +40,10 @@ WORKLOADS = {
                       "reference, -mode S (BASELINE configs[3]; 10 000 reads per GPU per step)",
                  mode="S", k=15, w=10, ref_len=250_000_000, ref_seed=3, n_contigs=5, read_len=10000, err=0.10, ratio=(4, 3, 3),
                  reads=10000, read_seed=31, sv=True),
+    "cfg4": dict(name="synthetic contigs (inversion + deletion + insertion, 0.1% divergence) vs GRCh38-sized (3.1 Gb) reference, "
+                      "-mode asm --H --fakecigar (BASELINE configs[4] at reduced contig length; one contig per GPU per step)",
+                 mode="asm", k=15, w=10, ref_len=3_100_000_000, ref_seed=2, n_contigs=62, read_len=2_000_000, err=0.001, ratio=(1, 1, 1),
+                 reads=1, read_seed=41, sv=False),
 }
 WL = WORKLOADS["cfg1"]
 
@@ -297,6 +301,116 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
+def make_asm_contig(ref, rank, length):
+    """One contig per rank: a slice of a reference contig with a 20 kb inversion, a 5 kb deletion, a 3 kb insertion and
+    0.1 % divergence."""
+    import synth
+    rng = np.random.default_rng(WL["read_seed"] + rank)
+    src = np.frombuffer(ref[rank % len(ref)][1].encode(), dtype=np.uint8)
+    st = int(rng.integers(0, len(src) - length - 10000))
+    src = src[st:st + length + 5000]
+    a, b, c = length // 5, int(length * 0.45), int(length * 0.7)
+    parts = [src[:a], synth._COMP[src[a:a + 20000]][::-1], src[a + 20000:b], src[b + 5000:c], synth.random_seq(rng, 3000), src[c:]]
+    return synth.mutate(rng, np.concatenate(parts), WL["err"], WL["ratio"]).tobytes().decode()
+
+
+def run_asm(args):
+    """--workload cfg4: contigs through `-mode asm` (vacmap_b200.asm.assembly_align: Python host loop like the reference's,
+    every hot loop a CUDA entry point).  A step = one contig per GPU, host sequence in, record rows out."""
+    import torch
+    import vacmap_b200 as vb
+    import vacmap_b200.__main__ as cli
+    from vacmap_b200 import asm, shard
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    args.warmup = max(args.warmup, 3)
+    ref = make_workload(0, ref_only=True)
+    contig = make_asm_contig(ref, rank, WL["read_len"])
+    ctx = vb._lib.Context(local_rank)
+    t_ix = time.perf_counter()
+    if dist is not None:
+        ix = shard.broadcast_index(vb.Index(ref, w=WL["w"], k=WL["k"], ctx=ctx) if rank == 0 else None, ctx=ctx, device=local_rank)
+    else:
+        ix = vb.Index(ref, w=WL["w"], k=WL["k"], ctx=ctx)
+    index_s = time.perf_counter() - t_ix
+    opt = cli.options_from(cli.build_parser().parse_args(["-ref", "x", "-read", "x", "-mode", "asm", "--H", "--fakecigar"]))
+    rows = None
+    for _ in range(args.warmup):
+        rows = asm.assembly_align("ctg%d" % rank, contig, ix, opt, ctx=ctx)
+    sampler = ClockSampler(list(range(int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    asm.STATS.clear()
+    l0 = ctx.kernel_launches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rows = asm.assembly_align("ctg%d" % rank, contig, ix, opt, ctx=ctx)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.kernel_launches - l0
+    aligned = len(contig) * args.steps if rows else 0
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([aligned, len(rows)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return
+    wall_max = float(t.cpu()[0])
+    value = float(tot.cpu()[0]) / wall_max / 1e9
+    stages = {k: round(1000 * v / args.steps, 1) for k, v in sorted(asm.STATS.items())}
+    stages["python_host_loop"] = round(1000 * wall / args.steps - sum(stages.values()), 1)
+    cpu = None
+    if not args.no_cpu:
+        # the oracle's restatement of the contig path on one core, on a 600 kb contig of a 5 Mb reference (the oracle's
+        # index build is single-threaded)
+        import oracle
+        import oracle.asm as oasm
+        import synth
+        small_ref = synth.make_reference(WL["ref_seed"], 5_000_000)
+        keep = WL["read_len"]
+        WL["read_len"] = 600_000
+        small = make_asm_contig(small_ref, 0, 600_000)
+        WL["read_len"] = keep
+        import oracle.pipeline as opl
+        ox = oracle.Index(small_ref, w=WL["w"], k=WL["k"])
+        octg = opl.Contigs([n for n, _ in small_ref], [s_ for _, s_ in small_ref])
+        tc = time.perf_counter()
+        oasm.assembly_align("ctg", small, ox, octg, opt)
+        dt = time.perf_counter() - tc
+        cpu = {"value": len(small) / dt / 1e9, "unit": "Gbp/s", "cores": 1, "kind": "port",
+               "sample": "one 600 kb contig vs a 5 Mb reference, oracle port of the contig path (C stages + Python glue), one core, %.1f s" % dt}
+    peak, peak_src = peaks()
+    emit({"metric": "aligned_gbp_per_s", "value": value, "unit": "Gbp/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": 1000 * wall_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64+i32",
+          "data": "synthetic",
+          "config": {"workload": WL["name"], "contig_len": len(contig), "contigs_per_gpu_per_step": 1, "ref_len": WL["ref_len"], "mode": "asm",
+                     "k": WL["k"], "w": WL["w"], "index_build_s": round(index_s, 2), "records_per_contig": len(rows),
+                     "l2": "a contig's anchors, hits and direction matrices exceed the 126 MB L2",
+                     "note": "no resident variant: a contig is processed batch by batch by the Python host loop, so value == e2e"},
+          "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": len(contig), "d2h_bytes_per_step": int(sum(len(r[8]) for r in rows))},
+          "gpu_launches": int(launches / max(args.steps, 1)), "stage_ms_per_step": stages,
+          "roofline": {"bound": "hbm", "kernel": None, "achieved": None, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": None,
+                       "traffic": None,
+                       "note": "host-bound: the time outside the CUDA entry points (python_host_loop) dominates; the kernels are the per-read "
+                               "path's (roofline in the default bench line)"},
+          "cpu_baseline": cpu, "clocks": clocks})
+
+
 KERNEL_BYTES_NOTE = {
     "k_fill": "B = sum(q+t) sequence bytes + 4 B per CIGAR op (SURVEY 8d's compulsory terms); the direction bytes of the band cells "
               "(one 128-byte line per step and direction word, written once, re-read along the path) exceed shared memory and "
@@ -340,6 +454,9 @@ def main():
     sys.stdout.flush()
     _STDOUT = os.dup(1)
     os.dup2(2, 1)
+    if args.workload == "cfg4" and args.impl != "reference":
+        run_asm(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

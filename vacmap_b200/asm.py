@@ -8,10 +8,26 @@ predecessor is skipped, a carried back-pointer of 0 is followed inside the curre
 in a carried anchor raises ``IndexError`` (the reference's traceback follows the negated "no predecessor" mark as an
 index; its worker then drops the contig).
 
-Still host-side here (numpy): the carry slice and the traceback.  Not mirrored yet: the seeding batches
-(``yield_mapinfo``), the re-seeding between the rounds and ``ass_extend_func``.
+Still host-side here (numpy): the carry slice and the traceback.  The rest of the contig path (seeding batches,
+re-seeding between the rounds, ``ass_extend_func``) follows below the chaining loops.
 """
+import time
+from contextlib import contextmanager
+
 import numpy as np
+
+# wall seconds spent inside the CUDA entry points, by stage (bench.py --workload cfg4 reads and resets it); everything
+# else of a contig's time is the Python host loop
+STATS = {}
+
+
+@contextmanager
+def _timed(name):
+    t0 = time.perf_counter()
+    try:
+        yield
+    finally:
+        STATS[name] = STATS.get(name, 0.0) + time.perf_counter() - t0
 
 from .chain import ChainParams, chain_linked_batch
 
@@ -44,7 +60,8 @@ def linked_chain_path(batches, params=None, second_round=False, ctx=None, dp=Non
                              params.large_readgap, 4)
     if dp is None:
         def dp(gs, gi, pS, pP, prl, linked):
-            r = chain_linked_batch([(gs, gi, pS, pP, prl, linked)], params, ctx=ctx)[0]
+            with _timed("linked_dp"):
+                r = chain_linked_batch([(gs, gi, pS, pP, prl, linked)], params, ctx=ctx)[0]
             return r.g_max_index, r.S, r.P, r.S_arg
     g_max_scores, g_max_index = 0, 0
     pre_S = np.zeros(0, np.float64)
@@ -162,7 +179,8 @@ def yield_mapinfo(seq, aligner, batch=100000):
     en = 0
     for g0 in range(0, len(slices), group):
         part = slices[g0:g0 + group]
-        maps = aligner.map_batch([seq[a:b] for a, b in part], check_num=-1, mid_occ=-1)
+        with _timed("seed"):
+            maps = aligner.map_batch([seq[a:b] for a, b in part], check_num=-1, mid_occ=-1)
         for (st, en), rows in zip(part, maps):
             one = np.array(rows, dtype=np.int64).reshape(-1, 4)
             if len(one) > 0:
@@ -237,7 +255,8 @@ def collect_second_round_anchors(r_st, r_en, raw, seq, index, ctg, k=9):
     kernels), then sorted by read position with numba's argsort, twice (:22754-22755)."""
     raw = np.ascontiguousarray(raw, dtype=np.int64)
     wins, guides = guide_windows(raw, ctg, 2000)
-    rows = align.local_reseed_batch(index, [seq], [(0, wins, guides, int(r_st), int(r_en) - k)])[0]
+    with _timed("reseed"):
+        rows = align.local_reseed_batch(index, [seq], [(0, wins, guides, int(r_st), int(r_en) - k)])[0]
     if len(rows) == 0:
         return rows
     rows = rows[numba_argsort(rows[:, 0])]
@@ -319,7 +338,8 @@ def _extend_edge(seq, L, al, ctg):
                 if look != 0:
                     query = seq[max(q_st - look, 0):q_st][::-1]
                     target = ref[slice(t_st - cs - len(query), t_st - cs)][::-1]
-                    r = _vi.k_cigar(target, query, **ext)
+                    with _timed("extend"):
+                        r = _vi.k_cigar(target, query, **ext)
                     one[0] = (q_st - r[2], t_st - r[3], 1, 0)
             else:
                 t_en, q_st = pre[1] + pre[3], pre[0]
@@ -328,7 +348,8 @@ def _extend_edge(seq, L, al, ctg):
                 if look != 0:
                     query = seq[max(q_st - look, 0):q_st][::-1]
                     target = reverse_complement(ref[slice(t_en - cs, t_en + len(query) - cs)])[::-1]
-                    r = _vi.k_cigar(target, query, **ext)
+                    with _timed("extend"):
+                        r = _vi.k_cigar(target, query, **ext)
                     one[0] = (q_st - r[2], t_en + r[3], -1, 0)
         else:
             t = one[0]
@@ -345,7 +366,8 @@ def _extend_edge(seq, L, al, ctg):
                 if look != 0:
                     query = seq[q_en:q_en + look]
                     target = ref[slice(t_en - cs, t_en + len(query) - cs)]
-                    r = _vi.k_cigar(target, query, **ext)
+                    with _timed("extend"):
+                        r = _vi.k_cigar(target, query, **ext)
                     one[-1] = (q_en + r[2], t_en + r[3], 1, 0)
             else:
                 t_st, q_en = now[1], now[0] + now[3]
@@ -353,7 +375,8 @@ def _extend_edge(seq, L, al, ctg):
                 if look != 0:
                     query = seq[q_en:q_en + look]
                     target = reverse_complement(ref[slice(t_st - cs - len(query), t_st - cs)])
-                    r = _vi.k_cigar(target, query, **ext)
+                    with _timed("extend"):
+                        r = _vi.k_cigar(target, query, **ext)
                     one[-1] = (q_en + r[2], t_st - r[3], -1, 0)
         else:
             t = one[-1]
@@ -485,7 +508,9 @@ def _split_alignment(alignment, seq, rc_seq, L, ctg, eqx):
     if not pairs:
         raise ContigDropped("no segment to fill")
     cigar = None
-    for r in _vi.k_cigar_batch(pairs, 2, -4, 4, 2, 24, 1, -1, -1, eqx):
+    with _timed("fill"):
+        filled = _vi.k_cigar_batch(pairs, 2, -4, 4, 2, 24, 1, -1, -1, eqx)
+    for r in filled:
         if r[0] == "":
             raise ContigDropped("mp.k_cigar ERROR: Failed to compute CIGAR")
         cigar = r[0] if cigar is None else link_cigar(cigar, r[0])
