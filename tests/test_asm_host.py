@@ -47,3 +47,24 @@ def test_second_round_paths_trimmed_and_the_traceback_quirk():
         path = asm.trim_overlaps(asm.linked_chain_path(batches, prm, second_round=True, dp=_second))
         assert np.array_equal(np.array(path, dtype=np.int64).reshape(-1, 4), G["l%d_path" % fi]), fi
     assert n_err == 1
+
+
+def test_product_link_cigar_matches_reference():
+    """vacmap_b200.asm.link_cigar (boundary-only) and its linear-time fold against the reference's link_cigar
+    (mammap_asm.py:22366-22410) on the recorded pairs (tests/golden/asm_link_cigar.json)."""
+    import json
+    import os
+    from vacmap_b200 import asm
+    rows = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_link_cigar.json")))
+    assert len(rows) >= 300
+    for a, b, want in rows:
+        assert asm.link_cigar(a, b) == want, (a, b)
+    # the fold: joining many pieces one boundary at a time equals the pairwise chain
+    import random
+    rnd = random.Random(3)
+    for _ in range(50):
+        pieces = ["".join("%d%s" % (rnd.randint(1, 30), rnd.choice("MID=X")) for _ in range(rnd.randint(1, 4))) for _ in range(rnd.randint(1, 12))]
+        ref = pieces[0]
+        for p in pieces[1:]:
+            ref = asm.link_cigar(ref, p)
+        assert asm.link_cigars(pieces) == ref

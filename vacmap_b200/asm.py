@@ -161,11 +161,47 @@ class Contigs:
 
 
 def link_cigar(c1, c2):
-    """:22366-22410 -- two CIGAR strings joined, the boundary ops merged when they are the same op."""
-    a, b = _CIG.findall(c1), _CIG.findall(c2)
-    if a and b and a[-1][1] == b[0][1]:
-        return "".join(n + o for n, o in a[:-1]) + str(int(a[-1][0]) + int(b[0][0])) + a[-1][1] + "".join(n + o for n, o in b[1:])
+    """:22366-22410 -- two CIGAR strings joined, the boundary ops merged when they are the same op.  Only the boundary is
+    looked at (a contig's CIGAR grows to megabytes)."""
+    if not c1 or not c2:
+        return c1 + c2
+    i = len(c1) - 1
+    j = i - 1
+    while j >= 0 and c1[j].isdigit():
+        j -= 1
+    k = 0
+    while k < len(c2) and c2[k].isdigit():
+        k += 1
+    if k < len(c2) and c1[i] == c2[k] and j + 1 < i and k > 0:
+        return c1[:j + 1] + str(int(c1[j + 1:i]) + int(c2[:k])) + c1[i] + c2[k + 1:]
     return c1 + c2
+
+
+def link_cigars(pieces):
+    """link_cigar folded over the segment CIGARs of a sub-alignment, in linear time: everything in front of the running
+    CIGAR's last piece is frozen, only that piece is looked at and rewritten."""
+    frozen, last = [], None
+    for piece in pieces:
+        if last is None:
+            last = piece
+            continue
+        if not last or not piece:
+            last = last + piece
+            continue
+        i = len(last) - 1
+        j = i - 1
+        while j >= 0 and last[j].isdigit():
+            j -= 1
+        k = 0
+        while k < len(piece) and piece[k].isdigit():
+            k += 1
+        if k < len(piece) and last[i] == piece[k] and j + 1 < i and k > 0:
+            frozen.append(last[:j + 1])
+            last = str(int(last[j + 1:i]) + int(piece[:k])) + last[i] + piece[k + 1:]
+        else:
+            frozen.append(last)
+            last = piece
+    return "".join(frozen) + (last or "")
 
 
 def yield_mapinfo(seq, aligner, batch=100000):
@@ -180,9 +216,9 @@ def yield_mapinfo(seq, aligner, batch=100000):
     for g0 in range(0, len(slices), group):
         part = slices[g0:g0 + group]
         with _timed("seed"):
-            maps = aligner.map_batch([seq[a:b] for a, b in part], check_num=-1, mid_occ=-1)
+            maps = aligner.map_batch([seq[a:b] for a, b in part], check_num=-1, mid_occ=-1, arrays=True)
         for (st, en), rows in zip(part, maps):
-            one = np.array(rows, dtype=np.int64).reshape(-1, 4)
+            one = np.array(rows, dtype=np.int64).reshape(-1, 4)      # a copy: the read offset is added in place
             if len(one) > 0:
                 one[:, 0] += st
             if len(one) + cache_size > 500000:
@@ -507,14 +543,12 @@ def _split_alignment(alignment, seq, rc_seq, L, ctg, eqx):
         pre = now
     if not pairs:
         raise ContigDropped("no segment to fill")
-    cigar = None
     with _timed("fill"):
         filled = _vi.k_cigar_batch(pairs, 2, -4, 4, 2, 24, 1, -1, -1, eqx)
     for r in filled:
         if r[0] == "":
             raise ContigDropped("mp.k_cigar ERROR: Failed to compute CIGAR")
-        cigar = r[0] if cigar is None else link_cigar(cigar, r[0])
-    return kept, cigar
+    return kept, link_cigars([r[0] for r in filled])
 
 
 def _records(new_al, cigars, readid, mapq, L, ctg, hardclip):

@@ -70,7 +70,7 @@ __host__ __device__ constexpr int vm_fb_cap(int G) { return G == 1 ? VM_FB_CAP :
 // need 40..60 rows) into 48, 56 or 64 rows instead of 64 or 96, and share the per-step bookkeeping (bounds, three
 // shuffles, the store, the loop) between eight jobs.
 template <int C, int G>
-__global__ void __launch_bounds__(128, (C == 6 && G == 4) ? 6 : 1) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
+__global__ void __launch_bounds__(128) vm_fillb_kernel(VmAlnJobDev *jobs, const VmFillBandPair *__restrict__ pairs, int pair_begin,
                                                        int pair_end, VmSeqSources S, int eqx, uint32_t *dir_all,
                                                        long long dir_words_per_warp, int *counter, uint32_t *cigar_out,
                                                        uint32_t *dense_out, unsigned long long *dense_count, uint2 *results)

@@ -43,8 +43,9 @@ class Aligner:
     def seq(self, name, start=0, end=0x7fffffff):
         return self._ix.seq(name, start, end)
 
-    def map_batch(self, seqs, check_num=100, mid_occ=-1):
-        """``map`` for many reads in one launch -> list of lists of (readpos, refpos_global, strand, len)."""
+    def map_batch(self, seqs, check_num=100, mid_occ=-1, arrays=False):
+        """``map`` for many reads in one launch -> list of lists of (readpos, refpos_global, strand, len); arrays=True:
+        int64 arrays [n, 4] instead of lists of tuples (the contig path's 100 kb slices carry ~20 000 anchors each)."""
         if mid_occ != -1:
             raise NotImplementedError("only the library default occurrence cap (mid_occ=-1) is on the path (clrnano:23985)")
         out = []
@@ -55,7 +56,7 @@ class Aligner:
                 rows = rows[::-1].copy()
                 rows[:, 0] = len(s) - rows[:, 0] - rows[:, 3]
                 rows[:, 2] *= -1
-            out.append([tuple(int(v) for v in r) for r in rows])
+            out.append(np.ascontiguousarray(rows, dtype=np.int64).reshape(-1, 4) if arrays else [tuple(int(v) for v in r) for r in rows])
         return out
 
     def map(self, seq, check_num=100, mid_occ=-1):
