@@ -304,11 +304,13 @@ int vm_index_build_buckets(VmIndex *ix, std::string &err)
     std::vector<int64_t> koff((size_t)VM_K9_KEYS + 1);
     if (cudaMemcpy(koff.data(), ix->d_koff, koff.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { err = "position directory: cannot read koff"; return -1; }
     std::vector<int32_t> krow((size_t)VM_K9_KEYS, -1), row_code;
+    const int64_t min_run = getenv("VM_KB_MIN_RUN") ? atoll(getenv("VM_KB_MIN_RUN")) : VM_KB_MIN_RUN;               // experiment knobs
+    const int64_t max_buckets = getenv("VM_KB_MAX_BUCKETS") ? atoll(getenv("VM_KB_MAX_BUCKETS")) : VM_KB_MAX_BUCKETS;
     for (int c = 0; c < VM_K9_KEYS; ++c)
-        if (koff[(size_t)c + 1] - koff[(size_t)c] >= VM_KB_MIN_RUN) { krow[(size_t)c] = (int32_t)row_code.size(); row_code.push_back(c); }
+        if (koff[(size_t)c + 1] - koff[(size_t)c] >= min_run) { krow[(size_t)c] = (int32_t)row_code.size(); row_code.push_back(c); }
     if (row_code.empty()) return 0;
     int shift = 8;
-    while (((ix->dev.ref_len >> shift) + 1) > VM_KB_MAX_BUCKETS ||
+    while (((ix->dev.ref_len >> shift) + 1) > max_buckets ||
            (unsigned long long)row_code.size() * (unsigned long long)((ix->dev.ref_len >> shift) + 2) * 4ULL > VM_KB_MAX_BYTES) ++shift;
     const int nb = (int)(ix->dev.ref_len >> shift) + 1;
     void *d_codes = nullptr;
