@@ -242,102 +242,9 @@ struct vm_job {
            band_redo = 0, dir_bytes = 0, chain_opcount = 0;
     int64_t launches = 0;
     std::chrono::steady_clock::time_point t0, t_done;
-    vm_result *res = nullptr;      // assembled by the worker that finishes the job's last chunk (job_assemble)
 };
 
 namespace {
-
-// The result arena of a finished job: offsets by prefix sums, records and CIGAR ops copied in parallel.  Runs in the worker
-// that finished the job's last chunk (not in vm_align_wait): the caller's thread is free to submit the next batch the
-// moment the job is done, so the workers' queue does not run empty while a result is being put together.
-static void job_assemble(vm_job *job)
-{
-    vm_ctx *c = job->c;
-    (void)c;
-    const int64_t n_reads = job->n_reads;
-    BatchResult &br = job->br;
-    vm_result *res = new vm_result();
-    job->res = res;
-    const double total = std::chrono::duration<double, std::milli>(job->t_done - job->t0).count();
-    auto t1 = std::chrono::steady_clock::now();
-    // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel.  A read's records are either in
-    // its chunk's flat arrays (device-resident extension stage) or, per read, in br.records (host glue, single-read redo)
-    const int64_t n_chunks = (int64_t)job->bounds.size() - 1;
-    std::vector<int32_t> chunk_of((size_t)n_reads, 0);
-    for (int64_t ci = 0; ci < n_chunks; ++ci)
-        for (int64_t r = job->bounds[(size_t)ci]; r < job->bounds[(size_t)ci + 1]; ++r) chunk_of[(size_t)r] = (int32_t)ci;
-    auto flat_of = [&](int64_t r, int64_t &lo, int64_t &hi) -> const vm_job::FlatChunk * {
-        const vm_job::FlatChunk &fc = job->flat[(size_t)chunk_of[(size_t)r]];
-        if (!fc.used || !br.records[(size_t)r].empty()) return nullptr;
-        const int64_t i = r - job->bounds[(size_t)chunk_of[(size_t)r]];
-        lo = fc.rec_off[(size_t)i]; hi = fc.rec_off[(size_t)i + 1];
-        return &fc;
-    };
-    res->rec_off.assign((size_t)n_reads + 1, 0);
-    std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
-    for (int64_t r = 0; r < n_reads; ++r) {
-        int64_t ops = 0, nrec = 0, lo = 0, hi = 0;
-        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
-            nrec = hi - lo;
-            if (nrec > 0) ops = fc->recs[(size_t)hi - 1].cigar_off + fc->recs[(size_t)hi - 1].cigar_len - fc->recs[(size_t)lo].cigar_off;
-        } else {
-            for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
-            nrec = (int64_t)br.records[r].size();
-        }
-        res->rec_off[r + 1] = res->rec_off[r] + nrec;
-        cig_off[r + 1] = cig_off[r] + ops;
-    }
-    res->recs.resize((size_t)res->rec_off[n_reads]);
-    res->cigar.resize((size_t)cig_off[n_reads]);
-    res->status.swap(br.status);
-    parallel_for(n_reads, job->threads, [&](int64_t r) {
-        int64_t ri = res->rec_off[r], co = cig_off[r], lo = 0, hi = 0;
-        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
-            if (hi <= lo) return;
-            // a read's records and CIGARs are contiguous in its chunk's arrays
-            const int64_t c0 = fc->recs[(size_t)lo].cigar_off;
-            for (int64_t q = lo; q < hi; ++q) {
-                vm_record o = fc->recs[(size_t)q];
-                o.cigar_off = co + (o.cigar_off - c0);
-                res->recs[(size_t)ri++] = o;
-            }
-            memcpy(res->cigar.data() + co, fc->cigar.data() + c0, (size_t)(cig_off[r + 1] - co) * 4);
-            return;
-        }
-        for (const vmg::Record &rec : br.records[r]) {
-            vm_record &o = res->recs[(size_t)ri++];
-            o.contig = rec.contig;
-            o.strand = rec.strand;
-            o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
-            o.mapq = rec.mapq;
-            o.cigar_off = co;
-            o.cigar_len = (int32_t)rec.cigar.size();
-            std::copy(rec.cigar.begin(), rec.cigar.end(), res->cigar.begin() + co);
-            co += (int64_t)rec.cigar.size();
-        }
-    }, 64);
-    Timeline::get().flush();
-    StageTimer &tm = job->timer;
-    tm.add("n_workers", job->workers);
-    tm.add("total", total);
-    tm.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
-    tm.add("n_fill_cells", job->fill_cells);
-    tm.add("n_fill_bases", job->fill_bases);
-    tm.add("n_fill_jobs", job->fill_jobs);
-    tm.add("n_fill_band_jobs", job->band_jobs);
-    tm.add("n_fill_band_redo", job->band_redo);
-    tm.add("n_fill_dir_bytes", job->dir_bytes);
-    tm.add("n_ed_cells", job->ed_cells);
-    tm.add("n_ed_upper_jobs", job->ed_upper);
-    tm.add("n_reseed_hits", job->reseed_hits);
-    tm.add("n_chain_anchors", job->chain_anchors);
-    tm.add("n_chain_opcount", job->chain_opcount);
-    for (auto &kv : tm.ms) {
-        res->stage_names.push_back(kv.first);
-        res->stage_ms.push_back(kv.second);
-        res->stage_text += kv.first + "=" + std::to_string(kv.second) + ";";
-    }
-}
 
 void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::string &err)
 {
@@ -354,13 +261,6 @@ void job_absorb(vm_job *job, CudaBackend &wb, int64_t launches, const std::strin
     if (!err.empty() && job->err.empty()) job->err = err;
     if (--job->chunks_left == 0) {
         job->t_done = std::chrono::steady_clock::now();
-        if (job->err.empty()) {
-            try {
-                job_assemble(job);
-            } catch (const std::exception &e) {
-                job->err = std::string("result arena: ") + e.what();
-            }
-        }
         job->cv.notify_all();
     }
 }
@@ -619,12 +519,92 @@ int vm_align_wait(vm_job *job, vm_result **out)
     }
     if (!job->err.empty()) {
         c->err = job->err;
-        delete job->res;
         delete job;
         return VM_ERR_CUDA;
     }
-    vm_result *res = job->res;
-    job->res = nullptr;
+    cudaSetDevice(c->device);
+    const int64_t n_reads = job->n_reads;
+    BatchResult &br = job->br;
+    vm_result *res = new vm_result();
+    const double total = std::chrono::duration<double, std::milli>(job->t_done - job->t0).count();
+    auto t1 = std::chrono::steady_clock::now();
+    // result arena: offsets by prefix sums, records and CIGAR ops copied in parallel.  A read's records are either in
+    // its chunk's flat arrays (device-resident extension stage) or, per read, in br.records (host glue, single-read redo)
+    const int64_t n_chunks = (int64_t)job->bounds.size() - 1;
+    std::vector<int32_t> chunk_of((size_t)n_reads, 0);
+    for (int64_t ci = 0; ci < n_chunks; ++ci)
+        for (int64_t r = job->bounds[(size_t)ci]; r < job->bounds[(size_t)ci + 1]; ++r) chunk_of[(size_t)r] = (int32_t)ci;
+    auto flat_of = [&](int64_t r, int64_t &lo, int64_t &hi) -> const vm_job::FlatChunk * {
+        const vm_job::FlatChunk &fc = job->flat[(size_t)chunk_of[(size_t)r]];
+        if (!fc.used || !br.records[(size_t)r].empty()) return nullptr;
+        const int64_t i = r - job->bounds[(size_t)chunk_of[(size_t)r]];
+        lo = fc.rec_off[(size_t)i]; hi = fc.rec_off[(size_t)i + 1];
+        return &fc;
+    };
+    res->rec_off.assign((size_t)n_reads + 1, 0);
+    std::vector<int64_t> cig_off((size_t)n_reads + 1, 0);
+    for (int64_t r = 0; r < n_reads; ++r) {
+        int64_t ops = 0, nrec = 0, lo = 0, hi = 0;
+        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
+            nrec = hi - lo;
+            if (nrec > 0) ops = fc->recs[(size_t)hi - 1].cigar_off + fc->recs[(size_t)hi - 1].cigar_len - fc->recs[(size_t)lo].cigar_off;
+        } else {
+            for (const vmg::Record &rec : br.records[r]) ops += (int64_t)rec.cigar.size();
+            nrec = (int64_t)br.records[r].size();
+        }
+        res->rec_off[r + 1] = res->rec_off[r] + nrec;
+        cig_off[r + 1] = cig_off[r] + ops;
+    }
+    res->recs.resize((size_t)res->rec_off[n_reads]);
+    res->cigar.resize((size_t)cig_off[n_reads]);
+    res->status.swap(br.status);
+    parallel_for(n_reads, job->threads, [&](int64_t r) {
+        int64_t ri = res->rec_off[r], co = cig_off[r], lo = 0, hi = 0;
+        if (const vm_job::FlatChunk *fc = flat_of(r, lo, hi)) {
+            if (hi <= lo) return;
+            // a read's records and CIGARs are contiguous in its chunk's arrays
+            const int64_t c0 = fc->recs[(size_t)lo].cigar_off;
+            for (int64_t q = lo; q < hi; ++q) {
+                vm_record o = fc->recs[(size_t)q];
+                o.cigar_off = co + (o.cigar_off - c0);
+                res->recs[(size_t)ri++] = o;
+            }
+            memcpy(res->cigar.data() + co, fc->cigar.data() + c0, (size_t)(cig_off[r + 1] - co) * 4);
+            return;
+        }
+        for (const vmg::Record &rec : br.records[r]) {
+            vm_record &o = res->recs[(size_t)ri++];
+            o.contig = rec.contig;
+            o.strand = rec.strand;
+            o.q_st = rec.q_st; o.q_en = rec.q_en; o.r_st = rec.r_st; o.r_en = rec.r_en;
+            o.mapq = rec.mapq;
+            o.cigar_off = co;
+            o.cigar_len = (int32_t)rec.cigar.size();
+            std::copy(rec.cigar.begin(), rec.cigar.end(), res->cigar.begin() + co);
+            co += (int64_t)rec.cigar.size();
+        }
+    }, 64);
+    Timeline::get().flush();
+    StageTimer &tm = job->timer;
+    tm.add("n_workers", job->workers);
+    tm.add("total", total);
+    tm.add("g_result_arena", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+    tm.add("n_fill_cells", job->fill_cells);
+    tm.add("n_fill_bases", job->fill_bases);
+    tm.add("n_fill_jobs", job->fill_jobs);
+    tm.add("n_fill_band_jobs", job->band_jobs);
+    tm.add("n_fill_band_redo", job->band_redo);
+    tm.add("n_fill_dir_bytes", job->dir_bytes);
+    tm.add("n_ed_cells", job->ed_cells);
+    tm.add("n_ed_upper_jobs", job->ed_upper);
+    tm.add("n_reseed_hits", job->reseed_hits);
+    tm.add("n_chain_anchors", job->chain_anchors);
+    tm.add("n_chain_opcount", job->chain_opcount);
+    for (auto &kv : tm.ms) {
+        res->stage_names.push_back(kv.first);
+        res->stage_ms.push_back(kv.second);
+        res->stage_text += kv.first + "=" + std::to_string(kv.second) + ";";
+    }
     if (job->workers > 1) c->launches += job->launches;   // lock-step jobs counted on the context directly
     delete job;
     *out = res;
