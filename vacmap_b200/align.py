@@ -432,10 +432,12 @@ def local_reseed_batch(index, reads, jobs):
     wh = np.array([w[1] for j in jobs for w in j[1]] or [0], np.int64)
     gx = np.concatenate([np.asarray(j[2])[:, 0] for j in jobs] or [np.zeros(0)]).astype(np.int32)
     gy = np.concatenate([np.asarray(j[2])[:, 1] for j in jobs] or [np.zeros(0)]).astype(np.int64)
-    cap = max(4096, 4 * int(off[-1]))
+    # room for 4 anchors per scanned read position (a job scans [readstart, readend), not the whole read -- a contig's
+    # batches are 100 kb of a multi-megabase read); rows beyond row_off[-1] are never looked at
+    cap = max(4096, 4 * int(sum(max(0, int(j[4]) - int(j[3])) for j in jobs)))
     ctx = index.ctx
     while True:
-        rows = np.zeros((cap, 4), np.int64)
+        rows = np.empty((cap, 4), np.int64)
         row_off = np.zeros(nj + 1, np.int64)
         rc = L.vm_local_reseed_batch(ctx.h, index.h, len(reads), b"".join(enc), _lib.ptr(off), nj, _lib.ptr(job_read), _lib.ptr(rs),
                                      _lib.ptr(re_), _lib.ptr(win_off), _lib.ptr(wl), _lib.ptr(wh), _lib.ptr(g_off), _lib.ptr(gx),

@@ -88,31 +88,37 @@ def linked_chain_path(batches, params=None, second_round=False, ctx=None, dp=Non
         saved.append((linked, P))
     path = []
     for linked, P in reversed(saved):
-        take = g
-        path.append(tuple(int(v) for v in linked[take]))
-        while P[take] >= 0:
-            take = P[take]                       # IndexError for a chain starting in a carried anchor, as the reference
-            path.append(tuple(int(v) for v in linked[take]))
-        g = abs(int(P[take]))
+        # follow the back-pointers on a plain list (a contig's path has ~10^5..10^6 anchors), gather the rows once
+        Pl = P.tolist()
+        take = int(g)
+        idx = [take]
+        while Pl[take] >= 0:
+            take = Pl[take]                      # IndexError for a chain starting in a carried anchor, as the reference
+            idx.append(take)
+        if idx[0] >= len(linked):
+            raise IndexError("index %d is out of bounds for the batch" % idx[0])
+        path.extend(map(tuple, linked[np.array(idx, dtype=np.int64)].tolist()))
+        g = abs(int(Pl[take]))
     return path if len(path) > 1 else []
 
 
 def trim_overlaps(path):
     """:23393-23403 -- ``path`` descending; an anchor reaching into its successor is cut back to the successor's start
     (compared against the untrimmed neighbour); returns the ASCENDING path ``ass_extend_func`` takes."""
-    path = list(path)
-    if not path:
+    if not len(path):
         return []
-    pre = path[0]
-    for t in range(1, len(path)):
-        now = path[t]
-        if not pre[0] >= now[0] + now[3]:
-            if now[2] == 1:
-                path[t] = (now[0], now[1], now[2], pre[0] - now[0])
-            else:
-                path[t] = (now[0], now[1] + now[3] - pre[0] + now[0], now[2], pre[0] - now[0])
-        pre = now
-    return path[::-1]
+    A = np.array(path, dtype=np.int64).reshape(-1, 4)
+    pre0 = A[:-1, 0]                              # start of the (untrimmed) neighbour in front
+    now = A[1:]
+    cut = ~(pre0 >= now[:, 0] + now[:, 3])
+    fwd = cut & (now[:, 2] == 1)
+    rev = cut & (now[:, 2] != 1)
+    out = A.copy()
+    new_len = pre0 - now[:, 0]
+    out[1:, 3] = np.where(cut, new_len, now[:, 3])
+    out[1:, 1] = np.where(rev, now[:, 1] + now[:, 3] - pre0 + now[:, 0], now[:, 1])
+    del fwd
+    return list(map(tuple, out[::-1].tolist()))
 
 
 # =================================================================================================================
@@ -245,9 +251,7 @@ def guide_windows(raw, ctg, look_span):
     max(largest read step + 1000, 5000) share a window, windows reach `look_span` beyond their guides (clipped to the
     contig), a window spanning two contigs makes the clustering start again contig by contig.
     -> ([(lo, hi)] global, guides sorted by read position)."""
-    readgap = 0
-    for t in range(1, len(raw)):
-        readgap = max(readgap, abs(int(raw[t][0]) - int(raw[t - 1][0])))
+    readgap = int(np.abs(np.diff(raw[:, 0])).max()) if len(raw) > 1 else 0
     readgap = max(readgap + 1000, 5000)
     by_y = raw[numba_argsort(raw[:, 1])]
 
@@ -306,11 +310,11 @@ def yield_second_mapinfo(raw, seq, index, ctg, k=9, batch=100000):
     raw = np.ascontiguousarray(raw, dtype=np.int64)
     n = len(raw)
     st_read = st_path = iloc_path = 0
-    for now in raw[1:]:
-        iloc_path += 1
-        if iloc_path == n - 1 or (iloc_path < n - 1 and raw[iloc_path + 1][0] > raw[iloc_path][0]):
-            if now[0] + now[3] > st_read + batch and iloc_path - st_path > 300:
-                en_read = int(raw[iloc_path][0])
+    x, ln = raw[:, 0].tolist(), raw[:, 3].tolist()       # plain ints: the scan below visits every path anchor
+    for iloc_path in range(1, n):
+        if iloc_path == n - 1 or x[iloc_path + 1] > x[iloc_path]:
+            if x[iloc_path] + ln[iloc_path] > st_read + batch and iloc_path - st_path > 300:
+                en_read = x[iloc_path]
                 rows = collect_second_round_anchors(st_read, en_read, raw[max(0, st_path - 20):min(iloc_path + 20, n)], seq, index, ctg, k)
                 if len(rows) > 0:
                     yield rows
@@ -578,7 +582,7 @@ def _records(new_al, cigars, readid, mapq, L, ctg, hardclip):
 def ass_extend(path, readid, seq, rc_seq, ctg, opt):
     """ass_extend_func (:23423-23460): no divergence filter, no misplaced-alignment drop; MAPQ 60."""
     L = len(seq)
-    al = _rebuild_chain_break(ctg, [tuple(int(v) for v in p) for p in path])
+    al = _rebuild_chain_break(ctg, list(map(tuple, np.asarray(path, dtype=np.int64).reshape(-1, 4).tolist())))
     _extend_edge(seq, L, al, ctg)
     _merge_conjacent(al, ctg)
     _fix_simple_inv(al, ctg, seq)
