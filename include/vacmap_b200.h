@@ -279,6 +279,37 @@ int vm_local_reseed_batch(vm_ctx *ctx, vm_index_handle *index, int64_t n_reads, 
  *         CIGAR ops, written at cigar[cig_off[j]...], cig_off[j] = sum_{i<j} (tlen_i + qlen_i + 2). */
 int vm_pairs_batch(vm_ctx *ctx, int32_t kind, int32_t eqx, int64_t n_pairs, const char *targets, const int64_t *t_off,
                    const char *queries, const int64_t *q_off, int64_t *out0, int64_t *out1, uint32_t *cigar);
+/* ------------------------------------------------------------------------
+ * SAM text of a batch's records on the library's host threads (no device needed): what the reference's emitter
+ * get_bam_dict_str (clrnano:20841-21021; reassign_mapq :11661, mergecigar_ :4773, get_MD_CSshort/long :19012-19112,
+ * P_alignmentstring :5391, output_functions.nm_from_cigar :300) writes for every read's onemapinfolist, byte for byte --
+ * FLAG / primary by longest query span, SA, NM, MD, cs, CG, --H / --fakecigar, the tags of a FASTQ comment
+ * (get_bam_dict_str_comments :21022).  A read whose NM / MD walk runs off a sequence emits nothing (the reference raises
+ * and its worker swallows the read).  Inputs: the arrays of a vm_result, the reads (upper-case) with names and optional
+ * qualities / comments (packed, [n_reads+1] offsets; NULL or an empty slice = absent), the contigs as the index gives them
+ * (vm_index_contig).  Output: one buffer, the lines of read r at [offsets[r], offsets[r+1]).
+ * ---------------------------------------------------------------------- */
+typedef struct vm_sam_options {
+    int32_t md;                /* --MD (MD and cs tags) */
+    int32_t shortcs;           /* cs in its short form unless --cs=long */
+    int32_t cigar2cg;          /* --L: CIGARs of more than 65 535 operations move to the CG tag */
+    int32_t markunbalancetra;  /* --markunbalancetra: reassign_mapq */
+    int32_t hardclip;          /* --H */
+    int32_t fakecigar;         /* --fakecigar: short CIGARs in the SA tag */
+    int32_t copycomments;      /* --copycomments */
+    int32_t reserved;
+    const char *rg_id;         /* RG:Z tag of every record (NULL: none) */
+} vm_sam_options;
+typedef struct vm_text vm_text;
+int vm_sam_batch(const vm_sam_options *opt, int32_t n_contigs, const char *const *contig_names, const char *const *contig_seqs,
+                 const int64_t *contig_lens, int64_t n_reads, const int64_t *rec_off, const vm_record *recs, const uint32_t *cigar,
+                 const char *seqs, const int64_t *seq_off, const char *names, const int64_t *name_off, const char *quals,
+                 const int64_t *qual_off, const char *comments, const int64_t *comment_off, int32_t threads, vm_text **out);
+const char *vm_text_data(vm_text *t);
+int64_t vm_text_size(vm_text *t);
+const int64_t *vm_text_offsets(vm_text *t);   /* [n_reads+1] */
+void vm_text_free(vm_text *t);
+
 int64_t vm_result_num_records(vm_result *r);
 int64_t vm_result_num_cigar_ops(vm_result *r);
 const int64_t *vm_result_read_offsets(vm_result *r);   /* [n_reads+1] into the record array */

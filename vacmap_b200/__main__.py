@@ -100,8 +100,8 @@ class BamSink:
         self.closed = False
 
     def write(self, text):
-        if isinstance(text, bytes):
-            text = text.decode()
+        if not isinstance(text, str):
+            text = bytes(text).decode()
         lines = (self.tail + text).split("\n")
         self.tail = lines.pop()
         self.w.write_sam_lines(lines)
@@ -201,13 +201,13 @@ def main(argv=None):
         import tempfile
         stem = args.o if args.o != "-" else os.path.join(tempfile.gettempdir(), "vacmap_b200.%s" % os.environ.get("MASTER_PORT", "0"))
         part_path = "%s.part%d" % (stem, rank)
-        out = open(part_path, "w")
+        out = open(part_path, "wb")
     else:
         if args.o.endswith(".bam"):
             out = BamSink(args.o, header)
         else:
-            out = sys.stdout if args.o == "-" else open(args.o, "w")
-            out.write(header)
+            out = sys.stdout.buffer if args.o == "-" else open(args.o, "wb")
+            out.write(header.encode())
     block_sizes = []      # multi-GPU: bytes of SAM text per unit (super-batch, or contig in asm mode) this rank owned
     mark = [0]
 
@@ -237,30 +237,23 @@ def main(argv=None):
                         qual = None if (args.Q or len(rec) < 3) else rec[2]
                         for line in sam.iterator_get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
                                                                   opt["cigar2cg"], opt["markunbalancetra"], opt):
-                            out.write(line + "\n")
+                            out.write((line + "\n").encode())
                     end_block()
         else:
             pending = None
 
+            table = sam.ContigTable(index)
+
             def collect(p):
-                handle, recs_in = p
+                # the whole batch's SAM text from the library's host threads (csrc/vm_sam.cu: byte for byte what
+                # sam.get_bam_dict_str / get_bam_dict_str_comments write read by read; a read on which the reference's emitter
+                # raises writes nothing, like its worker, clrnano:24116-24125)
+                handle, recs_in, enc = p
                 rec_off, recs, cig = al.wait(handle)
-                for i, rec in enumerate(recs_in):
-                    rows = al.rows_of(rec[0], recs[rec_off[i]:rec_off[i + 1]], cig)
-                    if not rows:
-                        continue
-                    qual = None if (args.Q or len(rec) < 3) else rec[2]
-                    try:
-                        if args.copycomments:
-                            lines = sam.get_bam_dict_str_comments(rows, rec[1].upper(), qual, rec[3] if len(rec) > 3 else None, contig2iloc,
-                                                                  contig2seq, opt["md"], opt["shortcs"], opt["cigar2cg"],
-                                                                  opt["markunbalancetra"], opt)
-                        else:
-                            lines = sam.get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
-                                                         opt["cigar2cg"], opt["markunbalancetra"], opt)
-                    except Exception:          # the reference's worker swallows the read (clrnano:24116-24125)
-                        continue
-                    out.write("\n".join(lines) + "\n")
+                reads = [(r[0], e) + tuple(r[2:]) for r, e in zip(recs_in, enc)]
+                sam.batch_text(reads, rec_off, recs, cig, table, opt, md=opt["md"], shortcs=opt["shortcs"], cigar2cg=opt["cigar2cg"],
+                               markunbalancetra=opt["markunbalancetra"], copycomments=args.copycomments, use_qual=not args.Q,
+                               threads=args.t, sink=out)
                 end_block()
 
             # several GPUs: every rank parses the input (the read-name filter needs all names) and keeps every world-th batch
@@ -269,7 +262,7 @@ def main(argv=None):
                     continue
                 enc = [r[1].upper().encode() for r in batch]
                 off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
-                nxt = (al.submit_packed(b"".join(enc), off), batch)
+                nxt = (al.submit_packed(b"".join(enc), off), batch, enc)
                 if pending is not None:
                     collect(pending)
                 pending = nxt
@@ -291,7 +284,7 @@ def main(argv=None):
             dist.barrier()
             os.remove(part_path)
     finally:
-        if out is not sys.stdout and not out.closed:
+        if out is not sys.stdout.buffer and not out.closed:
             out.close()
         index.close()
         if dist is not None:

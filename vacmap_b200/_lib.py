@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(_HERE, "libvacmap_b200.so")
 
 VM_OK = 0
 NOPRE = -9999999
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _ERRS = {-1: "CUDA error", -2: "no CUDA device (vacmap_b200 has no CPU fallback)", -3: "bad argument",
          -4: "out of memory", -5: "bad call order"}

@@ -8,7 +8,7 @@
 
 extern "C" {
 
-int vm_abi_version(void) { return 8; }
+int vm_abi_version(void) { return 9; }
 
 int vm_host_alloc(vm_ctx *c, int64_t bytes, void **out)
 {

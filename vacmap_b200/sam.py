@@ -9,6 +9,7 @@ insertion order RG, [CG], SA, NM, MD, cs; MD / cs empty unless the CIGAR uses ``
 ``--H`` computed at the reference's offsets; ``n_cigar`` counting numbers AND letters).  The per-base Python
 loops of the reference (NM over ``M`` runs, reverse complement) are numpy comparisons here.
 """
+import ctypes
 import re
 
 import numpy as np
@@ -346,3 +347,106 @@ def header_text(contigs, rg=None, command_line=None, version="1.0.2"):
     pg = {"ID": "VACmap", "PN": "VACmap", "VN": version, "CL": command_line if command_line is not None else ""}
     lines.append("@PG\t" + "\t".join("%s:%s" % (k, pg[k]) for k in PG_ORDER if k in pg))
     return "\n".join(lines) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The same text from the library's host threads (csrc/vm_sam.cu): what the command line uses for whole batches
+# ---------------------------------------------------------------------------------------------------------------
+class SamOptionsC(ctypes.Structure):          # == vm_sam_options
+    _fields_ = [("md", ctypes.c_int32), ("shortcs", ctypes.c_int32), ("cigar2cg", ctypes.c_int32), ("markunbalancetra", ctypes.c_int32),
+                ("hardclip", ctypes.c_int32), ("fakecigar", ctypes.c_int32), ("copycomments", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("rg_id", ctypes.c_char_p)]
+
+
+def _pack(items):
+    """list of bytes -> (concatenation, int64 offsets[n+1])"""
+    off = np.zeros(len(items) + 1, dtype=np.int64)
+    if items:
+        off[1:] = np.cumsum([len(x) for x in items])
+    return b"".join(items), off
+
+
+class ContigTable:
+    """The contigs as `vm_sam_batch` takes them: from an `Index` (pointers to the library's own copy, no conversion) or
+    from [(name, sequence)]."""
+
+    def __init__(self, source):
+        from . import _lib
+        if not (hasattr(source, "h") and getattr(source, "h")) and hasattr(source, "names") and hasattr(source, "seq"):
+            source = [(n, source.seq(n)) for n in source.names]      # an index-like object without a library handle
+        if hasattr(source, "h") and hasattr(source, "names"):
+            L = _lib.load()
+            self.names = list(source.names)
+            ptrs, lens = [], []
+            for i in range(len(self.names)):
+                p, ln = ctypes.c_void_p(), ctypes.c_int64()
+                L.vm_index_contig(source.h, i, None, None, ctypes.byref(ln), ctypes.byref(p))
+                ptrs.append(p.value)
+                lens.append(ln.value)
+            self._keep = source
+        else:
+            self.names = [n for n, _ in source]
+            self._keep = [s.encode() if isinstance(s, str) else s for _, s in source]
+            ptrs = [ctypes.cast(ctypes.c_char_p(b), ctypes.c_void_p).value for b in self._keep]
+            lens = [len(b) for b in self._keep]
+        n = len(self.names)
+        self._name_bytes = [x.encode() for x in self.names]
+        self.c_names = (ctypes.c_char_p * n)(*self._name_bytes)
+        self.c_seqs = (ctypes.c_void_p * n)(*ptrs)
+        self.c_lens = np.array(lens, dtype=np.int64)
+        self.n = n
+
+
+def batch_text(reads, rec_off, recs, cig, contigs, option, md=False, shortcs=True, cigar2cg=False, markunbalancetra=False,
+               copycomments=False, use_qual=True, threads=0, sink=None):
+    """SAM lines of a whole batch (`vm_sam_batch`): `reads` = [(name, SEQUENCE_UPPER[, qual[, comment]])] in batch order,
+    `rec_off` / `recs` / `cig` as `Aligner.wait` returns them, `contigs` a `ContigTable`.  -> (bytes of all lines,
+    int64 offsets[n+1] per read); with `sink` (a binary file object) the text is written to it straight from the
+    library's buffer and `None` stands in for the bytes.  Byte-identical to `get_bam_dict_str` / `get_bam_dict_str_comments` read by read; a read
+    on which they raise contributes nothing, as in the reference's worker."""
+    from . import _lib
+    L = _lib.load()
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    L.vm_sam_batch.argtypes = [ctypes.POINTER(SamOptionsC), i32, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32,
+                               ctypes.POINTER(vp)]
+    L.vm_text_data.restype = vp
+    L.vm_text_data.argtypes = [vp]
+    L.vm_text_size.restype = i64
+    L.vm_text_size.argtypes = [vp]
+    L.vm_text_offsets.restype = vp
+    L.vm_text_offsets.argtypes = [vp]
+    L.vm_text_free.argtypes = [vp]
+    L.vm_text_free.restype = None
+    n = len(reads)
+    seqs, seq_off = _pack([r[1].encode() if isinstance(r[1], str) else r[1] for r in reads])
+    names, name_off = _pack([r[0].encode() for r in reads])
+    quals = qual_off = comments = comment_off = None
+    if use_qual and any(len(r) > 2 and r[2] is not None for r in reads):
+        quals, qual_off = _pack([(r[2].encode() if len(r) > 2 and r[2] is not None else b"") for r in reads])
+    if copycomments and any(len(r) > 3 and isinstance(r[3], str) for r in reads):
+        comments, comment_off = _pack([(r[3].encode() if len(r) > 3 and isinstance(r[3], str) else b"") for r in reads])
+    rg = option.get("rg-id")
+    opt = SamOptionsC(int(bool(md)), int(bool(shortcs)), int(bool(cigar2cg)), int(bool(markunbalancetra)), int(bool(option["H"])),
+                      int(bool(option["fakecigar"])), int(bool(copycomments)), 0, None if rg is None else str(rg).encode())
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+    recs = np.ascontiguousarray(recs)
+    cig = np.ascontiguousarray(cig, dtype=np.uint32)
+    out = vp()
+    rc = L.vm_sam_batch(ctypes.byref(opt), contigs.n, contigs.c_names, contigs.c_seqs, _lib.ptr(contigs.c_lens), n, _lib.ptr(rec_off),
+                        _lib.ptr(recs) if len(recs) else None, _lib.ptr(cig) if len(cig) else None, seqs, _lib.ptr(seq_off), names,
+                        _lib.ptr(name_off), quals, _lib.ptr(qual_off) if qual_off is not None else None, comments,
+                        _lib.ptr(comment_off) if comment_off is not None else None, int(threads), ctypes.byref(out))
+    if rc != 0:
+        raise _lib.VacmapB200Error("vm_sam_batch failed (%d)" % rc)
+    try:
+        size = L.vm_text_size(out)
+        if sink is not None:
+            data = None
+            if size:
+                sink.write(memoryview((ctypes.c_char * size).from_address(L.vm_text_data(out))))
+        else:
+            data = ctypes.string_at(L.vm_text_data(out), size) if size else b""
+        off = np.ctypeslib.as_array(ctypes.cast(L.vm_text_offsets(out), ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,)).copy()
+    finally:
+        L.vm_text_free(out)
+    return data, off
