@@ -248,12 +248,12 @@ def main(argv=None):
                 # the whole batch's SAM text from the library's host threads (csrc/vm_sam.cu: byte for byte what
                 # sam.get_bam_dict_str / get_bam_dict_str_comments write read by read; a read on which the reference's emitter
                 # raises writes nothing, like its worker, clrnano:24116-24125)
-                handle, recs_in, enc = p
+                handle, recs_in, packed = p
                 rec_off, recs, cig = al.wait(handle)
-                reads = [(r[0], e) + tuple(r[2:]) for r, e in zip(recs_in, enc)]
+                reads = [(r[0], None) + tuple(r[2:]) for r in recs_in]
                 sam.batch_text(reads, rec_off, recs, cig, table, opt, md=opt["md"], shortcs=opt["shortcs"], cigar2cg=opt["cigar2cg"],
                                markunbalancetra=opt["markunbalancetra"], copycomments=args.copycomments, use_qual=not args.Q,
-                               threads=args.t, sink=out)
+                               threads=args.t, sink=out, packed_seqs=packed)
                 end_block()
 
             # several GPUs: every rank parses the input (the read-name filter needs all names) and keeps every world-th batch
@@ -262,7 +262,8 @@ def main(argv=None):
                     continue
                 enc = [r[1].upper().encode() for r in batch]
                 off = np.concatenate([[0], np.cumsum([len(e) for e in enc])]).astype(np.int64)
-                nxt = (al.submit_packed(b"".join(enc), off), batch, enc)
+                cat = b"".join(enc)
+                nxt = (al.submit_packed(cat, off), batch, (cat, off))
                 if pending is not None:
                     collect(pending)
                 pending = nxt

@@ -398,11 +398,12 @@ class ContigTable:
 
 
 def batch_text(reads, rec_off, recs, cig, contigs, option, md=False, shortcs=True, cigar2cg=False, markunbalancetra=False,
-               copycomments=False, use_qual=True, threads=0, sink=None):
+               copycomments=False, use_qual=True, threads=0, sink=None, packed_seqs=None):
     """SAM lines of a whole batch (`vm_sam_batch`): `reads` = [(name, SEQUENCE_UPPER[, qual[, comment]])] in batch order,
     `rec_off` / `recs` / `cig` as `Aligner.wait` returns them, `contigs` a `ContigTable`.  -> (bytes of all lines,
     int64 offsets[n+1] per read); with `sink` (a binary file object) the text is written to it straight from the
-    library's buffer and `None` stands in for the bytes.  Byte-identical to `get_bam_dict_str` / `get_bam_dict_str_comments` read by read; a read
+    library's buffer and `None` stands in for the bytes.  `packed_seqs` = (bytes of all upper-case reads, int64 offsets[n+1])
+    when the caller has packed the batch already (the sequences in `reads` are then not looked at).  Byte-identical to `get_bam_dict_str` / `get_bam_dict_str_comments` read by read; a read
     on which they raise contributes nothing, as in the reference's worker."""
     from . import _lib
     L = _lib.load()
@@ -418,7 +419,10 @@ def batch_text(reads, rec_off, recs, cig, contigs, option, md=False, shortcs=Tru
     L.vm_text_free.argtypes = [vp]
     L.vm_text_free.restype = None
     n = len(reads)
-    seqs, seq_off = _pack([r[1].encode() if isinstance(r[1], str) else r[1] for r in reads])
+    if packed_seqs is not None:
+        seqs, seq_off = packed_seqs[0], np.ascontiguousarray(packed_seqs[1], dtype=np.int64)
+    else:
+        seqs, seq_off = _pack([r[1].encode() if isinstance(r[1], str) else r[1] for r in reads])
     names, name_off = _pack([r[0].encode() for r in reads])
     quals = qual_off = comments = comment_off = None
     if use_qual and any(len(r) > 2 and r[2] is not None for r in reads):
