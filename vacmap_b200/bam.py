@@ -11,12 +11,33 @@ import gzip
 import struct
 import zlib
 
+import numpy as np
+
 _SEQ_CODES = "=ACMGRSVTWYHKDBN"
 _SEQ_ENC = {c: i for i, c in enumerate(_SEQ_CODES)}
 _CIGAR_OPS = "MIDNSHP=X"
 _CIGAR_ENC = {c: i for i, c in enumerate(_CIGAR_OPS)}
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 _COMP = str.maketrans("ACGTUNRYKMBDHVacgtunrykmbdhv", "TGCAANYRMKVHDBtgcaanyrmkvhdb")
+
+
+# per-base work goes through numpy tables: nibble codes of the letters, and the two letters of every packed byte
+_ENC_TAB = np.full(256, 15, dtype=np.uint8)
+for _c, _i in _SEQ_ENC.items():
+    _ENC_TAB[ord(_c)] = _i
+    _ENC_TAB[ord(_c.lower())] = _i
+_DEC_TAB = np.array([[ord(_SEQ_CODES[b >> 4]), ord(_SEQ_CODES[b & 15])] for b in range(256)], dtype=np.uint8)
+
+
+def _unpack_seq(packed, l_seq):
+    return _DEC_TAB[np.frombuffer(packed, dtype=np.uint8)].reshape(-1)[:l_seq].tobytes().decode()
+
+
+def _pack_seq(seq):
+    codes = _ENC_TAB[np.frombuffer(seq.encode(), dtype=np.uint8)]
+    if len(codes) & 1:
+        codes = np.append(codes, np.uint8(0))
+    return ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8).tobytes()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -56,14 +77,14 @@ def read_bam(path):
                 continue                      # pysam: query_sequence is None -> the reference skips the read
             packed = rec[p:p + (l_seq + 1) // 2]
             p += (l_seq + 1) // 2
-            seq = "".join(_SEQ_CODES[b >> 4] + _SEQ_CODES[b & 15] for b in packed)[:l_seq].upper()
+            seq = _unpack_seq(packed, l_seq).upper()
             q = rec[p:p + l_seq]
             qual = None if (not q or q[0] == 0xff) else q
             if flag & 16:
                 seq = seq.translate(_COMP)[::-1]
                 if qual is not None:
                     qual = qual[::-1]
-            yield (name, seq, None if qual is None else bytes(b + 33 for b in qual).decode("ascii"))
+            yield (name, seq, None if qual is None else (np.frombuffer(qual, dtype=np.uint8) + np.uint8(33)).tobytes().decode("ascii"))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -145,11 +166,8 @@ def encode_record(line, ref_index):
     else:
         body += struct.pack("<%dI" % len(ops), *[n << 4 | op for n, op in ops])
     if l_seq:
-        codes = [_SEQ_ENC.get(c, 15) for c in seq.upper()]
-        if l_seq & 1:
-            codes.append(0)
-        body += bytes(codes[i] << 4 | codes[i + 1] for i in range(0, len(codes), 2))
-        body += bytes([0xff]) * l_seq if qual == "*" else bytes(ord(c) - 33 for c in qual)
+        body += _pack_seq(seq)
+        body += bytes([0xff]) * l_seq if qual == "*" else (np.frombuffer(qual.encode(), dtype=np.uint8) - np.uint8(33)).tobytes()
     for tag in f[11:]:
         name2, typ, val = tag.split(":", 2)
         body += _aux(name2, typ, val)
@@ -254,7 +272,7 @@ def read_bam_records(path):
         q += 4 * n_cig
         packed = rec[q:q + (l_seq + 1) // 2]
         q += (l_seq + 1) // 2
-        seq = "".join(_SEQ_CODES[b >> 4] + _SEQ_CODES[b & 15] for b in packed)[:l_seq]
+        seq = _unpack_seq(packed, l_seq)
         qual = rec[q:q + l_seq]
         q += l_seq
         out.append(dict(name=name, flag=flag, ref_id=ref_id, pos=pos, mapq=mapq, bin=bin_, next_id=next_id, pnext=pnext, tlen=tlen,
