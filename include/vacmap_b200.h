@@ -211,7 +211,7 @@ typedef struct vm_align_params {
     int32_t local_maxgap;     /* 99 (H, S) / 50 (L)  (clrnano:24061) */
     int32_t clamp40;          /* 1 in mode L: min(skipcost, 40) in the multi-chain local DP */
     int32_t host_threads;     /* host glue threads, 0 = all cores */
-    int32_t workers;          /* size of the worker pool (own CUDA stream each), 0 = default (4), 1 = lock-step */
+    int32_t workers;          /* size of the worker pool (own CUDA stream each), 0 = default (6), 1 = lock-step */
     int32_t chunk_reads;      /* reads per sub-batch, 0 = half of the batch (at least 512) */
 } vm_align_params;
 

@@ -301,6 +301,35 @@ def gen_asm_e2e():
     print("asm_e2e.json.gz:", os.path.getsize(os.path.join(HERE, "asm_e2e.json.gz")), "bytes")
 
 
+def gen_asm_e2e_2():
+    """A second contig through the reference's assembly_get_readmap_DP_test: reverse strand, a translocated piece of the
+    other contig, a tandem duplication and a deletion (synth.asm_e2e_inputs_2) -> tests/golden/asm_e2e2.json.gz."""
+    import gzip
+    import json
+    import tempfile
+    import time
+    import refrun
+    from vacmap_b200.sam import reverse_complement
+    ref, read = synth.asm_e2e_inputs_2()
+    assert len(read) >= 500000
+    out = {"cases": []}
+    for eqx in (True,):
+        R = refrun.ReferenceRunner(ref, mode="asm", eqx=eqx)
+        wd = tempfile.mkdtemp() + "/w/"
+        t0 = time.time()
+        recs = R.mod.assembly_get_readmap_DP_test(wd, "ctgread2", read, reverse_complement(read), len(read), R.aligner,
+                                                  R.mod.pos2contig, R.contig2start, R.contig2seq, R.index2contig, R.option)
+        recs = [list(r) for r in recs]
+        for r in recs:
+            for i in (3, 4, 5, 6, 7):
+                r[i] = int(r[i])
+        print("eqx", eqx, len(recs), "records", [(r[1], r[2], r[3], r[4], r[5], r[6]) for r in recs], round(time.time() - t0, 1), "s")
+        out["cases"].append({"eqx": eqx, "records": recs})
+    with gzip.open(os.path.join(HERE, "asm_e2e2.json.gz"), "wt") as f:
+        json.dump(out, f)
+    print("asm_e2e2.json.gz:", os.path.getsize(os.path.join(HERE, "asm_e2e2.json.gz")), "bytes")
+
+
 def gen_asm_link():
     """link_cigar (mammap_asm.py:22366-22410, njit) on random CIGAR pairs -> tests/golden/asm_link_cigar.json."""
     import json
@@ -437,6 +466,8 @@ if __name__ == "__main__":
         gen_asm_reseed()
     if "asme2e" in what:
         gen_asm_e2e()
+    if "asme2e2" in what:
+        gen_asm_e2e_2()
     if "asmlink" in what:
         gen_asm_link()
     if "asmsam" in what:

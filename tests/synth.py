@@ -182,3 +182,18 @@ def asm_e2e_inputs():
              random_seq(rng, 1200), src[420000:]]
     read = mutate(rng, np.concatenate(parts), 0.005, ratio=(1, 1, 1))
     return ref, read.tobytes().decode()
+
+
+def asm_e2e_inputs_2():
+    """Second asm end-to-end fixture (tests/golden/make_golden.py::gen_asm_e2e_2, same seeds): a 1.6 Mb 2-contig reference
+    and a 560 kb contig read taken from chr1's REVERSE strand, carrying a 30 kb piece of chr2 (a translocation), a 6 kb
+    tandem duplication and a 3 kb deletion, 0.3 % divergence."""
+    ref = make_reference(93, 1600000, n_contigs=2)
+    rng = np.random.default_rng(94)
+    c1 = np.frombuffer(ref[0][1].encode(), dtype=np.uint8)
+    c2 = np.frombuffer(ref[1][1].encode(), dtype=np.uint8)
+    src = c1[100000:640000]
+    parts = [src[:120000], c2[300000:330000], src[120000:260000], src[254000:260000], src[260000:400000], src[403000:]]
+    fwd = np.concatenate(parts)
+    read = mutate(rng, _COMP[fwd][::-1].copy(), 0.003, ratio=(1, 1, 1))
+    return ref, read.tobytes().decode()

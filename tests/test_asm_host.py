@@ -131,19 +131,22 @@ class _OracleNatives:
         return [oracle.k_cigar(t, q, *a) for t, q in pairs]
 
 
-def test_product_contig_path_over_oracle_natives_matches_reference(monkeypatch):
+@pytest.mark.parametrize("fixture", ["asm_e2e", "asm_e2e2"])
+def test_product_contig_path_over_oracle_natives_matches_reference(monkeypatch, fixture):
     """vacmap_b200.asm.assembly_align -- the PRODUCT's host loop -- with every CUDA entry point swapped for the oracle's
     native of the same contract gives the rows and CIGARs the reference's assembly_get_readmap_DP_test gave for the 520 kb
-    contig read (tests/golden/asm_e2e.json.gz).  The GPU twin of this test (tests/test_zz_gpu_asm_host.py) runs the same
-    loop over the real entry points."""
+    contig read (tests/golden/asm_e2e.json.gz) and for the reverse-strand contig with a translocated piece, a tandem
+    duplication and a deletion (asm_e2e2.json.gz).  The GPU twin of the first case (tests/test_zz_gpu_asm_host.py) runs the
+    same loop over the real entry points."""
     import gzip
     import json
     import synth
     import vacmap_b200 as vb
     from vacmap_b200 import align
     here = os.path.dirname(os.path.abspath(__file__))
-    E = json.load(gzip.open(os.path.join(here, "golden", "asm_e2e.json.gz"), "rt"))
-    ref, read = synth.asm_e2e_inputs()
+    E = json.load(gzip.open(os.path.join(here, "golden", fixture + ".json.gz"), "rt"))
+    ref, read = synth.asm_e2e_inputs() if fixture == "asm_e2e" else synth.asm_e2e_inputs_2()
+    rid = "ctgread" if fixture == "asm_e2e" else "ctgread2"
     nat = _OracleNatives(ref)
     monkeypatch.setattr(asm, "chain_linked_batch", nat.chain_linked_batch)
     monkeypatch.setattr(align, "local_reseed_batch", nat.local_reseed_batch)
@@ -154,5 +157,5 @@ def test_product_contig_path_over_oracle_natives_matches_reference(monkeypatch):
     for case in E["cases"]:
         opt = vb.default_option("S", eqx=case["eqx"])
         opt.update({"golbal_skipcost": 30., "golbal_maxdiff": 50, "local_skipcost": 30., "local_maxdiff": 30, "local_kmersize": 9})
-        got = asm.assembly_align("ctgread", read, nat, opt)
+        got = asm.assembly_align(rid, read, nat, opt)
         assert [list(r) for r in got] == case["records"], case["eqx"]

@@ -158,3 +158,24 @@ def test_link_cigar_matches_reference():
     assert len(rows) == 300 and any(r[2] != r[0] + r[1] for r in rows)
     for a, b, want in rows:
         assert oasm.link_cigar(a, b) == want, (a, b)
+
+
+def test_asm_end_to_end_second_contig_matches_reference():
+    """A second contig pinned by the reference's own run (tests/golden/asm_e2e2.json.gz): taken from the reverse strand,
+    with a 30 kb piece of the other contig, a 6 kb tandem duplication and a 3 kb deletion -- records on two contigs and
+    the reverse strand."""
+    import gzip
+    import json
+    import oracle.pipeline as pl
+    import synth
+    E = json.load(gzip.open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "asm_e2e2.json.gz"), "rt"))
+    ref, read = synth.asm_e2e_inputs_2()
+    ox = oracle.Index(ref)
+    ctg = pl.Contigs([n for n, _ in ref], [s for _, s in ref])
+    for case in E["cases"]:
+        opt = {"eqx": case["eqx"], "H": False, "golbal_skipcost": 30., "golbal_maxdiff": 50, "local_skipcost": 30.,
+               "local_maxdiff": 30, "local_kmersize": 9}
+        got = oasm.assembly_align("ctgread2", read, ox, ctg, opt)
+        assert [list(r) for r in got] == case["records"], case["eqx"]
+    recs = E["cases"][0]["records"]
+    assert len(recs) == 5 and len({r[1] for r in recs}) == 2 and {r[2] for r in recs} == {"-"}
