@@ -591,6 +591,26 @@ def main():
             assert len(gathered[1]) == int(tot[2].item())
     else:
         gather_ms = 0.0
+    # ---- SAM text of one step's records on the host threads (vm_sam_batch; no device work): reported apart, the emitter
+    # is downstream of the metric ----
+    sam_text = None
+    if rank == 0:
+        try:
+            from vacmap_b200 import sam as _sam
+            table = _sam.ContigTable(ix)
+            sam_opt = {"H": False, "fakecigar": False, "rg-id": "1"}
+            batch = [(n, None) for n, _ in reads]
+            _sam.batch_text(batch, rec_off, recs, cig, table, sam_opt, packed_seqs=(cat, off))
+            ts = time.perf_counter()
+            text, _ = _sam.batch_text(batch, rec_off, recs, cig, table, sam_opt, packed_seqs=(cat, off))
+            dts = time.perf_counter() - ts
+            sam_text = {"ms_per_step": round(1000 * dts, 1), "gbp_per_s": round(bases / dts / 1e9, 3), "text_bytes": len(text),
+                        "threads": int(os.environ.get("VM_HOST_THREADS", os.cpu_count() or 1)),
+                        "note": "SAM lines of one step's records (NM, SA, RG; soft-clipped supplementary records carry the whole read) "
+                                "written by the library's host threads, byte-identical to the reference's emitter; not part of `value` / `e2e`"}
+            del text
+        except Exception as e:      # never let the side measurement break the line
+            sam_text = {"error": str(e)[:200]}
     # ---- roofline leg: one lock-step pass (one worker, one stream), so every kernel is timed alone by the CUDA
     # events the library records on its launching stream; the pipelined legs above overlap kernels of several
     # workers, which stretches their individual durations ----
@@ -689,7 +709,7 @@ def main():
                                          "steps complete inside the timed region" % args.ahead},
                 "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": len(cat) + off.nbytes, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "host_cores_busy": round(cpu_busy, 2), "host_cores": os.cpu_count(),
-                "records_per_step": nrec_all, "gather_ms": round(gather_ms, 2),
+                "records_per_step": nrec_all, "gather_ms": round(gather_ms, 2), "sam_text": sam_text,
                 "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
                 "work_per_step": counts,
                 "roofline": roof, "roofline_chain": roof_chain, "clocks": clocks}
