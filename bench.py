@@ -666,7 +666,9 @@ def main():
             achieved = alg_bytes.get(top, 0.0) / secs / 1e9 if secs > 0 else 0.0
             spill = counts["n_fill_dir_bytes"] if top == "k_fill" else 0.0
             roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic_of(top), "kernel_ms": kern[top],
+                    "frac": achieved / peak, "traffic": traffic_of(top),
+                    "traffic_source": ("profiles/" + os.path.basename(traffic_file)) if traffic_file and traffic_of(top) is not None else None,
+                    "kernel_ms": kern[top],
                     "kernel_ms_in_pipeline_per_step": per_step.get(top),
                     "timing": solo_note or "CUDA events on the launching stream, lock-step pass (one worker) after the timed region; one "
                                            "'launch' = the kernel's launches of one step (one per capacity class)",

@@ -36,6 +36,19 @@ def main(prefix):
                 if k.startswith("wr["):
                     wr += v * scale[k[3:-1]]
         print("fill DRAM bytes in the capture: read %.3e write %.3e" % (rd, wr))
+        # roofline.traffic of bench.py is scaled from this file: DRAM bytes per full-matrix-equivalent fill cell of the capture
+        import re
+        log = os.path.join(g, "ncu_fill.log")
+        if os.path.exists(log) and rd + wr > 0:
+            m = re.findall(r"'n_fill_cells': ([0-9.]+)", open(log).read())
+            if m:
+                cells = float(m[-1])
+                json.dump({"k_fill": {"dram_bytes_per_unit": (rd + wr) / cells, "unit_count": "n_fill_cells", "dram_read_bytes": rd,
+                                      "dram_write_bytes": wr, "units_in_capture": cells,
+                                      "source": "ncu --set full --clock-control none, python tests/quick_gpu.py 2000 1 (one lock-step pass of 2000 "
+                                                "reads; the %d banded + full-matrix class launches of the pass); profiles/%s_ncu_full_summary.json"
+                                                % (len(full["fill"]), prefix)}},
+                          open(os.path.join(p, "%s_kernel_traffic.json" % prefix), "w"), indent=1)
 
 
 if __name__ == "__main__":
