@@ -42,6 +42,7 @@ class FakeAligner:
 
     def __init__(self, index, opt, mode, host_threads=0, **_kw):
         self.index = index
+        self.last_stage_ms = {"total": 1.0, "k_fill": 0.5, "n_fill_jobs": 3.0}
 
     def submit_packed(self, seq_cat, seq_off, resident=False):
         seqs = [bytes(seq_cat[seq_off[i]:seq_off[i + 1]]).decode() for i in range(len(seq_off) - 1)]
@@ -107,3 +108,14 @@ def test_command_line_bam_output_and_duplicate_names(tmp_path, fake_gpu):
     assert [(r["name"], r["flag"], refs[r["ref_id"]][0], r["pos"] + 1, r["cigar"]) for r in recs] == \
            [(f[0], int(f[1]), f[2], int(f[3]), f[5]) for f in want]
     assert all(r["qual"] != "*" for r in recs)          # FASTQ qualities are carried (no --Q)
+
+
+def test_command_line_debug_flag_reports_batches(tmp_path, fake_gpu, capsys):
+    case = E2E["cases"][0]
+    ref, reads = case_inputs(case["name"])
+    FakeIndex.contigs = ref
+    FakeAligner.rows_by_seq = {seq.upper(): [tuple(r) for r in recs] for (_, seq), recs in zip(reads, case["records"])}
+    rpath = _write_inputs(tmp_path, ref, reads)
+    cli.main(["-ref", str(tmp_path / "ref.fa"), "-read", rpath, "-mode", "H", "--nowriteindex", "--debug", "-o", str(tmp_path / "o.sam")])
+    err = capsys.readouterr().err
+    assert "[vacmap_b200] batch of 1 reads, 3 records" in err and "k_fill 0.5" in err and "n_fill_jobs" not in err

@@ -57,6 +57,7 @@ def build_parser():
     p.add_argument("--rg-id", dest="rg_id", default=None)
     for f in RG_FLAGS[1:]:      # the other @RG fields of vacmap:134-150 (need --rg-id, vacmap:72-73)
         p.add_argument("--rg-" + f.lower(), dest="rg_" + f.lower(), default=None)
+    p.add_argument("--debug", action="store_true", help="per-batch stage times and read counts on stderr (the reference's --debug prints its own trace)")
     p.add_argument("--batch-bases", type=int, default=150_000_000, help="bases per super-batch")
     p.add_argument("--device", type=int, default=0)
     return p
@@ -254,6 +255,10 @@ def main(argv=None):
                 sam.batch_text(reads, rec_off, recs, cig, table, opt, md=opt["md"], shortcs=opt["shortcs"], cigar2cg=opt["cigar2cg"],
                                markunbalancetra=opt["markunbalancetra"], copycomments=args.copycomments, use_qual=not args.Q,
                                threads=args.t, sink=out, packed_seqs=packed)
+                if args.debug:
+                    top = sorted(((v, k) for k, v in al.last_stage_ms.items() if not k.startswith(("n_", "c_", "cpu_", "t_"))), reverse=True)[:8]
+                    sys.stderr.write("[vacmap_b200] batch of %d reads, %d records; ms: %s\n"
+                                     % (len(recs_in), len(recs), ", ".join("%s %.1f" % (k, v) for v, k in top)))
                 end_block()
 
             # several GPUs: every rank parses the input (the read-name filter needs all names) and keeps every world-th batch
