@@ -187,6 +187,7 @@ class BamWriter:
         self.sorted = path.endswith("sorted.bam")
         self.buf = bytearray()
         self.pending = []
+        self._pool = None
         refs = []
         lines = header_text.splitlines()
         for ln in lines:
@@ -203,18 +204,37 @@ class BamWriter:
             head += struct.pack("<i", len(nm)) + nm + struct.pack("<i", ln)
         self._put(bytes(head))
 
-    def _block(self, data):
-        comp = zlib.compressobj(self.level, zlib.DEFLATED, -15)
+    @staticmethod
+    def _compress(args):
+        data, level = args
+        comp = zlib.compressobj(level, zlib.DEFLATED, -15)
         cdata = comp.compress(data) + comp.flush()
-        bsize = len(cdata) + 25
-        self.f.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + cdata +
-                     struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(cdata) + 25) + cdata +
+                struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
+
+    def _flush_blocks(self, blocks):
+        """BGZF blocks are independent deflate streams: compressed by a few threads (zlib releases the GIL, like
+        `samtools view -@ 8`), written in order."""
+        if not blocks:
+            return
+        if len(blocks) < 4:
+            for b in blocks:
+                self.f.write(self._compress((b, self.level)))
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            import os
+            self._pool = ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1))
+        for c in self._pool.map(self._compress, [(b, self.level) for b in blocks]):
+            self.f.write(c)
 
     def _put(self, data):
         self.buf += data
-        while len(self.buf) >= 0xff00:
-            self._block(bytes(self.buf[:0xff00]))
-            del self.buf[:0xff00]
+        if len(self.buf) >= 64 * 0xff00:           # a few megabytes at a time
+            n = len(self.buf) // 0xff00
+            view = bytes(self.buf[:n * 0xff00])
+            del self.buf[:n * 0xff00]
+            self._flush_blocks([view[i * 0xff00:(i + 1) * 0xff00] for i in range(n)])
 
     def write_sam_lines(self, lines):
         for ln in lines:
@@ -235,8 +255,12 @@ class BamWriter:
                 self._put(rec)
             self.pending = []
         if self.buf:
-            self._block(bytes(self.buf))
+            view = bytes(self.buf)
+            self._flush_blocks([view[i:i + 0xff00] for i in range(0, len(view), 0xff00)])
             self.buf = bytearray()
+        if self._pool is not None:
+            self._pool.shutdown()
+            self._pool = None
         self.f.write(_BGZF_EOF)
         self.f.close()
         self.f = None
