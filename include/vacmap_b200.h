@@ -297,7 +297,8 @@ typedef struct vm_sam_options {
     int32_t hardclip;          /* --H */
     int32_t fakecigar;         /* --fakecigar: short CIGARs in the SA tag */
     int32_t copycomments;      /* --copycomments */
-    int32_t reserved;
+    int32_t asm_mode;          /* -mode asm's emitter (iterator_get_bam_dict_str, mammap_asm.py:22757-22941): NM from the CIGAR alone,
+                                  its primary-record rule, MAPQ written as 60 / 1 */
     const char *rg_id;         /* RG:Z tag of every record (NULL: none) */
 } vm_sam_options;
 typedef struct vm_text vm_text;

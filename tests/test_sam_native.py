@@ -147,3 +147,29 @@ def test_native_emitter_long_cigar_goes_to_cg():
         want = sam.get_bam_dict_str([tuple(rows[0][0])], seq, None, {"chr1": 0}, dict(contigs), False, True, l_flag, False, opt)
         assert data.decode().splitlines() == want
         assert ("\tCG:Z:" in data.decode()) == l_flag
+
+
+def test_native_emitter_asm_mode_matches_reference():
+    """asm mode's emitter in the library (`asm_mode`): the reference's own lines for the asm end-to-end records
+    (tests/golden/asm_sam.json.gz): NM from the CIGAR alone, the primary-record rule, MAPQ 60 / 1."""
+    import hashlib
+    import synth
+
+    def squash(line):
+        f = line.split("\t")
+        for i in (9, 10):
+            if len(f[i]) > 64:
+                f[i] = "%d:%s" % (len(f[i]), hashlib.sha1(f[i].encode()).hexdigest())
+        return "\t".join(f)
+    A = json.load(gzip.open(os.path.join(HERE, "golden", "asm_sam.json.gz"), "rt"))
+    ref, read = synth.asm_e2e_inputs()
+    table = sam.ContigTable([(n, s.upper()) for n, s in ref])
+    qual = "".join(chr(33 + (i * 11) % 41) for i in range(len(read)))
+    for case in A:
+        v = case["variant"]
+        opt = {"H": v["H"], "fakecigar": v["fakecigar"], "rg-id": "1"}
+        rows = [[tuple(r) for r in case["records"]]]
+        rec_off, recs, cig = pack_records(rows, [n for n, _ in ref])
+        data, off = sam.batch_text([(rows[0][0][0], read.upper(), qual if v["qual"] else None)], rec_off, recs, cig, table, opt, md=v["md"],
+                                   shortcs=v.get("shortcs", True), asm=True)
+        assert [squash(x) for x in data.decode().splitlines()] == case["sam"], v

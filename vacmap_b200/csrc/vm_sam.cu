@@ -52,7 +52,7 @@ struct Rec {
     int32_t mapq;
     std::vector<Op> ops;        // merged (mergecigar_)
     std::string cigar;          // "".join(oplist)
-    long long nm = 0;
+    long long nm = 0, nm_cigar = 0;
     std::string md, cs, fake;
 };
 
@@ -216,12 +216,16 @@ void one_read(const Ctx &C, const vm_record *recs, int64_t n_rec, const uint32_t
         Rec &x = rows[(size_t)i];
         x.contig = r.contig; x.strand = r.strand;
         x.q_st = r.q_st; x.q_en = r.q_en; x.r_st = r.r_st; x.r_en = r.r_en; x.mapq = r.mapq;
-        // mergecigar_: adjacent runs of the same op merged
+        // mergecigar_: adjacent runs of the same op merged.  asm mode's mergecigar_nm_ (mammap_asm.py:23126-23155) also sums
+        // the X / D / I lengths for NM -- only where a run STARTS: a length merged into the run in front is not added
         for (int32_t k = 0; k < r.cigar_len; ++k) {
             const uint32_t c = cigar[r.cigar_off + k];
             const char op = kOps[(c & 15u) < 9u ? (c & 15u) : 0u];
             if (!x.ops.empty() && x.ops.back().op == op) x.ops.back().n += (long long)(c >> 4);
-            else x.ops.push_back(Op{(long long)(c >> 4), op});
+            else {
+                x.ops.push_back(Op{(long long)(c >> 4), op});
+                if (op == 'X' || op == 'D' || op == 'I') x.nm_cigar += (long long)(c >> 4);
+            }
         }
         for (const Op &o : x.ops) { put_int(x.cigar, o.n); x.cigar += o.op; }
     }
@@ -240,26 +244,30 @@ void one_read(const Ctx &C, const vm_record *recs, int64_t n_rec, const uint32_t
         const char *target = C.ctg_seqs[it.contig] + tl;
         const long long tn = th - tl;
         if (!O.md) {
-            it.nm = nm_from_cigar(it.ops, oriented, qlen, target, tn);
+            it.nm = O.asm_mode ? it.nm_cigar : nm_from_cigar(it.ops, oriented, qlen, target, tn);
         } else {
             long long ql, qh;
             pyslice(qlen, it.q_st, it.q_en, ql, qh);
             md_cs(it.ops, target, tn, oriented + ql, qh - ql, O.shortcs != 0, it.md, it.cs);
-            it.nm = nm_from_cigar(it.ops, oriented + ql, qh - ql, target, tn);
+            it.nm = O.asm_mode ? it.nm_cigar : nm_from_cigar(it.ops, oriented + ql, qh - ql, target, tn);
         }
         if (O.fakecigar) fake_cigar(it, qlen, clip, it.fake);
     }
     const bool have_qual = qual != nullptr && qual_len == qlen;
     const size_t m = rows.size();
+    // asm mode (mammap_asm.py:22838-22841, 22873-22887): the second-longest record is primary when the longest has MAPQ 1 and
+    // it has not; MAPQ is written as 60 (anything non-zero) or 1
+    const size_t primary_iloc = (O.asm_mode && m > 1 && rows[0].mapq == 1 && rows[1].mapq != 1) ? 1 : 0;
+    auto mq_of = [&](int32_t v) -> long long { return O.asm_mode ? (v != 0 ? 60 : 1) : (long long)v; };
     for (size_t iloc = 0; iloc < m; ++iloc) {
         const Rec &p = rows[iloc];
         std::string &L = out;
         // fixed fields: QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL
         L.append(name, (size_t)name_len); L += '\t';
-        put_int(L, (iloc == 0 ? 0 : 2048) + (p.strand == 1 ? 0 : 16)); L += '\t';
+        put_int(L, (iloc == primary_iloc ? 0 : 2048) + (p.strand == 1 ? 0 : 16)); L += '\t';
         L += C.ctg_names[p.contig]; L += '\t';
         put_int(L, p.r_st + 1); L += '\t';
-        put_int(L, p.mapq); L += '\t';
+        put_int(L, mq_of(p.mapq)); L += '\t';
         const bool cg = (long long)p.ops.size() * 2 > 65535 && O.cigar2cg;
         if (cg) L += '*'; else L += p.cigar;
         L += "\t*\t0\t0\t";
@@ -285,7 +293,7 @@ void one_read(const Ctx &C, const vm_record *recs, int64_t n_rec, const uint32_t
                 put_int(L, it.r_st + 1); L += ',';
                 L += it.strand == 1 ? '+' : '-'; L += ',';
                 L += O.fakecigar ? it.fake : it.cigar; L += ',';
-                put_int(L, it.mapq); L += ',';
+                put_int(L, mq_of(it.mapq)); L += ',';
                 put_int(L, it.nm); L += ';';
             }
         }

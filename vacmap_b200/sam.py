@@ -354,7 +354,7 @@ def header_text(contigs, rg=None, command_line=None, version="1.0.2"):
 # ---------------------------------------------------------------------------------------------------------------
 class SamOptionsC(ctypes.Structure):          # == vm_sam_options
     _fields_ = [("md", ctypes.c_int32), ("shortcs", ctypes.c_int32), ("cigar2cg", ctypes.c_int32), ("markunbalancetra", ctypes.c_int32),
-                ("hardclip", ctypes.c_int32), ("fakecigar", ctypes.c_int32), ("copycomments", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("hardclip", ctypes.c_int32), ("fakecigar", ctypes.c_int32), ("copycomments", ctypes.c_int32), ("asm_mode", ctypes.c_int32),
                 ("rg_id", ctypes.c_char_p)]
 
 
@@ -398,13 +398,14 @@ class ContigTable:
 
 
 def batch_text(reads, rec_off, recs, cig, contigs, option, md=False, shortcs=True, cigar2cg=False, markunbalancetra=False,
-               copycomments=False, use_qual=True, threads=0, sink=None, packed_seqs=None):
+               copycomments=False, use_qual=True, threads=0, sink=None, packed_seqs=None, asm=False):
     """SAM lines of a whole batch (`vm_sam_batch`): `reads` = [(name, SEQUENCE_UPPER[, qual[, comment]])] in batch order,
     `rec_off` / `recs` / `cig` as `Aligner.wait` returns them, `contigs` a `ContigTable`.  -> (bytes of all lines,
     int64 offsets[n+1] per read); with `sink` (a binary file object) the text is written to it straight from the
     library's buffer and `None` stands in for the bytes.  `packed_seqs` = (bytes of all upper-case reads, int64 offsets[n+1])
     when the caller has packed the batch already (the sequences in `reads` are then not looked at).  Byte-identical to `get_bam_dict_str` / `get_bam_dict_str_comments` read by read; a read
-    on which they raise contributes nothing, as in the reference's worker."""
+    on which they raise contributes nothing, as in the reference's worker.  `asm`: the contig mode's emitter
+    (`iterator_get_bam_dict_str`)."""
     from . import _lib
     L = _lib.load()
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
@@ -431,7 +432,7 @@ def batch_text(reads, rec_off, recs, cig, contigs, option, md=False, shortcs=Tru
         comments, comment_off = _pack([(r[3].encode() if len(r) > 3 and isinstance(r[3], str) else b"") for r in reads])
     rg = option.get("rg-id")
     opt = SamOptionsC(int(bool(md)), int(bool(shortcs)), int(bool(cigar2cg)), int(bool(markunbalancetra)), int(bool(option["H"])),
-                      int(bool(option["fakecigar"])), int(bool(copycomments)), 0, None if rg is None else str(rg).encode())
+                      int(bool(option["fakecigar"])), int(bool(copycomments)), int(bool(asm)), None if rg is None else str(rg).encode())
     rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
     recs = np.ascontiguousarray(recs)
     cig = np.ascontiguousarray(cig, dtype=np.uint32)
