@@ -119,3 +119,30 @@ def test_command_line_debug_flag_reports_batches(tmp_path, fake_gpu, capsys):
     cli.main(["-ref", str(tmp_path / "ref.fa"), "-read", rpath, "-mode", "H", "--nowriteindex", "--debug", "-o", str(tmp_path / "o.sam")])
     err = capsys.readouterr().err
     assert "[vacmap_b200] batch of 1 reads, 3 records" in err and "k_fill 0.5" in err and "n_fill_jobs" not in err
+
+
+def test_command_line_asm_mode_uses_the_modes_emitter(tmp_path, fake_gpu, monkeypatch):
+    """`-mode asm`: contigs one at a time through asm.assembly_align (stubbed: the reference's rows for the 520 kb contig),
+    lines from the mode's own emitter -- the reference's asm lines (tests/golden/asm_sam.json.gz, default options + --eqx)."""
+    import hashlib
+    import json
+    import synth
+    from vacmap_b200 import asm
+    A = json.load(gzip.open(os.path.join(HERE, "golden", "asm_sam.json.gz"), "rt"))
+    case = next(c for c in A if not c["variant"]["H"] and not c["variant"]["fakecigar"] and not c["variant"]["md"] and not c["variant"]["qual"])
+    ref, read = synth.asm_e2e_inputs()
+    FakeIndex.contigs = [(n, s.upper()) for n, s in ref]
+    monkeypatch.setattr(asm, "assembly_align", lambda rid, seq, index, opt, ctx=None: [tuple(r) for r in case["records"]])
+    rid = case["records"][0][0]
+    rpath = _write_inputs(tmp_path, ref, [(rid, read)])
+    out = tmp_path / "asm.sam"
+    cli.main(["-ref", str(tmp_path / "ref.fa"), "-read", rpath, "-mode", "asm", "-workdir", str(tmp_path), "--nowriteindex", "-o", str(out)])
+
+    def squash(line):
+        f = line.split("\t")
+        for i in (9, 10):
+            if len(f[i]) > 64:
+                f[i] = "%d:%s" % (len(f[i]), hashlib.sha1(f[i].encode()).hexdigest())
+        return "\t".join(f)
+    body = [squash(l) for l in out.read_text().splitlines() if not l.startswith("@")]
+    assert body == case["sam"]

@@ -16,17 +16,8 @@ _ENC = {c: i for i, c in enumerate(OPS)}
 
 
 def pack_records(per_read_rows, contig_names):
-    """rows (readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar string) per read -> (rec_off, recs, cig) as Aligner.wait returns them"""
-    import re
-    rec_off = np.zeros(len(per_read_rows) + 1, np.int64)
-    recs, cig = [], []
-    for i, rows in enumerate(per_read_rows):
-        for r in rows:
-            ops = [(int(n) << 4) | _ENC[o] for n, o in re.findall(r"(\d+)([MIDNSHP=X])", r[8])]
-            recs.append((contig_names.index(r[1]), 1 if r[2] == "+" else -1, r[3], r[4], r[5], r[6], r[7], len(ops), len(cig)))
-            cig += ops
-        rec_off[i + 1] = len(recs)
-    return rec_off, np.array(recs, dtype=RECORD_DTYPE) if recs else np.zeros(0, RECORD_DTYPE), np.array(cig, dtype=np.uint32)
+    """rows (readid, contig, strand, q_st, q_en, r_st, r_en, mapq, cigar string) per read -> (rec_off, recs, cig)"""
+    return sam.pack_rows(per_read_rows, contig_names)
 
 
 def python_lines(rows, seq, qual, comment, c2i, c2s, opt, md, shortcs, cigar2cg, mark, copycomments):

@@ -225,6 +225,7 @@ def main(argv=None):
             from . import asm
             seen = set()
             unit = 0
+            asm_table = None
             for path in args.read:
                 for rec in read_records(path):
                     if rec[0] in seen:
@@ -235,10 +236,14 @@ def main(argv=None):
                         continue
                     rows = asm.assembly_align(rec[0], rec[1], index, opt)
                     if rows:
-                        qual = None if (args.Q or len(rec) < 3) else rec[2]
-                        for line in sam.iterator_get_bam_dict_str(rows, rec[1].upper(), qual, contig2iloc, contig2seq, opt["md"], opt["shortcs"],
-                                                                  opt["cigar2cg"], opt["markunbalancetra"], opt):
-                            out.write((line + "\n").encode())
+                        # the mode's own emitter (iterator_get_bam_dict_str), from the library's host code: MD / cs over a
+                        # 60 Mb contig are not a job for a Python loop
+                        if asm_table is None:
+                            asm_table = sam.ContigTable(index)
+                        rec_off, recs, cig = sam.pack_rows([rows], asm_table.names)
+                        sam.batch_text([(rec[0], rec[1].upper()) + tuple(rec[2:])], rec_off, recs, cig, asm_table, opt, md=opt["md"],
+                                       shortcs=opt["shortcs"], cigar2cg=opt["cigar2cg"], markunbalancetra=opt["markunbalancetra"],
+                                       use_qual=not args.Q, threads=args.t, sink=out, asm=True)
                     end_block()
         else:
             pending = None

@@ -366,6 +366,23 @@ def _pack(items):
     return b"".join(items), off
 
 
+def pack_rows(per_read_rows, contig_names):
+    """`onemapinfolist` rows (readid, contig, strand, q_st, q_en, r_st, r_en, mapq, CIGAR string) per read ->
+    (rec_off, recs, cig) in the layout of `Aligner.wait` (what `batch_text` takes)."""
+    from .align import OPS, RECORD_DTYPE
+    enc = {c: i for i, c in enumerate(OPS)}
+    index = {n: i for i, n in enumerate(contig_names)}
+    rec_off = np.zeros(len(per_read_rows) + 1, np.int64)
+    recs, cig = [], []
+    for i, rows in enumerate(per_read_rows):
+        for r in rows:
+            ops = [(int(n) << 4) | enc[o] for n, o in _CIGAR_RE.findall(r[8])]
+            recs.append((index[r[1]], 1 if r[2] == "+" else -1, r[3], r[4], r[5], r[6], r[7], len(ops), len(cig)))
+            cig += ops
+        rec_off[i + 1] = len(recs)
+    return rec_off, (np.array(recs, dtype=RECORD_DTYPE) if recs else np.zeros(0, RECORD_DTYPE)), np.array(cig, dtype=np.uint32)
+
+
 class ContigTable:
     """The contigs as `vm_sam_batch` takes them: from an `Index` (pointers to the library's own copy, no conversion) or
     from [(name, sequence)]."""
