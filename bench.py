@@ -281,8 +281,15 @@ def run_reference(args):
     sample = min(args.reads, args.cpu_sample)
     ref, reads, _note = cpu_inputs(sample)
     arm = CpuArm(ref, cores)
+    rate = None
     for _ in range(max(args.warmup, 1)):
-        arm.run(reads[:max(cores * 8, 64)])
+        wn = min(len(reads), max(cores * 8, 64))
+        _, wdt = arm.run(reads[:wn])
+        rate = wn / max(wdt, 1e-6)                 # reads per second of the warmed pool
+    # a bounded sample per step: the K timed steps together stay within ~75 s whatever K the caller asks for
+    budget_s = float(os.environ.get("VM_REF_BUDGET_S", "75"))
+    sample = max(min(sample, 256), min(sample, int(rate * budget_s / max(args.steps, 1))))
+    reads = reads[:sample]
     vals, t_all = [], 0.0
     for _ in range(args.steps):
         v, dt = arm.run(reads)
