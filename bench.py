@@ -722,7 +722,8 @@ def main():
                 "stage_ms_per_step": {k: round(v, 3) for k, v in per_step.items() if not k.startswith("n_")},
                 "work_per_step": counts,
                 "roofline": roof, "roofline_chain": roof_chain, "clocks": clocks}
-        if not args.no_cpu:
+        line["cpu_baseline"] = None
+        if not args.no_cpu and world == 1:      # the CPU leg belongs to the N = 1 line only (the other ranks' boxes would idle through it)
             cores = os.cpu_count() or 1
             sample = min(args.reads, args.cpu_sample)
             ref_c, reads_c, note = cpu_inputs(sample, ref)
